@@ -1,0 +1,76 @@
+"""ctypes binding of libacnn.so (the C ABI declared in include/acnn.h).
+
+There is no CPU fallback: if the library is missing or fails to load, every product entry point
+raises.  Build it with `python -m assembled_cnn_b200.build`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libacnn.so")
+
+c_void_p, c_int, c_float, c_int64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+
+class ConvGeom(C.Structure):
+    """struct acnn_conv_geom (include/acnn.h)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "B", "H", "W", "Cin", "Cout", "kh", "kw", "stride",
+        "pad_h_lo", "pad_h_hi", "pad_w_lo", "pad_w_hi")]
+
+    def out_hw(self):
+        ho = (self.H + self.pad_h_lo + self.pad_h_hi - self.kh) // self.stride + 1
+        wo = (self.W + self.pad_w_lo + self.pad_w_hi - self.kw) // self.stride + 1
+        return ho, wo
+
+
+class AcnnError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); must list every symbol include/acnn.h declares.
+PROTOTYPES = {
+    "acnn_last_error": (C.c_char_p, []),
+    "acnn_version": (c_int, []),
+    "acnn_launch_count": (c_int64, []),
+    "acnn_conv_fprop": (c_int, [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "acnn_conv_dgrad": (c_int, [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "acnn_conv_wgrad": (c_int, [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libacnn.so and bind prototypes; raises AcnnError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AcnnError(
+            f"{LIB_PATH} not found: the CUDA library is not built and there is no fallback. "
+            "Run `python -m assembled_cnn_b200.build`.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().acnn_last_error().decode("utf-8", "replace")
+        raise AcnnError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None passes NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()

@@ -1,0 +1,37 @@
+#include "common.h"
+
+#include <stdarg.h>
+#include <atomic>
+
+namespace acnn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return ACNN_ERR_CUDA;
+  }
+  return ACNN_OK;
+}
+
+}  // namespace acnn
+
+extern "C" {
+
+const char* acnn_last_error(void) { return acnn::g_err; }
+int acnn_version(void) { return 100; }
+int64_t acnn_launch_count(void) { return acnn::g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -1,0 +1,845 @@
+// tcgen05 implicit-GEMM convolutions for sm_100a.
+//
+//   conv_gemm_kernel : y[M, Cout] = im2col(x)[M, K] * w[Cout, K]^T          (fprop, dgrad, dense)
+//                      A tiles arrive by TMA (tiled 2-D for 1x1/s1, im2col 4-D otherwise) in the
+//                      128B/64B/32B-swizzled K-major layout tcgen05.mma reads directly; the fp32
+//                      accumulator lives in TMEM; a 4-warp epilogue drains it with tcgen05.ld and
+//                      fuses bias / gradient-accumulate / ReLU-mask / batch-norm column sums.
+//   wgrad_gemm_kernel: dw[Cout, K] += dy[P, Cout]^T * im2col(x)[P, K]       (split-K over pixels)
+//                      both operands are MN-major (the pixel index is the GEMM K dimension).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+//
+// Reference semantics: nets/model_helper.py:67-78 (conv2d_fixed_padding), tf.gradients backward.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace acnn {
+
+// ------------------------------------------------------------------------------------------
+// Tensor-map creation (driver entry points fetched lazily: libacnn.so does not link libcuda).
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn g_encode_tiled = nullptr;
+static EncodeIm2colFn g_encode_im2col = nullptr;
+static int g_driver_version = 0;
+
+static int load_driver_fns() {
+  if (g_encode_tiled && g_encode_im2col) return ACNN_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    return ACNN_ERR_CUDA;
+  }
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeIm2col entry point unavailable (%s)", cudaGetErrorString(e));
+    return ACNN_ERR_CUDA;
+  }
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  cudaDriverGetVersion(&g_driver_version);
+  return ACNN_OK;
+}
+
+static CUtensorMapSwizzle swizzle_enum(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                      : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// bf16 matrix [rows][cols] (cols contiguous, row pitch ld elements); box = [box_rows][box_cols].
+static int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld,
+                       int box_rows, int box_cols) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                              dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_enum(box_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rows=%lld cols=%lld ld=%lld box=%dx%d", (int)r,
+              (long long)rows, (long long)cols, (long long)ld, box_rows, box_cols);
+    return ACNN_ERR_CUDA;
+  }
+  return ACNN_OK;
+}
+
+// bf16 NHWC tensor [B][H][W][C]; one load = `pixels` consecutive output pixels x `cw` channels of
+// one filter tap.  The bounding box of base pixels is [-pad_lo, dim + pad_hi - (k-1)).
+static int make_map_im2col(CUtensorMap* m, const void* base, int B, int H, int W, int C, int kh,
+                           int kw, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
+                           int pad_w_hi, int cw, int pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {-pad_w_lo, -pad_h_lo};
+  int upper[2] = {pad_w_hi - (kw - 1), pad_h_hi - (kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
+                               dims, strides, lower, upper, (cuuint32_t)cw, (cuuint32_t)pixels,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(cw * 2),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d): B=%d H=%d W=%d C=%d k=%dx%d s=%d cw=%d px=%d",
+              (int)r, B, H, W, C, kh, kw, stride, cw, pixels);
+    return ACNN_ERR_CUDA;
+  }
+  // Driver <= 13.1 mis-encodes im2col maps of tensors smaller than 128 KiB (same fix-up the
+  // CUTLASS im2col descriptor builder applies): clear bit 21 of the second descriptor word.
+  if (g_driver_version <= 13010 && (int64_t)B * H * W * C * 2 < 131072) {
+    reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  }
+  return ACNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fprop / dgrad / dense kernel
+// ------------------------------------------------------------------------------------------
+struct ConvGemmParams {
+  int M;          // output pixels B*Ho*Wo
+  int Cout;       // GEMM N
+  int Cin;        // channels per filter tap
+  int Ktot;       // kh*kw*Cin
+  int kw;         // taps per filter row
+  int HoWo, Wo;   // to decompose a row index into (n, p, q)
+  int stride, pad_h_lo, pad_w_lo;
+  int b_sw_bytes; // swizzle span of the weight tile (128 unless Ktot < 64)
+  void* y;
+  float* ch_sum;
+  float* ch_sumsq;
+  const __nv_bfloat16* add_src;
+  const __nv_bfloat16* mask_src;
+  const float* bias;
+  int out_f32;
+};
+
+constexpr int kBM = 128;        // output pixels per CTA tile == UMMA M == TMEM lanes
+constexpr int kStageK = 64;     // K elements per pipeline stage
+constexpr int kThreads = 192;
+
+template <int BN>
+struct FpropCfg {
+  static constexpr int kABytes = kBM * kStageK * 2;   // 16 KiB
+  static constexpr int kBBytes = BN * kStageK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  // <= ~100 KiB so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop)
+  static constexpr int kStages = (BN >= 256) ? 4 : ((BN == 128) ? 3 : 4);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+};
+
+// Sum over the 32 lanes of a warp of 32 per-lane values each: on return lane l holds the total
+// of column l.  Butterfly exchange: 31 shuffles instead of 160.
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float send = (lane & 16) ? v[i] : v[i + 16];
+    float keep = (lane & 16) ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float send = (lane & 8) ? v[i] : v[i + 8];
+    float keep = (lane & 8) ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float send = (lane & 4) ? v[i] : v[i + 4];
+    float keep = (lane & 4) ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    float send = (lane & 2) ? v[i] : v[i + 2];
+    float keep = (lane & 2) ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    float send = (lane & 1) ? v[0] : v[1];
+    float keep = (lane & 1) ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+template <int BN, int CW, bool IM2COL>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvGemmParams p) {
+  using Cfg = FpropCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kChunks = kStageK / CW;        // A chunks (one filter tap each when Cin < 64)
+  constexpr int kChunkBytes = kBM * CW * 2;
+  constexpr int kKSteps = CW / 16;             // UMMA K = 16 bf16
+  constexpr uint32_t kIdesc = make_idesc_bf16(BN, false, false);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kStages];
+  __shared__ uint64_t empty_bar[kStages];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float red_sum[4][BN];
+  __shared__ float red_sq[4][BN];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBM;
+  const int num_kb = (p.Ktot + kStageK - 1) / kStageK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int img = 0, h0 = 0, w0 = 0;
+      if (IM2COL) {
+        img = m0 / p.HoWo;
+        const int rem = m0 - img * p.HoWo;
+        const int po = rem / p.Wo;
+        const int qo = rem - po * p.Wo;
+        h0 = po * p.stride - p.pad_h_lo;
+        w0 = qo * p.stride - p.pad_w_lo;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        const int k0 = kb * kStageK;
+        int nchunk = 0;
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) nchunk += (k0 + j * CW < p.Ktot) ? 1 : 0;
+        const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
+        mbar_expect_tx(&full_bar[stage], nchunk * kChunkBytes + b_bytes);
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) {
+          const int k = k0 + j * CW;
+          if (k < p.Ktot) {
+            if (IM2COL) {
+              const int tap = k / p.Cin;
+              const int c0 = k - tap * p.Cin;
+              const int r = tap / p.kw;
+              const int s = tap - r * p.kw;
+              tma_load_im2col_4d(sa + j * kChunkBytes, &tmA, &full_bar[stage], c0, w0, h0, img,
+                                 (uint16_t)s, (uint16_t)r);
+            } else {
+              tma_load_2d(sa + j * kChunkBytes, &tmA, &full_bar[stage], k, m0);
+            }
+          }
+        }
+        tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      const uint32_t a_lt = swizzle_layout_type(CW * 2);
+      const uint32_t b_lt = swizzle_layout_type(p.b_sw_bytes);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+        const int k0 = kb * kStageK;
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) {
+          if (k0 + j * CW < p.Ktot) {
+#pragma unroll
+            for (int ks = 0; ks < kKSteps; ++ks) {
+              const uint64_t da =
+                  make_smem_desc(sa + j * kChunkBytes + ks * 32, 16, 8 * CW * 2, a_lt);
+              const uint64_t db = make_smem_desc(sb + (j * kKSteps + ks) * 32, 16,
+                                                 8 * p.b_sw_bytes, b_lt);
+              umma_bf16(tmem_base, da, db, kIdesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int quarter = warp & 3;
+    const int row = m0 + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+    const bool stats = p.ch_sum != nullptr;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+      const int col0 = n0 + c * 32;
+      const size_t off = static_cast<size_t>(row) * p.Cout + col0;
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col0 + i);
+      }
+      if (p.add_src && row_ok) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.add_src + off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = __ldg(src + q);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
+            f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+          }
+        }
+      }
+      if (p.mask_src && row_ok) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.mask_src + off);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = __ldg(src + q);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(w4[e] << 16);
+            const float hi = __uint_as_float(w4[e] & 0xffff0000u);
+            if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
+            if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
+          }
+        }
+      }
+      if (p.out_f32) {
+        if (row_ok) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + off);
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            dst[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+        }
+      } else {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+        if (row_ok) {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            dst[q] = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+        }
+        if (stats) {
+          // statistics of the tensor as stored (bf16-rounded); rows past M contribute zero
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float lo = row_ok ? __uint_as_float(pk[i] << 16) : 0.f;
+            const float hi = row_ok ? __uint_as_float(pk[i] & 0xffff0000u) : 0.f;
+            s1[2 * i] = lo;
+            s1[2 * i + 1] = hi;
+            s2[2 * i] = lo * lo;
+            s2[2 * i + 1] = hi * hi;
+          }
+          const float cs = warp_transpose_sum(s1, lane);
+          const float cq = warp_transpose_sum(s2, lane);
+          red_sum[quarter][c * 32 + lane] = cs;
+          red_sq[quarter][c * 32 + lane] = cq;
+        }
+      }
+    }
+    if (stats) {
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      const int t = threadIdx.x - 64;  // 0..127
+      for (int col = t; col < BN; col += 128) {
+        const float s = red_sum[0][col] + red_sum[1][col] + red_sum[2][col] + red_sum[3][col];
+        const float q = red_sq[0][col] + red_sq[1][col] + red_sq[2][col] + red_sq[3][col];
+        atomicAdd(p.ch_sum + n0 + col, s);
+        atomicAdd(p.ch_sumsq + n0 + col, q);
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad kernel
+// ------------------------------------------------------------------------------------------
+struct WgradParams {
+  int P;           // pixels B*Ho*Wo (GEMM K)
+  int Cout;        // GEMM M
+  int Cin;
+  int Ktot;        // kh*kw*Cin (GEMM N)
+  int kw;
+  int HoWo, Wo;
+  int stride, pad_h_lo, pad_w_lo;
+  int stages_total;      // ceil(P / 64)
+  int stages_per_split;
+  float* dw;
+};
+
+constexpr int kWgPix = 64;   // pixels per pipeline stage (4 UMMA K-steps)
+
+template <int BNW>
+struct WgradCfg {
+  static constexpr int kABytes = kWgPix * 128 * 2;   // 64 pixels x 128 output channels
+  static constexpr int kBBytes = kWgPix * BNW * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BNW >= 256) ? 4 : 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+};
+
+template <int BNW, int CW, int CWA, bool IM2COL>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const WgradParams p) {
+  using Cfg = WgradCfg<BNW>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kNChunks = BNW / CW;
+  constexpr int kBChunkBytes = kWgPix * CW * 2;
+  constexpr int kAChunkBytes = kWgPix * CWA * 2;
+  constexpr uint32_t kIdesc = make_idesc_bf16(BNW, true, true);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[kStages];
+  __shared__ uint64_t empty_bar[kStages];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BNW;
+  const int co0 = blockIdx.y * 128;
+  const int ks_begin = blockIdx.z * p.stages_per_split;
+  int ks_end = ks_begin + p.stages_per_split;
+  if (ks_end > p.stages_total) ks_end = p.stages_total;
+  const int num_ks = ks_end - ks_begin;   // >= 1 by construction of the grid
+
+  int a_chunks = (p.Cout - co0 < 128 ? p.Cout - co0 : 128) / CWA;
+  int b_chunks = 0;
+#pragma unroll
+  for (int j = 0; j < kNChunks; ++j) b_chunks += (n0 + j * CW < p.Ktot) ? 1 : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<(BNW < 32 ? 32 : BNW)>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < num_ks; ++it) {
+        const int p0 = (ks_begin + it) * kWgPix;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        mbar_expect_tx(&full_bar[stage], a_chunks * kAChunkBytes + b_chunks * kBChunkBytes);
+        for (int i = 0; i < a_chunks; ++i)
+          tma_load_2d(sa + i * kAChunkBytes, &tmDY, &full_bar[stage], co0 + i * CWA, p0);
+        int img = 0, h0 = 0, w0 = 0;
+        if (IM2COL) {
+          img = p0 / p.HoWo;
+          const int rem = p0 - img * p.HoWo;
+          const int po = rem / p.Wo;
+          const int qo = rem - po * p.Wo;
+          h0 = po * p.stride - p.pad_h_lo;
+          w0 = qo * p.stride - p.pad_w_lo;
+        }
+#pragma unroll
+        for (int j = 0; j < kNChunks; ++j) {
+          const int n = n0 + j * CW;
+          if (n < p.Ktot) {
+            const int tap = n / p.Cin;
+            const int c0 = n - tap * p.Cin;
+            if (IM2COL) {
+              const int r = tap / p.kw;
+              const int s = tap - r * p.kw;
+              tma_load_im2col_4d(sb + j * kBChunkBytes, &tmX, &full_bar[stage], c0, w0, h0, img,
+                                 (uint16_t)s, (uint16_t)r);
+            } else {
+              tma_load_2d(sb + j * kBChunkBytes, &tmX, &full_bar[stage], c0, p0);
+            }
+          }
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t accumulate = 0;
+      const uint32_t a_lt = swizzle_layout_type(CWA * 2);
+      const uint32_t b_lt = swizzle_layout_type(CW * 2);
+      for (int it = 0; it < num_ks; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int ks = 0; ks < kWgPix / 16; ++ks) {
+          // MN-major operands: one pixel row = CW*2 bytes, 8-row groups SBO apart, column
+          // blocks (64/32/16 channels) LBO apart.  16 pixel rows per UMMA.
+          const uint64_t da = make_smem_desc(sa + ks * 16 * CWA * 2, kAChunkBytes, 8 * CWA * 2, a_lt);
+          const uint64_t db = make_smem_desc(sb + ks * 16 * CW * 2, kBChunkBytes, 8 * CW * 2, b_lt);
+          umma_bf16(tmem_base, da, db, kIdesc, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int co = co0 + quarter * 32 + lane;
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BNW / 32; ++c) {
+      if (n0 + c * 32 >= p.Ktot) break;   // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      if (co < p.Cout) {
+        float* dst = p.dw + static_cast<size_t>(co) * p.Ktot + n0 + c * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (n0 + c * 32 + i < p.Ktot) atomicAdd(dst + i, __uint_as_float(v[i]));
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<(BNW < 32 ? 32 : BNW)>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host launchers
+// ------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int CW, bool IM2COL>
+static int launch_conv_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p,
+                            cudaStream_t stream) {
+  using Cfg = FpropCfg<BN>;
+  static bool attr_set = false;
+  auto kern = conv_gemm_kernel<BN, CW, IM2COL>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid(p.Cout / BN, ceil_div(p.M, kBM), 1);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  count_launch();
+  return check_launch("conv_gemm_kernel");
+}
+
+template <int BN>
+static int dispatch_conv_gemm(int cw, bool im2col, const CUtensorMap& ta, const CUtensorMap& tb,
+                              const ConvGemmParams& p, cudaStream_t s) {
+  if (im2col) {
+    if (cw == 64) return launch_conv_gemm<BN, 64, true>(ta, tb, p, s);
+    if (cw == 32) return launch_conv_gemm<BN, 32, true>(ta, tb, p, s);
+    return launch_conv_gemm<BN, 16, true>(ta, tb, p, s);
+  }
+  if (cw == 64) return launch_conv_gemm<BN, 64, false>(ta, tb, p, s);
+  if (cw == 32) return launch_conv_gemm<BN, 32, false>(ta, tb, p, s);
+  return launch_conv_gemm<BN, 16, false>(ta, tb, p, s);
+}
+
+static int chunk_width(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
+
+static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w, void* y,
+                          float* ch_sum, float* ch_sumsq, const void* add_src,
+                          const void* mask_src, const float* bias, int out_f32,
+                          cudaStream_t stream) {
+  ACNN_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.Cin > 0 && g.Cout > 0, "conv: empty geometry");
+  ACNN_REQUIRE(g.Cin % 16 == 0, "conv: Cin=%d must be a multiple of 16", g.Cin);
+  ACNN_REQUIRE(g.Cout % 32 == 0, "conv: Cout=%d must be a multiple of 32", g.Cout);
+  ACNN_REQUIRE(g.stride >= 1 && g.kh >= 1 && g.kw >= 1, "conv: bad kernel/stride");
+  ACNN_REQUIRE((ch_sum == nullptr) == (ch_sumsq == nullptr), "conv: ch_sum/ch_sumsq must pair");
+  ACNN_REQUIRE(!(ch_sum && out_f32), "conv: statistics only with bf16 output");
+  const int Ho = (g.H + g.pad_h_lo + g.pad_h_hi - g.kh) / g.stride + 1;
+  const int Wo = (g.W + g.pad_w_lo + g.pad_w_hi - g.kw) / g.stride + 1;
+  ACNN_REQUIRE(Ho > 0 && Wo > 0, "conv: empty output");
+  ACNN_REQUIRE(g.pad_h_lo <= 128 && g.pad_w_lo <= 128 && g.kh <= 128 && g.kw <= 128,
+               "conv: padding / filter exceed the TMA im2col corner range");
+  int rc = load_driver_fns();
+  if (rc) return rc;
+
+  const bool plain = (g.kh == 1 && g.kw == 1 && g.stride == 1 && g.pad_h_lo == 0 &&
+                      g.pad_w_lo == 0 && g.pad_h_hi == 0 && g.pad_w_hi == 0);
+  const int cw = chunk_width(g.Cin);
+  ConvGemmParams p;
+  p.M = g.B * Ho * Wo;
+  p.Cout = g.Cout;
+  p.Cin = g.Cin;
+  p.Ktot = g.kh * g.kw * g.Cin;
+  p.kw = g.kw;
+  p.HoWo = Ho * Wo;
+  p.Wo = Wo;
+  p.stride = g.stride;
+  p.pad_h_lo = g.pad_h_lo;
+  p.pad_w_lo = g.pad_w_lo;
+  p.b_sw_bytes = p.Ktot >= 64 ? 128 : p.Ktot * 2;
+  p.y = y;
+  p.ch_sum = ch_sum;
+  p.ch_sumsq = ch_sumsq;
+  p.add_src = static_cast<const __nv_bfloat16*>(add_src);
+  p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
+  p.bias = bias;
+  p.out_f32 = out_f32;
+  ACNN_REQUIRE(p.b_sw_bytes == 128 || p.b_sw_bytes == 64 || p.b_sw_bytes == 32,
+               "conv: unsupported K=%d", p.Ktot);
+
+  const int bn = (g.Cout % 128 == 0) ? 128 : ((g.Cout % 64 == 0) ? 64 : 32);
+  CUtensorMap ta, tb;
+  if (plain) {
+    rc = make_map_2d(&ta, x, p.M, g.Cin, g.Cin, kBM, cw);
+  } else {
+    rc = make_map_im2col(&ta, x, g.B, g.H, g.W, g.Cin, g.kh, g.kw, g.stride, g.pad_h_lo,
+                         g.pad_h_hi, g.pad_w_lo, g.pad_w_hi, cw, kBM);
+  }
+  if (rc) return rc;
+  rc = make_map_2d(&tb, w, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
+  if (rc) return rc;
+  if (bn == 128) return dispatch_conv_gemm<128>(cw, !plain, ta, tb, p, stream);
+  if (bn == 64) return dispatch_conv_gemm<64>(cw, !plain, ta, tb, p, stream);
+  return dispatch_conv_gemm<32>(cw, !plain, ta, tb, p, stream);
+}
+
+template <int BNW, int CW, int CWA, bool IM2COL>
+static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgradParams p, int m_tiles,
+                        int n_tiles, cudaStream_t stream) {
+  using Cfg = WgradCfg<BNW>;
+  static bool attr_set = false;
+  auto kern = wgrad_gemm_kernel<BNW, CW, CWA, IM2COL>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(wgrad): %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  // split the pixel (K) range so that roughly two waves of CTAs cover the GPU
+  const int tiles = m_tiles * n_tiles;
+  int splits = ceil_div(2 * num_sms(), tiles);
+  const int max_splits = p.stages_total >= 8 ? p.stages_total / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.stages_per_split = ceil_div(p.stages_total, splits);
+  splits = ceil_div(p.stages_total, p.stages_per_split);
+  dim3 grid(n_tiles, m_tiles, splits);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tdy, tx, p);
+  count_launch();
+  return check_launch("wgrad_gemm_kernel");
+}
+
+template <int BNW, int CW, bool IM2COL>
+static int dispatch_wgrad_cwa(int cwa, const CUtensorMap& tdy, const CUtensorMap& tx,
+                              const WgradParams& p, int mt, int nt, cudaStream_t s) {
+  if (cwa == 64) return launch_wgrad<BNW, CW, 64, IM2COL>(tdy, tx, p, mt, nt, s);
+  return launch_wgrad<BNW, CW, 32, IM2COL>(tdy, tx, p, mt, nt, s);
+}
+
+template <int BNW, bool IM2COL>
+static int dispatch_wgrad_cw(int cw, int cwa, const CUtensorMap& tdy, const CUtensorMap& tx,
+                             const WgradParams& p, int mt, int nt, cudaStream_t s) {
+  if constexpr (BNW >= 64) {
+    if (cw == 64) return dispatch_wgrad_cwa<BNW, 64, IM2COL>(cwa, tdy, tx, p, mt, nt, s);
+  }
+  if (cw == 32) return dispatch_wgrad_cwa<BNW, 32, IM2COL>(cwa, tdy, tx, p, mt, nt, s);
+  if (cw == 16) return dispatch_wgrad_cwa<BNW, 16, IM2COL>(cwa, tdy, tx, p, mt, nt, s);
+  set_error("wgrad: chunk width %d wider than N tile %d", cw, BNW);
+  return ACNN_ERR_INVALID;
+}
+
+template <bool IM2COL>
+static int dispatch_wgrad(int bnw, int cw, int cwa, const CUtensorMap& tdy, const CUtensorMap& tx,
+                          const WgradParams& p, int mt, int nt, cudaStream_t s) {
+  if (bnw == 256) return dispatch_wgrad_cw<256, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
+  if (bnw == 128) return dispatch_wgrad_cw<128, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
+  if (bnw == 64) return dispatch_wgrad_cw<64, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
+  return dispatch_wgrad_cw<32, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
+}
+
+static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* dy, float* dw,
+                           cudaStream_t stream) {
+  ACNN_REQUIRE(g.Cin % 16 == 0 && g.Cout % 32 == 0, "wgrad: Cin %% 16 / Cout %% 32 required");
+  const int Ho = (g.H + g.pad_h_lo + g.pad_h_hi - g.kh) / g.stride + 1;
+  const int Wo = (g.W + g.pad_w_lo + g.pad_w_hi - g.kw) / g.stride + 1;
+  ACNN_REQUIRE(Ho > 0 && Wo > 0, "wgrad: empty output");
+  int rc = load_driver_fns();
+  if (rc) return rc;
+  const bool plain = (g.kh == 1 && g.kw == 1 && g.stride == 1 && g.pad_h_lo == 0 &&
+                      g.pad_w_lo == 0 && g.pad_h_hi == 0 && g.pad_w_hi == 0);
+  WgradParams p;
+  p.P = g.B * Ho * Wo;
+  p.Cout = g.Cout;
+  p.Cin = g.Cin;
+  p.Ktot = g.kh * g.kw * g.Cin;
+  p.kw = g.kw;
+  p.HoWo = Ho * Wo;
+  p.Wo = Wo;
+  p.stride = g.stride;
+  p.pad_h_lo = g.pad_h_lo;
+  p.pad_w_lo = g.pad_w_lo;
+  p.stages_total = ceil_div(p.P, kWgPix);
+  p.stages_per_split = p.stages_total;
+  p.dw = dw;
+  const int cw = chunk_width(g.Cin);
+  const int cwa = (g.Cout % 64 == 0) ? 64 : 32;
+  int bnw = 256;
+  if (p.Ktot < 256) bnw = p.Ktot >= 128 ? 128 : (p.Ktot >= 64 ? 64 : 32);
+  CUtensorMap tdy, tx;
+  rc = make_map_2d(&tdy, dy, p.P, g.Cout, g.Cout, kWgPix, cwa);
+  if (rc) return rc;
+  if (plain) {
+    rc = make_map_2d(&tx, x, p.P, g.Cin, g.Cin, kWgPix, cw);
+  } else {
+    rc = make_map_im2col(&tx, x, g.B, g.H, g.W, g.Cin, g.kh, g.kw, g.stride, g.pad_h_lo,
+                         g.pad_h_hi, g.pad_w_lo, g.pad_w_hi, cw, kWgPix);
+  }
+  if (rc) return rc;
+  const int mt = ceil_div(g.Cout, 128);
+  const int nt = ceil_div(p.Ktot, bnw);
+  if (plain) return dispatch_wgrad<false>(bnw, cw, cwa, tdy, tx, p, mt, nt, stream);
+  return dispatch_wgrad<true>(bnw, cw, cwa, tdy, tx, p, mt, nt, stream);
+}
+
+}  // namespace acnn
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int acnn_conv_fprop(const acnn_conv_geom* g, const void* x, const void* w, void* y, float* ch_sum,
+                    float* ch_sumsq, const void* add_src, const void* mask_src, const float* bias,
+                    int out_f32, void* stream) {
+  if (!g || !x || !w || !y) {
+    acnn::set_error("acnn_conv_fprop: null argument");
+    return ACNN_ERR_INVALID;
+  }
+  return acnn::conv_gemm_host(*g, x, w, y, ch_sum, ch_sumsq, add_src, mask_src, bias, out_f32,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int acnn_conv_dgrad(const acnn_conv_geom* g, const void* dy, const void* w_dgrad, void* dx,
+                    const void* add_src, const void* mask_src, void* stream) {
+  if (!g || !dy || !w_dgrad || !dx) {
+    acnn::set_error("acnn_conv_dgrad: null argument");
+    return ACNN_ERR_INVALID;
+  }
+  if (g->stride != 1) {
+    acnn::set_error("acnn_conv_dgrad: stride %d (zero-insert dy first, then call with stride 1)",
+                    g->stride);
+    return ACNN_ERR_UNSUPPORTED;
+  }
+  // dx = correlation of dy with the flipped, channel-transposed filter; padding k-1-pad.
+  const int Ho = g->H + g->pad_h_lo + g->pad_h_hi - g->kh + 1;
+  const int Wo = g->W + g->pad_w_lo + g->pad_w_hi - g->kw + 1;
+  acnn_conv_geom t;
+  t.B = g->B;
+  t.H = Ho;
+  t.W = Wo;
+  t.Cin = g->Cout;
+  t.Cout = g->Cin;
+  t.kh = g->kh;
+  t.kw = g->kw;
+  t.stride = 1;
+  t.pad_h_lo = g->kh - 1 - g->pad_h_lo;
+  t.pad_h_hi = g->kh - 1 - g->pad_h_hi;
+  t.pad_w_lo = g->kw - 1 - g->pad_w_lo;
+  t.pad_w_hi = g->kw - 1 - g->pad_w_hi;
+  return acnn::conv_gemm_host(t, dy, w_dgrad, dx, nullptr, nullptr, add_src, mask_src, nullptr, 0,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int acnn_conv_wgrad(const acnn_conv_geom* g, const void* x, const void* dy, float* dw,
+                    void* stream) {
+  if (!g || !x || !dy || !dw) {
+    acnn::set_error("acnn_conv_wgrad: null argument");
+    return ACNN_ERR_INVALID;
+  }
+  return acnn::conv_wgrad_host(*g, x, dy, dw, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolutions (through the C ABI) against the CPU oracle.
+
+Inputs are bf16-representable, so the only differences are fp32 accumulation order and the final
+bf16 rounding of the output: tolerance = 2^-8 relative to the tensor's max magnitude for bf16
+outputs, 1e-4 for fp32 outputs (wgrad, logits).
+"""
+import pytest
+import torch
+
+from oracle import tf_ops
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 2.0 ** -8
+F32_TOL = 1e-4
+
+
+def _geom(B, H, W, Cin, Cout, k, stride, pads=None):
+    from assembled_cnn_b200._lib import ConvGeom
+    kh, kw = (k, k) if isinstance(k, int) else k
+    if pads is None:
+        if stride == 1:
+            pads = ((kh - 1) // 2, kh - 1 - (kh - 1) // 2, (kw - 1) // 2, kw - 1 - (kw - 1) // 2)
+        else:  # fixed_padding
+            pads = ((kh - 1) // 2, kh - 1 - (kh - 1) // 2, (kw - 1) // 2, kw - 1 - (kw - 1) // 2)
+    return ConvGeom(B, H, W, Cin, Cout, kh, kw, stride, *pads)
+
+
+def _ref_conv(x, w_hwio, g):
+    import torch.nn.functional as F
+    xp = F.pad(x, (0, 0, g.pad_w_lo, g.pad_w_hi, g.pad_h_lo, g.pad_h_hi))
+    return tf_ops.conv2d(xp, w_hwio, g.stride, "VALID")
+
+
+def _rand_bf16(*shape, seed=0, scale=1.0):
+    gen = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=gen) * scale).bfloat16().float()
+
+
+def _relerr(a, b):
+    return (a.double() - b.double()).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+CASES = [
+    # B, H, W, Cin, Cout, k, stride, pads
+    (2, 16, 16, 64, 128, 1, 1, None),      # plain 1x1, SW128
+    (2, 16, 16, 32, 64, 1, 1, None),       # plain 1x1, Cin 32 (SW64 A and B)
+    (3, 7, 7, 256, 64, 1, 1, None),        # M = 147: ragged last tile, K loop 4 stages
+    (2, 14, 14, 64, 64, 3, 1, None),       # im2col 3x3, tiles cross image borders
+    (2, 12, 12, 32, 32, 3, 1, None),       # Cin 32: two taps per stage, odd tap count
+    (2, 16, 16, 64, 64, 3, 2, None),       # strided 3x3 with fixed_padding
+    (2, 12, 12, 16, 64, (4, 4), 1, (2, 1, 2, 1)),   # space-to-depth stem: 4x4, asymmetric pad
+    (2, 16, 16, 64, 128, 1, 2, (0, 0, 0, 0)),       # strided 1x1 projection (rv=1)
+    (2, 7, 7, 128, 256, 3, 1, None),       # 7x7 spatial, two N tiles
+    (1, 10, 10, 128, 32, 3, 1, None),      # narrow N = 32
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_fprop_matches_oracle(lib, case):
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout, k, stride, pads = case
+    g = _geom(B, H, W, Cin, Cout, k, stride, pads)
+    x = _rand_bf16(B, H, W, Cin, seed=1)
+    w_hwio = _rand_bf16(g.kh, g.kw, Cin, Cout, seed=2, scale=(g.kh * g.kw * Cin) ** -0.5)
+    ref = _ref_conv(x, w_hwio, g)
+    Ho, Wo = g.out_hw()
+    assert ref.shape == (B, Ho, Wo, Cout)
+    xd = x.bfloat16().cuda()
+    wd = w_hwio.permute(3, 0, 1, 2).contiguous().bfloat16().cuda()      # OHWI
+    yd = torch.full((B, Ho, Wo, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    s1 = torch.zeros(Cout, device="cuda")
+    s2 = torch.zeros(Cout, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(), s1.data_ptr(),
+                                   s2.data_ptr(), None, None, None, 0, st), "conv_fprop")
+    torch.cuda.synchronize()
+    y = yd.float().cpu()
+    assert _relerr(y, ref) < BF16_TOL
+    # fused batch-norm statistics are those of the stored (rounded) tensor
+    assert _relerr(s1.cpu(), y.sum(dim=(0, 1, 2))) < 1e-3 or (s1.cpu() - y.sum(dim=(0, 1, 2))).abs().max() < 1e-2
+    assert _relerr(s2.cpu(), (y * y).sum(dim=(0, 1, 2))) < 1e-3
+
+
+def test_fprop_epilogue_add_mask_bias(lib):
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout = 2, 8, 8, 64, 128
+    g = _geom(B, H, W, Cin, Cout, 3, 1)
+    x = _rand_bf16(B, H, W, Cin, seed=3)
+    w_hwio = _rand_bf16(3, 3, Cin, Cout, seed=4, scale=(9 * Cin) ** -0.5)
+    add = _rand_bf16(B, H, W, Cout, seed=5)
+    mask = _rand_bf16(B, H, W, Cout, seed=6)
+    bias = torch.randn(Cout, generator=torch.Generator().manual_seed(7))
+    ref = _ref_conv(x, w_hwio, g)
+    st = torch.cuda.current_stream().cuda_stream
+    xd, wd = x.bfloat16().cuda(), w_hwio.permute(3, 0, 1, 2).contiguous().bfloat16().cuda()
+    # add + mask, bf16 out
+    yd = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+    addd, maskd = add.bfloat16().cuda(), mask.bfloat16().cuda()
+    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(), None, None,
+                                   addd.data_ptr(), maskd.data_ptr(), None, 0, st))
+    torch.cuda.synchronize()
+    want = (ref + add) * (mask > 0)
+    assert _relerr(yd.float().cpu(), want) < BF16_TOL
+    # bias, fp32 out (dense path)
+    yf = torch.empty(B, H, W, Cout, dtype=torch.float32, device="cuda")
+    biasd = bias.cuda()
+    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yf.data_ptr(), None, None,
+                                   None, None, biasd.data_ptr(), 1, st))
+    torch.cuda.synchronize()
+    assert _relerr(yf.cpu(), ref + bias) < F32_TOL
+
+
+DGRAD_CASES = [c for c in CASES if c[6] == 1]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES, ids=[str(c) for c in DGRAD_CASES])
+def test_dgrad_matches_autograd(lib, case):
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout, k, stride, pads = case
+    if Cout % 16 or Cin % 32:
+        pytest.skip("dgrad needs Cout%16==0 (its K) and Cin%32==0 (its N)")
+    g = _geom(B, H, W, Cin, Cout, k, stride, pads)
+    x = _rand_bf16(B, H, W, Cin, seed=1).requires_grad_(True)
+    w_hwio = _rand_bf16(g.kh, g.kw, Cin, Cout, seed=2, scale=(g.kh * g.kw * Cin) ** -0.5)
+    y = _ref_conv(x, w_hwio, g)
+    dy = _rand_bf16(*y.shape, seed=8)
+    (dx_ref,) = torch.autograd.grad(y, x, dy)
+    # dgrad weight layout: [Cin][kh][kw][Cout] with taps flipped
+    wdg = w_hwio.flip(0, 1).permute(2, 0, 1, 3).contiguous().bfloat16().cuda()
+    dxd = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    dyd = dy.bfloat16().cuda()
+    _lib.check(lib.acnn_conv_dgrad(g, dyd.data_ptr(), wdg.data_ptr(),
+                                   dxd.data_ptr(), None, None, st), "conv_dgrad")
+    torch.cuda.synchronize()
+    assert _relerr(dxd.float().cpu(), dx_ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_wgrad_matches_autograd(lib, case):
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout, k, stride, pads = case
+    g = _geom(B, H, W, Cin, Cout, k, stride, pads)
+    x = _rand_bf16(B, H, W, Cin, seed=1)
+    w_hwio = _rand_bf16(g.kh, g.kw, Cin, Cout, seed=2).requires_grad_(True)
+    y = _ref_conv(x, w_hwio, g)
+    dy = _rand_bf16(*y.shape, seed=8)
+    (dw_ref,) = torch.autograd.grad(y, w_hwio, dy)
+    dwd = torch.zeros(Cout, g.kh, g.kw, Cin, dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    xd, dyd = x.bfloat16().cuda(), dy.bfloat16().cuda()
+    _lib.check(lib.acnn_conv_wgrad(g, xd.data_ptr(), dyd.data_ptr(), dwd.data_ptr(), st),
+               "conv_wgrad")
+    torch.cuda.synchronize()
+    got = dwd.cpu().permute(1, 2, 3, 0)      # OHWI -> HWIO
+    assert _relerr(got, dw_ref) < F32_TOL
+
+
+def test_large_shapes_linearity(lib):
+    """BASELINE-size layer (stage-4 SK 3x3 512->1024 at 14x14, B=32): conv(a*x1+x2) property and
+    a sampled check of output pixels against the oracle."""
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout = 32, 14, 14, 512, 1024
+    g = _geom(B, H, W, Cin, Cout, 3, 1)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=gen).bfloat16()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=gen) * (9 * Cin) ** -0.5).bfloat16()
+    y = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.acnn_conv_fprop(g, x.data_ptr(), w.data_ptr(), y.data_ptr(), None, None, None,
+                                   None, None, 0, st))
+    torch.cuda.synchronize()
+    # sampled pixels vs the oracle (image 0 and the last image)
+    for b in (0, B - 1):
+        ref = _ref_conv(x[b:b + 1].float().cpu(), w.float().cpu().permute(1, 2, 3, 0), g)
+        assert _relerr(y[b:b + 1].float().cpu(), ref) < BF16_TOL
