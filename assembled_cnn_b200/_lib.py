@@ -30,17 +30,47 @@ class AcnnError(RuntimeError):
     pass
 
 
-# name -> (restype, argtypes); must list every symbol include/acnn.h declares.
-PROTOTYPES = {
-    "acnn_last_error": (C.c_char_p, []),
-    "acnn_version": (c_int, []),
-    "acnn_launch_count": (c_int64, []),
-    "acnn_conv_fprop": (c_int, [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    "acnn_conv_dgrad": (c_int, [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p,
-                                c_void_p, c_void_p]),
-    "acnn_conv_wgrad": (c_int, [C.POINTER(ConvGeom), c_void_p, c_void_p, c_void_p, c_void_p]),
-}
+HEADER_PATH = os.path.join(_HERE, "..", "include", "acnn.h")
+
+
+class WeightDesc(C.Structure):
+    """struct acnn_weight_desc (include/acnn.h)."""
+    _fields_ = [("master_off", C.c_int64), ("fprop_off", C.c_int64), ("dgrad_off", C.c_int64),
+                ("Cout", C.c_int32), ("taps", C.c_int32), ("Cin", C.c_int32), ("pad_", C.c_int32)]
+
+
+def _parse_header(path: str = HEADER_PATH) -> dict:
+    """Prototype table generated from the header itself, so binding and ABI cannot drift.
+    Pointers (and the cudaStream_t passed as void*) bind as c_void_p."""
+    import re
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(?:^|\n)\s*(const\s+char\s*\*|int64_t|int)\s+(acnn_\w+)\s*\(([^;{]*?)\)\s*;",
+                         text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        res = C.c_char_p if "char" in ret else (c_int64 if ret == "int64_t" else c_int)
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "acnn_conv_geom" in a:
+                    argtypes.append(C.POINTER(ConvGeom))
+                elif "*" in a:
+                    argtypes.append(c_void_p)
+                elif a.startswith("int64_t"):
+                    argtypes.append(c_int64)
+                elif a.startswith("float"):
+                    argtypes.append(c_float)
+                elif a.startswith("int"):
+                    argtypes.append(c_int)
+                else:
+                    raise AcnnError(f"cannot bind argument {a!r} of {name}")
+        protos[name] = (res, argtypes)
+    return protos
+
+
+PROTOTYPES = _parse_header()
 
 _lib = None
 

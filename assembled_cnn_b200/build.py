@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "--extended-lambda",
 ]
 
 

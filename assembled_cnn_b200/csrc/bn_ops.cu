@@ -1,0 +1,593 @@
+// Batch-norm, SK and SE elementwise / reduction kernels (HBM-bound; 16-byte vector accesses along
+// the NHWC channel dimension, per-channel reductions through shared memory + one atomic per
+// channel per CTA).  Reference: nets/model_helper.py:26-37, nets/blocks.py:110-184 and the
+// backward formulas of SURVEY App. C.
+#include "common.h"
+#include "vec.cuh"
+
+namespace acnn {
+
+constexpr int kT = 256;
+
+// ------------------------------------------------------------------------------------------
+// bn_finalize
+// ------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+                                   float count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* moving_mean,
+                                   float* moving_var, float momentum, float eps, int training,
+                                   float* scale, float* shift, float* mean_out, float* rstd_out,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, var;
+  if (training) {
+    mean = sum[c] / count;
+    var = fmaxf(sumsq[c] / count - mean * mean, 0.f);
+    const float unbiased = var * (count / fmaxf(count - 1.f, 1.f));
+    moving_mean[c] = moving_mean[c] * momentum + mean * (1.f - momentum);
+    moving_var[c] = moving_var[c] * momentum + unbiased * (1.f - momentum);
+  } else {
+    mean = moving_mean[c];
+    var = moving_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  mean_out[c] = mean;
+  rstd_out[c] = rstd;
+}
+
+// ------------------------------------------------------------------------------------------
+// bn_act : out = relu?( (a*sa + ha) [*gate] + R )
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
+              const float* __restrict__ ha, const bf16* __restrict__ b,
+              const float* __restrict__ sb, const float* __restrict__ hb, int b_mode,
+              const float* __restrict__ gate, int relu, bf16* __restrict__ out, int H, int W, int C,
+              int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t pix = i / CG;
+    const int c0 = cg << 3;
+    float v[8], s[8], h[8];
+    load8(a + i * 8, v);
+    loadf8(sa + c0, s);
+    loadf8(ha + c0, h);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], s[k], h[k]);
+    if (gate) {
+      const int64_t bimg = pix / ((int64_t)H * W);
+      float g[8];
+      loadf8(gate + bimg * C + c0, g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= g[k];
+    }
+    if (b_mode == 1) {
+      float r[8];
+      load8(b + i * 8, r);
+      loadf8(sb + c0, s);
+      loadf8(hb + c0, h);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s[k], h[k]);
+    } else if (b_mode == 2) {
+      float r[8];
+      load8(b + i * 8, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    } else if (b_mode == 3) {
+      const int w = (int)(pix % W);
+      const int64_t t = pix / W;
+      const int hh = (int)(t % H);
+      const int64_t bimg = t / H;
+      const int64_t src = ((bimg * (H >> 1) + (hh >> 1)) * (W >> 1) + (w >> 1)) * C + c0;
+      float r[8];
+      load8(b + src, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += r[k];
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    store8(out + i * 8, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Column (per-channel) reductions over [M][C]
+// ------------------------------------------------------------------------------------------
+// Every thread owns one 8-channel group `cg` and walks rows; NACC accumulator vectors per thread.
+// dest(a, i) gives the index into `sums` of accumulator a, lane-channel i.
+template <int NACC, class Dest>
+__device__ __forceinline__ void block_reduce_atomic(float (&acc)[NACC][8], int CG, float* sums,
+                                                    Dest dest) {
+  __shared__ float red[kT][NACC * 8 + 1];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[tid][a * 8 + i] = acc[a][i];
+  __syncthreads();
+  const int RPB = kT / CG;
+  // spread the final sums over all threads: thread t reduces value (t % (NACC*8)) of group t / ..
+  for (int item = tid; item < CG * NACC * 8; item += kT) {
+    const int cg = item / (NACC * 8);
+    const int k = item % (NACC * 8);
+    float s = 0.f;
+    for (int r = 0; r < RPB; ++r) s += red[r * CG + cg][k];
+    atomicAdd(sums + dest(k >> 3, cg * 8 + (k & 7)), s);
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ gate, const float* __restrict__ addbc,
+                     float* sums, int64_t M, int HW, int C) {
+  const int CG = C >> 3;
+  const int RPB = kT / CG;
+  const int cg = threadIdx.x % CG;
+  const int rsub = threadIdx.x / CG;
+  const int c0 = cg << 3;
+  float mu[8], rs[8];
+  loadf8(mean + c0, mu);
+  loadf8(rstd + c0, rs);
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * RPB + rsub; r < M; r += (int64_t)gridDim.x * RPB) {
+    float gv[8], yv[8];
+    load8(g + r * C + c0, gv);
+    load8(y + r * C + c0, yv);
+    if (gate || addbc) {
+      const int64_t bimg = r / HW;
+      if (gate) {
+        float t[8];
+        loadf8(gate + bimg * C + c0, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gv[i] *= t[i];
+      }
+      if (addbc) {
+        float t[8];
+        loadf8(addbc + bimg * C + c0, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gv[i] += t[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += gv[i];
+      acc[1][i] += gv[i] * ((yv[i] - mu[i]) * rs[i]);
+    }
+  }
+  block_reduce_atomic<2>(acc, CG, sums, [C](int a, int c) { return a * C + c; });
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums,
+                                       const float* __restrict__ gamma,
+                                       const float* __restrict__ mean,
+                                       const float* __restrict__ rstd, float count, float* coef,
+                                       float* dgamma, float* dbeta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float s1 = sums[c], s2 = sums[C + c];
+  const float k1 = gamma[c] * rstd[c];
+  const float k2 = -k1 * rstd[c] * s2 / count;
+  const float k3 = -k1 * s1 / count - k2 * mean[c];
+  coef[c] = k1;
+  coef[C + c] = k2;
+  coef[2 * C + c] = k3;
+  dgamma[c] = s2;
+  dbeta[c] = s1;
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
+                    const float* __restrict__ coef, const float* __restrict__ gate,
+                    const float* __restrict__ addbc, bf16* __restrict__ dy, int HW, int C,
+                    int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int c0 = cg << 3;
+    float gv[8], yv[8], k1[8], k2[8], k3[8];
+    load8(g + i * 8, gv);
+    load8(y + i * 8, yv);
+    loadf8(coef + c0, k1);
+    loadf8(coef + C + c0, k2);
+    loadf8(coef + 2 * C + c0, k3);
+    if (gate || addbc) {
+      const int64_t bimg = (i / CG) / HW;
+      if (gate) {
+        float t[8];
+        loadf8(gate + bimg * C + c0, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[k] *= t[k];
+      }
+      if (addbc) {
+        float t[8];
+        loadf8(addbc + bimg * C + c0, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gv[k] += t[k];
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], gv[k], fmaf(k2[k], yv[k], k3[k]));
+    store8(dy + i * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-image spatial reductions  out[b, c] = (1/HW or 1) * sum_hw f(...)
+// MODE 0: sk_gap      relu(y0*s+h) + relu(y1*s+h)        (y has 2f channels)       * 1/HW
+// MODE 1: sk_bwd_gate dv * (u0 - u1)                                                * 1
+// MODE 2: se_gap      y*s+h                                                          * 1/HW
+// MODE 3: se_bwd_gate g * (y*s+h)                                                    * 1
+// MODE 4: gap         x                                 (bf16 output)                * 1/HW
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kT)
+image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
+                    const float* __restrict__ scale, const float* __restrict__ shift, void* out,
+                    int HW, int f) {
+  // f = number of OUTPUT channels; MODE 0/1 read y with 2f channels.
+  __shared__ float red[kT][9];
+  const int CG = f >> 3;
+  const int cgs_per_block = CG < kT ? CG : kT;   // CG <= 256 by construction
+  const int RPB = kT / cgs_per_block;
+  const int cg = threadIdx.x % cgs_per_block;
+  const int rsub = threadIdx.x / cgs_per_block;
+  const int b = blockIdx.x;
+  const int c0 = cg << 3;
+  const int ldy = (MODE <= 1) ? 2 * f : f;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  float s0[8], h0[8], s1[8], h1[8];
+  if (MODE <= 3) {
+    loadf8(scale + c0, s0);
+    loadf8(shift + c0, h0);
+    if (MODE <= 1) {
+      loadf8(scale + f + c0, s1);
+      loadf8(shift + f + c0, h1);
+    }
+  }
+  for (int r = rsub; r < HW; r += RPB) {
+    const int64_t row = (int64_t)b * HW + r;
+    if (MODE == 0 || MODE == 1) {
+      float y0[8], y1[8];
+      load8(p0 + row * ldy + c0, y0);
+      load8(p0 + row * ldy + f + c0, y1);
+      float dv[8];
+      if (MODE == 1) load8(p1 + row * f + c0, dv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
+        const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
+        acc[i] += (MODE == 0) ? (u0 + u1) : dv[i] * (u0 - u1);
+      }
+    } else if (MODE == 2 || MODE == 3) {
+      float yv[8], gv[8];
+      load8(p0 + row * ldy + c0, yv);
+      if (MODE == 3) load8(p1 + row * f + c0, gv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(yv[i], s0[i], h0[i]);
+        acc[i] += (MODE == 2) ? t : gv[i] * t;
+      }
+    } else {
+      float xv[8];
+      load8(p0 + row * ldy + c0, xv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += xv[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (rsub == 0) {
+    for (int r = 1; r < RPB; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += red[r * cgs_per_block + cg][i];
+    const float norm = (MODE == 0 || MODE == 2 || MODE == 4) ? 1.f / HW : 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= norm;
+    if (MODE == 4)
+      store8(reinterpret_cast<bf16*>(out) + (int64_t)b * f + c0, acc);
+    else
+      storef8(reinterpret_cast<float*>(out) + (int64_t)b * f + c0, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SK elementwise
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const float* __restrict__ att,
+                  bf16* __restrict__ v, int HW, int f, int64_t nvec) {
+  const int CG = f >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t row = i / CG;
+    const int64_t b = row / HW;
+    const int c0 = cg << 3;
+    float y0[8], y1[8], s0[8], h0[8], s1[8], h1[8], a[8], o[8];
+    load8(y + row * 2 * f + c0, y0);
+    load8(y + row * 2 * f + f + c0, y1);
+    loadf8(scale + c0, s0);
+    loadf8(shift + c0, h0);
+    loadf8(scale + f + c0, s1);
+    loadf8(shift + f + c0, h1);
+    loadf8(att + b * f + c0, a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
+      const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
+      o[k] = a[k] * u0 + (1.f - a[k]) * u1;
+    }
+    store8(v + row * f + c0, o);
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ att, const float* __restrict__ ds, float* sums,
+                        int64_t M, int HW, int f) {
+  const int CG = f >> 3;
+  const int RPB = kT / CG;
+  const int cg = threadIdx.x % CG;
+  const int rsub = threadIdx.x / CG;
+  const int c0 = cg << 3;
+  float s0[8], h0[8], s1[8], h1[8], m0[8], r0[8], m1[8], r1[8];
+  loadf8(scale + c0, s0);
+  loadf8(shift + c0, h0);
+  loadf8(scale + f + c0, s1);
+  loadf8(shift + f + c0, h1);
+  loadf8(mean + c0, m0);
+  loadf8(rstd + c0, r0);
+  loadf8(mean + f + c0, m1);
+  loadf8(rstd + f + c0, r1);
+  const float inv_hw = 1.f / HW;
+  float acc[4][8];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
+  for (int64_t r = (int64_t)blockIdx.x * RPB + rsub; r < M; r += (int64_t)gridDim.x * RPB) {
+    const int64_t b = r / HW;
+    float y0[8], y1[8], d[8], a[8], sgrad[8];
+    load8(y + r * 2 * f + c0, y0);
+    load8(y + r * 2 * f + f + c0, y1);
+    load8(dv + r * f + c0, d);
+    loadf8(att + b * f + c0, a);
+    loadf8(ds + b * f + c0, sgrad);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t0 = fmaf(y0[i], s0[i], h0[i]);
+      const float t1 = fmaf(y1[i], s1[i], h1[i]);
+      const float g0 = t0 > 0.f ? fmaf(a[i], d[i], sgrad[i] * inv_hw) : 0.f;
+      const float g1 = t1 > 0.f ? fmaf(1.f - a[i], d[i], sgrad[i] * inv_hw) : 0.f;
+      acc[0][i] += g0;
+      acc[1][i] += g1;
+      acc[2][i] += g0 * ((y0[i] - m0[i]) * r0[i]);
+      acc[3][i] += g1 * ((y1[i] - m1[i]) * r1[i]);
+    }
+  }
+  // acc 0/1: sum g (halves 0/1); acc 2/3: sum g*xhat.  sums layout [S1: 2f][S2: 2f]
+  block_reduce_atomic<4>(acc, CG, sums,
+                         [f](int a, int c) { return (a >> 1) * 2 * f + (a & 1) * f + c; });
+}
+
+__global__ void __launch_bounds__(kT)
+sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
+                       const float* __restrict__ scale, const float* __restrict__ shift,
+                       const float* __restrict__ att, const float* __restrict__ ds,
+                       const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f,
+                       int64_t nvec) {
+  const int CG = f >> 3;
+  const int C2 = 2 * f;
+  const float inv_hw = 1.f / HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t row = i / CG;
+    const int64_t b = row / HW;
+    const int c0 = cg << 3;
+    float y0[8], y1[8], d[8], a[8], sgrad[8];
+    load8(y + row * C2 + c0, y0);
+    load8(y + row * C2 + f + c0, y1);
+    load8(dv + row * f + c0, d);
+    loadf8(att + b * f + c0, a);
+    loadf8(ds + b * f + c0, sgrad);
+    float s0[8], h0[8], s1[8], h1[8];
+    loadf8(scale + c0, s0);
+    loadf8(shift + c0, h0);
+    loadf8(scale + f + c0, s1);
+    loadf8(shift + f + c0, h1);
+    float k1a[8], k2a[8], k3a[8], k1b[8], k2b[8], k3b[8];
+    loadf8(coef + c0, k1a);
+    loadf8(coef + C2 + c0, k2a);
+    loadf8(coef + 2 * C2 + c0, k3a);
+    loadf8(coef + f + c0, k1b);
+    loadf8(coef + C2 + f + c0, k2b);
+    loadf8(coef + 2 * C2 + f + c0, k3b);
+    float o0[8], o1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t0 = fmaf(y0[k], s0[k], h0[k]);
+      const float t1 = fmaf(y1[k], s1[k], h1[k]);
+      const float g0 = t0 > 0.f ? fmaf(a[k], d[k], sgrad[k] * inv_hw) : 0.f;
+      const float g1 = t1 > 0.f ? fmaf(1.f - a[k], d[k], sgrad[k] * inv_hw) : 0.f;
+      o0[k] = fmaf(k1a[k], g0, fmaf(k2a[k], y0[k], k3a[k]));
+      o1[k] = fmaf(k1b[k], g1, fmaf(k2b[k], y1[k], k3b[k]));
+    }
+    store8(dy + row * C2 + c0, o0);
+    store8(dy + row * C2 + f + c0, o1);
+  }
+}
+
+static bool cg_ok(int C) {
+  const int cg = C >> 3;
+  return C % 8 == 0 && cg >= 1 && cg <= kT && (kT % cg) == 0;
+}
+
+}  // namespace acnn
+
+using namespace acnn;
+
+extern "C" {
+
+int acnn_bn_finalize(const float* sum, const float* sumsq, int64_t count, const float* gamma,
+                     const float* beta, float* moving_mean, float* moving_var, float momentum,
+                     float eps, int training, float* scale, float* shift, float* mean, float* rstd,
+                     int C, void* stream) {
+  ACNN_REQUIRE(C > 0 && gamma && beta && moving_mean && moving_var && scale && shift && mean &&
+                   rstd, "bn_finalize: null argument");
+  ACNN_REQUIRE(!training || (sum && sumsq && count > 0), "bn_finalize: training needs sums");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      sum, sumsq, (float)count, gamma, beta, moving_mean, moving_var, momentum, eps, training,
+      scale, shift, mean, rstd, C);
+  count_launch();
+  return check_launch("bn_finalize");
+}
+
+int acnn_bn_act(const void* a, const float* scale_a, const float* shift_a, const void* b,
+                const float* scale_b, const float* shift_b, int b_mode, const float* gate, int relu,
+                void* out, int B, int H, int W, int C, void* stream) {
+  ACNN_REQUIRE(a && scale_a && shift_a && out && C % 8 == 0, "bn_act: bad arguments (C=%d)", C);
+  ACNN_REQUIRE(b_mode >= 0 && b_mode <= 3 && (b_mode == 0 || b), "bn_act: bad b_mode %d", b_mode);
+  ACNN_REQUIRE(b_mode != 1 || (scale_b && shift_b), "bn_act: b_mode 1 needs scale_b/shift_b");
+  ACNN_REQUIRE(b_mode != 3 || (H % 2 == 0 && W % 2 == 0), "bn_act: upsample needs even H, W");
+  const int64_t nvec = (int64_t)B * H * W * C / 8;
+  bn_act_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
+      (bf16*)out, H, W, C, nvec);
+  count_launch();
+  return check_launch("bn_act");
+}
+
+int acnn_bn_bwd_reduce(const void* g, const void* y, const float* mean, const float* rstd,
+                       const float* gate, const float* addbc, float* sums, int B, int HW, int C,
+                       void* stream) {
+  ACNN_REQUIRE(g && y && mean && rstd && sums && cg_ok(C), "bn_bwd_reduce: bad arguments C=%d", C);
+  const int64_t M = (int64_t)B * HW;
+  const int rpb = kT / (C >> 3);
+  bn_bwd_reduce_kernel<<<grid_for(ceil_div64(M, rpb), 1, 148 * 4), kT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)g, (const bf16*)y, mean, rstd, gate, addbc, sums, M, HW, C);
+  count_launch();
+  return check_launch("bn_bwd_reduce");
+}
+
+int acnn_bn_bwd_finalize(const float* sums, const float* gamma, const float* mean,
+                         const float* rstd, int64_t count, float* coef, float* dgamma, float* dbeta,
+                         int C, void* stream) {
+  ACNN_REQUIRE(sums && gamma && mean && rstd && coef && dgamma && dbeta && count > 0,
+               "bn_bwd_finalize: null argument");
+  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      sums, gamma, mean, rstd, (float)count, coef, dgamma, dbeta, C);
+  count_launch();
+  return check_launch("bn_bwd_finalize");
+}
+
+int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const float* gate,
+                      const float* addbc, void* dy, int B, int HW, int C, void* stream) {
+  ACNN_REQUIRE(g && y && coef && dy && C % 8 == 0, "bn_bwd_apply: bad arguments");
+  const int64_t nvec = (int64_t)B * HW * C / 8;
+  bn_bwd_apply_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)g, (const bf16*)y, coef, gate, addbc, (bf16*)dy, HW, C, nvec);
+  count_launch();
+  return check_launch("bn_bwd_apply");
+}
+
+int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s, int B, int HW,
+                int f, void* stream) {
+  ACNN_REQUIRE(y && scale && shift && s && cg_ok(f), "sk_gap: bad arguments f=%d", f);
+  image_reduce_kernel<0><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
+                                                             s, HW, f);
+  count_launch();
+  return check_launch("sk_gap");
+}
+
+int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const float* shift,
+                     float* dA, int B, int HW, int f, void* stream) {
+  ACNN_REQUIRE(dv && y && scale && shift && dA && cg_ok(f), "sk_bwd_gate: bad arguments");
+  image_reduce_kernel<1><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)dv,
+                                                             scale, shift, dA, HW, f);
+  count_launch();
+  return check_launch("sk_bwd_gate");
+}
+
+int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q, int B, int HW,
+                int C, void* stream) {
+  ACNN_REQUIRE(y && scale && shift && q && cg_ok(C), "se_gap: bad arguments");
+  image_reduce_kernel<2><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
+                                                             q, HW, C);
+  count_launch();
+  return check_launch("se_gap");
+}
+
+int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const float* shift,
+                     float* de, int B, int HW, int C, void* stream) {
+  ACNN_REQUIRE(g && y && scale && shift && de && cg_ok(C), "se_bwd_gate: bad arguments");
+  image_reduce_kernel<3><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)g, scale,
+                                                             shift, de, HW, C);
+  count_launch();
+  return check_launch("se_bwd_gate");
+}
+
+int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, void* stream) {
+  ACNN_REQUIRE(x && pooled && cg_ok(C), "gap_fwd: bad arguments C=%d", C);
+  image_reduce_kernel<4><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)x, nullptr, nullptr,
+                                                             nullptr, pooled, HW, C);
+  count_launch();
+  return check_launch("gap_fwd");
+}
+
+int acnn_sk_combine(const void* y, const float* scale, const float* shift, const float* att,
+                    void* v, int B, int HW, int f, void* stream) {
+  ACNN_REQUIRE(y && scale && shift && att && v && f % 8 == 0, "sk_combine: bad arguments");
+  const int64_t nvec = (int64_t)B * HW * f / 8;
+  sk_combine_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, scale, shift, att, (bf16*)v, HW, f, nvec);
+  count_launch();
+  return check_launch("sk_combine");
+}
+
+int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, const float* att, const float* ds,
+                          float* sums, int B, int HW, int f, void* stream) {
+  ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && sums && cg_ok(f),
+               "sk_bn_bwd_reduce: bad arguments");
+  const int64_t M = (int64_t)B * HW;
+  const int rpb = kT / (f >> 3);
+  sk_bn_bwd_reduce_kernel<<<grid_for(ceil_div64(M, rpb), 1, 148 * 4), kT, 0,
+                            (cudaStream_t)stream>>>((const bf16*)dv, (const bf16*)y, scale, shift,
+                                                    mean, rstd, att, ds, sums, M, HW, f);
+  count_launch();
+  return check_launch("sk_bn_bwd_reduce");
+}
+
+int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, const float* shift,
+                         const float* att, const float* ds, const float* coef, void* dy, int B,
+                         int HW, int f, void* stream) {
+  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && f % 8 == 0,
+               "sk_bn_bwd_apply: bad arguments");
+  const int64_t nvec = (int64_t)B * HW * f / 8;
+  sk_bn_bwd_apply_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f, nvec);
+  count_launch();
+  return check_launch("sk_bn_bwd_apply");
+}
+
+}  // extern "C"

@@ -1,0 +1,636 @@
+// Pooling / resampling, input packing + mixup, and the softmax cross-entropy loss.
+// All activations NHWC bf16, one thread per (pixel, 8-channel group), 16-byte accesses.
+// Reference: nets/blocks.py:45-107 (blur-pool), nets/resnet_model.py:123-141,421-424,499,560-561,
+// utils/data_util.py:97-158 (mixup), losses/cls_losses.py:28-33.
+#include "common.h"
+#include "vec.cuh"
+
+namespace acnn {
+
+constexpr int kPT = 256;
+
+struct Binomial {
+  float w[7];
+};
+
+static Binomial binomial(int filt) {
+  static const float rows[7][7] = {{1}, {1, 1}, {1, 2, 1}, {1, 3, 3, 1}, {1, 4, 6, 4, 1},
+                                   {1, 5, 10, 10, 5, 1}, {1, 6, 15, 20, 15, 6, 1}};
+  Binomial b;
+  float s = 0;
+  for (int i = 0; i < filt; ++i) s += rows[filt - 1][i];
+  for (int i = 0; i < 7; ++i) b.w[i] = i < filt ? rows[filt - 1][i] / s : 0.f;
+  return b;
+}
+
+__device__ __forceinline__ int reflect(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+// ---------------------------------------------------------------------------- blur-pool
+__global__ void __launch_bounds__(kPT)
+blurpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Binomial bw, int H, int W,
+                    int C, int filt, int stride, int pad, int Ho, int Wo, int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int q = (int)(t % Wo);
+    t /= Wo;
+    const int p = (int)(t % Ho);
+    const int64_t b = t / Ho;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int r = 0; r < filt; ++r) {
+      const int ih = reflect(p * stride + r - pad, H);
+      for (int s = 0; s < filt; ++s) {
+        const int iw = reflect(q * stride + s - pad, W);
+        float v[8];
+        load8(x + ((b * H + ih) * W + iw) * C + cg * 8, v);
+        const float wt = bw.w[r] * bw.w[s];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+      }
+    }
+    store8(out + i * 8, acc);
+  }
+}
+
+// 1-D adjoint weight: sum over padded positions ip that reflect onto i, and over output positions p
+// whose window covers ip.  Calls f(p, weight).
+template <class F>
+__device__ __forceinline__ void blur_adjoint_1d(int i, int n, int no, const Binomial& bw, int filt,
+                                                int stride, int pad, F f) {
+  int cand[3];
+  int nc = 0;
+  cand[nc++] = i;
+  if (i > 0 && i <= pad) cand[nc++] = -i;
+  if (i < n - 1 && (n - 1 - i) <= pad) cand[nc++] = 2 * (n - 1) - i;
+  for (int k = 0; k < nc; ++k) {
+    const int ip = cand[k] + pad;   // coordinate in the padded frame
+    // p*stride <= ip < p*stride + filt
+    int p_hi = ip / stride;
+    if (p_hi > no - 1) p_hi = no - 1;
+    for (int p = p_hi; p >= 0 && ip - p * stride < filt; --p) f(p, bw.w[ip - p * stride]);
+  }
+}
+
+__global__ void __launch_bounds__(kPT)
+blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
+                    const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src,
+                    Binomial bw, int H, int W, int C, int filt, int stride, int pad, int Ho, int Wo,
+                    int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int iw = (int)(t % W);
+    t /= W;
+    const int ih = (int)(t % H);
+    const int64_t b = t / H;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    blur_adjoint_1d(ih, H, Ho, bw, filt, stride, pad, [&](int p, float wr) {
+      blur_adjoint_1d(iw, W, Wo, bw, filt, stride, pad, [&](int q, float ws) {
+        float v[8];
+        load8(dout + ((b * Ho + p) * Wo + q) * C + cg * 8, v);
+        const float wt = wr * ws;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+      });
+    });
+    grad_epilogue(acc, add_src, mask_src, (size_t)i * 8);
+    store8(dx + i * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------- avg / max pool
+__global__ void __launch_bounds__(kPT)
+avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
+                   int stride, int pad, int Ho, int Wo, int count_pad, int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int q = (int)(t % Wo);
+    t /= Wo;
+    const int p = (int)(t % Ho);
+    const int64_t b = t / Ho;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    int cnt = 0;
+    for (int r = 0; r < k; ++r) {
+      const int ih = p * stride + r - pad;
+      if (ih < 0 || ih >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int iw = q * stride + s - pad;
+        if (iw < 0 || iw >= W) continue;
+        float v[8];
+        load8(x + ((b * H + ih) * W + iw) * C + cg * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        ++cnt;
+      }
+    }
+    const float inv = 1.f / (count_pad ? k * k : cnt);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    store8(out + i * 8, acc);
+  }
+}
+
+__device__ __forceinline__ int window_count(int p, int stride, int pad, int k, int n) {
+  int lo = p * stride - pad, hi = lo + k;
+  if (lo < 0) lo = 0;
+  if (hi > n) hi = n;
+  return hi - lo;
+}
+
+__global__ void __launch_bounds__(kPT)
+avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
+                   const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H, int W,
+                   int C, int k, int stride, int pad, int Ho, int Wo, int count_pad, int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int iw = (int)(t % W);
+    t /= W;
+    const int ih = (int)(t % H);
+    const int64_t b = t / H;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    int p_hi = (ih + pad) / stride;
+    if (p_hi > Ho - 1) p_hi = Ho - 1;
+    int q_hi = (iw + pad) / stride;
+    if (q_hi > Wo - 1) q_hi = Wo - 1;
+    for (int p = p_hi; p >= 0 && ih + pad - p * stride < k; --p) {
+      for (int q = q_hi; q >= 0 && iw + pad - q * stride < k; --q) {
+        float v[8];
+        load8(dout + ((b * Ho + p) * Wo + q) * C + cg * 8, v);
+        const float inv = count_pad ? 1.f / (k * k)
+                                    : 1.f / (window_count(p, stride, pad, k, H) *
+                                             window_count(q, stride, pad, k, W));
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(inv, v[e], acc[e]);
+      }
+    }
+    grad_epilogue(acc, add_src, mask_src, (size_t)i * 8);
+    store8(dx + i * 8, acc);
+  }
+}
+
+__global__ void __launch_bounds__(kPT)
+maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
+                   int stride, int pad, int Ho, int Wo, int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int q = (int)(t % Wo);
+    t /= Wo;
+    const int p = (int)(t % Ho);
+    const int64_t b = t / Ho;
+    float m[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m[e] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      const int ih = p * stride + r - pad;
+      if (ih < 0 || ih >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int iw = q * stride + s - pad;
+        if (iw < 0 || iw >= W) continue;
+        float v[8];
+        load8(x + ((b * H + ih) * W + iw) * C + cg * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], v[e]);
+      }
+    }
+    store8(out + i * 8, m);
+  }
+}
+
+__global__ void __launch_bounds__(kPT)
+maxpool_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ x,
+                   bf16* __restrict__ dx, const bf16* __restrict__ add_src,
+                   const bf16* __restrict__ mask_src, int H, int W, int C, int k, int stride,
+                   int pad, int Ho, int Wo, int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int iw = (int)(t % W);
+    t /= W;
+    const int ih = (int)(t % H);
+    const int64_t b = t / H;
+    float acc[8], me[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    load8(x + i * 8, me);
+    int p_hi = (ih + pad) / stride;
+    if (p_hi > Ho - 1) p_hi = Ho - 1;
+    int q_hi = (iw + pad) / stride;
+    if (q_hi > Wo - 1) q_hi = Wo - 1;
+    for (int p = p_hi; p >= 0 && ih + pad - p * stride < k; --p) {
+      for (int q = q_hi; q >= 0 && iw + pad - q * stride < k; --q) {
+        // (ih, iw) receives the gradient iff it is the FIRST maximum of window (p, q)
+        bool win[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) win[e] = true;
+        for (int r = 0; r < k; ++r) {
+          const int jh = p * stride + r - pad;
+          if (jh < 0 || jh >= H) continue;
+          for (int s = 0; s < k; ++s) {
+            const int jw = q * stride + s - pad;
+            if (jw < 0 || jw >= W) continue;
+            if (jh == ih && jw == iw) continue;
+            float v[8];
+            load8(x + ((b * H + jh) * W + jw) * C + cg * 8, v);
+            const bool before = (jh < ih) || (jh == ih && jw < iw);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (v[e] > me[e] || (before && v[e] == me[e])) win[e] = false;
+          }
+        }
+        float g[8];
+        load8(dout + ((b * Ho + p) * Wo + q) * C + cg * 8, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (win[e]) acc[e] += g[e];
+      }
+    }
+    grad_epilogue(acc, add_src, mask_src, (size_t)i * 8);
+    store8(dx + i * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------- resampling
+__global__ void __launch_bounds__(kPT)
+upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
+                      const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H,
+                      int W, int C, int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int64_t b = t / H;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[8];
+        load8(dout + ((b * 2 * H + 2 * h + a) * (2 * W) + 2 * w + c) * C + cg * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    grad_epilogue(acc, add_src, mask_src, (size_t)i * 8);
+    store8(dx + i * 8, acc);
+  }
+}
+
+__global__ void __launch_bounds__(kPT)
+zero_insert2x_kernel(const bf16* __restrict__ dy, bf16* __restrict__ out, int Ho, int Wo, int H,
+                     int W, int C, int64_t nvec) {
+  const int CG = C >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    int64_t t = i / CG;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int64_t b = t / H;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+      v = __ldg(reinterpret_cast<const uint4*>(dy + ((b * Ho + (h >> 1)) * Wo + (w >> 1)) * C +
+                                               cg * 8));
+    *reinterpret_cast<uint4*>(out + i * 8) = v;
+  }
+}
+
+__global__ void __launch_bounds__(kPT)
+gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_src,
+               bf16* __restrict__ dx, int HW, int C, int64_t nvec) {
+  const int CG = C >> 3;
+  const float inv = 1.f / HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t b = (i / CG) / HW;
+    float v[8];
+    load8(dpooled + b * C + cg * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= inv;
+    grad_epilogue(v, nullptr, mask_src, (size_t)i * 8);
+    store8(dx + i * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------------------- input packing
+// One thread per output pixel (b, i, j): 2x2 input pixels x 3 channels -> 16 bf16.
+__global__ void __launch_bounds__(kPT)
+pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
+                  const float* __restrict__ lam2, int mode, bf16* __restrict__ out, int Bin, int B,
+                  int H, int W, int64_t npix) {
+  const int H2 = H >> 1, W2 = W >> 1;
+  const int half = Bin >> 1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % W2);
+    int64_t t = i / W2;
+    const int ii = (int)(t % H2);
+    const int b = (int)(t / H2);
+    int b1 = b, b2 = b;
+    float lam = 1.f;
+    if (mode == 1) {
+      b1 = b;
+      b2 = half + b;
+      lam = lam1[b];
+    } else if (mode == 2) {
+      if (b < half) {
+        b1 = b;
+        b2 = half + b;
+        lam = lam1[b];
+      } else {
+        b1 = b - half;
+        b2 = half + (half - 1 - (b - half));
+        lam = lam2[b - half];
+      }
+    }
+    float o[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const size_t off = ((size_t)(2 * ii + dy) * W + (2 * j + dx)) * 3;
+        const float* p1 = img + (size_t)b1 * H * W * 3 + off;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float v = __ldg(p1 + c);
+          if (mode != 0) {
+            const float v2 = __ldg(img + (size_t)b2 * H * W * 3 + off + c);
+            v = lam * v + (1.f - lam) * v2;
+          }
+          o[(dy * 2 + dx) * 4 + c] = v;
+        }
+        o[(dy * 2 + dx) * 4 + 3] = 0.f;
+      }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      lo[e] = o[e];
+      hi[e] = o[8 + e];
+    }
+    store8(out + i * 16, lo);
+    store8(out + i * 16 + 8, hi);
+  }
+}
+
+__global__ void mix_labels_kernel(const int32_t* __restrict__ labels,
+                                  const float* __restrict__ lam1, const float* __restrict__ lam2,
+                                  int mode, float* __restrict__ y, int Bin, int B, int NC) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * NC) return;
+  const int b = (int)(i / NC), c = (int)(i - (int64_t)b * NC);
+  const int half = Bin >> 1;
+  int b1 = b, b2 = b;
+  float lam = 1.f;
+  if (mode == 1) {
+    b2 = half + b;
+    lam = lam1[b];
+  } else if (mode == 2) {
+    if (b < half) {
+      b2 = half + b;
+      lam = lam1[b];
+    } else {
+      b1 = b - half;
+      b2 = half + (half - 1 - (b - half));
+      lam = lam2[b - half];
+    }
+  }
+  const float v1 = labels[b1] == c ? 1.f : 0.f;
+  const float v2 = labels[b2] == c ? 1.f : 0.f;
+  y[i] = mode == 0 ? v1 : lam * v1 + (1.f - lam) * v2;
+}
+
+// ---------------------------------------------------------------------------- loss
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, t) : v + t;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  v = sh[0];
+  for (int w = 1; w < nw; ++w) v = is_max ? fmaxf(v, sh[w]) : v + sh[w];
+  return v;
+}
+
+__global__ void __launch_bounds__(kPT)
+softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y, int B, int NC,
+                  int ld, float ls, float grad_scale, float* loss_acc, bf16* __restrict__ dlogits,
+                  float* dbias) {
+  __shared__ float sh[kPT / 32];
+  const int b = blockIdx.x;
+  const float* lg = logits + (size_t)b * ld;
+  const float* yy = y + (size_t)b * NC;
+  const float unif = ls / NC;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < NC; c += kPT) mx = fmaxf(mx, lg[c]);
+  mx = block_reduce(mx, true, sh);
+  float se = 0.f, sy = 0.f, syl = 0.f;
+  for (int c = threadIdx.x; c < NC; c += kPT) {
+    const float l = lg[c];
+    const float yp = yy[c] * (1.f - ls) + unif;
+    se += expf(l - mx);
+    sy += yp;
+    syl += yp * l;
+  }
+  se = block_reduce(se, false, sh);
+  sy = block_reduce(sy, false, sh);
+  syl = block_reduce(syl, false, sh);
+  const float lse = mx + logf(se);
+  if (threadIdx.x == 0) atomicAdd(loss_acc, (lse * sy - syl) / B);
+  const float gs = grad_scale / B;
+  for (int c = threadIdx.x; c < ld; c += kPT) {
+    float g = 0.f;
+    if (c < NC) {
+      const float yp = yy[c] * (1.f - ls) + unif;
+      g = (expf(lg[c] - lse) * sy - yp) * gs;
+      if (dbias) atomicAdd(dbias + c, g);
+    }
+    dlogits[(size_t)b * ld + c] = __float2bfloat16_rn(g);
+  }
+}
+
+}  // namespace acnn
+
+using namespace acnn;
+
+extern "C" {
+
+int acnn_blurpool_fwd(const void* x, void* out, int B, int H, int W, int C, int filt, int stride,
+                      void* stream) {
+  ACNN_REQUIRE(x && out && C % 8 == 0 && filt >= 1 && filt <= 7 && stride >= 1,
+               "blurpool_fwd: bad arguments");
+  const int pad = (filt - 1) / 2;
+  ACNN_REQUIRE(pad < H && pad < W, "blurpool_fwd: reflect pad %d >= size", pad);
+  const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
+  const int64_t nvec = (int64_t)B * Ho * Wo * C / 8;
+  blurpool_fwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)out, binomial(filt), H, W, C, filt, stride, pad, Ho, Wo, nvec);
+  count_launch();
+  return check_launch("blurpool_fwd");
+}
+
+int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
+                      int H, int W, int C, int filt, int stride, void* stream) {
+  ACNN_REQUIRE(dout && dx && C % 8 == 0 && filt >= 1 && filt <= 7 && stride >= 1,
+               "blurpool_bwd: bad arguments");
+  const int pad = (filt - 1) / 2;
+  const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
+  const int64_t nvec = (int64_t)B * H * W * C / 8;
+  blurpool_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, binomial(filt), H,
+      W, C, filt, stride, pad, Ho, Wo, nvec);
+  count_launch();
+  return check_launch("blurpool_bwd");
+}
+
+int acnn_avgpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
+                     int pad_lo, int Ho, int Wo, int count_pad, void* stream) {
+  ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_fwd: bad arguments");
+  const int64_t nvec = (int64_t)B * Ho * Wo * C / 8;
+  avgpool_fwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad, nvec);
+  count_launch();
+  return check_launch("avgpool_fwd");
+}
+
+int acnn_avgpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
+                     int H, int W, int C, int k, int stride, int pad_lo, int Ho, int Wo,
+                     int count_pad, void* stream) {
+  ACNN_REQUIRE(dout && dx && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_bwd: bad arguments");
+  const int64_t nvec = (int64_t)B * H * W * C / 8;
+  avgpool_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k, stride,
+      pad_lo, Ho, Wo, count_pad, nvec);
+  count_launch();
+  return check_launch("avgpool_bwd");
+}
+
+int acnn_maxpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
+                     int pad_lo, int Ho, int Wo, void* stream) {
+  ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1, "maxpool_fwd: bad arguments");
+  const int64_t nvec = (int64_t)B * Ho * Wo * C / 8;
+  maxpool_fwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, nvec);
+  count_launch();
+  return check_launch("maxpool_fwd");
+}
+
+int acnn_maxpool_bwd(const void* dout, const void* x, void* dx, const void* add_src,
+                     const void* mask_src, int B, int H, int W, int C, int k, int stride,
+                     int pad_lo, int Ho, int Wo, void* stream) {
+  ACNN_REQUIRE(dout && x && dx && C % 8 == 0, "maxpool_bwd: bad arguments");
+  const int64_t nvec = (int64_t)B * H * W * C / 8;
+  maxpool_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dout, (const bf16*)x, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H,
+      W, C, k, stride, pad_lo, Ho, Wo, nvec);
+  count_launch();
+  return check_launch("maxpool_bwd");
+}
+
+int acnn_upsample2x_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src,
+                        int B, int H, int W, int C, void* stream) {
+  ACNN_REQUIRE(dout && dx && C % 8 == 0, "upsample2x_bwd: bad arguments");
+  const int64_t nvec = (int64_t)B * H * W * C / 8;
+  upsample2x_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, nvec);
+  count_launch();
+  return check_launch("upsample2x_bwd");
+}
+
+int acnn_zero_insert2x(const void* dy, void* out, int B, int Ho, int Wo, int H, int W, int C,
+                       void* stream) {
+  ACNN_REQUIRE(dy && out && C % 8 == 0, "zero_insert2x: bad arguments");
+  const int64_t nvec = (int64_t)B * H * W * C / 8;
+  zero_insert2x_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dy, (bf16*)out, Ho, Wo, H, W, C, nvec);
+  count_launch();
+  return check_launch("zero_insert2x");
+}
+
+int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int HW, int C,
+                 void* stream) {
+  ACNN_REQUIRE(dpooled && dx && C % 8 == 0, "gap_bwd: bad arguments");
+  const int64_t nvec = (int64_t)B * HW * C / 8;
+  gap_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dpooled, (const bf16*)mask_src, (bf16*)dx, HW, C, nvec);
+  count_launch();
+  return check_launch("gap_bwd");
+}
+
+int acnn_pack_input(const float* images, const float* lam1, const float* lam2, int mode, void* out,
+                    int Bin, int H, int W, void* stream) {
+  ACNN_REQUIRE(images && out && H % 2 == 0 && W % 2 == 0 && mode >= 0 && mode <= 2,
+               "pack_input: bad arguments");
+  ACNN_REQUIRE(mode == 0 || (lam1 && Bin % 2 == 0), "pack_input: mixup needs lam1 and even batch");
+  ACNN_REQUIRE(mode != 2 || lam2, "pack_input: mixup type 2 needs lam2");
+  const int B = mode == 1 ? Bin / 2 : Bin;
+  const int64_t npix = (int64_t)B * (H / 2) * (W / 2);
+  pack_input_kernel<<<grid_for(npix), kPT, 0, (cudaStream_t)stream>>>(
+      images, lam1, lam2, mode, (bf16*)out, Bin, B, H, W, npix);
+  count_launch();
+  return check_launch("pack_input");
+}
+
+int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2, int mode, float* y,
+                    int Bin, int NC, void* stream) {
+  ACNN_REQUIRE(labels && y && mode >= 0 && mode <= 2, "mix_labels: bad arguments");
+  ACNN_REQUIRE(mode == 0 || (lam1 && Bin % 2 == 0), "mix_labels: mixup needs lam1, even batch");
+  ACNN_REQUIRE(mode != 2 || lam2, "mix_labels: mixup type 2 needs lam2");
+  const int B = mode == 1 ? Bin / 2 : Bin;
+  const int64_t n = (int64_t)B * NC;
+  mix_labels_kernel<<<(int)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      labels, lam1, lam2, mode, y, Bin, B, NC);
+  count_launch();
+  return check_launch("mix_labels");
+}
+
+int acnn_softmax_ce(const float* logits, const float* y, int B, int NC, int ld,
+                    float label_smoothing, float grad_scale, float* loss_acc, void* dlogits,
+                    float* dbias, void* stream) {
+  ACNN_REQUIRE(logits && y && loss_acc && dlogits && NC <= ld && B > 0,
+               "softmax_ce: bad arguments");
+  softmax_ce_kernel<<<B, kPT, 0, (cudaStream_t)stream>>>(logits, y, B, NC, ld, label_smoothing,
+                                                         grad_scale, loss_acc, (bf16*)dlogits,
+                                                         dbias);
+  count_launch();
+  return check_launch("softmax_ce");
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// 16-byte vector helpers for the HBM-bound NHWC bf16 kernels (8 channels per thread).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace acnn {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = pack8(f);
+}
+__device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void storef8(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// Optional gradient epilogue shared by every backward kernel: (+ add_src) then (* (mask_src > 0)).
+__device__ __forceinline__ void grad_epilogue(float (&v)[8], const bf16* add_src,
+                                              const bf16* mask_src, size_t off) {
+  if (add_src) {
+    float a[8];
+    load8(add_src + off, a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += a[i];
+  }
+  if (mask_src) {
+    float m[8];
+    load8(mask_src + off, m);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (!(m[i] > 0.f)) v[i] = 0.f;
+  }
+}
+
+inline int grid_for(int64_t work_items, int threads = 256, int max_blocks = 148 * 16) {
+  int64_t b = (work_items + threads - 1) / threads;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace acnn

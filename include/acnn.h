@@ -67,6 +67,181 @@ int acnn_conv_dgrad(const acnn_conv_geom* g, const void* dy, const void* w_dgrad
  * fp32 atomics; dw must be zeroed (or hold the running sum) by the caller. */
 int acnn_conv_wgrad(const acnn_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Batch normalisation (tf.layers.batch_normalization fused=True, nets/model_helper.py:26-37)
+ * ------------------------------------------------------------------------------------------- */
+/* Training: mean = sum/count, var = sumsq/count - mean^2 (biased), rstd = rsqrt(var + eps);
+ * moving_mean <- m*moving_mean + (1-m)*mean, moving_var likewise with the UNBIASED variance.
+ * Inference (training == 0): statistics are the moving ones, nothing is updated.
+ * Outputs: scale = gamma*rstd, shift = beta - mean*scale, and mean / rstd for the backward. */
+int acnn_bn_finalize(const float* sum, const float* sumsq, int64_t count, const float* gamma,
+                     const float* beta, float* moving_mean, float* moving_var, float momentum,
+                     float eps, int training, float* scale, float* shift, float* mean, float* rstd,
+                     int C, void* stream);
+
+/* out = bf16( relu?( (a*scale_a + shift_a) [* gate[b,c]] + R ) ), all NHWC [B,H,W,C]:
+ *   b_mode 0: R = 0            1: R = b*scale_b + shift_b (projection shortcut BN)
+ *          2: R = b (identity) 3: R = nearest-2x upsample of b[B,H/2,W/2,C] (Big-Little merge,
+ *                                   nets/resnet_model.py:499-501)
+ * Replaces BN-apply + tf.nn.relu + residual add (nets/resnet_model.py:55,72,92-95,414,501) and
+ * the SE multiply (nets/blocks.py:183) when gate != NULL. */
+int acnn_bn_act(const void* a, const float* scale_a, const float* shift_a, const void* b,
+                const float* scale_b, const float* shift_b, int b_mode, const float* gate, int relu,
+                void* out, int B, int H, int W, int C, void* stream);
+
+/* Backward of y -> bn -> (gate) given the gradient g w.r.t. the block output (already
+ * ReLU-masked).  Effective gradient of the BN output: ge = g [* gate[b,c]] [+ addbc[b,c]] (the SE
+ * gate and the SE pooled-descriptor term; both NULL for a plain BN).
+ * sums[0:C] += sum_m ge, sums[C:2C] += sum_m ge*xhat, xhat = (y-mean)*rstd. */
+int acnn_bn_bwd_reduce(const void* g, const void* y, const float* mean, const float* rstd,
+                       const float* gate, const float* addbc, float* sums, int B, int HW, int C,
+                       void* stream);
+/* dgamma = sums[C:2C], dbeta = sums[0:C]; coef[0:C],[C:2C],[2C:3C] = k1,k2,k3 such that
+ * dy = k1*ge + k2*y + k3  (= gamma*rstd*(ge - mean(ge) - xhat*mean(ge*xhat))). */
+int acnn_bn_bwd_finalize(const float* sums, const float* gamma, const float* mean,
+                         const float* rstd, int64_t count, float* coef, float* dgamma, float* dbeta,
+                         int C, void* stream);
+int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const float* gate,
+                      const float* addbc, void* dy, int B, int HW, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Selective-kernel block after its 3x3 conv (nets/blocks.py:128-152).  y = raw conv output
+ * [B,H,W,2f]; u = relu(y*scale+shift) is never materialised.
+ * ------------------------------------------------------------------------------------------- */
+/* s[B,f] (fp32) = mean_HW(u[..., :f] + u[..., f:])                         (blocks.py:128-132) */
+int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s, int B, int HW,
+                int f, void* stream);
+/* zpre = s*W1^T ; z = relu(BN_batch(zpre)) ; a = z*W2^T ; att = sigmoid(a[:, :f] - a[:, f:])
+ * (2-way softmax over the halves, blocks.py:136-151).  w1 [d][f], w2 [2f][d] fp32 (OHWI 1x1).
+ * bnstat[0:d] = mean, [d:2d] = rstd (batch statistics over B; moving stats when !training). */
+int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const float* beta,
+                   float* moving_mean, float* moving_var, float momentum, float eps, int training,
+                   const float* w2, float* zpre, float* bnstat, float* z, float* att,
+                   float* scratch /* >= B*2f floats */, int B, int f, int d, void* stream);
+/* v[B,HW,f] = att*u0 + (1-att)*u1                                           (blocks.py:152) */
+int acnn_sk_combine(const void* y, const float* scale, const float* shift, const float* att,
+                    void* v, int B, int HW, int f, void* stream);
+/* dA[B,f] = sum_HW dv*(u0-u1) */
+int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const float* shift,
+                     float* dA, int B, int HW, int f, void* stream);
+/* Backward of the two fc layers + batch BN: consumes dA, produces ds[B,f] (gradient w.r.t. the
+ * pooled descriptor) and ACCUMULATES dw1[d][f], dw2[2f][d], dgamma[d], dbeta[d]. */
+int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const float* zpre,
+                   const float* bnstat, const float* gamma, const float* s, const float* w1,
+                   const float* w2, float* dw1, float* dw2, float* dgamma, float* dbeta, float* ds,
+                   float* scratch /* >= B*(2f+d) floats */, int B, int f, int d, void* stream);
+/* g_h = (att_h*dv + ds/HW) * [u_h > 0] for both halves; sums as acnn_bn_bwd_reduce over 2f. */
+int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, const float* shift,
+                          const float* mean, const float* rstd, const float* att, const float* ds,
+                          float* sums, int B, int HW, int f, void* stream);
+int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, const float* shift,
+                         const float* att, const float* ds, const float* coef, void* dy, int B,
+                         int HW, int f, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Squeeze-excitation gate (nets/blocks.py:156-184), applied to t = bn(y) before the residual add
+ * ------------------------------------------------------------------------------------------- */
+/* q[B,C] (fp32) = mean_HW(y*scale + shift) */
+int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q, int B, int HW,
+                int C, void* stream);
+/* h = relu(q*W1^T) [B,r]; e = sigmoid(h*W2^T) [B,C];  w1 [r][C], w2 [C][r] fp32. */
+int acnn_se_fc_fwd(const float* q, const float* w1, const float* w2, float* h, float* e, int B,
+                   int C, int r, void* stream);
+/* de[B,C] = sum_HW g*t (t = y*scale+shift, g = masked grad of the block output) */
+int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const float* shift,
+                     float* de, int B, int HW, int C, void* stream);
+/* consumes de; ACCUMULATES dw1, dw2; dq[B,C] = gradient w.r.t. q, pre-divided by HW. */
+int acnn_se_fc_bwd(const float* de, const float* e, const float* h, const float* q,
+                   const float* w1, const float* w2, float* dw1, float* dw2, float* dq,
+                   float* scratch /* >= B*(C+r) floats */, int B, int C, int r, int HW,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Pooling / resampling (all NHWC bf16).  Backward kernels take the same optional epilogue as the
+ * convs: (+ add_src) then (* (mask_src > 0)).
+ * ------------------------------------------------------------------------------------------- */
+/* Anti-alias blur-pool: REFLECT pad (filt-1)/2, binomial filt x filt / sum, stride, VALID
+ * (nets/blocks.py:45-107).  filt in [1,7]. */
+int acnn_blurpool_fwd(const void* x, void* out, int B, int H, int W, int C, int filt, int stride,
+                      void* stream);
+int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
+                      int H, int W, int C, int filt, int stride, void* stream);
+/* Average pool k x k, zero padding pad_lo before (pad after implied by Ho).  count_pad != 0:
+ * divide by k*k (bl shortcut, resnet_model.py:133-138); else by the number of in-bounds cells
+ * (TF SAME, resnet-d stride-1 shortcut :126). */
+int acnn_avgpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
+                     int pad_lo, int Ho, int Wo, int count_pad, void* stream);
+int acnn_avgpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
+                     int H, int W, int C, int k, int stride, int pad_lo, int Ho, int Wo,
+                     int count_pad, void* stream);
+/* Max pool k x k, -inf padding, pad_lo before (TF SAME puts the odd cell after: pad_lo = 0 for
+ * 3x3/s2 on even sizes, resnet_model.py:421-424).  Backward routes to the FIRST maximum. */
+int acnn_maxpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
+                     int pad_lo, int Ho, int Wo, void* stream);
+int acnn_maxpool_bwd(const void* dout, const void* x, void* dx, const void* add_src,
+                     const void* mask_src, int B, int H, int W, int C, int k, int stride,
+                     int pad_lo, int Ho, int Wo, void* stream);
+/* dx[B,H,W,C] = 2x2 block sums of dout[B,2H,2W,C] (backward of UpSampling2D) */
+int acnn_upsample2x_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src,
+                        int B, int H, int W, int C, void* stream);
+/* out[B,H,W,C]: out[2p,2q] = dy[p,q], zeros elsewhere (stride-2 dgrad = zero-insert + stride-1) */
+int acnn_zero_insert2x(const void* dy, void* out, int B, int Ho, int Wo, int H, int W, int C,
+                       void* stream);
+/* pooled[B,C] (bf16) = mean_HW(x)                              (nets/resnet_model.py:560-561) */
+int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, void* stream);
+/* dx = dpooled[b,c]/HW * (mask_src > 0) */
+int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int HW, int C,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input packing / mixup (utils/data_util.py:97-158) and the loss (losses/cls_losses.py:28-33)
+ * ------------------------------------------------------------------------------------------- */
+/* images fp32 NHWC [Bin,H,W,3] -> bf16 space-to-depth(2) [B,H/2,W/2,16]
+ *   (channel = (dy*2+dx)*4 + c, c==3 is zero) so that the stride-2 stem conv becomes a stride-1
+ *   conv with 16 input channels.  mode 0: B = Bin (copy); 1: mixup type 1, B = Bin/2,
+ *   out = lam1*x[:B] + (1-lam1)*x[B:]; 2: mixup type 2, B = Bin, second half uses lam2 and the
+ *   reversed second half. */
+int acnn_pack_input(const float* images, const float* lam1, const float* lam2, int mode, void* out,
+                    int Bin, int H, int W, void* stream);
+/* y[B,NC] (fp32) = (mixed) one-hot labels, same modes. */
+int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2, int mode, float* y,
+                    int Bin, int NC, void* stream);
+/* Softmax cross-entropy with label smoothing, mean over B: loss_acc[0] += loss (caller zeroes).
+ * dlogits (bf16 [B,ld], columns >= NC zeroed) = (softmax - y')/B * grad_scale;
+ * dbias[NC] (fp32) += column sums of the fp32 dlogits.  logits fp32 [B,ld]. */
+int acnn_softmax_ce(const float* logits, const float* y, int B, int NC, int ld,
+                    float label_smoothing, float grad_scale, float* loss_acc, void* dlogits,
+                    float* dbias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Parameters and optimizer (nets/optimizer_setting.py:23-38, run_loop_classification.py:166-179)
+ * ------------------------------------------------------------------------------------------- */
+/* One conv weight tensor of the flat fp32 master buffer. */
+typedef struct acnn_weight_desc {
+  int64_t master_off; /* elements, into the fp32 master buffer ([Cout][taps][Cin]) */
+  int64_t fprop_off;  /* elements, into the bf16 fprop buffer  ([Cout][taps][Cin]) */
+  int64_t dgrad_off;  /* elements, into the bf16 dgrad buffer  ([Cin][taps flipped][Cout]); <0: none */
+  int32_t Cout, taps, Cin;
+  int32_t pad_;
+} acnn_weight_desc;
+/* bf16 operand copies of every conv weight (fprop layout + flipped/transposed dgrad layout).
+ * `descs` is a DEVICE array of n descriptors. */
+int acnn_prep_weights(const float* master, const acnn_weight_desc* descs, int n, void* w_fprop,
+                      void* w_dgrad, void* stream);
+/* Stem: master [Cout][k][k][3] fp32 -> bf16 [Cout][k2][k2][16] for the space-to-depth input
+ * (k2 taps, see acnn_pack_input); and the inverse gather-add for its gradient. */
+int acnn_s2d_weight_pack(const float* w, void* w2, int Cout, int k, int pad, int k2, int pad2,
+                         void* stream);
+int acnn_s2d_wgrad_unpack(const float* dw2, float* dw, int Cout, int k, int pad, int k2, int pad2,
+                          void* stream);
+/* Fused weight decay + momentum SGD over a flat buffer:
+ *   g = grad*hp[3] + (decay ? hp[2]*w : 0);  acc = hp[1]*acc + g;  w -= hp[0]*acc
+ * hp = device float[4] {lr, momentum, weight_decay, grad_scale}; decay_flag: one byte per 256
+ * elements.  l2_acc[0] += sum over decayed elements of w^2/2 (pre-update), times weight_decay. */
+int acnn_sgd_momentum(float* w, const float* grad, float* acc, int64_t n,
+                      const uint8_t* decay_flag, const float* hp, float* l2_acc, void* stream);
+int acnn_fill_zero(void* p, int64_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
