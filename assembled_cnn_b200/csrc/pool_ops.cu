@@ -345,6 +345,18 @@ gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_s
   }
 }
 
+__global__ void __launch_bounds__(kPT)
+grad_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ add_src,
+                    const bf16* __restrict__ mask_src, bf16* __restrict__ out, int64_t nvec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    load8(a + i * 8, v);
+    grad_epilogue(v, add_src, mask_src, (size_t)i * 8);
+    store8(out + i * 8, v);
+  }
+}
+
 // ---------------------------------------------------------------------------- input packing
 // One thread per output pixel (b, i, j): 2x2 input pixels x 3 channels -> 16 bf16.
 __global__ void __launch_bounds__(kPT)
@@ -592,6 +604,15 @@ int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int
       (const bf16*)dpooled, (const bf16*)mask_src, (bf16*)dx, HW, C, nvec);
   count_launch();
   return check_launch("gap_bwd");
+}
+
+int acnn_grad_combine(const void* a, const void* add_src, const void* mask_src, void* out,
+                      int64_t n, void* stream) {
+  ACNN_REQUIRE(a && out && n % 8 == 0, "grad_combine: bad arguments");
+  grad_combine_kernel<<<grid_for(n / 8), kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)a, (const bf16*)add_src, (const bf16*)mask_src, (bf16*)out, n / 8);
+  count_launch();
+  return check_launch("grad_combine");
 }
 
 int acnn_pack_input(const float* images, const float* lam1, const float* lam2, int mode, void* out,

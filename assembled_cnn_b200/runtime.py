@@ -1,0 +1,407 @@
+"""Executes a layer plan on one B200 through the C ABI (libacnn.so).
+
+PyTorch is used only as the device-memory container (`torch.empty(..., device='cuda')`,
+`data_ptr()`), for streams and for CUDA-graph capture; every kernel on the path is ours.  There is
+no CPU path: constructing a Runtime without a CUDA device or without the built library raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .plan import Plan, Geom, Slot
+
+_TORCH_DTYPE = {"bf16": torch.bfloat16, "f32": torch.float32, "i32": torch.int32}
+
+
+class Runtime:
+    def __init__(self, plan: Plan, device="cuda:0", eps: float = 1e-5):
+        if not torch.cuda.is_available():
+            raise _lib.AcnnError("assembled_cnn_b200.Runtime needs a CUDA device (sm_100a); "
+                                 "there is no CPU fallback")
+        self.lib = _lib.load()
+        self.plan = plan
+        self.dev = torch.device(device)
+        torch.cuda.set_device(self.dev)
+        self.eps = eps
+        self.bn_momentum = plan.meta.get("bn_momentum", 0.997)
+        self.training = plan.meta["training"]
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.params = torch.zeros(plan.param_elems, **f32)
+        self.state = torch.zeros(max(plan.state_elems, 1), **f32)
+        self.zero = torch.zeros(max(plan.zero_elems, 1), **f32)
+        self.work = torch.zeros(max(plan.work_elems, 1), **f32)
+        self.w_fprop = torch.zeros(plan.param_elems, dtype=torch.bfloat16, device=self.dev)
+        if self.training:
+            self.grads = torch.zeros(plan.param_elems, **f32)
+            self.momentum = torch.zeros(plan.param_elems, **f32)
+            self.w_dgrad = torch.zeros(max(plan.dgrad_elems, 1), dtype=torch.bfloat16,
+                                       device=self.dev)
+        else:
+            self.grads = self.momentum = self.w_dgrad = None
+        self.hp = torch.tensor([0.1, 0.9, 0.0, 1.0], **f32)     # lr, momentum, wd, grad_scale
+        self.loss_scale = 1.0
+        for p in plan.state.values():
+            if p.kind == "moving_variance":
+                self.state[p.offset:p.offset + p.size] = 1.0
+        # activation / gradient buffers (statically shaped, allocated once)
+        self.t = {}
+        for name, t in plan.tensors.items():
+            self.t[name] = torch.zeros(t.shape, dtype=_TORCH_DTYPE[t.dtype], device=self.dev)
+        # conv weight descriptor table + weight-decay flags
+        descs = []
+        flags = torch.zeros(max(plan.param_elems // 256, 1), dtype=torch.uint8)
+        for p in plan.params.values():
+            if p.decay:
+                flags[p.offset // 256:(p.offset + p.size + 255) // 256] = 1
+            if p.kind in ("conv_kernel", "dense_kernel") and len(p.store_shape) == 4 \
+                    and p.store_shape[3] % 16 == 0 and p.store_shape[0] % 32 == 0:
+                co, kh, kw, ci = p.store_shape
+                descs.append(_lib.WeightDesc(p.offset, p.offset, p.dgrad_off, co, kh * kw, ci, 0))
+        self.decay_flags = flags.to(self.dev)
+        self.n_descs = len(descs)
+        raw = bytes((_lib.WeightDesc * len(descs))(*descs)) if descs else b"\0" * 40
+        self.descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
+        self.graph = None
+        self._geom_cache = {}
+
+    # ---------------------------------------------------------------- pointers
+    @property
+    def stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def P(self, name, buf=None):
+        p = self.plan.params.get(name) or self.plan.state[name]
+        base = buf if buf is not None else (self.params if p.trainable else self.state)
+        return base.data_ptr() + 4 * p.offset
+
+    def G(self, name):
+        return self.grads.data_ptr() + 4 * self.plan.params[name].offset
+
+    def WF(self, name):
+        return self.w_fprop.data_ptr() + 2 * self.plan.params[name].offset
+
+    def WD(self, name):
+        p = self.plan.params[name]
+        assert p.dgrad_off >= 0, name
+        return self.w_dgrad.data_ptr() + 2 * p.dgrad_off
+
+    def S(self, slot: Slot | None, extra=0):
+        if slot is None:
+            return None
+        buf = self.zero if slot.buf == "zero" else self.work
+        return buf.data_ptr() + 4 * (slot.offset + extra)
+
+    def T(self, name):
+        return None if name is None else self.t[name].data_ptr()
+
+    def geom(self, g: Geom):
+        key = g.astuple()
+        cg = self._geom_cache.get(key)
+        if cg is None:
+            cg = self._geom_cache[key] = _lib.ConvGeom(*key)
+        return cg
+
+    def slot_view(self, slot: Slot):
+        buf = self.zero if slot.buf == "zero" else self.work
+        return buf[slot.offset:slot.offset + slot.size]
+
+    def pview(self, name, buf=None):
+        p = self.plan.params.get(name) or self.plan.state[name]
+        base = buf if buf is not None else (self.params if p.trainable else self.state)
+        return base[p.offset:p.offset + p.size].view(p.store_shape)
+
+    # ---------------------------------------------------------------- weights (TF layout)
+    def set_weights(self, tf_vars):
+        """tf_vars: name -> array-like in the reference's layout (HWIO kernels, [in,out] dense)."""
+        for name, p in list(self.plan.params.items()) + list(self.plan.state.items()):
+            v = torch.as_tensor(tf_vars[name]).to(torch.float32)
+            if tuple(v.shape) != tuple(p.tf_shape):
+                raise ValueError("shape of %s: got %s, expected %s" % (name, tuple(v.shape), p.tf_shape))
+            dst = self.pview(name)
+            if p.kind == "conv_kernel":
+                dst.copy_(v.permute(3, 0, 1, 2))
+            elif p.kind == "dense_kernel":
+                dst.zero_()
+                dst[:v.shape[1], 0, 0, :] = v.t()
+            elif p.kind == "dense_bias":
+                dst.zero_()
+                dst[:v.shape[0]] = v
+            else:
+                dst.copy_(v)
+
+    def get_tf(self, name, buf=None):
+        p = self.plan.params.get(name) or self.plan.state[name]
+        v = self.pview(name, buf)
+        if p.kind == "conv_kernel":
+            return v.permute(1, 2, 3, 0)
+        if p.kind == "dense_kernel":
+            return v[:p.tf_shape[1], 0, 0, :].t()
+        if p.kind == "dense_bias":
+            return v[:p.tf_shape[0]]
+        return v
+
+    def set_hparams(self, lr=None, momentum=None, weight_decay=None, grad_scale=None):
+        cur = self.hp.tolist()
+        for i, v in enumerate((lr, momentum, weight_decay, grad_scale)):
+            if v is not None:
+                cur[i] = float(v)
+        self.hp.copy_(torch.tensor(cur, dtype=torch.float32), non_blocking=True)
+
+    # ---------------------------------------------------------------- execution
+    def _chk(self, rc, op):
+        if rc != 0:
+            _lib.check(rc, "op %s" % op.kind)
+
+    def run(self, ops):
+        for op in ops:
+            getattr(self, "op_" + op.kind)(op)
+
+    def zero_step_buffers(self):
+        st = self.stream
+        self.lib.acnn_fill_zero(self.zero.data_ptr(), self.zero.numel() * 4, st)
+        if self.grads is not None:
+            self.lib.acnn_fill_zero(self.grads.data_ptr(), self.grads.numel() * 4, st)
+
+    def run_forward(self):
+        self.zero_step_buffers()
+        self.run(self.plan.forward)
+
+    def run_step(self):
+        """zero -> forward -> backward -> SGD, all enqueued on the current stream."""
+        self.run_forward()
+        self.run(self.plan.backward)
+        self.run(self.plan.update)
+
+    def capture(self, train=True):
+        """Capture one full step (or forward) into a CUDA graph; inputs are read from the static
+        input buffers (plan.meta['images'] ...), hyper-parameters from the device `hp` vector."""
+        fn = self.run_step if train else self.run_forward
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=s):
+                fn()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        return self.graph
+
+    # ---------------------------------------------------------------- forward ops
+    def op_prep_weights(self, op):
+        if self.n_descs:
+            self._chk(self.lib.acnn_prep_weights(
+                self.params.data_ptr(), self.descs.data_ptr(), self.n_descs,
+                self.w_fprop.data_ptr(),
+                self.w_dgrad.data_ptr() if self.w_dgrad is not None else None, self.stream), op)
+
+    def op_pack_input(self, op):
+        self._chk(self.lib.acnn_pack_input(self.T(op.images), self.T(op.lam1), self.T(op.lam2),
+                                           op.mode, self.T(op.out), op.Bin, op.H, op.W,
+                                           self.stream), op)
+
+    def op_mix_labels(self, op):
+        self._chk(self.lib.acnn_mix_labels(self.T(op.labels), self.T(op.lam1), self.T(op.lam2),
+                                           op.mode, self.T(op.y), op.Bin, op.NC, self.stream), op)
+
+    def op_s2d_weight_pack(self, op):
+        self._chk(self.lib.acnn_s2d_weight_pack(self.P(op.w), self.T(op.w2), op.cout, op.k, op.pad,
+                                                op.k2, op.pad2, self.stream), op)
+
+    def op_conv(self, op):
+        w = self.T(op.w) if op.a.get("w_is_tensor") else self.WF(op.w)
+        st = op.stats
+        C_ = op.geom.Cout
+        self._chk(self.lib.acnn_conv_fprop(
+            self.geom(op.geom), self.T(op.x), w, self.T(op.y), self.S(st), self.S(st, C_) if st else None,
+            None, None, self.P(op.bias) if op.bias else None, 1 if op.out_f32 else 0, self.stream), op)
+
+    def op_bn_finalize(self, op):
+        bn = op.bn
+        C_ = bn.C
+        self._chk(self.lib.acnn_bn_finalize(
+            self.S(bn.stats), self.S(bn.stats, C_) if bn.stats else None, bn.count, self.P(bn.gamma),
+            self.P(bn.beta), self.P(bn.mm), self.P(bn.mv), self.bn_momentum, self.eps,
+            1 if self.training else 0, self.S(bn.work), self.S(bn.work, C_), self.S(bn.work, 2 * C_),
+            self.S(bn.work, 3 * C_), C_, self.stream), op)
+
+    def op_bn_act(self, op):
+        B, H, W, C_ = op.shape
+        bna, bnb = op.bn_a, op.bn_b
+        self._chk(self.lib.acnn_bn_act(
+            self.T(op.a["a"]), self.S(bna.work), self.S(bna.work, C_), self.T(op.b),
+            self.S(bnb.work) if bnb else None, self.S(bnb.work, C_) if bnb else None, op.b_mode,
+            self.S(op.gate), 1 if op.relu else 0, self.T(op.out), B, H, W, C_, self.stream), op)
+
+    def op_sk_gap(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_sk_gap(self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C),
+                                       self.S(op.s), op.B, op.HW, op.f, self.stream), op)
+
+    def op_sk_fc(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_sk_fc_fwd(
+            self.S(op.s), self.P(op.w1), self.P(bn.gamma), self.P(bn.beta), self.P(bn.mm),
+            self.P(bn.mv), self.bn_momentum, self.eps, 1 if self.training else 0, self.P(op.w2),
+            self.S(op.zpre), self.S(bn.work), self.S(op.z), self.S(op.att), self.S(op.scratch),
+            op.B, op.f, op.d, self.stream), op)
+
+    def op_sk_combine(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_sk_combine(self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C),
+                                           self.S(op.att), self.T(op.v), op.B, op.HW, op.f,
+                                           self.stream), op)
+
+    def op_se_gap(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_se_gap(self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C),
+                                       self.S(op.q), op.B, op.HW, op.C, self.stream), op)
+
+    def op_se_fc(self, op):
+        self._chk(self.lib.acnn_se_fc_fwd(self.S(op.q), self.P(op.w1), self.P(op.w2), self.S(op.h),
+                                          self.S(op.e), op.B, op.C, op.r, self.stream), op)
+
+    def op_blurpool(self, op):
+        self._chk(self.lib.acnn_blurpool_fwd(self.T(op.x), self.T(op.out), op.B, op.H, op.W, op.C,
+                                             op.filt, op.stride, self.stream), op)
+
+    def op_avgpool(self, op):
+        self._chk(self.lib.acnn_avgpool_fwd(self.T(op.x), self.T(op.out), op.B, op.H, op.W, op.C,
+                                            op.k, op.stride, op.pad_lo, op.Ho, op.Wo, op.count_pad,
+                                            self.stream), op)
+
+    def op_maxpool(self, op):
+        self._chk(self.lib.acnn_maxpool_fwd(self.T(op.x), self.T(op.out), op.B, op.H, op.W, op.C,
+                                            op.k, op.stride, op.pad_lo, op.Ho, op.Wo, self.stream),
+                  op)
+
+    def op_gap(self, op):
+        self._chk(self.lib.acnn_gap_fwd(self.T(op.x), self.T(op.out), op.B, op.HW, op.C,
+                                        self.stream), op)
+
+    def op_softmax_ce(self, op):
+        self._chk(self.lib.acnn_softmax_ce(
+            self.T(op.logits), self.T(op.y), op.B, op.NC, op.ld, op.label_smoothing,
+            self.loss_scale, self.S(op.loss), self.T(op.dlogits),
+            self.G(op.dbias) if (op.dbias and self.grads is not None) else None, self.stream), op)
+
+    # ---------------------------------------------------------------- backward ops
+    def op_conv_wgrad(self, op):
+        slot = op.a.get("dw_slot")
+        dw = self.S(slot) if slot is not None else self.G(op.w)
+        self._chk(self.lib.acnn_conv_wgrad(self.geom(op.geom), self.T(op.x), self.T(op.dy), dw,
+                                           self.stream), op)
+
+    def op_conv_dgrad(self, op):
+        self._chk(self.lib.acnn_conv_dgrad(self.geom(op.geom), self.T(op.dy), self.WD(op.w),
+                                           self.T(op.dx), self.T(op.add_src), self.T(op.mask_src),
+                                           self.stream), op)
+
+    def op_zero_insert(self, op):
+        self._chk(self.lib.acnn_zero_insert2x(self.T(op.dy), self.T(op.out), op.B, op.Ho, op.Wo,
+                                              op.H, op.W, op.C, self.stream), op)
+
+    def op_s2d_wgrad_unpack(self, op):
+        self._chk(self.lib.acnn_s2d_wgrad_unpack(self.S(op.dw2), self.G(op.w), op.cout, op.k,
+                                                 op.pad, op.k2, op.pad2, self.stream), op)
+
+    def op_bn_bwd_reduce(self, op):
+        B, H, W, C_ = op.shape
+        bn = op.bn
+        self._chk(self.lib.acnn_bn_bwd_reduce(
+            self.T(op.g), self.T(op.y), self.S(bn.work, 2 * C_), self.S(bn.work, 3 * C_),
+            self.S(op.gate), self.S(op.addbc), self.S(op.sums), B, H * W, C_, self.stream), op)
+
+    def op_bn_bwd_finalize(self, op):
+        bn = op.bn
+        C_ = op.sums.size // 2
+        self._chk(self.lib.acnn_bn_bwd_finalize(
+            self.S(op.sums), self.P(bn.gamma), self.S(bn.work, 2 * C_), self.S(bn.work, 3 * C_),
+            bn.count, self.S(op.coef), self.G(bn.gamma), self.G(bn.beta), C_, self.stream), op)
+
+    def op_bn_bwd_apply(self, op):
+        B, H, W, C_ = op.shape
+        self._chk(self.lib.acnn_bn_bwd_apply(self.T(op.g), self.T(op.y), self.S(op.coef),
+                                             self.S(op.gate), self.S(op.addbc), self.T(op.dy), B,
+                                             H * W, C_, self.stream), op)
+
+    def op_sk_bwd_gate(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_sk_bwd_gate(self.T(op.dv), self.T(op.y), self.S(bn.work),
+                                            self.S(bn.work, bn.C), self.S(op.dA), op.B, op.HW,
+                                            op.f, self.stream), op)
+
+    def op_sk_fc_bwd(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_sk_fc_bwd(
+            self.S(op.dA), self.S(op.att), self.S(op.z), self.S(op.zpre), self.S(bn.work),
+            self.P(bn.gamma), self.S(op.s), self.P(op.w1), self.P(op.w2), self.G(op.w1),
+            self.G(op.w2), self.G(bn.gamma), self.G(bn.beta), self.S(op.ds), self.S(op.scratch),
+            op.B, op.f, op.d, self.stream), op)
+
+    def op_sk_bn_bwd_reduce(self, op):
+        bn = op.bn
+        C_ = bn.C
+        self._chk(self.lib.acnn_sk_bn_bwd_reduce(
+            self.T(op.dv), self.T(op.y), self.S(bn.work), self.S(bn.work, C_),
+            self.S(bn.work, 2 * C_), self.S(bn.work, 3 * C_), self.S(op.att), self.S(op.ds),
+            self.S(op.sums), op.B, op.HW, op.f, self.stream), op)
+
+    def op_sk_bn_bwd_apply(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_sk_bn_bwd_apply(
+            self.T(op.dv), self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C), self.S(op.att),
+            self.S(op.ds), self.S(op.coef), self.T(op.dy), op.B, op.HW, op.f, self.stream), op)
+
+    def op_se_bwd_gate(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_se_bwd_gate(self.T(op.g), self.T(op.y), self.S(bn.work),
+                                            self.S(bn.work, bn.C), self.S(op.de), op.B, op.HW,
+                                            op.C, self.stream), op)
+
+    def op_se_fc_bwd(self, op):
+        self._chk(self.lib.acnn_se_fc_bwd(
+            self.S(op.de), self.S(op.e), self.S(op.h), self.S(op.q), self.P(op.w1), self.P(op.w2),
+            self.G(op.w1), self.G(op.w2), self.S(op.dq), self.S(op.scratch), op.B, op.C, op.r,
+            op.HW, self.stream), op)
+
+    def op_blurpool_bwd(self, op):
+        self._chk(self.lib.acnn_blurpool_bwd(self.T(op.dout), self.T(op.dx), self.T(op.add_src),
+                                             self.T(op.mask_src), op.B, op.H, op.W, op.C, op.filt,
+                                             op.stride, self.stream), op)
+
+    def op_avgpool_bwd(self, op):
+        self._chk(self.lib.acnn_avgpool_bwd(self.T(op.dout), self.T(op.dx), self.T(op.add_src),
+                                            self.T(op.mask_src), op.B, op.H, op.W, op.C, op.k,
+                                            op.stride, op.pad_lo, op.Ho, op.Wo, op.count_pad,
+                                            self.stream), op)
+
+    def op_maxpool_bwd(self, op):
+        self._chk(self.lib.acnn_maxpool_bwd(self.T(op.dout), self.T(op.x), self.T(op.dx),
+                                            self.T(op.add_src), self.T(op.mask_src), op.B, op.H,
+                                            op.W, op.C, op.k, op.stride, op.pad_lo, op.Ho, op.Wo,
+                                            self.stream), op)
+
+    def op_upsample2x_bwd(self, op):
+        self._chk(self.lib.acnn_upsample2x_bwd(self.T(op.dout), self.T(op.dx), self.T(op.add_src),
+                                               self.T(op.mask_src), op.B, op.H, op.W, op.C,
+                                               self.stream), op)
+
+    def op_gap_bwd(self, op):
+        self._chk(self.lib.acnn_gap_bwd(self.T(op.dpooled), self.T(op.mask_src), self.T(op.dx),
+                                        op.B, op.HW, op.C, self.stream), op)
+
+    def op_grad_combine(self, op):
+        n = 1
+        for s in op.shape:
+            n *= s
+        self._chk(self.lib.acnn_grad_combine(self.T(op.a["a"]), self.T(op.add_src),
+                                             self.T(op.mask_src), self.T(op.out), n, self.stream),
+                  op)
+
+    def op_sgd(self, op):
+        self._chk(self.lib.acnn_sgd_momentum(
+            self.params.data_ptr(), self.grads.data_ptr(), self.momentum.data_ptr(),
+            self.plan.param_elems, self.decay_flags.data_ptr(), self.hp.data_ptr(),
+            self.S(op.loss, 1), self.stream), op)

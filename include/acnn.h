@@ -187,6 +187,10 @@ int acnn_upsample2x_bwd(const void* dout, void* dx, const void* add_src, const v
 /* out[B,H,W,C]: out[2p,2q] = dy[p,q], zeros elsewhere (stride-2 dgrad = zero-insert + stride-1) */
 int acnn_zero_insert2x(const void* dy, void* out, int B, int Ho, int Wo, int H, int W, int C,
                        void* stream);
+/* out = (a [+ add_src]) [* (mask_src > 0)] over n bf16 elements: gradient merge when no consumer
+ * kernel can fuse it (identity shortcut as last contribution). */
+int acnn_grad_combine(const void* a, const void* add_src, const void* mask_src, void* out,
+                      int64_t n, void* stream);
 /* pooled[B,C] (bf16) = mean_HW(x)                              (nets/resnet_model.py:560-561) */
 int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, void* stream);
 /* dx = dpooled[b,c]/HW * (mask_src > 0) */
