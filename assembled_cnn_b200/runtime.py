@@ -17,7 +17,7 @@ _TORCH_DTYPE = {"bf16": torch.bfloat16, "f32": torch.float32, "i32": torch.int32
 
 
 class Runtime:
-    def __init__(self, plan: Plan, device="cuda:0", eps: float = 1e-5):
+    def __init__(self, plan: Plan, device="cuda:0", eps: float = 1e-5, share: "Runtime | None" = None):
         if not torch.cuda.is_available():
             raise _lib.AcnnError("assembled_cnn_b200.Runtime needs a CUDA device (sm_100a); "
                                  "there is no CPU fallback")
@@ -29,23 +29,33 @@ class Runtime:
         self.bn_momentum = plan.meta.get("bn_momentum", 0.997)
         self.training = plan.meta["training"]
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.params = torch.zeros(plan.param_elems, **f32)
-        self.state = torch.zeros(max(plan.state_elems, 1), **f32)
+        if share is not None:
+            # same model, another batch shape / mode: the variables are shared, not copied
+            if share.plan.param_elems != plan.param_elems or share.plan.state_elems != plan.state_elems:
+                raise ValueError("Runtime(share=...): parameter layouts differ")
+            self.params, self.state, self.w_fprop = share.params, share.state, share.w_fprop
+        else:
+            self.params = torch.zeros(plan.param_elems, **f32)
+            self.state = torch.zeros(max(plan.state_elems, 1), **f32)
+            self.w_fprop = torch.zeros(plan.param_elems, dtype=torch.bfloat16, device=self.dev)
         self.zero = torch.zeros(max(plan.zero_elems, 1), **f32)
         self.work = torch.zeros(max(plan.work_elems, 1), **f32)
-        self.w_fprop = torch.zeros(plan.param_elems, dtype=torch.bfloat16, device=self.dev)
         if self.training:
             self.grads = torch.zeros(plan.param_elems, **f32)
-            self.momentum = torch.zeros(plan.param_elems, **f32)
+            if share is not None and share.momentum is not None:
+                self.momentum = share.momentum
+            else:
+                self.momentum = torch.zeros(plan.param_elems, **f32)
             self.w_dgrad = torch.zeros(max(plan.dgrad_elems, 1), dtype=torch.bfloat16,
                                        device=self.dev)
         else:
             self.grads = self.momentum = self.w_dgrad = None
         self.hp = torch.tensor([0.1, 0.9, 0.0, 1.0], **f32)     # lr, momentum, wd, grad_scale
         self.loss_scale = 1.0
-        for p in plan.state.values():
-            if p.kind == "moving_variance":
-                self.state[p.offset:p.offset + p.size] = 1.0
+        if share is None:
+            for p in plan.state.values():
+                if p.kind == "moving_variance":
+                    self.state[p.offset:p.offset + p.size] = 1.0
         # activation / gradient buffers (statically shaped, allocated once)
         self.t = {}
         for name, t in plan.tensors.items():

@@ -7,7 +7,10 @@ Tolerances (relative to the output's max magnitude): bf16 tensors 2^-7 (one bf16
 of the range: accumulation-order differences can flip a rounding), fp32 vectors 2e-3 where sums
 of bf16 data cancel (BN backward sums), 1e-4 otherwise.
 """
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import pytest
 import torch
