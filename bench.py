@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the assembled-ResNet training step on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on host cores
+
+One JSON line on stdout (rank 0).  A "step" = one full training step of Assemble-ResNet-50
+(resnet_version=2, SK, anti-alias sconv/3) on one synthetic batch: mixup type 1 -> forward -> label-
+smoothed softmax CE -> backward -> (NCCL all-reduce) -> weight-decay + momentum SGD, 256 images per
+GPU at 224x224x3 (weak scaling).  `value` is timed on the device with inputs resident in HBM;
+`e2e` goes through the public API (Trainer.train_step) from pinned host buffers, with the H2D copy
+of every step's inputs and a D2H read of the loss inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec Assemble-ResNet-50 224^2 bf16 train step"
+MODEL_FLAGS = dict(resnet_size=50, resnet_version=2, use_sk_block=True, anti_alias_type="sconv",
+                   anti_alias_filter_size=3)
+TRAIN_FLAGS = dict(mixup_type=1, label_smoothing=0.1, weight_decay=1e-4, momentum=0.9,
+                   base_learning_rate=0.4, learning_rate_decay_type="cosine", lr_warmup_epochs=5,
+                   train_epochs=600, bn_momentum=0.997)
+PER_GPU_BATCH = 256
+TRAIN_GFLOP_PER_IMG = 34.12      # BASELINE.md section 2 (2*MAC: fwd + dgrad + wgrad)
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return dict(tflops=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], source="measured")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback")   # B200_PROFILING.md fallback
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_batch(n, hw, seed):
+    """images N(0, 64^2) clipped to [-124, 152], labels U{1..1000}."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(n, hw, hw, 3, generator=g) * 64.0).clamp_(-124.0, 152.0)
+    y = torch.randint(1, 1001, (n,), generator=g, dtype=torch.int32)
+    return x, y
+
+
+def cpu_reference(batch, steps, warmup, hw=224):
+    """The reference's TF1 CPU path, restated (oracle/model.py): same step, host cores."""
+    import torch
+    from oracle import model as M, tf_ops as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.set_flush_denormal(True)
+    model, vs = M.build(seed=42, input_hw=64, **MODEL_FLAGS)
+    names = [n for n in vs.vars if vs.trainable[n]]
+    mom = {n: torch.zeros_like(vs.vars[n]) for n in names}
+    x, lab = synth_batch(2 * batch, hw, 1234)
+    onehot = torch.nn.functional.one_hot(lab.long(), 1001).float()
+    g = torch.Generator().manual_seed(7)
+    times = []
+    for i in range(warmup + steps):
+        lam = torch.distributions.Beta(0.2, 0.2).sample((batch,))
+        t0 = time.perf_counter()
+        xm, ym = T.mixup(x, onehot, lam, keep_batch_size=False)
+        M.train_step(model, vs, mom, xm, ym, lr=1e-3, momentum=0.9, label_smoothing=0.1,
+                     weight_decay=1e-4)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return dict(value=batch / sec, unit="images/sec", cores=cores, kind="port",
+                sample="oracle/model.py train step (restatement of the reference TF1 CPU path; "
+                       "TF 1.14 not installable), Assemble-ResNet-50 224x224, batch %d "
+                       "(mixup type 1 from %d inputs), %d timed step(s) after %d warm-up, "
+                       "torch %d threads" % (batch, 2 * batch, steps, warmup, cores)), sec
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 8
+    steps = max(1, min(args.steps, 3))
+    warmup = 1
+    cb, sec = cpu_reference(batch, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "Assemble-ResNet-50 (rv=2, SK, sconv/3) full train step, "
+                               "mixup type 1 + label smoothing 0.1, 224x224, CPU batch %d" % batch,
+                   "note": "reference = torch-CPU restatement of the TF1 path (oracle port)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (256 = BASELINE)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from assembled_cnn_b200 import _lib
+    from assembled_cnn_b200.hparams import params_from_flags
+    from assembled_cnn_b200.model_fns import Model, Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    B = args.batch
+    params = params_from_flags(batch_size=B * world, **MODEL_FLAGS, **TRAIN_FLAGS)
+    model = Model(params["resnet_size"], num_classes=1001, resnet_version=params["resnet_version"],
+                  use_sk_block=True, anti_alias_type="sconv", anti_alias_filter_size=3,
+                  device="cuda:%d" % local)
+    tr = Trainer(model, params, 224, 224, use_cuda_graph=not args.no_graph)
+    n_in = tr.input_batch
+    x_host, y_host = synth_batch(n_in, 224, 1234 + rank)
+    x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
+    dev = torch.device("cuda", local)
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    h2d = x_host.numel() * 4 + y_host.numel() * 4 + (n_in // 2) * 4 + 16
+    d2h = 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # launches of OUR kernels per step (counted on an eager step; graph replays re-issue them)
+    tr_eager_graph = tr.use_graph
+    tr.use_graph = False
+    c0 = lib.acnn_launch_count()
+    tr.train_step(x_dev, y_dev)
+    torch.cuda.synchronize()
+    launches_per_step = lib.acnn_launch_count() - c0
+    tr.use_graph = tr_eager_graph
+
+    # ---- device-resident arm -------------------------------------------------------------
+    dev_step = lambda: tr.train_step(x_dev, y_dev)
+    for _ in range(args.warmup):
+        dev_step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_total = timed(dev_step, args.steps)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = B * world / (ms_step / 1e3)
+
+    # ---- end-to-end arm: pinned host -> H2D -> step -> D2H loss, every step -----------------
+    def e2e_step():
+        loss = tr.train_step(x_host, y_host)
+        return loss.tolist()
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e_value = B * world / (ms_e2e / 1e3)
+    last_loss = e2e_step()
+
+    # ---- roofline of the tcgen05 conv GEMMs, timed live (CUDA events around every launch) ---
+    peaks = read_peaks()
+    roof = None
+    if rank == 0:
+        roof = conv_roofline(tr, x_dev, y_dev, peaks, ms_step)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, _ = cpu_reference(8, 2, 1)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "Assemble-ResNet-50 (resnet_version=2, use_sk_block, "
+                                   "anti_alias sconv/3) full train step: mixup type 1 + label "
+                                   "smoothing 0.1 + wd 1e-4 + momentum SGD, 224x224x3",
+                       "per_gpu_batch": B, "global_batch": B * world, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (activations + gradients, several GB) >> 126 MB L2",
+                       "cuda_graph": tr.use_graph, "loss": last_loss},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "images/sec", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches_per_step * args.steps),
+            "conv_flop_roofline": {"gflop_per_img": TRAIN_GFLOP_PER_IMG,
+                                   "achieved_tflops": TRAIN_GFLOP_PER_IMG * value / 1e3,
+                                   "peak_tflops": peaks["tflops"] * world,
+                                   "frac": TRAIN_GFLOP_PER_IMG * value / 1e3 / (peaks["tflops"] * world),
+                                   "peak_source": peaks["source"] + " bf16_tflops_sustained"},
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def conv_roofline(tr, x_dev, y_dev, peaks, ms_step):
+    """Time every tcgen05 GEMM launch (fprop / dgrad / wgrad) of one eager step with CUDA events
+    on the launching stream; achieved = algorithmic FLOPs of those launches / their summed time."""
+    import torch
+    rt = tr.rt
+    stream = torch.cuda.current_stream()
+    evs = []
+    for name in ("op_conv", "op_conv_dgrad", "op_conv_wgrad"):
+        orig = getattr(rt, name)
+
+        def wrapped(op, orig=orig):
+            g = op.geom
+            flops = 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            orig(op)
+            b.record(stream)
+            evs.append((a, b, flops))
+        setattr(rt, name, wrapped)
+    was = tr.use_graph
+    tr.use_graph = False
+    try:
+        tr.train_step(x_dev, y_dev)          # warm
+        evs.clear()
+        tr.train_step(x_dev, y_dev)
+        torch.cuda.synchronize()
+    finally:
+        tr.use_graph = was
+        for name in ("op_conv", "op_conv_dgrad", "op_conv_wgrad"):
+            delattr(rt, name)
+    t_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
+    fl = sum(f for _, _, f in evs)
+    achieved = fl / (t_ms / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tflops"], "traffic": None,
+            "kernel": "conv_gemm_kernel + wgrad_gemm_kernel (all %d tcgen05 launches of a step)" % len(evs),
+            "launch_ms_sum": t_ms, "share_of_step": t_ms / ms_step,
+            "algorithmic_gflop_per_step": fl / 1e9,
+            "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""Per-op timing of one eager training step (CUDA events around every plan op), grouped by op kind
+and by conv layer.  Also the entry used under ncu (`--ncu` runs exactly one un-timed step after
+warm-up so `-s/-c` can select it).
+
+    python tools/profile_step.py [--batch 256] [--ncu]
+"""
+import argparse
+import os
+import sys
+from collections import defaultdict
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from assembled_cnn_b200.hparams import params_from_flags
+from assembled_cnn_b200.model_fns import Model, Trainer
+from bench import MODEL_FLAGS, TRAIN_FLAGS, synth_batch
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--ncu", action="store_true")
+ap.add_argument("--top", type=int, default=40)
+args = ap.parse_args()
+
+B = args.batch
+params = params_from_flags(batch_size=B, **MODEL_FLAGS, **TRAIN_FLAGS)
+model = Model(50, num_classes=1001, resnet_version=2, use_sk_block=True, anti_alias_type="sconv",
+              anti_alias_filter_size=3)
+tr = Trainer(model, params, 224, 224, use_cuda_graph=False)
+x, y = synth_batch(tr.input_batch, 224, 1234)
+x, y = x.cuda(), y.cuda()
+for _ in range(2):
+    tr.train_step(x, y)
+torch.cuda.synchronize()
+if args.ncu:
+    from assembled_cnn_b200 import _lib
+    c0 = _lib.load().acnn_launch_count()
+    tr.train_step(x, y)
+    torch.cuda.synchronize()
+    print("launches in profiled step:", _lib.load().acnn_launch_count() - c0)
+    sys.exit(0)
+
+rt = tr.rt
+records = []
+orig_run = rt.run
+
+
+def timed_run(ops):
+    for op in ops:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        getattr(rt, "op_" + op.kind)(op)
+        b.record()
+        records.append((op, a, b))
+
+
+rt.run = timed_run
+tr.train_step(x, y)
+torch.cuda.synchronize()
+rt.run = orig_run
+by_kind = defaultdict(lambda: [0.0, 0])
+rows = []
+for op, a, b in records:
+    ms = a.elapsed_time(b)
+    by_kind[op.kind][0] += ms
+    by_kind[op.kind][1] += 1
+    if op.kind in ("conv", "conv_dgrad", "conv_wgrad"):
+        g = op.geom
+        fl = 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
+        rows.append((ms, op.kind, "%dx%d %d->%d k%d s%d" % (g.H, g.W, g.Cin, g.Cout, g.kh, g.stride),
+                     fl / ms / 1e9))
+total = sum(v[0] for v in by_kind.values())
+print("total %.2f ms over %d ops" % (total, len(records)))
+for k, (ms, n) in sorted(by_kind.items(), key=lambda kv: -kv[1][0]):
+    print("%-20s %4d launches-ops %8.3f ms %5.1f%%" % (k, n, ms, 100 * ms / total))
+print("--- slowest conv GEMM launches (ms, kind, shape, TFLOP/s)")
+for ms, kind, shape, tf in sorted(rows, reverse=True)[:args.top]:
+    print("%7.3f %-11s %-28s %7.1f" % (ms, kind, shape, tf))
