@@ -18,7 +18,8 @@ class ConvGeom(C.Structure):
     """struct acnn_conv_geom (include/acnn.h)."""
     _fields_ = [(n, C.c_int32) for n in (
         "B", "H", "W", "Cin", "Cout", "kh", "kw", "stride",
-        "pad_h_lo", "pad_h_hi", "pad_w_lo", "pad_w_hi")]
+        "pad_h_lo", "pad_h_hi", "pad_w_lo", "pad_w_hi",
+        "x_pix_stride", "x_row_pitch", "x_img_pitch", "reserved_")]
 
     def out_hw(self):
         ho = (self.H + self.pad_h_lo + self.pad_h_hi - self.kh) // self.stride + 1

@@ -79,29 +79,45 @@ static int make_map_2d(CUtensorMap* m, const void* base, int64_t rows, int64_t c
   return ACNN_OK;
 }
 
+// Element pitches of the input tensor: dense NHWC unless the geometry overrides them (used by the
+// space-to-depth stem, whose "pixels" are overlapping 4-pixel windows of a W-padded image).
+static void input_pitches(const acnn_conv_geom& g, int64_t* pix, int64_t* row, int64_t* img) {
+  *pix = g.x_pix_stride > 0 ? g.x_pix_stride : g.Cin;
+  *row = g.x_row_pitch > 0 ? g.x_row_pitch : (int64_t)g.W * *pix;
+  *img = g.x_img_pitch > 0 ? g.x_img_pitch : (int64_t)g.H * *row;
+}
+
+static bool is_plain(const acnn_conv_geom& g) {
+  return g.kh == 1 && g.kw == 1 && g.stride == 1 && g.pad_h_lo == 0 && g.pad_w_lo == 0 &&
+         g.pad_h_hi == 0 && g.pad_w_hi == 0 && g.x_pix_stride <= 0 && g.x_row_pitch <= 0 &&
+         g.x_img_pitch <= 0;
+}
+
 // bf16 NHWC tensor [B][H][W][C]; one load = `pixels` consecutive output pixels x `cw` channels of
 // one filter tap.  The bounding box of base pixels is [-pad_lo, dim + pad_hi - (k-1)).
-static int make_map_im2col(CUtensorMap* m, const void* base, int B, int H, int W, int C, int kh,
-                           int kw, int stride, int pad_h_lo, int pad_h_hi, int pad_w_lo,
-                           int pad_w_hi, int cw, int pixels) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  int lower[2] = {-pad_w_lo, -pad_h_lo};
-  int upper[2] = {pad_w_hi - (kw - 1), pad_h_hi - (kh - 1)};
-  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+static int make_map_im2col(CUtensorMap* m, const void* base, const acnn_conv_geom& g, int cw,
+                           int pixels) {
+  int64_t pix, row, img;
+  input_pitches(g, &pix, &row, &img);
+  cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.B};
+  cuuint64_t strides[3] = {(cuuint64_t)pix * 2, (cuuint64_t)row * 2, (cuuint64_t)img * 2};
+  int lower[2] = {-g.pad_w_lo, -g.pad_h_lo};
+  int upper[2] = {g.pad_w_hi - (g.kw - 1), g.pad_h_hi - (g.kh - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
   CUresult r = g_encode_im2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base),
                                dims, strides, lower, upper, (cuuint32_t)cw, (cuuint32_t)pixels,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_enum(cw * 2),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeIm2col failed (%d): B=%d H=%d W=%d C=%d k=%dx%d s=%d cw=%d px=%d",
-              (int)r, B, H, W, C, kh, kw, stride, cw, pixels);
+    set_error("cuTensorMapEncodeIm2col failed (%d): B=%d H=%d W=%d C=%d k=%dx%d s=%d cw=%d px=%d "
+              "pitches=%lld/%lld/%lld", (int)r, g.B, g.H, g.W, g.Cin, g.kh, g.kw, g.stride, cw,
+              pixels, (long long)pix, (long long)row, (long long)img);
     return ACNN_ERR_CUDA;
   }
   // Driver <= 13.1 mis-encodes im2col maps of tensors smaller than 128 KiB (same fix-up the
   // CUTLASS im2col descriptor builder applies): clear bit 21 of the second descriptor word.
-  if (g_driver_version <= 13010 && (int64_t)B * H * W * C * 2 < 131072) {
+  if (g_driver_version <= 13010 && (int64_t)g.B * img * 2 < 131072) {
     reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
   }
   return ACNN_OK;
@@ -119,6 +135,7 @@ struct ConvGemmParams {
   int HoWo, Wo;   // to decompose a row index into (n, p, q)
   int stride, pad_h_lo, pad_w_lo;
   int b_sw_bytes; // swizzle span of the weight tile (128 unless Ktot < 64)
+  int stages;     // pipeline depth actually used (<= FpropCfg::kStages, <= number of K blocks)
   void* y;
   float* ch_sum;
   float* ch_sumsq;
@@ -137,9 +154,11 @@ struct FpropCfg {
   static constexpr int kABytes = kBM * kStageK * 2;   // 16 KiB
   static constexpr int kBBytes = BN * kStageK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // <= ~100 KiB so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop)
+  // <= ~100 KiB so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop);
+  // layers with few K blocks use fewer stages -> less shared memory -> up to 4 CTAs per SM.
   static constexpr int kStages = (BN >= 256) ? 4 : ((BN == 128) ? 3 : 4);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kSubW = BN < 64 ? BN : 64;          // output staging sub-tile width
+  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024; }
 };
 
 // Sum over the 32 lanes of a warp of 32 per-lane values each: on return lane l holds the total
@@ -178,19 +197,20 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 }
 
 template <int BN, int CW, bool IM2COL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
   using Cfg = FpropCfg<BN>;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kMaxStages = Cfg::kStages;
+  const int kStages = p.stages;
   constexpr int kChunks = kStageK / CW;        // A chunks (one filter tap each when Cin < 64)
   constexpr int kChunkBytes = kBM * CW * 2;
   constexpr int kKSteps = CW / 16;             // UMMA K = 16 bf16
   constexpr uint32_t kIdesc = make_idesc_bf16(BN, false, false);
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[kStages];
-  __shared__ uint64_t empty_bar[kStages];
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
   __shared__ uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float red_sum[4][BN];
@@ -207,6 +227,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (!p.out_f32) tma_prefetch_desc(&tmC);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -358,11 +379,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-        if (row_ok) {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off);
+        {
+          // Stage the tile in (now idle) pipeline smem in the TMA swizzle layout: sub-tiles of
+          // [128 rows][kSubW cols]; 16-byte piece j of row r lives at piece j ^ swz(r).
+          constexpr int kSubW = Cfg::kSubW;
+          constexpr int kRowBytes = kSubW * 2;
+          const int r = quarter * 32 + lane;
+          const int sub = (c * 32) / kSubW;
+          const int j0 = ((c * 32) % kSubW) / 8;
+          const int swz = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
+          uint8_t* base = smem + sub * (kBM * kRowBytes) + r * kRowBytes;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            dst[q] = make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+            *reinterpret_cast<uint4*>(base + (((j0 + q) ^ swz) << 4)) =
+                make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
         }
         if (stats) {
           // statistics of the tensor as stored (bf16-rounded); rows past M contribute zero
@@ -383,8 +413,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-    if (stats) {
+    if (!p.out_f32) {
+      fence_proxy_async();                       // generic-proxy smem writes -> async proxy
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        constexpr int kSubW = Cfg::kSubW;
+#pragma unroll
+        for (int sub = 0; sub < BN / kSubW; ++sub)
+          tma_store_2d(&tmC, smem + sub * (kBM * kSubW * 2), n0 + sub * kSubW, m0);
+        tma_store_commit_and_wait();
+      }
+    }
+    if (stats) {
+      if (p.out_f32) asm volatile("bar.sync 1, 128;\n" ::: "memory");
       const int t = threadIdx.x - 64;  // 0..127
       for (int col = t; col < BN; col += 128) {
         const float s = red_sum[0][col] + red_sum[1][col] + red_sum[2][col] + red_sum[3][col];
@@ -404,13 +445,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
-// wgrad kernel
+// wgrad kernel:  D[(tap,ci) = M 128 rows][co = N] += sum over pixels of  x_im2col^T * dy
 // ------------------------------------------------------------------------------------------
 struct WgradParams {
   int P;           // pixels B*Ho*Wo (GEMM K)
-  int Cout;        // GEMM M
+  int Cout;        // GEMM N
   int Cin;
-  int Ktot;        // kh*kw*Cin (GEMM N)
+  int Ktot;        // kh*kw*Cin (GEMM M)
   int kw;
   int HoWo, Wo;
   int stride, pad_h_lo, pad_w_lo;
@@ -421,25 +462,27 @@ struct WgradParams {
 
 constexpr int kWgPix = 64;   // pixels per pipeline stage (4 UMMA K-steps)
 
-template <int BNW>
+template <int BN>
 struct WgradCfg {
-  static constexpr int kABytes = kWgPix * 128 * 2;   // 64 pixels x 128 output channels
-  static constexpr int kBBytes = kWgPix * BNW * 2;
+  static constexpr int kABytes = kWgPix * 128 * 2;   // 64 pixels x 128 (tap,ci) columns
+  static constexpr int kBBytes = kWgPix * BN * 2;    // 64 pixels x BN output channels
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BNW >= 256) ? 4 : 4;
+  static constexpr int kStages = (BN >= 256) ? 4 : ((BN == 128) ? 3 : 4);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
 };
 
-template <int BNW, int CW, int CWA, bool IM2COL>
+// CW: channel width of one im2col chunk of x (16/32/64), CWB: channel width of one dy chunk.
+template <int BN, int CW, int CWB, bool IM2COL>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const WgradParams p) {
-  using Cfg = WgradCfg<BNW>;
+  using Cfg = WgradCfg<BN>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kNChunks = BNW / CW;
-  constexpr int kBChunkBytes = kWgPix * CW * 2;
-  constexpr int kAChunkBytes = kWgPix * CWA * 2;
-  constexpr uint32_t kIdesc = make_idesc_bf16(BNW, true, true);
+  constexpr int kAChunks = 128 / CW;
+  constexpr int kBChunks = BN / CWB;
+  constexpr int kAChunkBytes = kWgPix * CW * 2;
+  constexpr int kBChunkBytes = kWgPix * CWB * 2;
+  constexpr uint32_t kIdesc = make_idesc_bf16(BN, true, true);
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kStages];
@@ -451,17 +494,17 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BNW;
-  const int co0 = blockIdx.y * 128;
+  const int m0 = blockIdx.x * 128;      // first (tap,ci) column of dw handled here
+  const int co0 = blockIdx.y * BN;
   const int ks_begin = blockIdx.z * p.stages_per_split;
   int ks_end = ks_begin + p.stages_per_split;
   if (ks_end > p.stages_total) ks_end = p.stages_total;
   const int num_ks = ks_end - ks_begin;   // >= 1 by construction of the grid
 
-  int a_chunks = (p.Cout - co0 < 128 ? p.Cout - co0 : 128) / CWA;
-  int b_chunks = 0;
+  int a_chunks = 0;
 #pragma unroll
-  for (int j = 0; j < kNChunks; ++j) b_chunks += (n0 + j * CW < p.Ktot) ? 1 : 0;
+  for (int j = 0; j < kAChunks; ++j) a_chunks += (m0 + j * CW < p.Ktot) ? 1 : 0;
+  int b_chunks = (p.Cout - co0 < BN ? p.Cout - co0 : BN) / CWB;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDY);
@@ -473,7 +516,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<(BNW < 32 ? 32 : BNW)>(&tmem_base_smem);
+  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -489,8 +532,6 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
         mbar_expect_tx(&full_bar[stage], a_chunks * kAChunkBytes + b_chunks * kBChunkBytes);
-        for (int i = 0; i < a_chunks; ++i)
-          tma_load_2d(sa + i * kAChunkBytes, &tmDY, &full_bar[stage], co0 + i * CWA, p0);
         int img = 0, h0 = 0, w0 = 0;
         if (IM2COL) {
           img = p0 / p.HoWo;
@@ -501,21 +542,23 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
           w0 = qo * p.stride - p.pad_w_lo;
         }
 #pragma unroll
-        for (int j = 0; j < kNChunks; ++j) {
-          const int n = n0 + j * CW;
+        for (int j = 0; j < kAChunks; ++j) {
+          const int n = m0 + j * CW;
           if (n < p.Ktot) {
             const int tap = n / p.Cin;
             const int c0 = n - tap * p.Cin;
             if (IM2COL) {
               const int r = tap / p.kw;
               const int s = tap - r * p.kw;
-              tma_load_im2col_4d(sb + j * kBChunkBytes, &tmX, &full_bar[stage], c0, w0, h0, img,
+              tma_load_im2col_4d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], c0, w0, h0, img,
                                  (uint16_t)s, (uint16_t)r);
             } else {
-              tma_load_2d(sb + j * kBChunkBytes, &tmX, &full_bar[stage], c0, p0);
+              tma_load_2d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], c0, p0);
             }
           }
         }
+        for (int i = 0; i < b_chunks; ++i)
+          tma_load_2d(sb + i * kBChunkBytes, &tmDY, &full_bar[stage], co0 + i * CWB, p0);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -524,8 +567,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accumulate = 0;
-      const uint32_t a_lt = swizzle_layout_type(CWA * 2);
-      const uint32_t b_lt = swizzle_layout_type(CW * 2);
+      const uint32_t a_lt = swizzle_layout_type(CW * 2);
+      const uint32_t b_lt = swizzle_layout_type(CWB * 2);
       for (int it = 0; it < num_ks; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -533,10 +576,10 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         const uint32_t sb = sa + Cfg::kABytes;
 #pragma unroll
         for (int ks = 0; ks < kWgPix / 16; ++ks) {
-          // MN-major operands: one pixel row = CW*2 bytes, 8-row groups SBO apart, column
+          // MN-major operands: one pixel row = width*2 bytes, 8-row groups SBO apart, column
           // blocks (64/32/16 channels) LBO apart.  16 pixel rows per UMMA.
-          const uint64_t da = make_smem_desc(sa + ks * 16 * CWA * 2, kAChunkBytes, 8 * CWA * 2, a_lt);
-          const uint64_t db = make_smem_desc(sb + ks * 16 * CW * 2, kBChunkBytes, 8 * CW * 2, b_lt);
+          const uint64_t da = make_smem_desc(sa + ks * 16 * CW * 2, kAChunkBytes, 8 * CW * 2, a_lt);
+          const uint64_t db = make_smem_desc(sb + ks * 16 * CWB * 2, kBChunkBytes, 8 * CWB * 2, b_lt);
           umma_bf16(tmem_base, da, db, kIdesc, accumulate);
           accumulate = 1;
         }
@@ -546,21 +589,24 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       umma_commit(&tmem_full_bar);
     }
   } else {
+    // TMEM lane = row of D = (tap,ci) column of dw; consecutive lanes -> consecutive addresses.
     const int quarter = warp & 3;
-    const int co = co0 + quarter * 32 + lane;
+    const int n = m0 + quarter * 32 + lane;
+    const bool n_ok = n < p.Ktot;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BNW / 32; ++c) {
-      if (n0 + c * 32 >= p.Ktot) break;   // warp-uniform
+    for (int c = 0; c < BN / 32; ++c) {
+      if (co0 + c * 32 >= p.Cout) break;   // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
       tmem_ld_wait();
-      if (co < p.Cout) {
-        float* dst = p.dw + static_cast<size_t>(co) * p.Ktot + n0 + c * 32;
+      if (n_ok) {
+        float* dst = p.dw + static_cast<size_t>(co0 + c * 32) * p.Ktot + n;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          if (n0 + c * 32 + i < p.Ktot) atomicAdd(dst + i, __uint_as_float(v[i]));
+          if (co0 + c * 32 + i < p.Cout)
+            atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, __uint_as_float(v[i]));
         }
       }
     }
@@ -570,7 +616,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<(BNW < 32 ? 32 : BNW)>(tmem_base);
+    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
   }
 }
 
@@ -589,37 +635,40 @@ static int num_sms() {
 }
 
 template <int BN, int CW, bool IM2COL>
-static int launch_conv_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p,
-                            cudaStream_t stream) {
+static int launch_conv_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                            const ConvGemmParams& p, cudaStream_t stream) {
   using Cfg = FpropCfg<BN>;
   static bool attr_set = false;
   auto kern = conv_gemm_kernel<BN, CW, IM2COL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes);
+                                         Cfg::smem_bytes(Cfg::kStages));
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
       return ACNN_ERR_CUDA;
     }
     attr_set = true;
   }
+  ConvGemmParams q = p;
+  const int num_kb = ceil_div(p.Ktot, kStageK);
+  q.stages = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
   dim3 grid(p.Cout / BN, ceil_div(p.M, kBM), 1);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  kern<<<grid, kThreads, Cfg::smem_bytes(q.stages), stream>>>(ta, tb, tc, q);
   count_launch();
   return check_launch("conv_gemm_kernel");
 }
 
 template <int BN>
 static int dispatch_conv_gemm(int cw, bool im2col, const CUtensorMap& ta, const CUtensorMap& tb,
-                              const ConvGemmParams& p, cudaStream_t s) {
+                              const CUtensorMap& tc, const ConvGemmParams& p, cudaStream_t s) {
   if (im2col) {
-    if (cw == 64) return launch_conv_gemm<BN, 64, true>(ta, tb, p, s);
-    if (cw == 32) return launch_conv_gemm<BN, 32, true>(ta, tb, p, s);
-    return launch_conv_gemm<BN, 16, true>(ta, tb, p, s);
+    if (cw == 64) return launch_conv_gemm<BN, 64, true>(ta, tb, tc, p, s);
+    if (cw == 32) return launch_conv_gemm<BN, 32, true>(ta, tb, tc, p, s);
+    return launch_conv_gemm<BN, 16, true>(ta, tb, tc, p, s);
   }
-  if (cw == 64) return launch_conv_gemm<BN, 64, false>(ta, tb, p, s);
-  if (cw == 32) return launch_conv_gemm<BN, 32, false>(ta, tb, p, s);
-  return launch_conv_gemm<BN, 16, false>(ta, tb, p, s);
+  if (cw == 64) return launch_conv_gemm<BN, 64, false>(ta, tb, tc, p, s);
+  if (cw == 32) return launch_conv_gemm<BN, 32, false>(ta, tb, tc, p, s);
+  return launch_conv_gemm<BN, 16, false>(ta, tb, tc, p, s);
 }
 
 static int chunk_width(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
@@ -642,8 +691,7 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   int rc = load_driver_fns();
   if (rc) return rc;
 
-  const bool plain = (g.kh == 1 && g.kw == 1 && g.stride == 1 && g.pad_h_lo == 0 &&
-                      g.pad_w_lo == 0 && g.pad_h_hi == 0 && g.pad_w_hi == 0);
+  const bool plain = is_plain(g);
   const int cw = chunk_width(g.Cin);
   ConvGemmParams p;
   p.M = g.B * Ho * Wo;
@@ -672,23 +720,28 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   if (plain) {
     rc = make_map_2d(&ta, x, p.M, g.Cin, g.Cin, kBM, cw);
   } else {
-    rc = make_map_im2col(&ta, x, g.B, g.H, g.W, g.Cin, g.kh, g.kw, g.stride, g.pad_h_lo,
-                         g.pad_h_hi, g.pad_w_lo, g.pad_w_hi, cw, kBM);
+    rc = make_map_im2col(&ta, x, g, cw, kBM);
   }
   if (rc) return rc;
   rc = make_map_2d(&tb, w, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
   if (rc) return rc;
-  if (bn == 128) return dispatch_conv_gemm<128>(cw, !plain, ta, tb, p, stream);
-  if (bn == 64) return dispatch_conv_gemm<64>(cw, !plain, ta, tb, p, stream);
-  return dispatch_conv_gemm<32>(cw, !plain, ta, tb, p, stream);
+  CUtensorMap tc = tb;   // unused for fp32 output
+  if (!out_f32) {
+    rc = make_map_2d(&tc, y, p.M, g.Cout, g.Cout, kBM, bn < 64 ? bn : 64);
+    if (rc) return rc;
+  }
+  p.stages = 1;
+  if (bn == 128) return dispatch_conv_gemm<128>(cw, !plain, ta, tb, tc, p, stream);
+  if (bn == 64) return dispatch_conv_gemm<64>(cw, !plain, ta, tb, tc, p, stream);
+  return dispatch_conv_gemm<32>(cw, !plain, ta, tb, tc, p, stream);
 }
 
-template <int BNW, int CW, int CWA, bool IM2COL>
-static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgradParams p, int m_tiles,
+template <int BN, int CW, int CWB, bool IM2COL>
+static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, WgradParams p, int m_tiles,
                         int n_tiles, cudaStream_t stream) {
-  using Cfg = WgradCfg<BNW>;
+  using Cfg = WgradCfg<BN>;
   static bool attr_set = false;
-  auto kern = wgrad_gemm_kernel<BNW, CW, CWA, IM2COL>;
+  auto kern = wgrad_gemm_kernel<BN, CW, CWB, IM2COL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
@@ -699,45 +752,44 @@ static int launch_wgrad(const CUtensorMap& tdy, const CUtensorMap& tx, WgradPara
     attr_set = true;
   }
   // split the pixel (K) range so that roughly two waves of CTAs cover the GPU
+  const int ctas_per_sm = Cfg::kSmemBytes <= 110 * 1024 ? 2 : 1;
   const int tiles = m_tiles * n_tiles;
-  int splits = ceil_div(2 * num_sms(), tiles);
+  int splits = ceil_div(2 * ctas_per_sm * num_sms(), tiles);
   const int max_splits = p.stages_total >= 8 ? p.stages_total / 4 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.stages_per_split = ceil_div(p.stages_total, splits);
   splits = ceil_div(p.stages_total, p.stages_per_split);
-  dim3 grid(n_tiles, m_tiles, splits);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tdy, tx, p);
+  dim3 grid(m_tiles, n_tiles, splits);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tx, tdy, p);
   count_launch();
   return check_launch("wgrad_gemm_kernel");
 }
 
-template <int BNW, int CW, bool IM2COL>
-static int dispatch_wgrad_cwa(int cwa, const CUtensorMap& tdy, const CUtensorMap& tx,
+template <int BN, int CW, bool IM2COL>
+static int dispatch_wgrad_cwb(int cwb, const CUtensorMap& tx, const CUtensorMap& tdy,
                               const WgradParams& p, int mt, int nt, cudaStream_t s) {
-  if (cwa == 64) return launch_wgrad<BNW, CW, 64, IM2COL>(tdy, tx, p, mt, nt, s);
-  return launch_wgrad<BNW, CW, 32, IM2COL>(tdy, tx, p, mt, nt, s);
+  if constexpr (BN >= 64) {
+    if (cwb == 64) return launch_wgrad<BN, CW, 64, IM2COL>(tx, tdy, p, mt, nt, s);
+  }
+  return launch_wgrad<BN, CW, 32, IM2COL>(tx, tdy, p, mt, nt, s);
 }
 
-template <int BNW, bool IM2COL>
-static int dispatch_wgrad_cw(int cw, int cwa, const CUtensorMap& tdy, const CUtensorMap& tx,
+template <int BN, bool IM2COL>
+static int dispatch_wgrad_cw(int cw, int cwb, const CUtensorMap& tx, const CUtensorMap& tdy,
                              const WgradParams& p, int mt, int nt, cudaStream_t s) {
-  if constexpr (BNW >= 64) {
-    if (cw == 64) return dispatch_wgrad_cwa<BNW, 64, IM2COL>(cwa, tdy, tx, p, mt, nt, s);
-  }
-  if (cw == 32) return dispatch_wgrad_cwa<BNW, 32, IM2COL>(cwa, tdy, tx, p, mt, nt, s);
-  if (cw == 16) return dispatch_wgrad_cwa<BNW, 16, IM2COL>(cwa, tdy, tx, p, mt, nt, s);
-  set_error("wgrad: chunk width %d wider than N tile %d", cw, BNW);
-  return ACNN_ERR_INVALID;
+  if (cw == 64) return dispatch_wgrad_cwb<BN, 64, IM2COL>(cwb, tx, tdy, p, mt, nt, s);
+  if (cw == 32) return dispatch_wgrad_cwb<BN, 32, IM2COL>(cwb, tx, tdy, p, mt, nt, s);
+  return dispatch_wgrad_cwb<BN, 16, IM2COL>(cwb, tx, tdy, p, mt, nt, s);
 }
 
 template <bool IM2COL>
-static int dispatch_wgrad(int bnw, int cw, int cwa, const CUtensorMap& tdy, const CUtensorMap& tx,
+static int dispatch_wgrad(int bn, int cw, int cwb, const CUtensorMap& tx, const CUtensorMap& tdy,
                           const WgradParams& p, int mt, int nt, cudaStream_t s) {
-  if (bnw == 256) return dispatch_wgrad_cw<256, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
-  if (bnw == 128) return dispatch_wgrad_cw<128, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
-  if (bnw == 64) return dispatch_wgrad_cw<64, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
-  return dispatch_wgrad_cw<32, IM2COL>(cw, cwa, tdy, tx, p, mt, nt, s);
+  if (bn == 256) return dispatch_wgrad_cw<256, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
+  if (bn == 128) return dispatch_wgrad_cw<128, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
+  if (bn == 64) return dispatch_wgrad_cw<64, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
+  return dispatch_wgrad_cw<32, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
 }
 
 static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* dy, float* dw,
@@ -748,8 +800,7 @@ static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* d
   ACNN_REQUIRE(Ho > 0 && Wo > 0, "wgrad: empty output");
   int rc = load_driver_fns();
   if (rc) return rc;
-  const bool plain = (g.kh == 1 && g.kw == 1 && g.stride == 1 && g.pad_h_lo == 0 &&
-                      g.pad_w_lo == 0 && g.pad_h_hi == 0 && g.pad_w_hi == 0);
+  const bool plain = is_plain(g);
   WgradParams p;
   p.P = g.B * Ho * Wo;
   p.Cout = g.Cout;
@@ -765,23 +816,22 @@ static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* d
   p.stages_per_split = p.stages_total;
   p.dw = dw;
   const int cw = chunk_width(g.Cin);
-  const int cwa = (g.Cout % 64 == 0) ? 64 : 32;
-  int bnw = 256;
-  if (p.Ktot < 256) bnw = p.Ktot >= 128 ? 128 : (p.Ktot >= 64 ? 64 : 32);
+  const int cwb = (g.Cout % 64 == 0) ? 64 : 32;
+  const int bn = g.Cout >= 256 ? 256 : (g.Cout >= 128 ? 128 : (g.Cout >= 64 ? 64 : 32));
+  ACNN_REQUIRE(g.Cout % bn == 0, "wgrad: Cout=%d not a multiple of its N tile %d", g.Cout, bn);
   CUtensorMap tdy, tx;
-  rc = make_map_2d(&tdy, dy, p.P, g.Cout, g.Cout, kWgPix, cwa);
+  rc = make_map_2d(&tdy, dy, p.P, g.Cout, g.Cout, kWgPix, cwb);
   if (rc) return rc;
   if (plain) {
     rc = make_map_2d(&tx, x, p.P, g.Cin, g.Cin, kWgPix, cw);
   } else {
-    rc = make_map_im2col(&tx, x, g.B, g.H, g.W, g.Cin, g.kh, g.kw, g.stride, g.pad_h_lo,
-                         g.pad_h_hi, g.pad_w_lo, g.pad_w_hi, cw, kWgPix);
+    rc = make_map_im2col(&tx, x, g, cw, kWgPix);
   }
   if (rc) return rc;
-  const int mt = ceil_div(g.Cout, 128);
-  const int nt = ceil_div(p.Ktot, bnw);
-  if (plain) return dispatch_wgrad<false>(bnw, cw, cwa, tdy, tx, p, mt, nt, stream);
-  return dispatch_wgrad<true>(bnw, cw, cwa, tdy, tx, p, mt, nt, stream);
+  const int mt = ceil_div(p.Ktot, 128);
+  const int nt = g.Cout / bn;
+  if (plain) return dispatch_wgrad<false>(bn, cw, cwb, tx, tdy, p, mt, nt, stream);
+  return dispatch_wgrad<true>(bn, cw, cwb, tx, tdy, p, mt, nt, stream);
 }
 
 }  // namespace acnn
@@ -829,6 +879,7 @@ int acnn_conv_dgrad(const acnn_conv_geom* g, const void* dy, const void* w_dgrad
   t.pad_h_hi = g->kh - 1 - g->pad_h_hi;
   t.pad_w_lo = g->kw - 1 - g->pad_w_lo;
   t.pad_w_hi = g->kw - 1 - g->pad_w_hi;
+  t.x_pix_stride = t.x_row_pitch = t.x_img_pitch = t.reserved_ = 0;
   return acnn::conv_gemm_host(t, dy, w_dgrad, dx, nullptr, nullptr, add_src, mask_src, nullptr, 0,
                               static_cast<cudaStream_t>(stream));
 }

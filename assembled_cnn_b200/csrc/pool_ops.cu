@@ -362,15 +362,22 @@ grad_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ add_src
 __global__ void __launch_bounds__(kPT)
 pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
                   const float* __restrict__ lam2, int mode, bf16* __restrict__ out, int Bin, int B,
-                  int H, int W, int64_t npix) {
+                  int H, int W, int wpad_lo, int wpad_hi, int64_t npix) {
   const int H2 = H >> 1, W2 = W >> 1;
+  const int Wp = W2 + wpad_lo + wpad_hi;
   const int half = Bin >> 1;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix;
        i += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(i % W2);
-    int64_t t = i / W2;
+    const int j = (int)(i % Wp) - wpad_lo;
+    int64_t t = i / Wp;
     const int ii = (int)(t % H2);
     const int b = (int)(t / H2);
+    if (j < 0 || j >= W2) {              // physical zero padding of the W axis
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      reinterpret_cast<uint4*>(out + i * 16)[0] = z;
+      reinterpret_cast<uint4*>(out + i * 16)[1] = z;
+      continue;
+    }
     int b1 = b, b2 = b;
     float lam = 1.f;
     if (mode == 1) {
@@ -616,15 +623,16 @@ int acnn_grad_combine(const void* a, const void* add_src, const void* mask_src, 
 }
 
 int acnn_pack_input(const float* images, const float* lam1, const float* lam2, int mode, void* out,
-                    int Bin, int H, int W, void* stream) {
+                    int Bin, int H, int W, int wpad_lo, int wpad_hi, void* stream) {
   ACNN_REQUIRE(images && out && H % 2 == 0 && W % 2 == 0 && mode >= 0 && mode <= 2,
                "pack_input: bad arguments");
   ACNN_REQUIRE(mode == 0 || (lam1 && Bin % 2 == 0), "pack_input: mixup needs lam1 and even batch");
   ACNN_REQUIRE(mode != 2 || lam2, "pack_input: mixup type 2 needs lam2");
   const int B = mode == 1 ? Bin / 2 : Bin;
-  const int64_t npix = (int64_t)B * (H / 2) * (W / 2);
+  ACNN_REQUIRE(wpad_lo >= 0 && wpad_hi >= 0, "pack_input: negative padding");
+  const int64_t npix = (int64_t)B * (H / 2) * (W / 2 + wpad_lo + wpad_hi);
   pack_input_kernel<<<grid_for(npix), kPT, 0, (cudaStream_t)stream>>>(
-      images, lam1, lam2, mode, (bf16*)out, Bin, B, H, W, npix);
+      images, lam1, lam2, mode, (bf16*)out, Bin, B, H, W, wpad_lo, wpad_hi, npix);
   count_launch();
   return check_launch("pack_input");
 }

@@ -1,86 +1,102 @@
 // The tiny fully-connected layers of the SK / SE attention paths (<= 0.3 MMAC per image):
-// CUDA-core fp32 kernels on [B, <=2048] descriptors.  nets/blocks.py:136-151 (SK), :171-182 (SE).
+// fp32 CUDA-core GEMMs on [B, <=2048] descriptors.  nets/blocks.py:136-151 (SK), :171-182 (SE).
+//
+// One shared-memory-tiled SGEMM (64x64x16 tile, 4x4 micro-tile per thread, split-K with fp32
+// atomics) serves all of them through generic element strides; the batch-norm-over-batch, gate and
+// activation glue are separate one-warp-per-channel / elementwise kernels.
 #include "common.h"
 #include "vec.cuh"
 
 namespace acnn {
 
-constexpr int kTB = 4;       // batch rows per block
 constexpr int kFT = 256;
+constexpr int kTM = 64, kTN = 64, kTK = 16;
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return 1.f / (1.f + __expf(-v));
-  return v;
-}
-
-// out[b][j] = act(sum_k in[b][k] * W[j][k])          W row-major [J][K]
+// C[M][N] (row-major, ldc = N) += sum_k A(m,k) * B(k,n)
+//   A(m,k) = A[m*sAm + k*sAk],  B(k,n) = B[k*sBk + n*sBn]
+// gridDim = (ceil(N/64), ceil(M/64), splits); every CTA atomically adds its partial tile.
 __global__ void __launch_bounds__(kFT)
-fc_nt_kernel(const float* __restrict__ in, const float* __restrict__ W, float* __restrict__ out,
-             int B, int K, int J, int act) {
-  extern __shared__ float tile[];   // [kTB][K]
-  const int b0 = blockIdx.x * kTB;
-  for (int i = threadIdx.x; i < kTB * K; i += kFT) {
-    const int t = i / K, k = i - t * K;
-    tile[i] = (b0 + t < B) ? in[(size_t)(b0 + t) * K + k] : 0.f;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < J; j += kFT / 32) {
-    float acc[kTB];
+sgemm_acc_kernel(const float* __restrict__ A, const float* __restrict__ B, float* C, int M, int N,
+                 int K, int sAm, int sAk, int sBk, int sBn, int k_per_split) {
+  __shared__ float As[kTK][kTM + 4];
+  __shared__ float Bs[kTK][kTN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads, 4x4 outputs each
+  const int m0 = blockIdx.y * kTM, n0 = blockIdx.x * kTN;
+  const int k_begin = blockIdx.z * k_per_split;
+  int k_end = k_begin + k_per_split;
+  if (k_end > K) k_end = K;
+  float acc[4][4];
 #pragma unroll
-    for (int t = 0; t < kTB; ++t) acc[t] = 0.f;
-    const float* wr = W + (size_t)j * K;
-    for (int k = lane; k < K; k += 32) {
-      const float w = __ldg(wr + k);
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int t = 0; t < kTB; ++t) acc[t] = fmaf(tile[t * K + k], w, acc[t]);
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = k_begin; k0 < k_end; k0 += kTK) {
+    // coalesce along whichever index is unit-stride in global memory
+#pragma unroll
+    for (int e = 0; e < (kTM * kTK) / kFT; ++e) {
+      const int idx = tid + e * kFT;
+      int mm, kk;
+      if (sAm == 1) { mm = idx % kTM; kk = idx / kTM; } else { kk = idx % kTK; mm = idx / kTK; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < k_end) ? __ldg(A + (size_t)m * sAm + (size_t)k * sAk) : 0.f;
     }
 #pragma unroll
-    for (int t = 0; t < kTB; ++t) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], o);
+    for (int e = 0; e < (kTN * kTK) / kFT; ++e) {
+      const int idx = tid + e * kFT;
+      int nn, kk;
+      if (sBn == 1) { nn = idx % kTN; kk = idx / kTN; } else { kk = idx % kTK; nn = idx / kTK; }
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < N && k < k_end) ? __ldg(B + (size_t)k * sBk + (size_t)n * sBn) : 0.f;
     }
-    if (lane < kTB && b0 + lane < B) out[(size_t)(b0 + lane) * J + j] = apply_act(acc[lane], act);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) atomicAdd(C + (size_t)m * N + n, acc[i][j]);
+    }
   }
 }
 
-// out[b][j] = post * sum_k in[b][k] * W[k][j]          W row-major [K][J]
-__global__ void __launch_bounds__(kFT)
-fc_nn_kernel(const float* __restrict__ in, const float* __restrict__ W, float* __restrict__ out,
-             int B, int K, int J, float post) {
-  extern __shared__ float tile[];   // [kTB][K]
-  const int b0 = blockIdx.x * kTB;
-  for (int i = threadIdx.x; i < kTB * K; i += kFT) {
-    const int t = i / K, k = i - t * K;
-    tile[i] = (b0 + t < B) ? in[(size_t)(b0 + t) * K + k] : 0.f;
-  }
-  __syncthreads();
-  for (int j = threadIdx.x; j < J; j += kFT) {
-    float acc[kTB];
-#pragma unroll
-    for (int t = 0; t < kTB; ++t) acc[t] = 0.f;
-    for (int k = 0; k < K; ++k) {
-      const float w = __ldg(W + (size_t)k * J + j);
-#pragma unroll
-      for (int t = 0; t < kTB; ++t) acc[t] = fmaf(tile[t * K + k], w, acc[t]);
+// C (+)= A*B with split-K sized so that ~2 CTAs per SM are in flight.
+static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int sAm, int sAk,
+                 int sBk, int sBn, bool zero_c, cudaStream_t s) {
+  if (zero_c) {
+    cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
+    if (e != cudaSuccess) {
+      set_error("sgemm memset: %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
     }
-#pragma unroll
-    for (int t = 0; t < kTB; ++t)
-      if (b0 + t < B) out[(size_t)(b0 + t) * J + j] = acc[t] * post;
   }
-}
-
-// dW[k][j] += sum_b A[b][k] * Bm[b][j]
-__global__ void __launch_bounds__(kFT)
-outer_acc_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* dW, int B, int K,
-                 int J) {
-  const int64_t idx = blockIdx.x * (int64_t)kFT + threadIdx.x;
-  if (idx >= (int64_t)K * J) return;
-  const int k = (int)(idx / J), j = (int)(idx - (int64_t)k * J);
-  float acc = 0.f;
-  for (int b = 0; b < B; ++b) acc = fmaf(__ldg(A + (size_t)b * K + k), __ldg(Bm + (size_t)b * J + j), acc);
-  dW[idx] += acc;
+  const int tiles = ceil_div(M, kTM) * ceil_div(N, kTN);
+  int splits = ceil_div(296, tiles);
+  const int max_splits = ceil_div(K, 2 * kTK);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int kps = ceil_div(ceil_div(K, splits), kTK) * kTK;
+  splits = ceil_div(K, kps);
+  dim3 grid(ceil_div(N, kTN), ceil_div(M, kTM), splits);
+  sgemm_acc_kernel<<<grid, kFT, 0, s>>>(A, B, C, M, N, K, sAm, sAk, sBk, sBn, kps);
+  count_launch();
+  return check_launch("sgemm_acc");
 }
 
 // One warp per channel j: batch-norm over the batch dimension, then ReLU.
@@ -179,33 +195,27 @@ __global__ void sk_gate_bwd_kernel(const float* __restrict__ dA, const float* __
   da[(size_t)b * 2 * f + f + c] = -t;
 }
 
-// out = in * e * (1 - e)   (sigmoid backward)   /   out = in * (h > 0)   (relu backward)
-__global__ void ew_bwd_kernel(const float* in, const float* __restrict__ act,
-                              float* out, int64_t n, int mode) {
+// mode 1: out = relu(in) ; 2: out = sigmoid(in) ; 3: out = in*(act>0) ; 4: out = in*act*(1-act) ;
+// 5: out = in*scale
+__global__ void ew_kernel(const float* in, const float* act, float* out, int64_t n, int mode,
+                          float scale) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
-  out[i] = (mode == 2) ? in[i] * act[i] * (1.f - act[i]) : (act[i] > 0.f ? in[i] : 0.f);
+  const float v = in[i];
+  float o;
+  if (mode == 1) o = fmaxf(v, 0.f);
+  else if (mode == 2) o = 1.f / (1.f + expf(-v));
+  else if (mode == 3) o = act[i] > 0.f ? v : 0.f;
+  else if (mode == 4) o = v * act[i] * (1.f - act[i]);
+  else o = v * scale;
+  out[i] = o;
 }
 
-static int fc_nt(const float* in, const float* W, float* out, int B, int K, int J, int act,
-                 cudaStream_t s) {
-  ACNN_REQUIRE(kTB * K * 4 <= 48 * 1024, "fc: K=%d too large", K);
-  fc_nt_kernel<<<ceil_div(B, kTB), kFT, kTB * K * 4, s>>>(in, W, out, B, K, J, act);
+static int ew(const float* in, const float* act, float* out, int64_t n, int mode, float scale,
+              cudaStream_t s) {
+  ew_kernel<<<(int)ceil_div64(n, 256), 256, 0, s>>>(in, act, out, n, mode, scale);
   count_launch();
-  return check_launch("fc_nt");
-}
-static int fc_nn(const float* in, const float* W, float* out, int B, int K, int J, float post,
-                 cudaStream_t s) {
-  ACNN_REQUIRE(kTB * K * 4 <= 48 * 1024, "fc: K=%d too large", K);
-  fc_nn_kernel<<<ceil_div(B, kTB), kFT, kTB * K * 4, s>>>(in, W, out, B, K, J, post);
-  count_launch();
-  return check_launch("fc_nn");
-}
-static int outer_acc(const float* A, const float* Bm, float* dW, int B, int K, int J,
-                     cudaStream_t s) {
-  outer_acc_kernel<<<(int)ceil_div64((int64_t)K * J, kFT), kFT, 0, s>>>(A, Bm, dW, B, K, J);
-  count_launch();
-  return check_launch("outer_acc");
+  return check_launch("ew");
 }
 
 }  // namespace acnn
@@ -221,13 +231,15 @@ int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const fl
   ACNN_REQUIRE(s && w1 && gamma && beta && moving_mean && moving_var && w2 && zpre && bnstat && z &&
                    att && scratch, "sk_fc_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = fc_nt(s, w1, zpre, B, f, d, 0, st);
+  // zpre[B,d] = s[B,f] * W1[d,f]^T
+  int rc = sgemm(s, w1, zpre, B, d, f, f, 1, 1, f, true, st);
   if (rc) return rc;
   bn_batch_relu_fwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(
       zpre, gamma, beta, moving_mean, moving_var, momentum, eps, training, z, bnstat, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_fwd"))) return rc;
-  if ((rc = fc_nt(z, w2, scratch, B, d, 2 * f, 0, st))) return rc;
+  // a[B,2f] = z[B,d] * W2[2f,d]^T
+  if ((rc = sgemm(z, w2, scratch, B, 2 * f, d, d, 1, 1, d, true, st))) return rc;
   sk_gate_fwd_kernel<<<(int)ceil_div64((int64_t)B * f, 256), 256, 0, st>>>(scratch, att, B, f);
   count_launch();
   return check_launch("sk_gate_fwd");
@@ -246,23 +258,30 @@ int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const floa
   count_launch();
   int rc = check_launch("sk_gate_bwd");
   if (rc) return rc;
-  if ((rc = outer_acc(da, z, dw2, B, 2 * f, d, st))) return rc;        // dW2[2f][d]
-  if ((rc = fc_nn(da, w2, dz, B, 2 * f, d, 1.f, st))) return rc;        // dz = da * W2
+  // dW2[2f,d] += da^T[2f,B] * z[B,d]
+  if ((rc = sgemm(da, z, dw2, 2 * f, d, B, 1, 2 * f, d, 1, false, st))) return rc;
+  // dz[B,d] = da[B,2f] * W2[2f,d]
+  if ((rc = sgemm(da, w2, dz, B, d, 2 * f, 2 * f, 1, d, 1, true, st))) return rc;
   bn_batch_relu_bwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(dz, z, zpre, bnstat, gamma,
                                                                   dgamma, dbeta, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_bwd"))) return rc;
-  if ((rc = outer_acc(dz, s, dw1, B, d, f, st))) return rc;             // dW1[d][f]
-  return fc_nn(dz, w1, ds, B, d, f, 1.f, st);                           // ds = dzpre * W1
+  // dW1[d,f] += dzpre^T[d,B] * s[B,f]
+  if ((rc = sgemm(dz, s, dw1, d, f, B, 1, d, f, 1, false, st))) return rc;
+  // ds[B,f] = dzpre[B,d] * W1[d,f]
+  return sgemm(dz, w1, ds, B, f, d, d, 1, f, 1, true, st);
 }
 
 int acnn_se_fc_fwd(const float* q, const float* w1, const float* w2, float* h, float* e, int B,
                    int C, int r, void* stream) {
   ACNN_REQUIRE(q && w1 && w2 && h && e, "se_fc_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = fc_nt(q, w1, h, B, C, r, 1, st);
+  // h = relu(q[B,C] * W1[r,C]^T) ; e = sigmoid(h[B,r] * W2[C,r]^T)
+  int rc = sgemm(q, w1, h, B, r, C, C, 1, 1, C, true, st);
   if (rc) return rc;
-  return fc_nt(h, w2, e, B, r, C, 2, st);
+  if ((rc = ew(h, nullptr, h, (int64_t)B * r, 1, 0.f, st))) return rc;
+  if ((rc = sgemm(h, w2, e, B, C, r, r, 1, 1, r, true, st))) return rc;
+  return ew(e, nullptr, e, (int64_t)B * C, 2, 0.f, st);
 }
 
 int acnn_se_fc_bwd(const float* de, const float* e, const float* h, const float* q,
@@ -273,18 +292,14 @@ int acnn_se_fc_bwd(const float* de, const float* e, const float* h, const float*
   cudaStream_t st = (cudaStream_t)stream;
   float* da2 = scratch;                     // [B][C]
   float* dh = scratch + (size_t)B * C;      // [B][r]
-  const int64_t n2 = (int64_t)B * C, n1 = (int64_t)B * r;
-  ew_bwd_kernel<<<(int)ceil_div64(n2, 256), 256, 0, st>>>(de, e, da2, n2, 2);
-  count_launch();
-  int rc = check_launch("se sigmoid bwd");
+  int rc = ew(de, e, da2, (int64_t)B * C, 4, 0.f, st);
   if (rc) return rc;
-  if ((rc = outer_acc(da2, h, dw2, B, C, r, st))) return rc;            // dW2[C][r]
-  if ((rc = fc_nn(da2, w2, dh, B, C, r, 1.f, st))) return rc;           // dh = da2 * W2
-  ew_bwd_kernel<<<(int)ceil_div64(n1, 256), 256, 0, st>>>(dh, h, dh, n1, 1);
-  count_launch();
-  if ((rc = check_launch("se relu bwd"))) return rc;
-  if ((rc = outer_acc(dh, q, dw1, B, r, C, st))) return rc;             // dW1[r][C]
-  return fc_nn(dh, w1, dq, B, r, C, 1.f / HW, st);                      // dq = da1 * W1 / HW
+  if ((rc = sgemm(da2, h, dw2, C, r, B, 1, C, r, 1, false, st))) return rc;    // dW2[C,r]
+  if ((rc = sgemm(da2, w2, dh, B, r, C, C, 1, r, 1, true, st))) return rc;     // dh = da2 * W2
+  if ((rc = ew(dh, h, dh, (int64_t)B * r, 3, 0.f, st))) return rc;
+  if ((rc = sgemm(dh, q, dw1, r, C, B, 1, r, C, 1, false, st))) return rc;     // dW1[r,C]
+  if ((rc = sgemm(dh, w1, dq, B, C, r, r, 1, C, 1, true, st))) return rc;      // dq = da1 * W1
+  return ew(dq, nullptr, dq, (int64_t)B * C, 5, 1.f / HW, st);
 }
 
 }  // extern "C"

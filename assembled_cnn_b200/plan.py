@@ -350,15 +350,22 @@ class PlanBuilder:
             self.use(x)
         return ConvOut(x, y, g, w.name, bn)
 
-    def stem_conv(self, x0: Tensor, filters, k) -> ConvOut:
-        """First conv (k x k, stride 2, 3 input channels) run as a stride-1 conv on the
-        space-to-depth(2) input that pack_input produced."""
-        B, H2, W2, C16 = x0.shape
-        layer = self._unique("conv2d")
+    @staticmethod
+    def stem_s2d_taps(k):
+        """k x k stride-2 conv with padding (k-1)//2 == k2 x k2 stride-1 conv on the
+        space-to-depth(2) image with padding (lo2, hi2): input offset u - p = 2*r + a."""
         p = (k - 1) // 2
         rmin = math.floor(-p / 2)
         rmax = math.floor((k - 1 - p) / 2)
-        k2, lo2, hi2 = rmax - rmin + 1, -rmin, rmax
+        return p, rmax - rmin + 1, -rmin, rmax
+
+    def stem_conv(self, x0: Tensor, filters, k) -> ConvOut:
+        """First conv (k x k, stride 2, 3 input channels) run as a stride-1 conv on the
+        space-to-depth(2) input that pack_input produced."""
+        B, H2, Wp, C16 = x0.shape
+        layer = self._unique("conv2d")
+        p, k2, lo2, hi2 = self.stem_s2d_taps(k)
+        W2 = Wp - lo2 - hi2
         w = self._param(self._full(layer + "/kernel"), (k, k, 3, filters), "conv_kernel",
                         (filters, k, k, 3), decay=True)
         g = Geom(B, H2, W2, 16, filters, k2, k2, 1, lo2, hi2, lo2, hi2)
@@ -369,8 +376,10 @@ class PlanBuilder:
                     dw2=self.slot("zero", filters * k2 * k2 * 16) if self.training else None)
         self.emit("s2d_weight_pack", w=w.name, w2=stem["w2"].name, cout=filters, **{
             "k": k, "pad": p, "k2": k2, "pad2": lo2})
+        stem["x_wpad"] = (lo2, hi2)
         self.emit("conv", x=x0.name, w=stem["w2"].name, y=y.name, geom=g,
-                  stats=bn.stats if self.training else None, bias=None, out_f32=False, w_is_tensor=True)
+                  stats=bn.stats if self.training else None, bias=None, out_f32=False,
+                  w_is_tensor=True, x_wpad=(lo2, hi2))
         self.emit("bn_finalize", bn=bn)
         return ConvOut(x0, y, g, w.name, bn, stem)
 
@@ -399,7 +408,8 @@ class PlanBuilder:
     def conv_backward(self, co: ConvOut, dy: str, need_dgrad=True):
         g = co.geom
         if co.stem is not None:
-            self.emit("conv_wgrad", x=co.x.name, dy=dy, geom=g, dw_slot=co.stem["dw2"])
+            self.emit("conv_wgrad", x=co.x.name, dy=dy, geom=g, dw_slot=co.stem["dw2"],
+                      x_wpad=co.stem["x_wpad"])
             self.emit("s2d_wgrad_unpack", dw2=co.stem["dw2"], w=co.w, cout=g.Cout, k=co.stem["k"],
                       pad=co.stem["pad"], k2=co.stem["k2"], pad2=co.stem["pad2"])
             return
@@ -619,7 +629,9 @@ class PlanBuilder:
         Bin = meta["input_batch"]
         images = self.tensor("images", (Bin, H, W, 3), "f32")
         meta["images"] = images.name
-        x0 = self.tensor("x0", (B, H // 2, W // 2, 16))
+        # the W axis of the packed input is physically zero-padded for the stem's taps
+        _, _, wlo, whi = self.stem_s2d_taps(3 if cfg.use_resnet_d else 7)
+        x0 = self.tensor("x0", (B, H // 2, W // 2 + wlo + whi, 16))
         self.emit("prep_weights")
         lam1 = lam2 = None
         if self.mixup_type:
@@ -629,7 +641,8 @@ class PlanBuilder:
                 lam2 = self.tensor("lam2", (Bin // 2,), "f32")
                 meta["lam2"] = lam2.name
         self.emit("pack_input", images=images.name, lam1=lam1 and lam1.name,
-                  lam2=lam2 and lam2.name, mode=self.mixup_type, out=x0.name, Bin=Bin, H=H, W=W)
+                  lam2=lam2 and lam2.name, mode=self.mixup_type, out=x0.name, Bin=Bin, H=H, W=W,
+                  wpad=(wlo, whi))
 
         d = cfg.use_resnet_d
         if d and cfg.resnet_version == 1:

@@ -107,11 +107,21 @@ class Runtime:
     def T(self, name):
         return None if name is None else self.t[name].data_ptr()
 
-    def geom(self, g: Geom):
-        key = g.astuple()
+    def geom(self, g: Geom, x_wpad=None):
+        """ConvGeom for the C ABI.  With x_wpad=(lo, hi) the input is the W-padded space-to-depth
+        image: the k2 horizontal taps become channels of one wide pixel (x_pix_stride < Cin)."""
+        key = g.astuple() + (x_wpad,)
         cg = self._geom_cache.get(key)
         if cg is None:
-            cg = self._geom_cache[key] = _lib.ConvGeom(*key)
+            if x_wpad is None:
+                cg = _lib.ConvGeom(*g.astuple())
+            else:
+                lo, hi = x_wpad
+                assert g.stride == 1 and g.pad_w_lo == lo and g.pad_w_hi == hi
+                row = (g.W + lo + hi) * g.Cin
+                cg = _lib.ConvGeom(g.B, g.H, g.W, g.Cin * g.kw, g.Cout, g.kh, 1, 1,
+                                   g.pad_h_lo, g.pad_h_hi, 0, 0, g.Cin, row, g.H * row, 0)
+            self._geom_cache[key] = cg
         return cg
 
     def slot_view(self, slot: Slot):
@@ -209,7 +219,7 @@ class Runtime:
     def op_pack_input(self, op):
         self._chk(self.lib.acnn_pack_input(self.T(op.images), self.T(op.lam1), self.T(op.lam2),
                                            op.mode, self.T(op.out), op.Bin, op.H, op.W,
-                                           self.stream), op)
+                                           op.wpad[0], op.wpad[1], self.stream), op)
 
     def op_mix_labels(self, op):
         self._chk(self.lib.acnn_mix_labels(self.T(op.labels), self.T(op.lam1), self.T(op.lam2),
@@ -224,7 +234,7 @@ class Runtime:
         st = op.stats
         C_ = op.geom.Cout
         self._chk(self.lib.acnn_conv_fprop(
-            self.geom(op.geom), self.T(op.x), w, self.T(op.y), self.S(st), self.S(st, C_) if st else None,
+            self.geom(op.geom, op.a.get("x_wpad")), self.T(op.x), w, self.T(op.y), self.S(st), self.S(st, C_) if st else None,
             None, None, self.P(op.bias) if op.bias else None, 1 if op.out_f32 else 0, self.stream), op)
 
     def op_bn_finalize(self, op):
@@ -300,8 +310,8 @@ class Runtime:
     def op_conv_wgrad(self, op):
         slot = op.a.get("dw_slot")
         dw = self.S(slot) if slot is not None else self.G(op.w)
-        self._chk(self.lib.acnn_conv_wgrad(self.geom(op.geom), self.T(op.x), self.T(op.dy), dw,
-                                           self.stream), op)
+        self._chk(self.lib.acnn_conv_wgrad(self.geom(op.geom, op.a.get("x_wpad")), self.T(op.x),
+                                           self.T(op.dy), dw, self.stream), op)
 
     def op_conv_dgrad(self, op):
         self._chk(self.lib.acnn_conv_dgrad(self.geom(op.geom), self.T(op.dy), self.WD(op.w),

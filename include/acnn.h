@@ -41,6 +41,10 @@ typedef struct acnn_conv_geom {
   int32_t B, H, W, Cin;
   int32_t Cout, kh, kw, stride;
   int32_t pad_h_lo, pad_h_hi, pad_w_lo, pad_w_hi;
+  /* Optional element pitches of x (0 = dense NHWC): between W-adjacent pixels, between rows and
+   * between images.  x_pix_stride < Cin makes neighbouring "pixels" overlap: the stem conv reads
+   * its space-to-depth input [B][H][W+3][16] as W pixels of 64 channels (4 horizontal taps). */
+  int32_t x_pix_stride, x_row_pitch, x_img_pitch, reserved_;
 } acnn_conv_geom;
 
 /* y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w[Cout,kh,kw,Cin])  as a tcgen05 implicit GEMM
@@ -200,13 +204,14 @@ int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int
 /* ---------------------------------------------------------------------------------------------
  * Input packing / mixup (utils/data_util.py:97-158) and the loss (losses/cls_losses.py:28-33)
  * ------------------------------------------------------------------------------------------- */
-/* images fp32 NHWC [Bin,H,W,3] -> bf16 space-to-depth(2) [B,H/2,W/2,16]
+/* images fp32 NHWC [Bin,H,W,3] -> bf16 space-to-depth(2) [B,H/2,wpad_lo + W/2 + wpad_hi,16]
  *   (channel = (dy*2+dx)*4 + c, c==3 is zero) so that the stride-2 stem conv becomes a stride-1
- *   conv with 16 input channels.  mode 0: B = Bin (copy); 1: mixup type 1, B = Bin/2,
+ *   conv with 16 input channels; the W axis is physically zero-padded so that the stem can read
+ *   k2 horizontally adjacent pixels as one k2*16-channel pixel (acnn_conv_geom.x_pix_stride).  mode 0: B = Bin (copy); 1: mixup type 1, B = Bin/2,
  *   out = lam1*x[:B] + (1-lam1)*x[B:]; 2: mixup type 2, B = Bin, second half uses lam2 and the
  *   reversed second half. */
 int acnn_pack_input(const float* images, const float* lam1, const float* lam2, int mode, void* out,
-                    int Bin, int H, int W, void* stream);
+                    int Bin, int H, int W, int wpad_lo, int wpad_hi, void* stream);
 /* y[B,NC] (fp32) = (mixed) one-hot labels, same modes. */
 int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2, int mode, float* y,
                     int Bin, int NC, void* stream);

@@ -154,7 +154,9 @@ class PlanInterpreter:
         B, H, W, _ = x.shape
         x4 = F.pad(x, (0, 1))                                            # c: 3 -> 4
         x4 = x4.view(B, H // 2, 2, W // 2, 2, 4).permute(0, 1, 3, 2, 4, 5)   # b,i,j,dy,dx,c
-        self.store(op.out, x4.reshape(B, H // 2, W // 2, 16))
+        x4 = x4.reshape(B, H // 2, W // 2, 16)
+        lo, hi = op.wpad
+        self.store(op.out, F.pad(x4, (0, 0, lo, hi)))                    # physical W padding
 
     def op_mix_labels(self, op):
         lab = self.t[op.labels].long()
@@ -188,6 +190,9 @@ class PlanInterpreter:
         w = self.t[op.w] if op.a.get("w_is_tensor") else self.wq(self.pview(op.w))
         if x.dim() == 2:
             x = x[:, None, None, :]
+        if op.a.get("x_wpad"):
+            lo, hi = op.x_wpad
+            x = x[:, :, lo:x.shape[2] - hi, :]
         y = self._conv(x, w, g)
         if op.bias:
             y = y + self.pview(op.bias)
@@ -360,6 +365,9 @@ class PlanInterpreter:
         x, dy = self.t[op.x], self.t[op.dy]
         if x.dim() == 2:
             x, dy = x[:, None, None, :], dy[:, None, None, :]
+        if op.a.get("x_wpad"):
+            lo, hi = op.x_wpad
+            x = x[:, :, lo:x.shape[2] - hi, :]
         w = torch.zeros(g.Cout, g.kh, g.kw, g.Cin, dtype=self.dtype, requires_grad=True)
         (dw,) = torch.autograd.grad(self._conv(x, w, g), w, dy)
         if op.a.get("dw_slot") is not None:

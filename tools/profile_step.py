@@ -36,8 +36,10 @@ torch.cuda.synchronize()
 if args.ncu:
     from assembled_cnn_b200 import _lib
     c0 = _lib.load().acnn_launch_count()
+    torch.cuda.profiler.start()          # ncu --profile-from-start off
     tr.train_step(x, y)
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     print("launches in profiled step:", _lib.load().acnn_launch_count() - c0)
     sys.exit(0)
 
