@@ -107,11 +107,27 @@ def synth_batch(n, hw, seed):
     return x, y
 
 
+def effective_cores():
+    """Host cores this process may really use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, min(n, 64))
+
+
 def cpu_reference(batch, steps, warmup, hw=224):
     """The reference's TF1 CPU path, restated (oracle/model.py): same step, host cores."""
     import torch
     from oracle import model as M, tf_ops as T
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     torch.set_num_threads(cores)
     torch.set_flush_denormal(True)
     model, vs = M.build(seed=42, input_hw=64, **MODEL_FLAGS)
@@ -136,6 +152,21 @@ def cpu_reference(batch, steps, warmup, hw=224):
                        "TF 1.14 not installable), Assemble-ResNet-50 224x224, batch %d "
                        "(mixup type 1 from %d inputs), %d timed step(s) after %d warm-up, "
                        "torch %d threads" % (batch, 2 * batch, steps, warmup, cores)), sec
+
+
+def cpu_baseline_subprocess(timeout_s=240):
+    """Times the oracle in a child process (bounded: the bench line must not hang on a slow host)."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                            "--steps", "2"], capture_output=True, text=True, timeout=timeout_s)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"value": None, "unit": "images/sec", "cores": effective_cores(), "kind": "port",
+                "sample": "failed: " + (r.stderr.strip().splitlines() or ["no output"])[-1][:200]}
+    except subprocess.TimeoutExpired:
+        return {"value": None, "unit": "images/sec", "cores": effective_cores(), "kind": "port",
+                "sample": "timed out after %d s" % timeout_s}
 
 
 def run_reference_arm(args):
@@ -262,7 +293,7 @@ def main():
         roof = conv_roofline(tr, x_dev, y_dev, peaks, ms_step)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu, _ = cpu_reference(8, 2, 1)
+        cpu = cpu_baseline_subprocess()
 
     if rank == 0:
         line = {

