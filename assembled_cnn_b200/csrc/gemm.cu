@@ -124,7 +124,7 @@ static int make_map_im2col(CUtensorMap* m, const void* base, const acnn_conv_geo
 }
 
 // ------------------------------------------------------------------------------------------
-// fprop / dgrad / dense kernel
+// fprop / dgrad / dense kernel (persistent, warp-specialised)
 // ------------------------------------------------------------------------------------------
 struct ConvGemmParams {
   int M;          // output pixels B*Ho*Wo
@@ -135,30 +135,44 @@ struct ConvGemmParams {
   int HoWo, Wo;   // to decompose a row index into (n, p, q)
   int stride, pad_h_lo, pad_w_lo;
   int b_sw_bytes; // swizzle span of the weight tile (128 unless Ktot < 64)
-  int stages;     // pipeline depth actually used (<= FpropCfg::kStages, <= number of K blocks)
+  int stages;     // smem pipeline depth
+  int m_tiles, n_tiles;
   void* y;
   float* ch_sum;
   float* ch_sumsq;
-  const __nv_bfloat16* add_src;
-  const __nv_bfloat16* mask_src;
   const float* bias;
+  int has_add, has_mask;
   int out_f32;
 };
 
 constexpr int kBM = 128;        // output pixels per CTA tile == UMMA M == TMEM lanes
 constexpr int kStageK = 64;     // K elements per pipeline stage
 constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 216 * 1024;   // dynamic smem; ~4.5 KiB static comes on top (227 KiB max)
 
 template <int BN>
 struct FpropCfg {
   static constexpr int kABytes = kBM * kStageK * 2;   // 16 KiB
   static constexpr int kBBytes = BN * kStageK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // <= ~100 KiB so two CTAs share an SM (one CTA's epilogue overlaps the other's main loop);
-  // layers with few K blocks use fewer stages -> less shared memory -> up to 4 CTAs per SM.
-  static constexpr int kStages = (BN >= 256) ? 4 : ((BN == 128) ? 3 : 4);
-  static constexpr int kSubW = BN < 64 ? BN : 64;          // output staging sub-tile width
-  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024; }
+  static constexpr int kSubW = BN < 64 ? BN : 64;          // staging sub-tile width (TMA box)
+  static constexpr int kTileBytes = kBM * BN * 2;          // one bf16 output / add / mask tile
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator stages
+  // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
+  static int stages_for(int num_kb, bool has_add, bool has_mask, bool out_f32) {
+    const int fixed = 1024 + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
+                      (has_mask ? kTileBytes : 0);
+    int st = (kSmemBudget - fixed) / kStageBytes;
+    if (st > kMaxStages) st = kMaxStages;
+    if (st < 2) st = 2;
+    (void)num_kb;
+    return st;
+  }
+  static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32) {
+    return 1024 + stages * kStageBytes + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
+           (has_mask ? kTileBytes : 0);
+  }
 };
 
 // Sum over the 32 lanes of a warp of 32 per-lane values each: on return lane l holds the total
@@ -196,46 +210,69 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// One CTA per SM walks output tiles (fixed N tile, M tiles strided by the grid).  The TMA producer
+// runs ahead across tiles through the smem ring; the MMA issuer alternates between two TMEM
+// accumulators; the 4 epilogue warps drain accumulator i while the tensor core fills i^1.
 template <int BN, int CW, bool IM2COL>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd,
+                 const __grid_constant__ CUtensorMap tmMask, const ConvGemmParams p) {
   using Cfg = FpropCfg<BN>;
-  constexpr int kMaxStages = Cfg::kStages;
-  const int kStages = p.stages;
   constexpr int kChunks = kStageK / CW;        // A chunks (one filter tap each when Cin < 64)
   constexpr int kChunkBytes = kBM * CW * 2;
   constexpr int kKSteps = CW / 16;             // UMMA K = 16 bf16
   constexpr uint32_t kIdesc = make_idesc_bf16(BN, false, false);
+  constexpr int kSubW = Cfg::kSubW;
+  constexpr int kRowBytes = kSubW * 2;
+  constexpr int kSubBytes = kBM * kRowBytes;
+  constexpr int kNSub = BN / kSubW;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
-  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint64_t aux_bar;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float red_sum[4][BN];
   __shared__ float red_sq[4][BN];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int kStages = p.stages;
+  uint8_t* s_out = smem + kStages * Cfg::kStageBytes;
+  uint8_t* s_add = s_out + (p.out_f32 ? 0 : Cfg::kTileBytes);
+  uint8_t* s_mask = s_add + (p.has_add ? Cfg::kTileBytes : 0);
+
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * kBM;
   const int num_kb = (p.Ktot + kStageK - 1) / kStageK;
+  // static tile schedule: this CTA owns N tile n_tile and M tiles m_first, m_first + m_step, ...
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles;
+  const int m_step = gridDim.x / p.n_tiles;
+  const int n0 = n_tile * BN;
+  const int my_tiles = m_first < p.m_tiles ? (p.m_tiles - m_first + m_step - 1) / m_step : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (!p.out_f32) tma_prefetch_desc(&tmC);
+    if (p.has_add) tma_prefetch_desc(&tmAdd);
+    if (p.has_mask) tma_prefetch_desc(&tmMask);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 1);
+    }
+    mbar_init(&aux_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(&tmem_base_smem);
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -244,45 +281,48 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      int img = 0, h0 = 0, w0 = 0;
-      if (IM2COL) {
-        img = m0 / p.HoWo;
-        const int rem = m0 - img * p.HoWo;
-        const int po = rem / p.Wo;
-        const int qo = rem - po * p.Wo;
-        h0 = po * p.stride - p.pad_h_lo;
-        w0 = qo * p.stride - p.pad_w_lo;
-      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
-        const int k0 = kb * kStageK;
-        int nchunk = 0;
+      const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int m0 = (m_first + it * m_step) * kBM;
+        int img = 0, h0 = 0, w0 = 0;
+        if (IM2COL) {
+          img = m0 / p.HoWo;
+          const int rem = m0 - img * p.HoWo;
+          const int po = rem / p.Wo;
+          const int qo = rem - po * p.Wo;
+          h0 = po * p.stride - p.pad_h_lo;
+          w0 = qo * p.stride - p.pad_w_lo;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int k0 = kb * kStageK;
+          int nchunk = 0;
 #pragma unroll
-        for (int j = 0; j < kChunks; ++j) nchunk += (k0 + j * CW < p.Ktot) ? 1 : 0;
-        const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
-        mbar_expect_tx(&full_bar[stage], nchunk * kChunkBytes + b_bytes);
+          for (int j = 0; j < kChunks; ++j) nchunk += (k0 + j * CW < p.Ktot) ? 1 : 0;
+          mbar_expect_tx(&full_bar[stage], nchunk * kChunkBytes + b_bytes);
 #pragma unroll
-        for (int j = 0; j < kChunks; ++j) {
-          const int k = k0 + j * CW;
-          if (k < p.Ktot) {
-            if (IM2COL) {
-              const int tap = k / p.Cin;
-              const int c0 = k - tap * p.Cin;
-              const int r = tap / p.kw;
-              const int s = tap - r * p.kw;
-              tma_load_im2col_4d(sa + j * kChunkBytes, &tmA, &full_bar[stage], c0, w0, h0, img,
-                                 (uint16_t)s, (uint16_t)r);
-            } else {
-              tma_load_2d(sa + j * kChunkBytes, &tmA, &full_bar[stage], k, m0);
+          for (int j = 0; j < kChunks; ++j) {
+            const int k = k0 + j * CW;
+            if (k < p.Ktot) {
+              if (IM2COL) {
+                const int tap = k / p.Cin;
+                const int c0 = k - tap * p.Cin;
+                const int r = tap / p.kw;
+                const int s = tap - r * p.kw;
+                tma_load_im2col_4d(sa + j * kChunkBytes, &tmA, &full_bar[stage], c0, w0, h0, img,
+                                   (uint16_t)s, (uint16_t)r);
+              } else {
+                tma_load_2d(sa + j * kChunkBytes, &tmA, &full_bar[stage], k, m0);
+              }
             }
           }
+          tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -290,142 +330,175 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t accumulate = 0;
       const uint32_t a_lt = swizzle_layout_type(CW * 2);
       const uint32_t b_lt = swizzle_layout_type(p.b_sw_bytes);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
-        const int k0 = kb * kStageK;
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        uint32_t accumulate = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const int k0 = kb * kStageK;
 #pragma unroll
-        for (int j = 0; j < kChunks; ++j) {
-          if (k0 + j * CW < p.Ktot) {
+          for (int j = 0; j < kChunks; ++j) {
+            if (k0 + j * CW < p.Ktot) {
 #pragma unroll
-            for (int ks = 0; ks < kKSteps; ++ks) {
-              const uint64_t da =
-                  make_smem_desc(sa + j * kChunkBytes + ks * 32, 16, 8 * CW * 2, a_lt);
-              const uint64_t db = make_smem_desc(sb + (j * kKSteps + ks) * 32, 16,
-                                                 8 * p.b_sw_bytes, b_lt);
-              umma_bf16(tmem_base, da, db, kIdesc, accumulate);
-              accumulate = 1;
+              for (int ks = 0; ks < kKSteps; ++ks) {
+                const uint64_t da =
+                    make_smem_desc(sa + j * kChunkBytes + ks * 32, 16, 8 * CW * 2, a_lt);
+                const uint64_t db = make_smem_desc(sb + (j * kKSteps + ks) * 32, 16,
+                                                   8 * p.b_sw_bytes, b_lt);
+                umma_bf16(tmem_d, da, db, kIdesc, accumulate);
+                accumulate = 1;
+              }
             }
           }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&empty_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        umma_commit(&tfull_bar[acc]);
       }
-      umma_commit(&tmem_full_bar);
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
-    const bool row_ok = row < p.M;
+    const int r = quarter * 32 + lane;                 // row inside the tile == TMEM lane
+    const bool leader = (warp == 2 && lane == 0);
     const bool stats = p.ch_sum != nullptr;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      float f[32];
+    const int swz = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
+    float col_s[BN / 32], col_q[BN / 32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-      const int col0 = n0 + c * 32;
-      const size_t off = static_cast<size_t>(row) * p.Cout + col0;
-      if (p.bias) {
+    for (int c = 0; c < BN / 32; ++c) col_s[c] = col_q[c] = 0.f;
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int m0 = (m_first + it * m_step) * kBM;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = m0 + r;
+      const bool row_ok = row < p.M;
+      if (leader) {
+        // the previous tile's TMA store must have finished READING the staging buffer
+        if (!p.out_f32) tma_store_wait_read();
+        if (p.has_add || p.has_mask) {
+          mbar_expect_tx(&aux_bar, (p.has_add ? Cfg::kTileBytes : 0) +
+                                       (p.has_mask ? Cfg::kTileBytes : 0));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col0 + i);
-      }
-      if (p.add_src && row_ok) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.add_src + off);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 u = __ldg(src + q);
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
-            f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+          for (int sub = 0; sub < kNSub; ++sub) {
+            if (p.has_add)
+              tma_load_2d(s_add + sub * kSubBytes, &tmAdd, &aux_bar, n0 + sub * kSubW, m0);
+            if (p.has_mask)
+              tma_load_2d(s_mask + sub * kSubBytes, &tmMask, &aux_bar, n0 + sub * kSubW, m0);
           }
         }
       }
-      if (p.mask_src && row_ok) {
-        const uint4* src = reinterpret_cast<const uint4*>(p.mask_src + off);
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");   // staging buffer free for everyone
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (p.has_add || p.has_mask) mbar_wait(&aux_bar, it & 1);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 u = __ldg(src + q);
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = __uint_as_float(w4[e] << 16);
-            const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-            if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
-            if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        const int col0 = n0 + c * 32;
+        const int sub = (c * 32) / kSubW;
+        const int j0 = ((c * 32) % kSubW) / 8;
+        const int soff = sub * kSubBytes + r * kRowBytes;
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col0 + i);
+        }
+        if (p.has_add) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_add + soff + (((j0 + q) ^ swz) << 4));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
+              f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+            }
           }
         }
-      }
-      if (p.out_f32) {
-        if (row_ok) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + off);
+        if (p.has_mask) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            dst[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(w4[e] << 16);
+              const float hi = __uint_as_float(w4[e] & 0xffff0000u);
+              if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
+              if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
+            }
+          }
         }
-      } else {
-        uint32_t pk[16];
+        if (p.out_f32) {
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) +
+                                                    static_cast<size_t>(row) * p.Cout + col0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-        {
-          // Stage the tile in (now idle) pipeline smem in the TMA swizzle layout: sub-tiles of
-          // [128 rows][kSubW cols]; 16-byte piece j of row r lives at piece j ^ swz(r).
-          constexpr int kSubW = Cfg::kSubW;
-          constexpr int kRowBytes = kSubW * 2;
-          const int r = quarter * 32 + lane;
-          const int sub = (c * 32) / kSubW;
-          const int j0 = ((c * 32) % kSubW) / 8;
-          const int swz = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
-          uint8_t* base = smem + sub * (kBM * kRowBytes) + r * kRowBytes;
+            for (int q = 0; q < 8; ++q)
+              dst[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+          }
+        } else {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+          // stage the tile in the TMA swizzle layout: 16-byte piece j of row r at piece j ^ swz
 #pragma unroll
           for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(base + (((j0 + q) ^ swz) << 4)) =
+            *reinterpret_cast<uint4*>(s_out + soff + (((j0 + q) ^ swz) << 4)) =
                 make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
-        if (stats) {
-          // statistics of the tensor as stored (bf16-rounded); rows past M contribute zero
-          float s1[32], s2[32];
+          if (stats) {
+            // statistics of the tensor as stored (bf16-rounded); rows past M contribute zero
+            float s1[32], s2[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float lo = row_ok ? __uint_as_float(pk[i] << 16) : 0.f;
-            const float hi = row_ok ? __uint_as_float(pk[i] & 0xffff0000u) : 0.f;
-            s1[2 * i] = lo;
-            s1[2 * i + 1] = hi;
-            s2[2 * i] = lo * lo;
-            s2[2 * i + 1] = hi * hi;
+            for (int i = 0; i < 16; ++i) {
+              const float lo = row_ok ? __uint_as_float(pk[i] << 16) : 0.f;
+              const float hi = row_ok ? __uint_as_float(pk[i] & 0xffff0000u) : 0.f;
+              s1[2 * i] = lo;
+              s1[2 * i + 1] = hi;
+              s2[2 * i] = lo * lo;
+              s2[2 * i + 1] = hi * hi;
+            }
+            col_s[c] += warp_transpose_sum(s1, lane);
+            col_q[c] += warp_transpose_sum(s2, lane);
           }
-          const float cs = warp_transpose_sum(s1, lane);
-          const float cq = warp_transpose_sum(s2, lane);
-          red_sum[quarter][c * 32 + lane] = cs;
-          red_sq[quarter][c * 32 + lane] = cq;
+        }
+      }
+      // accumulator drained (and staging written): hand TMEM back, then store the tile
+      tc_fence_before();
+      if (!p.out_f32) fence_proxy_async();               // generic-proxy smem writes -> async proxy
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      if (leader) {
+        mbar_arrive(&tempty_bar[acc]);
+        if (!p.out_f32) {
+#pragma unroll
+          for (int sub = 0; sub < kNSub; ++sub)
+            tma_store_2d(&tmC, s_out + sub * kSubBytes, n0 + sub * kSubW, m0);
+          tma_store_commit();
         }
       }
     }
-    if (!p.out_f32) {
-      fence_proxy_async();                       // generic-proxy smem writes -> async proxy
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      if (warp == 2 && lane == 0) {
-        constexpr int kSubW = Cfg::kSubW;
+    if (leader && !p.out_f32) tma_store_wait_all();
+    if (stats && my_tiles > 0) {
 #pragma unroll
-        for (int sub = 0; sub < BN / kSubW; ++sub)
-          tma_store_2d(&tmC, smem + sub * (kBM * kSubW * 2), n0 + sub * kSubW, m0);
-        tma_store_commit_and_wait();
+      for (int c = 0; c < BN / 32; ++c) {
+        red_sum[quarter][c * 32 + lane] = col_s[c];
+        red_sq[quarter][c * 32 + lane] = col_q[c];
       }
-    }
-    if (stats) {
-      if (p.out_f32) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
       const int t = threadIdx.x - 64;  // 0..127
       for (int col = t; col < BN; col += 128) {
         const float s = red_sum[0][col] + red_sum[1][col] + red_sum[2][col] + red_sum[3][col];
@@ -440,7 +513,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -634,15 +707,18 @@ static int num_sms() {
   return g_num_sms;
 }
 
+struct ConvMaps {
+  CUtensorMap a, b, c, add, mask;
+};
+
 template <int BN, int CW, bool IM2COL>
-static int launch_conv_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
-                            const ConvGemmParams& p, cudaStream_t stream) {
+static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStream_t stream) {
   using Cfg = FpropCfg<BN>;
   static bool attr_set = false;
   auto kern = conv_gemm_kernel<BN, CW, IM2COL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::smem_bytes(Cfg::kStages));
+                                         kSmemBudget + 2048);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
       return ACNN_ERR_CUDA;
@@ -651,24 +727,32 @@ static int launch_conv_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const 
   }
   ConvGemmParams q = p;
   const int num_kb = ceil_div(p.Ktot, kStageK);
-  q.stages = num_kb < Cfg::kStages ? num_kb : Cfg::kStages;
-  dim3 grid(p.Cout / BN, ceil_div(p.M, kBM), 1);
-  kern<<<grid, kThreads, Cfg::smem_bytes(q.stages), stream>>>(ta, tb, tc, q);
+  q.stages = Cfg::stages_for(num_kb, p.has_add, p.has_mask, p.out_f32);
+  q.m_tiles = ceil_div(p.M, kBM);
+  q.n_tiles = p.Cout / BN;
+  // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
+  // its per-channel statistics), at most one CTA per SM
+  int per_n = num_sms() / q.n_tiles;
+  if (per_n < 1) per_n = 1;
+  if (per_n > q.m_tiles) per_n = q.m_tiles;
+  const int grid = per_n * q.n_tiles;
+  kern<<<grid, kThreads, Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32), stream>>>(
+      tm.a, tm.b, tm.c, tm.add, tm.mask, q);
   count_launch();
   return check_launch("conv_gemm_kernel");
 }
 
 template <int BN>
-static int dispatch_conv_gemm(int cw, bool im2col, const CUtensorMap& ta, const CUtensorMap& tb,
-                              const CUtensorMap& tc, const ConvGemmParams& p, cudaStream_t s) {
+static int dispatch_conv_gemm(int cw, bool im2col, const ConvMaps& tm, const ConvGemmParams& p,
+                              cudaStream_t s) {
   if (im2col) {
-    if (cw == 64) return launch_conv_gemm<BN, 64, true>(ta, tb, tc, p, s);
-    if (cw == 32) return launch_conv_gemm<BN, 32, true>(ta, tb, tc, p, s);
-    return launch_conv_gemm<BN, 16, true>(ta, tb, tc, p, s);
+    if (cw == 64) return launch_conv_gemm<BN, 64, true>(tm, p, s);
+    if (cw == 32) return launch_conv_gemm<BN, 32, true>(tm, p, s);
+    return launch_conv_gemm<BN, 16, true>(tm, p, s);
   }
-  if (cw == 64) return launch_conv_gemm<BN, 64, false>(ta, tb, tc, p, s);
-  if (cw == 32) return launch_conv_gemm<BN, 32, false>(ta, tb, tc, p, s);
-  return launch_conv_gemm<BN, 16, false>(ta, tb, tc, p, s);
+  if (cw == 64) return launch_conv_gemm<BN, 64, false>(tm, p, s);
+  if (cw == 32) return launch_conv_gemm<BN, 32, false>(tm, p, s);
+  return launch_conv_gemm<BN, 16, false>(tm, p, s);
 }
 
 static int chunk_width(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
@@ -708,32 +792,32 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   p.y = y;
   p.ch_sum = ch_sum;
   p.ch_sumsq = ch_sumsq;
-  p.add_src = static_cast<const __nv_bfloat16*>(add_src);
-  p.mask_src = static_cast<const __nv_bfloat16*>(mask_src);
   p.bias = bias;
+  p.has_add = add_src != nullptr;
+  p.has_mask = mask_src != nullptr;
   p.out_f32 = out_f32;
+  p.stages = p.m_tiles = p.n_tiles = 0;
   ACNN_REQUIRE(p.b_sw_bytes == 128 || p.b_sw_bytes == 64 || p.b_sw_bytes == 32,
                "conv: unsupported K=%d", p.Ktot);
 
   const int bn = (g.Cout % 128 == 0) ? 128 : ((g.Cout % 64 == 0) ? 64 : 32);
-  CUtensorMap ta, tb;
+  ConvMaps tm;
   if (plain) {
-    rc = make_map_2d(&ta, x, p.M, g.Cin, g.Cin, kBM, cw);
+    rc = make_map_2d(&tm.a, x, p.M, g.Cin, g.Cin, kBM, cw);
   } else {
-    rc = make_map_im2col(&ta, x, g, cw, kBM);
+    rc = make_map_im2col(&tm.a, x, g, cw, kBM);
   }
   if (rc) return rc;
-  rc = make_map_2d(&tb, w, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
+  rc = make_map_2d(&tm.b, w, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
   if (rc) return rc;
-  CUtensorMap tc = tb;   // unused for fp32 output
-  if (!out_f32) {
-    rc = make_map_2d(&tc, y, p.M, g.Cout, g.Cout, kBM, bn < 64 ? bn : 64);
-    if (rc) return rc;
-  }
-  p.stages = 1;
-  if (bn == 128) return dispatch_conv_gemm<128>(cw, !plain, ta, tb, tc, p, stream);
-  if (bn == 64) return dispatch_conv_gemm<64>(cw, !plain, ta, tb, tc, p, stream);
-  return dispatch_conv_gemm<32>(cw, !plain, ta, tb, tc, p, stream);
+  tm.c = tm.add = tm.mask = tm.b;   // placeholders when unused
+  const int subw = bn < 64 ? bn : 64;
+  if (!out_f32 && (rc = make_map_2d(&tm.c, y, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
+  if (add_src && (rc = make_map_2d(&tm.add, add_src, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
+  if (mask_src && (rc = make_map_2d(&tm.mask, mask_src, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
+  if (bn == 128) return dispatch_conv_gemm<128>(cw, !plain, tm, p, stream);
+  if (bn == 64) return dispatch_conv_gemm<64>(cw, !plain, tm, p, stream);
+  return dispatch_conv_gemm<32>(cw, !plain, tm, p, stream);
 }
 
 template <int BN, int CW, int CWB, bool IM2COL>

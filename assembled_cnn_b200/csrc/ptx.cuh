@@ -103,9 +103,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
       "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_store_commit_and_wait() {
+__device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+// all committed bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+}
+// ... and have completed their global writes
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
 }
 
 // ---------------------------------------------------------------- TMEM / tcgen05
