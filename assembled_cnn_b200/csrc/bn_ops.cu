@@ -140,29 +140,44 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
   float acc[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * RPB + rsub; r < M; r += (int64_t)gridDim.x * RPB) {
-    float gv[8], yv[8];
-    load8(g + r * C + c0, gv);
-    load8(y + r * C + c0, yv);
-    if (gate || addbc) {
-      const int64_t bimg = r / HW;
-      if (gate) {
-        float t[8];
-        loadf8(gate + bimg * C + c0, t);
+  // 4 rows per trip: 8 independent 16-byte loads in flight per thread
+  const int64_t step = (int64_t)gridDim.x * RPB;
+  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 4 * step) {
+    float gv[4][8], yv[4][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gv[i] *= t[i];
-      }
-      if (addbc) {
-        float t[8];
-        loadf8(addbc + bimg * C + c0, t);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * step;
+      if (r < M) {
+        load8(g + r * C + c0, gv[u]);
+        load8(y + r * C + c0, yv[u]);
+      } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) gv[i] += t[i];
+        for (int i = 0; i < 8; ++i) gv[u][i] = yv[u][i] = 0.f;
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[0][i] += gv[i];
-      acc[1][i] += gv[i] * ((yv[i] - mu[i]) * rs[i]);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * step;
+      if ((gate || addbc) && r < M) {
+        const int64_t bimg = r / HW;
+        if (gate) {
+          float t[8];
+          loadf8(gate + bimg * C + c0, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gv[u][i] *= t[i];
+        }
+        if (addbc) {
+          float t[8];
+          loadf8(addbc + bimg * C + c0, t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gv[u][i] += t[i];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[0][i] += gv[u][i];
+        acc[1][i] += gv[u][i] * ((yv[u][i] - mu[i]) * rs[i]);
+      }
     }
   }
   block_reduce_atomic<2>(acc, CG, sums, [C](int a, int c) { return a * C + c; });

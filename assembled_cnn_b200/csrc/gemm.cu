@@ -280,89 +280,117 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int m0 = (m_first + it * m_step) * kBM;
-        int img = 0, h0 = 0, w0 = 0;
-        if (IM2COL) {
-          img = m0 / p.HoWo;
-          const int rem = m0 - img * p.HoWo;
-          const int po = rem / p.Wo;
-          const int qo = rem - po * p.Wo;
-          h0 = po * p.stride - p.pad_h_lo;
-          w0 = qo * p.stride - p.pad_w_lo;
-        }
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // The whole warp stays converged (so the uniform-datapath TMA/MMA instructions need no
+    // election loops); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
+    for (int it = 0; it < my_tiles; ++it) {
+      const int m0 = (m_first + it * m_step) * kBM;
+      int img = 0, h0 = 0, w0 = 0;
+      if (IM2COL) {
+        img = m0 / p.HoWo;
+        const int rem = m0 - img * p.HoWo;
+        const int po = rem / p.Wo;
+        const int qo = rem - po * p.Wo;
+        h0 = po * p.stride - p.pad_h_lo;
+        w0 = qo * p.stride - p.pad_w_lo;
+      }
+      // filter tap (tr, ts) and channel offset tc of the next chunk, advanced incrementally
+      int tr = 0, ts = 0, tc = 0, k = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           const int k0 = kb * kStageK;
-          int nchunk = 0;
-#pragma unroll
-          for (int j = 0; j < kChunks; ++j) nchunk += (k0 + j * CW < p.Ktot) ? 1 : 0;
+          int nchunk = kChunks;
+          if (k0 + kStageK > p.Ktot) nchunk = (p.Ktot - k0 + CW - 1) / CW;
           mbar_expect_tx(&full_bar[stage], nchunk * kChunkBytes + b_bytes);
+          int kr = tr, ksn = ts, kc = tc, kk = k;
 #pragma unroll
           for (int j = 0; j < kChunks; ++j) {
-            const int k = k0 + j * CW;
-            if (k < p.Ktot) {
+            if (kk < p.Ktot) {
               if (IM2COL) {
-                const int tap = k / p.Cin;
-                const int c0 = k - tap * p.Cin;
-                const int r = tap / p.kw;
-                const int s = tap - r * p.kw;
-                tma_load_im2col_4d(sa + j * kChunkBytes, &tmA, &full_bar[stage], c0, w0, h0, img,
-                                   (uint16_t)s, (uint16_t)r);
+                tma_load_im2col_4d(sa + j * kChunkBytes, &tmA, &full_bar[stage], kc, w0, h0, img,
+                                   (uint16_t)ksn, (uint16_t)kr);
               } else {
-                tma_load_2d(sa + j * kChunkBytes, &tmA, &full_bar[stage], k, m0);
+                tma_load_2d(sa + j * kChunkBytes, &tmA, &full_bar[stage], kk, m0);
               }
+            }
+            kk += CW;
+            kc += CW;
+            if (kc >= p.Cin) {
+              kc = 0;
+              if (++ksn == p.kw) { ksn = 0; ++kr; }
             }
           }
           tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        // every lane tracks the tap state (cheap, keeps the warp converged)
+#pragma unroll
+        for (int j = 0; j < kChunks; ++j) {
+          k += CW;
+          tc += CW;
+          if (tc >= p.Cin) {
+            tc = 0;
+            if (++ts == p.kw) { ts = 0; ++tr; }
+          }
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t a_lt = swizzle_layout_type(CW * 2);
-      const uint32_t b_lt = swizzle_layout_type(p.b_sw_bytes);
-      for (int it = 0; it < my_tiles; ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+    int stage = 0;
+    uint32_t phase = 0;
+    // descriptors of stage 0 / chunk 0; everything else is an add on the 14-bit address field
+    const uint64_t a_desc0 =
+        make_smem_desc(smem_u32(smem), 16, 8 * CW * 2, swizzle_layout_type(CW * 2));
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 8 * p.b_sw_bytes,
+                                            swizzle_layout_type(p.b_sw_bytes));
+    for (int it = 0; it < my_tiles; ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
-        uint32_t accumulate = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+        if (elect_one()) {
+          const uint64_t da0 = a_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
+          const uint64_t db0 = b_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
           const int k0 = kb * kStageK;
+          if (k0 + kStageK <= p.Ktot) {
 #pragma unroll
-          for (int j = 0; j < kChunks; ++j) {
-            if (k0 + j * CW < p.Ktot) {
+            for (int j = 0; j < kChunks; ++j) {
 #pragma unroll
               for (int ks = 0; ks < kKSteps; ++ks) {
-                const uint64_t da =
-                    make_smem_desc(sa + j * kChunkBytes + ks * 32, 16, 8 * CW * 2, a_lt);
-                const uint64_t db = make_smem_desc(sb + (j * kKSteps + ks) * 32, 16,
-                                                   8 * p.b_sw_bytes, b_lt);
-                umma_bf16(tmem_d, da, db, kIdesc, accumulate);
-                accumulate = 1;
+                umma_bf16(tmem_d, da0 + ((j * kChunkBytes + ks * 32) >> 4),
+                          db0 + (((j * kKSteps + ks) * 32) >> 4), kIdesc,
+                          (kb | j | ks) ? 1u : 0u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < kChunks; ++j) {
+              if (k0 + j * CW < p.Ktot) {
+#pragma unroll
+                for (int ks = 0; ks < kKSteps; ++ks) {
+                  umma_bf16(tmem_d, da0 + ((j * kChunkBytes + ks * 32) >> 4),
+                            db0 + (((j * kKSteps + ks) * 32) >> 4), kIdesc,
+                            (kb | j | ks) ? 1u : 0u);
+                }
               }
             }
           }
           umma_commit(&empty_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
         }
-        umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -596,12 +624,23 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int it = 0; it < num_ks; ++it) {
-        const int p0 = (ks_begin + it) * kWgPix;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // whole warp converged, one elected lane issues (no election loops around TMA instructions)
+    int stage = 0;
+    uint32_t phase = 0;
+    // (tap r, tap s, channel) of each A chunk of this CTA: fixed for the whole kernel
+    int ch_r[kAChunks], ch_s[kAChunks], ch_c[kAChunks];
+#pragma unroll
+    for (int j = 0; j < kAChunks; ++j) {
+      const int n = m0 + j * CW;
+      const int tap = n / p.Cin;
+      ch_c[j] = n - tap * p.Cin;
+      ch_r[j] = tap / p.kw;
+      ch_s[j] = tap - ch_r[j] * p.kw;
+    }
+    for (int it = 0; it < num_ks; ++it) {
+      const int p0 = (ks_begin + it) * kWgPix;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
         mbar_expect_tx(&full_bar[stage], a_chunks * kAChunkBytes + b_chunks * kBChunkBytes);
@@ -616,50 +655,46 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
 #pragma unroll
         for (int j = 0; j < kAChunks; ++j) {
-          const int n = m0 + j * CW;
-          if (n < p.Ktot) {
-            const int tap = n / p.Cin;
-            const int c0 = n - tap * p.Cin;
+          if (j < a_chunks) {
             if (IM2COL) {
-              const int r = tap / p.kw;
-              const int s = tap - r * p.kw;
-              tma_load_im2col_4d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], c0, w0, h0, img,
-                                 (uint16_t)s, (uint16_t)r);
+              tma_load_im2col_4d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], ch_c[j], w0, h0,
+                                 img, (uint16_t)ch_s[j], (uint16_t)ch_r[j]);
             } else {
-              tma_load_2d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], c0, p0);
+              tma_load_2d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], ch_c[j], p0);
             }
           }
         }
         for (int i = 0; i < b_chunks; ++i)
           tma_load_2d(sb + i * kBChunkBytes, &tmDY, &full_bar[stage], co0 + i * CWB, p0);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t accumulate = 0;
-      const uint32_t a_lt = swizzle_layout_type(CW * 2);
-      const uint32_t b_lt = swizzle_layout_type(CWB * 2);
-      for (int it = 0; it < num_ks; ++it) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
+    int stage = 0;
+    uint32_t phase = 0;
+    // MN-major operands: one pixel row = width*2 bytes, 8-row groups SBO apart, column blocks
+    // (64/32/16 channels) LBO apart.  16 pixel rows per UMMA.
+    const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), kAChunkBytes, 8 * CW * 2,
+                                            swizzle_layout_type(CW * 2));
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, kBChunkBytes,
+                                            8 * CWB * 2, swizzle_layout_type(CWB * 2));
+    for (int it = 0; it < num_ks; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da0 = a_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
+        const uint64_t db0 = b_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
 #pragma unroll
         for (int ks = 0; ks < kWgPix / 16; ++ks) {
-          // MN-major operands: one pixel row = width*2 bytes, 8-row groups SBO apart, column
-          // blocks (64/32/16 channels) LBO apart.  16 pixel rows per UMMA.
-          const uint64_t da = make_smem_desc(sa + ks * 16 * CW * 2, kAChunkBytes, 8 * CW * 2, a_lt);
-          const uint64_t db = make_smem_desc(sb + ks * 16 * CWB * 2, kBChunkBytes, 8 * CWB * 2, b_lt);
-          umma_bf16(tmem_base, da, db, kIdesc, accumulate);
-          accumulate = 1;
+          umma_bf16(tmem_base, da0 + ((ks * 16 * CW * 2) >> 4), db0 + ((ks * 16 * CWB * 2) >> 4),
+                    kIdesc, (it | ks) ? 1u : 0u);
         }
         umma_commit(&empty_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (it == num_ks - 1) umma_commit(&tmem_full_bar);
       }
-      umma_commit(&tmem_full_bar);
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
   } else {
     // TMEM lane = row of D = (tap,ci) column of dw; consecutive lanes -> consecutive addresses.
