@@ -274,7 +274,11 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
       loadf8(shift + f + c0, h1);
     }
   }
-  for (int r = rsub; r < HW; r += RPB) {
+  // gridDim.y CTAs share one image: each takes a contiguous slab of rows
+  const int rows_per = (HW + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per;
+  const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
+  for (int r = r_begin + rsub; r < r_end; r += RPB) {
     const int64_t row = (int64_t)b * HW + r;
     if (MODE == 0 || MODE == 1) {
       float y0[8], y1[8];
@@ -314,10 +318,15 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
     const float norm = (MODE == 0 || MODE == 2 || MODE == 4) ? 1.f / HW : 1.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] *= norm;
-    if (MODE == 4)
+    if (MODE == 4) {
       store8(reinterpret_cast<bf16*>(out) + (int64_t)b * f + c0, acc);
-    else
+    } else if (gridDim.y == 1) {
       storef8(reinterpret_cast<float*>(out) + (int64_t)b * f + c0, acc);
+    } else {
+      float* o = reinterpret_cast<float*>(out) + (int64_t)b * f + c0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(o + i, acc[i]);
+    }
   }
 }
 
@@ -452,6 +461,16 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
   }
 }
 
+// CTAs per image for the per-image reductions: enough CTAs to cover the GPU a few times.  With
+// more than one, the (zero-initialised) output is accumulated atomically.
+static int image_splits(int B, int HW, int f) {
+  const int rpb = kT / (f >> 3);
+  int s = (148 * 6 + B - 1) / B;
+  const int max_s = (HW + 2 * rpb - 1) / (2 * rpb);
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
+}
+
 static bool cg_ok(int C) {
   const int cg = C >> 3;
   return C % 8 == 0 && cg >= 1 && cg <= kT && (kT % cg) == 0;
@@ -528,7 +547,15 @@ int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const flo
 int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s, int B, int HW,
                 int f, void* stream) {
   ACNN_REQUIRE(y && scale && shift && s && cg_ok(f), "sk_gap: bad arguments f=%d", f);
-  image_reduce_kernel<0><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
+  const int splits = image_splits(B, HW, f);
+  if (splits > 1) {
+    cudaError_t e = cudaMemsetAsync(s, 0, (size_t)B * f * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      set_error("sk_gap memset: %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
+    }
+  }
+  image_reduce_kernel<0><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
                                                              s, HW, f);
   count_launch();
   return check_launch("sk_gap");
@@ -537,7 +564,15 @@ int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s,
 int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const float* shift,
                      float* dA, int B, int HW, int f, void* stream) {
   ACNN_REQUIRE(dv && y && scale && shift && dA && cg_ok(f), "sk_bwd_gate: bad arguments");
-  image_reduce_kernel<1><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)dv,
+  const int splits = image_splits(B, HW, f);
+  if (splits > 1) {
+    cudaError_t e = cudaMemsetAsync(dA, 0, (size_t)B * f * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      set_error("sk_bwd_gate memset: %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
+    }
+  }
+  image_reduce_kernel<1><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)dv,
                                                              scale, shift, dA, HW, f);
   count_launch();
   return check_launch("sk_bwd_gate");
@@ -546,7 +581,15 @@ int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const fl
 int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q, int B, int HW,
                 int C, void* stream) {
   ACNN_REQUIRE(y && scale && shift && q && cg_ok(C), "se_gap: bad arguments");
-  image_reduce_kernel<2><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
+  const int splits = image_splits(B, HW, C);
+  if (splits > 1) {
+    cudaError_t e = cudaMemsetAsync(q, 0, (size_t)B * C * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      set_error("se_gap memset: %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
+    }
+  }
+  image_reduce_kernel<2><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
                                                              q, HW, C);
   count_launch();
   return check_launch("se_gap");
@@ -555,7 +598,15 @@ int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q,
 int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const float* shift,
                      float* de, int B, int HW, int C, void* stream) {
   ACNN_REQUIRE(g && y && scale && shift && de && cg_ok(C), "se_bwd_gate: bad arguments");
-  image_reduce_kernel<3><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)g, scale,
+  const int splits = image_splits(B, HW, C);
+  if (splits > 1) {
+    cudaError_t e = cudaMemsetAsync(de, 0, (size_t)B * C * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      set_error("se_bwd_gate memset: %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
+    }
+  }
+  image_reduce_kernel<3><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)g, scale,
                                                              shift, de, HW, C);
   count_launch();
   return check_launch("se_bwd_gate");

@@ -235,8 +235,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint64_t aux_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float red_sum[4][BN];
-  __shared__ float red_sq[4][BN];
+  __shared__ float red_sum[1024];   // [row groups][BN] partial column sums (kernel end only)
+  __shared__ float red_sq[1024];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -400,9 +400,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool leader = (warp == 2 && lane == 0);
     const bool stats = p.ch_sum != nullptr;
     const int swz = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
-    float col_s[BN / 32], col_q[BN / 32];
+    // batch-norm statistics: thread t owns the 8 columns of 16-byte chunk `st_chunk` over the
+    // rows st_rg, st_rg + kNRg, ... of every tile (read back from the staged bf16 tile)
+    constexpr int kNChunk = BN / 8;
+    constexpr int kNRg = kBM / kNChunk;
+    const int st_t = threadIdx.x - 64;
+    const int st_chunk = st_t % kNChunk, st_rg = st_t / kNChunk;
+    float acc_s[8], acc_q[8];
 #pragma unroll
-    for (int c = 0; c < BN / 32; ++c) col_s[c] = col_q[c] = 0.f;
+    for (int e = 0; e < 8; ++e) acc_s[e] = acc_q[e] = 0.f;
 
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = (m_first + it * m_step) * kBM;
@@ -488,21 +494,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int q = 0; q < 4; ++q)
             *reinterpret_cast<uint4*>(s_out + soff + (((j0 + q) ^ swz) << 4)) =
                 make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-          if (stats) {
-            // statistics of the tensor as stored (bf16-rounded); rows past M contribute zero
-            float s1[32], s2[32];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float lo = row_ok ? __uint_as_float(pk[i] << 16) : 0.f;
-              const float hi = row_ok ? __uint_as_float(pk[i] & 0xffff0000u) : 0.f;
-              s1[2 * i] = lo;
-              s1[2 * i + 1] = hi;
-              s2[2 * i] = lo * lo;
-              s2[2 * i + 1] = hi * hi;
-            }
-            col_s[c] += warp_transpose_sum(s1, lane);
-            col_q[c] += warp_transpose_sum(s2, lane);
-          }
         }
       }
       // accumulator drained (and staging written): hand TMEM back, then store the tile
@@ -518,21 +509,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tma_store_commit();
         }
       }
+      if (stats) {
+        // column sums of the tile as stored (bf16-rounded); rows past M were computed from
+        // zero-filled operands and contribute zero.  Overlaps the TMA store (both only read).
+        const int sub = st_chunk / (kSubW / 8), jj = st_chunk % (kSubW / 8);
+#pragma unroll 4
+        for (int i = 0; i < kNChunk; ++i) {
+          const int rr = st_rg + i * kNRg;
+          const int sw = (kRowBytes == 128) ? (rr & 7) : ((rr >> 1) & 3);
+          const uint4 u = *reinterpret_cast<const uint4*>(s_out + sub * kSubBytes +
+                                                          rr * kRowBytes + ((jj ^ sw) << 4));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(w4[e] << 16);
+            const float hi = __uint_as_float(w4[e] & 0xffff0000u);
+            acc_s[2 * e] += lo;
+            acc_q[2 * e] = fmaf(lo, lo, acc_q[2 * e]);
+            acc_s[2 * e + 1] += hi;
+            acc_q[2 * e + 1] = fmaf(hi, hi, acc_q[2 * e + 1]);
+          }
+        }
+      }
     }
     if (leader && !p.out_f32) tma_store_wait_all();
     if (stats && my_tiles > 0) {
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        red_sum[quarter][c * 32 + lane] = col_s[c];
-        red_sq[quarter][c * 32 + lane] = col_q[c];
+      for (int e = 0; e < 8; ++e) {
+        red_sum[st_rg * BN + st_chunk * 8 + e] = acc_s[e];
+        red_sq[st_rg * BN + st_chunk * 8 + e] = acc_q[e];
       }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      const int t = threadIdx.x - 64;  // 0..127
-      for (int col = t; col < BN; col += 128) {
-        const float s = red_sum[0][col] + red_sum[1][col] + red_sum[2][col] + red_sum[3][col];
-        const float q = red_sq[0][col] + red_sq[1][col] + red_sq[2][col] + red_sq[3][col];
-        atomicAdd(p.ch_sum + n0 + col, s);
-        atomicAdd(p.ch_sumsq + n0 + col, q);
+      for (int col = st_t; col < BN; col += 128) {
+        float ss = 0.f, qq = 0.f;
+        for (int g2 = 0; g2 < kNRg; ++g2) {
+          ss += red_sum[g2 * BN + col];
+          qq += red_sq[g2 * BN + col];
+        }
+        atomicAdd(p.ch_sum + n0 + col, ss);
+        atomicAdd(p.ch_sumsq + n0 + col, qq);
       }
     }
   }
