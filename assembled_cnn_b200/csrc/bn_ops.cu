@@ -49,15 +49,22 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
               const float* __restrict__ gate, int relu, bf16* __restrict__ out, int H, int W, int C,
               int64_t nvec) {
   const int CG = C >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  // CG divides the grid stride (a power of two <= 256 dividing 256*gridDim): the 8-channel group
+  // of a thread never changes, so its coefficients are loaded once
+  const int cg = (int)(i0 % CG);
+  const int c0 = cg << 3;
+  float s[8], h[8], s2[8], h2[8];
+  loadf8(sa + c0, s);
+  loadf8(ha + c0, h);
+  if (b_mode == 1) {
+    loadf8(sb + c0, s2);
+    loadf8(hb + c0, h2);
+  }
+  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t pix = i / CG;
-    const int c0 = cg << 3;
-    float v[8], s[8], h[8];
+    float v[8];
     load8(a + i * 8, v);
-    loadf8(sa + c0, s);
-    loadf8(ha + c0, h);
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], s[k], h[k]);
     if (gate) {
@@ -70,10 +77,8 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
     if (b_mode == 1) {
       float r[8];
       load8(b + i * 8, r);
-      loadf8(sb + c0, s);
-      loadf8(hb + c0, h);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s[k], h[k]);
+      for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s2[k], h2[k]);
     } else if (b_mode == 2) {
       float r[8];
       load8(b + i * 8, r);
@@ -124,7 +129,7 @@ __device__ __forceinline__ void block_reduce_atomic(float (&acc)[NACC][8], int C
   }
 }
 
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 4)
 bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gate, const float* __restrict__ addbc,
@@ -140,12 +145,12 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
   float acc[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
-  // 4 rows per trip: 8 independent 16-byte loads in flight per thread
+  // 2 rows per trip: 4 independent 16-byte loads in flight per thread, 4 CTAs per SM
   const int64_t step = (int64_t)gridDim.x * RPB;
-  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 4 * step) {
-    float gv[4][8], yv[4][8];
+  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 2 * step) {
+    float gv[2][8], yv[2][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       const int64_t r = r0 + u * step;
       if (r < M) {
         load8(g + r * C + c0, gv[u]);
@@ -156,7 +161,7 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       const int64_t r = r0 + u * step;
       if ((gate || addbc) && r < M) {
         const int64_t bimg = r / HW;
@@ -207,16 +212,17 @@ bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
                     const float* __restrict__ addbc, bf16* __restrict__ dy, int HW, int C,
                     int64_t nvec) {
   const int CG = C >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const int c0 = cg << 3;
-    float gv[8], yv[8], k1[8], k2[8], k3[8];
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int cg = (int)(i0 % CG);           // loop-invariant (see bn_act_kernel)
+  const int c0 = cg << 3;
+  float k1[8], k2[8], k3[8];
+  loadf8(coef + c0, k1);
+  loadf8(coef + C + c0, k2);
+  loadf8(coef + 2 * C + c0, k3);
+  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float gv[8], yv[8];
     load8(g + i * 8, gv);
     load8(y + i * 8, yv);
-    loadf8(coef + c0, k1);
-    loadf8(coef + C + c0, k2);
-    loadf8(coef + 2 * C + c0, k3);
     if (gate || addbc) {
       const int64_t bimg = (i / CG) / HW;
       if (gate) {
@@ -338,19 +344,20 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ att,
                   bf16* __restrict__ v, int HW, int f, int64_t nvec) {
   const int CG = f >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int cg = (int)(i0 % CG);           // loop-invariant (see bn_act_kernel)
+  const int c0 = cg << 3;
+  float s0[8], h0[8], s1[8], h1[8];
+  loadf8(scale + c0, s0);
+  loadf8(shift + c0, h0);
+  loadf8(scale + f + c0, s1);
+  loadf8(shift + f + c0, h1);
+  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = i / CG;
     const int64_t b = row / HW;
-    const int c0 = cg << 3;
-    float y0[8], y1[8], s0[8], h0[8], s1[8], h1[8], a[8], o[8];
+    float y0[8], y1[8], a[8], o[8];
     load8(y + row * 2 * f + c0, y0);
     load8(y + row * 2 * f + f + c0, y1);
-    loadf8(scale + c0, s0);
-    loadf8(shift + c0, h0);
-    loadf8(scale + f + c0, s1);
-    loadf8(shift + f + c0, h1);
     loadf8(att + b * f + c0, a);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -362,55 +369,66 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
   }
 }
 
-__global__ void __launch_bounds__(kT)
+// The 2f channels of the SK conv output are handled as one 2f-wide tensor whose gradient is
+// computed on the fly: g = (a_h * dv + ds/HW) * [u > 0], a_0 = att, a_1 = 1 - att.  One thread =
+// 8 channels of ONE half (few live coefficient registers -> 4 CTAs per SM).
+__global__ void __launch_bounds__(kT, 4)
 sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ att, const float* __restrict__ ds, float* sums,
                         int64_t M, int HW, int f) {
-  const int CG = f >> 3;
-  const int RPB = kT / CG;
-  const int cg = threadIdx.x % CG;
-  const int rsub = threadIdx.x / CG;
-  const int c0 = cg << 3;
-  float s0[8], h0[8], s1[8], h1[8], m0[8], r0[8], m1[8], r1[8];
-  loadf8(scale + c0, s0);
-  loadf8(shift + c0, h0);
-  loadf8(scale + f + c0, s1);
-  loadf8(shift + f + c0, h1);
-  loadf8(mean + c0, m0);
-  loadf8(rstd + c0, r0);
-  loadf8(mean + f + c0, m1);
-  loadf8(rstd + f + c0, r1);
+  const int C2 = 2 * f;
+  const int CG2 = C2 >> 3;
+  const int RPB = kT / CG2;
+  const int cg2 = threadIdx.x % CG2;
+  const int rsub = threadIdx.x / CG2;
+  const bool second = cg2 >= (CG2 >> 1);
+  const int cb = (cg2 % (CG2 >> 1)) << 3;      // channel inside the half
+  const int c0 = cg2 << 3;                      // channel inside the 2f-wide tensor
+  float sc[8], sh[8], mu[8], rs[8];
+  loadf8(scale + c0, sc);
+  loadf8(shift + c0, sh);
+  loadf8(mean + c0, mu);
+  loadf8(rstd + c0, rs);
   const float inv_hw = 1.f / HW;
-  float acc[4][8];
+  float acc[2][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
+  const int64_t step = (int64_t)gridDim.x * RPB;
+  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 2 * step) {
+    float yv[2][8], d[2][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[a][i] = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * RPB + rsub; r < M; r += (int64_t)gridDim.x * RPB) {
-    const int64_t b = r / HW;
-    float y0[8], y1[8], d[8], a[8], sgrad[8];
-    load8(y + r * 2 * f + c0, y0);
-    load8(y + r * 2 * f + f + c0, y1);
-    load8(dv + r * f + c0, d);
-    loadf8(att + b * f + c0, a);
-    loadf8(ds + b * f + c0, sgrad);
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * step;
+      if (r < M) {
+        load8(y + r * C2 + c0, yv[u]);
+        load8(dv + r * f + cb, d[u]);
+      } else {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float t0 = fmaf(y0[i], s0[i], h0[i]);
-      const float t1 = fmaf(y1[i], s1[i], h1[i]);
-      const float g0 = t0 > 0.f ? fmaf(a[i], d[i], sgrad[i] * inv_hw) : 0.f;
-      const float g1 = t1 > 0.f ? fmaf(1.f - a[i], d[i], sgrad[i] * inv_hw) : 0.f;
-      acc[0][i] += g0;
-      acc[1][i] += g1;
-      acc[2][i] += g0 * ((y0[i] - m0[i]) * r0[i]);
-      acc[3][i] += g1 * ((y1[i] - m1[i]) * r1[i]);
+        for (int i = 0; i < 8; ++i) yv[u][i] = d[u][i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t r = r0 + u * step;
+      if (r < M) {
+        const int64_t b = r / HW;
+        float a[8], sg[8];
+        loadf8(att + b * f + cb, a);
+        loadf8(ds + b * f + cb, sg);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = fmaf(yv[u][i], sc[i], sh[i]);
+          const float ah = second ? 1.f - a[i] : a[i];
+          const float g = t > 0.f ? fmaf(ah, d[u][i], sg[i] * inv_hw) : 0.f;
+          acc[0][i] += g;
+          acc[1][i] += g * ((yv[u][i] - mu[i]) * rs[i]);
+        }
+      }
     }
   }
-  // acc 0/1: sum g (halves 0/1); acc 2/3: sum g*xhat.  sums layout [S1: 2f][S2: 2f]
-  block_reduce_atomic<4>(acc, CG, sums,
-                         [f](int a, int c) { return (a >> 1) * 2 * f + (a & 1) * f + c; });
+  block_reduce_atomic<2>(acc, CG2, sums, [C2](int a, int c) { return a * C2 + c; });
 }
 
 __global__ void __launch_bounds__(kT)
@@ -419,45 +437,36 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                        const float* __restrict__ att, const float* __restrict__ ds,
                        const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f,
                        int64_t nvec) {
-  const int CG = f >> 3;
   const int C2 = 2 * f;
+  const int CG2 = C2 >> 3;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int cg2 = (int)(i0 % CG2);         // loop-invariant (see bn_act_kernel)
+  const bool second = cg2 >= (CG2 >> 1);
+  const int cb = (cg2 % (CG2 >> 1)) << 3;
+  const int c0 = cg2 << 3;
+  float sc[8], sh[8], k1[8], k2[8], k3[8];
+  loadf8(scale + c0, sc);
+  loadf8(shift + c0, sh);
+  loadf8(coef + c0, k1);
+  loadf8(coef + C2 + c0, k2);
+  loadf8(coef + 2 * C2 + c0, k3);
   const float inv_hw = 1.f / HW;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const int64_t row = i / CG;
+  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / CG2;
     const int64_t b = row / HW;
-    const int c0 = cg << 3;
-    float y0[8], y1[8], d[8], a[8], sgrad[8];
-    load8(y + row * C2 + c0, y0);
-    load8(y + row * C2 + f + c0, y1);
-    load8(dv + row * f + c0, d);
-    loadf8(att + b * f + c0, a);
-    loadf8(ds + b * f + c0, sgrad);
-    float s0[8], h0[8], s1[8], h1[8];
-    loadf8(scale + c0, s0);
-    loadf8(shift + c0, h0);
-    loadf8(scale + f + c0, s1);
-    loadf8(shift + f + c0, h1);
-    float k1a[8], k2a[8], k3a[8], k1b[8], k2b[8], k3b[8];
-    loadf8(coef + c0, k1a);
-    loadf8(coef + C2 + c0, k2a);
-    loadf8(coef + 2 * C2 + c0, k3a);
-    loadf8(coef + f + c0, k1b);
-    loadf8(coef + C2 + f + c0, k2b);
-    loadf8(coef + 2 * C2 + f + c0, k3b);
-    float o0[8], o1[8];
+    float yv[8], d[8], a[8], sg[8], o[8];
+    load8(y + row * C2 + c0, yv);
+    load8(dv + row * f + cb, d);
+    loadf8(att + b * f + cb, a);
+    loadf8(ds + b * f + cb, sg);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float t0 = fmaf(y0[k], s0[k], h0[k]);
-      const float t1 = fmaf(y1[k], s1[k], h1[k]);
-      const float g0 = t0 > 0.f ? fmaf(a[k], d[k], sgrad[k] * inv_hw) : 0.f;
-      const float g1 = t1 > 0.f ? fmaf(1.f - a[k], d[k], sgrad[k] * inv_hw) : 0.f;
-      o0[k] = fmaf(k1a[k], g0, fmaf(k2a[k], y0[k], k3a[k]));
-      o1[k] = fmaf(k1b[k], g1, fmaf(k2b[k], y1[k], k3b[k]));
+      const float t = fmaf(yv[k], sc[k], sh[k]);
+      const float ah = second ? 1.f - a[k] : a[k];
+      const float g = t > 0.f ? fmaf(ah, d[k], sg[k] * inv_hw) : 0.f;
+      o[k] = fmaf(k1[k], g, fmaf(k2[k], yv[k], k3[k]));
     }
-    store8(dy + row * C2 + c0, o0);
-    store8(dy + row * C2 + f + c0, o1);
+    store8(dy + row * C2 + c0, o);
   }
 }
 
@@ -633,10 +642,10 @@ int acnn_sk_combine(const void* y, const float* scale, const float* shift, const
 int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, const float* shift,
                           const float* mean, const float* rstd, const float* att, const float* ds,
                           float* sums, int B, int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && sums && cg_ok(f),
+  ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && sums && cg_ok(2 * f),
                "sk_bn_bwd_reduce: bad arguments");
   const int64_t M = (int64_t)B * HW;
-  const int rpb = kT / (f >> 3);
+  const int rpb = kT / (f >> 2);
   sk_bn_bwd_reduce_kernel<<<grid_for(ceil_div64(M, rpb), 1, 148 * 4), kT, 0,
                             (cudaStream_t)stream>>>((const bf16*)dv, (const bf16*)y, scale, shift,
                                                     mean, rstd, att, ds, sums, M, HW, f);
@@ -647,9 +656,9 @@ int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, con
 int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, const float* shift,
                          const float* att, const float* ds, const float* coef, void* dy, int B,
                          int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && f % 8 == 0,
+  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && cg_ok(2 * f),
                "sk_bn_bwd_apply: bad arguments");
-  const int64_t nvec = (int64_t)B * HW * f / 8;
+  const int64_t nvec = (int64_t)B * HW * f / 4;
   sk_bn_bwd_apply_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
       (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f, nvec);
   count_launch();

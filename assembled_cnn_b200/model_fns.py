@@ -278,6 +278,13 @@ class Trainer:
         self.lam2_buf = self.rt.t[m["lam2"]] if "lam2" in m else None
         self._hp_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self._loss_slot = self.rt.slot_view(m["loss"])
+        # input double-buffering: prefetch() copies the NEXT batch host->device on a side stream
+        # while the current step computes; train_step() then takes it with a device-side copy
+        self._copy_stream = torch.cuda.Stream(self.rt.dev)
+        self._staged = None
+        self._consumed = None
+        self._stage_imgs = None
+        self._stage_labs = None
 
     @property
     def input_batch(self):
@@ -307,13 +314,42 @@ class Trainer:
         rt.run_forward()
         rt.run(rt.plan.backward)
 
-    def train_step(self, images, labels, lam1=None, lam2=None):
-        """images fp32 [input_batch,H,W,3] and int32 labels [input_batch] (pinned host or device).
+    def prefetch(self, images, labels):
+        """Start the host->device copy of the next step's inputs (pinned host tensors) on a side
+        stream; the following train_step(None, None) consumes them.  Lets the PCIe transfer of
+        step i+1 overlap the compute of step i."""
+        if self._stage_imgs is None:
+            self._stage_imgs = torch.empty_like(self.images_buf)
+            self._stage_labs = torch.empty_like(self.labels_buf)
+        cs = self._copy_stream
+        # the staging buffers may still be read by the previous step's device-side copy (and only
+        # by that: waiting for the whole main stream would serialise the transfer behind the step)
+        if self._consumed is not None:
+            cs.wait_event(self._consumed)
+        with torch.cuda.stream(cs):
+            self._stage_imgs.copy_(images, non_blocking=True)
+            self._stage_labs.copy_(labels, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._staged = ev
+
+    def train_step(self, images=None, labels=None, lam1=None, lam2=None):
+        """images fp32 [input_batch,H,W,3] and int32 labels [input_batch] (pinned host or device),
+        or None to consume the batch given to prefetch().
         Returns the device tensor [cross_entropy, l2_loss] of this replica (read it with
         .tolist() -- that read is the only host sync of the step)."""
         rt = self.rt
+        if images is None:
+            if self._staged is None:
+                raise ValueError("train_step() without inputs needs a preceding prefetch()")
+            torch.cuda.current_stream(rt.dev).wait_event(self._staged)
+            self._staged = None
+            images, labels = self._stage_imgs, self._stage_labs
         self.images_buf.copy_(images, non_blocking=True)
         self.labels_buf.copy_(labels, non_blocking=True)
+        if images is self._stage_imgs:
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream(rt.dev))
         if self.mixup_type:
             n = self.input_batch // 2
             if lam1 is None:
