@@ -61,45 +61,59 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
     loadf8(sb + c0, s2);
     loadf8(hb + c0, h2);
   }
-  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t pix = i / CG;
-    float v[8];
-    load8(a + i * 8, v);
+  // 4 vectors per trip, loads batched ahead of the math (index clamped, store predicated)
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
+    uint4 av[4], bv[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], s[k], h[k]);
-    if (gate) {
-      const int64_t bimg = pix / ((int64_t)H * W);
-      float g[8];
-      loadf8(gate + bimg * C + c0, g);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] *= g[k];
+    for (int u = 0; u < 4; ++u) {
+      int64_t i = ib + u * stride;
+      i = i < nvec ? i : nvec - 1;
+      av[u] = __ldg(reinterpret_cast<const uint4*>(a + i * 8));
+      if (b_mode == 1 || b_mode == 2) {
+        bv[u] = __ldg(reinterpret_cast<const uint4*>(b + i * 8));
+      } else if (b_mode == 3) {
+        const int64_t pix = i / CG;
+        const int w = (int)(pix % W);
+        const int64_t t = pix / W;
+        const int hh = (int)(t % H);
+        const int64_t bimg = t / H;
+        const int64_t src = ((bimg * (H >> 1) + (hh >> 1)) * (W >> 1) + (w >> 1)) * C + c0;
+        bv[u] = __ldg(reinterpret_cast<const uint4*>(b + src));
+      }
     }
-    if (b_mode == 1) {
-      float r[8];
-      load8(b + i * 8, r);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s2[k], h2[k]);
-    } else if (b_mode == 2) {
-      float r[8];
-      load8(b + i * 8, r);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = ib + u * stride;
+      if (i >= nvec) break;
+      float v[8];
+      unpack8(av[u], v);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += r[k];
-    } else if (b_mode == 3) {
-      const int w = (int)(pix % W);
-      const int64_t t = pix / W;
-      const int hh = (int)(t % H);
-      const int64_t bimg = t / H;
-      const int64_t src = ((bimg * (H >> 1) + (hh >> 1)) * (W >> 1) + (w >> 1)) * C + c0;
-      float r[8];
-      load8(b + src, r);
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], s[k], h[k]);
+      if (gate) {
+        const int64_t bimg = (i / CG) / ((int64_t)H * W);
+        float g[8];
+        loadf8(gate + bimg * C + c0, g);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] += r[k];
+        for (int k = 0; k < 8; ++k) v[k] *= g[k];
+      }
+      if (b_mode == 1) {
+        float r[8];
+        unpack8(bv[u], r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s2[k], h2[k]);
+      } else if (b_mode >= 2) {
+        float r[8];
+        unpack8(bv[u], r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += r[k];
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+      store8(out + i * 8, v);
     }
-    if (relu) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
-    }
-    store8(out + i * 8, v);
   }
 }
 
@@ -129,7 +143,7 @@ __device__ __forceinline__ void block_reduce_atomic(float (&acc)[NACC][8], int C
   }
 }
 
-__global__ void __launch_bounds__(kT, 4)
+__global__ void __launch_bounds__(kT, 2)
 bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gate, const float* __restrict__ addbc,
@@ -145,43 +159,45 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
   float acc[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
-  // 2 rows per trip: 4 independent 16-byte loads in flight per thread, 4 CTAs per SM
+  // 4 rows per trip.  The loads are unconditional (row index clamped, contribution zeroed) so
+  // that all 8 of them are issued back to back: 8 x 16 B in flight per thread.
   const int64_t step = (int64_t)gridDim.x * RPB;
-  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 2 * step) {
-    float gv[2][8], yv[2][8];
+  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 4 * step) {
+    uint4 gq[4], yq[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t r = r0 + u * step;
-      if (r < M) {
-        load8(g + r * C + c0, gv[u]);
-        load8(y + r * C + c0, yv[u]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) gv[u][i] = yv[u][i] = 0.f;
-      }
+    for (int u = 0; u < 4; ++u) {
+      int64_t r = r0 + u * step;
+      r = r < M ? r : M - 1;
+      gq[u] = __ldg(reinterpret_cast<const uint4*>(g + r * C + c0));
+      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + r * C + c0));
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int64_t r = r0 + u * step;
-      if ((gate || addbc) && r < M) {
-        const int64_t bimg = r / HW;
+      const float valid = r < M ? 1.f : 0.f;
+      float gv[8], yv[8];
+      unpack8(gq[u], gv);
+      unpack8(yq[u], yv);
+      if (gate || addbc) {
+        const int64_t bimg = (r < M ? r : M - 1) / HW;
         if (gate) {
           float t[8];
           loadf8(gate + bimg * C + c0, t);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gv[u][i] *= t[i];
+          for (int i = 0; i < 8; ++i) gv[i] *= t[i];
         }
         if (addbc) {
           float t[8];
           loadf8(addbc + bimg * C + c0, t);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gv[u][i] += t[i];
+          for (int i = 0; i < 8; ++i) gv[i] += t[i];
         }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        acc[0][i] += gv[u][i];
-        acc[1][i] += gv[u][i] * ((yv[u][i] - mu[i]) * rs[i]);
+        const float gg = gv[i] * valid;
+        acc[0][i] += gg;
+        acc[1][i] += gg * ((yv[i] - mu[i]) * rs[i]);
       }
     }
   }
@@ -219,29 +235,43 @@ bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
   loadf8(coef + c0, k1);
   loadf8(coef + C + c0, k2);
   loadf8(coef + 2 * C + c0, k3);
-  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float gv[8], yv[8];
-    load8(g + i * 8, gv);
-    load8(y + i * 8, yv);
-    if (gate || addbc) {
-      const int64_t bimg = (i / CG) / HW;
-      if (gate) {
-        float t[8];
-        loadf8(gate + bimg * C + c0, t);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
+    uint4 gq[4], yq[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) gv[k] *= t[k];
-      }
-      if (addbc) {
-        float t[8];
-        loadf8(addbc + bimg * C + c0, t);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) gv[k] += t[k];
-      }
+    for (int u = 0; u < 4; ++u) {          // batched loads (index clamped)
+      int64_t i = ib + u * stride;
+      i = i < nvec ? i : nvec - 1;
+      gq[u] = __ldg(reinterpret_cast<const uint4*>(g + i * 8));
+      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + i * 8));
     }
-    float o[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], gv[k], fmaf(k2[k], yv[k], k3[k]));
-    store8(dy + i * 8, o);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = ib + u * stride;
+      if (i >= nvec) break;
+      float gv[8], yv[8];
+      unpack8(gq[u], gv);
+      unpack8(yq[u], yv);
+      if (gate || addbc) {
+        const int64_t bimg = (i / CG) / HW;
+        if (gate) {
+          float t[8];
+          loadf8(gate + bimg * C + c0, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gv[k] *= t[k];
+        }
+        if (addbc) {
+          float t[8];
+          loadf8(addbc + bimg * C + c0, t);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gv[k] += t[k];
+        }
+      }
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], gv[k], fmaf(k2[k], yv[k], k3[k]));
+      store8(dy + i * 8, o);
+    }
   }
 }
 
@@ -284,34 +314,44 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
   const int rows_per = (HW + gridDim.y - 1) / gridDim.y;
   const int r_begin = blockIdx.y * rows_per;
   const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
-  for (int r = r_begin + rsub; r < r_end; r += RPB) {
-    const int64_t row = (int64_t)b * HW + r;
-    if (MODE == 0 || MODE == 1) {
-      float y0[8], y1[8];
-      load8(p0 + row * ldy + c0, y0);
-      load8(p0 + row * ldy + f + c0, y1);
-      float dv[8];
-      if (MODE == 1) load8(p1 + row * f + c0, dv);
+  for (int rb = r_begin + rsub; rb < r_end; rb += 4 * RPB) {
+    uint4 q0[4], q1[4], q2[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
-        const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
-        acc[i] += (MODE == 0) ? (u0 + u1) : dv[i] * (u0 - u1);
+    for (int u = 0; u < 4; ++u) {          // unconditional, batched loads (row clamped)
+      int r = rb + u * RPB;
+      r = r < r_end ? r : r_end - 1;
+      const int64_t row = (int64_t)b * HW + r;
+      q0[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + c0));
+      if (MODE <= 1) q1[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + f + c0));
+      if (MODE == 1 || MODE == 3) q2[u] = __ldg(reinterpret_cast<const uint4*>(p1 + row * f + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float valid = (rb + u * RPB) < r_end ? 1.f : 0.f;
+      float y0[8];
+      unpack8(q0[u], y0);
+      if (MODE == 0 || MODE == 1) {
+        float y1[8], dv[8];
+        unpack8(q1[u], y1);
+        if (MODE == 1) unpack8(q2[u], dv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
+          const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
+          acc[i] += valid * ((MODE == 0) ? (u0 + u1) : dv[i] * (u0 - u1));
+        }
+      } else if (MODE == 2 || MODE == 3) {
+        float gv[8];
+        if (MODE == 3) unpack8(q2[u], gv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = fmaf(y0[i], s0[i], h0[i]);
+          acc[i] += valid * ((MODE == 2) ? t : gv[i] * t);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += valid * y0[i];
       }
-    } else if (MODE == 2 || MODE == 3) {
-      float yv[8], gv[8];
-      load8(p0 + row * ldy + c0, yv);
-      if (MODE == 3) load8(p1 + row * f + c0, gv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float t = fmaf(yv[i], s0[i], h0[i]);
-        acc[i] += (MODE == 2) ? t : gv[i] * t;
-      }
-    } else {
-      float xv[8];
-      load8(p0 + row * ldy + c0, xv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += xv[i];
     }
   }
 #pragma unroll
@@ -352,27 +392,41 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
   loadf8(shift + c0, h0);
   loadf8(scale + f + c0, s1);
   loadf8(shift + f + c0, h1);
-  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / CG;
-    const int64_t b = row / HW;
-    float y0[8], y1[8], a[8], o[8];
-    load8(y + row * 2 * f + c0, y0);
-    load8(y + row * 2 * f + f + c0, y1);
-    loadf8(att + b * f + c0, a);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
+    uint4 q0[4], q1[4];
+    float a[4][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
-      const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
-      o[k] = a[k] * u0 + (1.f - a[k]) * u1;
+    for (int u = 0; u < 4; ++u) {          // batched loads (index clamped)
+      int64_t i = ib + u * stride;
+      i = i < nvec ? i : nvec - 1;
+      const int64_t row = i / CG;
+      q0[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + c0));
+      q1[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + f + c0));
+      loadf8(att + (row / HW) * f + c0, a[u]);
     }
-    store8(v + row * f + c0, o);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = ib + u * stride;
+      if (i >= nvec) break;
+      float y0[8], y1[8], o[8];
+      unpack8(q0[u], y0);
+      unpack8(q1[u], y1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
+        const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
+        o[k] = a[u][k] * u0 + (1.f - a[u][k]) * u1;
+      }
+      store8(v + (i / CG) * f + c0, o);
+    }
   }
 }
 
 // The 2f channels of the SK conv output are handled as one 2f-wide tensor whose gradient is
 // computed on the fly: g = (a_h * dv + ds/HW) * [u > 0], a_0 = att, a_1 = 1 - att.  One thread =
 // 8 channels of ONE half (few live coefficient registers -> 4 CTAs per SM).
-__global__ void __launch_bounds__(kT, 4)
+__global__ void __launch_bounds__(kT, 2)
 sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -396,35 +450,32 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
   const int64_t step = (int64_t)gridDim.x * RPB;
-  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 2 * step) {
-    float yv[2][8], d[2][8];
+  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 4 * step) {
+    uint4 yq[4], dq[4];
+    float a[4][8], sg[4][8];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t r = r0 + u * step;
-      if (r < M) {
-        load8(y + r * C2 + c0, yv[u]);
-        load8(dv + r * f + cb, d[u]);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) yv[u][i] = d[u][i] = 0.f;
-      }
+    for (int u = 0; u < 4; ++u) {          // unconditional, batched loads (index clamped)
+      int64_t r = r0 + u * step;
+      r = r < M ? r : M - 1;
+      const int64_t b = r / HW;
+      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + r * C2 + c0));
+      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + r * f + cb));
+      loadf8(att + b * f + cb, a[u]);
+      loadf8(ds + b * f + cb, sg[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t r = r0 + u * step;
-      if (r < M) {
-        const int64_t b = r / HW;
-        float a[8], sg[8];
-        loadf8(att + b * f + cb, a);
-        loadf8(ds + b * f + cb, sg);
+    for (int u = 0; u < 4; ++u) {
+      const float valid = (r0 + u * step) < M ? 1.f : 0.f;
+      float yv[8], d[8];
+      unpack8(yq[u], yv);
+      unpack8(dq[u], d);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float t = fmaf(yv[u][i], sc[i], sh[i]);
-          const float ah = second ? 1.f - a[i] : a[i];
-          const float g = t > 0.f ? fmaf(ah, d[u][i], sg[i] * inv_hw) : 0.f;
-          acc[0][i] += g;
-          acc[1][i] += g * ((yv[u][i] - mu[i]) * rs[i]);
-        }
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(yv[i], sc[i], sh[i]);
+        const float ah = second ? 1.f - a[u][i] : a[u][i];
+        const float gg = t > 0.f ? valid * fmaf(ah, d[i], sg[u][i] * inv_hw) : 0.f;
+        acc[0][i] += gg;
+        acc[1][i] += gg * ((yv[i] - mu[i]) * rs[i]);
       }
     }
   }
@@ -451,22 +502,37 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
   loadf8(coef + C2 + c0, k2);
   loadf8(coef + 2 * C2 + c0, k3);
   const float inv_hw = 1.f / HW;
-  for (int64_t i = i0; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i / CG2;
-    const int64_t b = row / HW;
-    float yv[8], d[8], a[8], sg[8], o[8];
-    load8(y + row * C2 + c0, yv);
-    load8(dv + row * f + cb, d);
-    loadf8(att + b * f + cb, a);
-    loadf8(ds + b * f + cb, sg);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
+    uint4 yq[4], dq[4];
+    float a[4][8], sg[4][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float t = fmaf(yv[k], sc[k], sh[k]);
-      const float ah = second ? 1.f - a[k] : a[k];
-      const float g = t > 0.f ? fmaf(ah, d[k], sg[k] * inv_hw) : 0.f;
-      o[k] = fmaf(k1[k], g, fmaf(k2[k], yv[k], k3[k]));
+    for (int u = 0; u < 4; ++u) {          // batched loads (index clamped)
+      int64_t i = ib + u * stride;
+      i = i < nvec ? i : nvec - 1;
+      const int64_t row = i / CG2;
+      const int64_t b = row / HW;
+      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + row * C2 + c0));
+      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + row * f + cb));
+      loadf8(att + b * f + cb, a[u]);
+      loadf8(ds + b * f + cb, sg[u]);
     }
-    store8(dy + row * C2 + c0, o);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = ib + u * stride;
+      if (i >= nvec) break;
+      float yv[8], d[8], o[8];
+      unpack8(yq[u], yv);
+      unpack8(dq[u], d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = fmaf(yv[k], sc[k], sh[k]);
+        const float ah = second ? 1.f - a[u][k] : a[u][k];
+        const float g = t > 0.f ? fmaf(ah, d[k], sg[u][k] * inv_hw) : 0.f;
+        o[k] = fmaf(k1[k], g, fmaf(k2[k], yv[k], k3[k]));
+      }
+      store8(dy + (i / CG2) * C2 + c0, o);
+    }
   }
 }
 

@@ -70,12 +70,19 @@ for op, a, b in records:
     if op.kind in ("conv", "conv_dgrad", "conv_wgrad"):
         g = op.geom
         fl = 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
+        nin, nout = g.B * g.H * g.W * g.Cin, g.B * g.Ho * g.Wo * g.Cout
+        byt = 2.0 * (nin + nout)
+        if op.kind == "conv_dgrad":
+            byt += 2.0 * nin * ((op.add_src is not None) + (op.mask_src is not None))
+        ideal = max(fl / 1423.5e9, byt / 6572.9e6)          # ms: tensor vs HBM roofline
         rows.append((ms, op.kind, "%dx%d %d->%d k%d s%d" % (g.H, g.W, g.Cin, g.Cout, g.kh, g.stride),
-                     fl / ms / 1e9))
+                     fl / ms / 1e9, ideal))
 total = sum(v[0] for v in by_kind.values())
 print("total %.2f ms over %d ops" % (total, len(records)))
 for k, (ms, n) in sorted(by_kind.items(), key=lambda kv: -kv[1][0]):
     print("%-20s %4d launches-ops %8.3f ms %5.1f%%" % (k, n, ms, 100 * ms / total))
-print("--- slowest conv GEMM launches (ms, kind, shape, TFLOP/s)")
-for ms, kind, shape, tf in sorted(rows, reverse=True)[:args.top]:
-    print("%7.3f %-11s %-28s %7.1f" % (ms, kind, shape, tf))
+print("conv GEMMs: measured %.2f ms, roofline (max of tensor / HBM per launch) %.2f ms"
+      % (sum(r[0] for r in rows), sum(r[4] for r in rows)))
+print("--- conv GEMM launches by gap to their roofline (ms, ideal ms, kind, shape, TFLOP/s)")
+for ms, kind, shape, tf, ideal in sorted(rows, key=lambda r: r[4] - r[0])[:args.top]:
+    print("%7.3f %7.3f %-11s %-28s %7.1f" % (ms, ideal, kind, shape, tf))
