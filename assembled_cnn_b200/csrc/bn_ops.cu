@@ -310,48 +310,34 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
       loadf8(shift + f + c0, h1);
     }
   }
-  // gridDim.y CTAs share one image: each takes a contiguous slab of rows
-  const int rows_per = (HW + gridDim.y - 1) / gridDim.y;
-  const int r_begin = blockIdx.y * rows_per;
-  const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
-  for (int rb = r_begin + rsub; rb < r_end; rb += 4 * RPB) {
-    uint4 q0[4], q1[4], q2[4];
+  for (int r = rsub; r < HW; r += RPB) {
+    const int64_t row = (int64_t)b * HW + r;
+    if (MODE == 0 || MODE == 1) {
+      float y0[8], y1[8];
+      load8(p0 + row * ldy + c0, y0);
+      load8(p0 + row * ldy + f + c0, y1);
+      float dv[8];
+      if (MODE == 1) load8(p1 + row * f + c0, dv);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {          // unconditional, batched loads (row clamped)
-      int r = rb + u * RPB;
-      r = r < r_end ? r : r_end - 1;
-      const int64_t row = (int64_t)b * HW + r;
-      q0[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + c0));
-      if (MODE <= 1) q1[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + f + c0));
-      if (MODE == 1 || MODE == 3) q2[u] = __ldg(reinterpret_cast<const uint4*>(p1 + row * f + c0));
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float valid = (rb + u * RPB) < r_end ? 1.f : 0.f;
-      float y0[8];
-      unpack8(q0[u], y0);
-      if (MODE == 0 || MODE == 1) {
-        float y1[8], dv[8];
-        unpack8(q1[u], y1);
-        if (MODE == 1) unpack8(q2[u], dv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
-          const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
-          acc[i] += valid * ((MODE == 0) ? (u0 + u1) : dv[i] * (u0 - u1));
-        }
-      } else if (MODE == 2 || MODE == 3) {
-        float gv[8];
-        if (MODE == 3) unpack8(q2[u], gv);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float t = fmaf(y0[i], s0[i], h0[i]);
-          acc[i] += valid * ((MODE == 2) ? t : gv[i] * t);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += valid * y0[i];
+      for (int i = 0; i < 8; ++i) {
+        const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
+        const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
+        acc[i] += (MODE == 0) ? (u0 + u1) : dv[i] * (u0 - u1);
       }
+    } else if (MODE == 2 || MODE == 3) {
+      float yv[8], gv[8];
+      load8(p0 + row * ldy + c0, yv);
+      if (MODE == 3) load8(p1 + row * f + c0, gv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float t = fmaf(yv[i], s0[i], h0[i]);
+        acc[i] += (MODE == 2) ? t : gv[i] * t;
+      }
+    } else {
+      float xv[8];
+      load8(p0 + row * ldy + c0, xv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += xv[i];
     }
   }
 #pragma unroll
@@ -364,15 +350,10 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
     const float norm = (MODE == 0 || MODE == 2 || MODE == 4) ? 1.f / HW : 1.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] *= norm;
-    if (MODE == 4) {
+    if (MODE == 4)
       store8(reinterpret_cast<bf16*>(out) + (int64_t)b * f + c0, acc);
-    } else if (gridDim.y == 1) {
+    else
       storef8(reinterpret_cast<float*>(out) + (int64_t)b * f + c0, acc);
-    } else {
-      float* o = reinterpret_cast<float*>(out) + (int64_t)b * f + c0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(o + i, acc[i]);
-    }
   }
 }
 
@@ -384,42 +365,27 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ att,
                   bf16* __restrict__ v, int HW, int f, int64_t nvec) {
   const int CG = f >> 3;
-  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int cg = (int)(i0 % CG);           // loop-invariant (see bn_act_kernel)
-  const int c0 = cg << 3;
-  float s0[8], h0[8], s1[8], h1[8];
-  loadf8(scale + c0, s0);
-  loadf8(shift + c0, h0);
-  loadf8(scale + f + c0, s1);
-  loadf8(shift + f + c0, h1);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
-    uint4 q0[4], q1[4];
-    float a[4][8];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t row = i / CG;
+    const int64_t b = row / HW;
+    const int c0 = cg << 3;
+    float y0[8], y1[8], s0[8], h0[8], s1[8], h1[8], a[8], o[8];
+    load8(y + row * 2 * f + c0, y0);
+    load8(y + row * 2 * f + f + c0, y1);
+    loadf8(scale + c0, s0);
+    loadf8(shift + c0, h0);
+    loadf8(scale + f + c0, s1);
+    loadf8(shift + f + c0, h1);
+    loadf8(att + b * f + c0, a);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {          // batched loads (index clamped)
-      int64_t i = ib + u * stride;
-      i = i < nvec ? i : nvec - 1;
-      const int64_t row = i / CG;
-      q0[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + c0));
-      q1[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + f + c0));
-      loadf8(att + (row / HW) * f + c0, a[u]);
+    for (int k = 0; k < 8; ++k) {
+      const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
+      const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
+      o[k] = a[k] * u0 + (1.f - a[k]) * u1;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t i = ib + u * stride;
-      if (i >= nvec) break;
-      float y0[8], y1[8], o[8];
-      unpack8(q0[u], y0);
-      unpack8(q1[u], y1);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
-        const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
-        o[k] = a[u][k] * u0 + (1.f - a[u][k]) * u1;
-      }
-      store8(v + (i / CG) * f + c0, o);
-    }
+    store8(v + row * f + c0, o);
   }
 }
 
@@ -488,62 +454,46 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                        const float* __restrict__ att, const float* __restrict__ ds,
                        const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f,
                        int64_t nvec) {
+  const int CG = f >> 3;
   const int C2 = 2 * f;
-  const int CG2 = C2 >> 3;
-  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int cg2 = (int)(i0 % CG2);         // loop-invariant (see bn_act_kernel)
-  const bool second = cg2 >= (CG2 >> 1);
-  const int cb = (cg2 % (CG2 >> 1)) << 3;
-  const int c0 = cg2 << 3;
-  float sc[8], sh[8], k1[8], k2[8], k3[8];
-  loadf8(scale + c0, sc);
-  loadf8(shift + c0, sh);
-  loadf8(coef + c0, k1);
-  loadf8(coef + C2 + c0, k2);
-  loadf8(coef + 2 * C2 + c0, k3);
   const float inv_hw = 1.f / HW;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
-    uint4 yq[4], dq[4];
-    float a[4][8], sg[4][8];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    const int64_t row = i / CG;
+    const int64_t b = row / HW;
+    const int c0 = cg << 3;
+    float y0[8], y1[8], d[8], a[8], sgrad[8];
+    load8(y + row * C2 + c0, y0);
+    load8(y + row * C2 + f + c0, y1);
+    load8(dv + row * f + c0, d);
+    loadf8(att + b * f + c0, a);
+    loadf8(ds + b * f + c0, sgrad);
+    float s0[8], h0[8], s1[8], h1[8];
+    loadf8(scale + c0, s0);
+    loadf8(shift + c0, h0);
+    loadf8(scale + f + c0, s1);
+    loadf8(shift + f + c0, h1);
+    float k1a[8], k2a[8], k3a[8], k1b[8], k2b[8], k3b[8];
+    loadf8(coef + c0, k1a);
+    loadf8(coef + C2 + c0, k2a);
+    loadf8(coef + 2 * C2 + c0, k3a);
+    loadf8(coef + f + c0, k1b);
+    loadf8(coef + C2 + f + c0, k2b);
+    loadf8(coef + 2 * C2 + f + c0, k3b);
+    float o0[8], o1[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {          // batched loads (index clamped)
-      int64_t i = ib + u * stride;
-      i = i < nvec ? i : nvec - 1;
-      const int64_t row = i / CG2;
-      const int64_t b = row / HW;
-      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + row * C2 + c0));
-      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + row * f + cb));
-      loadf8(att + b * f + cb, a[u]);
-      loadf8(ds + b * f + cb, sg[u]);
+    for (int k = 0; k < 8; ++k) {
+      const float t0 = fmaf(y0[k], s0[k], h0[k]);
+      const float t1 = fmaf(y1[k], s1[k], h1[k]);
+      const float g0 = t0 > 0.f ? fmaf(a[k], d[k], sgrad[k] * inv_hw) : 0.f;
+      const float g1 = t1 > 0.f ? fmaf(1.f - a[k], d[k], sgrad[k] * inv_hw) : 0.f;
+      o0[k] = fmaf(k1a[k], g0, fmaf(k2a[k], y0[k], k3a[k]));
+      o1[k] = fmaf(k1b[k], g1, fmaf(k2b[k], y1[k], k3b[k]));
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t i = ib + u * stride;
-      if (i >= nvec) break;
-      float yv[8], d[8], o[8];
-      unpack8(yq[u], yv);
-      unpack8(dq[u], d);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float t = fmaf(yv[k], sc[k], sh[k]);
-        const float ah = second ? 1.f - a[u][k] : a[u][k];
-        const float g = t > 0.f ? fmaf(ah, d[k], sg[u][k] * inv_hw) : 0.f;
-        o[k] = fmaf(k1[k], g, fmaf(k2[k], yv[k], k3[k]));
-      }
-      store8(dy + (i / CG2) * C2 + c0, o);
-    }
+    store8(dy + row * C2 + c0, o0);
+    store8(dy + row * C2 + f + c0, o1);
   }
-}
-
-// CTAs per image for the per-image reductions: enough CTAs to cover the GPU a few times.  With
-// more than one, the (zero-initialised) output is accumulated atomically.
-static int image_splits(int B, int HW, int f) {
-  const int rpb = kT / (f >> 3);
-  int s = (148 * 6 + B - 1) / B;
-  const int max_s = (HW + 2 * rpb - 1) / (2 * rpb);
-  if (s > max_s) s = max_s;
-  return s < 1 ? 1 : s;
 }
 
 static bool cg_ok(int C) {
@@ -622,15 +572,7 @@ int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const flo
 int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s, int B, int HW,
                 int f, void* stream) {
   ACNN_REQUIRE(y && scale && shift && s && cg_ok(f), "sk_gap: bad arguments f=%d", f);
-  const int splits = image_splits(B, HW, f);
-  if (splits > 1) {
-    cudaError_t e = cudaMemsetAsync(s, 0, (size_t)B * f * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) {
-      set_error("sk_gap memset: %s", cudaGetErrorString(e));
-      return ACNN_ERR_CUDA;
-    }
-  }
-  image_reduce_kernel<0><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
+  image_reduce_kernel<0><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
                                                              s, HW, f);
   count_launch();
   return check_launch("sk_gap");
@@ -639,15 +581,7 @@ int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s,
 int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const float* shift,
                      float* dA, int B, int HW, int f, void* stream) {
   ACNN_REQUIRE(dv && y && scale && shift && dA && cg_ok(f), "sk_bwd_gate: bad arguments");
-  const int splits = image_splits(B, HW, f);
-  if (splits > 1) {
-    cudaError_t e = cudaMemsetAsync(dA, 0, (size_t)B * f * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) {
-      set_error("sk_bwd_gate memset: %s", cudaGetErrorString(e));
-      return ACNN_ERR_CUDA;
-    }
-  }
-  image_reduce_kernel<1><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)dv,
+  image_reduce_kernel<1><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)dv,
                                                              scale, shift, dA, HW, f);
   count_launch();
   return check_launch("sk_bwd_gate");
@@ -656,15 +590,7 @@ int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const fl
 int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q, int B, int HW,
                 int C, void* stream) {
   ACNN_REQUIRE(y && scale && shift && q && cg_ok(C), "se_gap: bad arguments");
-  const int splits = image_splits(B, HW, C);
-  if (splits > 1) {
-    cudaError_t e = cudaMemsetAsync(q, 0, (size_t)B * C * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) {
-      set_error("se_gap memset: %s", cudaGetErrorString(e));
-      return ACNN_ERR_CUDA;
-    }
-  }
-  image_reduce_kernel<2><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
+  image_reduce_kernel<2><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
                                                              q, HW, C);
   count_launch();
   return check_launch("se_gap");
@@ -673,15 +599,7 @@ int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q,
 int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const float* shift,
                      float* de, int B, int HW, int C, void* stream) {
   ACNN_REQUIRE(g && y && scale && shift && de && cg_ok(C), "se_bwd_gate: bad arguments");
-  const int splits = image_splits(B, HW, C);
-  if (splits > 1) {
-    cudaError_t e = cudaMemsetAsync(de, 0, (size_t)B * C * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) {
-      set_error("se_bwd_gate memset: %s", cudaGetErrorString(e));
-      return ACNN_ERR_CUDA;
-    }
-  }
-  image_reduce_kernel<3><<<dim3(B, splits), kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)g, scale,
+  image_reduce_kernel<3><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)g, scale,
                                                              shift, de, HW, C);
   count_launch();
   return check_launch("se_bwd_gate");
@@ -722,9 +640,9 @@ int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, con
 int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, const float* shift,
                          const float* att, const float* ds, const float* coef, void* dy, int B,
                          int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && cg_ok(2 * f),
+  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && f % 8 == 0,
                "sk_bn_bwd_apply: bad arguments");
-  const int64_t nvec = (int64_t)B * HW * f / 4;
+  const int64_t nvec = (int64_t)B * HW * f / 8;
   sk_bn_bwd_apply_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
       (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f, nvec);
   count_launch();

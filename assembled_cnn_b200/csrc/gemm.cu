@@ -149,24 +149,27 @@ constexpr int kBM = 128;        // output pixels per CTA tile == UMMA M == TMEM 
 constexpr int kStageK = 64;     // K elements per pipeline stage
 constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
-constexpr int kSmemBudget = 216 * 1024;   // dynamic smem; ~4.5 KiB static comes on top (227 KiB max)
+constexpr int kSmemBudget = 224 * 1024;   // dynamic smem (227 KiB max per CTA, ~0.2 KiB static)
 
 template <int BN>
 struct FpropCfg {
   static constexpr int kABytes = kBM * kStageK * 2;   // 16 KiB
   static constexpr int kBBytes = BN * kStageK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSubW = BN < 64 ? BN : 64;          // staging sub-tile width (TMA box)
-  static constexpr int kTileBytes = kBM * BN * 2;          // one bf16 output / add / mask tile
+  // the epilogue handles the accumulator in column halves of <= 128 (one staging buffer each for
+  // the output, add and mask tiles), so a 128 x 256 tile needs no more staging than 128 x 128
+  static constexpr int kHalfN = BN > 128 ? 128 : BN;
+  static constexpr int kNHalf = BN / kHalfN;
+  static constexpr int kSubW = kHalfN < 64 ? kHalfN : 64;  // staging sub-tile width (TMA box)
+  static constexpr int kTileBytes = kBM * kHalfN * 2;      // one staged half tile (bf16)
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator stages
   // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
-  static int stages_for(int num_kb, bool has_add, bool has_mask, bool out_f32) {
+  static int stages_for(bool has_add, bool has_mask, bool out_f32) {
     const int fixed = 1024 + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
                       (has_mask ? kTileBytes : 0);
     int st = (kSmemBudget - fixed) / kStageBytes;
     if (st > kMaxStages) st = kMaxStages;
     if (st < 2) st = 2;
-    (void)num_kb;
     return st;
   }
   static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32) {
@@ -223,10 +226,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int kChunkBytes = kBM * CW * 2;
   constexpr int kKSteps = CW / 16;             // UMMA K = 16 bf16
   constexpr uint32_t kIdesc = make_idesc_bf16(BN, false, false);
+  constexpr int kHalfN = Cfg::kHalfN;
+  constexpr int kNHalf = Cfg::kNHalf;
   constexpr int kSubW = Cfg::kSubW;
   constexpr int kRowBytes = kSubW * 2;
   constexpr int kSubBytes = kBM * kRowBytes;
-  constexpr int kNSub = BN / kSubW;
+  constexpr int kNSub = kHalfN / kSubW;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[kMaxStages];
@@ -235,8 +240,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint64_t aux_bar;
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float red_sum[1024];   // [row groups][BN] partial column sums (kernel end only)
-  __shared__ float red_sq[1024];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -399,16 +402,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = quarter * 32 + lane;                 // row inside the tile == TMEM lane
     const bool leader = (warp == 2 && lane == 0);
     const bool stats = p.ch_sum != nullptr;
+    const bool has_aux = p.has_add || p.has_mask;
     const int swz = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
-    // batch-norm statistics: thread t owns the 8 columns of 16-byte chunk `st_chunk` over the
-    // rows st_rg, st_rg + kNRg, ... of every tile (read back from the staged bf16 tile)
-    constexpr int kNChunk = BN / 8;
+    // batch-norm statistics: thread t owns the 8 columns of 16-byte chunk `st_chunk` (of every
+    // column half) over the rows st_rg, st_rg + kNRg, ... of every tile, read back from the
+    // staged bf16 tile
+    constexpr int kNChunk = kHalfN / 8;
     constexpr int kNRg = kBM / kNChunk;
     const int st_t = threadIdx.x - 64;
     const int st_chunk = st_t % kNChunk, st_rg = st_t / kNChunk;
-    float acc_s[8], acc_q[8];
+    float acc_s[kNHalf][8], acc_q[kNHalf][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc_s[e] = acc_q[e] = 0.f;
+    for (int hf = 0; hf < kNHalf; ++hf)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc_s[hf][e] = acc_q[hf][e] = 0.f;
+    uint32_t aux_n = 0;                                // completed aux-barrier phases
 
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = (m_first + it * m_step) * kBM;
@@ -416,129 +424,148 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m0 + r;
       const bool row_ok = row < p.M;
-      if (leader) {
-        // the previous tile's TMA store must have finished READING the staging buffer
-        if (!p.out_f32) tma_store_wait_read();
-        if (p.has_add || p.has_mask) {
-          mbar_expect_tx(&aux_bar, (p.has_add ? Cfg::kTileBytes : 0) +
-                                       (p.has_mask ? Cfg::kTileBytes : 0));
 #pragma unroll
-          for (int sub = 0; sub < kNSub; ++sub) {
-            if (p.has_add)
-              tma_load_2d(s_add + sub * kSubBytes, &tmAdd, &aux_bar, n0 + sub * kSubW, m0);
-            if (p.has_mask)
-              tma_load_2d(s_mask + sub * kSubBytes, &tmMask, &aux_bar, n0 + sub * kSubW, m0);
-          }
-        }
-      }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");   // staging buffer free for everyone
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      if (p.has_add || p.has_mask) mbar_wait(&aux_bar, it & 1);
+      for (int hf = 0; hf < kNHalf; ++hf) {
+        const int nh = n0 + hf * kHalfN;               // first output column of this half
+        if (leader) {
+          // the previous TMA store must have finished READING the staging buffer
+          if (!p.out_f32) tma_store_wait_read();
+          if (has_aux) {
+            mbar_expect_tx(&aux_bar, (p.has_add ? Cfg::kTileBytes : 0) +
+                                         (p.has_mask ? Cfg::kTileBytes : 0));
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        const int col0 = n0 + c * 32;
-        const int sub = (c * 32) / kSubW;
-        const int j0 = ((c * 32) % kSubW) / 8;
-        const int soff = sub * kSubBytes + r * kRowBytes;
-        if (p.bias) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col0 + i);
-        }
-        if (p.has_add) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = *reinterpret_cast<const uint4*>(s_add + soff + (((j0 + q) ^ swz) << 4));
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
-              f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+            for (int sub = 0; sub < kNSub; ++sub) {
+              if (p.has_add)
+                tma_load_2d(s_add + sub * kSubBytes, &tmAdd, &aux_bar, nh + sub * kSubW, m0);
+              if (p.has_mask)
+                tma_load_2d(s_mask + sub * kSubBytes, &tmMask, &aux_bar, nh + sub * kSubW, m0);
             }
           }
         }
-        if (p.has_mask) {
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");   // staging buffers free for everyone
+        if (hf == 0) {
+          mbar_wait(&tfull_bar[acc], acc_phase);
+          tc_fence_after();
+        }
+        if (has_aux) {
+          mbar_wait(&aux_bar, aux_n & 1);
+          ++aux_n;
+        }
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
+        for (int c = 0; c < kHalfN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
+                            hf * kHalfN + c * 32, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          const int col0 = nh + c * 32;
+          const int sub = (c * 32) / kSubW;
+          const int j0 = ((c * 32) % kSubW) / 8;
+          const int soff = sub * kSubBytes + r * kRowBytes;
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + col0 + i);
+          }
+          if (p.has_add) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u =
+                  *reinterpret_cast<const uint4*>(s_add + soff + (((j0 + q) ^ swz) << 4));
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
+                f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.has_mask) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u =
+                  *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
+              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float lo = __uint_as_float(w4[e] << 16);
+                const float hi = __uint_as_float(w4[e] & 0xffff0000u);
+                if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
+                if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
+              }
+            }
+          }
+          if (p.out_f32) {
+            if (row_ok) {
+              float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) +
+                                                      static_cast<size_t>(row) * p.Cout + col0);
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                dst[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
+            }
+          } else {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            // stage in the TMA swizzle layout: 16-byte piece j of row r at piece j ^ swz
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(s_out + soff + (((j0 + q) ^ swz) << 4)) =
+                  make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+          }
+        }
+        // half drained and staged: (after the last half) hand TMEM back, then store
+        if (hf == kNHalf - 1) tc_fence_before();
+        if (!p.out_f32) fence_proxy_async();             // generic smem writes -> async proxy
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (leader) {
+          if (hf == kNHalf - 1) mbar_arrive(&tempty_bar[acc]);
+          if (!p.out_f32) {
+#pragma unroll
+            for (int sub = 0; sub < kNSub; ++sub)
+              tma_store_2d(&tmC, s_out + sub * kSubBytes, nh + sub * kSubW, m0);
+            tma_store_commit();
+          }
+        }
+        if (stats) {
+          // column sums of the half tile as stored (bf16-rounded); rows past M were computed
+          // from zero-filled operands and contribute zero.  Overlaps the TMA store (both read).
+          const int sub = st_chunk / (kSubW / 8), jj = st_chunk % (kSubW / 8);
+#pragma unroll 4
+          for (int i = 0; i < kNChunk; ++i) {
+            const int rr = st_rg + i * kNRg;
+            const int sw = (kRowBytes == 128) ? (rr & 7) : ((rr >> 1) & 3);
+            const uint4 u = *reinterpret_cast<const uint4*>(s_out + sub * kSubBytes +
+                                                            rr * kRowBytes + ((jj ^ sw) << 4));
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float lo = __uint_as_float(w4[e] << 16);
               const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-              if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
-              if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
+              acc_s[hf][2 * e] += lo;
+              acc_q[hf][2 * e] = fmaf(lo, lo, acc_q[hf][2 * e]);
+              acc_s[hf][2 * e + 1] += hi;
+              acc_q[hf][2 * e + 1] = fmaf(hi, hi, acc_q[hf][2 * e + 1]);
             }
-          }
-        }
-        if (p.out_f32) {
-          if (row_ok) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) +
-                                                    static_cast<size_t>(row) * p.Cout + col0);
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              dst[q] = make_float4(f[q * 4], f[q * 4 + 1], f[q * 4 + 2], f[q * 4 + 3]);
-          }
-        } else {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-          // stage the tile in the TMA swizzle layout: 16-byte piece j of row r at piece j ^ swz
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(s_out + soff + (((j0 + q) ^ swz) << 4)) =
-                make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
-        }
-      }
-      // accumulator drained (and staging written): hand TMEM back, then store the tile
-      tc_fence_before();
-      if (!p.out_f32) fence_proxy_async();               // generic-proxy smem writes -> async proxy
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      if (leader) {
-        mbar_arrive(&tempty_bar[acc]);
-        if (!p.out_f32) {
-#pragma unroll
-          for (int sub = 0; sub < kNSub; ++sub)
-            tma_store_2d(&tmC, s_out + sub * kSubBytes, n0 + sub * kSubW, m0);
-          tma_store_commit();
-        }
-      }
-      if (stats) {
-        // column sums of the tile as stored (bf16-rounded); rows past M were computed from
-        // zero-filled operands and contribute zero.  Overlaps the TMA store (both only read).
-        const int sub = st_chunk / (kSubW / 8), jj = st_chunk % (kSubW / 8);
-#pragma unroll 4
-        for (int i = 0; i < kNChunk; ++i) {
-          const int rr = st_rg + i * kNRg;
-          const int sw = (kRowBytes == 128) ? (rr & 7) : ((rr >> 1) & 3);
-          const uint4 u = *reinterpret_cast<const uint4*>(s_out + sub * kSubBytes +
-                                                          rr * kRowBytes + ((jj ^ sw) << 4));
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = __uint_as_float(w4[e] << 16);
-            const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-            acc_s[2 * e] += lo;
-            acc_q[2 * e] = fmaf(lo, lo, acc_q[2 * e]);
-            acc_s[2 * e + 1] += hi;
-            acc_q[2 * e + 1] = fmaf(hi, hi, acc_q[2 * e + 1]);
           }
         }
       }
     }
     if (leader && !p.out_f32) tma_store_wait_all();
     if (stats && my_tiles > 0) {
+      // final cross-row-group reduction in the (now idle) output staging buffer
+      float* red_sum = reinterpret_cast<float*>(s_out);
+      float* red_sq = red_sum + kNRg * BN;
+      static_assert(2 * kNRg * BN * 4 <= Cfg::kTileBytes, "staging buffer too small for stats");
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");   // the last TMA store has drained
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        red_sum[st_rg * BN + st_chunk * 8 + e] = acc_s[e];
-        red_sq[st_rg * BN + st_chunk * 8 + e] = acc_q[e];
-      }
+      for (int hf = 0; hf < kNHalf; ++hf)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          red_sum[st_rg * BN + hf * kHalfN + st_chunk * 8 + e] = acc_s[hf][e];
+          red_sq[st_rg * BN + hf * kHalfN + st_chunk * 8 + e] = acc_q[hf][e];
+        }
       asm volatile("bar.sync 1, 128;\n" ::: "memory");
       for (int col = st_t; col < BN; col += 128) {
         float ss = 0.f, qq = 0.f;
@@ -777,7 +804,8 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
   }
   ConvGemmParams q = p;
   const int num_kb = ceil_div(p.Ktot, kStageK);
-  q.stages = Cfg::stages_for(num_kb, p.has_add, p.has_mask, p.out_f32);
+  q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32);
+  (void)num_kb;
   q.m_tiles = ceil_div(p.M, kBM);
   q.n_tiles = p.Cout / BN;
   // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
@@ -850,7 +878,10 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   ACNN_REQUIRE(p.b_sw_bytes == 128 || p.b_sw_bytes == 64 || p.b_sw_bytes == 32,
                "conv: unsupported K=%d", p.Ktot);
 
-  const int bn = (g.Cout % 128 == 0) ? 128 : ((g.Cout % 64 == 0) ? 64 : 32);
+  // N tile: 256 halves the A-operand traffic per FLOP (128 B/clk of smem reads at BN=128 is the
+  // SM's whole shared-memory bandwidth); dense / tiny-M problems keep 128 for more CTAs
+  int bn = (g.Cout % 128 == 0) ? 128 : ((g.Cout % 64 == 0) ? 64 : 32);
+  if (g.Cout % 256 == 0 && !out_f32 && (int64_t)ceil_div(p.M, kBM) * (g.Cout / 256) >= 96) bn = 256;
   ConvMaps tm;
   if (plain) {
     rc = make_map_2d(&tm.a, x, p.M, g.Cin, g.Cin, kBM, cw);
@@ -865,6 +896,7 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   if (!out_f32 && (rc = make_map_2d(&tm.c, y, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
   if (add_src && (rc = make_map_2d(&tm.add, add_src, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
   if (mask_src && (rc = make_map_2d(&tm.mask, mask_src, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
+  if (bn == 256) return dispatch_conv_gemm<256>(cw, !plain, tm, p, stream);
   if (bn == 128) return dispatch_conv_gemm<128>(cw, !plain, tm, p, stream);
   if (bn == 64) return dispatch_conv_gemm<64>(cw, !plain, tm, p, stream);
   return dispatch_conv_gemm<32>(cw, !plain, tm, p, stream);
