@@ -53,6 +53,8 @@ CASES = [
     (2, 16, 16, 64, 128, 1, 2, (0, 0, 0, 0)),       # strided 1x1 projection (rv=1)
     (2, 7, 7, 128, 256, 3, 1, None),       # 7x7 spatial, two N tiles
     (1, 10, 10, 128, 32, 3, 1, None),      # narrow N = 32
+    (8, 40, 40, 64, 256, 3, 1, None),      # 100 M tiles x N = 256: the 128x256 tile, two halves
+    (8, 40, 40, 256, 512, 1, 1, None),     # 1x1, two 256-wide N tiles; dgrad runs N = 256 too
 ]
 
 
