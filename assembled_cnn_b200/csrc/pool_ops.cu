@@ -154,40 +154,39 @@ __device__ __forceinline__ int window_count(int p, int stride, int pad, int k, i
   return hi - lo;
 }
 
+// grid = (ceil(W*C/8 / 256), H, B): no 64-bit index divisions on the hot path
 __global__ void __launch_bounds__(kPT)
 avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                    const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H, int W,
-                   int C, int k, int stride, int pad, int Ho, int Wo, int count_pad, int64_t nvec) {
+                   int C, int k, int stride, int pad, int Ho, int Wo, int count_pad) {
   const int CG = C >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    int64_t t = i / CG;
-    const int iw = (int)(t % W);
-    t /= W;
-    const int ih = (int)(t % H);
-    const int64_t b = t / H;
-    float acc[8];
+  const int idx = blockIdx.x * kPT + threadIdx.x;
+  if (idx >= W * CG) return;
+  const int iw = idx / CG;
+  const int cg = idx - iw * CG;
+  const int ih = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  float acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    int p_hi = (ih + pad) / stride;
-    if (p_hi > Ho - 1) p_hi = Ho - 1;
-    int q_hi = (iw + pad) / stride;
-    if (q_hi > Wo - 1) q_hi = Wo - 1;
-    for (int p = p_hi; p >= 0 && ih + pad - p * stride < k; --p) {
-      for (int q = q_hi; q >= 0 && iw + pad - q * stride < k; --q) {
-        float v[8];
-        load8(dout + ((b * Ho + p) * Wo + q) * C + cg * 8, v);
-        const float inv = count_pad ? 1.f / (k * k)
-                                    : 1.f / (window_count(p, stride, pad, k, H) *
-                                             window_count(q, stride, pad, k, W));
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  int p_hi = (ih + pad) / stride;
+  if (p_hi > Ho - 1) p_hi = Ho - 1;
+  int q_hi = (iw + pad) / stride;
+  if (q_hi > Wo - 1) q_hi = Wo - 1;
+  for (int p = p_hi; p >= 0 && ih + pad - p * stride < k; --p) {
+    for (int q = q_hi; q >= 0 && iw + pad - q * stride < k; --q) {
+      float v[8];
+      load8(dout + ((b * Ho + p) * Wo + q) * C + cg * 8, v);
+      const float inv = count_pad ? 1.f / (k * k)
+                                  : 1.f / (window_count(p, stride, pad, k, H) *
+                                           window_count(q, stride, pad, k, W));
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(inv, v[e], acc[e]);
-      }
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(inv, v[e], acc[e]);
     }
-    grad_epilogue(acc, add_src, mask_src, (size_t)i * 8);
-    store8(dx + i * 8, acc);
   }
+  const size_t off = (((size_t)b * H + ih) * W + iw) * C + cg * 8;
+  grad_epilogue(acc, add_src, mask_src, off);
+  store8(dx + off, acc);
 }
 
 __global__ void __launch_bounds__(kPT)
@@ -553,10 +552,11 @@ int acnn_avgpool_bwd(const void* dout, void* dx, const void* add_src, const void
                      int H, int W, int C, int k, int stride, int pad_lo, int Ho, int Wo,
                      int count_pad, void* stream) {
   ACNN_REQUIRE(dout && dx && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_bwd: bad arguments");
-  const int64_t nvec = (int64_t)B * H * W * C / 8;
-  avgpool_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+  ACNN_REQUIRE(H <= 65535 && B <= 65535, "avgpool_bwd: H / B exceed the grid limits");
+  dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
+  avgpool_bwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
       (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k, stride,
-      pad_lo, Ho, Wo, count_pad, nvec);
+      pad_lo, Ho, Wo, count_pad);
   count_launch();
   return check_launch("avgpool_bwd");
 }

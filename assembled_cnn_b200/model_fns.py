@@ -312,7 +312,7 @@ class Trainer:
     def _fwd_bwd(self):
         rt = self.rt
         rt.run_forward()
-        rt.run(rt.plan.backward)
+        rt.run(rt.plan.backward, overlap_wgrad=True)
 
     def prefetch(self, images, labels):
         """Start the host->device copy of the next step's inputs (pinned host tensors) on a side

@@ -75,6 +75,7 @@ class Runtime:
         raw = bytes((_lib.WeightDesc * len(descs))(*descs)) if descs else b"\0" * 40
         self.descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.dev)
         self.graph = None
+        self._side_stream = None
         self._geom_cache = {}
 
     # ---------------------------------------------------------------- pointers
@@ -175,9 +176,34 @@ class Runtime:
         if rc != 0:
             _lib.check(rc, "op %s" % op.kind)
 
-    def run(self, ops):
+    _SIDE_KINDS = ("conv_wgrad", "s2d_wgrad_unpack")
+
+    def run(self, ops, overlap_wgrad=False):
+        """Enqueue ops in order.  With overlap_wgrad the weight-gradient GEMMs (needed only by
+        the SGD step) go to a second stream: they depend on dy alone, so the tensor-core-bound
+        wgrads run concurrently with the HBM-bound batch-norm / pooling kernels of the dgrad
+        chain.  Works identically under CUDA-graph capture (fork / join through events)."""
+        if not overlap_wgrad:
+            for op in ops:
+                getattr(self, "op_" + op.kind)(op)
+            return
+        main = torch.cuda.current_stream(self.dev)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(self.dev)
+        side = self._side_stream
+        forked = False
         for op in ops:
-            getattr(self, "op_" + op.kind)(op)
+            if op.kind in self._SIDE_KINDS:
+                ev = torch.cuda.Event()
+                ev.record(main)                      # dy (and everything before it) is ready
+                side.wait_event(ev)
+                forked = True
+                with torch.cuda.stream(side):
+                    getattr(self, "op_" + op.kind)(op)
+            else:
+                getattr(self, "op_" + op.kind)(op)
+        if forked:
+            main.wait_stream(side)                   # join before the optimizer
 
     def zero_step_buffers(self):
         st = self.stream
@@ -192,7 +218,7 @@ class Runtime:
     def run_step(self):
         """zero -> forward -> backward -> SGD, all enqueued on the current stream."""
         self.run_forward()
-        self.run(self.plan.backward)
+        self.run(self.plan.backward, overlap_wgrad=True)
         self.run(self.plan.update)
 
     def capture(self, train=True):
