@@ -363,29 +363,49 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
 __global__ void __launch_bounds__(kT)
 sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ att,
-                  bf16* __restrict__ v, int HW, int f, int64_t nvec) {
+                  bf16* __restrict__ v, int HW, int f) {
+  // grid = (row slabs, images): the image and the channel group of a thread are fixed, so the
+  // BN coefficients and the attention weights live in registers for the whole kernel
   const int CG = f >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const int64_t row = i / CG;
-    const int64_t b = row / HW;
-    const int c0 = cg << 3;
-    float y0[8], y1[8], s0[8], h0[8], s1[8], h1[8], a[8], o[8];
-    load8(y + row * 2 * f + c0, y0);
-    load8(y + row * 2 * f + f + c0, y1);
-    loadf8(scale + c0, s0);
-    loadf8(shift + c0, h0);
-    loadf8(scale + f + c0, s1);
-    loadf8(shift + f + c0, h1);
-    loadf8(att + b * f + c0, a);
+  const int RPB = kT / CG;
+  const int cg = threadIdx.x % CG;
+  const int rsub = threadIdx.x / CG;
+  const int c0 = cg << 3;
+  const int64_t b = blockIdx.y;
+  const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rows_per;
+  const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
+  float s0[8], h0[8], s1[8], h1[8], a[8];
+  loadf8(scale + c0, s0);
+  loadf8(shift + c0, h0);
+  loadf8(scale + f + c0, s1);
+  loadf8(shift + f + c0, h1);
+  loadf8(att + b * f + c0, a);
+  for (int rb = r_begin + rsub; rb < r_end; rb += 2 * RPB) {
+    uint4 q0[2], q1[2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
-      const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
-      o[k] = a[k] * u0 + (1.f - a[k]) * u1;
+    for (int u = 0; u < 2; ++u) {          // batched loads (row clamped)
+      int r = rb + u * RPB;
+      r = r < r_end ? r : r_end - 1;
+      const int64_t row = b * HW + r;
+      q0[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + c0));
+      q1[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + f + c0));
     }
-    store8(v + row * f + c0, o);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = rb + u * RPB;
+      if (r >= r_end) break;
+      float y0[8], y1[8], o[8];
+      unpack8(q0[u], y0);
+      unpack8(q1[u], y1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
+        const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
+        o[k] = a[k] * u0 + (1.f - a[k]) * u1;
+      }
+      store8(v + (b * HW + r) * f + c0, o);
+    }
   }
 }
 
@@ -397,7 +417,8 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ att, const float* __restrict__ ds, float* sums,
-                        int64_t M, int HW, int f) {
+                        int HW, int f) {
+  // grid = (row slabs, images); one thread = 8 channels of ONE half of the 2f-wide tensor
   const int C2 = 2 * f;
   const int CG2 = C2 >> 3;
   const int RPB = kT / CG2;
@@ -406,40 +427,46 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
   const bool second = cg2 >= (CG2 >> 1);
   const int cb = (cg2 % (CG2 >> 1)) << 3;      // channel inside the half
   const int c0 = cg2 << 3;                      // channel inside the 2f-wide tensor
-  float sc[8], sh[8], mu[8], rs[8];
+  const int64_t b = blockIdx.y;
+  const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rows_per;
+  const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
+  float sc[8], sh[8], mu[8], rs[8], ah[8], sg[8];
   loadf8(scale + c0, sc);
   loadf8(shift + c0, sh);
   loadf8(mean + c0, mu);
   loadf8(rstd + c0, rs);
+  loadf8(att + b * f + cb, ah);
+  loadf8(ds + b * f + cb, sg);
   const float inv_hw = 1.f / HW;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (second) ah[i] = 1.f - ah[i];
+    sg[i] *= inv_hw;
+  }
   float acc[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
-  const int64_t step = (int64_t)gridDim.x * RPB;
-  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 4 * step) {
+  for (int rb = r_begin + rsub; rb < r_end; rb += 4 * RPB) {
     uint4 yq[4], dq[4];
-    float a[4][8], sg[4][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {          // unconditional, batched loads (index clamped)
-      int64_t r = r0 + u * step;
-      r = r < M ? r : M - 1;
-      const int64_t b = r / HW;
-      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + r * C2 + c0));
-      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + r * f + cb));
-      loadf8(att + b * f + cb, a[u]);
-      loadf8(ds + b * f + cb, sg[u]);
+    for (int u = 0; u < 4; ++u) {          // unconditional, batched loads (row clamped)
+      int r = rb + u * RPB;
+      r = r < r_end ? r : r_end - 1;
+      const int64_t row = b * HW + r;
+      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + row * C2 + c0));
+      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + row * f + cb));
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float valid = (r0 + u * step) < M ? 1.f : 0.f;
+      const float valid = (rb + u * RPB) < r_end ? 1.f : 0.f;
       float yv[8], d[8];
       unpack8(yq[u], yv);
       unpack8(dq[u], d);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float t = fmaf(yv[i], sc[i], sh[i]);
-        const float ah = second ? 1.f - a[u][i] : a[u][i];
-        const float gg = t > 0.f ? valid * fmaf(ah, d[i], sg[u][i] * inv_hw) : 0.f;
+        const float gg = t > 0.f ? valid * fmaf(ah[i], d[i], sg[i]) : 0.f;
         acc[0][i] += gg;
         acc[1][i] += gg * ((yv[i] - mu[i]) * rs[i]);
       }
@@ -448,52 +475,74 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
   block_reduce_atomic<2>(acc, CG2, sums, [C2](int a, int c) { return a * C2 + c; });
 }
 
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 2)
 sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        const float* __restrict__ att, const float* __restrict__ ds,
-                       const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f,
-                       int64_t nvec) {
-  const int CG = f >> 3;
+                       const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f) {
+  // grid = (row slabs, images); one thread = 8 channels of ONE half; everything that depends
+  // only on (image, channel) stays in registers
   const int C2 = 2 * f;
+  const int CG2 = C2 >> 3;
+  const int RPB = kT / CG2;
+  const int cg2 = threadIdx.x % CG2;
+  const int rsub = threadIdx.x / CG2;
+  const bool second = cg2 >= (CG2 >> 1);
+  const int cb = (cg2 % (CG2 >> 1)) << 3;
+  const int c0 = cg2 << 3;
+  const int64_t b = blockIdx.y;
+  const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
+  const int r_begin = blockIdx.x * rows_per;
+  const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
+  float sc[8], sh[8], k1[8], k2[8], k3[8], ah[8], sg[8];
+  loadf8(scale + c0, sc);
+  loadf8(shift + c0, sh);
+  loadf8(coef + c0, k1);
+  loadf8(coef + C2 + c0, k2);
+  loadf8(coef + 2 * C2 + c0, k3);
+  loadf8(att + b * f + cb, ah);
+  loadf8(ds + b * f + cb, sg);
   const float inv_hw = 1.f / HW;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    const int64_t row = i / CG;
-    const int64_t b = row / HW;
-    const int c0 = cg << 3;
-    float y0[8], y1[8], d[8], a[8], sgrad[8];
-    load8(y + row * C2 + c0, y0);
-    load8(y + row * C2 + f + c0, y1);
-    load8(dv + row * f + c0, d);
-    loadf8(att + b * f + c0, a);
-    loadf8(ds + b * f + c0, sgrad);
-    float s0[8], h0[8], s1[8], h1[8];
-    loadf8(scale + c0, s0);
-    loadf8(shift + c0, h0);
-    loadf8(scale + f + c0, s1);
-    loadf8(shift + f + c0, h1);
-    float k1a[8], k2a[8], k3a[8], k1b[8], k2b[8], k3b[8];
-    loadf8(coef + c0, k1a);
-    loadf8(coef + C2 + c0, k2a);
-    loadf8(coef + 2 * C2 + c0, k3a);
-    loadf8(coef + f + c0, k1b);
-    loadf8(coef + C2 + f + c0, k2b);
-    loadf8(coef + 2 * C2 + f + c0, k3b);
-    float o0[8], o1[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float t0 = fmaf(y0[k], s0[k], h0[k]);
-      const float t1 = fmaf(y1[k], s1[k], h1[k]);
-      const float g0 = t0 > 0.f ? fmaf(a[k], d[k], sgrad[k] * inv_hw) : 0.f;
-      const float g1 = t1 > 0.f ? fmaf(1.f - a[k], d[k], sgrad[k] * inv_hw) : 0.f;
-      o0[k] = fmaf(k1a[k], g0, fmaf(k2a[k], y0[k], k3a[k]));
-      o1[k] = fmaf(k1b[k], g1, fmaf(k2b[k], y1[k], k3b[k]));
-    }
-    store8(dy + row * C2 + c0, o0);
-    store8(dy + row * C2 + f + c0, o1);
+  for (int i = 0; i < 8; ++i) {
+    if (second) ah[i] = 1.f - ah[i];
+    sg[i] *= inv_hw;
   }
+  for (int rb = r_begin + rsub; rb < r_end; rb += 4 * RPB) {
+    uint4 yq[4], dq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {          // batched loads (row clamped)
+      int r = rb + u * RPB;
+      r = r < r_end ? r : r_end - 1;
+      const int64_t row = b * HW + r;
+      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + row * C2 + c0));
+      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + row * f + cb));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * RPB;
+      if (r >= r_end) break;
+      float yv[8], d[8], o[8];
+      unpack8(yq[u], yv);
+      unpack8(dq[u], d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float t = fmaf(yv[k], sc[k], sh[k]);
+        const float g = t > 0.f ? fmaf(ah[k], d[k], sg[k]) : 0.f;
+        o[k] = fmaf(k1[k], g, fmaf(k2[k], yv[k], k3[k]));
+      }
+      store8(dy + (b * HW + r) * C2 + c0, o);
+    }
+  }
+}
+
+// Row slabs per image for the image-aligned SK kernels: ~8 CTAs per SM overall, at least 4 trips
+// of the unrolled row loop per CTA.
+static int row_slabs(int B, int HW, int rpb) {
+  int s = (148 * 8 + B - 1) / B;
+  const int max_s = (HW + 4 * rpb - 1) / (4 * rpb);
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
 }
 
 static bool cg_ok(int C) {
@@ -615,10 +664,11 @@ int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, void* stream
 
 int acnn_sk_combine(const void* y, const float* scale, const float* shift, const float* att,
                     void* v, int B, int HW, int f, void* stream) {
-  ACNN_REQUIRE(y && scale && shift && att && v && f % 8 == 0, "sk_combine: bad arguments");
-  const int64_t nvec = (int64_t)B * HW * f / 8;
-  sk_combine_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)y, scale, shift, att, (bf16*)v, HW, f, nvec);
+  ACNN_REQUIRE(y && scale && shift && att && v && cg_ok(f) && B <= 65535,
+               "sk_combine: bad arguments");
+  dim3 grid(row_slabs(B, HW, kT / (f >> 3)), B);
+  sk_combine_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, scale, shift, att,
+                                                           (bf16*)v, HW, f);
   count_launch();
   return check_launch("sk_combine");
 }
@@ -626,13 +676,11 @@ int acnn_sk_combine(const void* y, const float* scale, const float* shift, const
 int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, const float* shift,
                           const float* mean, const float* rstd, const float* att, const float* ds,
                           float* sums, int B, int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && sums && cg_ok(2 * f),
-               "sk_bn_bwd_reduce: bad arguments");
-  const int64_t M = (int64_t)B * HW;
-  const int rpb = kT / (f >> 2);
-  sk_bn_bwd_reduce_kernel<<<grid_for(ceil_div64(M, rpb), 1, 148 * 4), kT, 0,
-                            (cudaStream_t)stream>>>((const bf16*)dv, (const bf16*)y, scale, shift,
-                                                    mean, rstd, att, ds, sums, M, HW, f);
+  ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && sums && cg_ok(2 * f) &&
+                   B <= 65535, "sk_bn_bwd_reduce: bad arguments");
+  dim3 grid(row_slabs(B, HW, kT / (f >> 2)), B);
+  sk_bn_bwd_reduce_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dv, (const bf16*)y, scale, shift, mean, rstd, att, ds, sums, HW, f);
   count_launch();
   return check_launch("sk_bn_bwd_reduce");
 }
@@ -640,11 +688,11 @@ int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, con
 int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, const float* shift,
                          const float* att, const float* ds, const float* coef, void* dy, int B,
                          int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && f % 8 == 0,
+  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && cg_ok(2 * f) && B <= 65535,
                "sk_bn_bwd_apply: bad arguments");
-  const int64_t nvec = (int64_t)B * HW * f / 8;
-  sk_bn_bwd_apply_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f, nvec);
+  dim3 grid(row_slabs(B, HW, kT / (f >> 2)), B);
+  sk_bn_bwd_apply_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f);
   count_launch();
   return check_launch("sk_bn_bwd_apply");
 }

@@ -312,7 +312,9 @@ class Trainer:
     def _fwd_bwd(self):
         rt = self.rt
         rt.run_forward()
-        rt.run(rt.plan.backward, overlap_wgrad=True)
+        # (a second stream for the wgrad GEMMs was measured to give nothing under a CUDA graph:
+        # every kernel already spans the GPU; Runtime.run(..., overlap_wgrad=True) keeps the option)
+        rt.run(rt.plan.backward)
 
     def prefetch(self, images, labels):
         """Start the host->device copy of the next step's inputs (pinned host tensors) on a side

@@ -218,7 +218,7 @@ class Runtime:
     def run_step(self):
         """zero -> forward -> backward -> SGD, all enqueued on the current stream."""
         self.run_forward()
-        self.run(self.plan.backward, overlap_wgrad=True)
+        self.run(self.plan.backward)
         self.run(self.plan.update)
 
     def capture(self, train=True):

@@ -150,6 +150,65 @@ def test_model_fn_cls_modes():
     assert pr.loss is None and pr.predictions["classes"].shape == (4,)
 
 
+def test_assemble_r152_biglittle_step_runs():
+    """BASELINE config 5 topology (Assemble-ResNet-152, bl_alpha=1, bl_beta=2, SK, sconv/3): one
+    training step at a small shape -- 969 trainable tensors, every op of the plan executes."""
+    from assembled_cnn_b200.model_fns import Model, Trainer
+    from assembled_cnn_b200.hparams import params_from_flags
+    flags = dict(resnet_size=152, resnet_version=2, use_sk_block=True, anti_alias_type="sconv",
+                 anti_alias_filter_size=3, bl_alpha=1, bl_beta=2)
+    model = Model(152, num_classes=1001, resnet_version=2, use_sk_block=True,
+                  anti_alias_type="sconv", anti_alias_filter_size=3, bl_alpha=1, bl_beta=2)
+    params = params_from_flags(batch_size=4, mixup_type=1, label_smoothing=0.1, weight_decay=1e-4,
+                               base_learning_rate=0.01, learning_rate_decay_type="fixed", **flags)
+    tr = Trainer(model, params, 64, 64, use_cuda_graph=True)
+    assert len(tr.rt.plan.params) == 969
+    x, lab, _ = _inputs(8, 64, seed=3)
+    l0 = tr.train_step(x, lab).tolist()
+    l1 = tr.train_step(x, lab).tolist()
+    assert all(map(lambda v: v == v and abs(v) < 1e4, l0 + l1))
+    assert torch.isfinite(tr.rt.params).all() and torch.isfinite(tr.rt.grads).all()
+    assert abs(l0[1] - l1[1]) > 0            # the weights (hence the L2 term) moved
+
+
+def test_full_size_step_properties():
+    """BASELINE config 3 at full size (batch 256, 224 x 224, mixup type 1): size-independent
+    properties of one training step: finite loss near ln(1001) for random weights, softmax-CE
+    bias gradient sums to zero, L2 term equals wd/2 * |decayed weights|^2, BN moving means move
+    towards the batch means by exactly (1 - momentum)."""
+    import math
+    from assembled_cnn_b200.model_fns import Model, Trainer
+    from assembled_cnn_b200.hparams import params_from_flags
+    model = Model(50, num_classes=1001, resnet_version=2, use_sk_block=True,
+                  anti_alias_type="sconv", anti_alias_filter_size=3)
+    params = params_from_flags(batch_size=256, mixup_type=1, label_smoothing=0.1, weight_decay=1e-4,
+                               base_learning_rate=0.0, learning_rate_decay_type="fixed", **ASSEMBLE)
+    tr = Trainer(model, params, 224, 224, use_cuda_graph=True)
+    rt = tr.rt
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(512, 224, 224, 3, generator=g) * 64).clamp(-124, 152)
+    lab = torch.randint(1, 1001, (512,), generator=g).int()
+    w_before = rt.params.clone()
+    ce, l2 = tr.train_step(x, lab).tolist()
+    assert abs(ce - math.log(1001)) < 1.5
+    # lr = 0: parameters unchanged, so the L2 term can be recomputed from them
+    assert torch.equal(w_before, rt.params)
+    want = 0.0
+    for n, p in rt.plan.params.items():
+        if p.decay:
+            want += 0.5e-4 * float((rt.pview(n).double() ** 2).sum())
+    assert abs(l2 - want) < 1e-4 * want
+    db = rt.get_tf("resnet_model/dense/bias", rt.grads)
+    assert abs(float(db.double().sum())) < 1e-4
+    assert torch.isfinite(rt.grads).all()
+    # first BN after the stem: moving_mean = (1 - 0.997) * batch_mean (initial value 0)
+    bn0 = rt.plan.bns[0]
+    w = rt.slot_view(bn0.work)
+    mean = w[2 * bn0.C:3 * bn0.C]
+    mm = rt.pview(bn0.mm)
+    assert torch.allclose(mm, mean * (1 - 0.997), rtol=1e-4, atol=1e-6)
+
+
 def test_no_silent_fallback():
     """The product path is the CUDA library: it must be loaded, and ops must count launches."""
     from assembled_cnn_b200 import _lib

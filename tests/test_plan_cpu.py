@@ -121,6 +121,18 @@ def test_bench_model_inventory():
     assert 5.7e9 < macs / 8 < 5.9e9
 
 
+def test_assemble_r152_inventory():
+    """BASELINE config 5: Assemble-ResNet-152 (rv=2, bl_alpha=1, bl_beta=2): SURVEY App. A.3."""
+    cfg = ModelConfig(resnet_size=152, resnet_version=2, use_sk_block=True, anti_alias_type="sconv",
+                      anti_alias_filter_size=3, bl_alpha=1, bl_beta=2)
+    plan = build_plan(cfg, 2, 224, 224, training=True, mixup_type=1)
+    assert len(plan.params) == 969
+    assert sum(torch.Size(p.tf_shape).numel() for p in plan.params.values()) == 117_006_249
+    assert sum(1 for o in plan.forward if o.kind == "conv") == 229 + 1
+    assert sum(1 for o in plan.forward if o.kind == "sk_fc") == 70
+    assert len(plan.bns) == 299
+
+
 def test_flag_validation_errors_match_reference():
     with pytest.raises(ValueError):
         ModelConfig(resnet_version=3).validate()

@@ -87,13 +87,14 @@ def _err(got, ref):
 
 
 def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbose=False):
+    H, W = (HW, HW) if isinstance(HW, int) else HW
     from oracle import model as M, plan_interp as PI
     from assembled_cnn_b200.plan import ModelConfig, build_plan
     from assembled_cnn_b200.runtime import Runtime
 
     cfg = ModelConfig(use_resnet_d=use_resnet_d, **cfg_kw)
-    plan = build_plan(cfg, B, HW, HW, training=training, mixup_type=mix, label_smoothing=0.1)
-    _, vs = M.build(seed=42, input_hw=HW, use_resnet_d=use_resnet_d, **cfg_kw)
+    plan = build_plan(cfg, B, H, W, training=training, mixup_type=mix, label_smoothing=0.1)
+    _, vs = M.build(seed=42, input_hw=64, use_resnet_d=use_resnet_d, **cfg_kw)
     g = torch.Generator().manual_seed(3)
     for n in vs.vars:       # non-trivial BN parameters / statistics
         if n.endswith("gamma"):
@@ -111,7 +112,7 @@ def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbo
     rt.set_hparams(**hp)
     m = plan.meta
     Bin = m["input_batch"]
-    x = (torch.randn(Bin, HW, HW, 3, generator=g) * 64).clamp(-124, 152)
+    x = (torch.randn(Bin, H, W, 3, generator=g) * 64).clamp(-124, 152)
     lab = torch.randint(1, 1001, (Bin,), generator=g).int()
     it.zero_step_buffers()
     rt.zero_step_buffers()
@@ -184,6 +185,13 @@ CONFIGS = {
 def test_train_step_lockstep(name):
     kw, d, mix = CONFIGS[name]
     failures, _ = lockstep(kw, d, B=4, HW=64, mix=mix, training=True)
+    assert not failures, "\n".join(failures[:20])
+
+
+def test_non_square_odd_batch_lockstep():
+    """Ragged shapes: 64 x 96 input, batch 3 (no dimension is a multiple of a tile size)."""
+    kw, d, _ = CONFIGS["assemble_rv2_sk_sconv_mix1"]
+    failures, _ = lockstep(kw, d, B=3, HW=(64, 96), mix=0, training=True)
     assert not failures, "\n".join(failures[:20])
 
 
