@@ -294,9 +294,12 @@ class Trainer:
 
     def _capture(self):
         rt = self.rt
-        # warm-up launch outside capture (cudaFuncSetAttribute, driver entry points, ...)
+        # warm-up launch outside capture (cudaFuncSetAttribute, driver entry points, ...); it is
+        # a real forward/backward, so the BN moving statistics it updated are put back
+        state_backup = rt.state.clone()
         self._fwd_bwd()
         torch.cuda.synchronize()
+        rt.state.copy_(state_backup)
         s = torch.cuda.Stream(rt.dev)
         s.wait_stream(torch.cuda.current_stream(rt.dev))
         graphs = []
