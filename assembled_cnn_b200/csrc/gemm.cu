@@ -147,7 +147,9 @@ struct ConvGemmParams {
 
 constexpr int kBM = 128;        // output pixels per CTA tile == UMMA M == TMEM lanes
 constexpr int kStageK = 64;     // K elements per pipeline stage
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // wgrad kernel: TMA warp + MMA warp + 4 epilogue warps
+constexpr int kConvThreads = 320;      // conv kernel: TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 224 * 1024;   // dynamic smem (227 KiB max per CTA, ~0.2 KiB static)
 
@@ -215,9 +217,10 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 
 // One CTA per SM walks output tiles (fixed N tile, M tiles strided by the grid).  The TMA producer
 // runs ahead across tiles through the smem ring; the MMA issuer alternates between two TMEM
-// accumulators; the 4 epilogue warps drain accumulator i while the tensor core fills i^1.
+// accumulators; the 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks)
+// drain accumulator i while the tensor core fills i^1.
 template <int BN, int CW, bool IM2COL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd,
                  const __grid_constant__ CUtensorMap tmMask, const ConvGemmParams p) {
@@ -397,8 +400,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int quarter = warp & 3;
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+    const int egrp = (warp - 2) >> 2;                  // 0 / 1: even / odd 32-column chunks
     const int r = quarter * 32 + lane;                 // row inside the tile == TMEM lane
     const bool leader = (warp == 2 && lane == 0);
     const bool stats = p.ch_sum != nullptr;
@@ -408,8 +412,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // column half) over the rows st_rg, st_rg + kNRg, ... of every tile, read back from the
     // staged bf16 tile
     constexpr int kNChunk = kHalfN / 8;
-    constexpr int kNRg = kBM / kNChunk;
+    constexpr int kStatThreads = (BN == 32) ? 128 : kEpiThreads;
+    constexpr int kNRg = kStatThreads / kNChunk;       // row groups; kBM / kNRg rows per thread
     const int st_t = threadIdx.x - 64;
+    const bool st_on = st_t < kStatThreads;
     const int st_chunk = st_t % kNChunk, st_rg = st_t / kNChunk;
     float acc_s[kNHalf][8], acc_q[kNHalf][8];
 #pragma unroll
@@ -442,7 +448,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");   // staging buffers free for everyone
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");   // staging buffers free for everyone
         if (hf == 0) {
           mbar_wait(&tfull_bar[acc], acc_phase);
           tc_fence_after();
@@ -452,7 +458,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ++aux_n;
         }
 #pragma unroll
-        for (int c = 0; c < kHalfN / 32; ++c) {
+        for (int c2 = 0; c2 < (kHalfN / 32 + 1) / 2; ++c2) {
+          const int c = c2 * 2 + egrp;                   // this warp group's chunk
+          if (c >= kHalfN / 32) break;                   // warp-uniform
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
                             hf * kHalfN + c * 32, v);
@@ -518,7 +526,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // half drained and staged: (after the last half) hand TMEM back, then store
         if (hf == kNHalf - 1) tc_fence_before();
         if (!p.out_f32) fence_proxy_async();             // generic smem writes -> async proxy
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (leader) {
           if (hf == kNHalf - 1) mbar_arrive(&tempty_bar[acc]);
           if (!p.out_f32) {
@@ -528,12 +536,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_store_commit();
           }
         }
-        if (stats) {
+        if (stats && st_on) {
           // column sums of the half tile as stored (bf16-rounded); rows past M were computed
           // from zero-filled operands and contribute zero.  Overlaps the TMA store (both read).
           const int sub = st_chunk / (kSubW / 8), jj = st_chunk % (kSubW / 8);
 #pragma unroll 4
-          for (int i = 0; i < kNChunk; ++i) {
+          for (int i = 0; i < kBM / kNRg; ++i) {
             const int rr = st_rg + i * kNRg;
             const int sw = (kRowBytes == 128) ? (rr & 7) : ((rr >> 1) & 3);
             const uint4 u = *reinterpret_cast<const uint4*>(s_out + sub * kSubBytes +
@@ -558,16 +566,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* red_sum = reinterpret_cast<float*>(s_out);
       float* red_sq = red_sum + kNRg * BN;
       static_assert(2 * kNRg * BN * 4 <= Cfg::kTileBytes, "staging buffer too small for stats");
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");   // the last TMA store has drained
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // the last TMA store has drained
+      if (st_on) {
 #pragma unroll
-      for (int hf = 0; hf < kNHalf; ++hf)
+        for (int hf = 0; hf < kNHalf; ++hf)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          red_sum[st_rg * BN + hf * kHalfN + st_chunk * 8 + e] = acc_s[hf][e];
-          red_sq[st_rg * BN + hf * kHalfN + st_chunk * 8 + e] = acc_q[hf][e];
-        }
-      asm volatile("bar.sync 1, 128;\n" ::: "memory");
-      for (int col = st_t; col < BN; col += 128) {
+          for (int e = 0; e < 8; ++e) {
+            red_sum[st_rg * BN + hf * kHalfN + st_chunk * 8 + e] = acc_s[hf][e];
+            red_sq[st_rg * BN + hf * kHalfN + st_chunk * 8 + e] = acc_q[hf][e];
+          }
+      }
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      for (int col = st_t; col < BN; col += kEpiThreads) {
         float ss = 0.f, qq = 0.f;
         for (int g2 = 0; g2 < kNRg; ++g2) {
           ss += red_sum[g2 * BN + col];
@@ -814,8 +824,8 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
   if (per_n < 1) per_n = 1;
   if (per_n > q.m_tiles) per_n = q.m_tiles;
   const int grid = per_n * q.n_tiles;
-  kern<<<grid, kThreads, Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32), stream>>>(
-      tm.a, tm.b, tm.c, tm.add, tm.mask, q);
+  kern<<<grid, kConvThreads, Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32),
+         stream>>>(tm.a, tm.b, tm.c, tm.add, tm.mask, q);
   count_launch();
   return check_launch("conv_gemm_kernel");
 }
