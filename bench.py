@@ -281,9 +281,15 @@ def main():
     sampler.start()
     for _ in range(args.warmup):
         dev_step()
-    while sampler.proc is not None and not sampler.lines:      # keep the GPU loaded meanwhile
-        dev_step()
-        sampler.wait_first_sample(0.05)
+    if world == 1:
+        while sampler.proc is not None and not sampler.lines:  # keep the GPU loaded meanwhile
+            dev_step()
+            sampler.wait_first_sample(0.05)
+    else:
+        # every rank must issue the same number of collectives: no data-dependent extra steps
+        sampler.wait_first_sample(3.0)
+        for _ in range(args.warmup):
+            dev_step()
     sampler.mark()
     ms_total = timed(dev_step, args.steps)
     clocks = sampler.stop()
@@ -361,8 +367,9 @@ def conv_roofline(tr, x_dev, y_dev, peaks, ms_step):
             b.record(stream)
             evs.append((a, b, flops))
         setattr(rt, name, wrapped)
-    was = tr.use_graph
+    was, was_world = tr.use_graph, tr.world
     tr.use_graph = False
+    tr.world = 1        # rank 0 only: no collective inside this instrumented step
     try:
         tr.train_step(x_dev, y_dev)          # warm
         evs.clear()
@@ -370,6 +377,7 @@ def conv_roofline(tr, x_dev, y_dev, peaks, ms_step):
         torch.cuda.synchronize()
     finally:
         tr.use_graph = was
+        tr.world = was_world
         for name in ("op_conv", "op_conv_dgrad", "op_conv_wgrad"):
             delattr(rt, name)
     t_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
