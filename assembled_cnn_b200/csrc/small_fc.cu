@@ -218,318 +218,6 @@ static int ew(const float* in, const float* act, float* out, int64_t n, int mode
   return check_launch("ew");
 }
 
-
-// ------------------------------------------------------------------------------------------
-// Fused SK attention kernels (2 launches forward, 2 backward instead of 4+6 and their memsets)
-// ------------------------------------------------------------------------------------------
-constexpr int kJ = 8;            // fc1 output channels per CTA
-constexpr int kMaxRowsPerThread = 4;   // B <= 4 * 256
-
-__device__ __forceinline__ float block_sum_256(float v, float* sh) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  float t = 0.f;
-#pragma unroll
-  for (int w = 0; w < kFT / 32; ++w) t += sh[w];
-  return t;
-}
-
-// zpre[:, j0:j0+8] = s * W1[j0:j0+8, :]^T for ALL batch rows, batch-norm over the batch, ReLU.
-__global__ void __launch_bounds__(kFT)
-sk_fc1_bn_relu_kernel(const float* __restrict__ s, const float* __restrict__ w1,
-                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float* moving_mean, float* moving_var, float momentum, float eps,
-                      int training, float* __restrict__ zpre, float* __restrict__ z,
-                      float* __restrict__ bnstat, int B, int f, int d) {
-  extern __shared__ float wsm[];          // [kJ][f]
-  __shared__ float red[kFT / 32];
-  __shared__ float stat[2][kJ];
-  const int j0 = blockIdx.x * kJ;
-  for (int i = threadIdx.x; i < kJ * f; i += kFT) {
-    const int j = i / f, c = i - j * f;
-    wsm[i] = (j0 + j < d) ? w1[(size_t)(j0 + j) * f + c] : 0.f;
-  }
-  __syncthreads();
-  float zp[kMaxRowsPerThread][kJ];
-  float s1[kJ], s2[kJ];
-#pragma unroll
-  for (int j = 0; j < kJ; ++j) s1[j] = s2[j] = 0.f;
-#pragma unroll
-  for (int rp = 0; rp < kMaxRowsPerThread; ++rp) {
-    const int b = threadIdx.x + rp * kFT;
-#pragma unroll
-    for (int j = 0; j < kJ; ++j) zp[rp][j] = 0.f;
-    if (b < B) {
-      const float4* sr = reinterpret_cast<const float4*>(s + (size_t)b * f);
-      for (int c4 = 0; c4 < f / 4; ++c4) {
-        const float4 v = __ldg(sr + c4);
-#pragma unroll
-        for (int j = 0; j < kJ; ++j) {
-          const float4 w = *reinterpret_cast<const float4*>(wsm + j * f + c4 * 4);
-          zp[rp][j] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, zp[rp][j]))));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) {
-        s1[j] += zp[rp][j];
-        s2[j] += zp[rp][j] * zp[rp][j];
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kJ; ++j) {
-    const float a = block_sum_256(s1[j], red);
-    const float q = block_sum_256(s2[j], red);
-    if (threadIdx.x == 0) {
-      float mean, var;
-      if (training) {
-        mean = a / B;
-        var = fmaxf(q / B - mean * mean, 0.f);
-        if (j0 + j < d) {
-          const float unbiased = var * ((float)B / fmaxf((float)B - 1.f, 1.f));
-          moving_mean[j0 + j] = moving_mean[j0 + j] * momentum + mean * (1.f - momentum);
-          moving_var[j0 + j] = moving_var[j0 + j] * momentum + unbiased * (1.f - momentum);
-        }
-      } else {
-        mean = (j0 + j < d) ? moving_mean[j0 + j] : 0.f;
-        var = (j0 + j < d) ? moving_var[j0 + j] : 1.f;
-      }
-      stat[0][j] = mean;
-      stat[1][j] = rsqrtf(var + eps);
-      if (j0 + j < d) {
-        bnstat[j0 + j] = mean;
-        bnstat[d + j0 + j] = stat[1][j];
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int rp = 0; rp < kMaxRowsPerThread; ++rp) {
-    const int b = threadIdx.x + rp * kFT;
-    if (b < B) {
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) {
-        if (j0 + j < d) {
-          const float sc = gamma[j0 + j] * stat[1][j];
-          zpre[(size_t)b * d + j0 + j] = zp[rp][j];
-          z[(size_t)b * d + j0 + j] =
-              fmaxf(fmaf(zp[rp][j] - stat[0][j], sc, beta[j0 + j]), 0.f);
-        }
-      }
-    }
-  }
-}
-
-// 64x64x16 tile of C = A*B with element functors; fa(m,k), fb(k,n) must be safe for any in-range
-// index.  A_M_CONTIG / B_N_CONTIG pick the load mapping that is coalesced in global memory.
-template <bool A_M_CONTIG, bool B_N_CONTIG, class FA, class FB, class EPI>
-__device__ __forceinline__ void tile_sgemm(int m0, int n0, int M, int N, int K, FA fa, FB fb,
-                                           EPI epi) {
-  __shared__ float As[kTK][kTM + 4];
-  __shared__ float Bs[kTK][kTN + 4];
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += kTK) {
-#pragma unroll
-    for (int e = 0; e < (kTM * kTK) / kFT; ++e) {
-      const int idx = tid + e * kFT;
-      int mm, kk;
-      if (A_M_CONTIG) { mm = idx % kTM; kk = idx / kTM; } else { kk = idx % kTK; mm = idx / kTK; }
-      const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < K) ? fa(m, k) : 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < (kTN * kTK) / kFT; ++e) {
-      const int idx = tid + e * kFT;
-      int nn, kk;
-      if (B_N_CONTIG) { nn = idx % kTN; kk = idx / kTN; } else { kk = idx % kTK; nn = idx / kTK; }
-      const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < N && k < K) ? fb(k, n) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < kTK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < N) epi(m, n, acc[i][j]);
-    }
-  }
-}
-
-// att[b,c] = sigmoid(z[b,:] . (W2[c,:] - W2[c+f,:]))   (2-way softmax == sigmoid of the difference)
-__global__ void __launch_bounds__(kFT)
-sk_fc2_gate_kernel(const float* __restrict__ z, const float* __restrict__ w2,
-                   float* __restrict__ att, int B, int f, int d) {
-  tile_sgemm<false, false>(
-      blockIdx.y * kTM, blockIdx.x * kTN, B, f, d,
-      [=](int m, int k) { return __ldg(z + (size_t)m * d + k); },
-      [=](int k, int n) {
-        return __ldg(w2 + (size_t)n * d + k) - __ldg(w2 + (size_t)(n + f) * d + k);
-      },
-      [=](int m, int n, float v) { att[(size_t)m * f + n] = 1.f / (1.f + expf(-v)); });
-}
-
-// dz[:, j0:j0+8] for ALL batch rows: dz = t * dW2[:, j] with t = att(1-att)dA, dW2 = W2[:f]-W2[f:];
-// ReLU mask; batch-norm backward over the batch -> dzpre (written to `dz`), dgamma/dbeta.
-__global__ void __launch_bounds__(kFT)
-sk_fc_bwd1_kernel(const float* __restrict__ dA, const float* __restrict__ att,
-                  const float* __restrict__ z, const float* __restrict__ zpre,
-                  const float* __restrict__ bnstat, const float* __restrict__ gamma,
-                  const float* __restrict__ w2, float* __restrict__ dz, float* dgamma,
-                  float* dbeta, int B, int f, int d) {
-  extern __shared__ float dws[];          // [f][kJ]
-  __shared__ float red[kFT / 32];
-  __shared__ float stat[2][kJ];
-  const int j0 = blockIdx.x * kJ;
-  for (int i = threadIdx.x; i < f * kJ; i += kFT) {
-    const int c = i / kJ, j = i - c * kJ;
-    dws[i] = (j0 + j < d) ? w2[(size_t)c * d + j0 + j] - w2[(size_t)(c + f) * d + j0 + j] : 0.f;
-  }
-  __syncthreads();
-  float g[kMaxRowsPerThread][kJ];
-  float s1[kJ], s2[kJ];
-#pragma unroll
-  for (int j = 0; j < kJ; ++j) s1[j] = s2[j] = 0.f;
-#pragma unroll
-  for (int rp = 0; rp < kMaxRowsPerThread; ++rp) {
-    const int b = threadIdx.x + rp * kFT;
-#pragma unroll
-    for (int j = 0; j < kJ; ++j) g[rp][j] = 0.f;
-    if (b < B) {
-      const float* ar = att + (size_t)b * f;
-      const float* dr = dA + (size_t)b * f;
-      for (int c = 0; c < f; ++c) {
-        const float a = __ldg(ar + c);
-        const float t = a * (1.f - a) * __ldg(dr + c);
-        const float4 w0 = *reinterpret_cast<const float4*>(dws + c * kJ);
-        const float4 w1v = *reinterpret_cast<const float4*>(dws + c * kJ + 4);
-        g[rp][0] = fmaf(t, w0.x, g[rp][0]);
-        g[rp][1] = fmaf(t, w0.y, g[rp][1]);
-        g[rp][2] = fmaf(t, w0.z, g[rp][2]);
-        g[rp][3] = fmaf(t, w0.w, g[rp][3]);
-        g[rp][4] = fmaf(t, w1v.x, g[rp][4]);
-        g[rp][5] = fmaf(t, w1v.y, g[rp][5]);
-        g[rp][6] = fmaf(t, w1v.z, g[rp][6]);
-        g[rp][7] = fmaf(t, w1v.w, g[rp][7]);
-      }
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) {
-        if (j0 + j < d) {
-          const size_t i = (size_t)b * d + j0 + j;
-          if (!(z[i] > 0.f)) g[rp][j] = 0.f;
-          const float xh = (zpre[i] - bnstat[j0 + j]) * bnstat[d + j0 + j];
-          s1[j] += g[rp][j];
-          s2[j] += g[rp][j] * xh;
-        } else {
-          g[rp][j] = 0.f;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < kJ; ++j) {
-    const float a = block_sum_256(s1[j], red);
-    const float q = block_sum_256(s2[j], red);
-    if (threadIdx.x == 0) {
-      stat[0][j] = a;
-      stat[1][j] = q;
-      if (j0 + j < d) {
-        dgamma[j0 + j] += q;
-        dbeta[j0 + j] += a;
-      }
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int rp = 0; rp < kMaxRowsPerThread; ++rp) {
-    const int b = threadIdx.x + rp * kFT;
-    if (b < B) {
-#pragma unroll
-      for (int j = 0; j < kJ; ++j) {
-        if (j0 + j < d) {
-          const size_t i = (size_t)b * d + j0 + j;
-          const float rstd = bnstat[d + j0 + j];
-          const float xh = (zpre[i] - bnstat[j0 + j]) * rstd;
-          dz[i] = gamma[j0 + j] * rstd * (g[rp][j] - stat[0][j] / B - xh * stat[1][j] / B);
-        }
-      }
-    }
-  }
-}
-
-// Three independent GEMMs in one launch (blockIdx.x enumerates the tiles of all of them):
-//   P1  G[c][j]  = sum_b t[b,c] z[b,j]      -> dW2[c] += G, dW2[c+f] -= G         (f x d, K = B)
-//   P2  dW1[j][c] += sum_b dzpre[b,j] s[b,c]                                        (d x f, K = B)
-//   P3  ds[b][c]  = sum_j dzpre[b,j] W1[j][c]                                       (B x f, K = d)
-__global__ void __launch_bounds__(kFT)
-sk_fc_bwd2_kernel(const float* __restrict__ dA, const float* __restrict__ att,
-                  const float* __restrict__ z, const float* __restrict__ dzpre,
-                  const float* __restrict__ s, const float* __restrict__ w1, float* dw1,
-                  float* dw2, float* __restrict__ ds, int B, int f, int d) {
-  const int tf = (f + kTM - 1) / kTM, td = (d + kTM - 1) / kTM, tb = (B + kTM - 1) / kTM;
-  int t = blockIdx.x;
-  if (t < tf * td) {
-    const int mt = t / td, nt = t % td;
-    tile_sgemm<true, true>(
-        mt * kTM, nt * kTN, f, d, B,
-        [=](int m, int k) {
-          const float a = __ldg(att + (size_t)k * f + m);
-          return a * (1.f - a) * __ldg(dA + (size_t)k * f + m);
-        },
-        [=](int k, int n) { return __ldg(z + (size_t)k * d + n); },
-        [=](int m, int n, float v) {
-          dw2[(size_t)m * d + n] += v;
-          dw2[(size_t)(m + f) * d + n] -= v;
-        });
-    return;
-  }
-  t -= tf * td;
-  if (t < td * tf) {
-    const int mt = t / tf, nt = t % tf;
-    tile_sgemm<true, true>(
-        mt * kTM, nt * kTN, d, f, B,
-        [=](int m, int k) { return __ldg(dzpre + (size_t)k * d + m); },
-        [=](int k, int n) { return __ldg(s + (size_t)k * f + n); },
-        [=](int m, int n, float v) { dw1[(size_t)m * f + n] += v; });
-    return;
-  }
-  t -= td * tf;
-  {
-    const int mt = t / tf, nt = t % tf;
-    if (mt >= tb) return;
-    tile_sgemm<false, true>(
-        mt * kTM, nt * kTN, B, f, d,
-        [=](int m, int k) { return __ldg(dzpre + (size_t)m * d + k); },
-        [=](int k, int n) { return __ldg(w1 + (size_t)k * f + n); },
-        [=](int m, int n, float v) { ds[(size_t)m * f + n] = v; });
-  }
-}
-
 }  // namespace acnn
 
 using namespace acnn;
@@ -542,19 +230,19 @@ int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const fl
                    float* scratch, int B, int f, int d, void* stream) {
   ACNN_REQUIRE(s && w1 && gamma && beta && moving_mean && moving_var && w2 && zpre && bnstat && z &&
                    att && scratch, "sk_fc_fwd: null argument");
-  ACNN_REQUIRE(B <= kMaxRowsPerThread * kFT && f % 4 == 0 && kJ * f * 4 <= 48 * 1024,
-               "sk_fc_fwd: unsupported size B=%d f=%d", B, f);
   cudaStream_t st = (cudaStream_t)stream;
-  sk_fc1_bn_relu_kernel<<<ceil_div(d, kJ), kFT, kJ * f * sizeof(float), st>>>(
-      s, w1, gamma, beta, moving_mean, moving_var, momentum, eps, training, zpre, z, bnstat, B, f,
-      d);
-  count_launch();
-  int rc = check_launch("sk_fc1_bn_relu");
+  // zpre[B,d] = s[B,f] * W1[d,f]^T
+  int rc = sgemm(s, w1, zpre, B, d, f, f, 1, 1, f, true, st);
   if (rc) return rc;
-  dim3 grid(ceil_div(f, kTN), ceil_div(B, kTM));
-  sk_fc2_gate_kernel<<<grid, kFT, 0, st>>>(z, w2, att, B, f, d);
+  bn_batch_relu_fwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(
+      zpre, gamma, beta, moving_mean, moving_var, momentum, eps, training, z, bnstat, B, d);
   count_launch();
-  return check_launch("sk_fc2_gate");
+  if ((rc = check_launch("sk bn_batch_relu_fwd"))) return rc;
+  // a[B,2f] = z[B,d] * W2[2f,d]^T
+  if ((rc = sgemm(z, w2, scratch, B, 2 * f, d, d, 1, 1, d, true, st))) return rc;
+  sk_gate_fwd_kernel<<<(int)ceil_div64((int64_t)B * f, 256), 256, 0, st>>>(scratch, att, B, f);
+  count_launch();
+  return check_launch("sk_gate_fwd");
 }
 
 int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const float* zpre,
@@ -563,20 +251,25 @@ int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const floa
                    float* scratch, int B, int f, int d, void* stream) {
   ACNN_REQUIRE(dA && att && z && zpre && bnstat && gamma && s && w1 && w2 && dw1 && dw2 && dgamma &&
                    dbeta && ds && scratch, "sk_fc_bwd: null argument");
-  ACNN_REQUIRE(B <= kMaxRowsPerThread * kFT && kJ * f * 4 <= 48 * 1024,
-               "sk_fc_bwd: unsupported size B=%d f=%d", B, f);
   cudaStream_t st = (cudaStream_t)stream;
-  float* dz = scratch;                       // [B][d] : gradient w.r.t. the pre-BN fc1 output
-  sk_fc_bwd1_kernel<<<ceil_div(d, kJ), kFT, kJ * f * sizeof(float), st>>>(
-      dA, att, z, zpre, bnstat, gamma, w2, dz, dgamma, dbeta, B, f, d);
+  float* da = scratch;                       // [B][2f]
+  float* dz = scratch + (size_t)B * 2 * f;   // [B][d]
+  sk_gate_bwd_kernel<<<(int)ceil_div64((int64_t)B * f, 256), 256, 0, st>>>(dA, att, da, B, f);
   count_launch();
-  int rc = check_launch("sk_fc_bwd1");
+  int rc = check_launch("sk_gate_bwd");
   if (rc) return rc;
-  const int tf = ceil_div(f, kTM), td = ceil_div(d, kTM), tb = ceil_div(B, kTM);
-  sk_fc_bwd2_kernel<<<2 * tf * td + tb * tf, kFT, 0, st>>>(dA, att, z, dz, s, w1, dw1, dw2, ds, B,
-                                                          f, d);
+  // dW2[2f,d] += da^T[2f,B] * z[B,d]
+  if ((rc = sgemm(da, z, dw2, 2 * f, d, B, 1, 2 * f, d, 1, false, st))) return rc;
+  // dz[B,d] = da[B,2f] * W2[2f,d]
+  if ((rc = sgemm(da, w2, dz, B, d, 2 * f, 2 * f, 1, d, 1, true, st))) return rc;
+  bn_batch_relu_bwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(dz, z, zpre, bnstat, gamma,
+                                                                  dgamma, dbeta, B, d);
   count_launch();
-  return check_launch("sk_fc_bwd2");
+  if ((rc = check_launch("sk bn_batch_relu_bwd"))) return rc;
+  // dW1[d,f] += dzpre^T[d,B] * s[B,f]
+  if ((rc = sgemm(dz, s, dw1, d, f, B, 1, d, f, 1, false, st))) return rc;
+  // ds[B,f] = dzpre[B,d] * W1[d,f]
+  return sgemm(dz, w1, ds, B, f, d, d, 1, f, 1, true, st);
 }
 
 int acnn_se_fc_fwd(const float* q, const float* w1, const float* w2, float* h, float* e, int B,
