@@ -137,7 +137,6 @@ struct ConvGemmParams {
   int b_sw_bytes; // swizzle span of the weight tile (128 unless Ktot < 64)
   int stages;     // smem pipeline depth
   int m_tiles, n_tiles;
-  int cluster;    // CTAs per cluster sharing one weight tile by TMA multicast (1 = no cluster)
   void* y;
   float* ch_sum;
   float* ch_sumsq;
@@ -255,21 +254,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.Ktot + kStageK - 1) / kStageK;
-  // static tile schedule: a cluster of CS CTAs owns N tile n_tile and the groups of CS consecutive
-  // M tiles g_first, g_first + g_step, ...; CTA `crank` of the cluster takes M tile g * CS + crank.
-  // All CTAs of a cluster walk the same number of tiles and k-blocks in lockstep: each loads
-  // 1/CS of every weight stage and multicasts it to the whole cluster.
-  const int CS = p.cluster;
-  const int crank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const uint16_t cmask = static_cast<uint16_t>((1u << CS) - 1);
-  const int cl = blockIdx.x / CS;
-  const int n_tile = cl % p.n_tiles;
-  const int g_first = cl / p.n_tiles;
-  const int g_step = (gridDim.x / CS) / p.n_tiles;
-  const int g_total = p.m_tiles / CS;                 // host guarantees m_tiles % CS == 0
+  // static tile schedule: this CTA owns N tile n_tile and M tiles m_first, m_first + m_step, ...
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles;
+  const int m_step = gridDim.x / p.n_tiles;
   const int n0 = n_tile * BN;
-  const int my_tiles = g_first < g_total ? (g_total - g_first + g_step - 1) / g_step : 0;
-  auto tile_m0 = [&](int it) { return ((g_first + it * g_step) * CS + crank) * kBM; };
+  const int my_tiles = m_first < p.m_tiles ? (p.m_tiles - m_first + m_step - 1) / m_step : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -279,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.has_mask) tma_prefetch_desc(&tmMask);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CS);      // one MMA commit per CTA that reads this stage's weights
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -292,7 +282,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (CS > 1) cluster_sync_all();        // peers' barriers are initialised before any multicast
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
@@ -303,7 +292,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
     for (int it = 0; it < my_tiles; ++it) {
-      const int m0 = tile_m0(it);
+      const int m0 = (m_first + it * m_step) * kBM;
       int img = 0, h0 = 0, w0 = 0;
       if (IM2COL) {
         img = m0 / p.HoWo;
@@ -342,14 +331,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (++ksn == p.kw) { ksn = 0; ++kr; }
             }
           }
-          if (CS > 1) {
-            // this CTA's slice of the weight tile, delivered to every CTA of the cluster
-            const int rows = BN / CS;
-            tma_load_2d_multicast(sb + crank * rows * 128, &tmB, &full_bar[stage], k0,
-                                  n0 + crank * rows, cmask);
-          } else {
-            tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
-          }
+          tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
         }
         __syncwarp();
         // every lane tracks the tap state (cheap, keeps the warp converged)
@@ -410,11 +392,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
-          if (CS > 1) {
-            umma_commit_multicast(&empty_bar[stage], cmask);
-          } else {
-            umma_commit(&empty_bar[stage]);
-          }
+          umma_commit(&empty_bar[stage]);
           if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
@@ -447,7 +425,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t aux_n = 0;                                // completed aux-barrier phases
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int m0 = tile_m0(it);
+      const int m0 = (m_first + it * m_step) * kBM;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int row = m0 + r;
@@ -613,8 +591,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  // no CTA may exit while a peer can still multicast into its smem or arrive on its barriers
-  if (CS > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -820,17 +796,12 @@ static int num_sms() {
 
 struct ConvMaps {
   CUtensorMap a, b, c, add, mask;
-  CUtensorMap b_half;   // weight tile in boxes of BN/2 rows (the slice one CTA of a pair loads)
 };
-
-// -1: pick per problem (default); 1: never cluster; 2: pair whenever the problem allows it
-static int g_conv_cluster_mode = -1;
 
 template <int BN, int CW, bool IM2COL>
 static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStream_t stream) {
   using Cfg = FpropCfg<BN>;
   static bool attr_set = false;
-  static int max_pairs = -1;     // co-resident 2-CTA clusters of this instantiation (0: unknown)
   auto kern = conv_gemm_kernel<BN, CW, IM2COL>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -842,66 +813,19 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
     attr_set = true;
   }
   ConvGemmParams q = p;
+  const int num_kb = ceil_div(p.Ktot, kStageK);
   q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32);
+  (void)num_kb;
   q.m_tiles = ceil_div(p.M, kBM);
   q.n_tiles = p.Cout / BN;
-  const int smem = Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32);
-  // Pairs of CTAs on neighbouring M tiles share every weight stage (each loads half of it and
-  // multicasts): the L2 -> SM traffic per FLOP, which bounds these GEMMs, drops by BN/(2(128+BN)).
-  const bool pair_ok = p.cluster == 2 && q.m_tiles % 2 == 0 && p.b_sw_bytes == 128 && BN >= 16;
-  q.cluster = 1;
-  if (pair_ok) {
-    if (max_pairs < 0) {
-      cudaLaunchConfig_t oc{};
-      oc.gridDim = dim3(2 * num_sms());
-      oc.blockDim = dim3(kConvThreads);
-      oc.dynamicSmemBytes = kSmemBudget + 2048;
-      cudaLaunchAttribute oa[1];
-      oa[0].id = cudaLaunchAttributeClusterDimension;
-      oa[0].val.clusterDim.x = 2;
-      oa[0].val.clusterDim.y = 1;
-      oa[0].val.clusterDim.z = 1;
-      oc.attrs = oa;
-      oc.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, kern, &oc) != cudaSuccess) {
-        (void)cudaGetLastError();
-        n = 0;
-      }
-      max_pairs = n;
-    }
-    // an odd GPC may strand an SM per cluster size; only pair when (almost) the whole GPU is used
-    if (max_pairs * 2 >= num_sms() - 8 || (g_conv_cluster_mode == 2 && max_pairs > 0)) q.cluster = 2;
-  }
-  // persistent grid: a multiple of n_tiles so that every cluster keeps one N tile (its weights
-  // and its per-channel statistics), at most one CTA per SM
-  const int CS = q.cluster;
-  const int slots = CS == 2 ? max_pairs : num_sms();
-  int per_n = slots / q.n_tiles;
+  // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
+  // its per-channel statistics), at most one CTA per SM
+  int per_n = num_sms() / q.n_tiles;
   if (per_n < 1) per_n = 1;
-  if (per_n > q.m_tiles / CS) per_n = q.m_tiles / CS;
-  const int grid = per_n * q.n_tiles * CS;
-  if (CS == 1) {
-    kern<<<grid, kConvThreads, smem, stream>>>(tm.a, tm.b, tm.c, tm.add, tm.mask, q);
-  } else {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CS;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm.a, tm.b_half, tm.c, tm.add, tm.mask, q);
-    if (e != cudaSuccess) {
-      set_error("cudaLaunchKernelEx(conv_gemm, cluster %d): %s", CS, cudaGetErrorString(e));
-      return ACNN_ERR_CUDA;
-    }
-  }
+  if (per_n > q.m_tiles) per_n = q.m_tiles;
+  const int grid = per_n * q.n_tiles;
+  kern<<<grid, kConvThreads, Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32),
+         stream>>>(tm.a, tm.b, tm.c, tm.add, tm.mask, q);
   count_launch();
   return check_launch("conv_gemm_kernel");
 }
@@ -977,16 +901,7 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   if (rc) return rc;
   rc = make_map_2d(&tm.b, w, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
   if (rc) return rc;
-  tm.c = tm.add = tm.mask = tm.b_half = tm.b;   // placeholders when unused
-  // request CTA pairs when there are at least two waves of tiles (or when forced, for tests)
-  const int64_t tiles = (int64_t)ceil_div(p.M, kBM) * (g.Cout / bn);
-  p.cluster = 1;
-  if (p.Ktot >= 64 && g_conv_cluster_mode != 1 &&
-      (g_conv_cluster_mode == 2 || tiles >= 2 * (int64_t)num_sms())) {
-    p.cluster = 2;
-    rc = make_map_2d(&tm.b_half, w, g.Cout, p.Ktot, p.Ktot, bn / 2, 64);
-    if (rc) return rc;
-  }
+  tm.c = tm.add = tm.mask = tm.b;   // placeholders when unused
   const int subw = bn < 64 ? bn : 64;
   if (!out_f32 && (rc = make_map_2d(&tm.c, y, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
   if (add_src && (rc = make_map_2d(&tm.add, add_src, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
@@ -1101,12 +1016,6 @@ static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* d
 // C ABI
 // ------------------------------------------------------------------------------------------
 extern "C" {
-
-int acnn_set_conv_cluster(int mode) {
-  const int prev = acnn::g_conv_cluster_mode;
-  acnn::g_conv_cluster_mode = (mode == 1 || mode == 2) ? mode : -1;
-  return prev;
-}
 
 int acnn_conv_fprop(const acnn_conv_geom* g, const void* x, const void* w, void* y, float* ch_sum,
                     float* ch_sumsq, const void* add_src, const void* mask_src, const float* bias,

@@ -81,17 +81,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// Same, delivered to the same smem offset (and signalling the same barrier offset) of every CTA
-// of the cluster named in `cta_mask`.
-__device__ __forceinline__ void tma_load_2d_multicast(void* smem_dst, const CUtensorMap* m,
-                                                      uint64_t* bar, int32_t c0, int32_t c1,
-                                                      uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
-      ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;\n" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
 // 4-D im2col load over an NHWC tensor: coords (c, w, h, n) name the first *base* pixel,
 // (off_w, off_h) the filter tap added to every base pixel of the column.
 __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m,
@@ -157,29 +146,6 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
           smem_u32(bar))
       : "memory");
-}
-
-// Arrive (once the MMAs issued so far have completed) on the barrier at this smem offset in every
-// CTA of `cta_mask`: frees a pipeline stage that a peer CTA multicasts into.
-__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
-      " [%0], %1;\n" ::"r"(smem_u32(bar)),
-      "h"(cta_mask)
-      : "memory");
-}
-
-// ---------------------------------------------------------------- thread-block clusters
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-  return r;
-}
-// all threads of all CTAs of the cluster (every warp converged)
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n"
-               "barrier.cluster.wait.acquire.aligned;\n" ::
-                   : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane == TMEM row).

@@ -34,10 +34,6 @@ const char* acnn_last_error(void);
 int acnn_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t acnn_launch_count(void);
-/* Tuning knob of the conv GEMM launcher (no effect on results): -1 = choose per problem
- * (default), 1 = never pair CTAs, 2 = run CTA pairs (2-CTA clusters sharing each weight tile by
- * TMA multicast) whenever the problem shape allows it.  Returns the previous mode. */
-int acnn_set_conv_cluster(int mode);
 
 /* Convolution geometry (correlation, no bias) -- nets/model_helper.py:67-78 conv2d_fixed_padding
  * + fixed_padding :40-64.  Ho = (H + pad_h_lo + pad_h_hi - kh) / stride + 1, same for W. */
