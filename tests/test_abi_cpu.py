@@ -30,7 +30,7 @@ def test_build_and_symbols():
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "libcuda.so" not in out
     # struct layouts the ABI passes by pointer
-    assert ctypes.sizeof(_lib.ConvGeom) == 48 and ctypes.sizeof(_lib.WeightDesc) == 40
+    assert ctypes.sizeof(_lib.ConvGeom) == 64 and ctypes.sizeof(_lib.WeightDesc) == 40
 
 
 def test_sass_uses_tcgen05_and_tma():
