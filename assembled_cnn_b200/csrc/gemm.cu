@@ -284,13 +284,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
+  // 32-bit shared-window addresses, computed once: the issue loops below run on one warp each and
+  // are instruction-latency bound (every instruction saved per k-block is ~1% of a small-N layer)
+  const uint32_t smem_a0 = smem_u32(smem);
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const uint32_t stage_wrap = static_cast<uint32_t>(kStages) * Cfg::kStageBytes;
+  // chunks of the last k-block (a partial stage exists only when a filter tap is narrower than
+  // a stage, i.e. Cin < 64 with an odd tap count)
+  const int tail_chunks = kChunks == 1 ? 1 : ((p.Ktot - (num_kb - 1) * kStageK + CW - 1) / CW);
+
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     // The whole warp stays converged (so the uniform-datapath TMA/MMA instructions need no
-    // election loops); one elected lane issues.
-    int stage = 0;
-    uint32_t phase = 0;
+    // election loops) and every lane tracks the same loop state; one elected lane issues.
+    uint32_t soff = 0, sbar = 0, phase = 0;             // stage byte offset / barrier offset
     const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
+    const uint32_t full_bytes = kChunks * kChunkBytes + b_bytes;
+    const uint32_t tail_bytes = tail_chunks * kChunkBytes + b_bytes;
+    const int Cin = p.Cin, fkw = p.kw;
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = (m_first + it * m_step) * kBM;
       int img = 0, h0 = 0, w0 = 0;
@@ -303,100 +314,84 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         w0 = qo * p.stride - p.pad_w_lo;
       }
       // filter tap (tr, ts) and channel offset tc of the next chunk, advanced incrementally
-      int tr = 0, ts = 0, tc = 0, k = 0;
+      int tr = 0, ts = 0, tc = 0, k0 = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        if (elect_one()) {
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          const int k0 = kb * kStageK;
-          int nchunk = kChunks;
-          if (k0 + kStageK > p.Ktot) nchunk = (p.Ktot - k0 + CW - 1) / CW;
-          mbar_expect_tx(&full_bar[stage], nchunk * kChunkBytes + b_bytes);
-          int kr = tr, ksn = ts, kc = tc, kk = k;
-#pragma unroll
-          for (int j = 0; j < kChunks; ++j) {
-            if (kk < p.Ktot) {
-              if (IM2COL) {
-                tma_load_im2col_4d(sa + j * kChunkBytes, &tmA, &full_bar[stage], kc, w0, h0, img,
-                                   (uint16_t)ksn, (uint16_t)kr);
-              } else {
-                tma_load_2d(sa + j * kChunkBytes, &tmA, &full_bar[stage], kk, m0);
-              }
-            }
-            kk += CW;
-            kc += CW;
-            if (kc >= p.Cin) {
-              kc = 0;
-              if (++ksn == p.kw) { ksn = 0; ++kr; }
-            }
-          }
-          tma_load_2d(sb, &tmB, &full_bar[stage], k0, n0);
+        const bool last = kb == num_kb - 1;
+        const int nch = (kChunks > 1 && last) ? tail_chunks : kChunks;
+        mbar_wait_a(empty0 + sbar, phase ^ 1);
+        const bool leader = elect_one();
+        const uint32_t fb = full0 + sbar;
+        const uint32_t sa = smem_a0 + soff;
+        if (leader) {
+          mbar_expect_tx_a(fb, (kChunks > 1 && last) ? tail_bytes : full_bytes);
+          tma_load_2d_a(sa + Cfg::kABytes, &tmB, fb, k0, n0);
         }
-        __syncwarp();
-        // every lane tracks the tap state (cheap, keeps the warp converged)
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
-          k += CW;
-          tc += CW;
-          if (tc >= p.Cin) {
-            tc = 0;
-            if (++ts == p.kw) { ts = 0; ++tr; }
+          if (j < nch) {
+            if (leader) {
+              if (IM2COL) {
+                tma_load_im2col_4d_a(sa + j * kChunkBytes, &tmA, fb, tc, w0, h0, img,
+                                     (uint16_t)ts, (uint16_t)tr);
+              } else {
+                tma_load_2d_a(sa + j * kChunkBytes, &tmA, fb, k0 + j * CW, m0);
+              }
+            }
+            tc += CW;
+            if (tc >= Cin) {
+              tc = 0;
+              if (++ts == fkw) { ts = 0; ++tr; }
+            }
           }
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        __syncwarp();
+        k0 += kStageK;
+        soff += Cfg::kStageBytes;
+        sbar += 8;
+        if (soff == stage_wrap) { soff = 0; sbar = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    int stage = 0;
-    uint32_t phase = 0;
+    uint32_t soff16 = 0, sbar = 0, phase = 0;            // stage offset in descriptor units (16 B)
+    const uint32_t stage_wrap16 = stage_wrap >> 4;
+    const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
     // descriptors of stage 0 / chunk 0; everything else is an add on the 14-bit address field
-    const uint64_t a_desc0 =
-        make_smem_desc(smem_u32(smem), 16, 8 * CW * 2, swizzle_layout_type(CW * 2));
-    const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, 16, 8 * p.b_sw_bytes,
+    const uint64_t a_desc0 = make_smem_desc(smem_a0, 16, 8 * CW * 2, swizzle_layout_type(CW * 2));
+    const uint64_t b_desc0 = make_smem_desc(smem_a0 + Cfg::kABytes, 16, 8 * p.b_sw_bytes,
                                             swizzle_layout_type(p.b_sw_bytes));
     for (int it = 0; it < my_tiles; ++it) {
-      const int acc = it & 1;
+      const uint32_t acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);      // epilogue has drained this accumulator
+      mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);   // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        const bool last = kb == num_kb - 1;
+        const int nch = (kChunks > 1 && last) ? tail_chunks : kChunks;
+        mbar_wait_a(full0 + sbar, phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t da0 = a_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
-          const uint64_t db0 = b_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
-          const int k0 = kb * kStageK;
-          if (k0 + kStageK <= p.Ktot) {
+          const uint64_t da0 = a_desc0 + soff16;
+          const uint64_t db0 = b_desc0 + soff16;
 #pragma unroll
-            for (int j = 0; j < kChunks; ++j) {
+          for (int j = 0; j < kChunks; ++j) {
+            if (j < nch) {
 #pragma unroll
               for (int ks = 0; ks < kKSteps; ++ks) {
                 umma_bf16(tmem_d, da0 + ((j * kChunkBytes + ks * 32) >> 4),
                           db0 + (((j * kKSteps + ks) * 32) >> 4), kIdesc,
-                          (kb | j | ks) ? 1u : 0u);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < kChunks; ++j) {
-              if (k0 + j * CW < p.Ktot) {
-#pragma unroll
-                for (int ks = 0; ks < kKSteps; ++ks) {
-                  umma_bf16(tmem_d, da0 + ((j * kChunkBytes + ks * 32) >> 4),
-                            db0 + (((j * kKSteps + ks) * 32) >> 4), kIdesc,
-                            (kb | j | ks) ? 1u : 0u);
-                }
+                          (j | ks) ? 1u : static_cast<uint32_t>(kb != 0));
               }
             }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);
+          umma_commit_a(empty0 + sbar);
+          if (last) umma_commit_a(tfull0 + acc * 8);
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        soff16 += Cfg::kStageBytes >> 4;
+        sbar += 8;
+        if (soff16 == stage_wrap16) { soff16 = 0; sbar = 0; phase ^= 1; }
       }
     }
   } else {
