@@ -21,6 +21,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--ncu", action="store_true")
 ap.add_argument("--top", type=int, default=40)
+ap.add_argument("--csv", default="", help="write every conv GEMM launch (ms, ideal, shape) here")
 args = ap.parse_args()
 
 B = args.batch
@@ -86,3 +87,8 @@ print("conv GEMMs: measured %.2f ms, roofline (max of tensor / HBM per launch) %
 print("--- conv GEMM launches by gap to their roofline (ms, ideal ms, kind, shape, TFLOP/s)")
 for ms, kind, shape, tf, ideal in sorted(rows, key=lambda r: r[4] - r[0])[:args.top]:
     print("%7.3f %7.3f %-11s %-28s %7.1f" % (ms, ideal, kind, shape, tf))
+if args.csv:
+    with open(args.csv, "w") as fh:
+        fh.write("ms,ideal_ms,kind,shape,tflops\n")
+        for ms, kind, shape, tf, ideal in rows:
+            fh.write("%.4f,%.4f,%s,%s,%.1f\n" % (ms, ideal, kind, shape, tf))
