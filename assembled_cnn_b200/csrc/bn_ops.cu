@@ -42,7 +42,11 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 // ------------------------------------------------------------------------------------------
 // bn_act : out = relu?( (a*sa + ha) [*gate] + R )
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kT)
+// U vectors per thread per trip: the loads of a trip are issued back to back, so U (x2 with a
+// second operand) x 16 B x resident threads is what is in flight per SM; ~64 KiB is needed to
+// cover the HBM latency at full bandwidth.
+template <int U, bool HAS_B>
+__global__ void __launch_bounds__(kT, 2)
 bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
               const float* __restrict__ ha, const bf16* __restrict__ b,
               const float* __restrict__ sb, const float* __restrict__ hb, int b_mode,
@@ -61,18 +65,18 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
     loadf8(sb + c0, s2);
     loadf8(hb + c0, h2);
   }
-  // 4 vectors per trip, loads batched ahead of the math (index clamped, store predicated)
+  // U vectors per trip, loads batched ahead of the math (index clamped, store predicated)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
-    uint4 av[4], bv[4];
+  for (int64_t ib = i0; ib < nvec; ib += U * stride) {
+    uint4 av[U], bv[HAS_B ? U : 1];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       int64_t i = ib + u * stride;
       i = i < nvec ? i : nvec - 1;
       av[u] = __ldg(reinterpret_cast<const uint4*>(a + i * 8));
-      if (b_mode == 1 || b_mode == 2) {
+      if (HAS_B && (b_mode == 1 || b_mode == 2)) {
         bv[u] = __ldg(reinterpret_cast<const uint4*>(b + i * 8));
-      } else if (b_mode == 3) {
+      } else if (HAS_B && b_mode == 3) {
         const int64_t pix = i / CG;
         const int w = (int)(pix % W);
         const int64_t t = pix / W;
@@ -83,7 +87,7 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int64_t i = ib + u * stride;
       if (i >= nvec) break;
       float v[8];
@@ -97,12 +101,12 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] *= g[k];
       }
-      if (b_mode == 1) {
+      if (HAS_B && b_mode == 1) {
         float r[8];
         unpack8(bv[u], r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s2[k], h2[k]);
-      } else if (b_mode >= 2) {
+      } else if (HAS_B && b_mode >= 2) {
         float r[8];
         unpack8(bv[u], r);
 #pragma unroll
@@ -310,34 +314,49 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
       loadf8(shift + f + c0, h1);
     }
   }
-  for (int r = rsub; r < HW; r += RPB) {
-    const int64_t row = (int64_t)b * HW + r;
-    if (MODE == 0 || MODE == 1) {
-      float y0[8], y1[8];
-      load8(p0 + row * ldy + c0, y0);
-      load8(p0 + row * ldy + f + c0, y1);
-      float dv[8];
-      if (MODE == 1) load8(p1 + row * f + c0, dv);
+  // U rows per trip: all loads of a trip are issued before any math (row clamped, contribution
+  // zeroed), since only ~1.7 CTAs of 256 threads are resident per SM (grid = images)
+  constexpr int U = (MODE == 1 || MODE == 3) ? 4 : 1;   // measured: batching only pays with 3 loads/row
+  for (int rb = rsub; rb < HW; rb += U * RPB) {
+    uint4 qa[U], qb[U], qc[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
-        const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
-        acc[i] += (MODE == 0) ? (u0 + u1) : dv[i] * (u0 - u1);
+    for (int u = 0; u < U; ++u) {
+      int r = rb + u * RPB;
+      r = r < HW ? r : HW - 1;
+      const int64_t row = (int64_t)b * HW + r;
+      qa[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + c0));
+      if (MODE <= 1) qb[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + f + c0));
+      if (MODE == 1 || MODE == 3) qc[u] = __ldg(reinterpret_cast<const uint4*>(p1 + row * f + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float valid = (rb + u * RPB) < HW ? 1.f : 0.f;
+      if (MODE == 0 || MODE == 1) {
+        float y0[8], y1[8], dv[8];
+        unpack8(qa[u], y0);
+        unpack8(qb[u], y1);
+        if (MODE == 1) unpack8(qc[u], dv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
+          const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
+          acc[i] += valid * ((MODE == 0) ? (u0 + u1) : dv[i] * (u0 - u1));
+        }
+      } else if (MODE == 2 || MODE == 3) {
+        float yv[8], gv[8];
+        unpack8(qa[u], yv);
+        if (MODE == 3) unpack8(qc[u], gv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = fmaf(yv[i], s0[i], h0[i]);
+          acc[i] += valid * ((MODE == 2) ? t : gv[i] * t);
+        }
+      } else {
+        float xv[8];
+        unpack8(qa[u], xv);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += valid * xv[i];
       }
-    } else if (MODE == 2 || MODE == 3) {
-      float yv[8], gv[8];
-      load8(p0 + row * ldy + c0, yv);
-      if (MODE == 3) load8(p1 + row * f + c0, gv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float t = fmaf(yv[i], s0[i], h0[i]);
-        acc[i] += (MODE == 2) ? t : gv[i] * t;
-      }
-    } else {
-      float xv[8];
-      load8(p0 + row * ldy + c0, xv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += xv[i];
     }
   }
 #pragma unroll
@@ -578,9 +597,15 @@ int acnn_bn_act(const void* a, const float* scale_a, const float* shift_a, const
   ACNN_REQUIRE(b_mode != 1 || (scale_b && shift_b), "bn_act: b_mode 1 needs scale_b/shift_b");
   ACNN_REQUIRE(b_mode != 3 || (H % 2 == 0 && W % 2 == 0), "bn_act: upsample needs even H, W");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  bn_act_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
-      (bf16*)out, H, W, C, nvec);
+  if (b_mode == 0) {
+    bn_act_kernel<8, false><<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
+        (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
+        (bf16*)out, H, W, C, nvec);
+  } else {
+    bn_act_kernel<4, true><<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
+        (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
+        (bf16*)out, H, W, C, nvec);
+  }
   count_launch();
   return check_launch("bn_act");
 }
@@ -591,7 +616,7 @@ int acnn_bn_bwd_reduce(const void* g, const void* y, const float* mean, const fl
   ACNN_REQUIRE(g && y && mean && rstd && sums && cg_ok(C), "bn_bwd_reduce: bad arguments C=%d", C);
   const int64_t M = (int64_t)B * HW;
   const int rpb = kT / (C >> 3);
-  bn_bwd_reduce_kernel<<<grid_for(ceil_div64(M, rpb), 1, 148 * 4), kT, 0, (cudaStream_t)stream>>>(
+  bn_bwd_reduce_kernel<<<grid_for(ceil_div64(M, 4 * rpb), 1, 148 * 2), kT, 0, (cudaStream_t)stream>>>(
       (const bf16*)g, (const bf16*)y, mean, rstd, gate, addbc, sums, M, HW, C);
   count_launch();
   return check_launch("bn_bwd_reduce");
