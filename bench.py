@@ -361,11 +361,18 @@ def conv_roofline(tr, x_dev, y_dev, peaks, ms_step):
         def wrapped(op, orig=orig):
             g = op.geom
             flops = 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
+            # algorithmic HBM bytes: both activation tensors once (bf16) + the filter (bf16, or
+            # the fp32 gradient for wgrad) + the tiles the dgrad epilogue adds / masks with
+            nin, nout = g.B * g.H * g.W * g.Cin, g.B * g.Ho * g.Wo * g.Cout
+            nw = g.kh * g.kw * g.Cin * g.Cout
+            byt = 2.0 * (nin + nout) + (4.0 if op.kind == "conv_wgrad" else 2.0) * nw
+            if op.kind == "conv_dgrad":
+                byt += 2.0 * nin * ((op.add_src is not None) + (op.mask_src is not None))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             orig(op)
             b.record(stream)
-            evs.append((a, b, flops))
+            evs.append((a, b, flops, byt))
         setattr(rt, name, wrapped)
     was, was_world = tr.use_graph, tr.world
     tr.use_graph = False
@@ -380,11 +387,24 @@ def conv_roofline(tr, x_dev, y_dev, peaks, ms_step):
         tr.world = was_world
         for name in ("op_conv", "op_conv_dgrad", "op_conv_wgrad"):
             delattr(rt, name)
-    t_ms = sum(a.elapsed_time(b) for a, b, _ in evs)
-    fl = sum(f for _, _, f in evs)
+    t_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
+    fl = sum(e[2] for e in evs)
+    alg_bytes = sum(e[3] for e in evs)
     achieved = fl / (t_ms / 1e3) / 1e12
+    # DRAM traffic of the same launches from the committed ncu launch list (profiles/): bytes per
+    # step over all tcgen05 launches, the same basis as `achieved`
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                                         "conv_dram_traffic.json")))
+        if tj.get("launches") == len(evs):
+            traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+    except (OSError, ValueError, KeyError):
+        pass
     return {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops"], "traffic": None,
+            "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_unit": "bytes per step "
+            "(dram__bytes_read+write summed over the same launches, ncu)", "traffic_source": traffic_src,
+            "algorithmic_bytes_per_step": alg_bytes,
             "kernel": "conv_gemm_kernel + wgrad_gemm_kernel (all %d tcgen05 launches of a step)" % len(evs),
             "launch_ms_sum": t_ms, "share_of_step": t_ms / ms_step,
             "algorithmic_gflop_per_step": fl / 1e9,
