@@ -3,6 +3,7 @@
 // channel per CTA).  Reference: nets/model_helper.py:26-37, nets/blocks.py:110-184 and the
 // backward formulas of SURVEY App. C.
 #include "common.h"
+#include "stream_pipe.cuh"
 #include "vec.cuh"
 
 namespace acnn {
@@ -430,68 +431,102 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
 
 // The 2f channels of the SK conv output are handled as one 2f-wide tensor whose gradient is
 // computed on the fly: g = (a_h * dv + ds/HW) * [u > 0], a_0 = att, a_1 = 1 - att.  One thread =
-// 8 channels of ONE half (few live coefficient registers -> 4 CTAs per SM).
+// 8 channels of ONE half.  grid = (row slabs, images): everything that depends only on (image,
+// channel) stays in registers, and the rows of y / dv are streamed through shared memory
+// (stream_pipe.cuh): a trip is 4 rows per thread = 16 KiB of y + 8 KiB of dv for every f.
+constexpr int kSkStages = 3;
+constexpr int kSkYBytes = 16 * 1024, kSkDvBytes = 8 * 1024;
+constexpr int kSkStageBytes = kSkYBytes + kSkDvBytes;
+constexpr int kSkSmemBytes = kSkStages * kSkStageBytes + 128;
+
+struct SkSlab {
+  int C2, CG2, RPB, RT, cg2, rsub, cb, c0, r_begin, r_end, trips;
+  bool second;
+  int64_t b;
+};
+__device__ __forceinline__ SkSlab sk_slab(int HW, int f) {
+  SkSlab q;
+  q.C2 = 2 * f;
+  q.CG2 = q.C2 >> 3;
+  q.RPB = kT / q.CG2;
+  q.RT = 4 * q.RPB;                              // rows per trip
+  q.cg2 = threadIdx.x % q.CG2;
+  q.rsub = threadIdx.x / q.CG2;
+  q.second = q.cg2 >= (q.CG2 >> 1);
+  q.cb = (q.cg2 % (q.CG2 >> 1)) << 3;            // channel inside the half
+  q.c0 = q.cg2 << 3;                             // channel inside the 2f-wide tensor
+  q.b = blockIdx.y;
+  const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
+  q.r_begin = blockIdx.x * rows_per;
+  q.r_end = (q.r_begin + rows_per < HW) ? q.r_begin + rows_per : HW;
+  const int n = q.r_end - q.r_begin;
+  q.trips = n > 0 ? (n + q.RT - 1) / q.RT : 0;
+  return q;
+}
+
 __global__ void __launch_bounds__(kT, 2)
 sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ att, const float* __restrict__ ds, float* sums,
                         int HW, int f) {
-  // grid = (row slabs, images); one thread = 8 channels of ONE half of the 2f-wide tensor
-  const int C2 = 2 * f;
-  const int CG2 = C2 >> 3;
-  const int RPB = kT / CG2;
-  const int cg2 = threadIdx.x % CG2;
-  const int rsub = threadIdx.x / CG2;
-  const bool second = cg2 >= (CG2 >> 1);
-  const int cb = (cg2 % (CG2 >> 1)) << 3;      // channel inside the half
-  const int c0 = cg2 << 3;                      // channel inside the 2f-wide tensor
-  const int64_t b = blockIdx.y;
-  const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
-  const int r_begin = blockIdx.x * rows_per;
-  const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
+  extern __shared__ uint8_t sk_smem_raw[];
+  __shared__ uint64_t bars[kSkStages];
+  const SkSlab q = sk_slab(HW, f);
+  const uint32_t sbase = (smem_u32(sk_smem_raw) + 127u) & ~127u;
+  const uint8_t* sgen = sk_smem_raw + (sbase - smem_u32(sk_smem_raw));
+  RowPipe<kSkStages> pipe(bars);
+  pipe.init(bars);
+  auto issue = [&](int t, int stage, uint32_t bar) {
+    const int r0 = q.r_begin + t * q.RT;
+    const int rows = (q.r_end - r0 < q.RT) ? q.r_end - r0 : q.RT;
+    const int64_t row = q.b * HW + r0;
+    mbar_expect_tx_a(bar, rows * (q.C2 + f) * 2);
+    bulk_load(sbase + stage * kSkStageBytes, y + row * q.C2, rows * q.C2 * 2, bar);
+    bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * 2, bar);
+  };
+  pipe.prologue(q.trips, issue);
   float sc[8], sh[8], mu[8], rs[8], ah[8], sg[8];
-  loadf8(scale + c0, sc);
-  loadf8(shift + c0, sh);
-  loadf8(mean + c0, mu);
-  loadf8(rstd + c0, rs);
-  loadf8(att + b * f + cb, ah);
-  loadf8(ds + b * f + cb, sg);
+  loadf8(scale + q.c0, sc);
+  loadf8(shift + q.c0, sh);
+  loadf8(mean + q.c0, mu);
+  loadf8(rstd + q.c0, rs);
+  loadf8(att + q.b * f + q.cb, ah);
+  loadf8(ds + q.b * f + q.cb, sg);
   const float inv_hw = 1.f / HW;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    if (second) ah[i] = 1.f - ah[i];
+    if (q.second) ah[i] = 1.f - ah[i];
     sg[i] *= inv_hw;
   }
   float acc[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.f;
-  for (int rb = r_begin + rsub; rb < r_end; rb += 4 * RPB) {
-    uint4 yq[4], dq[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {          // unconditional, batched loads (row clamped)
-      int r = rb + u * RPB;
-      r = r < r_end ? r : r_end - 1;
-      const int64_t row = b * HW + r;
-      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + row * C2 + c0));
-      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + row * f + cb));
-    }
+  for (int t = 0; t < q.trips; ++t) {
+    pipe.acquire(t, q.trips, issue);
+    const uint8_t* sy = sgen + pipe.stage(t) * kSkStageBytes;
+    const uint8_t* sd = sy + kSkYBytes;
+    const int rows = q.r_end - (q.r_begin + t * q.RT);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const float valid = (rb + u * RPB) < r_end ? 1.f : 0.f;
-      float yv[8], d[8];
-      unpack8(yq[u], yv);
-      unpack8(dq[u], d);
+      const int rl = q.rsub + u * q.RPB;
+      if (rl < rows) {
+        float yv[8], d[8];
+        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * q.C2 + q.c0) * 2), yv);
+        unpack8(*reinterpret_cast<const uint4*>(sd + (rl * f + q.cb) * 2), d);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float t = fmaf(yv[i], sc[i], sh[i]);
-        const float gg = t > 0.f ? valid * fmaf(ah[i], d[i], sg[i]) : 0.f;
-        acc[0][i] += gg;
-        acc[1][i] += gg * ((yv[i] - mu[i]) * rs[i]);
+        for (int i = 0; i < 8; ++i) {
+          const float tt = fmaf(yv[i], sc[i], sh[i]);
+          const float gg = tt > 0.f ? fmaf(ah[i], d[i], sg[i]) : 0.f;
+          acc[0][i] += gg;
+          acc[1][i] += gg * ((yv[i] - mu[i]) * rs[i]);
+        }
       }
     }
+    pipe.release();
   }
-  block_reduce_atomic<2>(acc, CG2, sums, [C2](int a, int c) { return a * C2 + c; });
+  const int C2 = q.C2;
+  block_reduce_atomic<2>(acc, q.CG2, sums, [C2](int a, int c) { return a * C2 + c; });
 }
 
 __global__ void __launch_bounds__(kT, 2)
@@ -499,66 +534,163 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        const float* __restrict__ att, const float* __restrict__ ds,
                        const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f) {
-  // grid = (row slabs, images); one thread = 8 channels of ONE half; everything that depends
-  // only on (image, channel) stays in registers
-  const int C2 = 2 * f;
-  const int CG2 = C2 >> 3;
-  const int RPB = kT / CG2;
-  const int cg2 = threadIdx.x % CG2;
-  const int rsub = threadIdx.x / CG2;
-  const bool second = cg2 >= (CG2 >> 1);
-  const int cb = (cg2 % (CG2 >> 1)) << 3;
-  const int c0 = cg2 << 3;
-  const int64_t b = blockIdx.y;
-  const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
-  const int r_begin = blockIdx.x * rows_per;
-  const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
-  float sc[8], sh[8], k1[8], k2[8], k3[8], ah[8], sg[8];
-  loadf8(scale + c0, sc);
-  loadf8(shift + c0, sh);
-  loadf8(coef + c0, k1);
-  loadf8(coef + C2 + c0, k2);
-  loadf8(coef + 2 * C2 + c0, k3);
-  loadf8(att + b * f + cb, ah);
-  loadf8(ds + b * f + cb, sg);
-  const float inv_hw = 1.f / HW;
+  extern __shared__ uint8_t sk_smem_raw[];
+  __shared__ uint64_t bars[kSkStages];
+  const SkSlab q = sk_slab(HW, f);
+  const uint32_t sbase = (smem_u32(sk_smem_raw) + 127u) & ~127u;
+  const uint8_t* sgen = sk_smem_raw + (sbase - smem_u32(sk_smem_raw));
+  RowPipe<kSkStages> pipe(bars);
+  pipe.init(bars);
+  auto issue = [&](int t, int stage, uint32_t bar) {
+    const int r0 = q.r_begin + t * q.RT;
+    const int rows = (q.r_end - r0 < q.RT) ? q.r_end - r0 : q.RT;
+    const int64_t row = q.b * HW + r0;
+    mbar_expect_tx_a(bar, rows * (q.C2 + f) * 2);
+    bulk_load(sbase + stage * kSkStageBytes, y + row * q.C2, rows * q.C2 * 2, bar);
+    bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * 2, bar);
+  };
+  pipe.prologue(q.trips, issue);
+  // o = k1 * g + k2 * y + k3 with g = [sc*y+sh > 0] (ah*dv + sg): folded into
+  // o = [..] (ka * dv + kb) + k2 * y + k3
+  float sc[8], sh[8], ka[8], kb[8], k2[8], k3[8];
+  {
+    float k1[8], ah[8], sg[8];
+    loadf8(coef + q.c0, k1);
+    loadf8(att + q.b * f + q.cb, ah);
+    loadf8(ds + q.b * f + q.cb, sg);
+    const float inv_hw = 1.f / HW;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (second) ah[i] = 1.f - ah[i];
-    sg[i] *= inv_hw;
-  }
-  for (int rb = r_begin + rsub; rb < r_end; rb += 4 * RPB) {
-    uint4 yq[4], dq[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {          // batched loads (row clamped)
-      int r = rb + u * RPB;
-      r = r < r_end ? r : r_end - 1;
-      const int64_t row = b * HW + r;
-      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + row * C2 + c0));
-      dq[u] = __ldg(reinterpret_cast<const uint4*>(dv + row * f + cb));
+    for (int i = 0; i < 8; ++i) {
+      const float a = q.second ? 1.f - ah[i] : ah[i];
+      ka[i] = k1[i] * a;
+      kb[i] = k1[i] * (sg[i] * inv_hw);
     }
+  }
+  loadf8(scale + q.c0, sc);
+  loadf8(shift + q.c0, sh);
+  loadf8(coef + q.C2 + q.c0, k2);
+  loadf8(coef + 2 * q.C2 + q.c0, k3);
+  for (int t = 0; t < q.trips; ++t) {
+    pipe.acquire(t, q.trips, issue);
+    const uint8_t* sy = sgen + pipe.stage(t) * kSkStageBytes;
+    const uint8_t* sd = sy + kSkYBytes;
+    const int r0 = q.r_begin + t * q.RT;
+    const int rows = q.r_end - r0;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int r = rb + u * RPB;
-      if (r >= r_end) break;
-      float yv[8], d[8], o[8];
-      unpack8(yq[u], yv);
-      unpack8(dq[u], d);
+      const int rl = q.rsub + u * q.RPB;
+      if (rl < rows) {
+        float yv[8], d[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * q.C2 + q.c0) * 2), yv);
+        unpack8(*reinterpret_cast<const uint4*>(sd + (rl * f + q.cb) * 2), d);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float t = fmaf(yv[k], sc[k], sh[k]);
-        const float g = t > 0.f ? fmaf(ah[k], d[k], sg[k]) : 0.f;
-        o[k] = fmaf(k1[k], g, fmaf(k2[k], yv[k], k3[k]));
+        for (int k = 0; k < 8; ++k) {
+          const float tt = fmaf(yv[k], sc[k], sh[k]);
+          const float base = fmaf(k2[k], yv[k], k3[k]);
+          o[k] = tt > 0.f ? base + fmaf(ka[k], d[k], kb[k]) : base;
+        }
+        store8(dy + (q.b * HW + r0 + rl) * q.C2 + q.c0, o);
       }
-      store8(dy + (b * HW + r) * C2 + c0, o);
     }
+    pipe.release();
   }
 }
 
-// Row slabs per image for the image-aligned SK kernels: ~8 CTAs per SM overall, at least 4 trips
-// of the unrolled row loop per CTA.
-static int row_slabs(int B, int HW, int rpb) {
-  int s = (148 * 8 + B - 1) / B;
+// Per-image reductions over the SK conv output, one CTA per image, rows streamed through shared
+// memory.  MODE 0 (sk_gap): s[b, c] = mean_hw relu(bn(y0)) + relu(bn(y1)); MODE 1 (sk_bwd_gate):
+// dA[b, c] = sum_hw dv * (u0 - u1).  One thread = 8 output channels (both halves of y); a trip is
+// 2 rows per thread = 16 KiB of y (+ 8 KiB of dv), the same stage layout as the kernels above.
+template <int MODE>
+__global__ void __launch_bounds__(kT, 2)
+sk_image_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dv,
+                       const float* __restrict__ scale, const float* __restrict__ shift,
+                       float* __restrict__ out, int HW, int f) {
+  extern __shared__ uint8_t sk_smem_raw[];
+  __shared__ uint64_t bars[kSkStages];
+  __shared__ float red[kT][9];
+  const int CG = f >> 3;
+  const int RPB = kT / CG;
+  const int RT = 2 * RPB;
+  const int cg = threadIdx.x % CG;
+  const int rsub = threadIdx.x / CG;
+  const int c0 = cg << 3;
+  const int64_t b = blockIdx.x;
+  const int trips = (HW + RT - 1) / RT;
+  const uint32_t sbase = (smem_u32(sk_smem_raw) + 127u) & ~127u;
+  const uint8_t* sgen = sk_smem_raw + (sbase - smem_u32(sk_smem_raw));
+  RowPipe<kSkStages> pipe(bars);
+  pipe.init(bars);
+  auto issue = [&](int t, int stage, uint32_t bar) {
+    const int r0 = t * RT;
+    const int rows = (HW - r0 < RT) ? HW - r0 : RT;
+    const int64_t row = b * HW + r0;
+    mbar_expect_tx_a(bar, rows * (MODE == 1 ? 3 : 2) * f * 2);
+    bulk_load(sbase + stage * kSkStageBytes, y + row * 2 * f, rows * 2 * f * 2, bar);
+    if (MODE == 1)
+      bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * 2, bar);
+  };
+  pipe.prologue(trips, issue);
+  float s0[8], h0[8], s1[8], h1[8], acc[8];
+  loadf8(scale + c0, s0);
+  loadf8(shift + c0, h0);
+  loadf8(scale + f + c0, s1);
+  loadf8(shift + f + c0, h1);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int t = 0; t < trips; ++t) {
+    pipe.acquire(t, trips, issue);
+    const uint8_t* sy = sgen + pipe.stage(t) * kSkStageBytes;
+    const uint8_t* sd = sy + kSkYBytes;
+    const int rows = HW - t * RT;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int rl = rsub + u * RPB;
+      if (rl < rows) {
+        float y0[8], y1[8], d[8];
+        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + c0) * 2), y0);
+        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + f + c0) * 2), y1);
+        if (MODE == 1) unpack8(*reinterpret_cast<const uint4*>(sd + (rl * f + c0) * 2), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
+          const float u1 = fmaxf(fmaf(y1[i], s1[i], h1[i]), 0.f);
+          acc[i] += (MODE == 0) ? (u0 + u1) : d[i] * (u0 - u1);
+        }
+      }
+    }
+    pipe.release();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (rsub == 0) {
+    for (int r = 1; r < RPB; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += red[r * CG + cg][i];
+    const float norm = (MODE == 0) ? 1.f / HW : 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= norm;
+    storef8(out + b * f + c0, acc);
+  }
+}
+
+template <int MODE>
+static void launch_sk_image_reduce(const bf16* y, const bf16* dv, const float* scale,
+                                   const float* shift, float* out, int B, int HW, int f,
+                                   cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(sk_image_reduce_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kSkSmemBytes);
+    attr = true;
+  }
+  sk_image_reduce_kernel<MODE><<<B, kT, kSkSmemBytes, st>>>(y, dv, scale, shift, out, HW, f);
+}
+
+// Row slabs per image for the image-aligned SK kernels: ~`ctas_per_sm` CTAs per SM overall, at
+// least one trip of the unrolled row loop (4 * rpb rows) per CTA.
+static int row_slabs(int B, int HW, int rpb, int ctas_per_sm = 8) {
+  int s = (148 * ctas_per_sm + B - 1) / B;
   const int max_s = (HW + 4 * rpb - 1) / (4 * rpb);
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;
@@ -646,8 +778,8 @@ int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const flo
 int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s, int B, int HW,
                 int f, void* stream) {
   ACNN_REQUIRE(y && scale && shift && s && cg_ok(f), "sk_gap: bad arguments f=%d", f);
-  image_reduce_kernel<0><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
-                                                             s, HW, f);
+  launch_sk_image_reduce<0>((const bf16*)y, nullptr, scale, shift, s, B, HW, f,
+                            (cudaStream_t)stream);
   count_launch();
   return check_launch("sk_gap");
 }
@@ -655,8 +787,8 @@ int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s,
 int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const float* shift,
                      float* dA, int B, int HW, int f, void* stream) {
   ACNN_REQUIRE(dv && y && scale && shift && dA && cg_ok(f), "sk_bwd_gate: bad arguments");
-  image_reduce_kernel<1><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)dv,
-                                                             scale, shift, dA, HW, f);
+  launch_sk_image_reduce<1>((const bf16*)y, (const bf16*)dv, scale, shift, dA, B, HW, f,
+                            (cudaStream_t)stream);
   count_launch();
   return check_launch("sk_bwd_gate");
 }
@@ -703,8 +835,15 @@ int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, con
                           float* sums, int B, int HW, int f, void* stream) {
   ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && sums && cg_ok(2 * f) &&
                    B <= 65535, "sk_bn_bwd_reduce: bad arguments");
-  dim3 grid(row_slabs(B, HW, kT / (f >> 2)), B);
-  sk_bn_bwd_reduce_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>(
+  // one resident wave of long-lived CTAs: every CTA ends with one atomic per channel
+  dim3 grid(row_slabs(B, HW, kT / (f >> 2), 2), B);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(sk_bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kSkSmemBytes);
+    attr = true;
+  }
+  sk_bn_bwd_reduce_kernel<<<grid, kT, kSkSmemBytes, (cudaStream_t)stream>>>(
       (const bf16*)dv, (const bf16*)y, scale, shift, mean, rstd, att, ds, sums, HW, f);
   count_launch();
   return check_launch("sk_bn_bwd_reduce");
@@ -716,7 +855,13 @@ int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, cons
   ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && cg_ok(2 * f) && B <= 65535,
                "sk_bn_bwd_apply: bad arguments");
   dim3 grid(row_slabs(B, HW, kT / (f >> 2)), B);
-  sk_bn_bwd_apply_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>(
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(sk_bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kSkSmemBytes);
+    attr = true;
+  }
+  sk_bn_bwd_apply_kernel<<<grid, kT, kSkSmemBytes, (cudaStream_t)stream>>>(
       (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f);
   count_launch();
   return check_launch("sk_bn_bwd_apply");

@@ -32,16 +32,17 @@ __device__ __forceinline__ int reflect(int i, int n) {
 // ---------------------------------------------------------------------------- blur-pool
 __global__ void __launch_bounds__(kPT)
 blurpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Binomial bw, int H, int W,
-                    int C, int filt, int stride, int pad, int Ho, int Wo, int64_t nvec) {
+                    int C, int filt, int stride, int pad, int Ho, int Wo) {
+  // grid = (ceil(Wo * C/8 / threads), Ho, B): no 64-bit index decomposition per element
   const int CG = C >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    int64_t t = i / CG;
-    const int q = (int)(t % Wo);
-    t /= Wo;
-    const int p = (int)(t % Ho);
-    const int64_t b = t / Ho;
+  const int idx = blockIdx.x * kPT + threadIdx.x;
+  if (idx >= Wo * CG) return;
+  const int q = idx / CG;
+  const int cg = idx - q * CG;
+  const int p = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  {
+    const int64_t i = ((b * Ho + p) * Wo + q) * CG + cg;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -82,17 +83,18 @@ __device__ __forceinline__ void blur_adjoint_1d(int i, int n, int no, const Bino
 __global__ void __launch_bounds__(kPT)
 blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                     const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src,
-                    Binomial bw, int H, int W, int C, int filt, int stride, int pad, int Ho, int Wo,
-                    int64_t nvec) {
+                    Binomial bw, int H, int W, int C, int filt, int stride, int pad, int Ho,
+                    int Wo) {
+  // grid = (ceil(W * C/8 / threads), H, B)
   const int CG = C >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    int64_t t = i / CG;
-    const int iw = (int)(t % W);
-    t /= W;
-    const int ih = (int)(t % H);
-    const int64_t b = t / H;
+  const int idx = blockIdx.x * kPT + threadIdx.x;
+  if (idx >= W * CG) return;
+  const int iw = idx / CG;
+  const int cg = idx - iw * CG;
+  const int ih = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  {
+    const int64_t i = ((b * H + ih) * W + iw) * CG + cg;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -113,16 +115,17 @@ blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 // ---------------------------------------------------------------------------- avg / max pool
 __global__ void __launch_bounds__(kPT)
 avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
-                   int stride, int pad, int Ho, int Wo, int count_pad, int64_t nvec) {
+                   int stride, int pad, int Ho, int Wo, int count_pad) {
+  // grid = (ceil(Wo * C/8 / threads), Ho, B)
   const int CG = C >> 3;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    int64_t t = i / CG;
-    const int q = (int)(t % Wo);
-    t /= Wo;
-    const int p = (int)(t % Ho);
-    const int64_t b = t / Ho;
+  const int idx = blockIdx.x * kPT + threadIdx.x;
+  if (idx >= Wo * CG) return;
+  const int q = idx / CG;
+  const int cg = idx - q * CG;
+  const int p = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  {
+    const int64_t i = ((b * Ho + p) * Wo + q) * CG + cg;
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -517,9 +520,10 @@ int acnn_blurpool_fwd(const void* x, void* out, int B, int H, int W, int C, int 
   const int pad = (filt - 1) / 2;
   ACNN_REQUIRE(pad < H && pad < W, "blurpool_fwd: reflect pad %d >= size", pad);
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
-  const int64_t nvec = (int64_t)B * Ho * Wo * C / 8;
-  blurpool_fwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)out, binomial(filt), H, W, C, filt, stride, pad, Ho, Wo, nvec);
+  ACNN_REQUIRE(Ho <= 65535 && B <= 65535, "blurpool_fwd: Ho / B exceed the grid limits");
+  dim3 grid(ceil_div(Wo * (C / 8), kPT), Ho, B);
+  blurpool_fwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)out, binomial(filt), H, W, C, filt, stride, pad, Ho, Wo);
   count_launch();
   return check_launch("blurpool_fwd");
 }
@@ -530,10 +534,11 @@ int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const voi
                "blurpool_bwd: bad arguments");
   const int pad = (filt - 1) / 2;
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
-  const int64_t nvec = (int64_t)B * H * W * C / 8;
-  blurpool_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
+  ACNN_REQUIRE(H <= 65535 && B <= 65535, "blurpool_bwd: H / B exceed the grid limits");
+  dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
+  blurpool_bwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
       (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, binomial(filt), H,
-      W, C, filt, stride, pad, Ho, Wo, nvec);
+      W, C, filt, stride, pad, Ho, Wo);
   count_launch();
   return check_launch("blurpool_bwd");
 }
@@ -541,9 +546,10 @@ int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const voi
 int acnn_avgpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
                      int pad_lo, int Ho, int Wo, int count_pad, void* stream) {
   ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_fwd: bad arguments");
-  const int64_t nvec = (int64_t)B * Ho * Wo * C / 8;
-  avgpool_fwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad, nvec);
+  ACNN_REQUIRE(Ho <= 65535 && B <= 65535, "avgpool_fwd: Ho / B exceed the grid limits");
+  dim3 grid(ceil_div(Wo * (C / 8), kPT), Ho, B);
+  avgpool_fwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad);
   count_launch();
   return check_launch("avgpool_fwd");
 }
