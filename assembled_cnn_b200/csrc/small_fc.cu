@@ -218,154 +218,6 @@ static int ew(const float* in, const float* act, float* out, int64_t n, int mode
   return check_launch("ew");
 }
 
-// 64x64x16 tile of C = A*B with element functors; fa(m,k), fb(k,n) must be safe for any in-range
-// index.  A_M_CONTIG / B_N_CONTIG pick the load mapping that is coalesced in global memory.
-template <bool A_M_CONTIG, bool B_N_CONTIG, class FA, class FB, class EPI>
-__device__ __forceinline__ void tile_sgemm(int m0, int n0, int M, int N, int K, FA fa, FB fb,
-                                           EPI epi) {
-  __shared__ float As[kTK][kTM + 4];
-  __shared__ float Bs[kTK][kTN + 4];
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += kTK) {
-#pragma unroll
-    for (int e = 0; e < (kTM * kTK) / kFT; ++e) {
-      const int idx = tid + e * kFT;
-      int mm, kk;
-      if (A_M_CONTIG) { mm = idx % kTM; kk = idx / kTM; } else { kk = idx % kTK; mm = idx / kTK; }
-      const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < K) ? fa(m, k) : 0.f;
-    }
-#pragma unroll
-    for (int e = 0; e < (kTN * kTK) / kFT; ++e) {
-      const int idx = tid + e * kFT;
-      int nn, kk;
-      if (B_N_CONTIG) { nn = idx % kTN; kk = idx / kTN; } else { kk = idx % kTK; nn = idx / kTK; }
-      const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < N && k < K) ? fb(k, n) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < kTK; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
-    if (m >= M) continue;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
-      if (n < N) epi(m, n, acc[i][j]);
-    }
-  }
-}
-
-// att[b,c] = sigmoid(z[b,:] . (W2[c,:] - W2[c+f,:]))   (2-way softmax == sigmoid of the difference)
-// zpre[B, d] = s[B, f] * W1[d, f]^T, stored directly (one CTA per 64 x 64 tile, whole K)
-__global__ void __launch_bounds__(kFT)
-sk_fc1_kernel(const float* __restrict__ s, const float* __restrict__ w1, float* __restrict__ zpre,
-              int B, int f, int d) {
-  tile_sgemm<false, false>(
-      blockIdx.y * kTM, blockIdx.x * kTN, B, d, f,
-      [=](int m, int k) { return __ldg(s + (size_t)m * f + k); },
-      [=](int k, int n) { return __ldg(w1 + (size_t)n * f + k); },
-      [=](int m, int n, float v) { zpre[(size_t)m * d + n] = v; });
-}
-
-// att = sigmoid(a0 - a1) with a = z * W2^T: one GEMM against the row differences of W2
-__global__ void __launch_bounds__(kFT)
-sk_fc2_gate_kernel(const float* __restrict__ z, const float* __restrict__ w2,
-                   float* __restrict__ att, int B, int f, int d) {
-  tile_sgemm<false, false>(
-      blockIdx.y * kTM, blockIdx.x * kTN, B, f, d,
-      [=](int m, int k) { return __ldg(z + (size_t)m * d + k); },
-      [=](int k, int n) {
-        return __ldg(w2 + (size_t)n * d + k) - __ldg(w2 + (size_t)(n + f) * d + k);
-      },
-      [=](int m, int n, float v) { att[(size_t)m * f + n] = 1.f / (1.f + expf(-v)); });
-}
-
-// dz[B, d] = t * (W2[:f] - W2[f:]) with t = att (1 - att) dA computed on the fly (the gradient of
-// the 2-way softmax written as a sigmoid of the logit difference)
-__global__ void __launch_bounds__(kFT)
-sk_dz_kernel(const float* __restrict__ dA, const float* __restrict__ att,
-             const float* __restrict__ w2, float* __restrict__ dz, int B, int f, int d) {
-  tile_sgemm<false, true>(
-      blockIdx.y * kTM, blockIdx.x * kTN, B, d, f,
-      [=](int m, int k) {
-        const float a = __ldg(att + (size_t)m * f + k);
-        return a * (1.f - a) * __ldg(dA + (size_t)m * f + k);
-      },
-      [=](int k, int n) {
-        return __ldg(w2 + (size_t)k * d + n) - __ldg(w2 + (size_t)(k + f) * d + n);
-      },
-      [=](int m, int n, float v) { dz[(size_t)m * d + n] = v; });
-}
-
-// Three independent GEMMs in one launch (blockIdx.x enumerates the tiles of all of them):
-//   P1  G[c][j]  = sum_b t[b,c] z[b,j]      -> dW2[c] += G, dW2[c+f] -= G         (f x d, K = B)
-//   P2  dW1[j][c] += sum_b dzpre[b,j] s[b,c]                                        (d x f, K = B)
-//   P3  ds[b][c]  = sum_j dzpre[b,j] W1[j][c]                                       (B x f, K = d)
-__global__ void __launch_bounds__(kFT)
-sk_fc_bwd2_kernel(const float* __restrict__ dA, const float* __restrict__ att,
-                  const float* __restrict__ z, const float* __restrict__ dzpre,
-                  const float* __restrict__ s, const float* __restrict__ w1, float* dw1,
-                  float* dw2, float* __restrict__ ds, int B, int f, int d) {
-  const int tf = (f + kTM - 1) / kTM, td = (d + kTM - 1) / kTM, tb = (B + kTM - 1) / kTM;
-  int t = blockIdx.x;
-  if (t < tf * td) {
-    const int mt = t / td, nt = t % td;
-    tile_sgemm<true, true>(
-        mt * kTM, nt * kTN, f, d, B,
-        [=](int m, int k) {
-          const float a = __ldg(att + (size_t)k * f + m);
-          return a * (1.f - a) * __ldg(dA + (size_t)k * f + m);
-        },
-        [=](int k, int n) { return __ldg(z + (size_t)k * d + n); },
-        [=](int m, int n, float v) {
-          dw2[(size_t)m * d + n] += v;
-          dw2[(size_t)(m + f) * d + n] -= v;
-        });
-    return;
-  }
-  t -= tf * td;
-  if (t < td * tf) {
-    const int mt = t / tf, nt = t % tf;
-    tile_sgemm<true, true>(
-        mt * kTM, nt * kTN, d, f, B,
-        [=](int m, int k) { return __ldg(dzpre + (size_t)k * d + m); },
-        [=](int k, int n) { return __ldg(s + (size_t)k * f + n); },
-        [=](int m, int n, float v) { dw1[(size_t)m * f + n] += v; });
-    return;
-  }
-  t -= td * tf;
-  {
-    const int mt = t / tf, nt = t % tf;
-    if (mt >= tb) return;
-    tile_sgemm<false, true>(
-        mt * kTM, nt * kTN, B, f, d,
-        [=](int m, int k) { return __ldg(dzpre + (size_t)m * d + k); },
-        [=](int k, int n) { return __ldg(w1 + (size_t)k * f + n); },
-        [=](int m, int n, float v) { ds[(size_t)m * f + n] = v; });
-  }
-}
-
 }  // namespace acnn
 
 using namespace acnn;
@@ -379,20 +231,18 @@ int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const fl
   ACNN_REQUIRE(s && w1 && gamma && beta && moving_mean && moving_var && w2 && zpre && bnstat && z &&
                    att && scratch, "sk_fc_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  // three launches: fc1 (direct store), batch-norm over the batch + ReLU, fc2 + gate
-  dim3 g1(ceil_div(d, kTN), ceil_div(B, kTM));
-  sk_fc1_kernel<<<g1, kFT, 0, st>>>(s, w1, zpre, B, f, d);
-  count_launch();
-  int rc = check_launch("sk_fc1");
+  // zpre[B,d] = s[B,f] * W1[d,f]^T
+  int rc = sgemm(s, w1, zpre, B, d, f, f, 1, 1, f, true, st);
   if (rc) return rc;
   bn_batch_relu_fwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(
       zpre, gamma, beta, moving_mean, moving_var, momentum, eps, training, z, bnstat, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_fwd"))) return rc;
-  dim3 g2(ceil_div(f, kTN), ceil_div(B, kTM));
-  sk_fc2_gate_kernel<<<g2, kFT, 0, st>>>(z, w2, att, B, f, d);
+  // a[B,2f] = z[B,d] * W2[2f,d]^T
+  if ((rc = sgemm(z, w2, scratch, B, 2 * f, d, d, 1, 1, d, true, st))) return rc;
+  sk_gate_fwd_kernel<<<(int)ceil_div64((int64_t)B * f, 256), 256, 0, st>>>(scratch, att, B, f);
   count_launch();
-  return check_launch("sk_fc2_gate");
+  return check_launch("sk_gate_fwd");
 }
 
 int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const float* zpre,
@@ -402,23 +252,24 @@ int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const floa
   ACNN_REQUIRE(dA && att && z && zpre && bnstat && gamma && s && w1 && w2 && dw1 && dw2 && dgamma &&
                    dbeta && ds && scratch, "sk_fc_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  // three launches: dz GEMM, batch-norm backward over the batch (in place -> dzpre), then the
-  // three remaining GEMMs (dW2, dW1, ds) as one grid
-  float* dz = scratch;                       // [B][d]
-  dim3 g1(ceil_div(d, kTN), ceil_div(B, kTM));
-  sk_dz_kernel<<<g1, kFT, 0, st>>>(dA, att, w2, dz, B, f, d);
+  float* da = scratch;                       // [B][2f]
+  float* dz = scratch + (size_t)B * 2 * f;   // [B][d]
+  sk_gate_bwd_kernel<<<(int)ceil_div64((int64_t)B * f, 256), 256, 0, st>>>(dA, att, da, B, f);
   count_launch();
-  int rc = check_launch("sk_dz");
+  int rc = check_launch("sk_gate_bwd");
   if (rc) return rc;
+  // dW2[2f,d] += da^T[2f,B] * z[B,d]
+  if ((rc = sgemm(da, z, dw2, 2 * f, d, B, 1, 2 * f, d, 1, false, st))) return rc;
+  // dz[B,d] = da[B,2f] * W2[2f,d]
+  if ((rc = sgemm(da, w2, dz, B, d, 2 * f, 2 * f, 1, d, 1, true, st))) return rc;
   bn_batch_relu_bwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(dz, z, zpre, bnstat, gamma,
                                                                   dgamma, dbeta, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_bwd"))) return rc;
-  const int tf = ceil_div(f, kTM), td = ceil_div(d, kTM), tb = ceil_div(B, kTM);
-  sk_fc_bwd2_kernel<<<2 * tf * td + tb * tf, kFT, 0, st>>>(dA, att, z, dz, s, w1, dw1, dw2, ds, B,
-                                                          f, d);
-  count_launch();
-  return check_launch("sk_fc_bwd2");
+  // dW1[d,f] += dzpre^T[d,B] * s[B,f]
+  if ((rc = sgemm(dz, s, dw1, d, f, B, 1, d, f, 1, false, st))) return rc;
+  // ds[B,f] = dzpre[B,d] * W1[d,f]
+  return sgemm(dz, w1, ds, B, f, d, d, 1, f, 1, true, st);
 }
 
 int acnn_se_fc_fwd(const float* q, const float* w1, const float* w2, float* h, float* e, int B,
