@@ -110,16 +110,17 @@ def full(src, dst):
                 if h in KEYS:
                     fh.write("| %s | %s | %s |\n" % (h, u, v))
             fh.write("\n")
-        src_csv = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv"], capture_output=True,
-                                 text=True).stdout
+        src_csv = subprocess.run(["ncu", "-i", src, "--page", "source", "--csv", "--print-source",
+                                  "sass"], capture_output=True, text=True).stdout
         srows = list(csv.reader(src_csv.splitlines()))
         if len(srows) > 2:
             h = srows[1]
             try:
                 ia, isamp = h.index("Source"), h.index("# Samples")
-                data = [(int(r[isamp]), r[ia].strip()) for r in srows[2:] if r[isamp].isdigit()]
+                data = [(int(r[isamp]), r[ia].strip()) for r in srows[2:]
+                        if len(r) > max(ia, isamp) and r[isamp].isdigit()]
                 tot = sum(x[0] for x in data) or 1
-                fh.write("Top warp-stall sample sites (SASS):\n\n| samples | share | instruction |\n|---:|---:|---|\n")
+                fh.write("Top warp-stall sample sites (SASS, all captured kernels of this report):\n\n| samples | share | instruction |\n|---:|---:|---|\n")
                 for sm, ins in sorted(data, reverse=True)[:8]:
                     fh.write("| %d | %.1f%% | `%s` |\n" % (sm, 100 * sm / tot, ins[:90]))
             except ValueError:
