@@ -153,9 +153,13 @@ constexpr int kEpiThreads = 256;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 224 * 1024;   // dynamic smem (227 KiB max per CTA, ~0.2 KiB static)
 
-template <int BN>
+// MT = 128-row M tiles per CTA tile (1 or 2).  With MT = 2 a CTA computes two output tiles that
+// share every weight stage: twice the tensor work per pipeline round-trip (the single-warp issue
+// loops, not bandwidth, bound the N <= 128 layers) and half the weight traffic per FLOP.
+template <int BN, int MT>
 struct FpropCfg {
-  static constexpr int kABytes = kBM * kStageK * 2;   // 16 KiB
+  static constexpr int kAHalfBytes = kBM * kStageK * 2;   // 16 KiB per M tile
+  static constexpr int kABytes = MT * kAHalfBytes;
   static constexpr int kBBytes = BN * kStageK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // the epilogue handles the accumulator in column halves of <= 128 (one staging buffer each for
@@ -164,7 +168,8 @@ struct FpropCfg {
   static constexpr int kNHalf = BN / kHalfN;
   static constexpr int kSubW = kHalfN < 64 ? kHalfN : 64;  // staging sub-tile width (TMA box)
   static constexpr int kTileBytes = kBM * kHalfN * 2;      // one staged half tile (bf16)
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulator stages
+  static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;   // two accumulator stages
+  static_assert(2 * MT * BN <= 512, "TMEM holds 512 columns");
   // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
   static int stages_for(bool has_add, bool has_mask, bool out_f32) {
     const int fixed = 1024 + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
@@ -219,12 +224,13 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // runs ahead across tiles through the smem ring; the MMA issuer alternates between two TMEM
 // accumulators; the 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks)
 // drain accumulator i while the tensor core fills i^1.
-template <int BN, int CW, bool IM2COL>
+template <int BN, int CW, bool IM2COL, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd,
                  const __grid_constant__ CUtensorMap tmMask, const ConvGemmParams p) {
-  using Cfg = FpropCfg<BN>;
+  using Cfg = FpropCfg<BN, MT>;
+  constexpr int kTileM = MT * kBM;              // output pixels per CTA tile
   constexpr int kChunks = kStageK / CW;        // A chunks (one filter tap each when Cin < 64)
   constexpr int kChunkBytes = kBM * CW * 2;
   constexpr int kKSteps = CW / 16;             // UMMA K = 16 bf16
@@ -299,19 +305,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // election loops) and every lane tracks the same loop state; one elected lane issues.
     uint32_t soff = 0, sbar = 0, phase = 0;             // stage byte offset / barrier offset
     const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
-    const uint32_t full_bytes = kChunks * kChunkBytes + b_bytes;
-    const uint32_t tail_bytes = tail_chunks * kChunkBytes + b_bytes;
+    const uint32_t full_bytes = MT * kChunks * kChunkBytes + b_bytes;
+    const uint32_t tail_bytes = MT * tail_chunks * kChunkBytes + b_bytes;
     const int Cin = p.Cin, fkw = p.kw;
     for (int it = 0; it < my_tiles; ++it) {
-      const int m0 = (m_first + it * m_step) * kBM;
-      int img = 0, h0 = 0, w0 = 0;
-      if (IM2COL) {
-        img = m0 / p.HoWo;
-        const int rem = m0 - img * p.HoWo;
-        const int po = rem / p.Wo;
-        const int qo = rem - po * p.Wo;
-        h0 = po * p.stride - p.pad_h_lo;
-        w0 = qo * p.stride - p.pad_w_lo;
+      const int m0 = (m_first + it * m_step) * kTileM;
+      int img[MT], h0[MT], w0[MT];
+#pragma unroll
+      for (int h = 0; h < MT; ++h) {
+        img[h] = h0[h] = w0[h] = 0;
+        if (IM2COL) {
+          const int mh = m0 + h * kBM;
+          img[h] = mh / p.HoWo;
+          const int rem = mh - img[h] * p.HoWo;
+          const int po = rem / p.Wo;
+          const int qo = rem - po * p.Wo;
+          h0[h] = po * p.stride - p.pad_h_lo;
+          w0[h] = qo * p.stride - p.pad_w_lo;
+        }
       }
       // filter tap (tr, ts) and channel offset tc of the next chunk, advanced incrementally
       int tr = 0, ts = 0, tc = 0, k0 = 0;
@@ -330,11 +341,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < kChunks; ++j) {
           if (j < nch) {
             if (leader) {
-              if (IM2COL) {
-                tma_load_im2col_4d_a(sa + j * kChunkBytes, &tmA, fb, tc, w0, h0, img,
-                                     (uint16_t)ts, (uint16_t)tr);
-              } else {
-                tma_load_2d_a(sa + j * kChunkBytes, &tmA, fb, k0 + j * CW, m0);
+#pragma unroll
+              for (int h = 0; h < MT; ++h) {
+                const uint32_t dst = sa + h * Cfg::kAHalfBytes + j * kChunkBytes;
+                if (IM2COL) {
+                  tma_load_im2col_4d_a(dst, &tmA, fb, tc, w0[h], h0[h], img[h], (uint16_t)ts,
+                                       (uint16_t)tr);
+                } else {
+                  tma_load_2d_a(dst, &tmA, fb, k0 + j * CW, m0 + h * kBM);
+                }
               }
             }
             tc += CW;
@@ -365,7 +380,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);   // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * BN;
+      const uint32_t tmem_d = tmem_base + acc * (MT * BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const bool last = kb == num_kb - 1;
         const int nch = (kChunks > 1 && last) ? tail_chunks : kChunks;
@@ -378,10 +393,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < kChunks; ++j) {
             if (j < nch) {
 #pragma unroll
-              for (int ks = 0; ks < kKSteps; ++ks) {
-                umma_bf16(tmem_d, da0 + ((j * kChunkBytes + ks * 32) >> 4),
-                          db0 + (((j * kKSteps + ks) * 32) >> 4), kIdesc,
-                          (j | ks) ? 1u : static_cast<uint32_t>(kb != 0));
+              for (int h = 0; h < MT; ++h) {
+#pragma unroll
+                for (int ks = 0; ks < kKSteps; ++ks) {
+                  umma_bf16(tmem_d + h * BN,
+                            da0 + ((h * Cfg::kAHalfBytes + j * kChunkBytes + ks * 32) >> 4),
+                            db0 + (((j * kKSteps + ks) * 32) >> 4), kIdesc,
+                            (j | ks) ? 1u : static_cast<uint32_t>(kb != 0));
+                }
               }
             }
           }
@@ -420,9 +439,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t aux_n = 0;                                // completed aux-barrier phases
 
     for (int it = 0; it < my_tiles; ++it) {
-      const int m0 = (m_first + it * m_step) * kBM;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+#pragma unroll
+      for (int mh = 0; mh < MT; ++mh) {
+      const int m0 = (m_first + it * m_step) * kTileM + mh * kBM;
+      const uint32_t acc_col = acc * (MT * BN) + mh * BN;
       const int row = m0 + r;
       const bool row_ok = row < p.M;
 #pragma unroll
@@ -444,7 +466,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");   // staging buffers free for everyone
-        if (hf == 0) {
+        if (hf == 0 && mh == 0) {
           mbar_wait(&tfull_bar[acc], acc_phase);
           tc_fence_after();
         }
@@ -457,7 +479,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int c = c2 * 2 + egrp;                   // this warp group's chunk
           if (c >= kHalfN / 32) break;                   // warp-uniform
           uint32_t v[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN +
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col +
                             hf * kHalfN + c * 32, v);
           tmem_ld_wait();
           float f[32];
@@ -519,11 +541,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // half drained and staged: (after the last half) hand TMEM back, then store
-        if (hf == kNHalf - 1) tc_fence_before();
+        if (hf == kNHalf - 1 && mh == MT - 1) tc_fence_before();
         if (!p.out_f32) fence_proxy_async();             // generic smem writes -> async proxy
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (leader) {
-          if (hf == kNHalf - 1) mbar_arrive(&tempty_bar[acc]);
+          if (hf == kNHalf - 1 && mh == MT - 1) mbar_arrive(&tempty_bar[acc]);
           if (!p.out_f32) {
 #pragma unroll
             for (int sub = 0; sub < kNSub; ++sub)
@@ -554,6 +576,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      }   // mh
     }
     if (leader && !p.out_f32) tma_store_wait_all();
     if (stats && my_tiles > 0) {
@@ -793,11 +816,11 @@ struct ConvMaps {
   CUtensorMap a, b, c, add, mask;
 };
 
-template <int BN, int CW, bool IM2COL>
+template <int BN, int CW, bool IM2COL, int MT>
 static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStream_t stream) {
-  using Cfg = FpropCfg<BN>;
+  using Cfg = FpropCfg<BN, MT>;
   static bool attr_set = false;
-  auto kern = conv_gemm_kernel<BN, CW, IM2COL>;
+  auto kern = conv_gemm_kernel<BN, CW, IM2COL, MT>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBudget + 2048);
@@ -808,10 +831,8 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
     attr_set = true;
   }
   ConvGemmParams q = p;
-  const int num_kb = ceil_div(p.Ktot, kStageK);
   q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32);
-  (void)num_kb;
-  q.m_tiles = ceil_div(p.M, kBM);
+  q.m_tiles = ceil_div(p.M, MT * kBM);
   q.n_tiles = p.Cout / BN;
   // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
   // its per-channel statistics), at most one CTA per SM
@@ -825,17 +846,42 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
   return check_launch("conv_gemm_kernel");
 }
 
+// -1: choose per problem; 1 / 2: force that many M tiles per CTA tile where the shape allows it
+static int g_conv_mtiles_mode = -1;
+
 template <int BN>
 static int dispatch_conv_gemm(int cw, bool im2col, const ConvMaps& tm, const ConvGemmParams& p,
                               cudaStream_t s) {
-  if (im2col) {
-    if (cw == 64) return launch_conv_gemm<BN, 64, true>(tm, p, s);
-    if (cw == 32) return launch_conv_gemm<BN, 32, true>(tm, p, s);
-    return launch_conv_gemm<BN, 16, true>(tm, p, s);
+  // Two M tiles per CTA when TMEM has room (N <= 128), the smem ring stays >= 3 stages deep (at
+  // N = 128 only without the add / mask staging buffers) and there are enough tiles to keep every
+  // SM busy for several rounds.
+  bool two = false;
+  if constexpr (BN <= 128) {
+    const bool fits = BN <= 64 || (!p.has_add && !p.has_mask);
+    const int64_t tiles = (int64_t)ceil_div(p.M, 2 * kBM) * (p.Cout / BN);
+    two = fits && !p.out_f32 &&
+          (g_conv_mtiles_mode == 2 || (g_conv_mtiles_mode == -1 && tiles >= 4 * (int64_t)num_sms()));
   }
-  if (cw == 64) return launch_conv_gemm<BN, 64, false>(tm, p, s);
-  if (cw == 32) return launch_conv_gemm<BN, 32, false>(tm, p, s);
-  return launch_conv_gemm<BN, 16, false>(tm, p, s);
+  if constexpr (BN <= 128) {
+    if (two) {
+      if (im2col) {
+        if (cw == 64) return launch_conv_gemm<BN, 64, true, 2>(tm, p, s);
+        if (cw == 32) return launch_conv_gemm<BN, 32, true, 2>(tm, p, s);
+        return launch_conv_gemm<BN, 16, true, 2>(tm, p, s);
+      }
+      if (cw == 64) return launch_conv_gemm<BN, 64, false, 2>(tm, p, s);
+      if (cw == 32) return launch_conv_gemm<BN, 32, false, 2>(tm, p, s);
+      return launch_conv_gemm<BN, 16, false, 2>(tm, p, s);
+    }
+  }
+  if (im2col) {
+    if (cw == 64) return launch_conv_gemm<BN, 64, true, 1>(tm, p, s);
+    if (cw == 32) return launch_conv_gemm<BN, 32, true, 1>(tm, p, s);
+    return launch_conv_gemm<BN, 16, true, 1>(tm, p, s);
+  }
+  if (cw == 64) return launch_conv_gemm<BN, 64, false, 1>(tm, p, s);
+  if (cw == 32) return launch_conv_gemm<BN, 32, false, 1>(tm, p, s);
+  return launch_conv_gemm<BN, 16, false, 1>(tm, p, s);
 }
 
 static int chunk_width(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
@@ -1011,6 +1057,12 @@ static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* d
 // C ABI
 // ------------------------------------------------------------------------------------------
 extern "C" {
+
+int acnn_set_conv_mtiles(int mode) {
+  const int prev = acnn::g_conv_mtiles_mode;
+  acnn::g_conv_mtiles_mode = (mode == 1 || mode == 2) ? mode : -1;
+  return prev;
+}
 
 int acnn_conv_fprop(const acnn_conv_geom* g, const void* x, const void* w, void* y, float* ch_sum,
                     float* ch_sumsq, const void* add_src, const void* mask_src, const float* bias,

@@ -34,6 +34,10 @@ const char* acnn_last_error(void);
 int acnn_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t acnn_launch_count(void);
+/* Tuning knob of the conv GEMM launcher (no effect on results): M tiles (128 output pixels each)
+ * per CTA tile.  -1 = choose per problem (default), 1 = always one, 2 = two wherever the shape
+ * allows it (N tile <= 128).  Returns the previous mode. */
+int acnn_set_conv_mtiles(int mode);
 
 /* Convolution geometry (correlation, no bias) -- nets/model_helper.py:67-78 conv2d_fixed_padding
  * + fixed_padding :40-64.  Ho = (H + pad_h_lo + pad_h_hi - kh) / stride + 1, same for W. */

@@ -4,6 +4,8 @@ Inputs are bf16-representable, so the only differences are fp32 accumulation ord
 bf16 rounding of the output: tolerance = 2^-8 relative to the tensor's max magnitude for bf16
 outputs, 1e-4 for fp32 outputs (wgrad, logits).
 """
+import contextlib
+
 import pytest
 import torch
 
@@ -41,6 +43,19 @@ def _relerr(a, b):
     return (a.double() - b.double()).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
+@contextlib.contextmanager
+def _mtiles(lib, mode):
+    """acnn_set_conv_mtiles: 2 forces two 128-pixel M tiles per CTA tile wherever legal."""
+    prev = lib.acnn_set_conv_mtiles(mode)
+    try:
+        yield
+    finally:
+        lib.acnn_set_conv_mtiles(prev)
+
+
+MT = [1, 2]
+MT_IDS = ["mt1", "mt2"]
+
 CASES = [
     # B, H, W, Cin, Cout, k, stride, pads
     (2, 16, 16, 64, 128, 1, 1, None),      # plain 1x1, SW128
@@ -58,8 +73,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("mt", MT, ids=MT_IDS)
 @pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
-def test_fprop_matches_oracle(lib, case):
+def test_fprop_matches_oracle(lib, case, mt):
     from assembled_cnn_b200 import _lib
     B, H, W, Cin, Cout, k, stride, pads = case
     g = _geom(B, H, W, Cin, Cout, k, stride, pads)
@@ -74,14 +90,48 @@ def test_fprop_matches_oracle(lib, case):
     s1 = torch.zeros(Cout, device="cuda")
     s2 = torch.zeros(Cout, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(), s1.data_ptr(),
-                                   s2.data_ptr(), None, None, None, 0, st), "conv_fprop")
+    with _mtiles(lib, mt):
+        _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(),
+                                       s1.data_ptr(), s2.data_ptr(), None, None, None, 0, st),
+                   "conv_fprop")
     torch.cuda.synchronize()
     y = yd.float().cpu()
     assert _relerr(y, ref) < BF16_TOL
     # fused batch-norm statistics are those of the stored (rounded) tensor
     assert _relerr(s1.cpu(), y.sum(dim=(0, 1, 2))) < 1e-3 or (s1.cpu() - y.sum(dim=(0, 1, 2))).abs().max() < 1e-2
     assert _relerr(s2.cpu(), (y * y).sum(dim=(0, 1, 2))) < 1e-3
+
+
+@pytest.mark.parametrize("mt", MT, ids=MT_IDS)
+@pytest.mark.parametrize("cout", [64, 128])
+def test_many_tiles_per_cta(lib, mt, cout):
+    """392 M tiles (196 double tiles): every persistent CTA walks several tiles, the smem ring
+    wraps many times and both TMEM accumulator stages are reused; with add + mask epilogue tiles
+    (which at N = 128 forces the single-M-tile kernel even in mode 2)."""
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout = 16, 56, 56, 64, cout
+    g = _geom(B, H, W, Cin, Cout, 3, 1)
+    x = _rand_bf16(B, H, W, Cin, seed=11)
+    w_hwio = _rand_bf16(3, 3, Cin, Cout, seed=12, scale=(9 * Cin) ** -0.5)
+    add = _rand_bf16(B, H, W, Cout, seed=13)
+    mask = _rand_bf16(B, H, W, Cout, seed=14)
+    ref = _ref_conv(x, w_hwio, g)
+    st = torch.cuda.current_stream().cuda_stream
+    xd, wd = x.bfloat16().cuda(), w_hwio.permute(3, 0, 1, 2).contiguous().bfloat16().cuda()
+    addd, maskd = add.bfloat16().cuda(), mask.bfloat16().cuda()
+    yd = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    y2 = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+    s1, s2 = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+    with _mtiles(lib, mt):
+        _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(),
+                                       s1.data_ptr(), s2.data_ptr(), None, None, None, 0, st))
+        _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), y2.data_ptr(), None, None,
+                                       addd.data_ptr(), maskd.data_ptr(), None, 0, st))
+    torch.cuda.synchronize()
+    y = yd.float().cpu()
+    assert _relerr(y, ref) < BF16_TOL
+    assert _relerr(s2.cpu(), (y * y).sum(dim=(0, 1, 2))) < 1e-3
+    assert _relerr(y2.float().cpu(), (ref + add) * (mask > 0)) < BF16_TOL
 
 
 def test_fprop_epilogue_add_mask_bias(lib):
@@ -116,8 +166,9 @@ def test_fprop_epilogue_add_mask_bias(lib):
 DGRAD_CASES = [c for c in CASES if c[6] == 1]
 
 
+@pytest.mark.parametrize("mt", MT, ids=MT_IDS)
 @pytest.mark.parametrize("case", DGRAD_CASES, ids=[str(c) for c in DGRAD_CASES])
-def test_dgrad_matches_autograd(lib, case):
+def test_dgrad_matches_autograd(lib, case, mt):
     from assembled_cnn_b200 import _lib
     B, H, W, Cin, Cout, k, stride, pads = case
     if Cout % 16 or Cin % 32:
@@ -133,8 +184,9 @@ def test_dgrad_matches_autograd(lib, case):
     dxd = torch.empty(B, H, W, Cin, dtype=torch.bfloat16, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     dyd = dy.bfloat16().cuda()
-    _lib.check(lib.acnn_conv_dgrad(g, dyd.data_ptr(), wdg.data_ptr(),
-                                   dxd.data_ptr(), None, None, st), "conv_dgrad")
+    with _mtiles(lib, mt):
+        _lib.check(lib.acnn_conv_dgrad(g, dyd.data_ptr(), wdg.data_ptr(),
+                                       dxd.data_ptr(), None, None, st), "conv_dgrad")
     torch.cuda.synchronize()
     assert _relerr(dxd.float().cpu(), dx_ref) < BF16_TOL
 

@@ -21,10 +21,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--ncu", action="store_true")
 ap.add_argument("--top", type=int, default=40)
+ap.add_argument("--conv-mtiles", type=int, default=-1,
+                help="acnn_set_conv_mtiles mode: -1 auto, 1 one M tile per CTA tile, 2 two where legal")
 ap.add_argument("--csv", default="", help="write every conv GEMM launch (ms, ideal, shape) here")
 args = ap.parse_args()
 
 B = args.batch
+if args.conv_mtiles != -1:
+    from assembled_cnn_b200 import _lib as _l
+    _l.load().acnn_set_conv_mtiles(args.conv_mtiles)
 params = params_from_flags(batch_size=B, **MODEL_FLAGS, **TRAIN_FLAGS)
 model = Model(50, num_classes=1001, resnet_version=2, use_sk_block=True, anti_alias_type="sconv",
               anti_alias_filter_size=3)
