@@ -633,23 +633,30 @@ struct WgradParams {
 
 constexpr int kWgPix = 64;   // pixels per pipeline stage (4 UMMA K-steps)
 
-template <int BN>
+// MT = 128-row blocks of (tap,ci) per CTA (1 or 2): with MT = 2 two accumulators share every dy
+// stage, i.e. twice the tensor work per pipeline round-trip and half the dy traffic per FLOP.
+template <int BN, int MT>
 struct WgradCfg {
-  static constexpr int kABytes = kWgPix * 128 * 2;   // 64 pixels x 128 (tap,ci) columns
+  static constexpr int kAHalfBytes = kWgPix * 128 * 2;   // 64 pixels x 128 (tap,ci) columns
+  static constexpr int kABytes = MT * kAHalfBytes;
   static constexpr int kBBytes = kWgPix * BN * 2;    // 64 pixels x BN output channels
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : ((BN == 128) ? 3 : 4);
+  static constexpr int kStagesFit = (kSmemBudget - 1024) / kStageBytes;
+  static constexpr int kStages = MT == 1 ? ((BN >= 256) ? 4 : ((BN == 128) ? 3 : 4))
+                                         : (kStagesFit > 5 ? 5 : kStagesFit);
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kTmemCols = MT * BN < 32 ? 32 : MT * BN;
+  static_assert(MT * BN <= 512 && kStages >= 3, "wgrad tile does not fit");
 };
 
 // CW: channel width of one im2col chunk of x (16/32/64), CWB: channel width of one dy chunk.
-template <int BN, int CW, int CWB, bool IM2COL>
+template <int BN, int CW, int CWB, bool IM2COL, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const WgradParams p) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, MT>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kAChunks = 128 / CW;
+  constexpr int kAChunks = MT * 128 / CW;        // chunks of both 128-row blocks, consecutive
   constexpr int kBChunks = BN / CWB;
   constexpr int kAChunkBytes = kWgPix * CW * 2;
   constexpr int kBChunkBytes = kWgPix * CWB * 2;
@@ -665,7 +672,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                                              ~static_cast<uintptr_t>(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;      // first (tap,ci) column of dw handled here
+  const int m0 = blockIdx.x * (MT * 128);   // first (tap,ci) column of dw handled here
+  const bool second = MT == 2 && m0 + 128 < p.Ktot;   // the second 128-row block exists
   const int co0 = blockIdx.y * BN;
   const int ks_begin = blockIdx.z * p.stages_per_split;
   int ks_end = ks_begin + p.stages_per_split;
@@ -687,7 +695,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     mbar_init(&tmem_full_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<(BN < 32 ? 32 : BN)>(&tmem_base_smem);
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -756,9 +764,15 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint64_t da0 = a_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
         const uint64_t db0 = b_desc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
 #pragma unroll
-        for (int ks = 0; ks < kWgPix / 16; ++ks) {
-          umma_bf16(tmem_base, da0 + ((ks * 16 * CW * 2) >> 4), db0 + ((ks * 16 * CWB * 2) >> 4),
-                    kIdesc, (it | ks) ? 1u : 0u);
+        for (int h = 0; h < MT; ++h) {
+          if (h == 0 || second) {
+#pragma unroll
+            for (int ks = 0; ks < kWgPix / 16; ++ks) {
+              umma_bf16(tmem_base + h * BN,
+                        da0 + ((h * Cfg::kAHalfBytes + ks * 16 * CW * 2) >> 4),
+                        db0 + ((ks * 16 * CWB * 2) >> 4), kIdesc, (it | ks) ? 1u : 0u);
+            }
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (it == num_ks - 1) umma_commit(&tmem_full_bar);
@@ -769,22 +783,27 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   } else {
     // TMEM lane = row of D = (tap,ci) column of dw; consecutive lanes -> consecutive addresses.
     const int quarter = warp & 3;
-    const int n = m0 + quarter * 32 + lane;
-    const bool n_ok = n < p.Ktot;
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      if (co0 + c * 32 >= p.Cout) break;   // warp-uniform
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      if (n_ok) {
-        float* dst = p.dw + static_cast<size_t>(co0 + c * 32) * p.Ktot + n;
+    for (int h = 0; h < MT; ++h) {
+      if (h == 1 && !second) break;          // warp-uniform
+      const int n = m0 + h * 128 + quarter * 32 + lane;
+      const bool n_ok = n < p.Ktot;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (co0 + c * 32 >= p.Cout) break;   // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + h * BN + c * 32,
+                      v);
+        tmem_ld_wait();
+        if (n_ok) {
+          float* dst = p.dw + static_cast<size_t>(co0 + c * 32) * p.Ktot + n;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (co0 + c * 32 + i < p.Cout)
-            atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (co0 + c * 32 + i < p.Cout)
+              atomicAdd(dst + static_cast<size_t>(i) * p.Ktot, __uint_as_float(v[i]));
+          }
         }
       }
     }
@@ -794,7 +813,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -953,12 +972,13 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   return dispatch_conv_gemm<32>(cw, !plain, tm, p, stream);
 }
 
-template <int BN, int CW, int CWB, bool IM2COL>
+template <int BN, int CW, int CWB, bool IM2COL, int MT>
 static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, WgradParams p, int m_tiles,
                         int n_tiles, cudaStream_t stream) {
-  using Cfg = WgradCfg<BN>;
+  using Cfg = WgradCfg<BN, MT>;
   static bool attr_set = false;
-  auto kern = wgrad_gemm_kernel<BN, CW, CWB, IM2COL>;
+  auto kern = wgrad_gemm_kernel<BN, CW, CWB, IM2COL, MT>;
+  m_tiles = ceil_div(p.Ktot, MT * 128);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
@@ -987,9 +1007,16 @@ template <int BN, int CW, bool IM2COL>
 static int dispatch_wgrad_cwb(int cwb, const CUtensorMap& tx, const CUtensorMap& tdy,
                               const WgradParams& p, int mt, int nt, cudaStream_t s) {
   if constexpr (BN >= 64) {
-    if (cwb == 64) return launch_wgrad<BN, CW, 64, IM2COL>(tx, tdy, p, mt, nt, s);
+    if (cwb == 64) {
+      // two 128-row blocks per CTA (full-width chunks only, to bound the instantiation count)
+      if constexpr (CW == 64) {
+        if (p.Ktot > 128 && g_conv_mtiles_mode != 1)
+          return launch_wgrad<BN, CW, 64, IM2COL, 2>(tx, tdy, p, mt, nt, s);
+      }
+      return launch_wgrad<BN, CW, 64, IM2COL, 1>(tx, tdy, p, mt, nt, s);
+    }
   }
-  return launch_wgrad<BN, CW, 32, IM2COL>(tx, tdy, p, mt, nt, s);
+  return launch_wgrad<BN, CW, 32, IM2COL, 1>(tx, tdy, p, mt, nt, s);
 }
 
 template <int BN, bool IM2COL>

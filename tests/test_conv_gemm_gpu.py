@@ -191,8 +191,9 @@ def test_dgrad_matches_autograd(lib, case, mt):
     assert _relerr(dxd.float().cpu(), dx_ref) < BF16_TOL
 
 
+@pytest.mark.parametrize("mt", [1, -1], ids=["mt1", "auto"])
 @pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
-def test_wgrad_matches_autograd(lib, case):
+def test_wgrad_matches_autograd(lib, case, mt):
     from assembled_cnn_b200 import _lib
     B, H, W, Cin, Cout, k, stride, pads = case
     g = _geom(B, H, W, Cin, Cout, k, stride, pads)
@@ -204,8 +205,9 @@ def test_wgrad_matches_autograd(lib, case):
     dwd = torch.zeros(Cout, g.kh, g.kw, Cin, dtype=torch.float32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     xd, dyd = x.bfloat16().cuda(), dy.bfloat16().cuda()
-    _lib.check(lib.acnn_conv_wgrad(g, xd.data_ptr(), dyd.data_ptr(), dwd.data_ptr(), st),
-               "conv_wgrad")
+    with _mtiles(lib, mt):
+        _lib.check(lib.acnn_conv_wgrad(g, xd.data_ptr(), dyd.data_ptr(), dwd.data_ptr(), st),
+                   "conv_wgrad")
     torch.cuda.synchronize()
     got = dwd.cpu().permute(1, 2, 3, 0)      # OHWI -> HWIO
     assert _relerr(got, dw_ref) < F32_TOL
