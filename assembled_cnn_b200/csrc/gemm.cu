@@ -1010,7 +1010,10 @@ static int dispatch_wgrad_cwb(int cwb, const CUtensorMap& tx, const CUtensorMap&
     if (cwb == 64) {
       // two 128-row blocks per CTA (full-width chunks only, to bound the instantiation count)
       if constexpr (CW == 64) {
-        if (p.Ktot > 128 && g_conv_mtiles_mode != 1)
+        // measured: pays when the (tap,ci) extent and the pixel count are both large (otherwise
+        // halving the number of CTAs costs more than the shared dy stage saves)
+        const bool big = (p.Ktot >= 1024 && p.P >= 50176) || p.Ktot >= 4096;
+        if (p.Ktot > 128 && (g_conv_mtiles_mode == 2 || (g_conv_mtiles_mode == -1 && big)))
           return launch_wgrad<BN, CW, 64, IM2COL, 2>(tx, tdy, p, mt, nt, s);
       }
       return launch_wgrad<BN, CW, 64, IM2COL, 1>(tx, tdy, p, mt, nt, s);

@@ -191,7 +191,7 @@ def test_dgrad_matches_autograd(lib, case, mt):
     assert _relerr(dxd.float().cpu(), dx_ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("mt", [1, -1], ids=["mt1", "auto"])
+@pytest.mark.parametrize("mt", MT, ids=MT_IDS)
 @pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
 def test_wgrad_matches_autograd(lib, case, mt):
     from assembled_cnn_b200 import _lib
