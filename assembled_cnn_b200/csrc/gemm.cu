@@ -871,12 +871,12 @@ static int g_conv_mtiles_mode = -1;
 template <int BN>
 static int dispatch_conv_gemm(int cw, bool im2col, const ConvMaps& tm, const ConvGemmParams& p,
                               cudaStream_t s) {
-  // Two M tiles per CTA when TMEM has room (N <= 128), the smem ring stays >= 3 stages deep (at
-  // N = 128 only without the add / mask staging buffers) and there are enough tiles to keep every
-  // SM busy for several rounds.
+  // Two M tiles per CTA when TMEM has room (N <= 128), the smem ring stays >= 3 stages deep and
+  // there are enough tiles to keep every SM busy for several rounds.
   bool two = false;
   if constexpr (BN <= 128) {
-    const bool fits = BN <= 64 || (!p.has_add && !p.has_mask);
+    // (at N = 128 that rules out only the add + mask epilogue: two 32 KiB aux staging tiles)
+    const bool fits = FpropCfg<BN, 2>::stages_for(p.has_add, p.has_mask, p.out_f32) >= 3;
     const int64_t tiles = (int64_t)ceil_div(p.M, 2 * kBM) * (p.Cout / BN);
     two = fits && !p.out_f32 &&
           (g_conv_mtiles_mode == 2 || (g_conv_mtiles_mode == -1 && tiles >= 4 * (int64_t)num_sms()));
