@@ -380,14 +380,24 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
 // ------------------------------------------------------------------------------------------
 // SK elementwise
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kT)
+constexpr int kSkStages = 3;
+constexpr int kSkYBytes = 16 * 1024, kSkDvBytes = 8 * 1024;
+constexpr int kSkStageBytes = kSkYBytes + kSkDvBytes;
+constexpr int kSkSmemBytes = kSkStages * kSkStageBytes + 128;
+
+// v = att * relu(bn(y0)) + (1 - att) * relu(bn(y1)).  grid = (row slabs, images): the image and the
+// channel group of a thread are fixed, so the BN coefficients and the attention weights live in
+// registers; the rows of y are streamed through shared memory (stream_pipe.cuh), 2 rows per thread
+// per trip = 16 KiB of y.
+__global__ void __launch_bounds__(kT, 2)
 sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ att,
                   bf16* __restrict__ v, int HW, int f) {
-  // grid = (row slabs, images): the image and the channel group of a thread are fixed, so the
-  // BN coefficients and the attention weights live in registers for the whole kernel
+  extern __shared__ uint8_t sk_smem_raw[];
+  __shared__ uint64_t bars[kSkStages];
   const int CG = f >> 3;
   const int RPB = kT / CG;
+  const int RT = 2 * RPB;
   const int cg = threadIdx.x % CG;
   const int rsub = threadIdx.x / CG;
   const int c0 = cg << 3;
@@ -395,37 +405,46 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
   const int rows_per = (HW + gridDim.x - 1) / gridDim.x;
   const int r_begin = blockIdx.x * rows_per;
   const int r_end = (r_begin + rows_per < HW) ? r_begin + rows_per : HW;
+  const int trips = r_end > r_begin ? (r_end - r_begin + RT - 1) / RT : 0;
+  const uint32_t sbase = (smem_u32(sk_smem_raw) + 127u) & ~127u;
+  const uint8_t* sgen = sk_smem_raw + (sbase - smem_u32(sk_smem_raw));
+  RowPipe<kSkStages> pipe(bars);
+  pipe.init(bars);
+  auto issue = [&](int t, int stage, uint32_t bar) {
+    const int r0 = r_begin + t * RT;
+    const int rows = (r_end - r0 < RT) ? r_end - r0 : RT;
+    mbar_expect_tx_a(bar, rows * 2 * f * 2);
+    bulk_load(sbase + stage * kSkStageBytes, y + (b * HW + r0) * 2 * f, rows * 2 * f * 2, bar);
+  };
+  pipe.prologue(trips, issue);
   float s0[8], h0[8], s1[8], h1[8], a[8];
   loadf8(scale + c0, s0);
   loadf8(shift + c0, h0);
   loadf8(scale + f + c0, s1);
   loadf8(shift + f + c0, h1);
   loadf8(att + b * f + c0, a);
-  for (int rb = r_begin + rsub; rb < r_end; rb += 2 * RPB) {
-    uint4 q0[2], q1[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {          // batched loads (row clamped)
-      int r = rb + u * RPB;
-      r = r < r_end ? r : r_end - 1;
-      const int64_t row = b * HW + r;
-      q0[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + c0));
-      q1[u] = __ldg(reinterpret_cast<const uint4*>(y + row * 2 * f + f + c0));
-    }
+  for (int t = 0; t < trips; ++t) {
+    pipe.acquire(t, trips, issue);
+    const uint8_t* sy = sgen + pipe.stage(t) * kSkStageBytes;
+    const int r0 = r_begin + t * RT;
+    const int rows = r_end - r0;
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const int r = rb + u * RPB;
-      if (r >= r_end) break;
-      float y0[8], y1[8], o[8];
-      unpack8(q0[u], y0);
-      unpack8(q1[u], y1);
+      const int rl = rsub + u * RPB;
+      if (rl < rows) {
+        float y0[8], y1[8], o[8];
+        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + c0) * 2), y0);
+        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + f + c0) * 2), y1);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
-        const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
-        o[k] = a[k] * u0 + (1.f - a[k]) * u1;
+        for (int k = 0; k < 8; ++k) {
+          const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
+          const float u1 = fmaxf(fmaf(y1[k], s1[k], h1[k]), 0.f);
+          o[k] = a[k] * u0 + (1.f - a[k]) * u1;
+        }
+        store8(v + (b * HW + r0 + rl) * f + c0, o);
       }
-      store8(v + (b * HW + r) * f + c0, o);
     }
+    pipe.release();
   }
 }
 
@@ -434,11 +453,6 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
 // 8 channels of ONE half.  grid = (row slabs, images): everything that depends only on (image,
 // channel) stays in registers, and the rows of y / dv are streamed through shared memory
 // (stream_pipe.cuh): a trip is 4 rows per thread = 16 KiB of y + 8 KiB of dv for every f.
-constexpr int kSkStages = 3;
-constexpr int kSkYBytes = 16 * 1024, kSkDvBytes = 8 * 1024;
-constexpr int kSkStageBytes = kSkYBytes + kSkDvBytes;
-constexpr int kSkSmemBytes = kSkStages * kSkStageBytes + 128;
-
 struct SkSlab {
   int C2, CG2, RPB, RT, cg2, rsub, cb, c0, r_begin, r_end, trips;
   bool second;
@@ -824,8 +838,14 @@ int acnn_sk_combine(const void* y, const float* scale, const float* shift, const
   ACNN_REQUIRE(y && scale && shift && att && v && cg_ok(f) && B <= 65535,
                "sk_combine: bad arguments");
   dim3 grid(row_slabs(B, HW, kT / (f >> 3)), B);
-  sk_combine_kernel<<<grid, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, scale, shift, att,
-                                                           (bf16*)v, HW, f);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(sk_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kSkSmemBytes);
+    attr = true;
+  }
+  sk_combine_kernel<<<grid, kT, kSkSmemBytes, (cudaStream_t)stream>>>(
+      (const bf16*)y, scale, shift, att, (bf16*)v, HW, f);
   count_launch();
   return check_launch("sk_combine");
 }

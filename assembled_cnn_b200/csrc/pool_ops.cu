@@ -157,11 +157,15 @@ __device__ __forceinline__ int window_count(int p, int stride, int pad, int k, i
   return hi - lo;
 }
 
-// grid = (ceil(W*C/8 / 256), H, B): no 64-bit index divisions on the hot path
+// grid = (ceil(W*C/8 / 256), H, B): no 64-bit index divisions on the hot path.  STRIDE > 0 makes
+// the stride a compile-time constant (shifts instead of divisions); the two full-size streams
+// (add / mask tiles) are requested first, the small dout gather (L2 hits) overlaps them.
+template <int STRIDE>
 __global__ void __launch_bounds__(kPT)
 avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                    const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H, int W,
-                   int C, int k, int stride, int pad, int Ho, int Wo, int count_pad) {
+                   int C, int k, int stride_rt, int pad, int Ho, int Wo, int count_pad) {
+  const int stride = STRIDE > 0 ? STRIDE : stride_rt;
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
   if (idx >= W * CG) return;
@@ -169,6 +173,10 @@ avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
   const int cg = idx - iw * CG;
   const int ih = blockIdx.y;
   const int64_t b = blockIdx.z;
+  const size_t off = (((size_t)b * H + ih) * W + iw) * C + cg * 8;
+  uint4 addv = make_uint4(0, 0, 0, 0), maskv = make_uint4(0, 0, 0, 0);
+  if (add_src) addv = __ldg(reinterpret_cast<const uint4*>(add_src + off));
+  if (mask_src) maskv = __ldg(reinterpret_cast<const uint4*>(mask_src + off));
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -176,19 +184,30 @@ avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
   if (p_hi > Ho - 1) p_hi = Ho - 1;
   int q_hi = (iw + pad) / stride;
   if (q_hi > Wo - 1) q_hi = Wo - 1;
+  const float inv_full = 1.f / (k * k);
   for (int p = p_hi; p >= 0 && ih + pad - p * stride < k; --p) {
+    const float inv_p = count_pad ? inv_full : 1.f / window_count(p, stride, pad, k, H);
     for (int q = q_hi; q >= 0 && iw + pad - q * stride < k; --q) {
       float v[8];
       load8(dout + ((b * Ho + p) * Wo + q) * C + cg * 8, v);
-      const float inv = count_pad ? 1.f / (k * k)
-                                  : 1.f / (window_count(p, stride, pad, k, H) *
-                                           window_count(q, stride, pad, k, W));
+      const float inv = count_pad ? inv_full : inv_p / window_count(q, stride, pad, k, W);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaf(inv, v[e], acc[e]);
     }
   }
-  const size_t off = (((size_t)b * H + ih) * W + iw) * C + cg * 8;
-  grad_epilogue(acc, add_src, mask_src, off);
+  if (add_src) {
+    float a[8];
+    unpack8(addv, a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += a[e];
+  }
+  if (mask_src) {
+    float m[8];
+    unpack8(maskv, m);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (!(m[e] > 0.f)) acc[e] = 0.f;
+  }
   store8(dx + off, acc);
 }
 
@@ -560,9 +579,19 @@ int acnn_avgpool_bwd(const void* dout, void* dx, const void* add_src, const void
   ACNN_REQUIRE(dout && dx && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_bwd: bad arguments");
   ACNN_REQUIRE(H <= 65535 && B <= 65535, "avgpool_bwd: H / B exceed the grid limits");
   dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
-  avgpool_bwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k, stride,
-      pad_lo, Ho, Wo, count_pad);
+  if (stride == 2) {
+    avgpool_bwd_kernel<2><<<grid, kPT, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
+        stride, pad_lo, Ho, Wo, count_pad);
+  } else if (stride == 1) {
+    avgpool_bwd_kernel<1><<<grid, kPT, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
+        stride, pad_lo, Ho, Wo, count_pad);
+  } else {
+    avgpool_bwd_kernel<0><<<grid, kPT, 0, (cudaStream_t)stream>>>(
+        (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
+        stride, pad_lo, Ho, Wo, count_pad);
+  }
   count_launch();
   return check_launch("avgpool_bwd");
 }
