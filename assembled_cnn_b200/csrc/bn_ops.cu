@@ -19,6 +19,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    float* moving_var, float momentum, float eps, int training,
                                    float* scale, float* shift, float* mean_out, float* rstd_out,
                                    int C) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, var;
@@ -53,6 +54,7 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
               const float* __restrict__ sb, const float* __restrict__ hb, int b_mode,
               const float* __restrict__ gate, int relu, bf16* __restrict__ out, int H, int W, int C,
               int64_t nvec) {
+  pdl_entry();
   const int CG = C >> 3;
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   // CG divides the grid stride (a power of two <= 256 dividing 256*gridDim): the 8-channel group
@@ -153,6 +155,7 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gate, const float* __restrict__ addbc,
                      float* sums, int64_t M, int HW, int C) {
+  pdl_entry();
   const int CG = C >> 3;
   const int RPB = kT / CG;
   const int cg = threadIdx.x % CG;
@@ -214,6 +217,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums,
                                        const float* __restrict__ mean,
                                        const float* __restrict__ rstd, float count, float* coef,
                                        float* dgamma, float* dbeta, int C) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float s1 = sums[c], s2 = sums[C + c];
@@ -232,6 +236,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
                     const float* __restrict__ coef, const float* __restrict__ gate,
                     const float* __restrict__ addbc, bf16* __restrict__ dy, int HW, int C,
                     int64_t nvec) {
+  pdl_entry();
   const int CG = C >> 3;
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int cg = (int)(i0 % CG);           // loop-invariant (see bn_act_kernel)
@@ -293,6 +298,7 @@ __global__ void __launch_bounds__(kT)
 image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
                     const float* __restrict__ scale, const float* __restrict__ shift, void* out,
                     int HW, int f) {
+  pdl_entry();
   // f = number of OUTPUT channels; MODE 0/1 read y with 2f channels.
   __shared__ float red[kT][9];
   const int CG = f >> 3;
@@ -393,6 +399,7 @@ __global__ void __launch_bounds__(kT, 2)
 sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ att,
                   bf16* __restrict__ v, int HW, int f) {
+  pdl_entry();
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   const int CG = f >> 3;
@@ -484,6 +491,7 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ att, const float* __restrict__ ds, float* sums,
                         int HW, int f) {
+  pdl_entry();
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   const SkSlab q = sk_slab(HW, f);
@@ -548,6 +556,7 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        const float* __restrict__ att, const float* __restrict__ ds,
                        const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f) {
+  pdl_entry();
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   const SkSlab q = sk_slab(HW, f);
@@ -619,6 +628,7 @@ __global__ void __launch_bounds__(kT, 2)
 sk_image_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dv,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        float* __restrict__ out, int HW, int f) {
+  pdl_entry();
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   __shared__ float red[kT][9];
@@ -698,7 +708,7 @@ static void launch_sk_image_reduce(const bf16* y, const bf16* dv, const float* s
                          kSkSmemBytes);
     attr = true;
   }
-  sk_image_reduce_kernel<MODE><<<B, kT, kSkSmemBytes, st>>>(y, dv, scale, shift, out, HW, f);
+  launch_k(sk_image_reduce_kernel<MODE>, dim3(B), dim3(kT), kSkSmemBytes, st, y, dv, scale, shift, out, HW, f);
 }
 
 // Row slabs per image for the image-aligned SK kernels: ~`ctas_per_sm` CTAs per SM overall, at
@@ -728,8 +738,7 @@ int acnn_bn_finalize(const float* sum, const float* sumsq, int64_t count, const 
   ACNN_REQUIRE(C > 0 && gamma && beta && moving_mean && moving_var && scale && shift && mean &&
                    rstd, "bn_finalize: null argument");
   ACNN_REQUIRE(!training || (sum && sumsq && count > 0), "bn_finalize: training needs sums");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
-      sum, sumsq, (float)count, gamma, beta, moving_mean, moving_var, momentum, eps, training,
+  launch_k(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sum, sumsq, (float)count, gamma, beta, moving_mean, moving_var, momentum, eps, training,
       scale, shift, mean, rstd, C);
   count_launch();
   return check_launch("bn_finalize");
@@ -744,12 +753,10 @@ int acnn_bn_act(const void* a, const float* scale_a, const float* shift_a, const
   ACNN_REQUIRE(b_mode != 3 || (H % 2 == 0 && W % 2 == 0), "bn_act: upsample needs even H, W");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
   if (b_mode == 0) {
-    bn_act_kernel<8, false><<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
-        (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
+    launch_k(bn_act_kernel<8, false>, dim3(grid_for(nvec)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
         (bf16*)out, H, W, C, nvec);
   } else {
-    bn_act_kernel<4, true><<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
-        (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
+    launch_k(bn_act_kernel<4, true>, dim3(grid_for(nvec)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
         (bf16*)out, H, W, C, nvec);
   }
   count_launch();
@@ -762,8 +769,7 @@ int acnn_bn_bwd_reduce(const void* g, const void* y, const float* mean, const fl
   ACNN_REQUIRE(g && y && mean && rstd && sums && cg_ok(C), "bn_bwd_reduce: bad arguments C=%d", C);
   const int64_t M = (int64_t)B * HW;
   const int rpb = kT / (C >> 3);
-  bn_bwd_reduce_kernel<<<grid_for(ceil_div64(M, 4 * rpb), 1, 148 * 2), kT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)g, (const bf16*)y, mean, rstd, gate, addbc, sums, M, HW, C);
+  launch_k(bn_bwd_reduce_kernel, dim3(grid_for(ceil_div64(M, 4 * rpb), 1, 148 * 2)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)g, (const bf16*)y, mean, rstd, gate, addbc, sums, M, HW, C);
   count_launch();
   return check_launch("bn_bwd_reduce");
 }
@@ -773,8 +779,7 @@ int acnn_bn_bwd_finalize(const float* sums, const float* gamma, const float* mea
                          int C, void* stream) {
   ACNN_REQUIRE(sums && gamma && mean && rstd && coef && dgamma && dbeta && count > 0,
                "bn_bwd_finalize: null argument");
-  bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
-      sums, gamma, mean, rstd, (float)count, coef, dgamma, dbeta, C);
+  launch_k(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, gamma, mean, rstd, (float)count, coef, dgamma, dbeta, C);
   count_launch();
   return check_launch("bn_bwd_finalize");
 }
@@ -783,8 +788,7 @@ int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const flo
                       const float* addbc, void* dy, int B, int HW, int C, void* stream) {
   ACNN_REQUIRE(g && y && coef && dy && C % 8 == 0, "bn_bwd_apply: bad arguments");
   const int64_t nvec = (int64_t)B * HW * C / 8;
-  bn_bwd_apply_kernel<<<grid_for(nvec), kT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)g, (const bf16*)y, coef, gate, addbc, (bf16*)dy, HW, C, nvec);
+  launch_k(bn_bwd_apply_kernel, dim3(grid_for(nvec)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)g, (const bf16*)y, coef, gate, addbc, (bf16*)dy, HW, C, nvec);
   count_launch();
   return check_launch("bn_bwd_apply");
 }
@@ -810,7 +814,7 @@ int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const fl
 int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q, int B, int HW,
                 int C, void* stream) {
   ACNN_REQUIRE(y && scale && shift && q && cg_ok(C), "se_gap: bad arguments");
-  image_reduce_kernel<2><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, nullptr, scale, shift,
+  launch_k(image_reduce_kernel<2>, dim3(B), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)y, nullptr, scale, shift,
                                                              q, HW, C);
   count_launch();
   return check_launch("se_gap");
@@ -819,7 +823,7 @@ int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q,
 int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const float* shift,
                      float* de, int B, int HW, int C, void* stream) {
   ACNN_REQUIRE(g && y && scale && shift && de && cg_ok(C), "se_bwd_gate: bad arguments");
-  image_reduce_kernel<3><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)y, (const bf16*)g, scale,
+  launch_k(image_reduce_kernel<3>, dim3(B), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)y, (const bf16*)g, scale,
                                                              shift, de, HW, C);
   count_launch();
   return check_launch("se_bwd_gate");
@@ -827,7 +831,7 @@ int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const flo
 
 int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, void* stream) {
   ACNN_REQUIRE(x && pooled && cg_ok(C), "gap_fwd: bad arguments C=%d", C);
-  image_reduce_kernel<4><<<B, kT, 0, (cudaStream_t)stream>>>((const bf16*)x, nullptr, nullptr,
+  launch_k(image_reduce_kernel<4>, dim3(B), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)x, nullptr, nullptr,
                                                              nullptr, pooled, HW, C);
   count_launch();
   return check_launch("gap_fwd");
@@ -844,8 +848,7 @@ int acnn_sk_combine(const void* y, const float* scale, const float* shift, const
                          kSkSmemBytes);
     attr = true;
   }
-  sk_combine_kernel<<<grid, kT, kSkSmemBytes, (cudaStream_t)stream>>>(
-      (const bf16*)y, scale, shift, att, (bf16*)v, HW, f);
+  launch_k(sk_combine_kernel, dim3(grid), dim3(kT), kSkSmemBytes, (cudaStream_t)stream, (const bf16*)y, scale, shift, att, (bf16*)v, HW, f);
   count_launch();
   return check_launch("sk_combine");
 }
@@ -863,8 +866,7 @@ int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, con
                          kSkSmemBytes);
     attr = true;
   }
-  sk_bn_bwd_reduce_kernel<<<grid, kT, kSkSmemBytes, (cudaStream_t)stream>>>(
-      (const bf16*)dv, (const bf16*)y, scale, shift, mean, rstd, att, ds, sums, HW, f);
+  launch_k(sk_bn_bwd_reduce_kernel, dim3(grid), dim3(kT), kSkSmemBytes, (cudaStream_t)stream, (const bf16*)dv, (const bf16*)y, scale, shift, mean, rstd, att, ds, sums, HW, f);
   count_launch();
   return check_launch("sk_bn_bwd_reduce");
 }
@@ -881,8 +883,7 @@ int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, cons
                          kSkSmemBytes);
     attr = true;
   }
-  sk_bn_bwd_apply_kernel<<<grid, kT, kSkSmemBytes, (cudaStream_t)stream>>>(
-      (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f);
+  launch_k(sk_bn_bwd_apply_kernel, dim3(grid), dim3(kT), kSkSmemBytes, (cudaStream_t)stream, (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f);
   count_launch();
   return check_launch("sk_bn_bwd_apply");
 }

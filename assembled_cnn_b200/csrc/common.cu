@@ -1,6 +1,7 @@
 #include "common.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 
 namespace acnn {
@@ -14,6 +15,12 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static int pdl_default() {
+  const char* e = getenv("ACNN_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}
+int g_use_pdl = pdl_default();
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -32,6 +39,11 @@ extern "C" {
 
 const char* acnn_last_error(void) { return acnn::g_err; }
 int acnn_version(void) { return 100; }
+int acnn_set_pdl(int on) {
+  const int prev = acnn::g_use_pdl;
+  acnn::g_use_pdl = on ? 1 : 0;
+  return prev;
+}
 int64_t acnn_launch_count(void) { return acnn::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -23,6 +23,30 @@ int check_launch(const char* what);
     }                                  \
   } while (0)
 
+// Programmatic dependent launch (PDL): every kernel of this library starts with
+// `griddepcontrol.launch_dependents; griddepcontrol.wait;` (pdl_entry() in vec.cuh / ptx.cuh), so a
+// kernel launched with the programmatic-stream-serialization attribute may be scheduled (CTAs
+// resident, prologue done) while its predecessor drains, and only proceeds past the wait once the
+// predecessor grid has completed and flushed.  This hides the per-kernel launch / drain latency of
+// the ~865 dependent launches of a step (also inside the captured CUDA graph).
+extern int g_use_pdl;   // 1 by default; ACNN_PDL=0 or acnn_set_pdl(0) turns the attribute off
+
+template <class... KArgs, class... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors: check_launch()
+}
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -288,6 +288,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
+  // the preceding kernel; its outputs are read only after this point
+  pdl_entry();
   const uint32_t tmem_base = tmem_base_smem;
 
   // 32-bit shared-window addresses, computed once: the issue loops below run on one warp each and
@@ -699,6 +702,9 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
+  // the preceding kernel; its outputs are read only after this point
+  pdl_entry();
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
@@ -859,8 +865,7 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
   if (per_n < 1) per_n = 1;
   if (per_n > q.m_tiles) per_n = q.m_tiles;
   const int grid = per_n * q.n_tiles;
-  kern<<<grid, kConvThreads, Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32),
-         stream>>>(tm.a, tm.b, tm.c, tm.add, tm.mask, q);
+  launch_k(kern, dim3(grid), dim3(kConvThreads), Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32), stream, tm.a, tm.b, tm.c, tm.add, tm.mask, q);
   count_launch();
   return check_launch("conv_gemm_kernel");
 }
@@ -998,7 +1003,7 @@ static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, WgradPara
   p.stages_per_split = ceil_div(p.stages_total, splits);
   splits = ceil_div(p.stages_total, p.stages_per_split);
   dim3 grid(m_tiles, n_tiles, splits);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tx, tdy, p);
+  launch_k(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tx, tdy, p);
   count_launch();
   return check_launch("wgrad_gemm_kernel");
 }

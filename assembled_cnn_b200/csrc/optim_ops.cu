@@ -11,6 +11,7 @@ namespace acnn {
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __restrict__ descs,
                     bf16* __restrict__ w_fprop, bf16* __restrict__ w_dgrad) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const acnn_weight_desc d = descs[blockIdx.y];
   const int tco = (d.Cout + 31) / 32, tci = (d.Cin + 31) / 32;
@@ -50,6 +51,7 @@ prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __
 // r = tap2 - pad2, a in {0,1};  channel = (a*2 + b)*4 + c.
 __global__ void s2d_weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ w2, int Cout,
                                        int k, int pad, int k2, int pad2) {
+  pdl_entry();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t n = (int64_t)Cout * k2 * k2 * 16;
   if (i >= n) return;
@@ -68,6 +70,7 @@ __global__ void s2d_weight_pack_kernel(const float* __restrict__ w, bf16* __rest
 
 __global__ void s2d_wgrad_unpack_kernel(const float* __restrict__ dw2, float* __restrict__ dw,
                                         int Cout, int k, int pad, int k2, int pad2) {
+  pdl_entry();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t n = (int64_t)Cout * k * k * 3;
   if (i >= n) return;
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(256)
 sgd_momentum_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ acc,
                     int64_t n, const uint8_t* __restrict__ decay_flag, const float* __restrict__ hp,
                     float* l2_acc) {
+  pdl_entry();
   __shared__ float sh[8];
   const float lr = hp[0], mom = hp[1], wd = hp[2], gs = hp[3];
   float l2 = 0.f;
@@ -139,7 +143,7 @@ int acnn_prep_weights(const float* master, const acnn_weight_desc* descs, int n,
                       void* w_dgrad, void* stream) {
   ACNN_REQUIRE(master && descs && w_fprop && n > 0 && n < 65536, "prep_weights: bad arguments");
   dim3 grid(96, n, 1);
-  prep_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(master, descs, (bf16*)w_fprop,
+  launch_k(prep_weights_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, master, descs, (bf16*)w_fprop,
                                                               (bf16*)w_dgrad);
   count_launch();
   return check_launch("prep_weights");
@@ -149,8 +153,7 @@ int acnn_s2d_weight_pack(const float* w, void* w2, int Cout, int k, int pad, int
                          void* stream) {
   ACNN_REQUIRE(w && w2, "s2d_weight_pack: null argument");
   const int64_t n = (int64_t)Cout * k2 * k2 * 16;
-  s2d_weight_pack_kernel<<<(int)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      w, (bf16*)w2, Cout, k, pad, k2, pad2);
+  launch_k(s2d_weight_pack_kernel, dim3((int)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, w, (bf16*)w2, Cout, k, pad, k2, pad2);
   count_launch();
   return check_launch("s2d_weight_pack");
 }
@@ -159,8 +162,7 @@ int acnn_s2d_wgrad_unpack(const float* dw2, float* dw, int Cout, int k, int pad,
                           void* stream) {
   ACNN_REQUIRE(dw2 && dw, "s2d_wgrad_unpack: null argument");
   const int64_t n = (int64_t)Cout * k * k * 3;
-  s2d_wgrad_unpack_kernel<<<(int)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      dw2, dw, Cout, k, pad, k2, pad2);
+  launch_k(s2d_wgrad_unpack_kernel, dim3((int)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, dw2, dw, Cout, k, pad, k2, pad2);
   count_launch();
   return check_launch("s2d_wgrad_unpack");
 }
@@ -169,8 +171,7 @@ int acnn_sgd_momentum(float* w, const float* grad, float* acc, int64_t n,
                       const uint8_t* decay_flag, const float* hp, float* l2_acc, void* stream) {
   ACNN_REQUIRE(w && grad && acc && decay_flag && hp && n % 256 == 0,
                "sgd_momentum: bad arguments (n must be a multiple of 256)");
-  sgd_momentum_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
-      w, grad, acc, n, decay_flag, hp, l2_acc);
+  launch_k(sgd_momentum_kernel, dim3(grid_for(n / 4, 256, 148 * 8)), dim3(256), 0, (cudaStream_t)stream, w, grad, acc, n, decay_flag, hp, l2_acc);
   count_launch();
   return check_launch("sgd_momentum");
 }

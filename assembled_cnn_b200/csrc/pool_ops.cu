@@ -33,6 +33,7 @@ __device__ __forceinline__ int reflect(int i, int n) {
 __global__ void __launch_bounds__(kPT)
 blurpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Binomial bw, int H, int W,
                     int C, int filt, int stride, int pad, int Ho, int Wo) {
+  pdl_entry();
   // grid = (ceil(Wo * C/8 / threads), Ho, B): no 64-bit index decomposition per element
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -85,6 +86,7 @@ blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                     const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src,
                     Binomial bw, int H, int W, int C, int filt, int stride, int pad, int Ho,
                     int Wo) {
+  pdl_entry();
   // grid = (ceil(W * C/8 / threads), H, B)
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -116,6 +118,7 @@ blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 __global__ void __launch_bounds__(kPT)
 avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
                    int stride, int pad, int Ho, int Wo, int count_pad) {
+  pdl_entry();
   // grid = (ceil(Wo * C/8 / threads), Ho, B)
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(kPT)
 avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                    const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H, int W,
                    int C, int k, int stride_rt, int pad, int Ho, int Wo, int count_pad) {
+  pdl_entry();
   const int stride = STRIDE > 0 ? STRIDE : stride_rt;
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -214,6 +218,7 @@ avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 __global__ void __launch_bounds__(kPT)
 maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
                    int stride, int pad, int Ho, int Wo, int64_t nvec) {
+  pdl_entry();
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -247,6 +252,7 @@ maxpool_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ x,
                    bf16* __restrict__ dx, const bf16* __restrict__ add_src,
                    const bf16* __restrict__ mask_src, int H, int W, int C, int k, int stride,
                    int pad, int Ho, int Wo, int64_t nvec) {
+  pdl_entry();
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -302,6 +308,7 @@ __global__ void __launch_bounds__(kPT)
 upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                       const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H,
                       int W, int C, int64_t nvec) {
+  pdl_entry();
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -331,6 +338,7 @@ upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 __global__ void __launch_bounds__(kPT)
 zero_insert2x_kernel(const bf16* __restrict__ dy, bf16* __restrict__ out, int Ho, int Wo, int H,
                      int W, int C, int64_t nvec) {
+  pdl_entry();
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -351,6 +359,7 @@ zero_insert2x_kernel(const bf16* __restrict__ dy, bf16* __restrict__ out, int Ho
 __global__ void __launch_bounds__(kPT)
 gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_src,
                bf16* __restrict__ dx, int HW, int C, int64_t nvec) {
+  pdl_entry();
   const int CG = C >> 3;
   const float inv = 1.f / HW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
@@ -369,6 +378,7 @@ gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_s
 __global__ void __launch_bounds__(kPT)
 grad_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ add_src,
                     const bf16* __restrict__ mask_src, bf16* __restrict__ out, int64_t nvec) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     float v[8];
@@ -384,6 +394,7 @@ __global__ void __launch_bounds__(kPT)
 pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
                   const float* __restrict__ lam2, int mode, bf16* __restrict__ out, int Bin, int B,
                   int H, int W, int wpad_lo, int wpad_hi, int64_t npix) {
+  pdl_entry();
   const int H2 = H >> 1, W2 = W >> 1;
   const int Wp = W2 + wpad_lo + wpad_hi;
   const int half = Bin >> 1;
@@ -448,6 +459,7 @@ pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
 __global__ void mix_labels_kernel(const int32_t* __restrict__ labels,
                                   const float* __restrict__ lam1, const float* __restrict__ lam2,
                                   int mode, float* __restrict__ y, int Bin, int B, int NC) {
+  pdl_entry();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * NC) return;
   const int b = (int)(i / NC), c = (int)(i - (int64_t)b * NC);
@@ -493,6 +505,7 @@ __global__ void __launch_bounds__(kPT)
 softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y, int B, int NC,
                   int ld, float ls, float grad_scale, float* loss_acc, bf16* __restrict__ dlogits,
                   float* dbias) {
+  pdl_entry();
   __shared__ float sh[kPT / 32];
   const int b = blockIdx.x;
   const float* lg = logits + (size_t)b * ld;
@@ -541,8 +554,7 @@ int acnn_blurpool_fwd(const void* x, void* out, int B, int H, int W, int C, int 
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
   ACNN_REQUIRE(Ho <= 65535 && B <= 65535, "blurpool_fwd: Ho / B exceed the grid limits");
   dim3 grid(ceil_div(Wo * (C / 8), kPT), Ho, B);
-  blurpool_fwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)out, binomial(filt), H, W, C, filt, stride, pad, Ho, Wo);
+  launch_k(blurpool_fwd_kernel, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, binomial(filt), H, W, C, filt, stride, pad, Ho, Wo);
   count_launch();
   return check_launch("blurpool_fwd");
 }
@@ -555,8 +567,7 @@ int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const voi
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
   ACNN_REQUIRE(H <= 65535 && B <= 65535, "blurpool_bwd: H / B exceed the grid limits");
   dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
-  blurpool_bwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, binomial(filt), H,
+  launch_k(blurpool_bwd_kernel, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, binomial(filt), H,
       W, C, filt, stride, pad, Ho, Wo);
   count_launch();
   return check_launch("blurpool_bwd");
@@ -567,8 +578,7 @@ int acnn_avgpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k
   ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_fwd: bad arguments");
   ACNN_REQUIRE(Ho <= 65535 && B <= 65535, "avgpool_fwd: Ho / B exceed the grid limits");
   dim3 grid(ceil_div(Wo * (C / 8), kPT), Ho, B);
-  avgpool_fwd_kernel<<<grid, kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad);
+  launch_k(avgpool_fwd_kernel, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad);
   count_launch();
   return check_launch("avgpool_fwd");
 }
@@ -580,16 +590,13 @@ int acnn_avgpool_bwd(const void* dout, void* dx, const void* add_src, const void
   ACNN_REQUIRE(H <= 65535 && B <= 65535, "avgpool_bwd: H / B exceed the grid limits");
   dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
   if (stride == 2) {
-    avgpool_bwd_kernel<2><<<grid, kPT, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
+    launch_k(avgpool_bwd_kernel<2>, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
         stride, pad_lo, Ho, Wo, count_pad);
   } else if (stride == 1) {
-    avgpool_bwd_kernel<1><<<grid, kPT, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
+    launch_k(avgpool_bwd_kernel<1>, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
         stride, pad_lo, Ho, Wo, count_pad);
   } else {
-    avgpool_bwd_kernel<0><<<grid, kPT, 0, (cudaStream_t)stream>>>(
-        (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
+    launch_k(avgpool_bwd_kernel<0>, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
         stride, pad_lo, Ho, Wo, count_pad);
   }
   count_launch();
@@ -600,8 +607,7 @@ int acnn_maxpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k
                      int pad_lo, int Ho, int Wo, void* stream) {
   ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1, "maxpool_fwd: bad arguments");
   const int64_t nvec = (int64_t)B * Ho * Wo * C / 8;
-  maxpool_fwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, nvec);
+  launch_k(maxpool_fwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, nvec);
   count_launch();
   return check_launch("maxpool_fwd");
 }
@@ -611,8 +617,7 @@ int acnn_maxpool_bwd(const void* dout, const void* x, void* dx, const void* add_
                      int pad_lo, int Ho, int Wo, void* stream) {
   ACNN_REQUIRE(dout && x && dx && C % 8 == 0, "maxpool_bwd: bad arguments");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  maxpool_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dout, (const bf16*)x, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H,
+  launch_k(maxpool_bwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (const bf16*)x, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H,
       W, C, k, stride, pad_lo, Ho, Wo, nvec);
   count_launch();
   return check_launch("maxpool_bwd");
@@ -622,8 +627,7 @@ int acnn_upsample2x_bwd(const void* dout, void* dx, const void* add_src, const v
                         int B, int H, int W, int C, void* stream) {
   ACNN_REQUIRE(dout && dx && C % 8 == 0, "upsample2x_bwd: bad arguments");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  upsample2x_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, nvec);
+  launch_k(upsample2x_bwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, nvec);
   count_launch();
   return check_launch("upsample2x_bwd");
 }
@@ -632,8 +636,7 @@ int acnn_zero_insert2x(const void* dy, void* out, int B, int Ho, int Wo, int H, 
                        void* stream) {
   ACNN_REQUIRE(dy && out && C % 8 == 0, "zero_insert2x: bad arguments");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  zero_insert2x_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dy, (bf16*)out, Ho, Wo, H, W, C, nvec);
+  launch_k(zero_insert2x_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dy, (bf16*)out, Ho, Wo, H, W, C, nvec);
   count_launch();
   return check_launch("zero_insert2x");
 }
@@ -642,8 +645,7 @@ int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int
                  void* stream) {
   ACNN_REQUIRE(dpooled && dx && C % 8 == 0, "gap_bwd: bad arguments");
   const int64_t nvec = (int64_t)B * HW * C / 8;
-  gap_bwd_kernel<<<grid_for(nvec), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)dpooled, (const bf16*)mask_src, (bf16*)dx, HW, C, nvec);
+  launch_k(gap_bwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dpooled, (const bf16*)mask_src, (bf16*)dx, HW, C, nvec);
   count_launch();
   return check_launch("gap_bwd");
 }
@@ -651,8 +653,7 @@ int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int
 int acnn_grad_combine(const void* a, const void* add_src, const void* mask_src, void* out,
                       int64_t n, void* stream) {
   ACNN_REQUIRE(a && out && n % 8 == 0, "grad_combine: bad arguments");
-  grad_combine_kernel<<<grid_for(n / 8), kPT, 0, (cudaStream_t)stream>>>(
-      (const bf16*)a, (const bf16*)add_src, (const bf16*)mask_src, (bf16*)out, n / 8);
+  launch_k(grad_combine_kernel, dim3(grid_for(n / 8)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)add_src, (const bf16*)mask_src, (bf16*)out, n / 8);
   count_launch();
   return check_launch("grad_combine");
 }
@@ -666,8 +667,7 @@ int acnn_pack_input(const float* images, const float* lam1, const float* lam2, i
   const int B = mode == 1 ? Bin / 2 : Bin;
   ACNN_REQUIRE(wpad_lo >= 0 && wpad_hi >= 0, "pack_input: negative padding");
   const int64_t npix = (int64_t)B * (H / 2) * (W / 2 + wpad_lo + wpad_hi);
-  pack_input_kernel<<<grid_for(npix), kPT, 0, (cudaStream_t)stream>>>(
-      images, lam1, lam2, mode, (bf16*)out, Bin, B, H, W, wpad_lo, wpad_hi, npix);
+  launch_k(pack_input_kernel, dim3(grid_for(npix)), dim3(kPT), 0, (cudaStream_t)stream, images, lam1, lam2, mode, (bf16*)out, Bin, B, H, W, wpad_lo, wpad_hi, npix);
   count_launch();
   return check_launch("pack_input");
 }
@@ -679,8 +679,7 @@ int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2,
   ACNN_REQUIRE(mode != 2 || lam2, "mix_labels: mixup type 2 needs lam2");
   const int B = mode == 1 ? Bin / 2 : Bin;
   const int64_t n = (int64_t)B * NC;
-  mix_labels_kernel<<<(int)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
-      labels, lam1, lam2, mode, y, Bin, B, NC);
+  launch_k(mix_labels_kernel, dim3((int)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, labels, lam1, lam2, mode, y, Bin, B, NC);
   count_launch();
   return check_launch("mix_labels");
 }
@@ -690,7 +689,7 @@ int acnn_softmax_ce(const float* logits, const float* y, int B, int NC, int ld,
                     float* dbias, void* stream) {
   ACNN_REQUIRE(logits && y && loss_acc && dlogits && NC <= ld && B > 0,
                "softmax_ce: bad arguments");
-  softmax_ce_kernel<<<B, kPT, 0, (cudaStream_t)stream>>>(logits, y, B, NC, ld, label_smoothing,
+  launch_k(softmax_ce_kernel, dim3(B), dim3(kPT), 0, (cudaStream_t)stream, logits, y, B, NC, ld, label_smoothing,
                                                          grad_scale, loss_acc, (bf16*)dlogits,
                                                          dbias);
   count_launch();

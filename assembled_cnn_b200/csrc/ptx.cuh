@@ -9,6 +9,21 @@
 
 namespace acnn {
 
+#ifndef ACNN_PDL_PRIMS
+#define ACNN_PDL_PRIMS
+// Programmatic dependent launch entry (see common.h): let the dependent kernel start launching, then
+// wait until the preceding kernel has completed and its writes are visible.  No-ops when the kernel
+// was launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+  pdl_trigger();
+  pdl_wait();
+}
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

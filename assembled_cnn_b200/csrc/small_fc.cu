@@ -18,6 +18,7 @@ constexpr int kTM = 64, kTN = 64, kTK = 16;
 __global__ void __launch_bounds__(kFT)
 sgemm_acc_kernel(const float* __restrict__ A, const float* __restrict__ B, float* C, int M, int N,
                  int K, int sAm, int sAk, int sBk, int sBn, int k_per_split) {
+  pdl_entry();
   __shared__ float As[kTK][kTM + 4];
   __shared__ float Bs[kTK][kTN + 4];
   const int tid = threadIdx.x;
@@ -94,7 +95,7 @@ static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, 
   int kps = ceil_div(ceil_div(K, splits), kTK) * kTK;
   splits = ceil_div(K, kps);
   dim3 grid(ceil_div(N, kTN), ceil_div(M, kTM), splits);
-  sgemm_acc_kernel<<<grid, kFT, 0, s>>>(A, B, C, M, N, K, sAm, sAk, sBk, sBn, kps);
+  launch_k(sgemm_acc_kernel, dim3(grid), dim3(kFT), 0, s, A, B, C, M, N, K, sAm, sAk, sBk, sBn, kps);
   count_launch();
   return check_launch("sgemm_acc");
 }
@@ -105,6 +106,7 @@ bn_batch_relu_fwd_kernel(const float* __restrict__ zpre, const float* __restrict
                          const float* __restrict__ beta, float* moving_mean, float* moving_var,
                          float momentum, float eps, int training, float* __restrict__ z,
                          float* __restrict__ bnstat, int B, int d) {
+  pdl_entry();
   const int j = blockIdx.x * (kFT / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (j >= d) return;
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(kFT)
 bn_batch_relu_bwd_kernel(float* dz, const float* __restrict__ z, const float* __restrict__ zpre,
                          const float* __restrict__ bnstat, const float* __restrict__ gamma,
                          float* dgamma, float* dbeta, int B, int d) {
+  pdl_entry();
   const int j = blockIdx.x * (kFT / 32) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (j >= d) return;
@@ -178,6 +181,7 @@ bn_batch_relu_bwd_kernel(float* dz, const float* __restrict__ z, const float* __
 
 __global__ void sk_gate_fwd_kernel(const float* __restrict__ a, float* __restrict__ att, int B,
                                    int f) {
+  pdl_entry();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * f) return;
   const int b = (int)(i / f), c = (int)(i - (int64_t)b * f);
@@ -187,6 +191,7 @@ __global__ void sk_gate_fwd_kernel(const float* __restrict__ a, float* __restric
 
 __global__ void sk_gate_bwd_kernel(const float* __restrict__ dA, const float* __restrict__ att,
                                    float* __restrict__ da, int B, int f) {
+  pdl_entry();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * f) return;
   const int b = (int)(i / f), c = (int)(i - (int64_t)b * f);
@@ -199,6 +204,7 @@ __global__ void sk_gate_bwd_kernel(const float* __restrict__ dA, const float* __
 // 5: out = in*scale
 __global__ void ew_kernel(const float* in, const float* act, float* out, int64_t n, int mode,
                           float scale) {
+  pdl_entry();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float v = in[i];
@@ -213,7 +219,7 @@ __global__ void ew_kernel(const float* in, const float* act, float* out, int64_t
 
 static int ew(const float* in, const float* act, float* out, int64_t n, int mode, float scale,
               cudaStream_t s) {
-  ew_kernel<<<(int)ceil_div64(n, 256), 256, 0, s>>>(in, act, out, n, mode, scale);
+  launch_k(ew_kernel, dim3((int)ceil_div64(n, 256)), dim3(256), 0, s, in, act, out, n, mode, scale);
   count_launch();
   return check_launch("ew");
 }
@@ -234,13 +240,12 @@ int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const fl
   // zpre[B,d] = s[B,f] * W1[d,f]^T
   int rc = sgemm(s, w1, zpre, B, d, f, f, 1, 1, f, true, st);
   if (rc) return rc;
-  bn_batch_relu_fwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(
-      zpre, gamma, beta, moving_mean, moving_var, momentum, eps, training, z, bnstat, B, d);
+  launch_k(bn_batch_relu_fwd_kernel, dim3(ceil_div(d, kFT / 32)), dim3(kFT), 0, st, zpre, gamma, beta, moving_mean, moving_var, momentum, eps, training, z, bnstat, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_fwd"))) return rc;
   // a[B,2f] = z[B,d] * W2[2f,d]^T
   if ((rc = sgemm(z, w2, scratch, B, 2 * f, d, d, 1, 1, d, true, st))) return rc;
-  sk_gate_fwd_kernel<<<(int)ceil_div64((int64_t)B * f, 256), 256, 0, st>>>(scratch, att, B, f);
+  launch_k(sk_gate_fwd_kernel, dim3((int)ceil_div64((int64_t)B * f, 256)), dim3(256), 0, st, scratch, att, B, f);
   count_launch();
   return check_launch("sk_gate_fwd");
 }
@@ -254,7 +259,7 @@ int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const floa
   cudaStream_t st = (cudaStream_t)stream;
   float* da = scratch;                       // [B][2f]
   float* dz = scratch + (size_t)B * 2 * f;   // [B][d]
-  sk_gate_bwd_kernel<<<(int)ceil_div64((int64_t)B * f, 256), 256, 0, st>>>(dA, att, da, B, f);
+  launch_k(sk_gate_bwd_kernel, dim3((int)ceil_div64((int64_t)B * f, 256)), dim3(256), 0, st, dA, att, da, B, f);
   count_launch();
   int rc = check_launch("sk_gate_bwd");
   if (rc) return rc;
@@ -262,7 +267,7 @@ int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const floa
   if ((rc = sgemm(da, z, dw2, 2 * f, d, B, 1, 2 * f, d, 1, false, st))) return rc;
   // dz[B,d] = da[B,2f] * W2[2f,d]
   if ((rc = sgemm(da, w2, dz, B, d, 2 * f, 2 * f, 1, d, 1, true, st))) return rc;
-  bn_batch_relu_bwd_kernel<<<ceil_div(d, kFT / 32), kFT, 0, st>>>(dz, z, zpre, bnstat, gamma,
+  launch_k(bn_batch_relu_bwd_kernel, dim3(ceil_div(d, kFT / 32)), dim3(kFT), 0, st, dz, z, zpre, bnstat, gamma,
                                                                   dgamma, dbeta, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_bwd"))) return rc;

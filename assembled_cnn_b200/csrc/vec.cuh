@@ -6,6 +6,21 @@
 
 namespace acnn {
 
+#ifndef ACNN_PDL_PRIMS
+#define ACNN_PDL_PRIMS
+// Programmatic dependent launch entry (see common.h): let the dependent kernel start launching, then
+// wait until the preceding kernel has completed and its writes are visible.  No-ops when the kernel
+// was launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+  pdl_trigger();
+  pdl_wait();
+}
+#endif
+
 typedef __nv_bfloat16 bf16;
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {

@@ -34,6 +34,9 @@ const char* acnn_last_error(void);
 int acnn_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t acnn_launch_count(void);
+/* Programmatic dependent launch of every kernel of the library (no effect on results): 1 (default)
+ * = on, 0 = plain stream order.  Returns the previous setting. */
+int acnn_set_pdl(int on);
 /* Tuning knob of the conv GEMM launcher (no effect on results): M tiles (128 output pixels each)
  * per CTA tile.  -1 = choose per problem (default), 1 = always one, 2 = two wherever the shape
  * allows it (N tile <= 128).  Returns the previous mode. */
