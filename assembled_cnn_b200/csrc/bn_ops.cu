@@ -54,7 +54,7 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
               const float* __restrict__ sb, const float* __restrict__ hb, int b_mode,
               const float* __restrict__ gate, int relu, bf16* __restrict__ out, int H, int W, int C,
               int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   // CG divides the grid stride (a power of two <= 256 dividing 256*gridDim): the 8-channel group
@@ -236,7 +236,7 @@ bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
                     const float* __restrict__ coef, const float* __restrict__ gate,
                     const float* __restrict__ addbc, bf16* __restrict__ dy, int HW, int C,
                     int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int cg = (int)(i0 % CG);           // loop-invariant (see bn_act_kernel)
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(kT, 2)
 sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ att,
                   bf16* __restrict__ v, int HW, int f) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   const int CG = f >> 3;
@@ -556,7 +556,7 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        const float* __restrict__ att, const float* __restrict__ ds,
                        const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   const SkSlab q = sk_slab(HW, f);

@@ -11,7 +11,7 @@ namespace acnn {
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __restrict__ descs,
                     bf16* __restrict__ w_fprop, bf16* __restrict__ w_dgrad) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   __shared__ float tile[32][33];
   const acnn_weight_desc d = descs[blockIdx.y];
   const int tco = (d.Cout + 31) / 32, tci = (d.Cin + 31) / 32;
@@ -51,7 +51,7 @@ prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __
 // r = tap2 - pad2, a in {0,1};  channel = (a*2 + b)*4 + c.
 __global__ void s2d_weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ w2, int Cout,
                                        int k, int pad, int k2, int pad2) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t n = (int64_t)Cout * k2 * k2 * 16;
   if (i >= n) return;
@@ -70,7 +70,7 @@ __global__ void s2d_weight_pack_kernel(const float* __restrict__ w, bf16* __rest
 
 __global__ void s2d_wgrad_unpack_kernel(const float* __restrict__ dw2, float* __restrict__ dw,
                                         int Cout, int k, int pad, int k2, int pad2) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t n = (int64_t)Cout * k * k * 3;
   if (i >= n) return;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(256)
 sgd_momentum_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ acc,
                     int64_t n, const uint8_t* __restrict__ decay_flag, const float* __restrict__ hp,
                     float* l2_acc) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   __shared__ float sh[8];
   const float lr = hp[0], mom = hp[1], wd = hp[2], gs = hp[3];
   float l2 = 0.f;

@@ -33,7 +33,7 @@ __device__ __forceinline__ int reflect(int i, int n) {
 __global__ void __launch_bounds__(kPT)
 blurpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Binomial bw, int H, int W,
                     int C, int filt, int stride, int pad, int Ho, int Wo) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   // grid = (ceil(Wo * C/8 / threads), Ho, B): no 64-bit index decomposition per element
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -86,7 +86,7 @@ blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                     const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src,
                     Binomial bw, int H, int W, int C, int filt, int stride, int pad, int Ho,
                     int Wo) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   // grid = (ceil(W * C/8 / threads), H, B)
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -118,7 +118,7 @@ blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 __global__ void __launch_bounds__(kPT)
 avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
                    int stride, int pad, int Ho, int Wo, int count_pad) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   // grid = (ceil(Wo * C/8 / threads), Ho, B)
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kPT)
 avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                    const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H, int W,
                    int C, int k, int stride_rt, int pad, int Ho, int Wo, int count_pad) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int stride = STRIDE > 0 ? STRIDE : stride_rt;
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
@@ -218,7 +218,7 @@ avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 __global__ void __launch_bounds__(kPT)
 maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
                    int stride, int pad, int Ho, int Wo, int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -252,7 +252,7 @@ maxpool_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ x,
                    bf16* __restrict__ dx, const bf16* __restrict__ add_src,
                    const bf16* __restrict__ mask_src, int H, int W, int C, int k, int stride,
                    int pad, int Ho, int Wo, int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(kPT)
 upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
                       const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H,
                       int W, int C, int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -338,7 +338,7 @@ upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 __global__ void __launch_bounds__(kPT)
 zero_insert2x_kernel(const bf16* __restrict__ dy, bf16* __restrict__ out, int Ho, int Wo, int H,
                      int W, int C, int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -359,7 +359,7 @@ zero_insert2x_kernel(const bf16* __restrict__ dy, bf16* __restrict__ out, int Ho
 __global__ void __launch_bounds__(kPT)
 gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_src,
                bf16* __restrict__ dx, int HW, int C, int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   const float inv = 1.f / HW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
@@ -378,7 +378,7 @@ gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_s
 __global__ void __launch_bounds__(kPT)
 grad_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ add_src,
                     const bf16* __restrict__ mask_src, bf16* __restrict__ out, int64_t nvec) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
     float v[8];
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(kPT)
 pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
                   const float* __restrict__ lam2, int mode, bf16* __restrict__ out, int Bin, int B,
                   int H, int W, int wpad_lo, int wpad_hi, int64_t npix) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int H2 = H >> 1, W2 = W >> 1;
   const int Wp = W2 + wpad_lo + wpad_hi;
   const int half = Bin >> 1;
@@ -459,7 +459,7 @@ pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
 __global__ void mix_labels_kernel(const int32_t* __restrict__ labels,
                                   const float* __restrict__ lam1, const float* __restrict__ lam2,
                                   int mode, float* __restrict__ y, int Bin, int B, int NC) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * NC) return;
   const int b = (int)(i / NC), c = (int)(i - (int64_t)b * NC);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(kPT)
 softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y, int B, int NC,
                   int ld, float ls, float grad_scale, float* loss_acc, bf16* __restrict__ dlogits,
                   float* dbias) {
-  pdl_entry();
+  pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   __shared__ float sh[kPT / 32];
   const int b = blockIdx.x;
   const float* lg = logits + (size_t)b * ld;
