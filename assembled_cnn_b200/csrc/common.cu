@@ -17,8 +17,11 @@ void set_error(const char* fmt, ...) {
 }
 
 static int pdl_default() {
+  // measured on the full training step: 25.3-25.5 ms with the attribute vs 24.9 ms without (an early
+  // resident dependent takes registers / SM slots from the still-running HBM-bound predecessor), so
+  // it is opt-in
   const char* e = getenv("ACNN_PDL");
-  return (e && e[0] == '0') ? 0 : 1;
+  return (e && e[0] == '1') ? 1 : 0;
 }
 int g_use_pdl = pdl_default();
 

@@ -27,9 +27,9 @@ int check_launch(const char* what);
 // `griddepcontrol.launch_dependents; griddepcontrol.wait;` (pdl_entry() in vec.cuh / ptx.cuh), so a
 // kernel launched with the programmatic-stream-serialization attribute may be scheduled (CTAs
 // resident, prologue done) while its predecessor drains, and only proceeds past the wait once the
-// predecessor grid has completed and flushed.  This hides the per-kernel launch / drain latency of
-// the ~865 dependent launches of a step (also inside the captured CUDA graph).
-extern int g_use_pdl;   // 1 by default; ACNN_PDL=0 or acnn_set_pdl(0) turns the attribute off
+// predecessor grid has completed and flushed.  Meant to hide the per-kernel launch / drain latency
+// of the ~865 dependent launches of a step; measured NOT to pay here (kept as an opt-in knob).
+extern int g_use_pdl;   // 0 by default (measured slower, see common.cu); ACNN_PDL=1 / acnn_set_pdl(1)
 
 template <class... KArgs, class... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

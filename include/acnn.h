@@ -34,8 +34,8 @@ const char* acnn_last_error(void);
 int acnn_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t acnn_launch_count(void);
-/* Programmatic dependent launch of every kernel of the library (no effect on results): 1 (default)
- * = on, 0 = plain stream order.  Returns the previous setting. */
+/* Programmatic dependent launch of every kernel of the library (no effect on results): 0 (default)
+ * = plain stream order, 1 = on (measured slower on the full step).  Returns the previous setting. */
 int acnn_set_pdl(int on);
 /* Tuning knob of the conv GEMM launcher (no effect on results): M tiles (128 output pixels each)
  * per CTA tile.  -1 = choose per problem (default), 1 = always one, 2 = two wherever the shape
