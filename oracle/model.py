@@ -1,6 +1,12 @@
 """CPU oracle, part 2: the assembled-ResNet forward pass, loss and SGD step (torch CPU, fp32/fp64).
 
-TEST INFRASTRUCTURE ONLY (see oracle/tf_ops.py header; PARITY UNPINNED by the reference).
+TEST INFRASTRUCTURE ONLY (see oracle/tf_ops.py header).  PINNED against the reference's own code:
+the reference's nets/resnet_model.py + nets/blocks.py + nets/model_helper.py are executed through
+a TF-1.14 API stand-in (tests/golden/tf1_shim) to produce tests/golden/reference_shim_golden.json;
+tests/test_reference_shim_golden_cpu.py checks this file's variable inventory (names, shapes,
+initializers, creation order: 8 configurations up to ResNet-152) and its logits / BN moving
+statistics (inference and training mode) against it.  The numerical semantics of the individual TF
+kernels stay unpinned (TensorFlow 1.14 is not installable): they are shared with the stand-in.
 
 Restates nets/resnet_model.py:35-599 (Model.__call__, block_layer, _bottleneck_block_v1),
 functions/model_fns.py:98-198 (topology constants), nets/run_loop_classification.py:86-179 (loss

@@ -3,11 +3,14 @@
 TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is imported by the product package; only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call it.
 
-PARITY UNPINNED: the reference (clovaai/assembled-cnn) ships no tests or golden vectors for this
-path and its arithmetic lives in the un-vendored dependency tensorflow==1.14.0 (README.md:85),
-which cannot be installed here (Python 3.12, no network).  This file restates the published TF-1.14
-semantics at the reference's own call sites (file:line below); tests/test_oracle_known_answers.py
-pins each rule with hand-computed micro-vectors.
+PARITY UNPINNED at the level of this file: the reference (clovaai/assembled-cnn) ships no tests or
+golden vectors for this path and its arithmetic lives in the un-vendored dependency
+tensorflow==1.14.0 (README.md:85), which cannot be installed here (Python 3.12, no network).  This
+file restates the published TF-1.14 semantics at the reference's own call sites (file:line below);
+tests/test_oracle_known_answers.py pins each rule with hand-computed micro-vectors.  What IS pinned
+against the reference itself is the model assembly built on these primitives: oracle/model.py is
+checked against golden vectors produced by executing the reference's own model code through a
+TF-API stand-in (tests/golden/make_reference_shim_golden.py, tests/test_reference_shim_golden_cpu.py).
 
 All tensors are torch CPU tensors, activations NHWC (the reference's CPU layout,
 nets/resnet_model.py:196-198), conv kernels HWIO, dense kernels [in, out].

@@ -1,6 +1,7 @@
 """Known-answer micro-vectors that pin the oracle to the TF-1.14 semantics the reference relies on
 (SURVEY App. B).  The reference ships no tests for this path, so these hand-computed vectors are
-the pin ("parity unpinned" by the reference itself -- see oracle/tf_ops.py header)."""
+the pin of the TF kernel semantics ("parity unpinned" by the reference itself -- see oracle/tf_ops.py
+header; the model assembly is pinned separately by tests/test_reference_shim_golden_cpu.py)."""
 import math
 
 import torch
