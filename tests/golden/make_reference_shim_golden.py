@@ -87,6 +87,20 @@ def names_digest(order):
     return h.hexdigest()
 
 
+def reference_function(rel_path, name):
+    """Compile ONE function of a reference module (by its AST) against the shim: the module's other
+    top-level imports (Estimator run loop, preprocessing, absl flags) are not needed for it."""
+    import ast
+    sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
+    import tensorflow as tf
+    src = open(os.path.join("/root/reference", rel_path)).read()
+    # (ast.walk: also finds functions nested inside other functions, e.g. exclude_batch_norm)
+    node = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"tf": tf}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), rel_path, "exec"), ns)
+    return ns[name], tf
+
+
 def run_reference(flags, use_resnet_d, batch, size):
     sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
     sys.path.insert(0, "/root/reference")
@@ -127,11 +141,87 @@ def run_reference(flags, use_resnet_d, batch, size):
     mv = torch.cat([tf.variables.vars[o[0]].t.flatten() for o in order if o[0].endswith("moving_variance")])
     out["moving_mean_after"] = digest(mm)
     out["moving_variance_after"] = digest(mv)
+    # nets/run_loop_classification.py:163-176: which trainable variables enter the L2 term
+    exclude_batch_norm, _ = reference_function("nets/run_loop_classification.py", "exclude_batch_norm")
+    decayed = [o[0] for o in order if o[3] and exclude_batch_norm(o[0] + ":0")]
+    out["num_decayed"] = len(decayed)
+    out["decayed_sha256"] = hashlib.sha256("\n".join(decayed).encode()).hexdigest()
     return out, order
 
 
+MIXUP_B, MIXUP_HW, MIXUP_NC = 8, 4, 5
+LR_CASES = {   # name -> kwargs of functions/model_fns.py learning_rate_with_decay (+ probe steps)
+    "cosine_warmup5_b1024": dict(learning_rate_decay_type="cosine", batch_size=1024, batch_denom=1024,
+                                 num_images=1281167, num_epochs_per_decay=2.0, learning_rate_decay_factor=0.94,
+                                 end_learning_rate=0.0001, piecewise_lr_boundary_epochs=[30, 60, 80, 90],
+                                 piecewise_lr_decay_rates=[1, 0.1, 0.01, 0.001, 1e-4], base_lr=0.4,
+                                 warmup_epochs=5, train_epochs=600),
+    "piecewise_b256": dict(learning_rate_decay_type="piecewise", batch_size=256, batch_denom=256,
+                           num_images=1281167, num_epochs_per_decay=2.0, learning_rate_decay_factor=0.94,
+                           end_learning_rate=0.0001, piecewise_lr_boundary_epochs=[30, 60, 80, 90],
+                           piecewise_lr_decay_rates=[1, 0.1, 0.01, 0.001, 1e-4], base_lr=0.1,
+                           warmup_epochs=0, train_epochs=100),
+    "exponential_warmup1": dict(learning_rate_decay_type="exponential", batch_size=512, batch_denom=512,
+                                num_images=1281167, num_epochs_per_decay=2.0, learning_rate_decay_factor=0.94,
+                                end_learning_rate=0.0001, piecewise_lr_boundary_epochs=[30],
+                                piecewise_lr_decay_rates=[1, 0.1], base_lr=0.2, warmup_epochs=1,
+                                train_epochs=100),
+    "polynomial": dict(learning_rate_decay_type="polynomial", batch_size=256, batch_denom=256,
+                       num_images=50000, num_epochs_per_decay=30.0, learning_rate_decay_factor=0.94,
+                       end_learning_rate=0.0001, piecewise_lr_boundary_epochs=[30],
+                       piecewise_lr_decay_rates=[1, 0.1], base_lr=0.1, warmup_epochs=0, train_epochs=100),
+    "fixed": dict(learning_rate_decay_type="fixed", batch_size=256, batch_denom=256, num_images=50000,
+                  num_epochs_per_decay=30.0, learning_rate_decay_factor=0.94, end_learning_rate=0.0001,
+                  piecewise_lr_boundary_epochs=[30], piecewise_lr_decay_rates=[1, 0.1], base_lr=0.05,
+                  warmup_epochs=0, train_epochs=100),
+}
+LR_STEPS = [0, 1, 100, 1250, 2501, 6254, 6256, 10000, 150134, 150136, 300000, 450408, 700000]
+
+
+def mixup_inputs():
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(MIXUP_B, MIXUP_HW, MIXUP_HW, 3, generator=g)
+    y = torch.nn.functional.one_hot(torch.randint(0, MIXUP_NC, (MIXUP_B,), generator=g), MIXUP_NC).float()
+    lam1 = torch.rand(MIXUP_B // 2, generator=g)
+    lam2 = torch.rand(MIXUP_B // 2, generator=g)
+    return x, y, lam1, lam2
+
+
+def loss_inputs():
+    g = torch.Generator().manual_seed(78)
+    logits = torch.randn(6, 11, generator=g) * 3
+    y = torch.softmax(torch.randn(6, 11, generator=g), dim=1)      # soft (mixed) labels
+    return logits, y
+
+
+def run_train_pieces():
+    out = {}
+    # utils/data_util.py:97-158 mixup (types 1 and 2)
+    mixup, tf = reference_function("utils/data_util.py", "mixup")
+    x, y, lam1, lam2 = mixup_inputs()
+    for keep in (False, True):
+        tf.beta_samples[:] = [lam1, lam2] if keep else [lam1]
+        mx, my, _ = mixup(tf.Tensor(x), tf.Tensor(y), alpha=0.2, keep_batch_size=keep)
+        out["mixup_keep_%d" % keep] = {"x": digest(mx.t), "y": digest(my.t), "x_shape": list(mx.t.shape),
+                                        "y_rows": my.t.tolist()}
+    # losses/cls_losses.py:23-41 get_sup_loss (softmax + label smoothing)
+    get_sup_loss, tf = reference_function("losses/cls_losses.py", "get_sup_loss")
+    logits, yy = loss_inputs()
+    for ls in (0.0, 0.1):
+        ce = get_sup_loss(tf.Tensor(logits), tf.Tensor(yy), None, 11,
+                          {"cls_loss_type": "softmax", "label_smoothing": ls})
+        out["softmax_ce_ls_%g" % ls] = float(ce.t)
+    # functions/model_fns.py:36-95 learning_rate_with_decay
+    lr_with_decay, tf = reference_function("functions/model_fns.py", "learning_rate_with_decay")
+    for name, kw in LR_CASES.items():
+        fn = lr_with_decay(**kw)
+        out["lr_" + name] = [float(tf._raw(fn(tf.Tensor(torch.tensor(s))))) for s in LR_STEPS]
+    return out
+
+
 if __name__ == "__main__":
-    gold = {}
+    gold = {"train_pieces": run_train_pieces()}
+    print("train pieces:", sorted(gold["train_pieces"]))
     for name, (flags, d, b, s) in CONFIGS.items():
         gold[name], _ = run_reference(flags, d, b, s)
         print(name, gold[name]["num_variables"], gold[name]["eval_logits"]["abs_sum"])

@@ -383,7 +383,7 @@ def split(x, num_or_size_splits, axis=0, name=None):
 def concat(xs, axis, name=None): return Tensor(torch.cat([_raw(x) for x in xs], dim=axis))
 def stack(xs, axis=0, name=None): return Tensor(torch.stack([torch.as_tensor(_raw(x)) for x in xs], dim=axis))
 def identity(x, name=None): return x
-def cast(x, dtype, name=None): return Tensor(_raw(x).to(dtype.torch))
+def cast(x, dtype, name=None): return Tensor(torch.as_tensor(_raw(x)).to(dtype.torch))
 def to_float(x): return Tensor(torch.as_tensor(_raw(x), dtype=torch.float32))
 def multiply(a, b, name=None):
     r = torch.as_tensor(_raw(a)) * torch.as_tensor(_raw(b))
@@ -406,6 +406,7 @@ def constant(value, dtype=None, name=None):
     return Tensor(torch.as_tensor(np.asarray(value), dtype=(dtype or float32).torch))
 
 
+
 def pad(x, paddings, mode="CONSTANT", name=None):
     t = _raw(x)
     assert t.dim() == 4 and paddings[0] == [0, 0] and paddings[3] == [0, 0]
@@ -423,6 +424,7 @@ class _Logging:
     @staticmethod
     def info(*a, **k): pass
     warn = warning = debug = info
+    error = info
 
 
 logging = _Logging()
@@ -434,6 +436,122 @@ class _Test:
 
 
 test = _Test()
+
+
+# ----------------------------------------------------------------------------- utils/data_util.mixup
+VERSION = "1.14.0"
+
+
+def shape(x, name=None):
+    return list(_raw(x).shape)
+
+
+def reverse(x, axis, name=None): return Tensor(torch.flip(_raw(x), dims=list(axis)))
+def stop_gradient(x, name=None): return Tensor(_raw(x).detach())
+
+
+Tensor.get_shape = lambda self: self.shape
+
+
+class _Beta:
+    """tf.contrib.distributions.Beta: samples come from the queue the golden generator fills
+    (`beta_samples`), so that the reference code and the oracle see the same lambdas."""
+    queue = []
+
+    def __init__(self, a, b):
+        self.a, self.b = a, b
+
+    def sample(self, shape):
+        n = int(shape[0])
+        v = _Beta.queue.pop(0)
+        assert v.numel() == n, (v.numel(), n)
+        return Tensor(v.clone())
+
+
+beta_samples = _Beta.queue
+
+
+class _Dummy:
+    """Anything else the reference's modules touch at import time (summaries, estimators, ...)."""
+
+    def __init__(self, name="tf"):
+        self._n = name
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return _Dummy(self._n + "." + k)
+
+    def __call__(self, *a, **k):
+        raise NotImplementedError("%s is outside the pinned path" % self._n)
+
+
+# ----------------------------------------------------------------------------- tf.train / tf.losses
+def _f(x):
+    return float(_raw(x)) if isinstance(x, Tensor) else float(x)
+
+
+class _Train:
+    """Learning-rate schedules as documented for TF 1.14 (python/training/learning_rate_decay*.py)."""
+
+    @staticmethod
+    def exponential_decay(lr, global_step, decay_steps, decay_rate, staircase=False, name=None):
+        p = _f(global_step) / decay_steps
+        return Tensor(torch.tensor(lr * decay_rate ** (np.floor(p) if staircase else p)))
+
+    @staticmethod
+    def polynomial_decay(lr, global_step, decay_steps, end_learning_rate=0.0001, power=1.0,
+                         cycle=False, name=None):
+        g = min(_f(global_step), decay_steps)
+        return Tensor(torch.tensor((lr - end_learning_rate) * (1 - g / decay_steps) ** power
+                                   + end_learning_rate))
+
+    @staticmethod
+    def piecewise_constant(x, boundaries, values, name=None):
+        # values[0] for x <= boundaries[0], values[i] for boundaries[i-1] < x <= boundaries[i]
+        return Tensor(torch.tensor(values[sum(1 for b in boundaries if _f(x) > b)]))
+
+    @staticmethod
+    def cosine_decay(lr, global_step, decay_steps, alpha=0.0, name=None):
+        g = min(_f(global_step), decay_steps)
+        cos = 0.5 * (1 + np.cos(np.pi * g / decay_steps))
+        return Tensor(torch.tensor(lr * ((1 - alpha) * cos + alpha)))
+
+
+train = _Train()
+
+
+def cond(pred, true_fn, false_fn, name=None):
+    return true_fn() if bool(_raw(pred)) else false_fn()
+
+
+Tensor.__lt__ = lambda self, o: Tensor(self.t < _raw(o))
+
+
+class _Losses:
+    @staticmethod
+    def softmax_cross_entropy(onehot_labels, logits, weights=1.0, label_smoothing=0, **kw):
+        """tf.losses.softmax_cross_entropy: labels smoothed towards 1/num_classes, per-example
+        cross entropy, reduction SUM_BY_NONZERO_WEIGHTS (= batch mean for a scalar weight)."""
+        y, z = _raw(onehot_labels).float(), _raw(logits).float()
+        if label_smoothing > 0:
+            n = y.shape[1]
+            y = y * (1 - label_smoothing) + label_smoothing / n
+        per = -(y * torch.log_softmax(z, dim=1)).sum(dim=1)
+        return Tensor((per * weights).sum() / per.numel())
+
+
+losses = _Losses()
+
+contrib = _NS()
+contrib.distributions = _NS()
+contrib.distributions.Beta = _Beta
+
+
+def __getattr__(name):          # PEP 562: unknown tf.<name>
+    if name.startswith("__"):
+        raise AttributeError(name)
+    return _Dummy("tf." + name)
 
 
 def reset(values=None):

@@ -5,8 +5,10 @@ container where /root/reference is mounted -- this test only reads the committed
 
 Pinned: variable names / shapes / initializer kinds / creation order of 8 model configurations
 (including the Assemble-ResNet-50 of the north star, ResNet-D, SE, proj anti-alias, zero-gamma, R101,
-R152), and the logits + updated BN moving statistics for seeded inputs and seeded variable values, in
-inference and in training mode."""
+R152), which of them enter the weight-decay term (nets/run_loop_classification.py:163-176), the
+logits + updated BN moving statistics for seeded inputs and seeded variable values in inference and
+in training mode, mixup types 1 / 2 (utils/data_util.py:97-158), the softmax cross entropy with label
+smoothing (losses/cls_losses.py) and the five learning-rate schedules (functions/model_fns.py:36-95)."""
 import hashlib
 import importlib.util
 import json
@@ -21,6 +23,7 @@ spec = importlib.util.spec_from_file_location(
 mg = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(mg)
 GOLD = json.load(open(os.path.join(HERE, "golden", "reference_shim_golden.json")))
+PIECES = GOLD["train_pieces"]
 
 KIND = {"conv_kernel": "variance_scaling", "dense_kernel": "glorot_uniform", "dense_bias": "zeros",
         "beta": "zeros", "moving_mean": "zeros", "moving_variance": "ones"}
@@ -56,6 +59,11 @@ def test_variable_inventory_matches_reference_code(name):
                                      bool(vs.trainable[n]))).encode())
     assert zero_gammas == gold["zero_init_gammas"]
     assert h.hexdigest() == gold["names_sha256"]
+    # the variables that enter the weight-decay term (run_loop_classification.py:163-176)
+    from oracle import model as M
+    decayed = [n for n in names if vs.trainable[n] and M.decayed(n)]
+    assert len(decayed) == gold["num_decayed"]
+    assert hashlib.sha256("\n".join(decayed).encode()).hexdigest() == gold["decayed_sha256"]
 
 
 @pytest.mark.parametrize("name", [n for n in sorted(mg.CONFIGS) if "152" not in n and "101" not in n])
@@ -85,3 +93,43 @@ def test_forward_matches_reference_code(name):
     for k in ("sum", "abs_sum"):
         assert _close(mg.digest(mm)[k], gold["moving_mean_after"][k], 1e-4)
         assert _close(mg.digest(mv)[k], gold["moving_variance_after"][k], 1e-4)
+
+
+@pytest.mark.parametrize("keep", [False, True], ids=["mixup_type_1", "mixup_type_2"])
+def test_mixup_matches_reference_code(keep):
+    """utils/data_util.py:97-158 executed through the stand-in with the same lambdas."""
+    from oracle import tf_ops as T
+    x, y, lam1, lam2 = mg.mixup_inputs()
+    mx, my = T.mixup(x, y, lam1, lam2 if keep else None, keep_batch_size=keep)
+    gold = PIECES["mixup_keep_%d" % keep]
+    assert list(mx.shape) == gold["x_shape"]
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(mg.digest(mx)[k], gold["x"][k], 1e-6)
+        assert _close(mg.digest(my)[k], gold["y"][k], 1e-6)
+    assert torch.allclose(my, torch.tensor(gold["y_rows"]), atol=1e-6)
+
+
+@pytest.mark.parametrize("ls", [0.0, 0.1])
+def test_softmax_ce_matches_reference_code(ls):
+    """losses/cls_losses.py:23-41 (soft labels, label smoothing over the given number of classes)."""
+    from oracle import tf_ops as T
+    logits, y = mg.loss_inputs()
+    got = float(T.softmax_cross_entropy(logits, y, ls))
+    assert _close(got, PIECES["softmax_ce_ls_%g" % ls], 1e-6)
+
+
+@pytest.mark.parametrize("case", sorted(mg.LR_CASES))
+def test_learning_rate_schedule_matches_reference_code(case):
+    """functions/model_fns.py:36-95 learning_rate_with_decay executed through the stand-in."""
+    from oracle import tf_ops as T
+    kw = mg.LR_CASES[case]
+    for step, want in zip(mg.LR_STEPS, PIECES["lr_" + case]):
+        got = T.learning_rate(step, decay_type=kw["learning_rate_decay_type"], batch_size=kw["batch_size"],
+                              num_images=kw["num_images"], base_lr=kw["base_lr"],
+                              warmup_epochs=kw["warmup_epochs"], train_epochs=kw["train_epochs"],
+                              num_epochs_per_decay=kw["num_epochs_per_decay"],
+                              decay_factor=kw["learning_rate_decay_factor"],
+                              end_learning_rate=kw["end_learning_rate"],
+                              boundary_epochs=tuple(kw["piecewise_lr_boundary_epochs"]),
+                              decay_rates=tuple(kw["piecewise_lr_decay_rates"]))
+        assert _close(got, want, 1e-5, 1e-9), (case, step, got, want)
