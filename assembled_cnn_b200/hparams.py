@@ -32,13 +32,13 @@ DEFAULTS = {
     "piecewise_lr_decay_rates": [1, 0.1, 0.01, 0.001, 1e-4],
     "lr_warmup_epochs": 0,                # :211
     "use_dropblock": False,               # :191
-    "dropblock_kp": [1.0, 1.0],
+    "dropblock_kp": [1.0, 0.9],           # :195 (inactive unless use_dropblock)
     "kd_temp": 0,                         # :204
     "pool_type": "gap",                   # :116
     "embedding_size": 0,                  # :76
     "no_downsample": False,
     "cls_loss_type": "softmax",
-    "dataset_name": "imagenet",           # :31 (None in the reference; ImageNet constants used here)
+    "dataset_name": None,                 # :31 (None -> the ImageNet constants, as data_config)
     # official/utils/flags/_base.py:50-105, _performance.py:74-137
     "batch_size": 32,
     "train_epochs": 90,                   # main_classification.py:38

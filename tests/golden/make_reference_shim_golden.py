@@ -194,8 +194,27 @@ def loss_inputs():
     return logits, y
 
 
-def run_train_pieces():
+def reference_flag_defaults():
+    """nets/hparams_config.py: every flags.DEFINE_*(name=..., default=...) call, read from the AST
+    (literal defaults only)."""
+    import ast
     out = {}
+    tree = ast.parse(open("/root/reference/nets/hparams_config.py").read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and \
+                node.func.attr.startswith("DEFINE_"):
+            kw = {k.arg: k.value for k in node.keywords}
+            if "name" in kw and "default" in kw:
+                try:
+                    out[ast.literal_eval(kw["name"])] = {"kind": node.func.attr[len("DEFINE_"):],
+                                                         "default": ast.literal_eval(kw["default"])}
+                except ValueError:
+                    pass
+    return out
+
+
+def run_train_pieces():
+    out = {"flag_defaults": reference_flag_defaults()}
     # utils/data_util.py:97-158 mixup (types 1 and 2)
     mixup, tf = reference_function("utils/data_util.py", "mixup")
     x, y, lam1, lam2 = mixup_inputs()

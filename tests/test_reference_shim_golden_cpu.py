@@ -133,3 +133,25 @@ def test_learning_rate_schedule_matches_reference_code(case):
                               boundary_epochs=tuple(kw["piecewise_lr_boundary_epochs"]),
                               decay_rates=tuple(kw["piecewise_lr_decay_rates"]))
         assert _close(got, want, 1e-5, 1e-9), (case, step, got, want)
+
+
+def test_flag_names_and_defaults_match_reference_code():
+    """nets/hparams_config.py: every flag the product exposes under the reference's name has the
+    reference's default (read from the AST of the DEFINE_* calls)."""
+    from assembled_cnn_b200.hparams import DEFAULTS
+    ref = PIECES["flag_defaults"]
+    assert len(ref) >= 50
+    common = [k for k in DEFAULTS if k in ref]
+    assert len(common) >= 30
+    for k in common:
+        want = ref[k]["default"]
+        got = DEFAULTS[k]
+        if ref[k]["kind"] == "enum" and not isinstance(got, str):
+            got = str(got)                     # e.g. resnet_version: enum of '1' / '2'
+        if isinstance(want, (list, tuple)):
+            assert [float(v) for v in got] == [float(v) for v in want], k
+        else:
+            assert got == want, (k, got, want)
+    # flags of the official.utils.flags core set / the run loop, not defined in hparams_config.py
+    assert set(DEFAULTS) - set(ref) <= {"resnet_size", "batch_size", "train_epochs", "dtype",
+                                        "loss_scale", "data_format", "num_gpus"}
