@@ -141,6 +141,23 @@ def run_reference(flags, use_resnet_d, batch, size):
     mv = torch.cat([tf.variables.vars[o[0]].t.flatten() for o in order if o[0].endswith("moving_variance")])
     out["moving_mean_after"] = digest(mm)
     out["moving_variance_after"] = digest(mv)
+    # gradients of the reference's graph (torch autograd through the stand-in) of
+    # loss = get_sup_loss(label_smoothing 0.1) + 1e-4 * sum l2_loss(decayed variables), inference-mode
+    # BN (well conditioned) -- what the product's explicit backward is tested against via the oracle
+    if out["num_variables"] < 600:
+        get_sup_loss, _ = reference_function("losses/cls_losses.py", "get_sup_loss")
+        exclude_bn, _ = reference_function("nets/run_loop_classification.py", "exclude_batch_norm")
+        tf.reset(values, requires_grad=True)
+        y = make()(tf.Tensor(x), training=False, use_resnet_d=use_resnet_d)
+        lab = torch.nn.functional.one_hot(torch.arange(batch) * 37 % 1001, 1001).float()
+        ce = get_sup_loss(y, tf.Tensor(lab), None, 1001, {"cls_loss_type": "softmax", "label_smoothing": 0.1})
+        l2 = sum((tf.variables.vars[o[0]].t ** 2).sum() / 2 for o in order if o[3] and exclude_bn(o[0] + ":0"))
+        loss = ce.t + 1e-4 * l2
+        loss.backward()
+        out["loss_eval_mode"] = float(loss)
+        tr = [o[0] for o in order if o[3]]
+        picks = [tr[0], tr[len(tr) // 3], tr[len(tr) // 2], tr[-2], tr[-1]]
+        out["grads_eval_mode"] = {n: digest(tf.variables.vars[n].t.grad) for n in picks}
     # nets/run_loop_classification.py:163-176: which trainable variables enter the L2 term
     exclude_batch_norm, _ = reference_function("nets/run_loop_classification.py", "exclude_batch_norm")
     decayed = [o[0] for o in order if o[3] and exclude_batch_norm(o[0] + ":0")]

@@ -155,9 +155,10 @@ class _Variables:
     def __init__(self):
         self.reset()
 
-    def reset(self, values=None):
+    def reset(self, values=None, requires_grad=False):
         self.order = []          # [(full name, shape, initializer kind, trainable)]
         self.values = values     # dict name -> torch tensor, or None (initializer defaults)
+        self.requires_grad = requires_grad   # leaves for torch autograd through the reference graph
         self.vars = {}
 
 
@@ -246,6 +247,8 @@ def _base_getter(name, shape=None, dtype=float32, initializer=None, trainable=Tr
     else:
         v = torch.zeros(shape)
     variables.order.append((name, shape, kind, bool(trainable)))
+    if variables.requires_grad and trainable:
+        v.requires_grad_(True)
     variables.vars[name] = Tensor(v, name=name)
     return variables.vars[name]
 
@@ -356,6 +359,7 @@ class _NN:
 
 
 nn = _NN()
+nn.l2_loss = staticmethod(lambda t, name=None: Tensor((_raw(t).float() ** 2).sum() / 2))
 
 
 def _axes(axis):
@@ -554,8 +558,9 @@ def __getattr__(name):          # PEP 562: unknown tf.<name>
     return _Dummy("tf." + name)
 
 
-def reset(values=None):
+def reset(values=None, requires_grad=False):
     """Start a fresh 'graph': empty scope counts, empty variable record; `values` (name -> tensor)
-    supplies the variable values, else the initializers' trivial defaults are used."""
+    supplies the variable values, else the initializers' trivial defaults are used.  With
+    requires_grad the trainable variables are autograd leaves (gradients of the reference's graph)."""
     _store.reset()
-    variables.reset(values)
+    variables.reset(values, requires_grad)

@@ -7,7 +7,8 @@ Pinned: variable names / shapes / initializer kinds / creation order of 8 model 
 (including the Assemble-ResNet-50 of the north star, ResNet-D, SE, proj anti-alias, zero-gamma, R101,
 R152), which of them enter the weight-decay term (nets/run_loop_classification.py:163-176), the
 logits + updated BN moving statistics for seeded inputs and seeded variable values in inference and
-in training mode, mixup types 1 / 2 (utils/data_util.py:97-158), the softmax cross entropy with label
+in training mode, the loss and its gradients (torch autograd through the reference's graph,
+inference-mode BN), mixup types 1 / 2 (utils/data_util.py:97-158), the softmax cross entropy with label
 smoothing (losses/cls_losses.py) and the five learning-rate schedules (functions/model_fns.py:36-95)."""
 import hashlib
 import importlib.util
@@ -81,6 +82,20 @@ def test_forward_matches_reference_code(name):
         assert _close(got[k], gold["eval_logits"][k], 2e-4, 1e-4), (k, got[k], gold["eval_logits"][k])
     for a, b in zip(y[0, :8].tolist(), gold["eval_logits_row0_head"]):
         assert _close(a, b, 2e-4, 1e-4)
+    # gradients of loss = smoothed CE + 1e-4 * L2 (inference-mode BN) through the reference's graph
+    for n in vs.vars:
+        vs.vars[n].requires_grad_(bool(vs.trainable[n]))
+    lab = torch.nn.functional.one_hot(torch.arange(batch) * 37 % 1001, 1001).float()
+    loss, _, _, _ = M.loss_fn(model, vs, x, lab, training=False, use_resnet_d=d, label_smoothing=0.1,
+                              weight_decay=1e-4)
+    loss.backward()
+    assert _close(float(loss.detach()), gold["loss_eval_mode"], 1e-5)
+    for n, want in gold["grads_eval_mode"].items():
+        got = mg.digest(vs.vars[n].grad)
+        assert _close(got["abs_sum"], want["abs_sum"], 2e-3, 1e-7), (n, got, want)
+        assert _close(got["sum"], want["sum"], 2e-3, 1e-3 * want["abs_sum"] + 1e-7), (n, got, want)
+    for n in vs.vars:
+        vs.vars[n] = vs.vars[n].detach()
     # training mode: batch statistics + moving-average updates (UPDATE_OPS)
     with torch.no_grad():
         y = M.forward(model, vs, x, training=True, use_resnet_d=d)
