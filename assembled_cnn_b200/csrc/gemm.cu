@@ -185,41 +185,6 @@ struct FpropCfg {
   }
 };
 
-// Sum over the 32 lanes of a warp of 32 per-lane values each: on return lane l holds the total
-// of column l.  Butterfly exchange: 31 shuffles instead of 160.
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float send = (lane & 16) ? v[i] : v[i + 16];
-    float keep = (lane & 16) ? v[i + 16] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float send = (lane & 8) ? v[i] : v[i + 8];
-    float keep = (lane & 8) ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float send = (lane & 4) ? v[i] : v[i + 4];
-    float keep = (lane & 4) ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float send = (lane & 2) ? v[i] : v[i + 2];
-    float keep = (lane & 2) ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  {
-    float send = (lane & 1) ? v[0] : v[1];
-    float keep = (lane & 1) ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  return v[0];
-}
-
 // One CTA per SM walks output tiles (fixed N tile, M tiles strided by the grid).  The TMA producer
 // runs ahead across tiles through the smem ring; the MMA issuer alternates between two TMEM
 // accumulators; the 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks)
