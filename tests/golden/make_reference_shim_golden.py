@@ -43,6 +43,9 @@ CONFIGS = {
     "assemble_r152_rv2_sk_sconv": (dict(resnet_size=152, resnet_version=2, use_sk_block=True,
                                         anti_alias_type="sconv", anti_alias_filter_size=3), False, 2, 64),
     "r101_rv1_resnet_d": (dict(resnet_size=101, resnet_version=1), True, 2, 64),
+    "baseline_c5_assemble_r152_alpha1_beta2": (dict(resnet_size=152, resnet_version=2, use_sk_block=True,
+                                                    anti_alias_type="sconv", anti_alias_filter_size=3,
+                                                    bl_alpha=1, bl_beta=2), False, 2, 64),
 }
 BLOCK_SIZES = {1: {50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3], 200: [3, 24, 36, 3]}}
 
@@ -126,6 +129,13 @@ def run_reference(flags, use_resnet_d, batch, size):
     out = {"num_variables": len(order), "names_sha256": names_digest(order),
            "first_names": [o[0] for o in order[:3]], "last_names": [o[0] for o in order[-2:]],
            "zero_init_gammas": sum(1 for o in order if o[2] == "zeros" and o[0].endswith("/gamma")),
+           # separate digests of the trainable variables (creation order, with TF shapes) and of the
+           # non-trainable BN statistics: what the product's plan (params / state) is checked against
+           "trainable_sha256": hashlib.sha256("\n".join(
+               "%s|%s" % (o[0], ",".join(map(str, o[1]))) for o in order if o[3]).encode()).hexdigest(),
+           "num_trainable": sum(1 for o in order if o[3]),
+           "state_sha256": hashlib.sha256("\n".join(
+               "%s|%s" % (o[0], ",".join(map(str, o[1]))) for o in order if not o[3]).encode()).hexdigest(),
            "batch": batch, "size": size, "use_resnet_d": use_resnet_d}
     x = seeded_input(batch, size)
     # pass 2: inference mode with the seeded values

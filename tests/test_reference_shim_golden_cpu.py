@@ -3,9 +3,9 @@
 (tests/golden/tf1_shim, generator tests/golden/make_reference_shim_golden.py; executed in the build
 container where /root/reference is mounted -- this test only reads the committed json).
 
-Pinned: variable names / shapes / initializer kinds / creation order of 8 model configurations
+Pinned: variable names / shapes / initializer kinds / creation order of 9 model configurations
 (including the Assemble-ResNet-50 of the north star, ResNet-D, SE, proj anti-alias, zero-gamma, R101,
-R152), which of them enter the weight-decay term (nets/run_loop_classification.py:163-176), the
+R152; the product plan is checked against the same inventories), which of them enter the weight-decay term (nets/run_loop_classification.py:163-176), the
 logits + updated BN moving statistics for seeded inputs and seeded variable values in inference and
 in training mode, the loss and its gradients (torch autograd through the reference's graph,
 inference-mode BN), mixup types 1 / 2 (utils/data_util.py:97-158), the softmax cross entropy with label
@@ -170,3 +170,18 @@ def test_flag_names_and_defaults_match_reference_code():
     # flags of the official.utils.flags core set / the run loop, not defined in hparams_config.py
     assert set(DEFAULTS) - set(ref) <= {"resnet_size", "batch_size", "train_epochs", "dtype",
                                         "loss_scale", "data_format", "num_gpus"}
+
+
+@pytest.mark.parametrize("name", sorted(mg.CONFIGS))
+def test_product_plan_inventory_matches_reference_code(name):
+    """The product's own layer plan (assembled_cnn_b200/plan.py): trainable variables in the reference's
+    creation order with the reference's (TF-layout) shapes, and the BN moving statistics."""
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    flags, d, batch, size = mg.CONFIGS[name]
+    gold = GOLD[name]
+    plan = build_plan(ModelConfig(use_resnet_d=d, **flags), 2, 64, 64, training=True)
+    assert len(plan.params) == gold["num_trainable"]
+    tr = "\n".join("%s|%s" % (n, ",".join(map(str, p.tf_shape))) for n, p in plan.params.items())
+    assert hashlib.sha256(tr.encode()).hexdigest() == gold["trainable_sha256"]
+    st = "\n".join("%s|%s" % (n, ",".join(map(str, p.tf_shape))) for n, p in plan.state.items())
+    assert hashlib.sha256(st.encode()).hexdigest() == gold["state_sha256"]
