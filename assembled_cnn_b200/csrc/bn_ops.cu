@@ -13,7 +13,11 @@ constexpr int kT = 256;
 // ------------------------------------------------------------------------------------------
 // bn_finalize
 // ------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq,
+// stats_mode 0: `stats` = [nparts][2][C] partial (sum x, sum x^2) rows written by the conv epilogue,
+//               summed here in a FIXED order (deterministic, no atomics) in double precision so
+//               that E[x^2] - E[x]^2 does not cancel in fp32;
+// stats_mode 1: `stats` = [mean | biased variance] from the two-pass bn_stats_kernel (fp32 mode).
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, int nparts, int stats_mode,
                                    float count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* moving_mean,
                                    float* moving_var, float momentum, float eps, int training,
@@ -24,8 +28,20 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   if (c >= C) return;
   float mean, var;
   if (training) {
-    mean = sum[c] / count;
-    var = fmaxf(sumsq[c] / count - mean * mean, 0.f);
+    if (stats_mode == 0) {
+      double s = 0.0, q = 0.0;
+      for (int p = 0; p < nparts; ++p) {
+        s += (double)stats[(size_t)p * 2 * C + c];
+        q += (double)stats[(size_t)p * 2 * C + C + c];
+      }
+      const double m = s / (double)count;
+      double v = q / (double)count - m * m;
+      mean = (float)m;
+      var = (float)(v > 0.0 ? v : 0.0);
+    } else {
+      mean = stats[c];
+      var = stats[C + c];
+    }
     const float unbiased = var * (count / fmaxf(count - 1.f, 1.f));
     moving_mean[c] = moving_mean[c] * momentum + mean * (1.f - momentum);
     moving_var[c] = moving_var[c] * momentum + unbiased * (1.f - momentum);
@@ -41,18 +57,67 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   rstd_out[c] = rstd;
 }
 
+// Two-pass batch statistics of an [M][C] tensor (fp32 parity mode): one CTA per 8-channel group,
+// fixed-order tree reductions -> bit-reproducible; out = [mean | biased variance].
+template <class T>
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t M, int C) {
+  pdl_entry();
+  __shared__ float red[256][9];
+  __shared__ float mean_s[8];
+  const int c0 = blockIdx.x * 8;
+  float acc[8];
+  for (int pass = 0; pass < 2; ++pass) {
+    float mu[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] = 0.f;
+      mu[i] = pass ? mean_s[i] : 0.f;
+    }
+    for (int64_t r = threadIdx.x; r < M; r += 256) {
+      float v[8];
+      load8(x + r * C + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[i] - mu[i];
+        acc[i] += pass ? d * d : d;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[threadIdx.x][i] += red[threadIdx.x + s][i];
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < 8) {
+      const float v = red[0][threadIdx.x] / (float)M;
+      if (pass == 0) {
+        mean_s[threadIdx.x] = v;
+        out[c0 + threadIdx.x] = v;
+      } else {
+        out[C + c0 + threadIdx.x] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // bn_act : out = relu?( (a*sa + ha) [*gate] + R )
 // ------------------------------------------------------------------------------------------
 // U vectors per thread per trip: the loads of a trip are issued back to back, so U (x2 with a
 // second operand) x 16 B x resident threads is what is in flight per SM; ~64 KiB is needed to
 // cover the HBM latency at full bandwidth.
-template <int U, bool HAS_B>
+template <class T, int U, bool HAS_B>
 __global__ void __launch_bounds__(kT, 2)
-bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
-              const float* __restrict__ ha, const bf16* __restrict__ b,
+bn_act_kernel(const T* __restrict__ a, const float* __restrict__ sa,
+              const float* __restrict__ ha, const T* __restrict__ b,
               const float* __restrict__ sb, const float* __restrict__ hb, int b_mode,
-              const float* __restrict__ gate, int relu, bf16* __restrict__ out, int H, int W, int C,
+              const float* __restrict__ gate, int relu, T* __restrict__ out, int H, int W, int C,
               int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
@@ -71,14 +136,14 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
   // U vectors per trip, loads batched ahead of the math (index clamped, store predicated)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t ib = i0; ib < nvec; ib += U * stride) {
-    uint4 av[U], bv[HAS_B ? U : 1];
+    V8<T> av[U], bv[HAS_B ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       int64_t i = ib + u * stride;
       i = i < nvec ? i : nvec - 1;
-      av[u] = __ldg(reinterpret_cast<const uint4*>(a + i * 8));
+      av[u].ld(a + i * 8);
       if (HAS_B && (b_mode == 1 || b_mode == 2)) {
-        bv[u] = __ldg(reinterpret_cast<const uint4*>(b + i * 8));
+        bv[u].ld(b + i * 8);
       } else if (HAS_B && b_mode == 3) {
         const int64_t pix = i / CG;
         const int w = (int)(pix % W);
@@ -86,7 +151,7 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
         const int hh = (int)(t % H);
         const int64_t bimg = t / H;
         const int64_t src = ((bimg * (H >> 1) + (hh >> 1)) * (W >> 1) + (w >> 1)) * C + c0;
-        bv[u] = __ldg(reinterpret_cast<const uint4*>(b + src));
+        bv[u].ld(b + src);
       }
     }
 #pragma unroll
@@ -94,7 +159,7 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
       const int64_t i = ib + u * stride;
       if (i >= nvec) break;
       float v[8];
-      unpack8(av[u], v);
+      av[u].unpack(v);
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], s[k], h[k]);
       if (gate) {
@@ -106,12 +171,12 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
       }
       if (HAS_B && b_mode == 1) {
         float r[8];
-        unpack8(bv[u], r);
+        bv[u].unpack(r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] += fmaf(r[k], s2[k], h2[k]);
       } else if (HAS_B && b_mode >= 2) {
         float r[8];
-        unpack8(bv[u], r);
+        bv[u].unpack(r);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] += r[k];
       }
@@ -128,10 +193,12 @@ bn_act_kernel(const bf16* __restrict__ a, const float* __restrict__ sa,
 // Column (per-channel) reductions over [M][C]
 // ------------------------------------------------------------------------------------------
 // Every thread owns one 8-channel group `cg` and walks rows; NACC accumulator vectors per thread.
-// dest(a, i) gives the index into `sums` of accumulator a, lane-channel i.
+// dest(a, i) gives the index into the partial row of accumulator a, lane-channel i.
+// The per-CTA result goes to row `part_row` of a [parts][ncols] partial buffer with PLAIN stores:
+// the finalize kernel sums the rows in a fixed order (deterministic; nothing to zero beforehand).
 template <int NACC, class Dest>
-__device__ __forceinline__ void block_reduce_atomic(float (&acc)[NACC][8], int CG, float* sums,
-                                                    Dest dest) {
+__device__ __forceinline__ void block_reduce_store(float (&acc)[NACC][8], int CG, float* part_row,
+                                                   Dest dest) {
   __shared__ float red[kT][NACC * 8 + 1];
   const int tid = threadIdx.x;
 #pragma unroll
@@ -146,12 +213,13 @@ __device__ __forceinline__ void block_reduce_atomic(float (&acc)[NACC][8], int C
     const int k = item % (NACC * 8);
     float s = 0.f;
     for (int r = 0; r < RPB; ++r) s += red[r * CG + cg][k];
-    atomicAdd(sums + dest(k >> 3, cg * 8 + (k & 7)), s);
+    part_row[dest(k >> 3, cg * 8 + (k & 7))] = s;
   }
 }
 
+template <class T>
 __global__ void __launch_bounds__(kT, 2)
-bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
+bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ y,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ gate, const float* __restrict__ addbc,
                      float* sums, int64_t M, int HW, int C) {
@@ -171,21 +239,21 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
   // that all 8 of them are issued back to back: 8 x 16 B in flight per thread.
   const int64_t step = (int64_t)gridDim.x * RPB;
   for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 4 * step) {
-    uint4 gq[4], yq[4];
+    V8<T> gq[4], yq[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       int64_t r = r0 + u * step;
       r = r < M ? r : M - 1;
-      gq[u] = __ldg(reinterpret_cast<const uint4*>(g + r * C + c0));
-      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + r * C + c0));
+      gq[u].ld(g + r * C + c0);
+      yq[u].ld(y + r * C + c0);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t r = r0 + u * step;
       const float valid = r < M ? 1.f : 0.f;
       float gv[8], yv[8];
-      unpack8(gq[u], gv);
-      unpack8(yq[u], yv);
+      gq[u].unpack(gv);
+      yq[u].unpack(yv);
       if (gate || addbc) {
         const int64_t bimg = (r < M ? r : M - 1) / HW;
         if (gate) {
@@ -209,10 +277,11 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
       }
     }
   }
-  block_reduce_atomic<2>(acc, CG, sums, [C](int a, int c) { return a * C + c; });
+  block_reduce_store<2>(acc, CG, sums + (size_t)blockIdx.x * 2 * C,
+                        [C](int a, int c) { return a * C + c; });
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums,
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int nparts,
                                        const float* __restrict__ gamma,
                                        const float* __restrict__ mean,
                                        const float* __restrict__ rstd, float count, float* coef,
@@ -220,7 +289,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums,
   pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float s1 = sums[c], s2 = sums[C + c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int p = 0; p < nparts; ++p) {            // fixed order: deterministic
+    s1 += sums[(size_t)p * 2 * C + c];
+    s2 += sums[(size_t)p * 2 * C + C + c];
+  }
   const float k1 = gamma[c] * rstd[c];
   const float k2 = -k1 * rstd[c] * s2 / count;
   const float k3 = -k1 * s1 / count - k2 * mean[c];
@@ -231,10 +304,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums,
   dbeta[c] = s1;
 }
 
+template <class T>
 __global__ void __launch_bounds__(kT)
-bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
+bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ y,
                     const float* __restrict__ coef, const float* __restrict__ gate,
-                    const float* __restrict__ addbc, bf16* __restrict__ dy, int HW, int C,
+                    const float* __restrict__ addbc, T* __restrict__ dy, int HW, int C,
                     int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
@@ -247,21 +321,21 @@ bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
   loadf8(coef + 2 * C + c0, k3);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t ib = i0; ib < nvec; ib += 4 * stride) {
-    uint4 gq[4], yq[4];
+    V8<T> gq[4], yq[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {          // batched loads (index clamped)
       int64_t i = ib + u * stride;
       i = i < nvec ? i : nvec - 1;
-      gq[u] = __ldg(reinterpret_cast<const uint4*>(g + i * 8));
-      yq[u] = __ldg(reinterpret_cast<const uint4*>(y + i * 8));
+      gq[u].ld(g + i * 8);
+      yq[u].ld(y + i * 8);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t i = ib + u * stride;
       if (i >= nvec) break;
       float gv[8], yv[8];
-      unpack8(gq[u], gv);
-      unpack8(yq[u], yv);
+      gq[u].unpack(gv);
+      yq[u].unpack(yv);
       if (gate || addbc) {
         const int64_t bimg = (i / CG) / HW;
         if (gate) {
@@ -293,9 +367,9 @@ bn_bwd_apply_kernel(const bf16* __restrict__ g, const bf16* __restrict__ y,
 // MODE 3: se_bwd_gate g * (y*s+h)                                                    * 1
 // MODE 4: gap         x                                 (bf16 output)                * 1/HW
 // ------------------------------------------------------------------------------------------
-template <int MODE>
+template <class T, int MODE>
 __global__ void __launch_bounds__(kT)
-image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
+image_reduce_kernel(const T* __restrict__ p0, const T* __restrict__ p1,
                     const float* __restrict__ scale, const float* __restrict__ shift, void* out,
                     int HW, int f) {
   pdl_entry();
@@ -325,24 +399,24 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
   // zeroed), since only ~1.7 CTAs of 256 threads are resident per SM (grid = images)
   constexpr int U = (MODE == 1 || MODE == 3) ? 4 : 1;   // measured: batching only pays with 3 loads/row
   for (int rb = rsub; rb < HW; rb += U * RPB) {
-    uint4 qa[U], qb[U], qc[U];
+    V8<T> qa[U], qb[U], qc[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       int r = rb + u * RPB;
       r = r < HW ? r : HW - 1;
       const int64_t row = (int64_t)b * HW + r;
-      qa[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + c0));
-      if (MODE <= 1) qb[u] = __ldg(reinterpret_cast<const uint4*>(p0 + row * ldy + f + c0));
-      if (MODE == 1 || MODE == 3) qc[u] = __ldg(reinterpret_cast<const uint4*>(p1 + row * f + c0));
+      qa[u].ld(p0 + row * ldy + c0);
+      if (MODE <= 1) qb[u].ld(p0 + row * ldy + f + c0);
+      if (MODE == 1 || MODE == 3) qc[u].ld(p1 + row * f + c0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const float valid = (rb + u * RPB) < HW ? 1.f : 0.f;
       if (MODE == 0 || MODE == 1) {
         float y0[8], y1[8], dv[8];
-        unpack8(qa[u], y0);
-        unpack8(qb[u], y1);
-        if (MODE == 1) unpack8(qc[u], dv);
+        qa[u].unpack(y0);
+        qb[u].unpack(y1);
+        if (MODE == 1) qc[u].unpack(dv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
@@ -351,8 +425,8 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
         }
       } else if (MODE == 2 || MODE == 3) {
         float yv[8], gv[8];
-        unpack8(qa[u], yv);
-        if (MODE == 3) unpack8(qc[u], gv);
+        qa[u].unpack(yv);
+        if (MODE == 3) qc[u].unpack(gv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float t = fmaf(yv[i], s0[i], h0[i]);
@@ -360,7 +434,7 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
         }
       } else {
         float xv[8];
-        unpack8(qa[u], xv);
+        qa[u].unpack(xv);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += valid * xv[i];
       }
@@ -377,7 +451,7 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] *= norm;
     if (MODE == 4)
-      store8(reinterpret_cast<bf16*>(out) + (int64_t)b * f + c0, acc);
+      store8(reinterpret_cast<T*>(out) + (int64_t)b * f + c0, acc);
     else
       storef8(reinterpret_cast<float*>(out) + (int64_t)b * f + c0, acc);
   }
@@ -387,18 +461,26 @@ image_reduce_kernel(const bf16* __restrict__ p0, const bf16* __restrict__ p1,
 // SK elementwise
 // ------------------------------------------------------------------------------------------
 constexpr int kSkStages = 3;
-constexpr int kSkYBytes = 16 * 1024, kSkDvBytes = 8 * 1024;
-constexpr int kSkStageBytes = kSkYBytes + kSkDvBytes;
-constexpr int kSkSmemBytes = kSkStages * kSkStageBytes + 128;
+// stage = the rows of y (2f wide) and of dv (f wide) of one trip; sized for bf16 (16 + 8 KiB) and
+// doubled for fp32 storage (the parity mode runs one CTA per SM there)
+template <class T>
+struct SkCfg {
+  static constexpr int kYBytes = 8 * 1024 * (int)sizeof(T);
+  static constexpr int kDvBytes = 4 * 1024 * (int)sizeof(T);
+  static constexpr int kStageBytes = kYBytes + kDvBytes;
+  static constexpr int kSmemBytes = kSkStages * kStageBytes + 128;
+};
 
 // v = att * relu(bn(y0)) + (1 - att) * relu(bn(y1)).  grid = (row slabs, images): the image and the
 // channel group of a thread are fixed, so the BN coefficients and the attention weights live in
 // registers; the rows of y are streamed through shared memory (stream_pipe.cuh), 2 rows per thread
 // per trip = 16 KiB of y.
+template <class T>
 __global__ void __launch_bounds__(kT, 2)
-sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
+sk_combine_kernel(const T* __restrict__ y, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ att,
-                  bf16* __restrict__ v, int HW, int f) {
+                  T* __restrict__ v, int HW, int f) {
+  constexpr int kSkStageBytes = SkCfg<T>::kStageBytes;
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
@@ -420,8 +502,8 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
   auto issue = [&](int t, int stage, uint32_t bar) {
     const int r0 = r_begin + t * RT;
     const int rows = (r_end - r0 < RT) ? r_end - r0 : RT;
-    mbar_expect_tx_a(bar, rows * 2 * f * 2);
-    bulk_load(sbase + stage * kSkStageBytes, y + (b * HW + r0) * 2 * f, rows * 2 * f * 2, bar);
+    mbar_expect_tx_a(bar, rows * 2 * f * (int)sizeof(T));
+    bulk_load(sbase + stage * kSkStageBytes, y + (b * HW + r0) * 2 * f, rows * 2 * f * (int)sizeof(T), bar);
   };
   pipe.prologue(trips, issue);
   float s0[8], h0[8], s1[8], h1[8], a[8];
@@ -440,8 +522,8 @@ sk_combine_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
       const int rl = rsub + u * RPB;
       if (rl < rows) {
         float y0[8], y1[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + c0) * 2), y0);
-        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + f + c0) * 2), y1);
+        lds8<T>(sy, rl * 2 * f + c0, y0);
+        lds8<T>(sy, rl * 2 * f + f + c0, y1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float u0 = fmaxf(fmaf(y0[k], s0[k], h0[k]), 0.f);
@@ -485,13 +567,15 @@ __device__ __forceinline__ SkSlab sk_slab(int HW, int f) {
   return q;
 }
 
+template <class T>
 __global__ void __launch_bounds__(kT, 2)
-sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
+sk_bn_bwd_reduce_kernel(const T* __restrict__ dv, const T* __restrict__ y,
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ att, const float* __restrict__ ds, float* sums,
                         int HW, int f) {
   pdl_entry();
+  constexpr int kSkStageBytes = SkCfg<T>::kStageBytes, kSkYBytes = SkCfg<T>::kYBytes;
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   const SkSlab q = sk_slab(HW, f);
@@ -503,9 +587,9 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
     const int r0 = q.r_begin + t * q.RT;
     const int rows = (q.r_end - r0 < q.RT) ? q.r_end - r0 : q.RT;
     const int64_t row = q.b * HW + r0;
-    mbar_expect_tx_a(bar, rows * (q.C2 + f) * 2);
-    bulk_load(sbase + stage * kSkStageBytes, y + row * q.C2, rows * q.C2 * 2, bar);
-    bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * 2, bar);
+    mbar_expect_tx_a(bar, rows * (q.C2 + f) * (int)sizeof(T));
+    bulk_load(sbase + stage * kSkStageBytes, y + row * q.C2, rows * q.C2 * (int)sizeof(T), bar);
+    bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * (int)sizeof(T), bar);
   };
   pipe.prologue(q.trips, issue);
   float sc[8], sh[8], mu[8], rs[8], ah[8], sg[8];
@@ -534,8 +618,8 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
       const int rl = q.rsub + u * q.RPB;
       if (rl < rows) {
         float yv[8], d[8];
-        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * q.C2 + q.c0) * 2), yv);
-        unpack8(*reinterpret_cast<const uint4*>(sd + (rl * f + q.cb) * 2), d);
+        lds8<T>(sy, rl * q.C2 + q.c0, yv);
+        lds8<T>(sd, rl * f + q.cb, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float tt = fmaf(yv[i], sc[i], sh[i]);
@@ -548,15 +632,18 @@ sk_bn_bwd_reduce_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
     pipe.release();
   }
   const int C2 = q.C2;
-  block_reduce_atomic<2>(acc, q.CG2, sums, [C2](int a, int c) { return a * C2 + c; });
+  block_reduce_store<2>(acc, q.CG2, sums + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C2,
+                        [C2](int a, int c) { return a * C2 + c; });
 }
 
+template <class T>
 __global__ void __launch_bounds__(kT, 2)
-sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
+sk_bn_bwd_apply_kernel(const T* __restrict__ dv, const T* __restrict__ y,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        const float* __restrict__ att, const float* __restrict__ ds,
-                       const float* __restrict__ coef, bf16* __restrict__ dy, int HW, int f) {
+                       const float* __restrict__ coef, T* __restrict__ dy, int HW, int f) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
+  constexpr int kSkStageBytes = SkCfg<T>::kStageBytes, kSkYBytes = SkCfg<T>::kYBytes;
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   const SkSlab q = sk_slab(HW, f);
@@ -568,9 +655,9 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
     const int r0 = q.r_begin + t * q.RT;
     const int rows = (q.r_end - r0 < q.RT) ? q.r_end - r0 : q.RT;
     const int64_t row = q.b * HW + r0;
-    mbar_expect_tx_a(bar, rows * (q.C2 + f) * 2);
-    bulk_load(sbase + stage * kSkStageBytes, y + row * q.C2, rows * q.C2 * 2, bar);
-    bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * 2, bar);
+    mbar_expect_tx_a(bar, rows * (q.C2 + f) * (int)sizeof(T));
+    bulk_load(sbase + stage * kSkStageBytes, y + row * q.C2, rows * q.C2 * (int)sizeof(T), bar);
+    bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * (int)sizeof(T), bar);
   };
   pipe.prologue(q.trips, issue);
   // o = k1 * g + k2 * y + k3 with g = [sc*y+sh > 0] (ah*dv + sg): folded into
@@ -604,8 +691,8 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
       const int rl = q.rsub + u * q.RPB;
       if (rl < rows) {
         float yv[8], d[8], o[8];
-        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * q.C2 + q.c0) * 2), yv);
-        unpack8(*reinterpret_cast<const uint4*>(sd + (rl * f + q.cb) * 2), d);
+        lds8<T>(sy, rl * q.C2 + q.c0, yv);
+        lds8<T>(sd, rl * f + q.cb, d);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float tt = fmaf(yv[k], sc[k], sh[k]);
@@ -623,12 +710,13 @@ sk_bn_bwd_apply_kernel(const bf16* __restrict__ dv, const bf16* __restrict__ y,
 // memory.  MODE 0 (sk_gap): s[b, c] = mean_hw relu(bn(y0)) + relu(bn(y1)); MODE 1 (sk_bwd_gate):
 // dA[b, c] = sum_hw dv * (u0 - u1).  One thread = 8 output channels (both halves of y); a trip is
 // 2 rows per thread = 16 KiB of y (+ 8 KiB of dv), the same stage layout as the kernels above.
-template <int MODE>
+template <class T, int MODE>
 __global__ void __launch_bounds__(kT, 2)
-sk_image_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dv,
+sk_image_reduce_kernel(const T* __restrict__ y, const T* __restrict__ dv,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        float* __restrict__ out, int HW, int f) {
   pdl_entry();
+  constexpr int kSkStageBytes = SkCfg<T>::kStageBytes, kSkYBytes = SkCfg<T>::kYBytes;
   extern __shared__ uint8_t sk_smem_raw[];
   __shared__ uint64_t bars[kSkStages];
   __shared__ float red[kT][9];
@@ -648,10 +736,10 @@ sk_image_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dv,
     const int r0 = t * RT;
     const int rows = (HW - r0 < RT) ? HW - r0 : RT;
     const int64_t row = b * HW + r0;
-    mbar_expect_tx_a(bar, rows * (MODE == 1 ? 3 : 2) * f * 2);
-    bulk_load(sbase + stage * kSkStageBytes, y + row * 2 * f, rows * 2 * f * 2, bar);
+    mbar_expect_tx_a(bar, rows * (MODE == 1 ? 3 : 2) * f * (int)sizeof(T));
+    bulk_load(sbase + stage * kSkStageBytes, y + row * 2 * f, rows * 2 * f * (int)sizeof(T), bar);
     if (MODE == 1)
-      bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * 2, bar);
+      bulk_load(sbase + stage * kSkStageBytes + kSkYBytes, dv + row * f, rows * f * (int)sizeof(T), bar);
   };
   pipe.prologue(trips, issue);
   float s0[8], h0[8], s1[8], h1[8], acc[8];
@@ -671,9 +759,9 @@ sk_image_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dv,
       const int rl = rsub + u * RPB;
       if (rl < rows) {
         float y0[8], y1[8], d[8];
-        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + c0) * 2), y0);
-        unpack8(*reinterpret_cast<const uint4*>(sy + (rl * 2 * f + f + c0) * 2), y1);
-        if (MODE == 1) unpack8(*reinterpret_cast<const uint4*>(sd + (rl * f + c0) * 2), d);
+        lds8<T>(sy, rl * 2 * f + c0, y0);
+        lds8<T>(sy, rl * 2 * f + f + c0, y1);
+        if (MODE == 1) lds8<T>(sd, rl * f + c0, d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float u0 = fmaxf(fmaf(y0[i], s0[i], h0[i]), 0.f);
@@ -698,17 +786,18 @@ sk_image_reduce_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dv,
   }
 }
 
-template <int MODE>
-static void launch_sk_image_reduce(const bf16* y, const bf16* dv, const float* scale,
+template <class T, int MODE>
+static void launch_sk_image_reduce(const void* y, const void* dv, const float* scale,
                                    const float* shift, float* out, int B, int HW, int f,
                                    cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(sk_image_reduce_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kSkSmemBytes);
+    cudaFuncSetAttribute(sk_image_reduce_kernel<T, MODE>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<T>::kSmemBytes);
     attr = true;
   }
-  launch_k(sk_image_reduce_kernel<MODE>, dim3(B), dim3(kT), kSkSmemBytes, st, y, dv, scale, shift, out, HW, f);
+  launch_k(sk_image_reduce_kernel<T, MODE>, dim3(B), dim3(kT), SkCfg<T>::kSmemBytes, st,
+           (const T*)y, (const T*)dv, scale, shift, out, HW, f);
 }
 
 // Row slabs per image for the image-aligned SK kernels: ~`ctas_per_sm` CTAs per SM overall, at
@@ -725,165 +814,238 @@ static bool cg_ok(int C) {
   return C % 8 == 0 && cg >= 1 && cg <= kT && (kT % cg) == 0;
 }
 
+static int bn_bwd_reduce_grid(int64_t M, int C) {
+  const int rpb = kT / (C >> 3);
+  return grid_for(ceil_div64(M, 4 * rpb), 1, 148 * 2);
+}
+
+template <class T>
+static void set_sk_attr(const void* kern) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<T>::kSmemBytes);
+}
+
 }  // namespace acnn
 
 using namespace acnn;
 
+#define ACNN_DTYPE_OK(dt) ((dt) == ACNN_BF16 || (dt) == ACNN_F32)
+#define ACNN_BY_DTYPE(dt, ...)      \
+  do {                              \
+    if ((dt) == ACNN_F32) {         \
+      using T = float;              \
+      __VA_ARGS__;                  \
+    } else {                        \
+      using T = bf16;               \
+      __VA_ARGS__;                  \
+    }                               \
+  } while (0)
+
+template <class T>
+static void launch_bn_act(cudaStream_t st, const void* a, const float* scale_a, const float* shift_a,
+                          const void* b, const float* scale_b, const float* shift_b, int b_mode,
+                          const float* gate, int relu, void* out, int H, int W, int C,
+                          int64_t nvec) {
+  if (b_mode == 0) {
+    launch_k(bn_act_kernel<T, 8, false>, dim3(grid_for(nvec)), dim3(kT), 0, st, (const T*)a, scale_a,
+             shift_a, (const T*)b, scale_b, shift_b, b_mode, gate, relu, (T*)out, H, W, C, nvec);
+  } else {
+    launch_k(bn_act_kernel<T, 4, true>, dim3(grid_for(nvec)), dim3(kT), 0, st, (const T*)a, scale_a,
+             shift_a, (const T*)b, scale_b, shift_b, b_mode, gate, relu, (T*)out, H, W, C, nvec);
+  }
+}
+
 extern "C" {
 
-int acnn_bn_finalize(const float* sum, const float* sumsq, int64_t count, const float* gamma,
-                     const float* beta, float* moving_mean, float* moving_var, float momentum,
-                     float eps, int training, float* scale, float* shift, float* mean, float* rstd,
-                     int C, void* stream) {
+int acnn_bn_stats(const void* x, float* mean_var, int64_t M, int C, int dtype, void* stream) {
+  ACNN_REQUIRE(x && mean_var && M > 0 && C % 8 == 0 && ACNN_DTYPE_OK(dtype),
+               "bn_stats: bad arguments");
+  ACNN_BY_DTYPE(dtype, launch_k(bn_stats_kernel<T>, dim3(C / 8), dim3(256), 0,
+                                (cudaStream_t)stream, (const T*)x, mean_var, M, C));
+  count_launch();
+  return check_launch("bn_stats");
+}
+
+int acnn_bn_finalize(const float* stats, int nparts, int stats_mode, int64_t count,
+                     const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                     float momentum, float eps, int training, float* scale, float* shift,
+                     float* mean, float* rstd, int C, void* stream) {
   ACNN_REQUIRE(C > 0 && gamma && beta && moving_mean && moving_var && scale && shift && mean &&
                    rstd, "bn_finalize: null argument");
-  ACNN_REQUIRE(!training || (sum && sumsq && count > 0), "bn_finalize: training needs sums");
-  launch_k(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sum, sumsq, (float)count, gamma, beta, moving_mean, moving_var, momentum, eps, training,
-      scale, shift, mean, rstd, C);
+  ACNN_REQUIRE(!training || (stats && count > 0 && (stats_mode == 1 || nparts >= 1)),
+               "bn_finalize: training needs statistics");
+  launch_k(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, stats,
+           nparts, stats_mode, (float)count, gamma, beta, moving_mean, moving_var, momentum, eps,
+           training, scale, shift, mean, rstd, C);
   count_launch();
   return check_launch("bn_finalize");
 }
 
 int acnn_bn_act(const void* a, const float* scale_a, const float* shift_a, const void* b,
                 const float* scale_b, const float* shift_b, int b_mode, const float* gate, int relu,
-                void* out, int B, int H, int W, int C, void* stream) {
-  ACNN_REQUIRE(a && scale_a && shift_a && out && C % 8 == 0, "bn_act: bad arguments (C=%d)", C);
+                void* out, int B, int H, int W, int C, int dtype, void* stream) {
+  ACNN_REQUIRE(a && scale_a && shift_a && out && C % 8 == 0 && ACNN_DTYPE_OK(dtype),
+               "bn_act: bad arguments (C=%d)", C);
   ACNN_REQUIRE(b_mode >= 0 && b_mode <= 3 && (b_mode == 0 || b), "bn_act: bad b_mode %d", b_mode);
   ACNN_REQUIRE(b_mode != 1 || (scale_b && shift_b), "bn_act: b_mode 1 needs scale_b/shift_b");
   ACNN_REQUIRE(b_mode != 3 || (H % 2 == 0 && W % 2 == 0), "bn_act: upsample needs even H, W");
+  // the channel group of a thread must be loop-invariant: C/8 divides the grid stride
+  ACNN_REQUIRE(cg_ok(C), "bn_act: C=%d (C/8 must divide 256)", C);
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  if (b_mode == 0) {
-    launch_k(bn_act_kernel<8, false>, dim3(grid_for(nvec)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
-        (bf16*)out, H, W, C, nvec);
-  } else {
-    launch_k(bn_act_kernel<4, true>, dim3(grid_for(nvec)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)a, scale_a, shift_a, (const bf16*)b, scale_b, shift_b, b_mode, gate, relu,
-        (bf16*)out, H, W, C, nvec);
-  }
+  ACNN_BY_DTYPE(dtype, launch_bn_act<T>((cudaStream_t)stream, a, scale_a, shift_a, b, scale_b,
+                                        shift_b, b_mode, gate, relu, out, H, W, C, nvec));
   count_launch();
   return check_launch("bn_act");
 }
 
+int acnn_bn_bwd_reduce_parts(int B, int HW, int C) {
+  if (!cg_ok(C) || B <= 0 || HW <= 0) return 0;
+  return bn_bwd_reduce_grid((int64_t)B * HW, C);
+}
+
 int acnn_bn_bwd_reduce(const void* g, const void* y, const float* mean, const float* rstd,
-                       const float* gate, const float* addbc, float* sums, int B, int HW, int C,
-                       void* stream) {
-  ACNN_REQUIRE(g && y && mean && rstd && sums && cg_ok(C), "bn_bwd_reduce: bad arguments C=%d", C);
+                       const float* gate, const float* addbc, float* parts, int B, int HW, int C,
+                       int dtype, void* stream) {
+  ACNN_REQUIRE(g && y && mean && rstd && parts && cg_ok(C) && ACNN_DTYPE_OK(dtype),
+               "bn_bwd_reduce: bad arguments C=%d", C);
   const int64_t M = (int64_t)B * HW;
-  const int rpb = kT / (C >> 3);
-  launch_k(bn_bwd_reduce_kernel, dim3(grid_for(ceil_div64(M, 4 * rpb), 1, 148 * 2)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)g, (const bf16*)y, mean, rstd, gate, addbc, sums, M, HW, C);
+  ACNN_BY_DTYPE(dtype, launch_k(bn_bwd_reduce_kernel<T>, dim3(bn_bwd_reduce_grid(M, C)), dim3(kT), 0,
+                                (cudaStream_t)stream, (const T*)g, (const T*)y, mean, rstd, gate,
+                                addbc, parts, M, HW, C));
   count_launch();
   return check_launch("bn_bwd_reduce");
 }
 
-int acnn_bn_bwd_finalize(const float* sums, const float* gamma, const float* mean,
+int acnn_bn_bwd_finalize(const float* parts, int nparts, const float* gamma, const float* mean,
                          const float* rstd, int64_t count, float* coef, float* dgamma, float* dbeta,
                          int C, void* stream) {
-  ACNN_REQUIRE(sums && gamma && mean && rstd && coef && dgamma && dbeta && count > 0,
-               "bn_bwd_finalize: null argument");
-  launch_k(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, sums, gamma, mean, rstd, (float)count, coef, dgamma, dbeta, C);
+  ACNN_REQUIRE(parts && nparts >= 1 && gamma && mean && rstd && coef && dgamma && dbeta && count > 0,
+               "bn_bwd_finalize: bad argument");
+  launch_k(bn_bwd_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, (cudaStream_t)stream, parts,
+           nparts, gamma, mean, rstd, (float)count, coef, dgamma, dbeta, C);
   count_launch();
   return check_launch("bn_bwd_finalize");
 }
 
 int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const float* gate,
-                      const float* addbc, void* dy, int B, int HW, int C, void* stream) {
-  ACNN_REQUIRE(g && y && coef && dy && C % 8 == 0, "bn_bwd_apply: bad arguments");
+                      const float* addbc, void* dy, int B, int HW, int C, int dtype, void* stream) {
+  ACNN_REQUIRE(g && y && coef && dy && cg_ok(C) && ACNN_DTYPE_OK(dtype),
+               "bn_bwd_apply: bad arguments");
   const int64_t nvec = (int64_t)B * HW * C / 8;
-  launch_k(bn_bwd_apply_kernel, dim3(grid_for(nvec)), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)g, (const bf16*)y, coef, gate, addbc, (bf16*)dy, HW, C, nvec);
+  ACNN_BY_DTYPE(dtype, launch_k(bn_bwd_apply_kernel<T>, dim3(grid_for(nvec)), dim3(kT), 0,
+                                (cudaStream_t)stream, (const T*)g, (const T*)y, coef, gate, addbc,
+                                (T*)dy, HW, C, nvec));
   count_launch();
   return check_launch("bn_bwd_apply");
 }
 
 int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s, int B, int HW,
-                int f, void* stream) {
-  ACNN_REQUIRE(y && scale && shift && s && cg_ok(f), "sk_gap: bad arguments f=%d", f);
-  launch_sk_image_reduce<0>((const bf16*)y, nullptr, scale, shift, s, B, HW, f,
-                            (cudaStream_t)stream);
+                int f, int dtype, void* stream) {
+  ACNN_REQUIRE(y && scale && shift && s && cg_ok(f) && ACNN_DTYPE_OK(dtype),
+               "sk_gap: bad arguments f=%d", f);
+  ACNN_BY_DTYPE(dtype, (launch_sk_image_reduce<T, 0>(y, nullptr, scale, shift, s, B, HW, f,
+                                                     (cudaStream_t)stream)));
   count_launch();
   return check_launch("sk_gap");
 }
 
 int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const float* shift,
-                     float* dA, int B, int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && dA && cg_ok(f), "sk_bwd_gate: bad arguments");
-  launch_sk_image_reduce<1>((const bf16*)y, (const bf16*)dv, scale, shift, dA, B, HW, f,
-                            (cudaStream_t)stream);
+                     float* dA, int B, int HW, int f, int dtype, void* stream) {
+  ACNN_REQUIRE(dv && y && scale && shift && dA && cg_ok(f) && ACNN_DTYPE_OK(dtype),
+               "sk_bwd_gate: bad arguments");
+  ACNN_BY_DTYPE(dtype, (launch_sk_image_reduce<T, 1>(y, dv, scale, shift, dA, B, HW, f,
+                                                     (cudaStream_t)stream)));
   count_launch();
   return check_launch("sk_bwd_gate");
 }
 
 int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q, int B, int HW,
-                int C, void* stream) {
-  ACNN_REQUIRE(y && scale && shift && q && cg_ok(C), "se_gap: bad arguments");
-  launch_k(image_reduce_kernel<2>, dim3(B), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)y, nullptr, scale, shift,
-                                                             q, HW, C);
+                int C, int dtype, void* stream) {
+  ACNN_REQUIRE(y && scale && shift && q && cg_ok(C) && ACNN_DTYPE_OK(dtype), "se_gap: bad arguments");
+  ACNN_BY_DTYPE(dtype, (launch_k(image_reduce_kernel<T, 2>, dim3(B), dim3(kT), 0,
+                                 (cudaStream_t)stream, (const T*)y, (const T*)nullptr, scale, shift,
+                                 (void*)q, HW, C)));
   count_launch();
   return check_launch("se_gap");
 }
 
 int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const float* shift,
-                     float* de, int B, int HW, int C, void* stream) {
-  ACNN_REQUIRE(g && y && scale && shift && de && cg_ok(C), "se_bwd_gate: bad arguments");
-  launch_k(image_reduce_kernel<3>, dim3(B), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)y, (const bf16*)g, scale,
-                                                             shift, de, HW, C);
+                     float* de, int B, int HW, int C, int dtype, void* stream) {
+  ACNN_REQUIRE(g && y && scale && shift && de && cg_ok(C) && ACNN_DTYPE_OK(dtype),
+               "se_bwd_gate: bad arguments");
+  ACNN_BY_DTYPE(dtype, (launch_k(image_reduce_kernel<T, 3>, dim3(B), dim3(kT), 0,
+                                 (cudaStream_t)stream, (const T*)y, (const T*)g, scale, shift,
+                                 (void*)de, HW, C)));
   count_launch();
   return check_launch("se_bwd_gate");
 }
 
-int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, void* stream) {
-  ACNN_REQUIRE(x && pooled && cg_ok(C), "gap_fwd: bad arguments C=%d", C);
-  launch_k(image_reduce_kernel<4>, dim3(B), dim3(kT), 0, (cudaStream_t)stream, (const bf16*)x, nullptr, nullptr,
-                                                             nullptr, pooled, HW, C);
+int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, int dtype, void* stream) {
+  ACNN_REQUIRE(x && pooled && cg_ok(C) && ACNN_DTYPE_OK(dtype), "gap_fwd: bad arguments C=%d", C);
+  ACNN_BY_DTYPE(dtype, (launch_k(image_reduce_kernel<T, 4>, dim3(B), dim3(kT), 0,
+                                 (cudaStream_t)stream, (const T*)x, (const T*)nullptr,
+                                 (const float*)nullptr, (const float*)nullptr, pooled, HW, C)));
   count_launch();
   return check_launch("gap_fwd");
 }
 
 int acnn_sk_combine(const void* y, const float* scale, const float* shift, const float* att,
-                    void* v, int B, int HW, int f, void* stream) {
-  ACNN_REQUIRE(y && scale && shift && att && v && cg_ok(f) && B <= 65535,
+                    void* v, int B, int HW, int f, int dtype, void* stream) {
+  ACNN_REQUIRE(y && scale && shift && att && v && cg_ok(f) && B <= 65535 && ACNN_DTYPE_OK(dtype),
                "sk_combine: bad arguments");
   dim3 grid(row_slabs(B, HW, kT / (f >> 3)), B);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(sk_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kSkSmemBytes);
-    attr = true;
-  }
-  launch_k(sk_combine_kernel, dim3(grid), dim3(kT), kSkSmemBytes, (cudaStream_t)stream, (const bf16*)y, scale, shift, att, (bf16*)v, HW, f);
+  ACNN_BY_DTYPE(dtype, {
+    static bool attr = false;
+    if (!attr) {
+      set_sk_attr<T>((const void*)sk_combine_kernel<T>);
+      attr = true;
+    }
+    launch_k(sk_combine_kernel<T>, grid, dim3(kT), SkCfg<T>::kSmemBytes, (cudaStream_t)stream,
+             (const T*)y, scale, shift, att, (T*)v, HW, f);
+  });
   count_launch();
   return check_launch("sk_combine");
 }
 
+int acnn_sk_bn_bwd_reduce_parts(int B, int HW, int f) {
+  if (!cg_ok(2 * f) || B <= 0 || HW <= 0) return 0;
+  return row_slabs(B, HW, kT / (f >> 2), 2) * B;
+}
+
 int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, const float* shift,
                           const float* mean, const float* rstd, const float* att, const float* ds,
-                          float* sums, int B, int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && sums && cg_ok(2 * f) &&
-                   B <= 65535, "sk_bn_bwd_reduce: bad arguments");
-  // one resident wave of long-lived CTAs: every CTA ends with one atomic per channel
+                          float* parts, int B, int HW, int f, int dtype, void* stream) {
+  ACNN_REQUIRE(dv && y && scale && shift && mean && rstd && att && ds && parts && cg_ok(2 * f) &&
+                   B <= 65535 && ACNN_DTYPE_OK(dtype), "sk_bn_bwd_reduce: bad arguments");
+  // one resident wave of long-lived CTAs; every CTA writes one partial row (2 x 2f floats)
   dim3 grid(row_slabs(B, HW, kT / (f >> 2), 2), B);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(sk_bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kSkSmemBytes);
-    attr = true;
-  }
-  launch_k(sk_bn_bwd_reduce_kernel, dim3(grid), dim3(kT), kSkSmemBytes, (cudaStream_t)stream, (const bf16*)dv, (const bf16*)y, scale, shift, mean, rstd, att, ds, sums, HW, f);
+  ACNN_BY_DTYPE(dtype, {
+    static bool attr = false;
+    if (!attr) {
+      set_sk_attr<T>((const void*)sk_bn_bwd_reduce_kernel<T>);
+      attr = true;
+    }
+    launch_k(sk_bn_bwd_reduce_kernel<T>, grid, dim3(kT), SkCfg<T>::kSmemBytes, (cudaStream_t)stream,
+             (const T*)dv, (const T*)y, scale, shift, mean, rstd, att, ds, parts, HW, f);
+  });
   count_launch();
   return check_launch("sk_bn_bwd_reduce");
 }
 
 int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, const float* shift,
                          const float* att, const float* ds, const float* coef, void* dy, int B,
-                         int HW, int f, void* stream) {
-  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && cg_ok(2 * f) && B <= 65535,
-               "sk_bn_bwd_apply: bad arguments");
+                         int HW, int f, int dtype, void* stream) {
+  ACNN_REQUIRE(dv && y && scale && shift && att && ds && coef && dy && cg_ok(2 * f) && B <= 65535 &&
+                   ACNN_DTYPE_OK(dtype), "sk_bn_bwd_apply: bad arguments");
   dim3 grid(row_slabs(B, HW, kT / (f >> 2)), B);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(sk_bn_bwd_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kSkSmemBytes);
-    attr = true;
-  }
-  launch_k(sk_bn_bwd_apply_kernel, dim3(grid), dim3(kT), kSkSmemBytes, (cudaStream_t)stream, (const bf16*)dv, (const bf16*)y, scale, shift, att, ds, coef, (bf16*)dy, HW, f);
+  ACNN_BY_DTYPE(dtype, {
+    static bool attr = false;
+    if (!attr) {
+      set_sk_attr<T>((const void*)sk_bn_bwd_apply_kernel<T>);
+      attr = true;
+    }
+    launch_k(sk_bn_bwd_apply_kernel<T>, grid, dim3(kT), SkCfg<T>::kSmemBytes, (cudaStream_t)stream,
+             (const T*)dv, (const T*)y, scale, shift, att, ds, coef, (T*)dy, HW, f);
+  });
   count_launch();
   return check_launch("sk_bn_bwd_apply");
 }

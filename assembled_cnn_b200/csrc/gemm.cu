@@ -138,8 +138,7 @@ struct ConvGemmParams {
   int stages;     // smem pipeline depth
   int m_tiles, n_tiles;
   void* y;
-  float* ch_sum;
-  float* ch_sumsq;
+  float* ch_part;   // [gridDim.x / n_tiles][2][Cout] per-CTA partial (sum, sum of squares) rows
   const float* bias;
   int has_add, has_mask;
   int out_f32;
@@ -156,12 +155,35 @@ constexpr int kSmemBudget = 224 * 1024;   // dynamic smem (227 KiB max per CTA, 
 // MT = 128-row M tiles per CTA tile (1 or 2).  With MT = 2 a CTA computes two output tiles that
 // share every weight stage: twice the tensor work per pipeline round-trip (the single-warp issue
 // loops, not bandwidth, bound the N <= 128 layers) and half the weight traffic per FLOP.
-template <int BN, int MT>
+// (a-plane, b-plane) of the t-th cross product of two 3-plane operands, smallest magnitude first:
+// (2,0) (1,1) (0,2) [2^-16]  (1,0) (0,1) [2^-8]  (0,0)
+__host__ __device__ constexpr int plane_term_a(int t) { return t == 0 ? 2 : ((t == 1 || t == 3) ? 1 : 0); }
+__host__ __device__ constexpr int plane_term_b(int t) { return t == 2 ? 2 : ((t == 1 || t == 4) ? 1 : 0); }
+
+// NP = operand planes: 1 = bf16 operands; 3 = fp32 operands split into three bf16 planes
+// (x = hi + mid + lo, 24 mantissa bits) whose six significant cross products are accumulated in the
+// same fp32 TMEM accumulator -- the fp32 parity mode (acnn.h ACNN_F32) on the same TMA / im2col /
+// descriptor / epilogue code as the bf16 path.
+static inline int fprop_stage_bytes(int bn, int mt, int np) {
+  return np * (mt * kBM * kStageK * 2 + bn * kStageK * 2);
+}
+static inline int fprop_stages(int bn, int mt, int np, bool has_add, bool has_mask, bool out_f32) {
+  const int half_n = bn > 128 ? 128 : bn;
+  const int tile = kBM * half_n * 2;
+  const int fixed = 1024 + (out_f32 ? 0 : tile) + (has_add ? tile : 0) + (has_mask ? tile : 0);
+  int st = (kSmemBudget - fixed) / fprop_stage_bytes(bn, mt, np);
+  if (st > kMaxStages) st = kMaxStages;
+  if (st < 2) st = 2;
+  return st;
+}
+
+template <int BN, int MT, int NP = 1>
 struct FpropCfg {
   static constexpr int kAHalfBytes = kBM * kStageK * 2;   // 16 KiB per M tile
-  static constexpr int kABytes = MT * kAHalfBytes;
-  static constexpr int kBBytes = BN * kStageK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kABytes = MT * kAHalfBytes;        // one plane
+  static constexpr int kBBytes = BN * kStageK * 2;        // one plane
+  static constexpr int kStageBytes = NP * (kABytes + kBBytes);
+  static_assert(2 * kStageBytes + 1024 <= kSmemBudget, "two pipeline stages must fit");
   // the epilogue handles the accumulator in column halves of <= 128 (one staging buffer each for
   // the output, add and mask tiles), so a 128 x 256 tile needs no more staging than 128 x 128
   static constexpr int kHalfN = BN > 128 ? 128 : BN;
@@ -172,12 +194,7 @@ struct FpropCfg {
   static_assert(2 * MT * BN <= 512, "TMEM holds 512 columns");
   // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
   static int stages_for(bool has_add, bool has_mask, bool out_f32) {
-    const int fixed = 1024 + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
-                      (has_mask ? kTileBytes : 0);
-    int st = (kSmemBudget - fixed) / kStageBytes;
-    if (st > kMaxStages) st = kMaxStages;
-    if (st < 2) st = 2;
-    return st;
+    return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32);
   }
   static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32) {
     return 1024 + stages * kStageBytes + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
@@ -189,12 +206,14 @@ struct FpropCfg {
 // runs ahead across tiles through the smem ring; the MMA issuer alternates between two TMEM
 // accumulators; the 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks)
 // drain accumulator i while the tensor core fills i^1.
-template <int BN, int CW, bool IM2COL, int MT>
+template <int BN, int CW, bool IM2COL, int MT, int NP>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd,
-                 const __grid_constant__ CUtensorMap tmMask, const ConvGemmParams p) {
-  using Cfg = FpropCfg<BN, MT>;
+                 const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmA1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmB2, const ConvGemmParams p) {
+  using Cfg = FpropCfg<BN, MT, NP>;
   constexpr int kTileM = MT * kBM;              // output pixels per CTA tile
   constexpr int kChunks = kStageK / CW;        // A chunks (one filter tap each when Cin < 64)
   constexpr int kChunkBytes = kBM * CW * 2;
@@ -235,6 +254,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (NP == 3) {
+      tma_prefetch_desc(&tmA1);
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB1);
+      tma_prefetch_desc(&tmB2);
+    }
     if (!p.out_f32) tma_prefetch_desc(&tmC);
     if (p.has_add) tma_prefetch_desc(&tmAdd);
     if (p.has_mask) tma_prefetch_desc(&tmMask);
@@ -273,8 +298,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // election loops) and every lane tracks the same loop state; one elected lane issues.
     uint32_t soff = 0, sbar = 0, phase = 0;             // stage byte offset / barrier offset
     const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
-    const uint32_t full_bytes = MT * kChunks * kChunkBytes + b_bytes;
-    const uint32_t tail_bytes = MT * tail_chunks * kChunkBytes + b_bytes;
+    const uint32_t full_bytes = NP * (MT * kChunks * kChunkBytes + b_bytes);
+    const uint32_t tail_bytes = NP * (MT * tail_chunks * kChunkBytes + b_bytes);
     const int Cin = p.Cin, fkw = p.kw;
     for (int it = 0; it < my_tiles; ++it) {
       const int m0 = (m_first + it * m_step) * kTileM;
@@ -303,20 +328,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t sa = smem_a0 + soff;
         if (leader) {
           mbar_expect_tx_a(fb, (kChunks > 1 && last) ? tail_bytes : full_bytes);
-          tma_load_2d_a(sa + Cfg::kABytes, &tmB, fb, k0, n0);
+#pragma unroll
+          for (int pl = 0; pl < NP; ++pl)
+            tma_load_2d_a(sa + NP * Cfg::kABytes + pl * Cfg::kBBytes,
+                          pl == 0 ? &tmB : (pl == 1 ? &tmB1 : &tmB2), fb, k0, n0);
         }
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
           if (j < nch) {
             if (leader) {
 #pragma unroll
-              for (int h = 0; h < MT; ++h) {
-                const uint32_t dst = sa + h * Cfg::kAHalfBytes + j * kChunkBytes;
-                if (IM2COL) {
-                  tma_load_im2col_4d_a(dst, &tmA, fb, tc, w0[h], h0[h], img[h], (uint16_t)ts,
-                                       (uint16_t)tr);
-                } else {
-                  tma_load_2d_a(dst, &tmA, fb, k0 + j * CW, m0 + h * kBM);
+              for (int pl = 0; pl < NP; ++pl) {
+                const CUtensorMap* mA = pl == 0 ? &tmA : (pl == 1 ? &tmA1 : &tmA2);
+#pragma unroll
+                for (int h = 0; h < MT; ++h) {
+                  const uint32_t dst =
+                      sa + pl * Cfg::kABytes + h * Cfg::kAHalfBytes + j * kChunkBytes;
+                  if (IM2COL) {
+                    tma_load_im2col_4d_a(dst, mA, fb, tc, w0[h], h0[h], img[h], (uint16_t)ts,
+                                         (uint16_t)tr);
+                  } else {
+                    tma_load_2d_a(dst, mA, fb, k0 + j * CW, m0 + h * kBM);
+                  }
                 }
               }
             }
@@ -341,7 +374,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
     // descriptors of stage 0 / chunk 0; everything else is an add on the 14-bit address field
     const uint64_t a_desc0 = make_smem_desc(smem_a0, 16, 8 * CW * 2, swizzle_layout_type(CW * 2));
-    const uint64_t b_desc0 = make_smem_desc(smem_a0 + Cfg::kABytes, 16, 8 * p.b_sw_bytes,
+    const uint64_t b_desc0 = make_smem_desc(smem_a0 + NP * Cfg::kABytes, 16, 8 * p.b_sw_bytes,
                                             swizzle_layout_type(p.b_sw_bytes));
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t acc = it & 1;
@@ -364,10 +397,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int h = 0; h < MT; ++h) {
 #pragma unroll
                 for (int ks = 0; ks < kKSteps; ++ks) {
-                  umma_bf16(tmem_d + h * BN,
-                            da0 + ((h * Cfg::kAHalfBytes + j * kChunkBytes + ks * 32) >> 4),
-                            db0 + (((j * kKSteps + ks) * 32) >> 4), kIdesc,
-                            (j | ks) ? 1u : static_cast<uint32_t>(kb != 0));
+                  // NP == 3: the six cross products of the (hi, mid, lo) planes that are
+                  // significant at fp32 precision, smallest first
+#pragma unroll
+                  for (int t = 0; t < (NP == 3 ? 6 : 1); ++t) {
+                    const int pa = NP == 3 ? plane_term_a(t) : 0;
+                    const int pb = NP == 3 ? plane_term_b(t) : 0;
+                    umma_bf16(tmem_d + h * BN,
+                              da0 + ((pa * Cfg::kABytes + h * Cfg::kAHalfBytes + j * kChunkBytes +
+                                      ks * 32) >> 4),
+                              db0 + ((pb * Cfg::kBBytes + (j * kKSteps + ks) * 32) >> 4), kIdesc,
+                              (j | ks | t) ? 1u : static_cast<uint32_t>(kb != 0));
+                  }
                 }
               }
             }
@@ -387,7 +428,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int egrp = (warp - 2) >> 2;                  // 0 / 1: even / odd 32-column chunks
     const int r = quarter * 32 + lane;                 // row inside the tile == TMEM lane
     const bool leader = (warp == 2 && lane == 0);
-    const bool stats = p.ch_sum != nullptr;
+    const bool stats = p.ch_part != nullptr;
     const bool has_aux = p.has_add || p.has_mask;
     const int swz = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
     // batch-norm statistics: thread t owns the 8 columns of 16-byte chunk `st_chunk` (of every
@@ -569,8 +610,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ss += red_sum[g2 * BN + col];
           qq += red_sq[g2 * BN + col];
         }
-        atomicAdd(p.ch_sum + n0 + col, ss);
-        atomicAdd(p.ch_sumsq + n0 + col, qq);
+        // one partial row per CTA of this N tile, plain stores: bn_finalize sums the rows in a
+        // fixed order (deterministic; no pre-zeroed accumulator)
+        float* row = p.ch_part + static_cast<size_t>(m_first) * 2 * p.Cout;
+        row[n0 + col] = ss;
+        row[p.Cout + n0 + col] = qq;
       }
     }
   }
@@ -603,26 +647,30 @@ constexpr int kWgPix = 64;   // pixels per pipeline stage (4 UMMA K-steps)
 
 // MT = 128-row blocks of (tap,ci) per CTA (1 or 2): with MT = 2 two accumulators share every dy
 // stage, i.e. twice the tensor work per pipeline round-trip and half the dy traffic per FLOP.
-template <int BN, int MT>
+template <int BN, int MT, int NP = 1>
 struct WgradCfg {
   static constexpr int kAHalfBytes = kWgPix * 128 * 2;   // 64 pixels x 128 (tap,ci) columns
-  static constexpr int kABytes = MT * kAHalfBytes;
-  static constexpr int kBBytes = kWgPix * BN * 2;    // 64 pixels x BN output channels
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kABytes = MT * kAHalfBytes;       // one plane
+  static constexpr int kBBytes = kWgPix * BN * 2;    // 64 pixels x BN output channels, one plane
+  static constexpr int kStageBytes = NP * (kABytes + kBBytes);
   static constexpr int kStagesFit = (kSmemBudget - 1024) / kStageBytes;
-  static constexpr int kStages = MT == 1 ? ((BN >= 256) ? 4 : ((BN == 128) ? 3 : 4))
-                                         : (kStagesFit > 5 ? 5 : kStagesFit);
+  static constexpr int kStages =
+      NP == 3 ? (kStagesFit > 3 ? 3 : kStagesFit)
+              : (MT == 1 ? ((BN >= 256) ? 4 : ((BN == 128) ? 3 : 4))
+                         : (kStagesFit > 5 ? 5 : kStagesFit));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
   static constexpr int kTmemCols = MT * BN < 32 ? 32 : MT * BN;
-  static_assert(MT * BN <= 512 && kStages >= 3, "wgrad tile does not fit");
+  static_assert(MT * BN <= 512 && kStages >= (NP == 3 ? 2 : 3), "wgrad tile does not fit");
 };
 
 // CW: channel width of one im2col chunk of x (16/32/64), CWB: channel width of one dy chunk.
-template <int BN, int CW, int CWB, bool IM2COL, int MT>
+template <int BN, int CW, int CWB, bool IM2COL, int MT, int NP>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
-                  const WgradParams p) {
-  using Cfg = WgradCfg<BN, MT>;
+                  const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
+                  const __grid_constant__ CUtensorMap tmDY1,
+                  const __grid_constant__ CUtensorMap tmDY2, const WgradParams p) {
+  using Cfg = WgradCfg<BN, MT, NP>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAChunks = MT * 128 / CW;        // chunks of both 128-row blocks, consecutive
   constexpr int kBChunks = BN / CWB;
@@ -691,8 +739,8 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        uint8_t* sb = sa + Cfg::kABytes;
-        mbar_expect_tx(&full_bar[stage], a_chunks * kAChunkBytes + b_chunks * kBChunkBytes);
+        uint8_t* sb = sa + NP * Cfg::kABytes;
+        mbar_expect_tx(&full_bar[stage], NP * (a_chunks * kAChunkBytes + b_chunks * kBChunkBytes));
         int img = 0, h0 = 0, w0 = 0;
         if (IM2COL) {
           img = p0 / p.HoWo;
@@ -703,18 +751,25 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           w0 = qo * p.stride - p.pad_w_lo;
         }
 #pragma unroll
-        for (int j = 0; j < kAChunks; ++j) {
-          if (j < a_chunks) {
-            if (IM2COL) {
-              tma_load_im2col_4d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], ch_c[j], w0, h0,
-                                 img, (uint16_t)ch_s[j], (uint16_t)ch_r[j]);
-            } else {
-              tma_load_2d(sa + j * kAChunkBytes, &tmX, &full_bar[stage], ch_c[j], p0);
+        for (int pl = 0; pl < NP; ++pl) {
+          const CUtensorMap* mX = pl == 0 ? &tmX : (pl == 1 ? &tmX1 : &tmX2);
+          const CUtensorMap* mDY = pl == 0 ? &tmDY : (pl == 1 ? &tmDY1 : &tmDY2);
+#pragma unroll
+          for (int j = 0; j < kAChunks; ++j) {
+            if (j < a_chunks) {
+              uint8_t* dst = sa + pl * Cfg::kABytes + j * kAChunkBytes;
+              if (IM2COL) {
+                tma_load_im2col_4d(dst, mX, &full_bar[stage], ch_c[j], w0, h0, img,
+                                   (uint16_t)ch_s[j], (uint16_t)ch_r[j]);
+              } else {
+                tma_load_2d(dst, mX, &full_bar[stage], ch_c[j], p0);
+              }
             }
           }
+          for (int i = 0; i < b_chunks; ++i)
+            tma_load_2d(sb + pl * Cfg::kBBytes + i * kBChunkBytes, mDY, &full_bar[stage],
+                        co0 + i * CWB, p0);
         }
-        for (int i = 0; i < b_chunks; ++i)
-          tma_load_2d(sb + i * kBChunkBytes, &tmDY, &full_bar[stage], co0 + i * CWB, p0);
       }
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -726,7 +781,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // (64/32/16 channels) LBO apart.  16 pixel rows per UMMA.
     const uint64_t a_desc0 = make_smem_desc(smem_u32(smem), kAChunkBytes, 8 * CW * 2,
                                             swizzle_layout_type(CW * 2));
-    const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, kBChunkBytes,
+    const uint64_t b_desc0 = make_smem_desc(smem_u32(smem) + NP * Cfg::kABytes, kBChunkBytes,
                                             8 * CWB * 2, swizzle_layout_type(CWB * 2));
     for (int it = 0; it < num_ks; ++it) {
       mbar_wait(&full_bar[stage], phase);
@@ -739,9 +794,15 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           if (h == 0 || second) {
 #pragma unroll
             for (int ks = 0; ks < kWgPix / 16; ++ks) {
-              umma_bf16(tmem_base + h * BN,
-                        da0 + ((h * Cfg::kAHalfBytes + ks * 16 * CW * 2) >> 4),
-                        db0 + ((ks * 16 * CWB * 2) >> 4), kIdesc, (it | ks) ? 1u : 0u);
+#pragma unroll
+              for (int t = 0; t < (NP == 3 ? 6 : 1); ++t) {
+                const int pa = NP == 3 ? plane_term_a(t) : 0;
+                const int pb = NP == 3 ? plane_term_b(t) : 0;
+                umma_bf16(tmem_base + h * BN,
+                          da0 + ((pa * Cfg::kABytes + h * Cfg::kAHalfBytes + ks * 16 * CW * 2) >> 4),
+                          db0 + ((pb * Cfg::kBBytes + ks * 16 * CWB * 2) >> 4), kIdesc,
+                          (it | ks | t) ? 1u : 0u);
+              }
             }
           }
         }
@@ -803,14 +864,15 @@ static int num_sms() {
 }
 
 struct ConvMaps {
-  CUtensorMap a, b, c, add, mask;
+  CUtensorMap a[3], b[3], c, add, mask;
 };
 
-template <int BN, int CW, bool IM2COL, int MT>
-static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStream_t stream) {
-  using Cfg = FpropCfg<BN, MT>;
+template <int BN, int CW, bool IM2COL, int MT, int NP>
+static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per_n,
+                            cudaStream_t stream) {
+  using Cfg = FpropCfg<BN, MT, NP>;
   static bool attr_set = false;
-  auto kern = conv_gemm_kernel<BN, CW, IM2COL, MT>;
+  auto kern = conv_gemm_kernel<BN, CW, IM2COL, MT, NP>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBudget + 2048);
@@ -824,13 +886,10 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
   q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32);
   q.m_tiles = ceil_div(p.M, MT * kBM);
   q.n_tiles = p.Cout / BN;
-  // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
-  // its per-channel statistics), at most one CTA per SM
-  int per_n = num_sms() / q.n_tiles;
-  if (per_n < 1) per_n = 1;
-  if (per_n > q.m_tiles) per_n = q.m_tiles;
   const int grid = per_n * q.n_tiles;
-  launch_k(kern, dim3(grid), dim3(kConvThreads), Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32), stream, tm.a, tm.b, tm.c, tm.add, tm.mask, q);
+  launch_k(kern, dim3(grid), dim3(kConvThreads),
+           Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32), stream, tm.a[0], tm.b[0],
+           tm.c, tm.add, tm.mask, tm.a[1], tm.a[2], tm.b[1], tm.b[2], q);
   count_launch();
   return check_launch("conv_gemm_kernel");
 }
@@ -838,56 +897,98 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, cudaStr
 // -1: choose per problem; 1 / 2: force that many M tiles per CTA tile where the shape allows it
 static int g_conv_mtiles_mode = -1;
 
-template <int BN>
-static int dispatch_conv_gemm(int cw, bool im2col, const ConvMaps& tm, const ConvGemmParams& p,
-                              cudaStream_t s) {
+// Tile shape and persistent grid of one conv GEMM: a pure function of the problem, shared by the
+// launcher and by acnn_conv_stats_parts() (the number of partial statistics rows = per_n).
+struct ConvTiling {
+  int bn;      // N tile
+  int mt;      // M tiles (128 pixels) per CTA tile
+  int per_n;   // CTAs per N tile = rows of the partial statistics buffer
+};
+
+static ConvTiling conv_tiling(int M, int Cout, bool has_add, bool has_mask, bool out_f32, int np) {
+  ConvTiling t;
+  // N tile: 256 halves the A-operand traffic per FLOP (128 B/clk of smem reads at BN=128 is the
+  // SM's whole shared-memory bandwidth); dense / tiny-M problems keep 128 for more CTAs
+  t.bn = (Cout % 128 == 0) ? 128 : ((Cout % 64 == 0) ? 64 : 32);
+  if (np == 1 && Cout % 256 == 0 && !out_f32 && (int64_t)ceil_div(M, kBM) * (Cout / 256) >= 96)
+    t.bn = 256;
   // Two M tiles per CTA when TMEM has room (N <= 128), the smem ring stays >= 3 stages deep and
   // there are enough tiles to keep every SM busy for several rounds.
-  bool two = false;
-  if constexpr (BN <= 128) {
-    // (at N = 128 that rules out only the add + mask epilogue: two 32 KiB aux staging tiles)
-    const bool fits = FpropCfg<BN, 2>::stages_for(p.has_add, p.has_mask, p.out_f32) >= 3;
-    const int64_t tiles = (int64_t)ceil_div(p.M, 2 * kBM) * (p.Cout / BN);
-    two = fits && !p.out_f32 &&
-          (g_conv_mtiles_mode == 2 || (g_conv_mtiles_mode == -1 && tiles >= 4 * (int64_t)num_sms()));
+  // (at N = 128 that rules out only the add + mask epilogue: two 32 KiB aux staging tiles)
+  t.mt = 1;
+  if (np == 1 && t.bn <= 128 && !out_f32) {
+    const bool fits = fprop_stages(t.bn, 2, 1, has_add, has_mask, out_f32) >= 3;
+    const int64_t tiles = (int64_t)ceil_div(M, 2 * kBM) * (Cout / t.bn);
+    if (fits && (g_conv_mtiles_mode == 2 ||
+                 (g_conv_mtiles_mode == -1 && tiles >= 4 * (int64_t)num_sms())))
+      t.mt = 2;
   }
-  if constexpr (BN <= 128) {
-    if (two) {
-      if (im2col) {
-        if (cw == 64) return launch_conv_gemm<BN, 64, true, 2>(tm, p, s);
-        if (cw == 32) return launch_conv_gemm<BN, 32, true, 2>(tm, p, s);
-        return launch_conv_gemm<BN, 16, true, 2>(tm, p, s);
-      }
-      if (cw == 64) return launch_conv_gemm<BN, 64, false, 2>(tm, p, s);
-      if (cw == 32) return launch_conv_gemm<BN, 32, false, 2>(tm, p, s);
-      return launch_conv_gemm<BN, 16, false, 2>(tm, p, s);
-    }
-  }
+  // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
+  // its per-channel statistics), at most one CTA per SM
+  const int n_tiles = Cout / t.bn;
+  const int m_tiles = ceil_div(M, t.mt * kBM);
+  t.per_n = num_sms() / n_tiles;
+  if (t.per_n < 1) t.per_n = 1;
+  if (t.per_n > m_tiles) t.per_n = m_tiles;
+  return t;
+}
+
+template <int BN, int MT, int NP>
+static int dispatch_conv_cw(int cw, bool im2col, const ConvMaps& tm, const ConvGemmParams& p,
+                            int per_n, cudaStream_t s) {
   if (im2col) {
-    if (cw == 64) return launch_conv_gemm<BN, 64, true, 1>(tm, p, s);
-    if (cw == 32) return launch_conv_gemm<BN, 32, true, 1>(tm, p, s);
-    return launch_conv_gemm<BN, 16, true, 1>(tm, p, s);
+    if (cw == 64) return launch_conv_gemm<BN, 64, true, MT, NP>(tm, p, per_n, s);
+    if (cw == 32) return launch_conv_gemm<BN, 32, true, MT, NP>(tm, p, per_n, s);
+    return launch_conv_gemm<BN, 16, true, MT, NP>(tm, p, per_n, s);
   }
-  if (cw == 64) return launch_conv_gemm<BN, 64, false, 1>(tm, p, s);
-  if (cw == 32) return launch_conv_gemm<BN, 32, false, 1>(tm, p, s);
-  return launch_conv_gemm<BN, 16, false, 1>(tm, p, s);
+  if (cw == 64) return launch_conv_gemm<BN, 64, false, MT, NP>(tm, p, per_n, s);
+  if (cw == 32) return launch_conv_gemm<BN, 32, false, MT, NP>(tm, p, per_n, s);
+  return launch_conv_gemm<BN, 16, false, MT, NP>(tm, p, per_n, s);
+}
+
+template <int BN>
+static int dispatch_conv_gemm(const ConvTiling& t, int np, int cw, bool im2col, const ConvMaps& tm,
+                              const ConvGemmParams& p, cudaStream_t s) {
+  if constexpr (BN <= 128) {
+    if (np == 3) return dispatch_conv_cw<BN, 1, 3>(cw, im2col, tm, p, t.per_n, s);
+    if (t.mt == 2) return dispatch_conv_cw<BN, 2, 1>(cw, im2col, tm, p, t.per_n, s);
+  }
+  return dispatch_conv_cw<BN, 1, 1>(cw, im2col, tm, p, t.per_n, s);
 }
 
 static int chunk_width(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
 
+static int out_hw(const acnn_conv_geom& g, int* Ho, int* Wo) {
+  *Ho = (g.H + g.pad_h_lo + g.pad_h_hi - g.kh) / g.stride + 1;
+  *Wo = (g.W + g.pad_w_lo + g.pad_w_hi - g.kw) / g.stride + 1;
+  return (*Ho > 0 && *Wo > 0) ? 1 : 0;
+}
+
+// elements of the input tensor (one operand plane)
+static int64_t input_elems(const acnn_conv_geom& g) {
+  int64_t pix, row, img;
+  input_pitches(g, &pix, &row, &img);
+  return (int64_t)g.B * img;
+}
+
+// precision 0: x / w are bf16.  precision 1 (fp32 parity mode): x and w each are THREE consecutive
+// bf16 planes (acnn_split3 / acnn_prep_weights with planes = 3), plane p of x at x + p * numel(x),
+// plane p of w at w + p * w_plane_stride elements; y must be fp32 (out_f32), no fused epilogue.
 static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w, void* y,
-                          float* ch_sum, float* ch_sumsq, const void* add_src,
-                          const void* mask_src, const float* bias, int out_f32,
+                          float* ch_part, const void* add_src, const void* mask_src,
+                          const float* bias, int out_f32, int precision, int64_t w_plane_stride,
                           cudaStream_t stream) {
   ACNN_REQUIRE(g.B > 0 && g.H > 0 && g.W > 0 && g.Cin > 0 && g.Cout > 0, "conv: empty geometry");
   ACNN_REQUIRE(g.Cin % 16 == 0, "conv: Cin=%d must be a multiple of 16", g.Cin);
   ACNN_REQUIRE(g.Cout % 32 == 0, "conv: Cout=%d must be a multiple of 32", g.Cout);
   ACNN_REQUIRE(g.stride >= 1 && g.kh >= 1 && g.kw >= 1, "conv: bad kernel/stride");
-  ACNN_REQUIRE((ch_sum == nullptr) == (ch_sumsq == nullptr), "conv: ch_sum/ch_sumsq must pair");
-  ACNN_REQUIRE(!(ch_sum && out_f32), "conv: statistics only with bf16 output");
-  const int Ho = (g.H + g.pad_h_lo + g.pad_h_hi - g.kh) / g.stride + 1;
-  const int Wo = (g.W + g.pad_w_lo + g.pad_w_hi - g.kw) / g.stride + 1;
-  ACNN_REQUIRE(Ho > 0 && Wo > 0, "conv: empty output");
+  ACNN_REQUIRE(!(ch_part && out_f32), "conv: statistics only with bf16 output");
+  ACNN_REQUIRE(precision == 0 || precision == 1, "conv: precision must be 0 (bf16) or 1 (fp32)");
+  ACNN_REQUIRE(precision == 0 || (out_f32 && !add_src && !mask_src && !ch_part && w_plane_stride > 0),
+               "conv: the fp32 (3-plane) mode needs fp32 output, a weight plane stride and no "
+               "fused add / mask / statistics epilogue");
+  int Ho, Wo;
+  ACNN_REQUIRE(out_hw(g, &Ho, &Wo), "conv: empty output");
   ACNN_REQUIRE(g.pad_h_lo <= 128 && g.pad_w_lo <= 128 && g.kh <= 128 && g.kw <= 128,
                "conv: padding / filter exceed the TMA im2col corner range");
   int rc = load_driver_fns();
@@ -895,6 +996,7 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
 
   const bool plain = is_plain(g);
   const int cw = chunk_width(g.Cin);
+  const int np = precision ? 3 : 1;
   ConvGemmParams p;
   p.M = g.B * Ho * Wo;
   p.Cout = g.Cout;
@@ -908,8 +1010,7 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   p.pad_w_lo = g.pad_w_lo;
   p.b_sw_bytes = p.Ktot >= 64 ? 128 : p.Ktot * 2;
   p.y = y;
-  p.ch_sum = ch_sum;
-  p.ch_sumsq = ch_sumsq;
+  p.ch_part = ch_part;
   p.bias = bias;
   p.has_add = add_src != nullptr;
   p.has_mask = mask_src != nullptr;
@@ -918,37 +1019,48 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   ACNN_REQUIRE(p.b_sw_bytes == 128 || p.b_sw_bytes == 64 || p.b_sw_bytes == 32,
                "conv: unsupported K=%d", p.Ktot);
 
-  // N tile: 256 halves the A-operand traffic per FLOP (128 B/clk of smem reads at BN=128 is the
-  // SM's whole shared-memory bandwidth); dense / tiny-M problems keep 128 for more CTAs
-  int bn = (g.Cout % 128 == 0) ? 128 : ((g.Cout % 64 == 0) ? 64 : 32);
-  if (g.Cout % 256 == 0 && !out_f32 && (int64_t)ceil_div(p.M, kBM) * (g.Cout / 256) >= 96) bn = 256;
+  const ConvTiling t = conv_tiling(p.M, g.Cout, p.has_add, p.has_mask, out_f32 != 0, np);
+  const int bn = t.bn;
   ConvMaps tm;
-  if (plain) {
-    rc = make_map_2d(&tm.a, x, p.M, g.Cin, g.Cin, kBM, cw);
-  } else {
-    rc = make_map_im2col(&tm.a, x, g, cw, kBM);
+  const int64_t x_plane = input_elems(g);
+  for (int pl = 0; pl < np; ++pl) {
+    const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x) + pl * x_plane;
+    const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w) + pl * w_plane_stride;
+    if (plain) {
+      rc = make_map_2d(&tm.a[pl], xp, p.M, g.Cin, g.Cin, kBM, cw);
+    } else {
+      rc = make_map_im2col(&tm.a[pl], xp, g, cw, kBM);
+    }
+    if (rc) return rc;
+    rc = make_map_2d(&tm.b[pl], wp, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
+    if (rc) return rc;
   }
-  if (rc) return rc;
-  rc = make_map_2d(&tm.b, w, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
-  if (rc) return rc;
-  tm.c = tm.add = tm.mask = tm.b;   // placeholders when unused
+  for (int pl = np; pl < 3; ++pl) {   // placeholders
+    tm.a[pl] = tm.a[0];
+    tm.b[pl] = tm.b[0];
+  }
+  tm.c = tm.add = tm.mask = tm.b[0];   // placeholders when unused
   const int subw = bn < 64 ? bn : 64;
   if (!out_f32 && (rc = make_map_2d(&tm.c, y, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
   if (add_src && (rc = make_map_2d(&tm.add, add_src, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
   if (mask_src && (rc = make_map_2d(&tm.mask, mask_src, p.M, g.Cout, g.Cout, kBM, subw))) return rc;
-  if (bn == 256) return dispatch_conv_gemm<256>(cw, !plain, tm, p, stream);
-  if (bn == 128) return dispatch_conv_gemm<128>(cw, !plain, tm, p, stream);
-  if (bn == 64) return dispatch_conv_gemm<64>(cw, !plain, tm, p, stream);
-  return dispatch_conv_gemm<32>(cw, !plain, tm, p, stream);
+  if (bn == 256) return dispatch_conv_gemm<256>(t, np, cw, !plain, tm, p, stream);
+  if (bn == 128) return dispatch_conv_gemm<128>(t, np, cw, !plain, tm, p, stream);
+  if (bn == 64) return dispatch_conv_gemm<64>(t, np, cw, !plain, tm, p, stream);
+  return dispatch_conv_gemm<32>(t, np, cw, !plain, tm, p, stream);
 }
 
-template <int BN, int CW, int CWB, bool IM2COL, int MT>
-static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, WgradParams p, int m_tiles,
-                        int n_tiles, cudaStream_t stream) {
-  using Cfg = WgradCfg<BN, MT>;
+struct WgradMaps {
+  CUtensorMap x[3], dy[3];
+};
+
+template <int BN, int CW, int CWB, bool IM2COL, int MT, int NP>
+static int launch_wgrad(const WgradMaps& tm, WgradParams p, int n_tiles, int deterministic,
+                        cudaStream_t stream) {
+  using Cfg = WgradCfg<BN, MT, NP>;
   static bool attr_set = false;
-  auto kern = wgrad_gemm_kernel<BN, CW, CWB, IM2COL, MT>;
-  m_tiles = ceil_div(p.Ktot, MT * 128);
+  auto kern = wgrad_gemm_kernel<BN, CW, CWB, IM2COL, MT, NP>;
+  const int m_tiles = ceil_div(p.Ktot, MT * 128);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
@@ -958,24 +1070,34 @@ static int launch_wgrad(const CUtensorMap& tx, const CUtensorMap& tdy, WgradPara
     }
     attr_set = true;
   }
-  // split the pixel (K) range so that roughly two waves of CTAs cover the GPU
+  // split the pixel (K) range so that roughly two waves of CTAs cover the GPU; deterministic mode:
+  // no split -- every dw element receives exactly one (atomic) add onto the zeroed buffer
   const int ctas_per_sm = Cfg::kSmemBytes <= 110 * 1024 ? 2 : 1;
   const int tiles = m_tiles * n_tiles;
   int splits = ceil_div(2 * ctas_per_sm * num_sms(), tiles);
   const int max_splits = p.stages_total >= 8 ? p.stages_total / 4 : 1;
   if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  if (splits < 1 || deterministic) splits = 1;
   p.stages_per_split = ceil_div(p.stages_total, splits);
   splits = ceil_div(p.stages_total, p.stages_per_split);
   dim3 grid(m_tiles, n_tiles, splits);
-  launch_k(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tx, tdy, p);
+  launch_k(kern, dim3(grid), dim3(kThreads), Cfg::kSmemBytes, stream, tm.x[0], tm.dy[0], tm.x[1],
+           tm.x[2], tm.dy[1], tm.dy[2], p);
   count_launch();
   return check_launch("wgrad_gemm_kernel");
 }
 
 template <int BN, int CW, bool IM2COL>
-static int dispatch_wgrad_cwb(int cwb, const CUtensorMap& tx, const CUtensorMap& tdy,
-                              const WgradParams& p, int mt, int nt, cudaStream_t s) {
+static int dispatch_wgrad_cwb(int cwb, int np, const WgradMaps& tm, const WgradParams& p, int nt,
+                              int det, cudaStream_t s) {
+  if constexpr (BN <= 128) {
+    if (np == 3) {
+      if constexpr (BN >= 64) {
+        if (cwb == 64) return launch_wgrad<BN, CW, 64, IM2COL, 1, 3>(tm, p, nt, det, s);
+      }
+      return launch_wgrad<BN, CW, 32, IM2COL, 1, 3>(tm, p, nt, det, s);
+    }
+  }
   if constexpr (BN >= 64) {
     if (cwb == 64) {
       // two 128-row blocks per CTA (full-width chunks only, to bound the instantiation count)
@@ -984,40 +1106,41 @@ static int dispatch_wgrad_cwb(int cwb, const CUtensorMap& tx, const CUtensorMap&
         // halving the number of CTAs costs more than the shared dy stage saves)
         const bool big = (p.Ktot >= 1024 && p.P >= 50176) || p.Ktot >= 4096;
         if (p.Ktot > 128 && (g_conv_mtiles_mode == 2 || (g_conv_mtiles_mode == -1 && big)))
-          return launch_wgrad<BN, CW, 64, IM2COL, 2>(tx, tdy, p, mt, nt, s);
+          return launch_wgrad<BN, CW, 64, IM2COL, 2, 1>(tm, p, nt, det, s);
       }
-      return launch_wgrad<BN, CW, 64, IM2COL, 1>(tx, tdy, p, mt, nt, s);
+      return launch_wgrad<BN, CW, 64, IM2COL, 1, 1>(tm, p, nt, det, s);
     }
   }
-  return launch_wgrad<BN, CW, 32, IM2COL, 1>(tx, tdy, p, mt, nt, s);
+  return launch_wgrad<BN, CW, 32, IM2COL, 1, 1>(tm, p, nt, det, s);
 }
 
 template <int BN, bool IM2COL>
-static int dispatch_wgrad_cw(int cw, int cwb, const CUtensorMap& tx, const CUtensorMap& tdy,
-                             const WgradParams& p, int mt, int nt, cudaStream_t s) {
-  if (cw == 64) return dispatch_wgrad_cwb<BN, 64, IM2COL>(cwb, tx, tdy, p, mt, nt, s);
-  if (cw == 32) return dispatch_wgrad_cwb<BN, 32, IM2COL>(cwb, tx, tdy, p, mt, nt, s);
-  return dispatch_wgrad_cwb<BN, 16, IM2COL>(cwb, tx, tdy, p, mt, nt, s);
+static int dispatch_wgrad_cw(int cw, int cwb, int np, const WgradMaps& tm, const WgradParams& p,
+                             int nt, int det, cudaStream_t s) {
+  if (cw == 64) return dispatch_wgrad_cwb<BN, 64, IM2COL>(cwb, np, tm, p, nt, det, s);
+  if (cw == 32) return dispatch_wgrad_cwb<BN, 32, IM2COL>(cwb, np, tm, p, nt, det, s);
+  return dispatch_wgrad_cwb<BN, 16, IM2COL>(cwb, np, tm, p, nt, det, s);
 }
 
 template <bool IM2COL>
-static int dispatch_wgrad(int bn, int cw, int cwb, const CUtensorMap& tx, const CUtensorMap& tdy,
-                          const WgradParams& p, int mt, int nt, cudaStream_t s) {
-  if (bn == 256) return dispatch_wgrad_cw<256, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
-  if (bn == 128) return dispatch_wgrad_cw<128, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
-  if (bn == 64) return dispatch_wgrad_cw<64, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
-  return dispatch_wgrad_cw<32, IM2COL>(cw, cwb, tx, tdy, p, mt, nt, s);
+static int dispatch_wgrad(int bn, int cw, int cwb, int np, const WgradMaps& tm, const WgradParams& p,
+                          int nt, int det, cudaStream_t s) {
+  if (bn == 256) return dispatch_wgrad_cw<256, IM2COL>(cw, cwb, np, tm, p, nt, det, s);
+  if (bn == 128) return dispatch_wgrad_cw<128, IM2COL>(cw, cwb, np, tm, p, nt, det, s);
+  if (bn == 64) return dispatch_wgrad_cw<64, IM2COL>(cw, cwb, np, tm, p, nt, det, s);
+  return dispatch_wgrad_cw<32, IM2COL>(cw, cwb, np, tm, p, nt, det, s);
 }
 
 static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* dy, float* dw,
-                           cudaStream_t stream) {
+                           int precision, int deterministic, cudaStream_t stream) {
   ACNN_REQUIRE(g.Cin % 16 == 0 && g.Cout % 32 == 0, "wgrad: Cin %% 16 / Cout %% 32 required");
-  const int Ho = (g.H + g.pad_h_lo + g.pad_h_hi - g.kh) / g.stride + 1;
-  const int Wo = (g.W + g.pad_w_lo + g.pad_w_hi - g.kw) / g.stride + 1;
-  ACNN_REQUIRE(Ho > 0 && Wo > 0, "wgrad: empty output");
+  ACNN_REQUIRE(precision == 0 || precision == 1, "wgrad: precision must be 0 (bf16) or 1 (fp32)");
+  int Ho, Wo;
+  ACNN_REQUIRE(out_hw(g, &Ho, &Wo), "wgrad: empty output");
   int rc = load_driver_fns();
   if (rc) return rc;
   const bool plain = is_plain(g);
+  const int np = precision ? 3 : 1;
   WgradParams p;
   p.P = g.B * Ho * Wo;
   p.Cout = g.Cout;
@@ -1034,21 +1157,30 @@ static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* d
   p.dw = dw;
   const int cw = chunk_width(g.Cin);
   const int cwb = (g.Cout % 64 == 0) ? 64 : 32;
-  const int bn = g.Cout >= 256 ? 256 : (g.Cout >= 128 ? 128 : (g.Cout >= 64 ? 64 : 32));
+  int bn = g.Cout >= 256 ? 256 : (g.Cout >= 128 ? 128 : (g.Cout >= 64 ? 64 : 32));
+  if (np == 3 && bn > 128) bn = 128;   // three operand planes per stage: smem
   ACNN_REQUIRE(g.Cout % bn == 0, "wgrad: Cout=%d not a multiple of its N tile %d", g.Cout, bn);
-  CUtensorMap tdy, tx;
-  rc = make_map_2d(&tdy, dy, p.P, g.Cout, g.Cout, kWgPix, cwb);
-  if (rc) return rc;
-  if (plain) {
-    rc = make_map_2d(&tx, x, p.P, g.Cin, g.Cin, kWgPix, cw);
-  } else {
-    rc = make_map_im2col(&tx, x, g, cw, kWgPix);
+  WgradMaps tm;
+  const int64_t x_plane = input_elems(g), dy_plane = (int64_t)p.P * g.Cout;
+  for (int pl = 0; pl < np; ++pl) {
+    const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x) + pl * x_plane;
+    const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(dy) + pl * dy_plane;
+    rc = make_map_2d(&tm.dy[pl], dp, p.P, g.Cout, g.Cout, kWgPix, cwb);
+    if (rc) return rc;
+    if (plain) {
+      rc = make_map_2d(&tm.x[pl], xp, p.P, g.Cin, g.Cin, kWgPix, cw);
+    } else {
+      rc = make_map_im2col(&tm.x[pl], xp, g, cw, kWgPix);
+    }
+    if (rc) return rc;
   }
-  if (rc) return rc;
-  const int mt = ceil_div(p.Ktot, 128);
+  for (int pl = np; pl < 3; ++pl) {
+    tm.x[pl] = tm.x[0];
+    tm.dy[pl] = tm.dy[0];
+  }
   const int nt = g.Cout / bn;
-  if (plain) return dispatch_wgrad<false>(bn, cw, cwb, tx, tdy, p, mt, nt, stream);
-  return dispatch_wgrad<true>(bn, cw, cwb, tx, tdy, p, mt, nt, stream);
+  if (plain) return dispatch_wgrad<false>(bn, cw, cwb, np, tm, p, nt, deterministic, stream);
+  return dispatch_wgrad<true>(bn, cw, cwb, np, tm, p, nt, deterministic, stream);
 }
 
 }  // namespace acnn
@@ -1064,19 +1196,27 @@ int acnn_set_conv_mtiles(int mode) {
   return prev;
 }
 
-int acnn_conv_fprop(const acnn_conv_geom* g, const void* x, const void* w, void* y, float* ch_sum,
-                    float* ch_sumsq, const void* add_src, const void* mask_src, const float* bias,
-                    int out_f32, void* stream) {
+int acnn_conv_stats_parts(const acnn_conv_geom* g) {
+  if (!g) return 0;
+  int Ho, Wo;
+  if (!acnn::out_hw(*g, &Ho, &Wo) || g->Cout % 32 != 0) return 0;
+  return acnn::conv_tiling(g->B * Ho * Wo, g->Cout, false, false, false, 1).per_n;
+}
+
+int acnn_conv_fprop(const acnn_conv_geom* g, const void* x, const void* w, void* y,
+                    float* ch_part, const void* add_src, const void* mask_src, const float* bias,
+                    int out_f32, int precision, int64_t w_plane_stride, void* stream) {
   if (!g || !x || !w || !y) {
     acnn::set_error("acnn_conv_fprop: null argument");
     return ACNN_ERR_INVALID;
   }
-  return acnn::conv_gemm_host(*g, x, w, y, ch_sum, ch_sumsq, add_src, mask_src, bias, out_f32,
-                              static_cast<cudaStream_t>(stream));
+  return acnn::conv_gemm_host(*g, x, w, y, ch_part, add_src, mask_src, bias, out_f32, precision,
+                              w_plane_stride, static_cast<cudaStream_t>(stream));
 }
 
 int acnn_conv_dgrad(const acnn_conv_geom* g, const void* dy, const void* w_dgrad, void* dx,
-                    const void* add_src, const void* mask_src, void* stream) {
+                    const void* add_src, const void* mask_src, int precision,
+                    int64_t w_plane_stride, void* stream) {
   if (!g || !dy || !w_dgrad || !dx) {
     acnn::set_error("acnn_conv_dgrad: null argument");
     return ACNN_ERR_INVALID;
@@ -1103,17 +1243,19 @@ int acnn_conv_dgrad(const acnn_conv_geom* g, const void* dy, const void* w_dgrad
   t.pad_w_lo = g->kw - 1 - g->pad_w_lo;
   t.pad_w_hi = g->kw - 1 - g->pad_w_hi;
   t.x_pix_stride = t.x_row_pitch = t.x_img_pitch = t.reserved_ = 0;
-  return acnn::conv_gemm_host(t, dy, w_dgrad, dx, nullptr, nullptr, add_src, mask_src, nullptr, 0,
+  return acnn::conv_gemm_host(t, dy, w_dgrad, dx, nullptr, add_src, mask_src, nullptr,
+                              precision ? 1 : 0, precision, w_plane_stride,
                               static_cast<cudaStream_t>(stream));
 }
 
 int acnn_conv_wgrad(const acnn_conv_geom* g, const void* x, const void* dy, float* dw,
-                    void* stream) {
+                    int precision, int deterministic, void* stream) {
   if (!g || !x || !dy || !dw) {
     acnn::set_error("acnn_conv_wgrad: null argument");
     return ACNN_ERR_INVALID;
   }
-  return acnn::conv_wgrad_host(*g, x, dy, dw, static_cast<cudaStream_t>(stream));
+  return acnn::conv_wgrad_host(*g, x, dy, dw, precision, deterministic,
+                               static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

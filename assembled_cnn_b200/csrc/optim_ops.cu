@@ -8,9 +8,53 @@ namespace acnn {
 
 // blockIdx.y = tensor; 32x32 tiles of the [Cout][Cin] matrix of every tap, transposed through
 // shared memory so both the read (along Cin) and the dgrad write (along Cout) are coalesced.
+// x = hi + mid + lo with three bf16 values (24 mantissa bits): the operand planes of the fp32
+// parity mode of the conv GEMMs.
+__device__ __forceinline__ void split3(float v, bf16& h, bf16& m, bf16& l) {
+  h = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(h);      // exact
+  m = __float2bfloat16_rn(r1);
+  l = __float2bfloat16_rn(r1 - __bfloat162float(m));
+}
+__device__ __forceinline__ void store_planes(bf16* base, int64_t idx, float v, int planes,
+                                             int64_t plane_stride) {
+  if (planes == 1) {
+    base[idx] = __float2bfloat16_rn(v);
+  } else {
+    bf16 h, m, l;
+    split3(v, h, m, l);
+    base[idx] = h;
+    base[idx + plane_stride] = m;
+    base[idx + 2 * plane_stride] = l;
+  }
+}
+
+// x fp32 [n] -> planes bf16 [3][n]
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ x, bf16* __restrict__ planes, int64_t nvec) {
+  pdl_wait();
+  const int64_t n = nvec * 8;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8], h[8], m[8], l[8];
+    loadf8(x + i * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      h[k] = __bfloat162float(__float2bfloat16_rn(v[k]));
+      const float r1 = v[k] - h[k];
+      m[k] = __bfloat162float(__float2bfloat16_rn(r1));
+      l[k] = r1 - m[k];
+    }
+    store8(planes + i * 8, h);
+    store8(planes + n + i * 8, m);
+    store8(planes + 2 * n + i * 8, l);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __restrict__ descs,
-                    bf16* __restrict__ w_fprop, bf16* __restrict__ w_dgrad) {
+                    bf16* __restrict__ w_fprop, bf16* __restrict__ w_dgrad, int planes,
+                    int64_t fprop_plane_stride, int64_t dgrad_plane_stride) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   __shared__ float tile[32][33];
   const acnn_weight_desc d = descs[blockIdx.y];
@@ -29,7 +73,7 @@ prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __
       if (co < d.Cout && ci < d.Cin) {
         const int64_t idx = ((int64_t)co * d.taps + t) * d.Cin + ci;
         v = master[d.master_off + idx];
-        w_fprop[d.fprop_off + idx] = __float2bfloat16_rn(v);
+        store_planes(w_fprop, d.fprop_off + idx, v, planes, fprop_plane_stride);
       }
       tile[ty + k * 8][tx] = v;
     }
@@ -40,7 +84,8 @@ prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __
         const int ci = ci0 + ty + k * 8, co = co0 + tx;
         if (co < d.Cout && ci < d.Cin) {
           const int64_t idx = ((int64_t)ci * d.taps + (d.taps - 1 - t)) * d.Cout + co;
-          w_dgrad[d.dgrad_off + idx] = __float2bfloat16_rn(tile[tx][ty + k * 8]);
+          store_planes(w_dgrad, d.dgrad_off + idx, tile[tx][ty + k * 8], planes,
+                       dgrad_plane_stride);
         }
       }
     }
@@ -49,7 +94,8 @@ prep_weights_kernel(const float* __restrict__ master, const acnn_weight_desc* __
 
 // w [Cout][k][k][3] -> w2 [Cout][k2][k2][16]; input pixel offset u - pad = 2*r + a with
 // r = tap2 - pad2, a in {0,1};  channel = (a*2 + b)*4 + c.
-__global__ void s2d_weight_pack_kernel(const float* __restrict__ w, bf16* __restrict__ w2, int Cout,
+template <class T>
+__global__ void s2d_weight_pack_kernel(const float* __restrict__ w, T* __restrict__ w2, int Cout,
                                        int k, int pad, int k2, int pad2) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -65,7 +111,7 @@ __global__ void s2d_weight_pack_kernel(const float* __restrict__ w, bf16* __rest
   const int u = 2 * (r2 - pad2) + a + pad, v = 2 * (s2 - pad2) + b + pad;
   float val = 0.f;
   if (c < 3 && u >= 0 && u < k && v >= 0 && v < k) val = w[(((int64_t)co * k + u) * k + v) * 3 + c];
-  w2[i] = __float2bfloat16_rn(val);
+  store1(w2 + i, val);
 }
 
 __global__ void s2d_wgrad_unpack_kernel(const float* __restrict__ dw2, float* __restrict__ dw,
@@ -89,10 +135,11 @@ __global__ void s2d_wgrad_unpack_kernel(const float* __restrict__ dw2, float* __
   dw[i] = dw2[(((int64_t)co * k2 + r2) * k2 + s2) * 16 + (a * 2 + b) * 4 + c];
 }
 
+// l2_part: [gridDim.x + 1] floats of scratch; the last slot is the arrival counter (self-resetting)
 __global__ void __launch_bounds__(256)
 sgd_momentum_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ acc,
                     int64_t n, const uint8_t* __restrict__ decay_flag, const float* __restrict__ hp,
-                    float* l2_acc) {
+                    float* l2_acc, float* l2_part) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   __shared__ float sh[8];
   const float lr = hp[0], mom = hp[1], wd = hp[2], gs = hp[3];
@@ -128,7 +175,19 @@ sgd_momentum_kernel(float* __restrict__ w, const float* __restrict__ grad, float
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int k = 0; k < 8; ++k) s += sh[k];
-      atomicAdd(l2_acc, 0.5f * wd * s);
+      // per-CTA partial, then the LAST CTA to arrive adds all partials in index order:
+      // deterministic (the arrival order does not enter the sum)
+      l2_part[blockIdx.x] = s;
+      __threadfence();
+      unsigned int* counter = reinterpret_cast<unsigned int*>(l2_part + gridDim.x);
+      const unsigned int prev = atomicAdd(counter, 1u);
+      if (prev == gridDim.x - 1) {
+        __threadfence();
+        float tot = 0.f;
+        for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(l2_part + b);
+        l2_acc[0] += 0.5f * wd * tot;
+        *counter = 0u;
+      }
     }
   }
 }
@@ -140,20 +199,36 @@ using namespace acnn;
 extern "C" {
 
 int acnn_prep_weights(const float* master, const acnn_weight_desc* descs, int n, void* w_fprop,
-                      void* w_dgrad, void* stream) {
-  ACNN_REQUIRE(master && descs && w_fprop && n > 0 && n < 65536, "prep_weights: bad arguments");
+                      void* w_dgrad, int planes, int64_t fprop_plane_stride,
+                      int64_t dgrad_plane_stride, void* stream) {
+  ACNN_REQUIRE(master && descs && w_fprop && n > 0 && n < 65536 && (planes == 1 || planes == 3),
+               "prep_weights: bad arguments");
   dim3 grid(96, n, 1);
-  launch_k(prep_weights_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, master, descs, (bf16*)w_fprop,
-                                                              (bf16*)w_dgrad);
+  launch_k(prep_weights_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, master, descs,
+           (bf16*)w_fprop, (bf16*)w_dgrad, planes, fprop_plane_stride, dgrad_plane_stride);
   count_launch();
   return check_launch("prep_weights");
 }
 
+int acnn_split3(const float* x, void* planes, int64_t n, void* stream) {
+  ACNN_REQUIRE(x && planes && n > 0 && n % 8 == 0, "split3: bad arguments (n %% 8)");
+  launch_k(split3_kernel, dim3(grid_for(n / 8)), dim3(256), 0, (cudaStream_t)stream, x,
+           (bf16*)planes, n / 8);
+  count_launch();
+  return check_launch("split3");
+}
+
 int acnn_s2d_weight_pack(const float* w, void* w2, int Cout, int k, int pad, int k2, int pad2,
-                         void* stream) {
-  ACNN_REQUIRE(w && w2, "s2d_weight_pack: null argument");
+                         int dtype, void* stream) {
+  ACNN_REQUIRE(w && w2 && (dtype == ACNN_BF16 || dtype == ACNN_F32), "s2d_weight_pack: bad argument");
   const int64_t n = (int64_t)Cout * k2 * k2 * 16;
-  launch_k(s2d_weight_pack_kernel, dim3((int)ceil_div64(n, 256)), dim3(256), 0, (cudaStream_t)stream, w, (bf16*)w2, Cout, k, pad, k2, pad2);
+  if (dtype == ACNN_F32) {
+    launch_k(s2d_weight_pack_kernel<float>, dim3((int)ceil_div64(n, 256)), dim3(256), 0,
+             (cudaStream_t)stream, w, (float*)w2, Cout, k, pad, k2, pad2);
+  } else {
+    launch_k(s2d_weight_pack_kernel<bf16>, dim3((int)ceil_div64(n, 256)), dim3(256), 0,
+             (cudaStream_t)stream, w, (bf16*)w2, Cout, k, pad, k2, pad2);
+  }
   count_launch();
   return check_launch("s2d_weight_pack");
 }
@@ -167,11 +242,15 @@ int acnn_s2d_wgrad_unpack(const float* dw2, float* dw, int Cout, int k, int pad,
   return check_launch("s2d_wgrad_unpack");
 }
 
+int acnn_sgd_scratch_floats(void) { return 148 * 8 + 1; }
+
 int acnn_sgd_momentum(float* w, const float* grad, float* acc, int64_t n,
-                      const uint8_t* decay_flag, const float* hp, float* l2_acc, void* stream) {
-  ACNN_REQUIRE(w && grad && acc && decay_flag && hp && n % 256 == 0,
-               "sgd_momentum: bad arguments (n must be a multiple of 256)");
-  launch_k(sgd_momentum_kernel, dim3(grid_for(n / 4, 256, 148 * 8)), dim3(256), 0, (cudaStream_t)stream, w, grad, acc, n, decay_flag, hp, l2_acc);
+                      const uint8_t* decay_flag, const float* hp, float* l2_acc, float* scratch,
+                      void* stream) {
+  ACNN_REQUIRE(w && grad && acc && decay_flag && hp && n % 256 == 0 && (!l2_acc || scratch),
+               "sgd_momentum: bad arguments (n must be a multiple of 256; l2_acc needs scratch)");
+  launch_k(sgd_momentum_kernel, dim3(grid_for(n / 4, 256, 148 * 8)), dim3(256), 0,
+           (cudaStream_t)stream, w, grad, acc, n, decay_flag, hp, l2_acc, scratch);
   count_launch();
   return check_launch("sgd_momentum");
 }

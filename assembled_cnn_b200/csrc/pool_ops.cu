@@ -30,8 +30,9 @@ __device__ __forceinline__ int reflect(int i, int n) {
 }
 
 // ---------------------------------------------------------------------------- blur-pool
+template <class T>
 __global__ void __launch_bounds__(kPT)
-blurpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, Binomial bw, int H, int W,
+blurpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, Binomial bw, int H, int W,
                     int C, int filt, int stride, int pad, int Ho, int Wo) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   // grid = (ceil(Wo * C/8 / threads), Ho, B): no 64-bit index decomposition per element
@@ -81,9 +82,10 @@ __device__ __forceinline__ void blur_adjoint_1d(int i, int n, int no, const Bino
   }
 }
 
+template <class T>
 __global__ void __launch_bounds__(kPT)
-blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
-                    const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src,
+blurpool_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx,
+                    const T* __restrict__ add_src, const T* __restrict__ mask_src,
                     Binomial bw, int H, int W, int C, int filt, int stride, int pad, int Ho,
                     int Wo) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
@@ -115,8 +117,9 @@ blurpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
 }
 
 // ---------------------------------------------------------------------------- avg / max pool
+template <class T>
 __global__ void __launch_bounds__(kPT)
-avgpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
+avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int H, int W, int C, int k,
                    int stride, int pad, int Ho, int Wo, int count_pad) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   // grid = (ceil(Wo * C/8 / threads), Ho, B)
@@ -163,10 +166,10 @@ __device__ __forceinline__ int window_count(int p, int stride, int pad, int k, i
 // grid = (ceil(W*C/8 / 256), H, B): no 64-bit index divisions on the hot path.  STRIDE > 0 makes
 // the stride a compile-time constant (shifts instead of divisions); the two full-size streams
 // (add / mask tiles) are requested first, the small dout gather (L2 hits) overlaps them.
-template <int STRIDE>
+template <class T, int STRIDE>
 __global__ void __launch_bounds__(kPT)
-avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
-                   const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H, int W,
+avgpool_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx,
+                   const T* __restrict__ add_src, const T* __restrict__ mask_src, int H, int W,
                    int C, int k, int stride_rt, int pad, int Ho, int Wo, int count_pad) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int stride = STRIDE > 0 ? STRIDE : stride_rt;
@@ -178,9 +181,11 @@ avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
   const int ih = blockIdx.y;
   const int64_t b = blockIdx.z;
   const size_t off = (((size_t)b * H + ih) * W + iw) * C + cg * 8;
-  uint4 addv = make_uint4(0, 0, 0, 0), maskv = make_uint4(0, 0, 0, 0);
-  if (add_src) addv = __ldg(reinterpret_cast<const uint4*>(add_src + off));
-  if (mask_src) maskv = __ldg(reinterpret_cast<const uint4*>(mask_src + off));
+  V8<T> addv, maskv;
+  addv.zero();
+  maskv.zero();
+  if (add_src) addv.ld(add_src + off);
+  if (mask_src) maskv.ld(mask_src + off);
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -201,13 +206,13 @@ avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
   }
   if (add_src) {
     float a[8];
-    unpack8(addv, a);
+    addv.unpack(a);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] += a[e];
   }
   if (mask_src) {
     float m[8];
-    unpack8(maskv, m);
+    maskv.unpack(m);
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       if (!(m[e] > 0.f)) acc[e] = 0.f;
@@ -215,8 +220,9 @@ avgpool_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
   store8(dx + off, acc);
 }
 
+template <class T>
 __global__ void __launch_bounds__(kPT)
-maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, int W, int C, int k,
+maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int H, int W, int C, int k,
                    int stride, int pad, int Ho, int Wo, int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
@@ -247,10 +253,11 @@ maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int H, in
   }
 }
 
+template <class T>
 __global__ void __launch_bounds__(kPT)
-maxpool_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ x,
-                   bf16* __restrict__ dx, const bf16* __restrict__ add_src,
-                   const bf16* __restrict__ mask_src, int H, int W, int C, int k, int stride,
+maxpool_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ x,
+                   T* __restrict__ dx, const T* __restrict__ add_src,
+                   const T* __restrict__ mask_src, int H, int W, int C, int k, int stride,
                    int pad, int Ho, int Wo, int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
@@ -304,9 +311,10 @@ maxpool_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ x,
 }
 
 // ---------------------------------------------------------------------------- resampling
+template <class T>
 __global__ void __launch_bounds__(kPT)
-upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
-                      const bf16* __restrict__ add_src, const bf16* __restrict__ mask_src, int H,
+upsample2x_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx,
+                      const T* __restrict__ add_src, const T* __restrict__ mask_src, int H,
                       int W, int C, int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
@@ -335,8 +343,9 @@ upsample2x_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx,
   }
 }
 
+template <class T>
 __global__ void __launch_bounds__(kPT)
-zero_insert2x_kernel(const bf16* __restrict__ dy, bf16* __restrict__ out, int Ho, int Wo, int H,
+zero_insert2x_kernel(const T* __restrict__ dy, T* __restrict__ out, int Ho, int Wo, int H,
                      int W, int C, int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
@@ -348,17 +357,18 @@ zero_insert2x_kernel(const bf16* __restrict__ dy, bf16* __restrict__ out, int Ho
     t /= W;
     const int h = (int)(t % H);
     const int64_t b = t / H;
-    uint4 v = make_uint4(0, 0, 0, 0);
+    V8<T> v;
+    v.zero();
     if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
-      v = __ldg(reinterpret_cast<const uint4*>(dy + ((b * Ho + (h >> 1)) * Wo + (w >> 1)) * C +
-                                               cg * 8));
-    *reinterpret_cast<uint4*>(out + i * 8) = v;
+      v.ld(dy + ((b * Ho + (h >> 1)) * Wo + (w >> 1)) * C + cg * 8);
+    v.st(out + i * 8);
   }
 }
 
+template <class T>
 __global__ void __launch_bounds__(kPT)
-gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_src,
-               bf16* __restrict__ dx, int HW, int C, int64_t nvec) {
+gap_bwd_kernel(const T* __restrict__ dpooled, const T* __restrict__ mask_src,
+               T* __restrict__ dx, int HW, int C, int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int CG = C >> 3;
   const float inv = 1.f / HW;
@@ -370,14 +380,15 @@ gap_bwd_kernel(const bf16* __restrict__ dpooled, const bf16* __restrict__ mask_s
     load8(dpooled + b * C + cg * 8, v);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] *= inv;
-    grad_epilogue(v, nullptr, mask_src, (size_t)i * 8);
+    grad_epilogue(v, (const T*)nullptr, mask_src, (size_t)i * 8);
     store8(dx + i * 8, v);
   }
 }
 
+template <class T>
 __global__ void __launch_bounds__(kPT)
-grad_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ add_src,
-                    const bf16* __restrict__ mask_src, bf16* __restrict__ out, int64_t nvec) {
+grad_combine_kernel(const T* __restrict__ a, const T* __restrict__ add_src,
+                    const T* __restrict__ mask_src, T* __restrict__ out, int64_t nvec) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec;
        i += (int64_t)gridDim.x * blockDim.x) {
@@ -390,9 +401,10 @@ grad_combine_kernel(const bf16* __restrict__ a, const bf16* __restrict__ add_src
 
 // ---------------------------------------------------------------------------- input packing
 // One thread per output pixel (b, i, j): 2x2 input pixels x 3 channels -> 16 bf16.
+template <class T>
 __global__ void __launch_bounds__(kPT)
 pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
-                  const float* __restrict__ lam2, int mode, bf16* __restrict__ out, int Bin, int B,
+                  const float* __restrict__ lam2, int mode, T* __restrict__ out, int Bin, int B,
                   int H, int W, int wpad_lo, int wpad_hi, int64_t npix) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   const int H2 = H >> 1, W2 = W >> 1;
@@ -405,9 +417,10 @@ pack_input_kernel(const float* __restrict__ img, const float* __restrict__ lam1,
     const int ii = (int)(t % H2);
     const int b = (int)(t / H2);
     if (j < 0 || j >= W2) {              // physical zero padding of the W axis
-      const uint4 z = make_uint4(0, 0, 0, 0);
-      reinterpret_cast<uint4*>(out + i * 16)[0] = z;
-      reinterpret_cast<uint4*>(out + i * 16)[1] = z;
+      V8<T> z;
+      z.zero();
+      z.st(out + i * 16);
+      z.st(out + i * 16 + 8);
       continue;
     }
     int b1 = b, b2 = b;
@@ -501,10 +514,11 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
   return v;
 }
 
+template <class T>
 __global__ void __launch_bounds__(kPT)
 softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y, int B, int NC,
-                  int ld, float ls, float grad_scale, float* loss_acc, bf16* __restrict__ dlogits,
-                  float* dbias) {
+                  int ld, float ls, float grad_scale, float* __restrict__ loss_rows,
+                  float* __restrict__ g32, T* __restrict__ dlogits) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   __shared__ float sh[kPT / 32];
   const int b = blockIdx.x;
@@ -526,16 +540,36 @@ softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y,
   sy = block_reduce(sy, false, sh);
   syl = block_reduce(syl, false, sh);
   const float lse = mx + logf(se);
-  if (threadIdx.x == 0) atomicAdd(loss_acc, (lse * sy - syl) / B);
+  // per-example loss (already / B); summed in a fixed order by ce_finalize_kernel
+  if (threadIdx.x == 0) loss_rows[b] = (lse * sy - syl) / B;
   const float gs = grad_scale / B;
   for (int c = threadIdx.x; c < ld; c += kPT) {
     float g = 0.f;
     if (c < NC) {
       const float yp = yy[c] * (1.f - ls) + unif;
       g = (expf(lg[c] - lse) * sy - yp) * gs;
-      if (dbias) atomicAdd(dbias + c, g);
     }
-    dlogits[(size_t)b * ld + c] = __float2bfloat16_rn(g);
+    g32[(size_t)b * ld + c] = g;
+    store1(dlogits + (size_t)b * ld + c, g);
+  }
+}
+
+// loss_acc[0] += sum_b loss_rows[b]; dbias[c] += sum_b g32[b][c] -- one thread per column, rows in
+// order: deterministic (no atomics).  One CTA.
+__global__ void __launch_bounds__(1024)
+ce_finalize_kernel(const float* __restrict__ loss_rows, const float* __restrict__ g32, int B, int NC,
+                   int ld, float* loss_acc, float* dbias) {
+  pdl_entry();
+  for (int c = threadIdx.x; c <= NC; c += blockDim.x) {
+    if (c == NC) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += loss_rows[b];
+      loss_acc[0] += s;
+    } else if (dbias) {
+      float s = 0.f;
+      for (int b = 0; b < B; ++b) s += g32[(size_t)b * ld + c];
+      dbias[c] += s;
+    }
   }
 }
 
@@ -543,131 +577,173 @@ softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y,
 
 using namespace acnn;
 
+// Storage type of the activation tensors of a call: ACNN_BF16 (production) or ACNN_F32 (parity mode).
+#define ACNN_DTYPE_OK(dt) ((dt) == ACNN_BF16 || (dt) == ACNN_F32)
+#define ACNN_BY_DTYPE(dt, ...)      \
+  do {                              \
+    if ((dt) == ACNN_F32) {         \
+      using T = float;              \
+      __VA_ARGS__;                  \
+    } else {                        \
+      using T = bf16;               \
+      __VA_ARGS__;                  \
+    }                               \
+  } while (0)
+
+template <class T>
+static void launch_avgpool_bwd(dim3 grid, cudaStream_t st, const void* dout, void* dx,
+                               const void* add_src, const void* mask_src, int H, int W, int C, int k,
+                               int stride, int pad_lo, int Ho, int Wo, int count_pad) {
+  if (stride == 2) {
+    launch_k(avgpool_bwd_kernel<T, 2>, grid, dim3(kPT), 0, st, (const T*)dout, (T*)dx,
+             (const T*)add_src, (const T*)mask_src, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad);
+  } else if (stride == 1) {
+    launch_k(avgpool_bwd_kernel<T, 1>, grid, dim3(kPT), 0, st, (const T*)dout, (T*)dx,
+             (const T*)add_src, (const T*)mask_src, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad);
+  } else {
+    launch_k(avgpool_bwd_kernel<T, 0>, grid, dim3(kPT), 0, st, (const T*)dout, (T*)dx,
+             (const T*)add_src, (const T*)mask_src, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad);
+  }
+}
+
 extern "C" {
 
 int acnn_blurpool_fwd(const void* x, void* out, int B, int H, int W, int C, int filt, int stride,
-                      void* stream) {
-  ACNN_REQUIRE(x && out && C % 8 == 0 && filt >= 1 && filt <= 7 && stride >= 1,
-               "blurpool_fwd: bad arguments");
+                      int dtype, void* stream) {
+  ACNN_REQUIRE(x && out && C % 8 == 0 && filt >= 1 && filt <= 7 && stride >= 1 &&
+                   ACNN_DTYPE_OK(dtype), "blurpool_fwd: bad arguments");
   const int pad = (filt - 1) / 2;
   ACNN_REQUIRE(pad < H && pad < W, "blurpool_fwd: reflect pad %d >= size", pad);
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
   ACNN_REQUIRE(Ho <= 65535 && B <= 65535, "blurpool_fwd: Ho / B exceed the grid limits");
   dim3 grid(ceil_div(Wo * (C / 8), kPT), Ho, B);
-  launch_k(blurpool_fwd_kernel, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, binomial(filt), H, W, C, filt, stride, pad, Ho, Wo);
+  ACNN_BY_DTYPE(dtype, launch_k(blurpool_fwd_kernel<T>, grid, dim3(kPT), 0, (cudaStream_t)stream,
+                                (const T*)x, (T*)out, binomial(filt), H, W, C, filt, stride, pad,
+                                Ho, Wo));
   count_launch();
   return check_launch("blurpool_fwd");
 }
 
 int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
-                      int H, int W, int C, int filt, int stride, void* stream) {
-  ACNN_REQUIRE(dout && dx && C % 8 == 0 && filt >= 1 && filt <= 7 && stride >= 1,
-               "blurpool_bwd: bad arguments");
+                      int H, int W, int C, int filt, int stride, int dtype, void* stream) {
+  ACNN_REQUIRE(dout && dx && C % 8 == 0 && filt >= 1 && filt <= 7 && stride >= 1 &&
+                   ACNN_DTYPE_OK(dtype), "blurpool_bwd: bad arguments");
   const int pad = (filt - 1) / 2;
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
   ACNN_REQUIRE(H <= 65535 && B <= 65535, "blurpool_bwd: H / B exceed the grid limits");
   dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
-  launch_k(blurpool_bwd_kernel, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, binomial(filt), H,
-      W, C, filt, stride, pad, Ho, Wo);
+  ACNN_BY_DTYPE(dtype, launch_k(blurpool_bwd_kernel<T>, grid, dim3(kPT), 0, (cudaStream_t)stream,
+                                (const T*)dout, (T*)dx, (const T*)add_src, (const T*)mask_src,
+                                binomial(filt), H, W, C, filt, stride, pad, Ho, Wo));
   count_launch();
   return check_launch("blurpool_bwd");
 }
 
 int acnn_avgpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
-                     int pad_lo, int Ho, int Wo, int count_pad, void* stream) {
-  ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_fwd: bad arguments");
+                     int pad_lo, int Ho, int Wo, int count_pad, int dtype, void* stream) {
+  ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1 && ACNN_DTYPE_OK(dtype),
+               "avgpool_fwd: bad arguments");
   ACNN_REQUIRE(Ho <= 65535 && B <= 65535, "avgpool_fwd: Ho / B exceed the grid limits");
   dim3 grid(ceil_div(Wo * (C / 8), kPT), Ho, B);
-  launch_k(avgpool_fwd_kernel, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, count_pad);
+  ACNN_BY_DTYPE(dtype, launch_k(avgpool_fwd_kernel<T>, grid, dim3(kPT), 0, (cudaStream_t)stream,
+                                (const T*)x, (T*)out, H, W, C, k, stride, pad_lo, Ho, Wo,
+                                count_pad));
   count_launch();
   return check_launch("avgpool_fwd");
 }
 
 int acnn_avgpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
                      int H, int W, int C, int k, int stride, int pad_lo, int Ho, int Wo,
-                     int count_pad, void* stream) {
-  ACNN_REQUIRE(dout && dx && C % 8 == 0 && k >= 1 && stride >= 1, "avgpool_bwd: bad arguments");
+                     int count_pad, int dtype, void* stream) {
+  ACNN_REQUIRE(dout && dx && C % 8 == 0 && k >= 1 && stride >= 1 && ACNN_DTYPE_OK(dtype),
+               "avgpool_bwd: bad arguments");
   ACNN_REQUIRE(H <= 65535 && B <= 65535, "avgpool_bwd: H / B exceed the grid limits");
   dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
-  if (stride == 2) {
-    launch_k(avgpool_bwd_kernel<2>, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
-        stride, pad_lo, Ho, Wo, count_pad);
-  } else if (stride == 1) {
-    launch_k(avgpool_bwd_kernel<1>, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
-        stride, pad_lo, Ho, Wo, count_pad);
-  } else {
-    launch_k(avgpool_bwd_kernel<0>, dim3(grid), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, k,
-        stride, pad_lo, Ho, Wo, count_pad);
-  }
+  ACNN_BY_DTYPE(dtype, launch_avgpool_bwd<T>(grid, (cudaStream_t)stream, dout, dx, add_src, mask_src,
+                                             H, W, C, k, stride, pad_lo, Ho, Wo, count_pad));
   count_launch();
   return check_launch("avgpool_bwd");
 }
 
 int acnn_maxpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
-                     int pad_lo, int Ho, int Wo, void* stream) {
-  ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1, "maxpool_fwd: bad arguments");
+                     int pad_lo, int Ho, int Wo, int dtype, void* stream) {
+  ACNN_REQUIRE(x && out && C % 8 == 0 && k >= 1 && stride >= 1 && ACNN_DTYPE_OK(dtype),
+               "maxpool_fwd: bad arguments");
   const int64_t nvec = (int64_t)B * Ho * Wo * C / 8;
-  launch_k(maxpool_fwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)out, H, W, C, k, stride, pad_lo, Ho, Wo, nvec);
+  ACNN_BY_DTYPE(dtype, launch_k(maxpool_fwd_kernel<T>, dim3(grid_for(nvec)), dim3(kPT), 0,
+                                (cudaStream_t)stream, (const T*)x, (T*)out, H, W, C, k, stride,
+                                pad_lo, Ho, Wo, nvec));
   count_launch();
   return check_launch("maxpool_fwd");
 }
 
 int acnn_maxpool_bwd(const void* dout, const void* x, void* dx, const void* add_src,
                      const void* mask_src, int B, int H, int W, int C, int k, int stride,
-                     int pad_lo, int Ho, int Wo, void* stream) {
-  ACNN_REQUIRE(dout && x && dx && C % 8 == 0, "maxpool_bwd: bad arguments");
+                     int pad_lo, int Ho, int Wo, int dtype, void* stream) {
+  ACNN_REQUIRE(dout && x && dx && C % 8 == 0 && ACNN_DTYPE_OK(dtype), "maxpool_bwd: bad arguments");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  launch_k(maxpool_bwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (const bf16*)x, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H,
-      W, C, k, stride, pad_lo, Ho, Wo, nvec);
+  ACNN_BY_DTYPE(dtype, launch_k(maxpool_bwd_kernel<T>, dim3(grid_for(nvec)), dim3(kPT), 0,
+                                (cudaStream_t)stream, (const T*)dout, (const T*)x, (T*)dx,
+                                (const T*)add_src, (const T*)mask_src, H, W, C, k, stride, pad_lo,
+                                Ho, Wo, nvec));
   count_launch();
   return check_launch("maxpool_bwd");
 }
 
 int acnn_upsample2x_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src,
-                        int B, int H, int W, int C, void* stream) {
-  ACNN_REQUIRE(dout && dx && C % 8 == 0, "upsample2x_bwd: bad arguments");
+                        int B, int H, int W, int C, int dtype, void* stream) {
+  ACNN_REQUIRE(dout && dx && C % 8 == 0 && ACNN_DTYPE_OK(dtype), "upsample2x_bwd: bad arguments");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  launch_k(upsample2x_bwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dout, (bf16*)dx, (const bf16*)add_src, (const bf16*)mask_src, H, W, C, nvec);
+  ACNN_BY_DTYPE(dtype, launch_k(upsample2x_bwd_kernel<T>, dim3(grid_for(nvec)), dim3(kPT), 0,
+                                (cudaStream_t)stream, (const T*)dout, (T*)dx, (const T*)add_src,
+                                (const T*)mask_src, H, W, C, nvec));
   count_launch();
   return check_launch("upsample2x_bwd");
 }
 
 int acnn_zero_insert2x(const void* dy, void* out, int B, int Ho, int Wo, int H, int W, int C,
-                       void* stream) {
-  ACNN_REQUIRE(dy && out && C % 8 == 0, "zero_insert2x: bad arguments");
+                       int dtype, void* stream) {
+  ACNN_REQUIRE(dy && out && C % 8 == 0 && ACNN_DTYPE_OK(dtype), "zero_insert2x: bad arguments");
   const int64_t nvec = (int64_t)B * H * W * C / 8;
-  launch_k(zero_insert2x_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dy, (bf16*)out, Ho, Wo, H, W, C, nvec);
+  ACNN_BY_DTYPE(dtype, launch_k(zero_insert2x_kernel<T>, dim3(grid_for(nvec)), dim3(kPT), 0,
+                                (cudaStream_t)stream, (const T*)dy, (T*)out, Ho, Wo, H, W, C, nvec));
   count_launch();
   return check_launch("zero_insert2x");
 }
 
 int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int HW, int C,
-                 void* stream) {
-  ACNN_REQUIRE(dpooled && dx && C % 8 == 0, "gap_bwd: bad arguments");
+                 int dtype, void* stream) {
+  ACNN_REQUIRE(dpooled && dx && C % 8 == 0 && ACNN_DTYPE_OK(dtype), "gap_bwd: bad arguments");
   const int64_t nvec = (int64_t)B * HW * C / 8;
-  launch_k(gap_bwd_kernel, dim3(grid_for(nvec)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)dpooled, (const bf16*)mask_src, (bf16*)dx, HW, C, nvec);
+  ACNN_BY_DTYPE(dtype, launch_k(gap_bwd_kernel<T>, dim3(grid_for(nvec)), dim3(kPT), 0,
+                                (cudaStream_t)stream, (const T*)dpooled, (const T*)mask_src, (T*)dx,
+                                HW, C, nvec));
   count_launch();
   return check_launch("gap_bwd");
 }
 
 int acnn_grad_combine(const void* a, const void* add_src, const void* mask_src, void* out,
-                      int64_t n, void* stream) {
-  ACNN_REQUIRE(a && out && n % 8 == 0, "grad_combine: bad arguments");
-  launch_k(grad_combine_kernel, dim3(grid_for(n / 8)), dim3(kPT), 0, (cudaStream_t)stream, (const bf16*)a, (const bf16*)add_src, (const bf16*)mask_src, (bf16*)out, n / 8);
+                      int64_t n, int dtype, void* stream) {
+  ACNN_REQUIRE(a && out && n % 8 == 0 && ACNN_DTYPE_OK(dtype), "grad_combine: bad arguments");
+  ACNN_BY_DTYPE(dtype, launch_k(grad_combine_kernel<T>, dim3(grid_for(n / 8)), dim3(kPT), 0,
+                                (cudaStream_t)stream, (const T*)a, (const T*)add_src,
+                                (const T*)mask_src, (T*)out, n / 8));
   count_launch();
   return check_launch("grad_combine");
 }
 
 int acnn_pack_input(const float* images, const float* lam1, const float* lam2, int mode, void* out,
-                    int Bin, int H, int W, int wpad_lo, int wpad_hi, void* stream) {
-  ACNN_REQUIRE(images && out && H % 2 == 0 && W % 2 == 0 && mode >= 0 && mode <= 2,
-               "pack_input: bad arguments");
+                    int Bin, int H, int W, int wpad_lo, int wpad_hi, int dtype, void* stream) {
+  ACNN_REQUIRE(images && out && H % 2 == 0 && W % 2 == 0 && mode >= 0 && mode <= 2 &&
+                   ACNN_DTYPE_OK(dtype), "pack_input: bad arguments");
   ACNN_REQUIRE(mode == 0 || (lam1 && Bin % 2 == 0), "pack_input: mixup needs lam1 and even batch");
   ACNN_REQUIRE(mode != 2 || lam2, "pack_input: mixup type 2 needs lam2");
   const int B = mode == 1 ? Bin / 2 : Bin;
   ACNN_REQUIRE(wpad_lo >= 0 && wpad_hi >= 0, "pack_input: negative padding");
   const int64_t npix = (int64_t)B * (H / 2) * (W / 2 + wpad_lo + wpad_hi);
-  launch_k(pack_input_kernel, dim3(grid_for(npix)), dim3(kPT), 0, (cudaStream_t)stream, images, lam1, lam2, mode, (bf16*)out, Bin, B, H, W, wpad_lo, wpad_hi, npix);
+  ACNN_BY_DTYPE(dtype, launch_k(pack_input_kernel<T>, dim3(grid_for(npix)), dim3(kPT), 0,
+                                (cudaStream_t)stream, images, lam1, lam2, mode, (T*)out, Bin, B, H,
+                                W, wpad_lo, wpad_hi, npix));
   count_launch();
   return check_launch("pack_input");
 }
@@ -686,14 +762,21 @@ int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2,
 
 int acnn_softmax_ce(const float* logits, const float* y, int B, int NC, int ld,
                     float label_smoothing, float grad_scale, float* loss_acc, void* dlogits,
-                    float* dbias, void* stream) {
-  ACNN_REQUIRE(logits && y && loss_acc && dlogits && NC <= ld && B > 0,
-               "softmax_ce: bad arguments");
-  launch_k(softmax_ce_kernel, dim3(B), dim3(kPT), 0, (cudaStream_t)stream, logits, y, B, NC, ld, label_smoothing,
-                                                         grad_scale, loss_acc, (bf16*)dlogits,
-                                                         dbias);
+                    float* dbias, float* work, int dtype, void* stream) {
+  ACNN_REQUIRE(logits && y && loss_acc && dlogits && work && NC <= ld && B > 0 &&
+                   ACNN_DTYPE_OK(dtype), "softmax_ce: bad arguments");
+  float* loss_rows = work;                     // [B]
+  float* g32 = work + ((B + 31) / 32) * 32;    // [B][ld]
+  ACNN_BY_DTYPE(dtype, launch_k(softmax_ce_kernel<T>, dim3(B), dim3(kPT), 0, (cudaStream_t)stream,
+                                logits, y, B, NC, ld, label_smoothing, grad_scale, loss_rows, g32,
+                                (T*)dlogits));
   count_launch();
-  return check_launch("softmax_ce");
+  int rc = check_launch("softmax_ce");
+  if (rc) return rc;
+  launch_k(ce_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream,
+           (const float*)loss_rows, (const float*)g32, B, NC, ld, loss_acc, dbias);
+  count_launch();
+  return check_launch("ce_finalize");
 }
 
 }  // extern "C"

@@ -78,8 +78,9 @@ sgemm_acc_kernel(const float* __restrict__ A, const float* __restrict__ B, float
 }
 
 // C (+)= A*B with split-K sized so that ~2 CTAs per SM are in flight.
+// det: no split-K -- every element of C receives exactly one add (bit-reproducible).
 static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, int sAm, int sAk,
-                 int sBk, int sBn, bool zero_c, cudaStream_t s) {
+                 int sBk, int sBn, bool zero_c, int det, cudaStream_t s) {
   if (zero_c) {
     cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), s);
     if (e != cudaSuccess) {
@@ -91,7 +92,7 @@ static int sgemm(const float* A, const float* B, float* C, int M, int N, int K, 
   int splits = ceil_div(296, tiles);
   const int max_splits = ceil_div(K, 2 * kTK);
   if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  if (splits < 1 || det) splits = 1;
   int kps = ceil_div(ceil_div(K, splits), kTK) * kTK;
   splits = ceil_div(K, kps);
   dim3 grid(ceil_div(N, kTN), ceil_div(M, kTM), splits);
@@ -233,18 +234,18 @@ extern "C" {
 int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const float* beta,
                    float* moving_mean, float* moving_var, float momentum, float eps, int training,
                    const float* w2, float* zpre, float* bnstat, float* z, float* att,
-                   float* scratch, int B, int f, int d, void* stream) {
+                   float* scratch, int B, int f, int d, int deterministic, void* stream) {
   ACNN_REQUIRE(s && w1 && gamma && beta && moving_mean && moving_var && w2 && zpre && bnstat && z &&
                    att && scratch, "sk_fc_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   // zpre[B,d] = s[B,f] * W1[d,f]^T
-  int rc = sgemm(s, w1, zpre, B, d, f, f, 1, 1, f, true, st);
+  int rc = sgemm(s, w1, zpre, B, d, f, f, 1, 1, f, true, deterministic, st);
   if (rc) return rc;
   launch_k(bn_batch_relu_fwd_kernel, dim3(ceil_div(d, kFT / 32)), dim3(kFT), 0, st, zpre, gamma, beta, moving_mean, moving_var, momentum, eps, training, z, bnstat, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_fwd"))) return rc;
   // a[B,2f] = z[B,d] * W2[2f,d]^T
-  if ((rc = sgemm(z, w2, scratch, B, 2 * f, d, d, 1, 1, d, true, st))) return rc;
+  if ((rc = sgemm(z, w2, scratch, B, 2 * f, d, d, 1, 1, d, true, deterministic, st))) return rc;
   launch_k(sk_gate_fwd_kernel, dim3((int)ceil_div64((int64_t)B * f, 256)), dim3(256), 0, st, scratch, att, B, f);
   count_launch();
   return check_launch("sk_gate_fwd");
@@ -253,7 +254,7 @@ int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const fl
 int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const float* zpre,
                    const float* bnstat, const float* gamma, const float* s, const float* w1,
                    const float* w2, float* dw1, float* dw2, float* dgamma, float* dbeta, float* ds,
-                   float* scratch, int B, int f, int d, void* stream) {
+                   float* scratch, int B, int f, int d, int deterministic, void* stream) {
   ACNN_REQUIRE(dA && att && z && zpre && bnstat && gamma && s && w1 && w2 && dw1 && dw2 && dgamma &&
                    dbeta && ds && scratch, "sk_fc_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -264,34 +265,35 @@ int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const floa
   int rc = check_launch("sk_gate_bwd");
   if (rc) return rc;
   // dW2[2f,d] += da^T[2f,B] * z[B,d]
-  if ((rc = sgemm(da, z, dw2, 2 * f, d, B, 1, 2 * f, d, 1, false, st))) return rc;
+  if ((rc = sgemm(da, z, dw2, 2 * f, d, B, 1, 2 * f, d, 1, false, deterministic, st))) return rc;
   // dz[B,d] = da[B,2f] * W2[2f,d]
-  if ((rc = sgemm(da, w2, dz, B, d, 2 * f, 2 * f, 1, d, 1, true, st))) return rc;
+  if ((rc = sgemm(da, w2, dz, B, d, 2 * f, 2 * f, 1, d, 1, true, deterministic, st))) return rc;
   launch_k(bn_batch_relu_bwd_kernel, dim3(ceil_div(d, kFT / 32)), dim3(kFT), 0, st, dz, z, zpre, bnstat, gamma,
                                                                   dgamma, dbeta, B, d);
   count_launch();
   if ((rc = check_launch("sk bn_batch_relu_bwd"))) return rc;
   // dW1[d,f] += dzpre^T[d,B] * s[B,f]
-  if ((rc = sgemm(dz, s, dw1, d, f, B, 1, d, f, 1, false, st))) return rc;
+  if ((rc = sgemm(dz, s, dw1, d, f, B, 1, d, f, 1, false, deterministic, st))) return rc;
   // ds[B,f] = dzpre[B,d] * W1[d,f]
-  return sgemm(dz, w1, ds, B, f, d, d, 1, f, 1, true, st);
+  return sgemm(dz, w1, ds, B, f, d, d, 1, f, 1, true, deterministic, st);
 }
 
 int acnn_se_fc_fwd(const float* q, const float* w1, const float* w2, float* h, float* e, int B,
-                   int C, int r, void* stream) {
+                   int C, int r, int deterministic, void* stream) {
   ACNN_REQUIRE(q && w1 && w2 && h && e, "se_fc_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   // h = relu(q[B,C] * W1[r,C]^T) ; e = sigmoid(h[B,r] * W2[C,r]^T)
-  int rc = sgemm(q, w1, h, B, r, C, C, 1, 1, C, true, st);
+  int rc = sgemm(q, w1, h, B, r, C, C, 1, 1, C, true, deterministic, st);
   if (rc) return rc;
   if ((rc = ew(h, nullptr, h, (int64_t)B * r, 1, 0.f, st))) return rc;
-  if ((rc = sgemm(h, w2, e, B, C, r, r, 1, 1, r, true, st))) return rc;
+  if ((rc = sgemm(h, w2, e, B, C, r, r, 1, 1, r, true, deterministic, st))) return rc;
   return ew(e, nullptr, e, (int64_t)B * C, 2, 0.f, st);
 }
 
 int acnn_se_fc_bwd(const float* de, const float* e, const float* h, const float* q,
                    const float* w1, const float* w2, float* dw1, float* dw2, float* dq,
-                   float* scratch, int B, int C, int r, int HW, void* stream) {
+                   float* scratch, int B, int C, int r, int HW, int deterministic,
+                   void* stream) {
   ACNN_REQUIRE(de && e && h && q && w1 && w2 && dw1 && dw2 && dq && scratch,
                "se_fc_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -299,11 +301,11 @@ int acnn_se_fc_bwd(const float* de, const float* e, const float* h, const float*
   float* dh = scratch + (size_t)B * C;      // [B][r]
   int rc = ew(de, e, da2, (int64_t)B * C, 4, 0.f, st);
   if (rc) return rc;
-  if ((rc = sgemm(da2, h, dw2, C, r, B, 1, C, r, 1, false, st))) return rc;    // dW2[C,r]
-  if ((rc = sgemm(da2, w2, dh, B, r, C, C, 1, r, 1, true, st))) return rc;     // dh = da2 * W2
+  if ((rc = sgemm(da2, h, dw2, C, r, B, 1, C, r, 1, false, deterministic, st))) return rc;    // dW2[C,r]
+  if ((rc = sgemm(da2, w2, dh, B, r, C, C, 1, r, 1, true, deterministic, st))) return rc;     // dh = da2 * W2
   if ((rc = ew(dh, h, dh, (int64_t)B * r, 3, 0.f, st))) return rc;
-  if ((rc = sgemm(dh, q, dw1, r, C, B, 1, r, C, 1, false, st))) return rc;     // dW1[r,C]
-  if ((rc = sgemm(dh, w1, dq, B, C, r, r, 1, C, 1, true, st))) return rc;      // dq = da1 * W1
+  if ((rc = sgemm(dh, q, dw1, r, C, B, 1, r, C, 1, false, deterministic, st))) return rc;     // dW1[r,C]
+  if ((rc = sgemm(dh, w1, dq, B, C, r, r, 1, C, 1, true, deterministic, st))) return rc;      // dq = da1 * W1
   return ew(dq, nullptr, dq, (int64_t)B * C, 5, 1.f / HW, st);
 }
 

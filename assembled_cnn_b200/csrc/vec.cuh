@@ -57,9 +57,64 @@ __device__ __forceinline__ void storef8(float* p, const float (&f)[8]) {
   reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
 }
 
+// fp32 activation storage (the parity mode, acnn.h ACNN_F32): the same 8-element accessors on float.
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) { loadf8(p, f); }
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) { storef8(p, f); }
+
+__device__ __forceinline__ void store1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ float load1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float load1(const float* p) { return *p; }
+
+// Raw 8-element vector of an activation tensor: loads can be issued back to back (batched ahead
+// of the math) and unpacked later.  V8<bf16> is one 16-byte register quad, V8<float> two.
+template <class T>
+struct V8;
+template <>
+struct V8<bf16> {
+  uint4 r;
+  __device__ __forceinline__ void ld(const bf16* p) { r = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void lds(const uint8_t* base, int elem) {
+    r = *reinterpret_cast<const uint4*>(base + (size_t)elem * 2);
+  }
+  __device__ __forceinline__ void zero() { r = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void unpack(float (&f)[8]) const { unpack8(r, f); }
+  __device__ __forceinline__ void st(bf16* p) const { *reinterpret_cast<uint4*>(p) = r; }
+};
+template <>
+struct V8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+  __device__ __forceinline__ void lds(const uint8_t* base, int elem) {
+    a = *reinterpret_cast<const float4*>(base + (size_t)elem * 4);
+    b = *reinterpret_cast<const float4*>(base + (size_t)elem * 4 + 16);
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void unpack(float (&f)[8]) const {
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
+  __device__ __forceinline__ void st(float* p) const {
+    reinterpret_cast<float4*>(p)[0] = a;
+    reinterpret_cast<float4*>(p)[1] = b;
+  }
+};
+
+// 8 elements at element offset `elem` of a shared-memory staging area holding T.
+template <class T>
+__device__ __forceinline__ void lds8(const uint8_t* base, int elem, float (&f)[8]) {
+  V8<T> v;
+  v.lds(base, elem);
+  v.unpack(f);
+}
+
 // Optional gradient epilogue shared by every backward kernel: (+ add_src) then (* (mask_src > 0)).
-__device__ __forceinline__ void grad_epilogue(float (&v)[8], const bf16* add_src,
-                                              const bf16* mask_src, size_t off) {
+template <class T>
+__device__ __forceinline__ void grad_epilogue(float (&v)[8], const T* add_src,
+                                              const T* mask_src, size_t off) {
   if (add_src) {
     float a[8];
     load8(add_src + off, a);

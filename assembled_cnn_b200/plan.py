@@ -25,6 +25,11 @@ BLOCK_SIZES = {   # functions/model_fns.py:113-127
     2: {50: [3, 4, 6, 3], 101: [4, 8, 18, 3], 152: [5, 12, 30, 3]},
 }
 ALIGN = 256   # every tensor of a flat buffer starts at a multiple of 256 elements
+# capacities (rows) of the per-CTA partial-sum buffers the reductions write (include/acnn.h:
+# acnn_conv_stats_parts / acnn_bn_bwd_reduce_parts / acnn_sk_bn_bwd_reduce_parts give the real counts)
+STATS_PARTS_CAP = 148
+BWD_PARTS_CAP = 296
+SGD_SCRATCH = 148 * 8 + 1
 
 
 def _round_up(n, a=ALIGN):
@@ -113,7 +118,8 @@ class BN:
     mm: str
     mv: str
     count: int
-    stats: Slot | None      # [sum | sumsq], zeroed each step (training only)
+    stats: Slot | None      # bf16 mode: [parts][sum | sumsq] partial rows written by the conv
+                            # epilogue; fp32 mode: [mean | var] from bn_stats (training only)
     work: Slot              # [scale | shift | mean | rstd]
 
 
@@ -192,8 +198,15 @@ class Plan:
 class PlanBuilder:
     def __init__(self, cfg: ModelConfig, batch: int, height: int = 224, width: int = 224, *,
                  training: bool = True, mixup_type: int = 0, label_smoothing: float = 0.0,
-                 with_loss: bool = True):
+                 with_loss: bool = True, dtype: str = "bf16"):
         cfg.validate()
+        if dtype not in ("bf16", "fp32"):
+            raise ValueError("dtype must be one of: ('bf16', 'fp32')")
+        # fp32 = the reference's default dtype (nets/resnet_model.py:30-33): fp32 activation storage,
+        # conv GEMMs on 3-way bf16-split operands, deterministic reductions -- the parity mode
+        self.fp32 = dtype == "fp32"
+        self.adt = "f32" if self.fp32 else "bf16"
+        self._planes = {}
         if height % 32 or width % 32:
             raise ValueError("input size must be a multiple of 32 (got %dx%d)" % (height, width))
         if mixup_type not in (0, 1, 2):
@@ -213,7 +226,7 @@ class PlanBuilder:
         p.meta.update(batch=batch, height=height, width=width, training=training,
                       mixup_type=self.mixup_type, label_smoothing=label_smoothing,
                       num_classes=cfg.num_classes, ld_logits=_round_up(cfg.num_classes, 128),
-                      bn_momentum=cfg.bn_momentum,
+                      bn_momentum=cfg.bn_momentum, dtype=dtype,
                       input_batch=batch * 2 if self.mixup_type == 1 else batch)
         self._build(height, width)
 
@@ -241,7 +254,8 @@ class PlanBuilder:
         return "/".join(self._scope + [name])
 
     # ---------------------------------------------------------------- allocation helpers
-    def tensor(self, base, shape, dtype="bf16", relu=False):
+    def tensor(self, base, shape, dtype=None, relu=False):
+        dtype = dtype or self.adt
         self._tid += 1
         name = "%s#%d" % (base, self._tid)
         t = Tensor(name, tuple(shape), dtype, relu)
@@ -282,6 +296,22 @@ class PlanBuilder:
     def emit(self, kind, **a):
         self.ops.append(Op(kind, a))
 
+    def planes(self, name):
+        """fp32 mode: the (hi, mid, lo) bf16 operand planes of a GEMM operand tensor, split once
+        (op `split3`) right before its first consumer and reused by later ones (fprop + wgrad)."""
+        if not self.fp32:
+            return None
+        pl = self._planes.get(name)
+        if pl is None:
+            t = self.plan.tensors[name]
+            n = 1
+            for d in t.shape:
+                n *= d
+            pt = self.tensor("planes", (3,) + tuple(t.shape), "bf16")
+            self.emit("split3", src=name, dst=pt.name, n=n)
+            self._planes[name] = pl = pt.name
+        return pl
+
     # ---------------------------------------------------------------- gradient accumulation
     def use(self, t: Tensor):
         t.consumers += 1
@@ -292,7 +322,7 @@ class PlanBuilder:
         t.contribs += 1
         last = t.contribs == t.consumers
         assert t.contribs <= t.consumers, t.name
-        out = self.tensor("d_" + t.name.split("#")[0], t.shape, "bf16")
+        out = self.tensor("d_" + t.name.split("#")[0], t.shape)
         emit_fn(out.name, t.grad, t.name if (last and t.relu) else None)
         t.grad = out.name
 
@@ -303,7 +333,7 @@ class PlanBuilder:
         if t.grad is None and not (last and t.relu):
             t.grad = buf
             return
-        out = self.tensor("d_" + t.name.split("#")[0], t.shape, "bf16")
+        out = self.tensor("d_" + t.name.split("#")[0], t.shape)
         self.emit("grad_combine", a=buf, add_src=t.grad, mask_src=t.name if (last and t.relu) else None,
                   out=out.name, shape=t.shape)
         t.grad = out.name
@@ -327,8 +357,10 @@ class PlanBuilder:
         mm = self._param(self._full(layer + "/moving_mean"), (C,), "moving_mean", (C,), trainable=False)
         mv = self._param(self._full(layer + "/moving_variance"), (C,), "moving_variance", (C,),
                          trainable=False)
-        bn = BN(C, g.name, b.name, mm.name, mv.name, count,
-                self.slot("zero", 2 * C) if self.training else None, self.slot("work", 4 * C))
+        stats = None
+        if self.training:
+            stats = self.slot("work", 2 * C if self.fp32 else STATS_PARTS_CAP * 2 * C)
+        bn = BN(C, g.name, b.name, mm.name, mv.name, count, stats, self.slot("work", 4 * C))
         self.plan.bns.append(bn)
         return bn
 
@@ -342,13 +374,24 @@ class PlanBuilder:
                         (filters, k, k, Cin), decay=True, need_dgrad=need_dgrad and self.training)
         y = self.tensor("y", (B, g.Ho, g.Wo, filters))
         bn = self.bn_layer(filters, B * g.Ho * g.Wo, zero_gamma) if with_bn else None
-        self.emit("conv", x=x.name, w=w.name, y=y.name, geom=g,
-                  stats=bn.stats if (bn and self.training) else None, bias=None, out_f32=False)
+        self.emit("conv", x=x.name, xp=self.planes(x.name), w=w.name, y=y.name, geom=g,
+                  stats=bn.stats if (bn and self.training and not self.fp32) else None, bias=None,
+                  out_f32=False)
         if bn:
-            self.emit("bn_finalize", bn=bn)
+            self.emit_bn_finalize(bn, y, g)
         if need_dgrad:
             self.use(x)
         return ConvOut(x, y, g, w.name, bn)
+
+    def emit_bn_finalize(self, bn: BN, y: Tensor, geom: Geom, x_wpad=None):
+        """Batch statistics -> scale / shift / mean / rstd (+ moving statistics).  bf16 mode: the
+        conv epilogue left partial (sum, sumsq) rows (stats_mode 0); fp32 mode: a separate two-pass
+        kernel computes mean / variance of the fp32 conv output (stats_mode 1)."""
+        mode = 0
+        if self.training and self.fp32:
+            self.emit("bn_stats", x=y.name, bn=bn, M=bn.count, C=bn.C)
+            mode = 1
+        self.emit("bn_finalize", bn=bn, stats_mode=mode, geom=geom, x_wpad=x_wpad)
 
     @staticmethod
     def stem_s2d_taps(k):
@@ -377,10 +420,11 @@ class PlanBuilder:
         self.emit("s2d_weight_pack", w=w.name, w2=stem["w2"].name, cout=filters, **{
             "k": k, "pad": p, "k2": k2, "pad2": lo2})
         stem["x_wpad"] = (lo2, hi2)
-        self.emit("conv", x=x0.name, w=stem["w2"].name, y=y.name, geom=g,
-                  stats=bn.stats if self.training else None, bias=None, out_f32=False,
-                  w_is_tensor=True, x_wpad=(lo2, hi2))
-        self.emit("bn_finalize", bn=bn)
+        self.emit("conv", x=x0.name, xp=self.planes(x0.name), w=stem["w2"].name,
+                  wp=self.planes(stem["w2"].name), y=y.name, geom=g,
+                  stats=bn.stats if (self.training and not self.fp32) else None, bias=None,
+                  out_f32=False, w_is_tensor=True, x_wpad=(lo2, hi2))
+        self.emit_bn_finalize(bn, y, g, (lo2, hi2))
         return ConvOut(x0, y, g, w.name, bn, stem)
 
     def bn_act(self, co: ConvOut, *, relu, b=None, b_mode=0, gate=None, name="u") -> Tensor:
@@ -395,7 +439,7 @@ class PlanBuilder:
     # -- backward helpers ----------------------------------------------------------------------
     def bn_backward(self, co: ConvOut, g: str, gate=None, addbc=None) -> str:
         bn, y = co.bn, co.y
-        sums = self.slot("zero", 2 * bn.C)
+        sums = self.slot("work", BWD_PARTS_CAP * 2 * bn.C)   # per-CTA partial rows
         coef = self.slot("work", 3 * bn.C)
         dy = self.tensor("dy", y.shape)
         self.emit("bn_bwd_reduce", g=g, y=y.name, bn=bn, gate=gate, addbc=addbc, sums=sums,
@@ -407,18 +451,20 @@ class PlanBuilder:
 
     def conv_backward(self, co: ConvOut, dy: str, need_dgrad=True):
         g = co.geom
+        dyp = self.planes(dy)
         if co.stem is not None:
-            self.emit("conv_wgrad", x=co.x.name, dy=dy, geom=g, dw_slot=co.stem["dw2"],
-                      x_wpad=co.stem["x_wpad"])
+            self.emit("conv_wgrad", x=co.x.name, xp=self.planes(co.x.name), dy=dy, dyp=dyp, geom=g,
+                      dw_slot=co.stem["dw2"], x_wpad=co.stem["x_wpad"])
             self.emit("s2d_wgrad_unpack", dw2=co.stem["dw2"], w=co.w, cout=g.Cout, k=co.stem["k"],
                       pad=co.stem["pad"], k2=co.stem["k2"], pad2=co.stem["pad2"])
             return
-        self.emit("conv_wgrad", x=co.x.name, dy=dy, geom=g, w=co.w)
+        self.emit("conv_wgrad", x=co.x.name, xp=self.planes(co.x.name), dy=dy, dyp=dyp, geom=g,
+                  w=co.w)
         if not need_dgrad:
             return
         if g.stride == 1:
-            self.contribute(co.x, lambda out, add, mask: self.emit(
-                "conv_dgrad", dy=dy, w=co.w, dx=out, geom=g, add_src=add, mask_src=mask))
+            self.contribute(co.x, lambda out, add, mask: self.emit_dgrad(
+                dy, co.w, out, g, add, mask))
         else:
             assert g.stride == 2
             dyz = self.tensor("dyz", (g.B, g.H, g.W, g.Cout))
@@ -426,8 +472,22 @@ class PlanBuilder:
                       C=g.Cout)
             g1 = Geom(g.B, g.H, g.W, g.Cin, g.Cout, g.kh, g.kw, 1, g.pad_h_lo,
                       g.kh - 1 - g.pad_h_lo, g.pad_w_lo, g.kw - 1 - g.pad_w_lo)
-            self.contribute(co.x, lambda out, add, mask: self.emit(
-                "conv_dgrad", dy=dyz.name, w=co.w, dx=out, geom=g1, add_src=add, mask_src=mask))
+            self.contribute(co.x, lambda out, add, mask: self.emit_dgrad(
+                dyz.name, co.w, out, g1, add, mask))
+
+    def emit_dgrad(self, dy, w, out, g, add, mask):
+        """dx = conv_transpose(dy) (+ add_src) (* relu mask).  bf16 mode fuses the accumulate / mask
+        into the GEMM epilogue; fp32 mode (fp32 output straight from TMEM) runs them as one extra
+        elementwise pass."""
+        if self.fp32 and (add is not None or mask is not None):
+            shape = self.plan.tensors[out].shape
+            tmp = self.tensor("dx_raw", shape)
+            self.emit("conv_dgrad", dy=dy, dyp=self.planes(dy), w=w, dx=tmp.name, geom=g,
+                      add_src=None, mask_src=None)
+            self.emit("grad_combine", a=tmp.name, add_src=add, mask_src=mask, out=out, shape=shape)
+        else:
+            self.emit("conv_dgrad", dy=dy, dyp=self.planes(dy), w=w, dx=out, geom=g, add_src=add,
+                      mask_src=mask)
 
     # -- composite modules -----------------------------------------------------------------------
     def cbr(self, x: Tensor, filters, k, stride, need_dgrad=True) -> Tensor:
@@ -472,7 +532,7 @@ class PlanBuilder:
             gv = self.grad_of(v)
             dA = self.slot("work", B * f)
             ds = self.slot("work", B * f)
-            sums = self.slot("zero", 4 * f)
+            sums = self.slot("work", (BWD_PARTS_CAP + B) * 4 * f)   # per-CTA partial rows
             coef = self.slot("work", 6 * f)
             dy = self.tensor("dy", co.y.shape)
             self.emit("sk_bwd_gate", dv=gv, y=co.y.name, bn=co.bn, dA=dA, **dims)
@@ -716,8 +776,8 @@ class PlanBuilder:
         bk = self._param("resnet_model/dense/bias", (nc,), "dense_bias", (ld,), decay=True)
         logits = self.tensor("logits", (B, ld), "f32")
         gd = Geom(B, 1, 1, Cx, ld, 1, 1, 1, 0, 0, 0, 0)
-        self.emit("conv", x=pooled.name, w=wk.name, y=logits.name, geom=gd, stats=None, bias=bk.name,
-                  out_f32=True)
+        self.emit("conv", x=pooled.name, xp=self.planes(pooled.name), w=wk.name, y=logits.name,
+                  geom=gd, stats=None, bias=bk.name, out_f32=True)
         meta.update(logits=logits.name, pooled=pooled.name, feature_shape=x.shape)
         if not self.with_loss:
             return
@@ -731,16 +791,18 @@ class PlanBuilder:
         meta.update(labels=labels.name, ysoft=ysoft.name, loss=loss)
         self.emit("softmax_ce", logits=logits.name, y=ysoft.name, B=B, NC=nc, ld=ld,
                   label_smoothing=meta["label_smoothing"], loss=loss, dlogits=dlogits.name,
-                  dbias=bk.name if self.training else None)
+                  dbias=bk.name if self.training else None,
+                  work=self.slot("work", _round_up(B, 32) + B * ld))
         if not self.training:
             return
 
         # ---------------- backward ----------------
         self.ops = p.backward
-        self.emit("conv_wgrad", x=pooled.name, dy=dlogits.name, geom=gd, w=wk.name)
+        self.emit("conv_wgrad", x=pooled.name, xp=self.planes(pooled.name), dy=dlogits.name,
+                  dyp=self.planes(dlogits.name), geom=gd, w=wk.name)
         dpooled = self.tensor("dpooled", (B, Cx))
-        self.emit("conv_dgrad", dy=dlogits.name, w=wk.name, dx=dpooled.name, geom=gd, add_src=None,
-                  mask_src=None)
+        self.emit("conv_dgrad", dy=dlogits.name, dyp=self.planes(dlogits.name), w=wk.name,
+                  dx=dpooled.name, geom=gd, add_src=None, mask_src=None)
 
         def gap_bwd(out, add, mask):
             assert add is None
@@ -750,7 +812,7 @@ class PlanBuilder:
             fn()
         # ---------------- update ----------------
         self.ops = p.update
-        self.emit("sgd", loss=loss)
+        self.emit("sgd", loss=loss, scratch=self.slot("work", SGD_SCRATCH))
         for t in p.tensors.values():
             assert t.contribs == t.consumers or t.name == x0.name, (t.name, t.contribs, t.consumers)
 
@@ -781,9 +843,9 @@ class PlanBuilder:
         """BN created after a with_bn=False conv: add the statistics to the conv op, finalize."""
         for op in reversed(self.ops):
             if op.kind == "conv" and op.y == co.y.name:
-                op.a["stats"] = co.bn.stats if self.training else None
+                op.a["stats"] = co.bn.stats if (self.training and not self.fp32) else None
                 break
-        self.emit("bn_finalize", bn=co.bn)
+        self.emit_bn_finalize(co.bn, co.y, co.geom)
 
 
 def build_plan(cfg: ModelConfig, batch: int, height: int = 224, width: int = 224, **kw) -> Plan:

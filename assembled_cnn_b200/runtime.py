@@ -17,7 +17,8 @@ _TORCH_DTYPE = {"bf16": torch.bfloat16, "f32": torch.float32, "i32": torch.int32
 
 
 class Runtime:
-    def __init__(self, plan: Plan, device="cuda:0", eps: float = 1e-5, share: "Runtime | None" = None):
+    def __init__(self, plan: Plan, device="cuda:0", eps: float = 1e-5, share: "Runtime | None" = None,
+                 deterministic: "bool | None" = None):
         if not torch.cuda.is_available():
             raise _lib.AcnnError("assembled_cnn_b200.Runtime needs a CUDA device (sm_100a); "
                                  "there is no CPU fallback")
@@ -28,16 +29,25 @@ class Runtime:
         self.eps = eps
         self.bn_momentum = plan.meta.get("bn_momentum", 0.997)
         self.training = plan.meta["training"]
+        # fp32 plan = parity mode: fp32 activations, 3-plane GEMM operands, deterministic reductions
+        self.fp32 = plan.meta.get("dtype", "bf16") == "fp32"
+        self.adt = 1 if self.fp32 else 0               # ACNN_F32 / ACNN_BF16
+        self.planes = 3 if self.fp32 else 1
+        # deterministic: also the split-K of wgrad and of the small SK / SE GEMMs is disabled, so two
+        # runs are bit-identical (every other reduction of the library is ordered in both modes)
+        self.det = int(self.fp32 if deterministic is None else bool(deterministic))
         f32 = dict(dtype=torch.float32, device=self.dev)
         if share is not None:
             # same model, another batch shape / mode: the variables are shared, not copied
-            if share.plan.param_elems != plan.param_elems or share.plan.state_elems != plan.state_elems:
+            if share.plan.param_elems != plan.param_elems or share.plan.state_elems != plan.state_elems \
+                    or share.fp32 != self.fp32:
                 raise ValueError("Runtime(share=...): parameter layouts differ")
             self.params, self.state, self.w_fprop = share.params, share.state, share.w_fprop
         else:
             self.params = torch.zeros(plan.param_elems, **f32)
             self.state = torch.zeros(max(plan.state_elems, 1), **f32)
-            self.w_fprop = torch.zeros(plan.param_elems, dtype=torch.bfloat16, device=self.dev)
+            self.w_fprop = torch.zeros(self.planes * plan.param_elems, dtype=torch.bfloat16,
+                                       device=self.dev)
         self.zero = torch.zeros(max(plan.zero_elems, 1), **f32)
         self.work = torch.zeros(max(plan.work_elems, 1), **f32)
         if self.training:
@@ -46,7 +56,7 @@ class Runtime:
                 self.momentum = share.momentum
             else:
                 self.momentum = torch.zeros(plan.param_elems, **f32)
-            self.w_dgrad = torch.zeros(max(plan.dgrad_elems, 1), dtype=torch.bfloat16,
+            self.w_dgrad = torch.zeros(self.planes * max(plan.dgrad_elems, 1), dtype=torch.bfloat16,
                                        device=self.dev)
         else:
             self.grads = self.momentum = self.w_dgrad = None
@@ -77,6 +87,7 @@ class Runtime:
         self.graph = None
         self._side_stream = None
         self._geom_cache = {}
+        self._parts_cache = {}
 
     # ---------------------------------------------------------------- pointers
     @property
@@ -240,12 +251,16 @@ class Runtime:
             self._chk(self.lib.acnn_prep_weights(
                 self.params.data_ptr(), self.descs.data_ptr(), self.n_descs,
                 self.w_fprop.data_ptr(),
-                self.w_dgrad.data_ptr() if self.w_dgrad is not None else None, self.stream), op)
+                self.w_dgrad.data_ptr() if self.w_dgrad is not None else None, self.planes,
+                self.plan.param_elems, max(self.plan.dgrad_elems, 1), self.stream), op)
+
+    def op_split3(self, op):
+        self._chk(self.lib.acnn_split3(self.T(op.src), self.T(op.dst), op.n, self.stream), op)
 
     def op_pack_input(self, op):
         self._chk(self.lib.acnn_pack_input(self.T(op.images), self.T(op.lam1), self.T(op.lam2),
                                            op.mode, self.T(op.out), op.Bin, op.H, op.W,
-                                           op.wpad[0], op.wpad[1], self.stream), op)
+                                           op.wpad[0], op.wpad[1], self.adt, self.stream), op)
 
     def op_mix_labels(self, op):
         self._chk(self.lib.acnn_mix_labels(self.T(op.labels), self.T(op.lam1), self.T(op.lam2),
@@ -253,21 +268,52 @@ class Runtime:
 
     def op_s2d_weight_pack(self, op):
         self._chk(self.lib.acnn_s2d_weight_pack(self.P(op.w), self.T(op.w2), op.cout, op.k, op.pad,
-                                                op.k2, op.pad2, self.stream), op)
+                                                op.k2, op.pad2, self.adt, self.stream), op)
+
+    def stats_parts(self, geom, x_wpad=None):
+        """Rows of the partial-statistics buffer the conv of this geometry writes."""
+        key = ("conv", geom.astuple(), x_wpad)
+        n = self._parts_cache.get(key)
+        if n is None:
+            n = self.lib.acnn_conv_stats_parts(self.geom(geom, x_wpad))
+            if n < 1:
+                raise _lib.AcnnError("acnn_conv_stats_parts failed for %r" % (geom,))
+            self._parts_cache[key] = n
+        return n
 
     def op_conv(self, op):
-        w = self.T(op.w) if op.a.get("w_is_tensor") else self.WF(op.w)
+        is_t = op.a.get("w_is_tensor")
+        if self.fp32:
+            x = self.T(op.xp)
+            w = self.T(op.wp) if is_t else self.WF(op.w)
+            wstride = self.t[op.wp].numel() // 3 if is_t else self.plan.param_elems
+        else:
+            x = self.T(op.x)
+            w = self.T(op.w) if is_t else self.WF(op.w)
+            wstride = 0
         st = op.stats
-        C_ = op.geom.Cout
+        if st is not None:
+            n = self.stats_parts(op.geom, op.a.get("x_wpad"))
+            assert n * 2 * op.geom.Cout <= st.size, (n, st.size)
         self._chk(self.lib.acnn_conv_fprop(
-            self.geom(op.geom, op.a.get("x_wpad")), self.T(op.x), w, self.T(op.y), self.S(st), self.S(st, C_) if st else None,
-            None, None, self.P(op.bias) if op.bias else None, 1 if op.out_f32 else 0, self.stream), op)
+            self.geom(op.geom, op.a.get("x_wpad")), x, w, self.T(op.y), self.S(st),
+            None, None, self.P(op.bias) if op.bias else None,
+            1 if (op.out_f32 or self.fp32) else 0, self.adt, wstride, self.stream), op)
+
+    def op_bn_stats(self, op):
+        bn = op.bn
+        self._chk(self.lib.acnn_bn_stats(self.T(op.x), self.S(bn.stats), op.M, op.C, self.adt,
+                                         self.stream), op)
 
     def op_bn_finalize(self, op):
         bn = op.bn
         C_ = bn.C
+        mode = op.a.get("stats_mode", 0)
+        nparts = 1
+        if self.training and mode == 0:
+            nparts = self.stats_parts(op.geom, op.a.get("x_wpad"))
         self._chk(self.lib.acnn_bn_finalize(
-            self.S(bn.stats), self.S(bn.stats, C_) if bn.stats else None, bn.count, self.P(bn.gamma),
+            self.S(bn.stats), nparts, mode, bn.count, self.P(bn.gamma),
             self.P(bn.beta), self.P(bn.mm), self.P(bn.mv), self.bn_momentum, self.eps,
             1 if self.training else 0, self.S(bn.work), self.S(bn.work, C_), self.S(bn.work, 2 * C_),
             self.S(bn.work, 3 * C_), C_, self.stream), op)
@@ -278,12 +324,13 @@ class Runtime:
         self._chk(self.lib.acnn_bn_act(
             self.T(op.a["a"]), self.S(bna.work), self.S(bna.work, C_), self.T(op.b),
             self.S(bnb.work) if bnb else None, self.S(bnb.work, C_) if bnb else None, op.b_mode,
-            self.S(op.gate), 1 if op.relu else 0, self.T(op.out), B, H, W, C_, self.stream), op)
+            self.S(op.gate), 1 if op.relu else 0, self.T(op.out), B, H, W, C_, self.adt,
+            self.stream), op)
 
     def op_sk_gap(self, op):
         bn = op.bn
         self._chk(self.lib.acnn_sk_gap(self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C),
-                                       self.S(op.s), op.B, op.HW, op.f, self.stream), op)
+                                       self.S(op.s), op.B, op.HW, op.f, self.adt, self.stream), op)
 
     def op_sk_fc(self, op):
         bn = op.bn
@@ -291,62 +338,65 @@ class Runtime:
             self.S(op.s), self.P(op.w1), self.P(bn.gamma), self.P(bn.beta), self.P(bn.mm),
             self.P(bn.mv), self.bn_momentum, self.eps, 1 if self.training else 0, self.P(op.w2),
             self.S(op.zpre), self.S(bn.work), self.S(op.z), self.S(op.att), self.S(op.scratch),
-            op.B, op.f, op.d, self.stream), op)
+            op.B, op.f, op.d, self.det, self.stream), op)
 
     def op_sk_combine(self, op):
         bn = op.bn
         self._chk(self.lib.acnn_sk_combine(self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C),
                                            self.S(op.att), self.T(op.v), op.B, op.HW, op.f,
-                                           self.stream), op)
+                                           self.adt, self.stream), op)
 
     def op_se_gap(self, op):
         bn = op.bn
         self._chk(self.lib.acnn_se_gap(self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C),
-                                       self.S(op.q), op.B, op.HW, op.C, self.stream), op)
+                                       self.S(op.q), op.B, op.HW, op.C, self.adt, self.stream), op)
 
     def op_se_fc(self, op):
         self._chk(self.lib.acnn_se_fc_fwd(self.S(op.q), self.P(op.w1), self.P(op.w2), self.S(op.h),
-                                          self.S(op.e), op.B, op.C, op.r, self.stream), op)
+                                          self.S(op.e), op.B, op.C, op.r, self.det, self.stream), op)
 
     def op_blurpool(self, op):
         self._chk(self.lib.acnn_blurpool_fwd(self.T(op.x), self.T(op.out), op.B, op.H, op.W, op.C,
-                                             op.filt, op.stride, self.stream), op)
+                                             op.filt, op.stride, self.adt, self.stream), op)
 
     def op_avgpool(self, op):
         self._chk(self.lib.acnn_avgpool_fwd(self.T(op.x), self.T(op.out), op.B, op.H, op.W, op.C,
                                             op.k, op.stride, op.pad_lo, op.Ho, op.Wo, op.count_pad,
-                                            self.stream), op)
+                                            self.adt, self.stream), op)
 
     def op_maxpool(self, op):
         self._chk(self.lib.acnn_maxpool_fwd(self.T(op.x), self.T(op.out), op.B, op.H, op.W, op.C,
-                                            op.k, op.stride, op.pad_lo, op.Ho, op.Wo, self.stream),
-                  op)
+                                            op.k, op.stride, op.pad_lo, op.Ho, op.Wo, self.adt,
+                                            self.stream), op)
 
     def op_gap(self, op):
         self._chk(self.lib.acnn_gap_fwd(self.T(op.x), self.T(op.out), op.B, op.HW, op.C,
-                                        self.stream), op)
+                                        self.adt, self.stream), op)
 
     def op_softmax_ce(self, op):
         self._chk(self.lib.acnn_softmax_ce(
             self.T(op.logits), self.T(op.y), op.B, op.NC, op.ld, op.label_smoothing,
             self.loss_scale, self.S(op.loss), self.T(op.dlogits),
-            self.G(op.dbias) if (op.dbias and self.grads is not None) else None, self.stream), op)
+            self.G(op.dbias) if (op.dbias and self.grads is not None) else None, self.S(op.work),
+            self.adt, self.stream), op)
 
     # ---------------------------------------------------------------- backward ops
     def op_conv_wgrad(self, op):
         slot = op.a.get("dw_slot")
         dw = self.S(slot) if slot is not None else self.G(op.w)
-        self._chk(self.lib.acnn_conv_wgrad(self.geom(op.geom, op.a.get("x_wpad")), self.T(op.x),
-                                           self.T(op.dy), dw, self.stream), op)
+        x, dy = (self.T(op.xp), self.T(op.dyp)) if self.fp32 else (self.T(op.x), self.T(op.dy))
+        self._chk(self.lib.acnn_conv_wgrad(self.geom(op.geom, op.a.get("x_wpad")), x, dy, dw,
+                                           self.adt, self.det, self.stream), op)
 
     def op_conv_dgrad(self, op):
-        self._chk(self.lib.acnn_conv_dgrad(self.geom(op.geom), self.T(op.dy), self.WD(op.w),
+        dy = self.T(op.dyp) if self.fp32 else self.T(op.dy)
+        self._chk(self.lib.acnn_conv_dgrad(self.geom(op.geom), dy, self.WD(op.w),
                                            self.T(op.dx), self.T(op.add_src), self.T(op.mask_src),
-                                           self.stream), op)
+                                           self.adt, max(self.plan.dgrad_elems, 1), self.stream), op)
 
     def op_zero_insert(self, op):
         self._chk(self.lib.acnn_zero_insert2x(self.T(op.dy), self.T(op.out), op.B, op.Ho, op.Wo,
-                                              op.H, op.W, op.C, self.stream), op)
+                                              op.H, op.W, op.C, self.adt, self.stream), op)
 
     def op_s2d_wgrad_unpack(self, op):
         self._chk(self.lib.acnn_s2d_wgrad_unpack(self.S(op.dw2), self.G(op.w), op.cout, op.k,
@@ -355,28 +405,33 @@ class Runtime:
     def op_bn_bwd_reduce(self, op):
         B, H, W, C_ = op.shape
         bn = op.bn
+        n = self.lib.acnn_bn_bwd_reduce_parts(B, H * W, C_)
+        assert 1 <= n and n * 2 * C_ <= op.sums.size, (n, C_, op.sums.size)
+        self._parts_cache[("bwd", op.sums.buf, op.sums.offset)] = n
         self._chk(self.lib.acnn_bn_bwd_reduce(
             self.T(op.g), self.T(op.y), self.S(bn.work, 2 * C_), self.S(bn.work, 3 * C_),
-            self.S(op.gate), self.S(op.addbc), self.S(op.sums), B, H * W, C_, self.stream), op)
+            self.S(op.gate), self.S(op.addbc), self.S(op.sums), B, H * W, C_, self.adt,
+            self.stream), op)
 
     def op_bn_bwd_finalize(self, op):
         bn = op.bn
-        C_ = op.sums.size // 2
+        C_ = bn.C
+        n = self._parts_cache[("bwd", op.sums.buf, op.sums.offset)]
         self._chk(self.lib.acnn_bn_bwd_finalize(
-            self.S(op.sums), self.P(bn.gamma), self.S(bn.work, 2 * C_), self.S(bn.work, 3 * C_),
+            self.S(op.sums), n, self.P(bn.gamma), self.S(bn.work, 2 * C_), self.S(bn.work, 3 * C_),
             bn.count, self.S(op.coef), self.G(bn.gamma), self.G(bn.beta), C_, self.stream), op)
 
     def op_bn_bwd_apply(self, op):
         B, H, W, C_ = op.shape
         self._chk(self.lib.acnn_bn_bwd_apply(self.T(op.g), self.T(op.y), self.S(op.coef),
                                              self.S(op.gate), self.S(op.addbc), self.T(op.dy), B,
-                                             H * W, C_, self.stream), op)
+                                             H * W, C_, self.adt, self.stream), op)
 
     def op_sk_bwd_gate(self, op):
         bn = op.bn
         self._chk(self.lib.acnn_sk_bwd_gate(self.T(op.dv), self.T(op.y), self.S(bn.work),
                                             self.S(bn.work, bn.C), self.S(op.dA), op.B, op.HW,
-                                            op.f, self.stream), op)
+                                            op.f, self.adt, self.stream), op)
 
     def op_sk_fc_bwd(self, op):
         bn = op.bn
@@ -384,70 +439,74 @@ class Runtime:
             self.S(op.dA), self.S(op.att), self.S(op.z), self.S(op.zpre), self.S(bn.work),
             self.P(bn.gamma), self.S(op.s), self.P(op.w1), self.P(op.w2), self.G(op.w1),
             self.G(op.w2), self.G(bn.gamma), self.G(bn.beta), self.S(op.ds), self.S(op.scratch),
-            op.B, op.f, op.d, self.stream), op)
+            op.B, op.f, op.d, self.det, self.stream), op)
 
     def op_sk_bn_bwd_reduce(self, op):
         bn = op.bn
         C_ = bn.C
+        n = self.lib.acnn_sk_bn_bwd_reduce_parts(op.B, op.HW, op.f)
+        assert 1 <= n and n * 2 * C_ <= op.sums.size, (n, C_, op.sums.size)
+        self._parts_cache[("bwd", op.sums.buf, op.sums.offset)] = n
         self._chk(self.lib.acnn_sk_bn_bwd_reduce(
             self.T(op.dv), self.T(op.y), self.S(bn.work), self.S(bn.work, C_),
             self.S(bn.work, 2 * C_), self.S(bn.work, 3 * C_), self.S(op.att), self.S(op.ds),
-            self.S(op.sums), op.B, op.HW, op.f, self.stream), op)
+            self.S(op.sums), op.B, op.HW, op.f, self.adt, self.stream), op)
 
     def op_sk_bn_bwd_apply(self, op):
         bn = op.bn
         self._chk(self.lib.acnn_sk_bn_bwd_apply(
             self.T(op.dv), self.T(op.y), self.S(bn.work), self.S(bn.work, bn.C), self.S(op.att),
-            self.S(op.ds), self.S(op.coef), self.T(op.dy), op.B, op.HW, op.f, self.stream), op)
+            self.S(op.ds), self.S(op.coef), self.T(op.dy), op.B, op.HW, op.f, self.adt,
+            self.stream), op)
 
     def op_se_bwd_gate(self, op):
         bn = op.bn
         self._chk(self.lib.acnn_se_bwd_gate(self.T(op.g), self.T(op.y), self.S(bn.work),
                                             self.S(bn.work, bn.C), self.S(op.de), op.B, op.HW,
-                                            op.C, self.stream), op)
+                                            op.C, self.adt, self.stream), op)
 
     def op_se_fc_bwd(self, op):
         self._chk(self.lib.acnn_se_fc_bwd(
             self.S(op.de), self.S(op.e), self.S(op.h), self.S(op.q), self.P(op.w1), self.P(op.w2),
             self.G(op.w1), self.G(op.w2), self.S(op.dq), self.S(op.scratch), op.B, op.C, op.r,
-            op.HW, self.stream), op)
+            op.HW, self.det, self.stream), op)
 
     def op_blurpool_bwd(self, op):
         self._chk(self.lib.acnn_blurpool_bwd(self.T(op.dout), self.T(op.dx), self.T(op.add_src),
                                              self.T(op.mask_src), op.B, op.H, op.W, op.C, op.filt,
-                                             op.stride, self.stream), op)
+                                             op.stride, self.adt, self.stream), op)
 
     def op_avgpool_bwd(self, op):
         self._chk(self.lib.acnn_avgpool_bwd(self.T(op.dout), self.T(op.dx), self.T(op.add_src),
                                             self.T(op.mask_src), op.B, op.H, op.W, op.C, op.k,
                                             op.stride, op.pad_lo, op.Ho, op.Wo, op.count_pad,
-                                            self.stream), op)
+                                            self.adt, self.stream), op)
 
     def op_maxpool_bwd(self, op):
         self._chk(self.lib.acnn_maxpool_bwd(self.T(op.dout), self.T(op.x), self.T(op.dx),
                                             self.T(op.add_src), self.T(op.mask_src), op.B, op.H,
                                             op.W, op.C, op.k, op.stride, op.pad_lo, op.Ho, op.Wo,
-                                            self.stream), op)
+                                            self.adt, self.stream), op)
 
     def op_upsample2x_bwd(self, op):
         self._chk(self.lib.acnn_upsample2x_bwd(self.T(op.dout), self.T(op.dx), self.T(op.add_src),
                                                self.T(op.mask_src), op.B, op.H, op.W, op.C,
-                                               self.stream), op)
+                                               self.adt, self.stream), op)
 
     def op_gap_bwd(self, op):
         self._chk(self.lib.acnn_gap_bwd(self.T(op.dpooled), self.T(op.mask_src), self.T(op.dx),
-                                        op.B, op.HW, op.C, self.stream), op)
+                                        op.B, op.HW, op.C, self.adt, self.stream), op)
 
     def op_grad_combine(self, op):
         n = 1
         for s in op.shape:
             n *= s
         self._chk(self.lib.acnn_grad_combine(self.T(op.a["a"]), self.T(op.add_src),
-                                             self.T(op.mask_src), self.T(op.out), n, self.stream),
-                  op)
+                                             self.T(op.mask_src), self.T(op.out), n, self.adt,
+                                             self.stream), op)
 
     def op_sgd(self, op):
         self._chk(self.lib.acnn_sgd_momentum(
             self.params.data_ptr(), self.grads.data_ptr(), self.momentum.data_ptr(),
             self.plan.param_elems, self.decay_flags.data_ptr(), self.hp.data_ptr(),
-            self.S(op.loss, 1), self.stream), op)
+            self.S(op.loss, 1), self.S(op.scratch), self.stream), op)

@@ -29,6 +29,13 @@ extern "C" {
 #define ACNN_ERR_CUDA 2
 #define ACNN_ERR_UNSUPPORTED 3
 
+/* Storage type of the activation tensors of a call (`dtype` arguments): bf16 is the production
+ * path; fp32 is the parity mode (the reference's own default dtype, nets/resnet_model.py:30-33):
+ * fp32 activations, every elementwise / reduction kernel instantiated on float, and the conv GEMMs
+ * run on operands split into three bf16 planes (`precision` = 1 below). */
+#define ACNN_BF16 0
+#define ACNN_F32 1
+
 /* Library / environment ------------------------------------------------------------------- */
 const char* acnn_last_error(void);
 int acnn_version(void);
@@ -60,35 +67,59 @@ typedef struct acnn_conv_geom {
  *   + bias[Cout] (fp32)            -> dense bias
  *   + add_src[B,Ho,Wo,Cout] (bf16) -> gradient accumulation across consumers
  *   * (mask_src > 0)               -> ReLU backward of the tensor this gradient belongs to
- *   ch_sum/ch_sumsq[Cout] += column sums of the bf16-rounded output (batch-norm statistics,
- *                             nets/model_helper.py:34-37; buffers must be zeroed by the caller)
- * out_f32 != 0 stores y as fp32 (logits), else bf16.  Requires Cin % 16 == 0, Cout % 32 == 0. */
+ *   ch_part[parts][2][Cout]        -> batch-norm statistics (nets/model_helper.py:34-37): every CTA
+ *                                     row of the persistent grid STORES its partial column sums and
+ *                                     sums of squares of the bf16-rounded output (no atomics, nothing
+ *                                     to zero); parts = acnn_conv_stats_parts(g); acnn_bn_finalize
+ *                                     adds the rows in a fixed order (bit-reproducible)
+ * out_f32 != 0 stores y as fp32 (logits), else bf16.  Requires Cin % 16 == 0, Cout % 32 == 0.
+ * precision 0: x, w bf16.  precision 1 (fp32 parity mode): x and w are each three consecutive bf16
+ * planes hi / mid / lo of an fp32 tensor (acnn_split3, acnn_prep_weights(planes = 3)); plane p of x
+ * starts at x + p * numel(x), plane p of w at w + p * w_plane_stride elements; the six significant
+ * cross products accumulate in the fp32 TMEM accumulator; requires out_f32 and no add / mask /
+ * statistics epilogue. */
 int acnn_conv_fprop(const acnn_conv_geom* g, const void* x, const void* w, void* y,
-                    float* ch_sum, float* ch_sumsq, const void* add_src, const void* mask_src,
-                    const float* bias, int out_f32, void* stream);
+                    float* ch_part, const void* add_src, const void* mask_src,
+                    const float* bias, int out_f32, int precision, int64_t w_plane_stride,
+                    void* stream);
+/* Rows of the partial statistics buffer acnn_conv_fprop(g, ..., ch_part, ...) writes (a pure
+ * function of the geometry and the device's SM count; <= 148). */
+int acnn_conv_stats_parts(const acnn_conv_geom* g);
 
 /* dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout]) for a stride-1 conv of geometry g (the backward
  * of tf.layers.conv2d the reference gets from tf.gradients, nets/optimizer_setting.py:30).
  * w_dgrad is [Cin][kh][kw][Cout] with taps already flipped (acnn_prep_weights writes it).
- * Same optional add_src / mask_src epilogue as acnn_conv_fprop (shapes of dx). */
+ * Same optional add_src / mask_src epilogue as acnn_conv_fprop (shapes of dx).  precision 1: dy and
+ * w_dgrad are 3-plane operands, dx is fp32 and no epilogue may be fused. */
 int acnn_conv_dgrad(const acnn_conv_geom* g, const void* dy, const void* w_dgrad, void* dx,
-                    const void* add_src, const void* mask_src, void* stream);
+                    const void* add_src, const void* mask_src, int precision,
+                    int64_t w_plane_stride, void* stream);
 
 /* dw[Cout,kh,kw,Cin] (fp32) += sum_pixels x (*) dy  -- weight gradient, split-K over pixels with
- * fp32 atomics; dw must be zeroed (or hold the running sum) by the caller. */
-int acnn_conv_wgrad(const acnn_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
+ * fp32 atomics; dw must be zeroed (or hold the running sum) by the caller.  deterministic != 0:
+ * no split (one add per element: bit-reproducible).  precision 1: x and dy are 3-plane operands. */
+int acnn_conv_wgrad(const acnn_conv_geom* g, const void* x, const void* dy, float* dw,
+                    int precision, int deterministic, void* stream);
+/* planes bf16 [3][n] = (hi, mid, lo) of x fp32 [n], x = hi + mid + lo to 24 bits (n % 8 == 0). */
+int acnn_split3(const float* x, void* planes, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Batch normalisation (tf.layers.batch_normalization fused=True, nets/model_helper.py:26-37)
  * ------------------------------------------------------------------------------------------- */
 /* Training: mean = sum/count, var = sumsq/count - mean^2 (biased), rstd = rsqrt(var + eps);
  * moving_mean <- m*moving_mean + (1-m)*mean, moving_var likewise with the UNBIASED variance.
+ * stats_mode 0: stats = [nparts][2][C] partial (sum, sumsq) rows from acnn_conv_fprop, added here
+ *               in a fixed order in double precision (so E[x^2] - E[x]^2 does not cancel in fp32);
+ * stats_mode 1: stats = [mean | biased variance] from acnn_bn_stats (two-pass; nparts ignored).
  * Inference (training == 0): statistics are the moving ones, nothing is updated.
  * Outputs: scale = gamma*rstd, shift = beta - mean*scale, and mean / rstd for the backward. */
-int acnn_bn_finalize(const float* sum, const float* sumsq, int64_t count, const float* gamma,
-                     const float* beta, float* moving_mean, float* moving_var, float momentum,
-                     float eps, int training, float* scale, float* shift, float* mean, float* rstd,
-                     int C, void* stream);
+int acnn_bn_finalize(const float* stats, int nparts, int stats_mode, int64_t count,
+                     const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                     float momentum, float eps, int training, float* scale, float* shift,
+                     float* mean, float* rstd, int C, void* stream);
+/* Two-pass batch statistics of x [M][C] (fp32 parity mode): mean_var = [mean | biased variance],
+ * fixed-order reductions (bit-reproducible). */
+int acnn_bn_stats(const void* x, float* mean_var, int64_t M, int C, int dtype, void* stream);
 
 /* out = bf16( relu?( (a*scale_a + shift_a) [* gate[b,c]] + R ) ), all NHWC [B,H,W,C]:
  *   b_mode 0: R = 0            1: R = b*scale_b + shift_b (projection shortcut BN)
@@ -98,22 +129,25 @@ int acnn_bn_finalize(const float* sum, const float* sumsq, int64_t count, const 
  * the SE multiply (nets/blocks.py:183) when gate != NULL. */
 int acnn_bn_act(const void* a, const float* scale_a, const float* shift_a, const void* b,
                 const float* scale_b, const float* shift_b, int b_mode, const float* gate, int relu,
-                void* out, int B, int H, int W, int C, void* stream);
+                void* out, int B, int H, int W, int C, int dtype, void* stream);
 
 /* Backward of y -> bn -> (gate) given the gradient g w.r.t. the block output (already
  * ReLU-masked).  Effective gradient of the BN output: ge = g [* gate[b,c]] [+ addbc[b,c]] (the SE
  * gate and the SE pooled-descriptor term; both NULL for a plain BN).
- * sums[0:C] += sum_m ge, sums[C:2C] += sum_m ge*xhat, xhat = (y-mean)*rstd. */
+ * parts[p][0:C] = partial sum_m ge, parts[p][C:2C] = partial sum_m ge*xhat, xhat = (y-mean)*rstd,
+ * one row per CTA, p < acnn_bn_bwd_reduce_parts(B, HW, C) (plain stores: no atomics, no zeroing). */
 int acnn_bn_bwd_reduce(const void* g, const void* y, const float* mean, const float* rstd,
-                       const float* gate, const float* addbc, float* sums, int B, int HW, int C,
-                       void* stream);
-/* dgamma = sums[C:2C], dbeta = sums[0:C]; coef[0:C],[C:2C],[2C:3C] = k1,k2,k3 such that
+                       const float* gate, const float* addbc, float* parts, int B, int HW, int C,
+                       int dtype, void* stream);
+int acnn_bn_bwd_reduce_parts(int B, int HW, int C);
+/* sums = rows of `parts` added in index order (deterministic); dgamma = sums[C:2C], dbeta =
+ * sums[0:C]; coef[0:C],[C:2C],[2C:3C] = k1,k2,k3 such that
  * dy = k1*ge + k2*y + k3  (= gamma*rstd*(ge - mean(ge) - xhat*mean(ge*xhat))). */
-int acnn_bn_bwd_finalize(const float* sums, const float* gamma, const float* mean,
+int acnn_bn_bwd_finalize(const float* parts, int nparts, const float* gamma, const float* mean,
                          const float* rstd, int64_t count, float* coef, float* dgamma, float* dbeta,
                          int C, void* stream);
 int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const float* gate,
-                      const float* addbc, void* dy, int B, int HW, int C, void* stream);
+                      const float* addbc, void* dy, int B, int HW, int C, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Selective-kernel block after its 3x3 conv (nets/blocks.py:128-152).  y = raw conv output
@@ -121,92 +155,98 @@ int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const flo
  * ------------------------------------------------------------------------------------------- */
 /* s[B,f] (fp32) = mean_HW(u[..., :f] + u[..., f:])                         (blocks.py:128-132) */
 int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s, int B, int HW,
-                int f, void* stream);
+                int f, int dtype, void* stream);
 /* zpre = s*W1^T ; z = relu(BN_batch(zpre)) ; a = z*W2^T ; att = sigmoid(a[:, :f] - a[:, f:])
  * (2-way softmax over the halves, blocks.py:136-151).  w1 [d][f], w2 [2f][d] fp32 (OHWI 1x1).
- * bnstat[0:d] = mean, [d:2d] = rstd (batch statistics over B; moving stats when !training). */
+ * bnstat[0:d] = mean, [d:2d] = rstd (batch statistics over B; moving stats when !training).
+ * deterministic != 0 (here and in the three functions below): the small fp32 GEMMs run without
+ * split-K, so every output receives one add (bit-reproducible). */
 int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const float* beta,
                    float* moving_mean, float* moving_var, float momentum, float eps, int training,
                    const float* w2, float* zpre, float* bnstat, float* z, float* att,
-                   float* scratch /* >= B*2f floats */, int B, int f, int d, void* stream);
+                   float* scratch /* >= B*2f floats */, int B, int f, int d, int deterministic,
+                   void* stream);
 /* v[B,HW,f] = att*u0 + (1-att)*u1                                           (blocks.py:152) */
 int acnn_sk_combine(const void* y, const float* scale, const float* shift, const float* att,
-                    void* v, int B, int HW, int f, void* stream);
+                    void* v, int B, int HW, int f, int dtype, void* stream);
 /* dA[B,f] = sum_HW dv*(u0-u1) */
 int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const float* shift,
-                     float* dA, int B, int HW, int f, void* stream);
+                     float* dA, int B, int HW, int f, int dtype, void* stream);
 /* Backward of the two fc layers + batch BN: consumes dA, produces ds[B,f] (gradient w.r.t. the
  * pooled descriptor) and ACCUMULATES dw1[d][f], dw2[2f][d], dgamma[d], dbeta[d]. */
 int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const float* zpre,
                    const float* bnstat, const float* gamma, const float* s, const float* w1,
                    const float* w2, float* dw1, float* dw2, float* dgamma, float* dbeta, float* ds,
-                   float* scratch /* >= B*(2f+d) floats */, int B, int f, int d, void* stream);
-/* g_h = (att_h*dv + ds/HW) * [u_h > 0] for both halves; sums as acnn_bn_bwd_reduce over 2f. */
+                   float* scratch /* >= B*(2f+d) floats */, int B, int f, int d, int deterministic,
+                   void* stream);
+/* g_h = (att_h*dv + ds/HW) * [u_h > 0] for both halves; partial rows as acnn_bn_bwd_reduce over 2f
+ * channels, acnn_sk_bn_bwd_reduce_parts(B, HW, f) rows. */
 int acnn_sk_bn_bwd_reduce(const void* dv, const void* y, const float* scale, const float* shift,
                           const float* mean, const float* rstd, const float* att, const float* ds,
-                          float* sums, int B, int HW, int f, void* stream);
+                          float* parts, int B, int HW, int f, int dtype, void* stream);
+int acnn_sk_bn_bwd_reduce_parts(int B, int HW, int f);
 int acnn_sk_bn_bwd_apply(const void* dv, const void* y, const float* scale, const float* shift,
                          const float* att, const float* ds, const float* coef, void* dy, int B,
-                         int HW, int f, void* stream);
+                         int HW, int f, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Squeeze-excitation gate (nets/blocks.py:156-184), applied to t = bn(y) before the residual add
  * ------------------------------------------------------------------------------------------- */
 /* q[B,C] (fp32) = mean_HW(y*scale + shift) */
 int acnn_se_gap(const void* y, const float* scale, const float* shift, float* q, int B, int HW,
-                int C, void* stream);
+                int C, int dtype, void* stream);
 /* h = relu(q*W1^T) [B,r]; e = sigmoid(h*W2^T) [B,C];  w1 [r][C], w2 [C][r] fp32. */
 int acnn_se_fc_fwd(const float* q, const float* w1, const float* w2, float* h, float* e, int B,
-                   int C, int r, void* stream);
+                   int C, int r, int deterministic, void* stream);
 /* de[B,C] = sum_HW g*t (t = y*scale+shift, g = masked grad of the block output) */
 int acnn_se_bwd_gate(const void* g, const void* y, const float* scale, const float* shift,
-                     float* de, int B, int HW, int C, void* stream);
+                     float* de, int B, int HW, int C, int dtype, void* stream);
 /* consumes de; ACCUMULATES dw1, dw2; dq[B,C] = gradient w.r.t. q, pre-divided by HW. */
 int acnn_se_fc_bwd(const float* de, const float* e, const float* h, const float* q,
                    const float* w1, const float* w2, float* dw1, float* dw2, float* dq,
                    float* scratch /* >= B*(C+r) floats */, int B, int C, int r, int HW,
-                   void* stream);
+                   int deterministic, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Pooling / resampling (all NHWC bf16).  Backward kernels take the same optional epilogue as the
- * convs: (+ add_src) then (* (mask_src > 0)).
+ * Pooling / resampling (all NHWC, element type `dtype`).  Backward kernels take the same optional
+ * epilogue as the convs: (+ add_src) then (* (mask_src > 0)).
  * ------------------------------------------------------------------------------------------- */
 /* Anti-alias blur-pool: REFLECT pad (filt-1)/2, binomial filt x filt / sum, stride, VALID
  * (nets/blocks.py:45-107).  filt in [1,7]. */
 int acnn_blurpool_fwd(const void* x, void* out, int B, int H, int W, int C, int filt, int stride,
-                      void* stream);
+                      int dtype, void* stream);
 int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
-                      int H, int W, int C, int filt, int stride, void* stream);
+                      int H, int W, int C, int filt, int stride, int dtype, void* stream);
 /* Average pool k x k, zero padding pad_lo before (pad after implied by Ho).  count_pad != 0:
  * divide by k*k (bl shortcut, resnet_model.py:133-138); else by the number of in-bounds cells
  * (TF SAME, resnet-d stride-1 shortcut :126). */
 int acnn_avgpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
-                     int pad_lo, int Ho, int Wo, int count_pad, void* stream);
+                     int pad_lo, int Ho, int Wo, int count_pad, int dtype, void* stream);
 int acnn_avgpool_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src, int B,
                      int H, int W, int C, int k, int stride, int pad_lo, int Ho, int Wo,
-                     int count_pad, void* stream);
+                     int count_pad, int dtype, void* stream);
 /* Max pool k x k, -inf padding, pad_lo before (TF SAME puts the odd cell after: pad_lo = 0 for
  * 3x3/s2 on even sizes, resnet_model.py:421-424).  Backward routes to the FIRST maximum. */
 int acnn_maxpool_fwd(const void* x, void* out, int B, int H, int W, int C, int k, int stride,
-                     int pad_lo, int Ho, int Wo, void* stream);
+                     int pad_lo, int Ho, int Wo, int dtype, void* stream);
 int acnn_maxpool_bwd(const void* dout, const void* x, void* dx, const void* add_src,
                      const void* mask_src, int B, int H, int W, int C, int k, int stride,
-                     int pad_lo, int Ho, int Wo, void* stream);
+                     int pad_lo, int Ho, int Wo, int dtype, void* stream);
 /* dx[B,H,W,C] = 2x2 block sums of dout[B,2H,2W,C] (backward of UpSampling2D) */
 int acnn_upsample2x_bwd(const void* dout, void* dx, const void* add_src, const void* mask_src,
-                        int B, int H, int W, int C, void* stream);
+                        int B, int H, int W, int C, int dtype, void* stream);
 /* out[B,H,W,C]: out[2p,2q] = dy[p,q], zeros elsewhere (stride-2 dgrad = zero-insert + stride-1) */
 int acnn_zero_insert2x(const void* dy, void* out, int B, int Ho, int Wo, int H, int W, int C,
-                       void* stream);
+                       int dtype, void* stream);
 /* out = (a [+ add_src]) [* (mask_src > 0)] over n bf16 elements: gradient merge when no consumer
  * kernel can fuse it (identity shortcut as last contribution). */
 int acnn_grad_combine(const void* a, const void* add_src, const void* mask_src, void* out,
-                      int64_t n, void* stream);
-/* pooled[B,C] (bf16) = mean_HW(x)                              (nets/resnet_model.py:560-561) */
-int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, void* stream);
+                      int64_t n, int dtype, void* stream);
+/* pooled[B,C] = mean_HW(x)                                     (nets/resnet_model.py:560-561) */
+int acnn_gap_fwd(const void* x, void* pooled, int B, int HW, int C, int dtype, void* stream);
 /* dx = dpooled[b,c]/HW * (mask_src > 0) */
 int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int HW, int C,
-                 void* stream);
+                 int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Input packing / mixup (utils/data_util.py:97-158) and the loss (losses/cls_losses.py:28-33)
@@ -218,16 +258,18 @@ int acnn_gap_bwd(const void* dpooled, const void* mask_src, void* dx, int B, int
  *   out = lam1*x[:B] + (1-lam1)*x[B:]; 2: mixup type 2, B = Bin, second half uses lam2 and the
  *   reversed second half. */
 int acnn_pack_input(const float* images, const float* lam1, const float* lam2, int mode, void* out,
-                    int Bin, int H, int W, int wpad_lo, int wpad_hi, void* stream);
+                    int Bin, int H, int W, int wpad_lo, int wpad_hi, int dtype, void* stream);
 /* y[B,NC] (fp32) = (mixed) one-hot labels, same modes. */
 int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2, int mode, float* y,
                     int Bin, int NC, void* stream);
 /* Softmax cross-entropy with label smoothing, mean over B: loss_acc[0] += loss (caller zeroes).
- * dlogits (bf16 [B,ld], columns >= NC zeroed) = (softmax - y')/B * grad_scale;
- * dbias[NC] (fp32) += column sums of the fp32 dlogits.  logits fp32 [B,ld]. */
+ * dlogits (`dtype` [B,ld], columns >= NC zeroed) = (softmax - y')/B * grad_scale;
+ * dbias[NC] (fp32) += column sums of the fp32 dlogits.  logits fp32 [B,ld].  Two launches: per-row
+ * losses / gradients, then a fixed-order sum (no atomics: bit-reproducible).
+ * work: >= roundup(B, 32) + B*ld floats of scratch. */
 int acnn_softmax_ce(const float* logits, const float* y, int B, int NC, int ld,
                     float label_smoothing, float grad_scale, float* loss_acc, void* dlogits,
-                    float* dbias, void* stream);
+                    float* dbias, float* work, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Parameters and optimizer (nets/optimizer_setting.py:23-38, run_loop_classification.py:166-179)
@@ -241,21 +283,27 @@ typedef struct acnn_weight_desc {
   int32_t pad_;
 } acnn_weight_desc;
 /* bf16 operand copies of every conv weight (fprop layout + flipped/transposed dgrad layout).
- * `descs` is a DEVICE array of n descriptors. */
+ * `descs` is a DEVICE array of n descriptors.  planes = 1: one bf16 copy; planes = 3 (fp32 parity
+ * mode): hi / mid / lo planes, plane p at element offset p * {fprop,dgrad}_plane_stride. */
 int acnn_prep_weights(const float* master, const acnn_weight_desc* descs, int n, void* w_fprop,
-                      void* w_dgrad, void* stream);
+                      void* w_dgrad, int planes, int64_t fprop_plane_stride,
+                      int64_t dgrad_plane_stride, void* stream);
 /* Stem: master [Cout][k][k][3] fp32 -> bf16 [Cout][k2][k2][16] for the space-to-depth input
  * (k2 taps, see acnn_pack_input); and the inverse gather-add for its gradient. */
 int acnn_s2d_weight_pack(const float* w, void* w2, int Cout, int k, int pad, int k2, int pad2,
-                         void* stream);
+                         int dtype, void* stream);
 int acnn_s2d_wgrad_unpack(const float* dw2, float* dw, int Cout, int k, int pad, int k2, int pad2,
                           void* stream);
 /* Fused weight decay + momentum SGD over a flat buffer:
  *   g = grad*hp[3] + (decay ? hp[2]*w : 0);  acc = hp[1]*acc + g;  w -= hp[0]*acc
  * hp = device float[4] {lr, momentum, weight_decay, grad_scale}; decay_flag: one byte per 256
- * elements.  l2_acc[0] += sum over decayed elements of w^2/2 (pre-update), times weight_decay. */
+ * elements.  l2_acc[0] += sum over decayed elements of w^2/2 (pre-update), times weight_decay;
+ * the per-CTA partial sums are added in index order by the last CTA to finish (bit-reproducible).
+ * scratch: acnn_sgd_scratch_floats() floats, ZERO before the first call (self-resetting after). */
 int acnn_sgd_momentum(float* w, const float* grad, float* acc, int64_t n,
-                      const uint8_t* decay_flag, const float* hp, float* l2_acc, void* stream);
+                      const uint8_t* decay_flag, const float* hp, float* l2_acc, float* scratch,
+                      void* stream);
+int acnn_sgd_scratch_floats(void);
 int acnn_fill_zero(void* p, int64_t bytes, void* stream);
 
 #ifdef __cplusplus

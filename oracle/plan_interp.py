@@ -144,6 +144,17 @@ class PlanInterpreter:
     def op_prep_weights(self, op):
         pass                                            # bf16 operand copies: layout only
 
+    def op_split3(self, op):
+        pass                                            # fp32 mode operand planes: representation only
+
+    def op_bn_stats(self, op):
+        """fp32 mode: two-pass batch statistics [mean | biased variance]."""
+        x = self.t[op.x]
+        s = self.slot(op.bn.stats)
+        C = op.C
+        s[:C] = x.mean(dim=(0, 1, 2))
+        s[C:2 * C] = x.var(dim=(0, 1, 2), unbiased=False)
+
     def op_pack_input(self, op):
         x = self.t[op.images]
         if op.mode:
@@ -202,10 +213,11 @@ class PlanInterpreter:
         self.store(op.y, y)
         if op.stats is not None:
             ys = self.t[op.y]
-            s = self.slot(op.stats)
+            s = self.slot(op.stats)         # row 0 of the [parts][2][C] partial buffer = the total
             C = ys.shape[-1]
-            s[:C] += ys.sum(dim=(0, 1, 2))
-            s[C:] += (ys * ys).sum(dim=(0, 1, 2))
+            s.zero_()
+            s[:C] = ys.sum(dim=(0, 1, 2))
+            s[C:2 * C] = (ys * ys).sum(dim=(0, 1, 2))
 
     def op_bn_finalize(self, op):
         bn = op.bn
@@ -215,8 +227,11 @@ class PlanInterpreter:
         if self.plan.meta["training"]:
             s = self.slot(bn.stats)
             n = bn.count
-            mean = s[:bn.C] / n
-            var = (s[bn.C:] / n - mean * mean).clamp_min(0)
+            if op.a.get("stats_mode", 0) == 1:
+                mean, var = s[:bn.C].clone(), s[bn.C:2 * bn.C].clone()
+            else:
+                mean = s[:bn.C] / n
+                var = (s[bn.C:2 * bn.C] / n - mean * mean).clamp_min(0)
             mom = self.plan.meta.get("bn_momentum", 0.997)
             mm.copy_(mm * mom + mean * (1 - mom))
             mv.copy_(mv * mom + var * (n / max(n - 1, 1)) * (1 - mom))
@@ -415,14 +430,15 @@ class PlanInterpreter:
         B, _, _, C = y.shape
         _, _, mean, rstd = self.bn_scale_shift(op.bn)
         ge = self._eff_grad(g, op, B, C)
-        s = self.slot(op.sums)
-        s[:C] += ge.sum(dim=(0, 1, 2))
-        s[C:] += (ge * (y - mean) * rstd).sum(dim=(0, 1, 2))
+        s = self.slot(op.sums)              # row 0 of the partial buffer = the total
+        s.zero_()
+        s[:C] = ge.sum(dim=(0, 1, 2))
+        s[C:2 * C] = (ge * (y - mean) * rstd).sum(dim=(0, 1, 2))
 
     def op_bn_bwd_finalize(self, op):
         bn = op.bn
-        C = op.sums.size // 2
-        s = self.slot(op.sums)
+        C = bn.C
+        s = self.slot(op.sums)[:2 * C]
         w = self.slot(bn.work)
         mean, rstd = w[2 * C:3 * C], w[3 * C:4 * C]
         gamma = self.pview(bn.gamma)
@@ -485,8 +501,9 @@ class PlanInterpreter:
         _, _, mean, rstd = self.bn_scale_shift(op.bn)
         C = 2 * op.f
         s = self.slot(op.sums)
-        s[:C] += g.sum(dim=(0, 1, 2))
-        s[C:] += (g * (y - mean) * rstd).sum(dim=(0, 1, 2))
+        s.zero_()
+        s[:C] = g.sum(dim=(0, 1, 2))
+        s[C:2 * C] = (g * (y - mean) * rstd).sum(dim=(0, 1, 2))
 
     def op_sk_bn_bwd_apply(self, op):
         y, g = self._sk_g(op)

@@ -87,19 +87,26 @@ def test_fprop_matches_oracle(lib, case, mt):
     xd = x.bfloat16().cuda()
     wd = w_hwio.permute(3, 0, 1, 2).contiguous().bfloat16().cuda()      # OHWI
     yd = torch.full((B, Ho, Wo, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-    s1 = torch.zeros(Cout, device="cuda")
-    s2 = torch.zeros(Cout, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     with _mtiles(lib, mt):
+        parts = lib.acnn_conv_stats_parts(g)
+        assert 1 <= parts <= 148
+        # partial (sum, sumsq) rows: poisoned first -- the kernel must STORE every row it owns
+        sp = torch.full((parts, 2, Cout), float("nan"), device="cuda")
         _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(),
-                                       s1.data_ptr(), s2.data_ptr(), None, None, None, 0, st),
+                                       sp.data_ptr(), None, None, None, 0, 0, 0, st),
                    "conv_fprop")
+        sp2 = torch.full((parts, 2, Cout), float("nan"), device="cuda")
+        _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(),
+                                       sp2.data_ptr(), None, None, None, 0, 0, 0, st))
     torch.cuda.synchronize()
     y = yd.float().cpu()
     assert _relerr(y, ref) < BF16_TOL
+    assert torch.equal(sp, sp2)            # no atomics: bit-reproducible
+    s1, s2 = sp[:, 0].double().sum(0).cpu(), sp[:, 1].double().sum(0).cpu()
     # fused batch-norm statistics are those of the stored (rounded) tensor
-    assert _relerr(s1.cpu(), y.sum(dim=(0, 1, 2))) < 1e-3 or (s1.cpu() - y.sum(dim=(0, 1, 2))).abs().max() < 1e-2
-    assert _relerr(s2.cpu(), (y * y).sum(dim=(0, 1, 2))) < 1e-3
+    assert _relerr(s1, y.sum(dim=(0, 1, 2))) < 1e-3 or (s1 - y.sum(dim=(0, 1, 2))).abs().max() < 1e-2
+    assert _relerr(s2, (y * y).sum(dim=(0, 1, 2))) < 1e-3
 
 
 @pytest.mark.parametrize("mt", MT, ids=MT_IDS)
@@ -121,16 +128,16 @@ def test_many_tiles_per_cta(lib, mt, cout):
     addd, maskd = add.bfloat16().cuda(), mask.bfloat16().cuda()
     yd = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     y2 = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
-    s1, s2 = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
     with _mtiles(lib, mt):
+        sp = torch.full((lib.acnn_conv_stats_parts(g), 2, Cout), float("nan"), device="cuda")
         _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(),
-                                       s1.data_ptr(), s2.data_ptr(), None, None, None, 0, st))
-        _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), y2.data_ptr(), None, None,
-                                       addd.data_ptr(), maskd.data_ptr(), None, 0, st))
+                                       sp.data_ptr(), None, None, None, 0, 0, 0, st))
+        _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), y2.data_ptr(), None,
+                                       addd.data_ptr(), maskd.data_ptr(), None, 0, 0, 0, st))
     torch.cuda.synchronize()
     y = yd.float().cpu()
     assert _relerr(y, ref) < BF16_TOL
-    assert _relerr(s2.cpu(), (y * y).sum(dim=(0, 1, 2))) < 1e-3
+    assert _relerr(sp[:, 1].double().sum(0).cpu(), (y * y).sum(dim=(0, 1, 2))) < 1e-3
     assert _relerr(y2.float().cpu(), (ref + add) * (mask > 0)) < BF16_TOL
 
 
@@ -149,16 +156,16 @@ def test_fprop_epilogue_add_mask_bias(lib):
     # add + mask, bf16 out
     yd = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
     addd, maskd = add.bfloat16().cuda(), mask.bfloat16().cuda()
-    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(), None, None,
-                                   addd.data_ptr(), maskd.data_ptr(), None, 0, st))
+    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yd.data_ptr(), None,
+                                   addd.data_ptr(), maskd.data_ptr(), None, 0, 0, 0, st))
     torch.cuda.synchronize()
     want = (ref + add) * (mask > 0)
     assert _relerr(yd.float().cpu(), want) < BF16_TOL
     # bias, fp32 out (dense path)
     yf = torch.empty(B, H, W, Cout, dtype=torch.float32, device="cuda")
     biasd = bias.cuda()
-    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yf.data_ptr(), None, None,
-                                   None, None, biasd.data_ptr(), 1, st))
+    _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), yf.data_ptr(), None,
+                                   None, None, biasd.data_ptr(), 1, 0, 0, st))
     torch.cuda.synchronize()
     assert _relerr(yf.cpu(), ref + bias) < F32_TOL
 
@@ -186,7 +193,7 @@ def test_dgrad_matches_autograd(lib, case, mt):
     dyd = dy.bfloat16().cuda()
     with _mtiles(lib, mt):
         _lib.check(lib.acnn_conv_dgrad(g, dyd.data_ptr(), wdg.data_ptr(),
-                                       dxd.data_ptr(), None, None, st), "conv_dgrad")
+                                       dxd.data_ptr(), None, None, 0, 0, st), "conv_dgrad")
     torch.cuda.synchronize()
     assert _relerr(dxd.float().cpu(), dx_ref) < BF16_TOL
 
@@ -206,7 +213,7 @@ def test_wgrad_matches_autograd(lib, case, mt):
     st = torch.cuda.current_stream().cuda_stream
     xd, dyd = x.bfloat16().cuda(), dy.bfloat16().cuda()
     with _mtiles(lib, mt):
-        _lib.check(lib.acnn_conv_wgrad(g, xd.data_ptr(), dyd.data_ptr(), dwd.data_ptr(), st),
+        _lib.check(lib.acnn_conv_wgrad(g, xd.data_ptr(), dyd.data_ptr(), dwd.data_ptr(), 0, 0, st),
                    "conv_wgrad")
     torch.cuda.synchronize()
     got = dwd.cpu().permute(1, 2, 3, 0)      # OHWI -> HWIO
@@ -224,10 +231,79 @@ def test_large_shapes_linearity(lib):
     w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=gen) * (9 * Cin) ** -0.5).bfloat16()
     y = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.acnn_conv_fprop(g, x.data_ptr(), w.data_ptr(), y.data_ptr(), None, None, None,
-                                   None, None, 0, st))
+    _lib.check(lib.acnn_conv_fprop(g, x.data_ptr(), w.data_ptr(), y.data_ptr(), None, None,
+                                   None, None, 0, 0, 0, st))
     torch.cuda.synchronize()
     # sampled pixels vs the oracle (image 0 and the last image)
     for b in (0, B - 1):
         ref = _ref_conv(x[b:b + 1].float().cpu(), w.float().cpu().permute(1, 2, 3, 0), g)
         assert _relerr(y[b:b + 1].float().cpu(), ref) < BF16_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 parity mode: operands split into three bf16 planes (acnn_split3), six cross products in the
+# fp32 TMEM accumulator.  Inputs are full-precision fp32; tolerance 2e-6 relative to the output's
+# max magnitude against an fp64 oracle (fp32 rounding of the result itself is 6e-8).
+# ---------------------------------------------------------------------------------------------
+F32MODE_TOL = 2e-6
+
+
+def _planes(lib, t):
+    """fp32 CUDA tensor -> bf16 [3, ...] planes through the C ABI."""
+    from assembled_cnn_b200 import _lib
+    t = t.contiguous()
+    out = torch.empty((3,) + tuple(t.shape), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.acnn_split3(t.data_ptr(), out.data_ptr(), t.numel(),
+                               torch.cuda.current_stream().cuda_stream), "split3")
+    return out
+
+
+def test_split3_reconstructs_fp32(lib):
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(4096, generator=g) * torch.logspace(-6, 6, 4096)).cuda()
+    pl = _planes(lib, x)
+    torch.cuda.synchronize()
+    rec = pl[0].double() + pl[1].double() + pl[2].double()
+    assert ((rec - x.double()).abs() <= x.double().abs() * 2.0 ** -23).all()
+
+
+@pytest.mark.parametrize("case", CASES[:10], ids=[str(c) for c in CASES[:10]])
+def test_fp32_mode_fprop_dgrad_wgrad(lib, case):
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout, k, stride, pads = case
+    g = _geom(B, H, W, Cin, Cout, k, stride, pads)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, Cin, generator=gen)
+    w_hwio = torch.randn(g.kh, g.kw, Cin, Cout, generator=gen) * (g.kh * g.kw * Cin) ** -0.5
+    xr = x.double().requires_grad_(True)
+    wr = w_hwio.double().requires_grad_(True)
+    ref = _ref_conv(xr, wr, g)
+    dy = torch.randn(ref.shape, generator=gen)
+    dx_ref, dw_ref = torch.autograd.grad(ref, (xr, wr), dy.double())
+    Ho, Wo = g.out_hw()
+    st = torch.cuda.current_stream().cuda_stream
+    xp = _planes(lib, x.cuda())
+    wp = _planes(lib, w_hwio.permute(3, 0, 1, 2).contiguous().cuda())           # OHWI
+    y = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda")
+    _lib.check(lib.acnn_conv_fprop(g, xp.data_ptr(), wp.data_ptr(), y.data_ptr(), None, None, None,
+                                   None, 1, 1, wp[0].numel(), st), "conv_fprop fp32")
+    torch.cuda.synchronize()
+    assert _relerr(y.cpu(), ref.detach()) < F32MODE_TOL
+    # wgrad (deterministic: no split-K), twice -> bit-identical
+    dyp = _planes(lib, dy.cuda())
+    dws = []
+    for _ in range(2):
+        dw = torch.zeros(Cout, g.kh, g.kw, Cin, device="cuda")
+        _lib.check(lib.acnn_conv_wgrad(g, xp.data_ptr(), dyp.data_ptr(), dw.data_ptr(), 1, 1, st),
+                   "conv_wgrad fp32")
+        dws.append(dw)
+    torch.cuda.synchronize()
+    assert torch.equal(dws[0], dws[1])
+    assert _relerr(dws[0].cpu().permute(1, 2, 3, 0), dw_ref) < F32MODE_TOL
+    if stride == 1 and Cout % 16 == 0 and Cin % 32 == 0:
+        wdg = _planes(lib, w_hwio.flip(0, 1).permute(2, 0, 1, 3).contiguous().cuda())
+        dx = torch.full((B, H, W, Cin), float("nan"), device="cuda")
+        _lib.check(lib.acnn_conv_dgrad(g, dyp.data_ptr(), wdg.data_ptr(), dx.data_ptr(), None, None,
+                                       1, wdg[0].numel(), st), "conv_dgrad fp32")
+        torch.cuda.synchronize()
+        assert _relerr(dx.cpu(), dx_ref) < F32MODE_TOL

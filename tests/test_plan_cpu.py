@@ -28,9 +28,10 @@ CASES = {
 }
 
 
-def _setup(kw, d, mix, hw, B=4, dtype=torch.float64, training=True):
+def _setup(kw, d, mix, hw, B=4, dtype=torch.float64, training=True, plan_dtype="bf16"):
     cfg = ModelConfig(use_resnet_d=d, **kw)
-    plan = build_plan(cfg, B, hw, hw, training=training, mixup_type=mix, label_smoothing=0.1)
+    plan = build_plan(cfg, B, hw, hw, training=training, mixup_type=mix, label_smoothing=0.1,
+                      dtype=plan_dtype)
     model, vs = M.build(seed=42, dtype=dtype, input_hw=hw, use_resnet_d=d, **kw)
     g = torch.Generator().manual_seed(1)
     for n in vs.vars:
@@ -52,10 +53,21 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
+@pytest.mark.parametrize("plan_dtype", ["bf16", "fp32"])
 @pytest.mark.parametrize("name", list(CASES))
-def test_plan_train_step_matches_autograd_oracle(name):
+def test_plan_train_step_matches_autograd_oracle(name, plan_dtype):
     kw, d, mix, hw = CASES[name]
-    plan, model, vs, it, x, lab, lam1, lam2 = _setup(kw, d, mix, hw)
+    if plan_dtype == "fp32" and name not in ("assemble_rv2_mix1", "rv1_d_sk_sconv_mix2",
+                                             "rv2_se_proj5"):
+        pytest.skip("fp32 plan: three configurations cover every op kind")
+    plan, model, vs, it, x, lab, lam1, lam2 = _setup(kw, d, mix, hw, plan_dtype=plan_dtype)
+    if plan_dtype == "fp32":
+        # the parity mode's plan: fp32 tensors, operand planes, two-pass statistics, unfused
+        # dgrad epilogue -- same mathematics
+        assert plan.meta["dtype"] == "fp32"
+        assert any(o.kind == "split3" for o in plan.forward)
+        assert any(o.kind == "bn_stats" for o in plan.forward)
+        assert all(t.dtype != "bf16" or n.startswith("planes") for n, t in plan.tensors.items())
     names = [n for n in vs.vars if vs.trainable[n]]
     # same variables, same creation order, same TF-style names
     assert names == list(plan.params)

@@ -6,6 +6,9 @@ in isolation on identical inputs.
 Tolerances (relative to the output's max magnitude): bf16 tensors 2^-7 (one bf16 ulp at the top
 of the range: accumulation-order differences can flip a rounding), fp32 vectors 2e-3 where sums
 of bf16 data cancel (BN backward sums), 1e-4 otherwise.
+
+The fp32 parity mode (dtype='fp32': fp32 storage, 3-plane tcgen05 GEMMs) runs the same lock-step
+against the exact fp32 interpreter with every tensor at 2e-5 and the reductions at 2e-4.
 """
 import os
 import sys
@@ -26,8 +29,10 @@ def _outputs(op):
     T = lambda key: [("t", a[key])]
     S = lambda key: [("slot", a[key])]
     G = lambda *names: [("grad", n) for n in names]
-    if k in ("prep_weights",):
+    if k in ("prep_weights", "split3"):
         return []
+    if k == "bn_stats":
+        return [("slot", a["bn"].stats)]
     if k == "pack_input":
         return T("out")
     if k == "mix_labels":
@@ -35,7 +40,8 @@ def _outputs(op):
     if k == "s2d_weight_pack":
         return T("w2")
     if k == "conv":
-        return T("y") + (S("stats") if a.get("stats") is not None else [])
+        return T("y") + ([("parts", a["stats"], 2 * a["geom"].Cout)]
+                         if a.get("stats") is not None else [])
     if k == "bn_finalize":
         bn = a["bn"]
         return [("slot", bn.work), ("state", bn.mm), ("state", bn.mv)]
@@ -61,7 +67,7 @@ def _outputs(op):
     if k == "s2d_wgrad_unpack":
         return G(a["w"])
     if k in ("bn_bwd_reduce", "sk_bn_bwd_reduce"):
-        return S("sums")
+        return [("parts", a["sums"], 2 * a["bn"].C)]
     if k == "bn_bwd_finalize":
         return S("coef") + G(a["bn"].gamma, a["bn"].beta)
     if k in ("bn_bwd_apply", "sk_bn_bwd_apply"):
@@ -86,14 +92,18 @@ def _err(got, ref):
     return (got - ref).abs().max().item() / scale, scale
 
 
-def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbose=False):
+def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbose=False,
+             dtype="bf16"):
     H, W = (HW, HW) if isinstance(HW, int) else HW
     from oracle import model as M, plan_interp as PI
     from assembled_cnn_b200.plan import ModelConfig, build_plan
     from assembled_cnn_b200.runtime import Runtime
 
     cfg = ModelConfig(use_resnet_d=use_resnet_d, **cfg_kw)
-    plan = build_plan(cfg, B, H, W, training=training, mixup_type=mix, label_smoothing=0.1)
+    fp32 = dtype == "fp32"
+    bf16_tol, f32_tol = (2e-5, 2e-4) if fp32 else (BF16_TOL, F32_TOL)
+    plan = build_plan(cfg, B, H, W, training=training, mixup_type=mix, label_smoothing=0.1,
+                      dtype=dtype)
     _, vs = M.build(seed=42, input_hw=64, use_resnet_d=use_resnet_d, **cfg_kw)
     g = torch.Generator().manual_seed(3)
     for n in vs.vars:       # non-trivial BN parameters / statistics
@@ -103,7 +113,8 @@ def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbo
             vs.vars[n] = 0.1 * torch.randn(vs.vars[n].shape, generator=g)
         elif n.endswith("moving_variance"):
             vs.vars[n] = 0.5 + torch.rand(vs.vars[n].shape, generator=g)
-    it = PI.PlanInterpreter(plan, dtype=torch.float32, emulate_bf16=True)
+    it = PI.PlanInterpreter(plan, dtype=torch.float64 if fp32 else torch.float32,
+                            emulate_bf16=not fp32)
     rt = Runtime(plan)
     it.set_weights(vs.vars)
     rt.set_weights(vs.vars)
@@ -124,7 +135,7 @@ def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbo
     if mix == 2:
         feeds[m["lam2"]] = torch.rand(Bin // 2, generator=g)
     for name, v in feeds.items():
-        it.t[name] = v
+        it.t[name] = v.to(it.dtype) if v.is_floating_point() else v
         rt.t[name].copy_(v)
 
     worst = {}
@@ -137,15 +148,27 @@ def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbo
             kind = out[0]
             if kind == "t":
                 ref, got = it.t[out[1]], rt.t[out[1]]
-                tol = BF16_TOL if plan.tensors[out[1]].dtype == "bf16" else 1e-4
+                tol = bf16_tol if plan.tensors[out[1]].dtype == "bf16" else (2e-5 if fp32 else 1e-4)
                 force = lambda r=ref, gt=got: gt.copy_(r)
             elif kind == "slot":
                 ref, got = it.slot(out[1]), rt.slot_view(out[1])
-                tol = F32_TOL
+                tol = f32_tol
                 force = lambda r=ref, gt=got: gt.copy_(r)
+            elif kind == "parts":
+                # [parts][ncols] per-CTA partial rows on the GPU (unused rows stay zero); the
+                # interpreter keeps the total in row 0
+                ncols = out[2]
+                full = rt.slot_view(out[1])
+                ref = it.slot(out[1])[:ncols]
+                got = full.view(-1, ncols).double().sum(0)
+                tol = f32_tol
+
+                def force(r=ref, f=full, n=ncols):
+                    f.zero_()
+                    f[:n].copy_(r)
             elif kind == "grad":
                 ref, got = it.pview(out[1], it.grads), rt.pview(out[1], rt.grads)
-                tol = F32_TOL
+                tol = f32_tol
                 force = lambda r=ref, gt=got: gt.copy_(r)
             elif kind == "state":
                 ref, got = it.pview(out[1]), rt.pview(out[1])
@@ -188,6 +211,14 @@ def test_train_step_lockstep(name):
     assert not failures, "\n".join(failures[:20])
 
 
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_train_step_lockstep_fp32_mode(name):
+    """dtype='fp32' (the reference's default dtype): every op against the exact interpreter."""
+    kw, d, mix = CONFIGS[name]
+    failures, _ = lockstep(kw, d, B=4, HW=64, mix=mix, training=True, dtype="fp32")
+    assert not failures, "\n".join(failures[:20])
+
+
 def test_non_square_odd_batch_lockstep():
     """Ragged shapes: 64 x 96 input, batch 3 (no dimension is a multiple of a tile size)."""
     kw, d, _ = CONFIGS["assemble_rv2_sk_sconv_mix1"]
@@ -202,9 +233,10 @@ def test_eval_forward_lockstep():
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(CONFIGS)
+    dtype = "fp32" if "--fp32" in sys.argv else "bf16"
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CONFIGS)
     for n in names:
         kw, d, mix = CONFIGS[n]
-        print("=====", n, flush=True)
-        f, w = lockstep(kw, d, mix=mix, verbose=True)
+        print("=====", n, dtype, flush=True)
+        f, w = lockstep(kw, d, mix=mix, verbose=True, dtype=dtype)
         print("FAILURES:", len(f))

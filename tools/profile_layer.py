@@ -38,6 +38,7 @@ dx = torch.empty_like(x)
 dw = torch.zeros(a.Cout, a.k, a.k, a.Cin, device=dev)
 s1 = torch.zeros(a.Cout, device=dev)
 s2 = torch.zeros(a.Cout, device=dev)
+sp = torch.zeros(148, 2, a.Cout, device=dev)     # partial BN statistics rows
 st = torch.cuda.current_stream().cuda_stream
 flops = 2.0 * a.B * Ho * Wo * a.Cout * a.k * a.k * a.Cin
 
@@ -57,9 +58,9 @@ def timed(name, fn):
 
 if "fprop" in a.which:
     timed("fprop", lambda: _lib.check(lib.acnn_conv_fprop(
-        g, x.data_ptr(), w.data_ptr(), y.data_ptr(), s1.data_ptr(), s2.data_ptr(), None, None, None, 0, st)))
+        g, x.data_ptr(), w.data_ptr(), y.data_ptr(), sp.data_ptr(), None, None, None, 0, 0, 0, st)))
 if "dgrad" in a.which and a.stride == 1:
     timed("dgrad", lambda: _lib.check(lib.acnn_conv_dgrad(
-        g, dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), None, x.data_ptr(), st)))
+        g, dy.data_ptr(), wd.data_ptr(), dx.data_ptr(), None, x.data_ptr(), 0, 0, st)))
 if "wgrad" in a.which:
-    timed("wgrad", lambda: _lib.check(lib.acnn_conv_wgrad(g, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), st)))
+    timed("wgrad", lambda: _lib.check(lib.acnn_conv_wgrad(g, x.data_ptr(), dy.data_ptr(), dw.data_ptr(), 0, 0, st)))
