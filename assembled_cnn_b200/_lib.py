@@ -61,6 +61,8 @@ def _parse_header(path: str = HEADER_PATH) -> dict:
                     argtypes.append(c_void_p)
                 elif a.startswith("int64_t"):
                     argtypes.append(c_int64)
+                elif a.startswith("uint64_t"):
+                    argtypes.append(C.c_uint64)
                 elif a.startswith("float"):
                     argtypes.append(c_float)
                 elif a.startswith("int"):

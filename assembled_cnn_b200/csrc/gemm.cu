@@ -190,8 +190,13 @@ struct FpropCfg {
   static constexpr int kNHalf = BN / kHalfN;
   static constexpr int kSubW = kHalfN < 64 ? kHalfN : 64;  // staging sub-tile width (TMA box)
   static constexpr int kTileBytes = kBM * kHalfN * 2;      // one staged half tile (bf16)
-  static constexpr int kTmemCols = 2 * MT * BN < 32 ? 32 : 2 * MT * BN;   // two accumulator stages
-  static_assert(2 * MT * BN <= 512, "TMEM holds 512 columns");
+  // accumulator columns of one stage: MT tiles of BN columns; NP == 3 keeps TWO accumulators per
+  // tile -- the hi*hi products and the five small cross terms separately (added in the epilogue) --
+  // because the tensor core truncates an addend below the accumulator's ulp: small terms summed
+  // into the big accumulator lose ~6 bits each (measured 2e-5 relative at K = 4608)
+  static constexpr int kAccCols = (NP == 3 ? 2 : MT) * BN;
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // two accumulator stages
+  static_assert(2 * kAccCols <= 512 && (NP == 1 || MT == 1), "TMEM holds 512 columns");
   // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
   static int stages_for(bool has_add, bool has_mask, bool out_f32) {
     return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32);
@@ -381,7 +386,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);   // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * (MT * BN);
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
       for (int kb = 0; kb < num_kb; ++kb) {
         const bool last = kb == num_kb - 1;
         const int nch = (kChunks > 1 && last) ? tail_chunks : kChunks;
@@ -403,11 +408,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   for (int t = 0; t < (NP == 3 ? 6 : 1); ++t) {
                     const int pa = NP == 3 ? plane_term_a(t) : 0;
                     const int pb = NP == 3 ? plane_term_b(t) : 0;
-                    umma_bf16(tmem_d + h * BN,
+                    // NP == 3: t = 5 is hi*hi -> accumulator 0; t < 5 -> the small-term
+                    // accumulator at column offset BN (its first MMA of a tile is t = 0)
+                    const bool small = NP == 3 && t < 5;
+                    umma_bf16(tmem_d + h * BN + (small ? BN : 0),
                               da0 + ((pa * Cfg::kABytes + h * Cfg::kAHalfBytes + j * kChunkBytes +
                                       ks * 32) >> 4),
                               db0 + ((pb * Cfg::kBBytes + (j * kKSteps + ks) * 32) >> 4), kIdesc,
-                              (j | ks | t) ? 1u : static_cast<uint32_t>(kb != 0));
+                              (j | ks | (small ? t : 0)) ? 1u : static_cast<uint32_t>(kb != 0));
                   }
                 }
               }
@@ -453,7 +461,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int mh = 0; mh < MT; ++mh) {
       const int m0 = (m_first + it * m_step) * kTileM + mh * kBM;
-      const uint32_t acc_col = acc * (MT * BN) + mh * BN;
+      const uint32_t acc_col = acc * Cfg::kAccCols + mh * BN;
       const int row = m0 + r;
       const bool row_ok = row < p.M;
 #pragma unroll
@@ -494,6 +502,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (NP == 3) {   // + the small-term accumulator
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc_col + BN +
+                              hf * kHalfN + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] += __uint_as_float(v[i]);
+          }
           const int col0 = nh + c * 32;
           const int sub = (c * 32) / kSubW;
           const int j0 = ((c * 32) % kSubW) / 8;
@@ -659,8 +674,11 @@ struct WgradCfg {
               : (MT == 1 ? ((BN >= 256) ? 4 : ((BN == 128) ? 3 : 4))
                          : (kStagesFit > 5 ? 5 : kStagesFit));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
-  static constexpr int kTmemCols = MT * BN < 32 ? 32 : MT * BN;
-  static_assert(MT * BN <= 512 && kStages >= (NP == 3 ? 2 : 3), "wgrad tile does not fit");
+  // NP == 3: a second accumulator (columns BN..2BN) for the small cross terms, see FpropCfg
+  static constexpr int kAccCols = (NP == 3 ? 2 : MT) * BN;
+  static constexpr int kTmemCols = kAccCols < 32 ? 32 : kAccCols;
+  static_assert(kAccCols <= 512 && (NP == 1 || MT == 1) && kStages >= (NP == 3 ? 2 : 3),
+                "wgrad tile does not fit");
 };
 
 // CW: channel width of one im2col chunk of x (16/32/64), CWB: channel width of one dy chunk.
@@ -798,10 +816,11 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               for (int t = 0; t < (NP == 3 ? 6 : 1); ++t) {
                 const int pa = NP == 3 ? plane_term_a(t) : 0;
                 const int pb = NP == 3 ? plane_term_b(t) : 0;
-                umma_bf16(tmem_base + h * BN,
+                const bool small = NP == 3 && t < 5;
+                umma_bf16(tmem_base + h * BN + (small ? BN : 0),
                           da0 + ((pa * Cfg::kABytes + h * Cfg::kAHalfBytes + ks * 16 * CW * 2) >> 4),
                           db0 + ((pb * Cfg::kBBytes + ks * 16 * CWB * 2) >> 4), kIdesc,
-                          (it | ks | t) ? 1u : 0u);
+                          (it | ks | (small ? t : 0)) ? 1u : 0u);
               }
             }
           }
@@ -829,6 +848,14 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + h * BN + c * 32,
                       v);
         tmem_ld_wait();
+        if (NP == 3) {   // + the small-term accumulator
+          uint32_t v2[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + BN + c * 32, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(v2[i]));
+        }
         if (n_ok) {
           float* dst = p.dw + static_cast<size_t>(co0 + c * 32) * p.Ktot + n;
 #pragma unroll

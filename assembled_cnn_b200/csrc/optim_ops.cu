@@ -172,19 +172,30 @@ sgd_momentum_kernel(float* __restrict__ w, const float* __restrict__ grad, float
     for (int o = 16; o > 0; o >>= 1) l2 += __shfl_xor_sync(0xffffffffu, l2, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = l2;
     __syncthreads();
+    // per-CTA partial, then the LAST CTA to arrive adds all partials in a fixed pattern (thread t
+    // takes partials t, t+256, ...; the 256 thread sums are added in index order): deterministic,
+    // the arrival order does not enter the sum
+    __shared__ bool is_last;
+    __shared__ float tsum[256];
+    unsigned int* counter = reinterpret_cast<unsigned int*>(l2_part + gridDim.x);
     if (threadIdx.x == 0) {
       float s = 0.f;
       for (int k = 0; k < 8; ++k) s += sh[k];
-      // per-CTA partial, then the LAST CTA to arrive adds all partials in index order:
-      // deterministic (the arrival order does not enter the sum)
       l2_part[blockIdx.x] = s;
       __threadfence();
-      unsigned int* counter = reinterpret_cast<unsigned int*>(l2_part + gridDim.x);
       const unsigned int prev = atomicAdd(counter, 1u);
-      if (prev == gridDim.x - 1) {
-        __threadfence();
+      is_last = prev == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      float t = 0.f;
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += 256) t += __ldcg(l2_part + b);
+      tsum[threadIdx.x] = t;
+      __syncthreads();
+      if (threadIdx.x == 0) {
         float tot = 0.f;
-        for (unsigned int b = 0; b < gridDim.x; ++b) tot += __ldcg(l2_part + b);
+        for (int k = 0; k < 256; ++k) tot += tsum[k];
         l2_acc[0] += 0.5f * wd * tot;
         *counter = 0u;
       }

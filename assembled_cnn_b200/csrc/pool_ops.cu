@@ -516,8 +516,9 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sh) {
 
 template <class T>
 __global__ void __launch_bounds__(kPT)
-softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y, int B, int NC,
-                  int ld, float ls, float grad_scale, float* __restrict__ loss_rows,
+softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y,
+                  const float* __restrict__ yt, float kd_temp, int B, int NC, int ld, float ls,
+                  float grad_scale, float* __restrict__ loss_rows, float* __restrict__ kd_rows,
                   float* __restrict__ g32, T* __restrict__ dlogits) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
   __shared__ float sh[kPT / 32];
@@ -542,12 +543,31 @@ softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y,
   const float lse = mx + logf(se);
   // per-example loss (already / B); summed in a fixed order by ce_finalize_kernel
   if (threadIdx.x == 0) loss_rows[b] = (lse * sy - syl) / B;
+  // knowledge distillation (run_loop_classification.py:156-162): T^2 * CE(logits / T, teacher),
+  // no label smoothing; d/dlogits = T * (softmax(logits / T) * sum(t) - t) / B
+  const float* tt = yt ? yt + (size_t)b * NC : nullptr;
+  float lse_t = 0.f, st = 0.f, inv_t = 0.f;
+  if (tt) {
+    inv_t = 1.f / kd_temp;
+    float se_t = 0.f, stl = 0.f;
+    for (int c = threadIdx.x; c < NC; c += kPT) {
+      se_t += expf((lg[c] - mx) * inv_t);
+      st += tt[c];
+      stl += tt[c] * lg[c] * inv_t;
+    }
+    se_t = block_reduce(se_t, false, sh);
+    st = block_reduce(st, false, sh);
+    stl = block_reduce(stl, false, sh);
+    lse_t = mx * inv_t + logf(se_t);
+    if (threadIdx.x == 0) kd_rows[b] = kd_temp * kd_temp * (lse_t * st - stl) / B;
+  }
   const float gs = grad_scale / B;
   for (int c = threadIdx.x; c < ld; c += kPT) {
     float g = 0.f;
     if (c < NC) {
       const float yp = yy[c] * (1.f - ls) + unif;
       g = (expf(lg[c] - lse) * sy - yp) * gs;
+      if (tt) g += kd_temp * (expf(lg[c] * inv_t - lse_t) * st - tt[c]) * gs;
     }
     g32[(size_t)b * ld + c] = g;
     store1(dlogits + (size_t)b * ld + c, g);
@@ -557,17 +577,27 @@ softmax_ce_kernel(const float* __restrict__ logits, const float* __restrict__ y,
 // loss_acc[0] += sum_b loss_rows[b]; dbias[c] += sum_b g32[b][c] -- one thread per column, rows in
 // order: deterministic (no atomics).  One CTA.
 __global__ void __launch_bounds__(1024)
-ce_finalize_kernel(const float* __restrict__ loss_rows, const float* __restrict__ g32, int B, int NC,
-                   int ld, float* loss_acc, float* dbias) {
+ce_finalize_kernel(const float* __restrict__ loss_rows, const float* __restrict__ kd_rows,
+                   const float* __restrict__ g32, int B, int NC, int ld, float* loss_acc,
+                   float* dbias) {
   pdl_entry();
-  for (int c = threadIdx.x; c <= NC; c += blockDim.x) {
-    if (c == NC) {
+  for (int c = threadIdx.x; c <= NC + 1; c += blockDim.x) {
+    if (c == NC + 1) {
+      if (kd_rows) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int b = 0; b < B; ++b) s += __ldg(kd_rows + b);
+        loss_acc[2] += s;
+      }
+    } else if (c == NC) {
       float s = 0.f;
-      for (int b = 0; b < B; ++b) s += loss_rows[b];
+#pragma unroll 8
+      for (int b = 0; b < B; ++b) s += __ldg(loss_rows + b);
       loss_acc[0] += s;
     } else if (dbias) {
       float s = 0.f;
-      for (int b = 0; b < B; ++b) s += g32[(size_t)b * ld + c];
+#pragma unroll 8
+      for (int b = 0; b < B; ++b) s += __ldg(g32 + (size_t)b * ld + c);
       dbias[c] += s;
     }
   }
@@ -760,21 +790,24 @@ int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2,
   return check_launch("mix_labels");
 }
 
-int acnn_softmax_ce(const float* logits, const float* y, int B, int NC, int ld,
-                    float label_smoothing, float grad_scale, float* loss_acc, void* dlogits,
-                    float* dbias, float* work, int dtype, void* stream) {
+int acnn_softmax_ce(const float* logits, const float* y, const float* teacher, float kd_temp, int B,
+                    int NC, int ld, float label_smoothing, float grad_scale, float* loss_acc,
+                    void* dlogits, float* dbias, float* work, int dtype, void* stream) {
   ACNN_REQUIRE(logits && y && loss_acc && dlogits && work && NC <= ld && B > 0 &&
-                   ACNN_DTYPE_OK(dtype), "softmax_ce: bad arguments");
-  float* loss_rows = work;                     // [B]
-  float* g32 = work + ((B + 31) / 32) * 32;    // [B][ld]
+                   ACNN_DTYPE_OK(dtype) && (!teacher || kd_temp > 0.f), "softmax_ce: bad arguments");
+  const int Bp = ((B + 31) / 32) * 32;
+  float* loss_rows = work;                     // [Bp]
+  float* kd_rows = work + Bp;                  // [Bp]
+  float* g32 = work + 2 * Bp;                  // [B][ld]
   ACNN_BY_DTYPE(dtype, launch_k(softmax_ce_kernel<T>, dim3(B), dim3(kPT), 0, (cudaStream_t)stream,
-                                logits, y, B, NC, ld, label_smoothing, grad_scale, loss_rows, g32,
-                                (T*)dlogits));
+                                logits, y, teacher, kd_temp, B, NC, ld, label_smoothing, grad_scale,
+                                loss_rows, kd_rows, g32, (T*)dlogits));
   count_launch();
   int rc = check_launch("softmax_ce");
   if (rc) return rc;
   launch_k(ce_finalize_kernel, dim3(1), dim3(1024), 0, (cudaStream_t)stream,
-           (const float*)loss_rows, (const float*)g32, B, NC, ld, loss_acc, dbias);
+           (const float*)loss_rows, teacher ? (const float*)kd_rows : (const float*)nullptr,
+           (const float*)g32, B, NC, ld, loss_acc, dbias);
   count_launch();
   return check_launch("ce_finalize");
 }

@@ -20,9 +20,10 @@ from collections import namedtuple
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, dp
 from .hparams import DATASETS, DEFAULTS, params_from_flags
 from .plan import BLOCK_SIZES, ModelConfig, build_plan
+from .metrics import EvalMetrics
 from .runtime import Runtime
 
 DEFAULT_VERSION = 1
@@ -132,15 +133,16 @@ class Model:
 
     # ---------------------------------------------------------------- runtimes / parameters
     def runtime(self, batch, height, width, *, training, use_resnet_d=False, mixup_type=0,
-                label_smoothing=0.0, with_loss=False) -> Runtime:
+                label_smoothing=0.0, with_loss=False, use_dropblock=False, kd_temp=0.0) -> Runtime:
         key = (batch, height, width, bool(training), bool(use_resnet_d), mixup_type,
-               float(label_smoothing), bool(with_loss or training))
+               float(label_smoothing), bool(with_loss or training), bool(use_dropblock and training),
+               float(kd_temp) if training else 0.0)
         rt = self._runtimes.get(key)
         if rt is None:
             cfg = ModelConfig(use_resnet_d=bool(use_resnet_d), **self.cfg_kwargs)
             plan = build_plan(cfg, batch, height, width, training=training, mixup_type=mixup_type,
                               label_smoothing=label_smoothing, with_loss=with_loss,
-                              dtype=self.dtype)
+                              dtype=self.dtype, use_dropblock=use_dropblock, kd_temp=kd_temp)
             prim = self._primary.get(bool(use_resnet_d))
             rt = Runtime(plan, self.device, share=prim)
             if prim is None:
@@ -195,8 +197,9 @@ class Model:
                  return_embedding=False):
         """nets/resnet_model.py:305-599.  inputs: float32 [N,H,W,3] NHWC (CPU or CUDA tensor).
         Returns logits [N, num_classes] fp32 on the GPU (or the pooled embedding [N, C])."""
-        if not (isinstance(keep_prob, float) and keep_prob == 1.0):
-            raise NotImplementedError("DropBlock (keep_prob != 1.0) is a SURVEY 8(f) 'next' row")
+        # keep_prob == 1.0 (a Python float) is the reference's "DropBlock off" (nets/blocks.py:209);
+        # anything else runs the DropBlock plan in training mode (inference ignores it, :205)
+        use_db = bool(training) and not (isinstance(keep_prob, float) and keep_prob == 1.0)
         if use_resnet_d is None:
             # the reference's call-time default is False (nets/resnet_model.py:308); build_model()
             # records the flag it was given as the default of this model's calls
@@ -206,17 +209,25 @@ class Model:
             raise ValueError("inputs must be [N, H, W, 3] (NHWC)")
         n, h, w, _ = inputs.shape
         rt = self.runtime(n, h, w, training=False, use_resnet_d=use_resnet_d) if not training \
-            else self.runtime(n, h, w, training=True, use_resnet_d=use_resnet_d)
+            else self.runtime(n, h, w, training=True, use_resnet_d=use_resnet_d,
+                              use_dropblock=use_db)
         m = rt.plan.meta
         rt.t[m["images"]].copy_(inputs.to(torch.float32), non_blocking=True)
         if training:
+            if use_db:
+                self._fwd_calls = getattr(self, "_fwd_calls", 0) + 1
+                rt.set_hparams(keep_prob=float(keep_prob), step=self._fwd_calls)
             rt.zero_step_buffers()
-            fwd = [op for op in rt.plan.forward if op.kind not in ("mix_labels", "softmax_ce")]
+            fwd = [op for op in rt.plan.forward
+                   if op.kind not in ("mix_labels", "softmax_ce", "kd_teacher")]
             rt.run(fwd)
         else:
             rt.run_forward()
         if return_embedding:
-            return rt.t[m["pooled"]].float()
+            # nets/resnet_model.py:586-590: the (BN-normalised) embedding when embedding_size > 0,
+            # else the pooled features
+            feat = rt.t[m["embedding"]] if "embedding" in m else rt.t[m["pooled"]]
+            return feat.reshape(n, -1).float()
         return rt.t[m["logits"]][:, :self.num_classes]
 
 
@@ -246,10 +257,6 @@ class Trainer:
     def __init__(self, model: Model, params: dict, height=224, width=224, *, use_cuda_graph=True,
                  lam_seed=7):
         p = params
-        if p.get("kd_temp", 0) > 0:
-            raise NotImplementedError("knowledge distillation is a SURVEY 8(f) 'next' row")
-        if p.get("use_dropblock", False):
-            raise NotImplementedError("DropBlock is a SURVEY 8(f) 'next' row")
         if p.get("cls_loss_type", "softmax") != "softmax":
             raise NotImplementedError("only cls_loss_type='softmax' is on the hot path")
         self.model = model
@@ -262,11 +269,20 @@ class Trainer:
                              .format(self.world, p["batch_size"]))
         self.local_batch = p["batch_size"] // self.world
         self.mixup_type = int(p.get("mixup_type", 0))
+        self.kd_temp = float(p.get("kd_temp", 0) or 0)
+        self.use_dropblock = bool(p.get("use_dropblock", False))
         self.rt = model.runtime(self.local_batch, height, width, training=True,
                                 use_resnet_d=p.get("use_resnet_d", False),
                                 mixup_type=self.mixup_type,
-                                label_smoothing=float(p.get("label_smoothing", 0.0)))
+                                label_smoothing=float(p.get("label_smoothing", 0.0)),
+                                use_dropblock=self.use_dropblock, kd_temp=self.kd_temp)
         ds = DATASETS[p.get("dataset_name") or "imagenet"]
+        # functions/model_fns.py:221-228: keep_prob decays linearly over the whole run
+        self.keep_prob_fn = None
+        if self.use_dropblock:
+            kp0, kp1 = p["dropblock_kp"]
+            bpe = ds["num_images"]["train"] / p["batch_size"]
+            self.keep_prob_fn = keep_prob_decay(kp0, kp1, int(p["train_epochs"] * bpe))
         self.learning_rate_fn = learning_rate_with_decay(
             learning_rate_decay_type=p["learning_rate_decay_type"], batch_size=p["batch_size"],
             batch_denom=p["batch_size"], num_images=ds["num_images"]["train"],
@@ -288,8 +304,17 @@ class Trainer:
         self.labels_buf = self.rt.t[m["labels"]]
         self.lam1_buf = self.rt.t[m["lam1"]] if "lam1" in m else None
         self.lam2_buf = self.rt.t[m["lam2"]] if "lam2" in m else None
-        self._hp_host = torch.zeros(4, dtype=torch.float32).pin_memory()
-        self._loss_slot = self.rt.slot_view(m["loss"])
+        self.teacher_buf = self.rt.t[m["teacher_logits"]] if "teacher_logits" in m else None
+        # hyper-parameters reach the device through a RING of pinned host buffers (one per step in
+        # flight, guarded by an event): the host may run several steps ahead of the GPU, and a
+        # single buffer would be overwritten before its asynchronous copy has executed
+        self._hp_ring = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._hp_events = [None] * len(self._hp_ring)
+        self._loss_slot = self.rt.slot_view(m["loss"])[:3 if self.kd_temp > 0 else 2]
+        self._buckets = self._segments = None
+        if self.world > 1:
+            self._buckets = dp.grad_buckets(self.rt.plan)
+            self._segments = dp.backward_segments(self.rt.plan, self._buckets)
         # input double-buffering: prefetch() copies the NEXT batch host->device on a side stream
         # while the current step computes; train_step() then takes it with a device-side copy
         self._copy_stream = torch.cuda.Stream(self.rt.dev)
@@ -314,9 +339,20 @@ class Trainer:
         rt.state.copy_(state_backup)
         s = torch.cuda.Stream(rt.dev)
         s.wait_stream(torch.cuda.current_stream(rt.dev))
+        # one graph for forward + backward on a single GPU; with data parallelism the backward is cut
+        # at the gradient-bucket boundaries (the all-reduces are issued between the graph replays)
+        fns = [self._fwd_bwd]
+        if self.world > 1:
+            bwd = rt.plan.backward
+            fns = []
+            for k, (a, b) in enumerate(self._segments):
+                if k == 0:
+                    fns.append(lambda ops=bwd[a:b]: (rt.run_forward(), rt.run(ops)))
+                else:
+                    fns.append(lambda ops=bwd[a:b]: rt.run(ops))
         graphs = []
         with torch.cuda.stream(s):
-            for fn in (self._fwd_bwd, lambda: rt.run(rt.plan.update)):
+            for fn in fns + [lambda: rt.run(rt.plan.update)]:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=s):
                     fn()
@@ -350,10 +386,13 @@ class Trainer:
             ev.record(cs)
         self._staged = ev
 
-    def train_step(self, images=None, labels=None, lam1=None, lam2=None):
+    def train_step(self, images=None, labels=None, lam1=None, lam2=None, teacher_logits=None,
+                   keep_prob=None):
         """images fp32 [input_batch,H,W,3] and int32 labels [input_batch] (pinned host or device),
-        or None to consume the batch given to prefetch().
-        Returns the device tensor [cross_entropy, l2_loss] of this replica (read it with
+        or None to consume the batch given to prefetch().  teacher_logits fp32 [input_batch, classes]
+        when kd_temp > 0 (the second half of the reference's KD label tensor).  keep_prob overrides
+        the DropBlock schedule for this step.
+        Returns the device tensor [cross_entropy, l2_loss(, kd_loss)] of this replica (read it with
         .tolist() -- that read is the only host sync of the step)."""
         rt = self.rt
         if images is None:
@@ -376,40 +415,97 @@ class Trainer:
                 if lam2 is None:
                     lam2 = torch.from_numpy(self.rng.beta(0.2, 0.2, n).astype(np.float32))
                 self.lam2_buf.copy_(torch.as_tensor(lam2, dtype=torch.float32), non_blocking=True)
+        if self.kd_temp > 0:
+            if teacher_logits is None:
+                raise ValueError("kd_temp > 0: train_step needs teacher_logits")
+            self.teacher_buf.copy_(torch.as_tensor(teacher_logits, dtype=torch.float32),
+                                   non_blocking=True)
         lr = self.learning_rate_fn(self.global_step)
-        self._hp_host[0] = lr
-        self._hp_host[1] = self.p["momentum"]
-        self._hp_host[2] = self.p["weight_decay"]
-        self._hp_host[3] = 1.0 / (self.world * self.loss_scale)
-        rt.hp.copy_(self._hp_host, non_blocking=True)
+        slot = self.global_step % len(self._hp_ring)
+        if self._hp_events[slot] is not None:
+            self._hp_events[slot].synchronize()          # its copy of 4 steps ago has executed
+        hp = self._hp_ring[slot]
+        hp[0] = lr
+        hp[1] = self.p["momentum"]
+        hp[2] = self.p["weight_decay"]
+        hp[3] = 1.0 / (self.world * self.loss_scale)
+        if keep_prob is None:
+            keep_prob = self.keep_prob_fn(self.global_step) if self.keep_prob_fn else 1.0
+        hp[4] = keep_prob
+        hp.view(torch.int32)[5] = self.global_step & 0x7fffffff      # Philox counter of the masks
+        rt.hp.copy_(hp, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(rt.dev))
+        self._hp_events[slot] = ev
         if self.use_graph and self._graphs is None:
             self._capture()
-        if self.use_graph:
-            self._graphs[0].replay()
+        if self.world == 1:
+            if self.use_graph:
+                self._graphs[0].replay()
+            else:
+                self._fwd_bwd()
         else:
-            self._fwd_bwd()
-        if self.world > 1:
-            # MirroredStrategy semantics: sum of per-replica gradients, 1/N folded
-            # into the SGD kernel's grad_scale; one NCCL all-reduce of the flat buffer per step.
-            torch.distributed.all_reduce(rt.grads)
+            self._fwd_bwd_allreduce()
         if self.use_graph:
-            self._graphs[1].replay()
+            self._graphs[-1].replay()
         else:
             rt.run(rt.plan.update)
+        if self.world > 1:
+            self.sync_moving_statistics()
         self.global_step += 1
         self.last_lr = lr
+        self.last_keep_prob = keep_prob
         return self._loss_slot
+
+    # ---------------------------------------------------------------- data parallelism
+    def sync_moving_statistics(self):
+        """MirroredStrategy keeps the BN moving statistics as mirrored variables whose per-replica
+        updates are MEAN-aggregated (official/utils/misc/distribution_utils.py:24-45)."""
+        dp.average_moving_statistics(self.rt.state, self.world)
+
+    def _fwd_bwd_allreduce(self):
+        """forward + backward with the gradient all-reduce overlapped: the backward is cut into
+        segments (each its own CUDA graph), and as soon as a segment has produced the last gradient
+        of a bucket that bucket is all-reduced asynchronously on NCCL's stream while the next
+        segment computes (assembled_cnn_b200/dp.py)."""
+        rt = self.rt
+        works, k = [], 0
+        for ev in dp.schedule(self._buckets, self._segments):
+            if ev[0] == "run":
+                if self.use_graph:
+                    self._graphs[k].replay()
+                else:
+                    if k == 0:
+                        rt.run_forward()
+                    rt.run(rt.plan.backward[ev[1]:ev[2]])
+                k += 1
+            else:
+                works.append(dp.all_reduce_bucket(rt.grads, ev[1], ev[2], async_op=True))
+        for w in works:
+            w.wait()            # stream-level wait: the update runs after every bucket
 
 
 _TRAINERS = {}
 
 
+def l2_loss(rt: Runtime, weight_decay: float):
+    """weight_decay * sum over the decayed variables of |v|^2 / 2 (run_loop_classification.py:
+    166-177), from the flat master buffer and its per-256-element decay flags.  TRAIN gets the same
+    number from the SGD kernel; this is the EVAL-mode path (a reduction over 42 M floats, once per
+    evaluation batch)."""
+    w = rt.params.view(-1, 256)
+    return 0.5 * weight_decay * (w[rt.decay_flags.bool()[:w.shape[0]]].double() ** 2).sum().float()
+
+
 def model_fn_cls(features, labels, mode, params):
     """functions/model_fns.py:201-239 -> nets/run_loop_classification.py:60-234.
 
-    features: {'image': float32 [N,H,W,3]} (or the tensor itself in PREDICT mode), labels: int32 [N].
-    TRAIN executes one training step and returns the spec with its loss; EVAL returns loss and
-    predictions of a forward pass with moving statistics; PREDICT only predictions.
+    features: {'image': float32 [N,H,W,3]} (or the tensor itself in PREDICT mode), labels: int32 [N]
+    -- or, with kd_temp > 0, the reference's float KD label tensor [N, 2*num_classes] = one-hot
+    labels ++ teacher logits (nets/run_loop_classification.py:86-93).
+    TRAIN executes one training step and returns the spec with its loss; EVAL returns loss
+    (cross-entropy + L2, as the reference) and predictions of a forward pass with moving statistics
+    plus the accuracy / top-5 / ECE metrics; PREDICT only predictions.
     """
     if int(params["resnet_size"]) < 50:
         assert not params.get("use_dropblock")
@@ -442,11 +538,20 @@ def model_fn_cls(features, labels, mode, params):
     if mode == PREDICT:
         logits = model(images, False, False, use_resnet_d=p["use_resnet_d"])
         return EstimatorSpec(mode, predictions_of(logits), None, None, None)
+    teacher_logits = None
+    if mode != PREDICT and p.get("kd_temp", 0) > 0:
+        kd_labels = torch.as_tensor(labels, dtype=torch.float32)
+        if kd_labels.dim() != 2 or kd_labels.shape[1] != 2 * ds["num_classes"]:
+            raise ValueError("kd_temp > 0: labels must be [N, 2*num_classes] (one-hot ++ teacher "
+                             "logits, nets/run_loop_classification.py:86-93)")
+        onehot, teacher_logits = kd_labels.split(ds["num_classes"], dim=1)
+        labels = onehot.argmax(dim=1).to(torch.int32)
     if mode == TRAIN:
         if entry["trainer"] is None:
             entry["trainer"] = Trainer(model, p, images.shape[1], images.shape[2])
         tr = entry["trainer"]
-        loss = tr.train_step(images, torch.as_tensor(labels, dtype=torch.int32))
+        loss = tr.train_step(images, torch.as_tensor(labels, dtype=torch.int32),
+                             teacher_logits=teacher_logits)
         m = tr.rt.plan.meta
         logits = tr.rt.t[m["logits"]][:, :model.num_classes]
         return EstimatorSpec(mode, predictions_of(logits), loss.sum(), tr, None)
@@ -461,7 +566,24 @@ def model_fn_cls(features, labels, mode, params):
         logits = rt.t[m["logits"]][:, :model.num_classes]
         lab = rt.t[m["labels"]].long()
         pred = predictions_of(logits)
-        metrics = {"accuracy": (pred["classes"] == lab).float().mean(),
-                   "accuracy_top_5": (logits.topk(5, dim=1).indices == lab[:, None]).any(1).float().mean()}
-        return EstimatorSpec(mode, pred, rt.slot_view(m["loss"])[0], None, metrics)
+        # eval_metric_ops are streaming in the reference (tf.metrics.*): they accumulate over the
+        # batches of one evaluation; reset with model_fn_cls.reset_metrics(params)
+        em = entry.setdefault("metrics", EvalMetrics(device=logits.device))
+        metrics = em.update(logits, lab)
+        # loss = cross_entropy + l2_loss in EVAL too (nets/run_loop_classification.py:166-179)
+        loss = rt.slot_view(m["loss"])[0] + l2_loss(rt, p["weight_decay"])
+        if teacher_logits is not None:
+            t = torch.softmax(teacher_logits.to(logits.device) / p["kd_temp"], dim=1)
+            loss = loss + p["kd_temp"] ** 2 * -(t * torch.log_softmax(logits / p["kd_temp"], 1)
+                                                ).sum(1).mean()
+        return EstimatorSpec(mode, pred, loss, None, metrics)
     raise ValueError("unknown mode %r" % (mode,))
+
+
+def reset_metrics(params=None):
+    """Start a new evaluation: drop the streaming accuracy / ECE accumulators."""
+    for entry in _TRAINERS.values():
+        entry.pop("metrics", None)
+
+
+model_fn_cls.reset_metrics = reset_metrics

@@ -162,11 +162,10 @@ class ModelConfig:
             raise ValueError("Could not find layers for selected Resnet size.\nSize received: {}; "
                              "sizes allowed: {}.".format(
                                  self.resnet_size, BLOCK_SIZES[self.resnet_version].keys()))
-        if self.pool_type != "gap":
-            raise NotImplementedError("pool_type=%r: GeM / flatten heads are SURVEY 8(f) 'next' rows"
-                                      % self.pool_type)
-        if self.embedding_size:
-            raise NotImplementedError("embedding head is a SURVEY 8(f) 'next' row")
+        if self.pool_type not in ("gap", "gem", "flatten"):
+            raise NotImplementedError("pool_type=%r (nets/resnet_model.py:560-573)" % self.pool_type)
+        if self.embedding_size and self.embedding_size % 32:
+            raise ValueError("embedding_size must be a multiple of 32 (tensor-core N tile)")
         if self.loss_type != "softmax":
             raise NotImplementedError("only the softmax loss is on the hot path (SURVEY 8a a11)")
         if self.anti_alias_type and self.anti_alias_filter_size not in range(1, 8):
@@ -198,8 +197,16 @@ class Plan:
 class PlanBuilder:
     def __init__(self, cfg: ModelConfig, batch: int, height: int = 224, width: int = 224, *,
                  training: bool = True, mixup_type: int = 0, label_smoothing: float = 0.0,
-                 with_loss: bool = True, dtype: str = "bf16"):
+                 with_loss: bool = True, dtype: str = "bf16", use_dropblock: bool = False,
+                 kd_temp: float = 0.0):
         cfg.validate()
+        # DropBlock (nets/blocks.py:187-251) is active in training only; its keep probability is a
+        # device scalar (hp[4]) because it follows a schedule (functions/model_fns.py:221-228)
+        self.use_dropblock = bool(use_dropblock) and training
+        if self.use_dropblock and cfg.use_se_block:
+            raise NotImplementedError("use_dropblock together with use_se_block")
+        self.kd_temp = float(kd_temp) if training else 0.0
+        self._identity_bns = {}
         if dtype not in ("bf16", "fp32"):
             raise ValueError("dtype must be one of: ('bf16', 'fp32')")
         # fp32 = the reference's default dtype (nets/resnet_model.py:30-33): fp32 activation storage,
@@ -226,7 +233,8 @@ class PlanBuilder:
         p.meta.update(batch=batch, height=height, width=width, training=training,
                       mixup_type=self.mixup_type, label_smoothing=label_smoothing,
                       num_classes=cfg.num_classes, ld_logits=_round_up(cfg.num_classes, 128),
-                      bn_momentum=cfg.bn_momentum, dtype=dtype,
+                      bn_momentum=cfg.bn_momentum, dtype=dtype, use_dropblock=self.use_dropblock,
+                      kd_temp=self.kd_temp, dropblock_u=[], ones=[],
                       input_batch=batch * 2 if self.mixup_type == 1 else batch)
         self._build(height, width)
 
@@ -423,7 +431,10 @@ class PlanBuilder:
         self.emit("conv", x=x0.name, xp=self.planes(x0.name), w=stem["w2"].name,
                   wp=self.planes(stem["w2"].name), y=y.name, geom=g,
                   stats=bn.stats if (self.training and not self.fp32) else None, bias=None,
-                  out_f32=False, w_is_tensor=True, x_wpad=(lo2, hi2))
+                  out_f32=False, w_is_tensor=True, x_wpad=(lo2, hi2),
+                  alg_macs=B * H2 * W2 * filters * k * k * 3)   # the k x k x 3 conv, not its
+        # zero-padded k2 x k2 x 16 space-to-depth form (bench.py's roofline counts algorithmic work)
+        stem["alg_macs"] = B * H2 * W2 * filters * k * k * 3
         self.emit_bn_finalize(bn, y, g, (lo2, hi2))
         return ConvOut(x0, y, g, w.name, bn, stem)
 
@@ -435,6 +446,58 @@ class PlanBuilder:
                   bn_b=(b.bn if b_mode == 1 else None), b_mode=b_mode, gate=gate, relu=relu,
                   out=out.name, shape=co.y.shape)
         return out
+
+    # -- DropBlock -----------------------------------------------------------------------------
+    def identity_bn(self, C):
+        """scale = 1, shift = 0: lets bn_act consume an already-normalised tensor."""
+        bn = self._identity_bns.get(C)
+        if bn is None:
+            work = self.slot("work", 4 * C)
+            self.plan.meta["ones"].append((work.offset, C))        # runtime presets scale = 1
+            bn = self._identity_bns[C] = BN(C, None, None, None, None, 0, None, work)
+        return bn
+
+    def dropblock_mask(self, H, W, C, gamma_scale, block_size=7):
+        """One DropBlock call of the reference = one mask [H,W,C] shared by the batch + its
+        renormalisation factor (op `dropblock_mask`, forward list)."""
+        if H < block_size or W < block_size:
+            raise ValueError("dropblock: feature map %dx%d smaller than block_size %d (the reference "
+                             "fails the same way: nets/blocks.py:222-229)" % (H, W, block_size))
+        hs, ws = H - block_size + 1, W - block_size + 1
+        u = self.tensor("dropblock_u", (hs, ws, C), "f32")
+        index = len(self.plan.meta["dropblock_u"])
+        self.plan.meta["dropblock_u"].append(u.name)
+        m = dict(keep=self.slot("work", H * W * C), scale=self.slot("work", 1),
+                 scratch=self.slot("work", hs * ws * C + (H * W * C + 255) // 256),
+                 H=H, W=W, C=C, gamma_scale=gamma_scale, block_size=block_size, u=u.name,
+                 index=index)
+        self.emit("dropblock_mask", **m)
+        return m
+
+    def dropblock_apply(self, x: Tensor, m, relu, name="db") -> Tensor:
+        """out = relu?(x * keep * scale); registers the backward (same kernel, no relu)."""
+        B, H, W, C = x.shape
+        out = self.tensor(name, x.shape, relu=relu)
+        self.emit("dropblock_apply", x=x.name, keep=m["keep"], scale=m["scale"], relu=relu,
+                  out=out.name, B=B, HW=H * W, C=C)
+        return out
+
+    def dropblock_bwd(self, g: str, m, shape) -> str:
+        B, H, W, C = shape
+        dt = self.tensor("d_db", shape)
+        self.emit("dropblock_apply", x=g, keep=m["keep"], scale=m["scale"], relu=False,
+                  out=dt.name, B=B, HW=H * W, C=C)
+        return dt.name
+
+    def cbr_db(self, x: Tensor, filters, k, stride, gamma_scale) -> Tensor:
+        """conv -> BN -> dropblock -> ReLU (nets/resnet_model.py:49-56,65-72)."""
+        co = self.conv(x, filters, k, stride)
+        t = self.bn_act(co, relu=False, name="t")
+        m = self.dropblock_mask(t.shape[1], t.shape[2], t.shape[3], gamma_scale)
+        u = self.dropblock_apply(t, m, relu=True, name="u")
+        self.tape.append(lambda: self.conv_backward(co, self.bn_backward(
+            co, self.dropblock_bwd(self.grad_of(u), m, t.shape))))
+        return u
 
     # -- backward helpers ----------------------------------------------------------------------
     def bn_backward(self, co: ConvOut, g: str, gate=None, addbc=None) -> str:
@@ -454,7 +517,8 @@ class PlanBuilder:
         dyp = self.planes(dy)
         if co.stem is not None:
             self.emit("conv_wgrad", x=co.x.name, xp=self.planes(co.x.name), dy=dy, dyp=dyp, geom=g,
-                      dw_slot=co.stem["dw2"], x_wpad=co.stem["x_wpad"])
+                      dw_slot=co.stem["dw2"], x_wpad=co.stem["x_wpad"],
+                      alg_macs=co.stem["alg_macs"])
             self.emit("s2d_wgrad_unpack", dw2=co.stem["dw2"], w=co.w, cout=g.Cout, k=co.stem["k"],
                       pad=co.stem["pad"], k2=co.stem["k2"], pad2=co.stem["pad2"])
             return
@@ -472,10 +536,12 @@ class PlanBuilder:
                       C=g.Cout)
             g1 = Geom(g.B, g.H, g.W, g.Cin, g.Cout, g.kh, g.kw, 1, g.pad_h_lo,
                       g.kh - 1 - g.pad_h_lo, g.pad_w_lo, g.kw - 1 - g.pad_w_lo)
+            # executed on the zero-inserted dy (4x the MACs of the stride-2 transposed conv)
+            alg = g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
             self.contribute(co.x, lambda out, add, mask: self.emit_dgrad(
-                dyz.name, co.w, out, g1, add, mask))
+                dyz.name, co.w, out, g1, add, mask, alg_macs=alg))
 
-    def emit_dgrad(self, dy, w, out, g, add, mask):
+    def emit_dgrad(self, dy, w, out, g, add, mask, alg_macs=None):
         """dx = conv_transpose(dy) (+ add_src) (* relu mask).  bf16 mode fuses the accumulate / mask
         into the GEMM epilogue; fp32 mode (fp32 output straight from TMEM) runs them as one extra
         elementwise pass."""
@@ -483,11 +549,11 @@ class PlanBuilder:
             shape = self.plan.tensors[out].shape
             tmp = self.tensor("dx_raw", shape)
             self.emit("conv_dgrad", dy=dy, dyp=self.planes(dy), w=w, dx=tmp.name, geom=g,
-                      add_src=None, mask_src=None)
+                      add_src=None, mask_src=None, alg_macs=alg_macs)
             self.emit("grad_combine", a=tmp.name, add_src=add, mask_src=mask, out=out, shape=shape)
         else:
             self.emit("conv_dgrad", dy=dy, dyp=self.planes(dy), w=w, dx=out, geom=g, add_src=add,
-                      mask_src=mask)
+                      mask_src=mask, alg_macs=alg_macs)
 
     # -- composite modules -----------------------------------------------------------------------
     def cbr(self, x: Tensor, filters, k, stride, need_dgrad=True) -> Tensor:
@@ -583,6 +649,36 @@ class PlanBuilder:
             "maxpool_bwd", dout=self.grad_of(out), x=x.name, dx=o, add_src=add, mask_src=mask, **a)))
         return out
 
+    def residual_tail_db(self, co3: ConvOut, *, shortcut, mode, relu, gamma_scale, ms=None) -> Tensor:
+        """Block tail with DropBlock (nets/resnet_model.py:42-47,84-95): out = act(db(bn(y3)) + R),
+        R = db(bn(shortcut conv)) for a projection shortcut, x for an identity shortcut."""
+        B, H, W, C = co3.y.shape
+        t3 = self.bn_act(co3, relu=False, name="t3")
+        m3 = self.dropblock_mask(H, W, C, gamma_scale)
+        t3d = self.dropblock_apply(t3, m3, relu=False, name="t3d")
+        if mode == "bn":
+            # ms: the shortcut's mask, drawn by the caller where the reference draws it (first in
+            # the block, :42-47), so that meta['dropblock_u'] lists the draws in the reference's order
+            ts = self.bn_act(shortcut, relu=False, name="ts")
+            r = self.dropblock_apply(ts, ms, relu=False, name="tsd")
+        else:
+            assert mode == "identity"
+            r = shortcut
+            self.use(shortcut)
+        ident = ConvOut(None, t3d, None, None, self.identity_bn(C))
+        out = self.bn_act(ident, relu=relu, b=r, b_mode=2, name="out")
+
+        def bwd():
+            g = self.grad_of(out)
+            self.conv_backward(co3, self.bn_backward(co3, self.dropblock_bwd(g, m3, co3.y.shape)))
+            if mode == "bn":
+                self.conv_backward(shortcut, self.bn_backward(
+                    shortcut, self.dropblock_bwd(g, ms, co3.y.shape)))
+            else:
+                self.contribute_alias(shortcut, g)
+        self.tape.append(bwd)
+        return out
+
     def residual_tail(self, co3: ConvOut, *, shortcut, mode, relu, se=None) -> Tensor:
         """out = act(bn(y3) [*gate] + R); mode: 'bn' (ConvOut), 'identity' / 'up2' (Tensor)."""
         b_mode = {"bn": 1, "identity": 2, "up2": 3, None: 0}[mode]
@@ -632,9 +728,12 @@ class PlanBuilder:
         self.emit("se_fc", q=q, w1=w1.name, w2=w2.name, h=h, e=e, **dims)
         return dict(q=q, h=h, e=e, w1=w1.name, w2=w2.name, r=r, scratch=scratch)
 
-    def bottleneck(self, x: Tensor, filters, shortcut_kind, strides, last_relu=True) -> Tensor:
-        """nets/resnet_model.py:35-97 (_bottleneck_block_v1, dropblock off)."""
+    def bottleneck(self, x: Tensor, filters, shortcut_kind, strides, last_relu=True, db=None) -> Tensor:
+        """nets/resnet_model.py:35-97 (_bottleneck_block_v1); db = DropBlock gamma_scale of this
+        stage (None: off)."""
         cfg = self.cfg
+        if not self.use_dropblock:
+            db = None
         sconv = "sconv" in cfg.anti_alias_type
         sc = None
         if shortcut_kind is not None:
@@ -657,28 +756,49 @@ class PlanBuilder:
                     xs = self.avgpool(x, 3, strides, 1, (H + 2 - 3) // strides + 1,
                                       (W + 2 - 3) // strides + 1, 1)
             sc = self.conv(xs, filters * 4, 1, k_s)
-        t = self.cbr(x, filters, 1, 1)
+        ms = None
+        if db is not None and sc is not None:
+            ms = self.dropblock_mask(sc.y.shape[1], sc.y.shape[2], sc.y.shape[3], db)
+        t = self.cbr(x, filters, 1, 1) if db is None else self.cbr_db(x, filters, 1, 1, db)
         s3 = 1 if sconv else strides
         if cfg.use_sk_block:
             t = self.sk(t, filters, s3)
+            if db is not None:                                   # :57-63 dropblock on the SK output
+                v = t
+                m = self.dropblock_mask(v.shape[1], v.shape[2], v.shape[3], db)
+                t = self.dropblock_apply(v, m, relu=False, name="vd")
+                self.use(v)
+                self.tape.append(lambda v=v, m=m, t=t: self.contribute(
+                    v, lambda out, add, mask: self._emit_db_contrib(self.grad_of(t), m, v, out, add,
+                                                                     mask)))
         else:
-            t = self.cbr(t, filters, 3, s3)
+            t = self.cbr(t, filters, 3, s3) if db is None else self.cbr_db(t, filters, 3, s3, db)
         if sconv and strides != 1:
             t = self.blurpool(t, cfg.anti_alias_filter_size, strides)
         co3 = self.conv(t, filters * 4, 1, 1, zero_gamma=cfg.zero_gamma)
+        if db is not None:
+            return self.residual_tail_db(co3, shortcut=sc if sc is not None else x,
+                                         mode="bn" if sc is not None else "identity",
+                                         relu=last_relu, gamma_scale=db, ms=ms)
         se = self.se(co3) if cfg.use_se_block else None
         if sc is not None:
             return self.residual_tail(co3, shortcut=sc, mode="bn", relu=last_relu, se=se)
         return self.residual_tail(co3, shortcut=x, mode="identity", relu=last_relu, se=se)
 
+    def _emit_db_contrib(self, g, m, v, out, add, mask):
+        assert add is None and mask is None
+        B, H, W, C = v.shape
+        self.emit("dropblock_apply", x=g, keep=m["keep"], scale=m["scale"], relu=False, out=out,
+                  B=B, HW=H * W, C=C)
+
     def block_layer(self, x, filters, num_blocks, strides, *, use_resnet_d=False, use_bl=False,
-                    last_relu=True):
+                    last_relu=True, db=None):
         """nets/resnet_model.py:99-163: the first block always projects and never sees last_relu."""
         kind = "resnet_d" if use_resnet_d else ("bl" if use_bl else "proj")
-        x = self.bottleneck(x, filters, kind, strides)
+        x = self.bottleneck(x, filters, kind, strides, db=db)
         for i in range(1, num_blocks):
             x = self.bottleneck(x, filters, None, 1,
-                                last_relu=last_relu if i == num_blocks - 1 else True)
+                                last_relu=last_relu if i == num_blocks - 1 else True, db=db)
         return x
 
     # ---------------------------------------------------------------- the network
@@ -748,36 +868,70 @@ class PlanBuilder:
             strides[-1] = 1
         for i, nb in enumerate(sizes):
             f = nf * (2 ** i)
+            # dropblock_for_group3 (gamma_scale 0.25) / group4 (1.0): nets/resnet_model.py:432-453
+            db = {2: 0.25, 3: 1.0}.get(i)
             if cfg.resnet_version == 2 and i < 3:
                 with self.scope("stage%d" % (i + 1)):
                     with self.scope("big%d" % (i + 1)):
-                        big = self.block_layer(x, f, nb - 1, 2, use_bl=True, last_relu=False)
+                        big = self.block_layer(x, f, nb - 1, 2, use_bl=True, last_relu=False, db=db)
                     with self.scope("little%d" % (i + 1)):
                         little = self.block_layer(x, f // cfg.bl_alpha,
-                                                  max(1, nb // cfg.bl_beta - 1), 1, use_bl=True)
+                                                  max(1, nb // cfg.bl_beta - 1), 1, use_bl=True,
+                                                  db=db)
                         le = self.conv(little, f * 4, 1, 1)
                     with self.scope("merge%d" % (i + 1)):
                         x = self.residual_tail(le, shortcut=big, mode="up2", relu=True)
-                        x = self.block_layer(x, f, 1, strides[i], use_bl=True)
+                        x = self.block_layer(x, f, 1, strides[i], use_bl=True, db=db)
             elif cfg.resnet_version == 2:
                 with self.scope("stage%d" % (i + 1)):
-                    x = self.block_layer(x, f, nb, strides[i], use_resnet_d=d, use_bl=True)
+                    x = self.block_layer(x, f, nb, strides[i], use_resnet_d=d, use_bl=True, db=db)
             else:
-                x = self.block_layer(x, f, nb, strides[i], use_resnet_d=d)
+                x = self.block_layer(x, f, nb, strides[i], use_resnet_d=d, db=db)
 
-        # head: GAP -> dense (nets/resnet_model.py:560-599)
+        # head: pool -> [embedding conv + BN] -> dense (nets/resnet_model.py:552-599)
         Bx, Hx, Wx, Cx = x.shape
-        pooled = self.tensor("pooled", (B, Cx))
-        self.emit("gap", x=x.name, out=pooled.name, B=B, HW=Hx * Wx, C=Cx)
-        self.use(x)
         nc, ld = cfg.num_classes, meta["ld_logits"]
-        wk = self._param("resnet_model/dense/kernel", (Cx, nc), "dense_kernel", (ld, 1, 1, Cx),
+        self.use(x)
+        if cfg.pool_type == "gap":
+            pooled = self.tensor("pooled", (B, Cx))
+            self.emit("gap", x=x.name, out=pooled.name, B=B, HW=Hx * Wx, C=Cx)
+        elif cfg.pool_type == "gem":
+            pooled = self.tensor("pooled", (B, Cx))
+            gem_s = self.slot("work", B * Cx)
+            self.emit("gem", x=x.name, out=pooled.name, ssum=gem_s, B=B, HW=Hx * Wx, C=Cx)
+        else:                                            # flatten, NHWC order (:568-571)
+            pooled = self.tensor("pooled", (B, Hx * Wx * Cx))
+            self.emit("grad_combine", a=x.name, add_src=None, mask_src=None, out=pooled.name,
+                      shape=x.shape)
+        Cf = pooled.shape[1]
+        feat, emb_co = pooled, None
+        if cfg.embedding_size > 0:
+            # 1x1 conv 'embedding_dense' (no bias) + BN 'embedding_dense_batch_normalization' on the
+            # [B,1,1,Cf] pooled tensor (:575-584); return_embedding = the BN output; ReLU before dense
+            E = cfg.embedding_size
+            we = self._param("resnet_model/embedding_dense/kernel", (1, 1, Cf, E), "conv_kernel",
+                             (E, 1, 1, Cf), decay=True, need_dgrad=self.training)
+            ge = Geom(B, 1, 1, Cf, E, 1, 1, 1, 0, 0, 0, 0)
+            ye = self.tensor("y", (B, 1, 1, E))
+            bne = self.bn_layer(E, B, layer="embedding_dense_batch_normalization")
+            self.emit("conv", x=pooled.name, xp=self.planes(pooled.name), w=we.name, y=ye.name,
+                      geom=ge, stats=bne.stats if (self.training and not self.fp32) else None,
+                      bias=None, out_f32=False)
+            self.emit_bn_finalize(bne, ye, ge)
+            self.use(pooled)
+            emb_co = ConvOut(pooled, ye, ge, we.name, bne)
+            emb = self.bn_act(emb_co, relu=False, name="embedding")
+            feat = self.bn_act(emb_co, relu=True, name="embedding_relu")
+            meta["embedding"] = emb.name
+            Cf = E
+        wk = self._param("resnet_model/dense/kernel", (Cf, nc), "dense_kernel", (ld, 1, 1, Cf),
                          decay=True, need_dgrad=self.training)
         bk = self._param("resnet_model/dense/bias", (nc,), "dense_bias", (ld,), decay=True)
         logits = self.tensor("logits", (B, ld), "f32")
-        gd = Geom(B, 1, 1, Cx, ld, 1, 1, 1, 0, 0, 0, 0)
-        self.emit("conv", x=pooled.name, xp=self.planes(pooled.name), w=wk.name, y=logits.name,
+        gd = Geom(B, 1, 1, Cf, ld, 1, 1, 1, 0, 0, 0, 0)
+        self.emit("conv", x=feat.name, xp=self.planes(feat.name), w=wk.name, y=logits.name,
                   geom=gd, stats=None, bias=bk.name, out_f32=True)
+        self.use(feat)
         meta.update(logits=logits.name, pooled=pooled.name, feature_shape=x.shape)
         if not self.with_loss:
             return
@@ -786,28 +940,49 @@ class PlanBuilder:
         lam_names = dict(lam1=lam1 and lam1.name, lam2=lam2 and lam2.name)
         self.emit("mix_labels", labels=labels.name, mode=self.mixup_type, y=ysoft.name, Bin=Bin,
                   NC=nc, **lam_names)
-        loss = self.slot("zero", 2)          # [cross_entropy, l2_loss]
+        yt = None
+        if self.kd_temp > 0:
+            # knowledge distillation (nets/run_loop_classification.py:86-96): the labels carry the
+            # teacher's logits; teacher labels = softmax(. / T), mixed like the supervised labels
+            tlog = self.tensor("teacher_logits", (Bin, nc), "f32")
+            yt = self.tensor("yteacher", (B, nc), "f32")
+            meta["teacher_logits"] = tlog.name
+            self.emit("kd_teacher", teacher_logits=tlog.name, labels=labels.name,
+                      mode=self.mixup_type, kd_temp=self.kd_temp, yt=yt.name, Bin=Bin, NC=nc,
+                      **lam_names)
+        loss = self.slot("zero", 4)          # [cross_entropy, l2_loss, kd_loss, -]
         dlogits = self.tensor("dlogits", (B, ld))
         meta.update(labels=labels.name, ysoft=ysoft.name, loss=loss)
-        self.emit("softmax_ce", logits=logits.name, y=ysoft.name, B=B, NC=nc, ld=ld,
+        self.emit("softmax_ce", logits=logits.name, y=ysoft.name, yt=yt and yt.name,
+                  kd_temp=self.kd_temp, B=B, NC=nc, ld=ld,
                   label_smoothing=meta["label_smoothing"], loss=loss, dlogits=dlogits.name,
                   dbias=bk.name if self.training else None,
-                  work=self.slot("work", _round_up(B, 32) + B * ld))
+                  work=self.slot("work", 2 * _round_up(B, 32) + B * ld))
         if not self.training:
             return
 
         # ---------------- backward ----------------
         self.ops = p.backward
-        self.emit("conv_wgrad", x=pooled.name, xp=self.planes(pooled.name), dy=dlogits.name,
+        self.emit("conv_wgrad", x=feat.name, xp=self.planes(feat.name), dy=dlogits.name,
                   dyp=self.planes(dlogits.name), geom=gd, w=wk.name)
-        dpooled = self.tensor("dpooled", (B, Cx))
-        self.emit("conv_dgrad", dy=dlogits.name, dyp=self.planes(dlogits.name), w=wk.name,
-                  dx=dpooled.name, geom=gd, add_src=None, mask_src=None)
+        self.contribute(feat, lambda out, add, mask: self.emit_dgrad(
+            dlogits.name, wk.name, out, gd, add, mask))
+        if emb_co is not None:
+            self.conv_backward(emb_co, self.bn_backward(emb_co, self.grad_of(feat)))
+        dpooled = self.grad_of(pooled)
 
-        def gap_bwd(out, add, mask):
+        def pool_bwd(out, add, mask):
             assert add is None
-            self.emit("gap_bwd", dpooled=dpooled.name, mask_src=mask, dx=out, B=B, HW=Hx * Wx, C=Cx)
-        self.contribute(x, gap_bwd)
+            if cfg.pool_type == "gap":
+                self.emit("gap_bwd", dpooled=dpooled, mask_src=mask, dx=out, B=B, HW=Hx * Wx, C=Cx)
+            elif cfg.pool_type == "gem":
+                # x <= 0 is outside GeM's clip range: the ReLU mask is implied
+                self.emit("gem_bwd", dpooled=dpooled, ssum=gem_s, x=x.name, dx=out, B=B,
+                          HW=Hx * Wx, C=Cx)
+            else:
+                self.emit("grad_combine", a=dpooled, add_src=None, mask_src=mask, out=out,
+                          shape=x.shape)
+        self.contribute(x, pool_bwd)
         for fn in reversed(self.tape):
             fn()
         # ---------------- update ----------------

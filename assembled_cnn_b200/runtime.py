@@ -60,12 +60,18 @@ class Runtime:
                                        device=self.dev)
         else:
             self.grads = self.momentum = self.w_dgrad = None
-        self.hp = torch.tensor([0.1, 0.9, 0.0, 1.0], **f32)     # lr, momentum, wd, grad_scale
+        # device hyper-parameters: lr, momentum, wd, grad_scale, dropblock keep_prob, global step
+        # (uint32 bits, the Philox counter of the DropBlock masks), 2 spare
+        self.hp = torch.tensor([0.1, 0.9, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0], **f32)
         self.loss_scale = 1.0
+        self.dropblock_seed = 0x5EED5EED
+        self.dropblock_feed = False     # True: masks from the uniforms in plan.meta['dropblock_u']
         if share is None:
             for p in plan.state.values():
                 if p.kind == "moving_variance":
                     self.state[p.offset:p.offset + p.size] = 1.0
+        for off, C_ in plan.meta.get("ones", []):        # identity-BN scale vectors (DropBlock tails)
+            self.work[off:off + C_] = 1.0
         # activation / gradient buffers (statically shaped, allocated once)
         self.t = {}
         for name, t in plan.tensors.items():
@@ -164,6 +170,22 @@ class Runtime:
             else:
                 dst.copy_(v)
 
+    def set_tf(self, name, value, buf=None):
+        """Inverse of get_tf for one variable (or its momentum slot with buf=self.momentum)."""
+        p = self.plan.params.get(name) or self.plan.state[name]
+        v = torch.as_tensor(value).to(torch.float32)
+        dst = self.pview(name, buf)
+        if p.kind == "conv_kernel":
+            dst.copy_(v.permute(3, 0, 1, 2))
+        elif p.kind == "dense_kernel":
+            dst.zero_()
+            dst[:v.shape[1], 0, 0, :] = v.t()
+        elif p.kind == "dense_bias":
+            dst.zero_()
+            dst[:v.shape[0]] = v
+        else:
+            dst.copy_(v)
+
     def get_tf(self, name, buf=None):
         p = self.plan.params.get(name) or self.plan.state[name]
         v = self.pview(name, buf)
@@ -175,12 +197,15 @@ class Runtime:
             return v[:p.tf_shape[0]]
         return v
 
-    def set_hparams(self, lr=None, momentum=None, weight_decay=None, grad_scale=None):
-        cur = self.hp.tolist()
-        for i, v in enumerate((lr, momentum, weight_decay, grad_scale)):
+    def set_hparams(self, lr=None, momentum=None, weight_decay=None, grad_scale=None,
+                    keep_prob=None, step=None):
+        cur = self.hp.cpu()
+        for i, v in enumerate((lr, momentum, weight_decay, grad_scale, keep_prob)):
             if v is not None:
                 cur[i] = float(v)
-        self.hp.copy_(torch.tensor(cur, dtype=torch.float32), non_blocking=True)
+        if step is not None:
+            cur.view(torch.int32)[5] = int(step) & 0x7fffffff
+        self.hp.copy_(cur, non_blocking=True)
 
     # ---------------------------------------------------------------- execution
     def _chk(self, rc, op):
@@ -369,13 +394,43 @@ class Runtime:
                                             op.k, op.stride, op.pad_lo, op.Ho, op.Wo, self.adt,
                                             self.stream), op)
 
+    def op_gem(self, op):
+        self._chk(self.lib.acnn_gem_fwd(self.T(op.x), self.T(op.out), self.S(op.ssum), op.B, op.HW,
+                                        op.C, self.adt, self.stream), op)
+
+    def op_gem_bwd(self, op):
+        self._chk(self.lib.acnn_gem_bwd(self.T(op.dpooled), self.S(op.ssum), self.T(op.x),
+                                        self.T(op.dx), op.B, op.HW, op.C, self.adt, self.stream), op)
+
+    def op_dropblock_mask(self, op):
+        need = self.lib.acnn_dropblock_scratch_floats(op.H, op.W, op.C, op.block_size)
+        assert 0 < need <= op.scratch.size, (need, op.scratch.size)
+        u = self.T(op.u) if self.dropblock_feed else None
+        # one Philox key per call site: the masks of different layers are independent
+        seed = (self.dropblock_seed + 0x9E3779B97F4A7C15 * (op.index + 1)) & 0xFFFFFFFFFFFFFFFF
+        self._chk(self.lib.acnn_dropblock_mask(
+            u, self.hp.data_ptr() + 16, self.hp.data_ptr() + 20, seed, op.gamma_scale,
+            op.block_size, self.S(op.keep), self.S(op.scale), self.S(op.scratch), op.H, op.W, op.C,
+            self.stream), op)
+
+    def op_dropblock_apply(self, op):
+        self._chk(self.lib.acnn_dropblock_apply(self.T(op.x), self.S(op.keep), self.S(op.scale),
+                                                1 if op.relu else 0, self.T(op.out), op.B, op.HW,
+                                                op.C, self.adt, self.stream), op)
+
+    def op_kd_teacher(self, op):
+        self._chk(self.lib.acnn_kd_teacher_labels(
+            self.T(op.teacher_logits), self.T(op.labels), self.T(op.lam1), self.T(op.lam2), op.mode,
+            op.kd_temp, self.T(op.yt), op.Bin, op.NC, self.stream), op)
+
     def op_gap(self, op):
         self._chk(self.lib.acnn_gap_fwd(self.T(op.x), self.T(op.out), op.B, op.HW, op.C,
                                         self.adt, self.stream), op)
 
     def op_softmax_ce(self, op):
         self._chk(self.lib.acnn_softmax_ce(
-            self.T(op.logits), self.T(op.y), op.B, op.NC, op.ld, op.label_smoothing,
+            self.T(op.logits), self.T(op.y), self.T(op.a.get("yt")), float(op.a.get("kd_temp", 0.0)),
+            op.B, op.NC, op.ld, op.label_smoothing,
             self.loss_scale, self.S(op.loss), self.T(op.dlogits),
             self.G(op.dbias) if (op.dbias and self.grads is not None) else None, self.S(op.work),
             self.adt, self.stream), op)

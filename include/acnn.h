@@ -266,10 +266,44 @@ int acnn_mix_labels(const int32_t* labels, const float* lam1, const float* lam2,
  * dlogits (`dtype` [B,ld], columns >= NC zeroed) = (softmax - y')/B * grad_scale;
  * dbias[NC] (fp32) += column sums of the fp32 dlogits.  logits fp32 [B,ld].  Two launches: per-row
  * losses / gradients, then a fixed-order sum (no atomics: bit-reproducible).
- * work: >= roundup(B, 32) + B*ld floats of scratch. */
-int acnn_softmax_ce(const float* logits, const float* y, int B, int NC, int ld,
-                    float label_smoothing, float grad_scale, float* loss_acc, void* dlogits,
-                    float* dbias, float* work, int dtype, void* stream);
+ * teacher != NULL adds the knowledge-distillation term (nets/run_loop_classification.py:156-162):
+ * loss_acc[2] += kd_temp^2 * mean_b CE(logits / kd_temp, teacher[b]) and its gradient to dlogits /
+ * dbias; teacher [B,NC] = (mixed) softmax(teacher_logits / kd_temp) from acnn_kd_teacher_labels.
+ * work: >= 2*roundup(B, 32) + B*ld floats of scratch. */
+int acnn_softmax_ce(const float* logits, const float* y, const float* teacher, float kd_temp, int B,
+                    int NC, int ld, float label_smoothing, float grad_scale, float* loss_acc,
+                    void* dlogits, float* dbias, float* work, int dtype, void* stream);
+/* Teacher labels of knowledge distillation: softmax(teacher_logits[Bin,NC] / kd_temp) mixed with the
+ * images' mixup pairing (utils/data_util.py:128-156, modes as acnn_pack_input; the second half of a
+ * type-2 batch mixes the supervised one-hot of `labels`, as the reference does at :154). */
+int acnn_kd_teacher_labels(const float* teacher_logits, const int32_t* labels, const float* lam1,
+                           const float* lam2, int mode, float kd_temp, float* yt, int Bin, int NC,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DropBlock (nets/blocks.py:187-251; call sites nets/resnet_model.py:35-97,432-453) and GeM pooling
+ * (nets/blocks.py:22-42)
+ * ------------------------------------------------------------------------------------------- */
+/* keep[H,W,C] (fp32, ONE mask for the whole batch, as the reference samples it) = 1 - dilation by a
+ * block_size window of bernoulli(gamma) drawn on the [H-bs+1, W-bs+1, C] interior and zero-padded;
+ * gamma = gamma_scale * (1 - keep_prob) * H*W / bs^2 / ((H-bs+1)(W-bs+1)); *scale = H*W*C /
+ * (sum(keep) + 1e-8).  keep_prob is read from DEVICE memory (it follows a schedule,
+ * functions/model_fns.py:26-33,221-228).  u != NULL supplies the uniform draws [hs,ws,C] (parity
+ * tests); otherwise Philox4x32-10 keyed by `seed` with counter (element, *step).
+ * scratch: acnn_dropblock_scratch_floats(H, W, C, block_size) floats. */
+int acnn_dropblock_mask(const float* u, const float* keep_prob, const uint32_t* step, uint64_t seed,
+                        float gamma_scale, int block_size, float* keep, float* scale,
+                        float* scratch, int H, int W, int C, void* stream);
+int acnn_dropblock_scratch_floats(int H, int W, int C, int block_size);
+/* out[B,HW,C] = relu?(x * keep[HW,C] * *scale); with relu = 0 also the backward on gradients. */
+int acnn_dropblock_apply(const void* x, const float* keep, const float* scale, int relu, void* out,
+                         int B, int HW, int C, int dtype, void* stream);
+/* pooled[B,C] = HW^(-1/3) * cbrt(max(S, 1e-6)), S[B,C] (fp32, kept for the backward) =
+ * sum_hw clip(x, 1e-6, 1e12)^3;  dx = dpooled * HW^(-1/3) * S^(-2/3) * x^2 inside the clip range. */
+int acnn_gem_fwd(const void* x, void* pooled, float* ssum, int B, int HW, int C, int dtype,
+                 void* stream);
+int acnn_gem_bwd(const void* dpooled, const float* ssum, const void* x, void* dx, int B, int HW,
+                 int C, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Parameters and optimizer (nets/optimizer_setting.py:23-38, run_loop_classification.py:166-179)

@@ -176,28 +176,50 @@ class OracleModel:
             _, w2 = vs.conv_kernel("seblock_dense_2", 1, c // 16, c)
         return T.se_block(x, w1[0, 0], w2[0, 0])
 
-    def _bottleneck(self, vs, x, filters, training, shortcut_fn, strides, last_relu=True):
-        """nets/resnet_model.py:35-97 _bottleneck_block_v1 (dropblock off)."""
+    def _dropblock(self, x, training, gamma_scale):
+        """blocks.dropblock(block_size=7) with the uniform draws taken from self.dropblock_u (a
+        callable shape -> tensor, or a list consumed in call order): nets/resnet_model.py:432-438."""
+        if gamma_scale is None or not training:
+            return x
+        kp = self.keep_prob
+        if isinstance(kp, float) and kp == 1:
+            return x
+        _, h, w, c = x.shape
+        shape = (1, h - 7 + 1, w - 7 + 1, c)
+        if shape[1] < 1 or shape[2] < 1:
+            raise ValueError("dropblock: feature map %dx%d smaller than block_size 7" % (h, w))
+        u = self.dropblock_u(shape) if callable(self.dropblock_u) else self.dropblock_u.pop(0)
+        assert tuple(u.shape) == shape, (u.shape, shape)
+        self.dropblock_shapes.append(shape)
+        return T.dropblock(x, kp, 7, gamma_scale, u)
+
+    def _bottleneck(self, vs, x, filters, training, shortcut_fn, strides, last_relu=True, db=None):
+        """nets/resnet_model.py:35-97 _bottleneck_block_v1; db = dropblock gamma_scale or None."""
         shortcut = x
         if shortcut_fn is not None:
             shortcut = self._bn(vs, shortcut_fn(x), training)
+            shortcut = self._dropblock(shortcut, training, db)
         sconv = "sconv" in self.aa_type
-        y = torch.relu(self._bn(vs, self._conv(vs, x, filters, 1, 1), training))
+        y = self._dropblock(self._bn(vs, self._conv(vs, x, filters, 1, 1), training), training, db)
+        y = torch.relu(y)
         s3 = 1 if sconv else strides
         if self.use_sk:
-            y = self._sk(vs, y, filters, s3, training)
+            y = self._dropblock(self._sk(vs, y, filters, s3, training), training, db)
         else:
-            y = torch.relu(self._bn(vs, self._conv(vs, y, filters, 3, s3), training))
+            y = self._dropblock(self._bn(vs, self._conv(vs, y, filters, 3, s3), training), training,
+                                db)
+            y = torch.relu(y)
         if sconv and strides != 1:
             y = T.anti_aliased_downsample(y, self.aa_size, strides)
         y = self._bn(vs, self._conv(vs, y, 4 * filters, 1, 1), training, self.zero_gamma)
+        y = self._dropblock(y, training, db)
         if self.use_se:
             y = self._se(vs, y)
         y = y + shortcut
         return torch.relu(y) if last_relu else y
 
     def _block_layer(self, vs, x, filters, num_blocks, strides, training, use_resnet_d=False,
-                     use_bl=False, last_relu=True):
+                     use_bl=False, last_relu=True, db=None):
         """nets/resnet_model.py:99-163."""
         filters_out = filters * 4
 
@@ -215,16 +237,21 @@ class OracleModel:
 
         fn = resnet_d_shortcut if use_resnet_d else (bl_shortcut if use_bl else projection_shortcut)
         # NB: the first block never receives last_relu (reference :151-155)
-        x = self._bottleneck(vs, x, filters, training, fn, strides)
+        x = self._bottleneck(vs, x, filters, training, fn, strides, db=db)
         for i in range(1, num_blocks):
             x = self._bottleneck(vs, x, filters, training, None, 1,
-                                 last_relu=last_relu if i == num_blocks - 1 else True)
+                                 last_relu=last_relu if i == num_blocks - 1 else True, db=db)
         return x
 
     # -- the network ---------------------------------------------------------------------------
-    def forward(self, vs, x, training, use_resnet_d=False, return_embedding=False):
-        """nets/resnet_model.py:305-599.  x: [B,H,W,3] NHWC.  Returns logits [B,num_classes]."""
+    def forward(self, vs, x, training, use_resnet_d=False, return_embedding=False, keep_prob=1.0,
+                dropblock_u=None):
+        """nets/resnet_model.py:305-599.  x: [B,H,W,3] NHWC.  Returns logits [B,num_classes].
+        keep_prob / dropblock_u: DropBlock keep probability and the source of its uniform draws."""
         self.bn_updates = OrderedDict()
+        self.keep_prob = keep_prob
+        self.dropblock_u = dropblock_u
+        self.dropblock_shapes = []
         nf = self.num_filters
         if use_resnet_d and self.rv == 1:
             x = torch.relu(self._bn(vs, self._conv(vs, x, nf // 2, 3, 2), training))
@@ -257,35 +284,48 @@ class OracleModel:
 
         for i, nb in enumerate(self.block_sizes):
             f = nf * (2 ** i)
+            # dropblock_for_group3 (gamma_scale 0.25) / group4 (1.0): nets/resnet_model.py:432-453
+            db = {2: 0.25, 3: 1.0}.get(i)
             if self.rv == 2 and i < 3:
                 with vs.scope("stage%d" % (i + 1)):
                     with vs.scope("big%d" % (i + 1)):
                         big = self._block_layer(vs, x, f, nb - 1, 2, training, use_bl=True,
-                                                last_relu=False)
+                                                last_relu=False, db=db)
                     with vs.scope("little%d" % (i + 1)):
                         little = self._block_layer(vs, x, f // self.alpha,
                                                    max(1, nb // self.beta - 1), 1, training,
-                                                   use_bl=True)
+                                                   use_bl=True, db=db)
                         little_e = self._bn(vs, self._conv(vs, little, f * 4, 1, 1), training)
                     with vs.scope("merge%d" % (i + 1)):
                         x = torch.relu(little_e + T.upsample2x(big))
                         x = self._block_layer(vs, x, f, 1, self.block_strides[i], training,
-                                              use_bl=True)
+                                              use_bl=True, db=db)
             elif self.rv == 2:
                 with vs.scope("stage%d" % (i + 1)):
                     x = self._block_layer(vs, x, f, nb, self.block_strides[i], training,
-                                          use_resnet_d=use_resnet_d, use_bl=True)
+                                          use_resnet_d=use_resnet_d, use_bl=True, db=db)
             else:
                 x = self._block_layer(vs, x, f, nb, self.block_strides[i], training,
-                                      use_resnet_d=use_resnet_d)
+                                      use_resnet_d=use_resnet_d, db=db)
 
-        if self.pool_type != "gap":
-            raise NotImplementedError("pool_type %s (SURVEY 8f: GeM/flatten are 'next')" % self.pool_type)
-        pooled = T.global_avg_pool(x)                          # [B, C]
+        # head: nets/resnet_model.py:552-599
+        if self.pool_type == "gap":
+            pooled = T.global_avg_pool(x)                      # [B, C]
+        elif self.pool_type == "gem":
+            pooled = T.generalized_mean_pooling(x)
+        elif self.pool_type == "flatten":
+            pooled = x.reshape(x.shape[0], -1)                 # NHWC flatten order
+        else:
+            raise NotImplementedError
         if self.embedding_size > 0:
-            raise NotImplementedError("embedding head (SURVEY 8f 'next')")
+            _, w = vs.conv_kernel("embedding_dense", 1, pooled.shape[-1], self.embedding_size)
+            emb = pooled[:, None, None, :] @ w[0, 0]
+            emb = self._bn(vs, emb, training, layer="embedding_dense_batch_normalization")
+            pooled = emb[:, 0, 0, :]
         if return_embedding:
             return pooled
+        if self.embedding_size > 0:
+            pooled = torch.relu(pooled)
         (kn, k), (bn_, b) = vs.dense("dense", pooled.shape[-1], self.num_classes)
         return pooled @ k + b
 
@@ -301,9 +341,9 @@ def build(seed=42, dtype=torch.float32, input_hw=64, use_resnet_d=False, **model
     return model, vs
 
 
-def forward(model, vs, x, training, use_resnet_d=False):
+def forward(model, vs, x, training, use_resnet_d=False, **kw):
     vs.reset_walk()
-    return model.forward(vs, x, training, use_resnet_d=use_resnet_d)
+    return model.forward(vs, x, training, use_resnet_d=use_resnet_d, **kw)
 
 
 def decayed(name):
@@ -312,18 +352,23 @@ def decayed(name):
 
 
 def loss_fn(model, vs, images, onehot, *, training=True, use_resnet_d=False, label_smoothing=0.0,
-            weight_decay=0.0):
-    """resnet_model_fn (run_loop_classification.py:121-179) without KD: returns
-    (loss, cross_entropy, l2_loss, logits)."""
-    logits = forward(model, vs, images, training, use_resnet_d).float()
+            weight_decay=0.0, teacher_labels=None, kd_temp=0.0, keep_prob=1.0, dropblock_u=None):
+    """resnet_model_fn (run_loop_classification.py:121-179): returns (loss, cross_entropy, l2_loss,
+    logits); with kd_temp > 0 the knowledge-distillation term T^2 * CE(logits / T, teacher_labels)
+    (:156-162) is added to the loss and left in `loss_fn.last_kd`."""
+    logits = forward(model, vs, images, training, use_resnet_d, keep_prob=keep_prob,
+                     dropblock_u=dropblock_u).float()
     ce = T.softmax_cross_entropy(logits, onehot, label_smoothing)
     l2 = weight_decay * sum(T.l2_loss(v) for n, v in vs.vars.items()
                             if vs.trainable[n] and decayed(n))
-    return ce + l2, ce, l2, logits
+    kd = T.kd_loss(logits, teacher_labels.float(), kd_temp) if kd_temp > 0 else 0.0
+    loss_fn.last_kd = kd
+    return ce + l2 + kd, ce, l2, logits
 
 
 def train_step(model, vs, momentum_buf, images, onehot, *, lr, momentum=0.9, use_resnet_d=False,
-               label_smoothing=0.0, weight_decay=0.0, n_replicas=1):
+               label_smoothing=0.0, weight_decay=0.0, n_replicas=1, teacher_labels=None,
+               kd_temp=0.0, keep_prob=1.0, dropblock_u=None):
     """One full training step on one replica (or the average over `n_replicas` shards of the batch,
     each with its own BN statistics: MirroredStrategy semantics).  Updates vs.vars and
     momentum_buf in place; returns dict(loss, cross_entropy, l2_loss, logits, grads)."""
@@ -338,7 +383,11 @@ def train_step(model, vs, momentum_buf, images, onehot, *, lr, momentum=0.9, use
         sl = slice(r * shards, (r + 1) * shards)
         loss, ce, l2, logits = loss_fn(model, vs, images[sl], onehot[sl], training=True,
                                        use_resnet_d=use_resnet_d, label_smoothing=label_smoothing,
-                                       weight_decay=weight_decay)
+                                       weight_decay=weight_decay,
+                                       teacher_labels=None if teacher_labels is None
+                                       else teacher_labels[sl], kd_temp=kd_temp,
+                                       keep_prob=keep_prob, dropblock_u=dropblock_u)
+        kd_val = loss_fn.last_kd
         g = torch.autograd.grad(loss, [vs.vars[n] for n in names])
         grads = [gi / n_replicas for gi in g] if grads is None else \
             [a + gi / n_replicas for a, gi in zip(grads, g)]
@@ -357,6 +406,7 @@ def train_step(model, vs, momentum_buf, images, onehot, *, lr, momentum=0.9, use
         "loss": sum(o[0] for o in outs) / n_replicas,
         "cross_entropy": sum(o[1] for o in outs) / n_replicas,
         "l2_loss": outs[0][2],
+        "kd_loss": kd_val.detach() if torch.is_tensor(kd_val) else kd_val,
         "logits": torch.cat([o[3] for o in outs], 0),
         "grads": OrderedDict(zip(names, grads)),
     }

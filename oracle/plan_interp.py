@@ -40,10 +40,12 @@ class PlanInterpreter:
         self.state = torch.zeros(plan.state_elems, dtype=dtype)
         self.zero = torch.zeros(max(plan.zero_elems, 1), dtype=dtype)
         self.work = torch.zeros(max(plan.work_elems, 1), dtype=dtype)
-        self.hp = dict(lr=0.1, momentum=0.9, weight_decay=0.0, grad_scale=1.0)
+        self.hp = dict(lr=0.1, momentum=0.9, weight_decay=0.0, grad_scale=1.0, keep_prob=1.0)
         for p in plan.state.values():
             if p.kind == "moving_variance":
                 self.state[p.offset:p.offset + p.size] = 1.0
+        for off, C in plan.meta.get("ones", []):          # identity-BN scale vectors
+            self.work[off:off + C] = 1.0
 
     # ---------------------------------------------------------------- parameter access
     def pview(self, name, buf=None):
@@ -356,6 +358,45 @@ class PlanInterpreter:
     def op_gap(self, op):
         self.store(op.out, self.t[op.x].mean(dim=(1, 2)))
 
+    def op_gem(self, op):
+        """nets/blocks.py:22-42, p = 3; the clipped cube sum is kept for the backward."""
+        x = self.t[op.x]
+        s = (x.clamp(1e-6, 1e12) ** 3).sum(dim=(1, 2))
+        self.slot(op.ssum).copy_(s.reshape(-1))
+        self.store(op.out, float(op.HW) ** (-1.0 / 3) * s.clamp_min(1e-6) ** (1.0 / 3))
+
+    def op_gem_bwd(self, op):
+        x = self.t[op.x].clone().requires_grad_(True)
+        y = T.generalized_mean_pooling(x)
+        (dx,) = torch.autograd.grad(y, x, self.t[op.dpooled].reshape(y.shape))
+        self.store(op.dx, dx)
+
+    def op_dropblock_mask(self, op):
+        """nets/blocks.py:209-246 with the uniform draws fed through plan.meta['dropblock_u']."""
+        u = self.t[op.u].to(self.dtype)[None]
+        keep, factor = T.dropblock_keep_mask(u, self.hp["keep_prob"], op.block_size, op.gamma_scale,
+                                             op.H, op.W)
+        self.slot(op.keep).copy_(keep.reshape(-1))
+        self.slot(op.scale)[0] = factor
+
+    def op_dropblock_apply(self, op):
+        x = self.t[op.x]
+        keep = self.slot(op.keep).view(1, *x.shape[1:])
+        v = x * keep * self.slot(op.scale)[0]
+        self.store(op.out, torch.relu(v) if op.relu else v)
+
+    def op_kd_teacher(self, op):
+        """softmax(teacher_logits / T), mixed with the batch's mixup pairing (data_util.py:128-156)."""
+        p = torch.softmax(self.t[op.teacher_logits].to(self.dtype) / op.kd_temp, dim=1)
+        if op.mode:
+            lab = self.t[op.labels].long()
+            y = F.one_hot(lab, op.NC).to(self.dtype)
+            lam1 = self.t[op.lam1]
+            lam2 = self.t[op.lam2] if op.lam2 else None
+            _, _, p = T.mixup(torch.zeros(p.shape[0], 1, 1, 1, dtype=self.dtype), y, lam1, lam2,
+                              keep_batch_size=(op.mode == 2), y_t=p)
+        self.store(op.yt, p)
+
     def op_softmax_ce(self, op):
         logits = self.t[op.logits][:, :op.NC]
         y = self.t[op.y]
@@ -365,6 +406,10 @@ class PlanInterpreter:
         self.slot(op.loss)[0] += -(yp * lsm).sum(1).mean()
         gs = self.hp["grad_scale"]
         d = (torch.softmax(logits, 1) * yp.sum(1, keepdim=True) - yp) / op.B * gs
+        if op.a.get("yt"):
+            tt, Tk = self.t[op.yt], op.kd_temp
+            self.slot(op.loss)[2] += Tk * Tk * -(tt * F.log_softmax(logits / Tk, dim=1)).sum(1).mean()
+            d = d + Tk * (torch.softmax(logits / Tk, 1) * tt.sum(1, keepdim=True) - tt) / op.B * gs
         if op.dbias:
             self.pview(op.dbias, self.grads)[:op.NC] += d.sum(0)
         self.store(op.dlogits, F.pad(d, (0, op.ld - op.NC)))
@@ -379,7 +424,9 @@ class PlanInterpreter:
         g = op.geom
         x, dy = self.t[op.x], self.t[op.dy]
         if x.dim() == 2:
-            x, dy = x[:, None, None, :], dy[:, None, None, :]
+            x = x[:, None, None, :]
+        if dy.dim() == 2:
+            dy = dy[:, None, None, :]
         if op.a.get("x_wpad"):
             lo, hi = op.x_wpad
             x = x[:, :, lo:x.shape[2] - hi, :]
@@ -398,8 +445,7 @@ class PlanInterpreter:
             dy = dy[:, None, None, :]
         w = self.wq(self.pview(op.w))
         dx = self._adjoint(lambda x: self._conv(x, w, g), (g.B, g.H, g.W, g.Cin), dy)
-        if two_d:
-            dx = dx[:, 0, 0, :]
+        dx = dx.reshape(self.plan.tensors[op.dx].shape)
         self.store(op.dx, self.grad_epilogue(dx, op.add_src, op.mask_src))
 
     def op_zero_insert(self, op):
@@ -557,7 +603,8 @@ class PlanInterpreter:
         self.store(op.dx, self.grad_epilogue(dx.reshape(shape), None, op.mask_src))
 
     def op_grad_combine(self, op):
-        self.store(op.out, self.grad_epilogue(self.t[op.a["a"]], op.add_src, op.mask_src))
+        a = self.t[op.a["a"]].reshape(self.plan.tensors[op.out].shape)   # flatten head: a view
+        self.store(op.out, self.grad_epilogue(a, op.add_src, op.mask_src))
 
     def op_sgd(self, op):
         hp = self.hp

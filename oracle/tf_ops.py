@@ -203,10 +203,13 @@ def softmax_cross_entropy(logits, onehot, label_smoothing=0.0):
     return -(onehot * F.log_softmax(logits.float(), dim=1)).sum(dim=1).mean()
 
 
-def mixup(x, y, lam1, lam2=None, keep_batch_size=True):
+def mixup(x, y, lam1, lam2=None, keep_batch_size=True, y_t=None):
     """utils/data_util.py:97-158 with the Beta(0.2,0.2) draws passed in (TF's RNG is not
     reproducible).  x [2B',H,W,C], y [2B',classes]; lam1/lam2 [B'].
-    keep_batch_size=False (mixup_type 1): returns B' mixed examples; True (type 2): 2B'."""
+    keep_batch_size=False (mixup_type 1): returns B' mixed examples; True (type 2): 2B'.
+    With y_t (knowledge-distillation teacher labels) a third value, the mixed teacher labels, is
+    returned -- including the reference's own quirk at utils/data_util.py:154, where the second half
+    of a type-2 batch mixes y1 (the SUPERVISED labels) instead of y1_t with the reversed y2_t."""
     b = x.shape[0] // 2
     x1, x2 = x[:b], x[b:]
     y1, y2 = y[:b], y[b:]
@@ -214,6 +217,10 @@ def mixup(x, y, lam1, lam2=None, keep_batch_size=True):
     l1y = lam1.view(b, 1)
     mx = l1x * x1 + (1.0 - l1x) * x2
     my = l1y * y1 + (1.0 - l1y) * y2
+    myt = None
+    if y_t is not None:
+        y1_t, y2_t = y_t[:b], y_t[b:]
+        myt = l1y * y1_t + (1.0 - l1y) * y2_t
     if keep_batch_size:
         l2x = lam2.view(b, 1, 1, 1)
         l2y = lam2.view(b, 1)
@@ -221,7 +228,69 @@ def mixup(x, y, lam1, lam2=None, keep_batch_size=True):
         y3 = torch.flip(y2, [0])
         mx = torch.cat([mx, l2x * x1 + (1.0 - l2x) * x3], 0)
         my = torch.cat([my, l2y * y1 + (1.0 - l2y) * y3], 0)
+        if y_t is not None:
+            y3_t = torch.flip(y2_t, [0])
+            myt = torch.cat([myt, l2y * y1 + (1.0 - l2y) * y3_t], 0)     # sic: y1, not y1_t
+    if y_t is not None:
+        return mx.detach(), my.detach(), myt.detach()
     return mx.detach(), my.detach()
+
+
+def kd_loss(logits, teacher_labels, kd_temp):
+    """nets/run_loop_classification.py:156-162: T^2 * softmax_cross_entropy(logits / T, teacher)
+    with teacher = softmax(teacher_logits / T) (:90-93), no label smoothing, mean over the batch."""
+    return kd_temp * kd_temp * softmax_cross_entropy(logits / kd_temp, teacher_labels, 0.0)
+
+
+def generalized_mean_pooling(x, p=3):
+    """nets/blocks.py:22-42 (NHWC): N^(-1/p) * (max(sum_hw clip(x, 1e-6, 1e12)^p, 1e-6))^(1/p)."""
+    n = x.shape[1] * x.shape[2]
+    eps = 1e-6
+    xp = x.clamp(eps, 1e12) ** p
+    s = xp.sum(dim=(1, 2)).clamp_min(eps)
+    return (float(n) ** (-1.0 / p)) * s ** (1.0 / p)
+
+
+def dropblock_keep_mask(u, keep_prob, block_size, gamma_scale, h, w):
+    """nets/blocks.py:191-251, the random part: u = the uniform draws of _bernoulli, shape
+    [1, h-bs+1, w-bs+1, c] (ONE mask for the whole batch).  Returns the keep mask [1,h,w,c] (1 = kept)
+    and the renormalisation factor size / (sum + 1e-8)."""
+    bs = block_size
+    br = (bs - 1) // 2
+    tl = (bs - 1) - br
+    gamma = (1.0 - keep_prob) * (w * h) / (bs ** 2) / ((w - bs + 1) * (h - bs + 1)) * gamma_scale
+    m = torch.relu(torch.sign(gamma - u))                       # 1 with probability gamma
+    m = F.pad(m, (0, 0, tl, br, tl, br))                        # [1,h,w,c]
+    m = F.max_pool2d(m.permute(0, 3, 1, 2), bs, 1, bs // 2).permute(0, 2, 3, 1)   # SAME, odd bs
+    keep = 1.0 - m
+    factor = keep.numel() / (keep.float().sum() + 1e-8)
+    return keep, factor
+
+
+def dropblock(x, keep_prob, block_size, gamma_scale, u):
+    """x * keep_mask * size/sum(keep_mask); identity when keep_prob == 1 or gamma_scale == 0."""
+    if (isinstance(keep_prob, float) and keep_prob == 1) or gamma_scale == 0 or u is None:
+        return x
+    keep, factor = dropblock_keep_mask(u.to(x.dtype), keep_prob, block_size, gamma_scale,
+                                       x.shape[1], x.shape[2])
+    return x * keep * factor.to(x.dtype)
+
+
+def ece(conf, pred, label, num_thresholds=10):
+    """metric/ece_metric.py:171-298 for one batch: per-bin (correct, confidence sum, count) and the
+    expected calibration error sum_b cnt_b/sum(cnt) * |correct_b/(eps+cnt_b) - conf_b/(eps+cnt_b)|."""
+    eps = 1e-7
+    th = [0.0 - eps] + [(i + 1) / num_thresholds for i in range(num_thresholds - 1)] + [1.0 + eps]
+    lo = torch.tensor(th[:num_thresholds]).view(-1, 1)
+    hi = torch.tensor(th[1:]).view(-1, 1)
+    c = conf.float().view(1, -1)
+    inb = (c > lo) & (c <= hi)
+    ok = (pred.view(1, -1) == label.view(1, -1)) & inb
+    correct = ok.float().sum(1)
+    csum = (c * inb.float()).sum(1)
+    cnt = inb.float().sum(1)
+    val = ((cnt / cnt.sum()) * (correct / (eps + cnt) - csum / (eps + cnt)).abs()).sum()
+    return val, correct, csum, cnt
 
 
 def l2_loss(t):

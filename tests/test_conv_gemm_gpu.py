@@ -242,10 +242,11 @@ def test_large_shapes_linearity(lib):
 
 # ---------------------------------------------------------------------------------------------
 # fp32 parity mode: operands split into three bf16 planes (acnn_split3), six cross products in the
-# fp32 TMEM accumulator.  Inputs are full-precision fp32; tolerance 2e-6 relative to the output's
-# max magnitude against an fp64 oracle (fp32 rounding of the result itself is 6e-8).
+# fp32 TMEM accumulator.  Inputs are full-precision fp32; tolerance 5e-6 relative to the output's
+# max magnitude against an fp64 oracle (the tensor core's fp32 accumulation truncates: measured
+# 1-3e-6 at K = 2304; fp32 rounding of the result itself is 6e-8).
 # ---------------------------------------------------------------------------------------------
-F32MODE_TOL = 2e-6
+F32MODE_TOL = 5e-6
 
 
 def _planes(lib, t):

@@ -1,8 +1,10 @@
 """Data-parallel semantics on CPU with 2 gloo ranks: every rank runs the product's layer plan on
-its shard (torch interpreter standing in for the kernels), gradients are sum-all-reduced and the
-1/N is folded into the SGD step -- exactly what Trainer.train_step does with NCCL.  The result must
-equal the oracle's MirroredStrategy semantics (per-replica BN statistics, averaged gradients;
-SURVEY 3.4 / official/utils/misc/distribution_utils.py:24-76)."""
+its shard (torch interpreter standing in for the kernels) and drives the SAME data-parallel code as
+Trainer.train_step (assembled_cnn_b200/dp.py): the backward cut into segments, each followed by the
+sum-all-reduce of its gradient bucket, the 1/N folded into the SGD step, and the mean aggregation of
+the BN moving statistics.  The result must equal the oracle's MirroredStrategy semantics
+(per-replica BN statistics, averaged gradients, averaged moving statistics; SURVEY 3.4 /
+official/utils/misc/distribution_utils.py:24-76)."""
 import os
 import socket
 
@@ -28,6 +30,7 @@ def _worker(rank, port, out_path):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
     torch.set_num_threads(4)
+    from assembled_cnn_b200 import dp
     from assembled_cnn_b200.plan import ModelConfig, build_plan
     from oracle import model as M, plan_interp as PI
     plan = build_plan(ModelConfig(**KW), B_LOCAL, HW, HW, training=True, mixup_type=0,
@@ -41,12 +44,24 @@ def _worker(rank, port, out_path):
     lab = torch.randint(1, 1001, (B_LOCAL * WORLD,), generator=g).int()
     sl = slice(rank * B_LOCAL, (rank + 1) * B_LOCAL)
     it.forward(x[sl], lab[sl])
-    it.run(plan.backward)
-    dist.all_reduce(it.grads)                 # one collective per step over the flat buffer
+    # the Trainer's schedule: backward segments interleaved with the bucket all-reduces
+    buckets = dp.grad_buckets(plan)
+    segments = dp.backward_segments(plan, buckets)
+    assert len(buckets) >= 4 and segments[0][0] == 0 and segments[-1][1] == len(plan.backward)
+    assert buckets[0][1] == plan.param_elems and buckets[-1][0] == 0
+    reduced = torch.zeros(plan.param_elems, dtype=torch.bool)
+    for ev in dp.schedule(buckets, segments):
+        if ev[0] == "run":
+            it.run(plan.backward[ev[1]:ev[2]])
+        else:
+            snapshot = it.grads[ev[1]:ev[2]].clone()
+            dp.all_reduce_bucket(it.grads, ev[1], ev[2])
+            reduced[ev[1]:ev[2]] = True
+            it._bucket_check = getattr(it, "_bucket_check", []) + [(ev[1], ev[2], snapshot)]
+    assert reduced.all()
     it.run(plan.update)
     # BN moving statistics are averaged across replicas (mirrored-variable mean aggregation)
-    dist.all_reduce(it.state)
-    it.state /= WORLD
+    dp.average_moving_statistics(it.state, WORLD)
     if rank == 0:
         torch.save({n: it.get_tf(n).clone() for n in list(plan.params) + list(plan.state)}, out_path)
     dist.barrier()

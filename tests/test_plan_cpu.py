@@ -153,4 +153,7 @@ def test_flag_validation_errors_match_reference():
     with pytest.raises(ValueError):
         ModelConfig(resnet_size=77).validate()
     with pytest.raises(NotImplementedError):
-        ModelConfig(pool_type="gem").validate()
+        ModelConfig(pool_type="max").validate()
+    ModelConfig(pool_type="gem", embedding_size=256).validate()      # supported
+    with pytest.raises(ValueError):
+        ModelConfig(embedding_size=100).validate()

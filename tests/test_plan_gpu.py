@@ -45,8 +45,17 @@ def _outputs(op):
     if k == "bn_finalize":
         bn = a["bn"]
         return [("slot", bn.work), ("state", bn.mm), ("state", bn.mv)]
-    if k in ("bn_act", "blurpool", "avgpool", "maxpool", "gap", "zero_insert", "grad_combine"):
+    if k in ("bn_act", "blurpool", "avgpool", "maxpool", "gap", "zero_insert", "grad_combine",
+             "dropblock_apply"):
         return T("out")
+    if k == "gem":
+        return T("out") + S("ssum")
+    if k == "gem_bwd":
+        return T("dx")
+    if k == "dropblock_mask":
+        return S("keep") + S("scale")
+    if k == "kd_teacher":
+        return T("yt")
     if k == "sk_gap":
         return S("s")
     if k == "sk_fc":
@@ -93,7 +102,7 @@ def _err(got, ref):
 
 
 def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbose=False,
-             dtype="bf16"):
+             dtype="bf16", use_dropblock=False, kd_temp=0.0, keep_prob=0.9):
     H, W = (HW, HW) if isinstance(HW, int) else HW
     from oracle import model as M, plan_interp as PI
     from assembled_cnn_b200.plan import ModelConfig, build_plan
@@ -103,7 +112,7 @@ def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbo
     fp32 = dtype == "fp32"
     bf16_tol, f32_tol = (2e-5, 2e-4) if fp32 else (BF16_TOL, F32_TOL)
     plan = build_plan(cfg, B, H, W, training=training, mixup_type=mix, label_smoothing=0.1,
-                      dtype=dtype)
+                      dtype=dtype, use_dropblock=use_dropblock, kd_temp=kd_temp)
     _, vs = M.build(seed=42, input_hw=64, use_resnet_d=use_resnet_d, **cfg_kw)
     g = torch.Generator().manual_seed(3)
     for n in vs.vars:       # non-trivial BN parameters / statistics
@@ -118,9 +127,10 @@ def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbo
     rt = Runtime(plan)
     it.set_weights(vs.vars)
     rt.set_weights(vs.vars)
-    hp = dict(lr=0.05, momentum=0.9, weight_decay=1e-4)
+    hp = dict(lr=0.05, momentum=0.9, weight_decay=1e-4, keep_prob=keep_prob)
     it.hp.update(hp)
     rt.set_hparams(**hp)
+    rt.dropblock_feed = True          # masks from the fed uniforms (identical on both sides)
     m = plan.meta
     Bin = m["input_batch"]
     x = (torch.randn(Bin, H, W, 3, generator=g) * 64).clamp(-124, 152)
@@ -134,6 +144,10 @@ def lockstep(cfg_kw, use_resnet_d=False, B=4, HW=64, mix=0, training=True, verbo
         feeds[m["lam1"]] = torch.rand(Bin // 2, generator=g)
     if mix == 2:
         feeds[m["lam2"]] = torch.rand(Bin // 2, generator=g)
+    for name in m.get("dropblock_u", []):
+        feeds[name] = torch.rand(plan.tensors[name].shape, generator=g)
+    if "teacher_logits" in m:
+        feeds[m["teacher_logits"]] = 3.0 * torch.randn(Bin, 1001, generator=g)
     for name, v in feeds.items():
         it.t[name] = v.to(it.dtype) if v.is_floating_point() else v
         rt.t[name].copy_(v)
@@ -216,6 +230,32 @@ def test_train_step_lockstep_fp32_mode(name):
     """dtype='fp32' (the reference's default dtype): every op against the exact interpreter."""
     kw, d, mix = CONFIGS[name]
     failures, _ = lockstep(kw, d, B=4, HW=64, mix=mix, training=True, dtype="fp32")
+    assert not failures, "\n".join(failures[:20])
+
+
+FEATURE_CONFIGS = {
+    # SURVEY 8(f) rows: GeM pooling + embedding head + KD (mixup 2: the teacher-label quirk);
+    # flatten pooling + KD in the fp32 mode; DropBlock on both block kinds (needs 224 px: the
+    # stage-4 feature map must be >= the 7 x 7 block)
+    "gem_embedding_kd_mix2": dict(cfg=dict(pool_type="gem", embedding_size=64, resnet_size=50,
+                                           resnet_version=2, use_sk_block=True,
+                                           anti_alias_type="sconv", anti_alias_filter_size=3),
+                                  mix=2, kd_temp=2.0),
+    "flatten_kd_fp32": dict(cfg=dict(resnet_size=50, resnet_version=1, pool_type="flatten"), mix=1,
+                            kd_temp=1.0, dtype="fp32"),
+    "dropblock_assemble": dict(cfg=dict(resnet_size=50, resnet_version=2, use_sk_block=True,
+                                        anti_alias_type="sconv", anti_alias_filter_size=3),
+                               use_dropblock=True, B=2, HW=224),
+    "dropblock_vanilla_fp32": dict(cfg=dict(resnet_size=50, resnet_version=1), use_dropblock=True,
+                                   B=2, HW=224, dtype="fp32"),
+}
+
+
+@pytest.mark.parametrize("name", list(FEATURE_CONFIGS))
+def test_feature_rows_lockstep(name):
+    kw = dict(FEATURE_CONFIGS[name])
+    cfg = kw.pop("cfg")
+    failures, _ = lockstep(cfg, False, training=True, **kw)
     assert not failures, "\n".join(failures[:20])
 
 
