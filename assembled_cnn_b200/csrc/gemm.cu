@@ -653,24 +653,28 @@ struct WgradParams {
   int kw;
   int HoWo, Wo;
   int stride, pad_h_lo, pad_w_lo;
-  int stages_total;      // ceil(P / 64)
+  int pix;               // pixels per stage (64 or 128)
+  int stages_total;      // ceil(P / pix)
   int stages_per_split;
   float* dw;
 };
 
-constexpr int kWgPix = 64;   // pixels per pipeline stage (4 UMMA K-steps)
+constexpr int kWgPix = 64;   // default pixels per pipeline stage (4 UMMA K-steps); PIX = 128: 8 steps
 
 // MT = 128-row blocks of (tap,ci) per CTA (1 or 2): with MT = 2 two accumulators share every dy
 // stage, i.e. twice the tensor work per pipeline round-trip and half the dy traffic per FLOP.
-template <int BN, int MT, int NP = 1>
+// PIX = pixels (GEMM K) per pipeline stage: 64, or 128 (twice the MMAs per TMA / barrier round trip
+// of the single-warp issue loops, which bound the small-N layers)
+template <int BN, int MT, int NP = 1, int PIX = kWgPix>
 struct WgradCfg {
-  static constexpr int kAHalfBytes = kWgPix * 128 * 2;   // 64 pixels x 128 (tap,ci) columns
+  static constexpr int kAHalfBytes = PIX * 128 * 2;   // PIX pixels x 128 (tap,ci) columns
   static constexpr int kABytes = MT * kAHalfBytes;       // one plane
-  static constexpr int kBBytes = kWgPix * BN * 2;    // 64 pixels x BN output channels, one plane
+  static constexpr int kBBytes = PIX * BN * 2;    // PIX pixels x BN output channels, one plane
   static constexpr int kStageBytes = NP * (kABytes + kBBytes);
   static constexpr int kStagesFit = (kSmemBudget - 1024) / kStageBytes;
   static constexpr int kStages =
-      NP == 3 ? (kStagesFit > 3 ? 3 : kStagesFit)
+      PIX != kWgPix ? (kStagesFit > 4 ? 4 : kStagesFit)
+      : NP == 3 ? (kStagesFit > 3 ? 3 : kStagesFit)
               : (MT == 1 ? ((BN >= 256) ? 4 : ((BN == 128) ? 3 : 4))
                          : (kStagesFit > 5 ? 5 : kStagesFit));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
@@ -682,18 +686,18 @@ struct WgradCfg {
 };
 
 // CW: channel width of one im2col chunk of x (16/32/64), CWB: channel width of one dy chunk.
-template <int BN, int CW, int CWB, bool IM2COL, int MT, int NP>
+template <int BN, int CW, int CWB, bool IM2COL, int MT, int NP, int PIX>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const __grid_constant__ CUtensorMap tmX1, const __grid_constant__ CUtensorMap tmX2,
                   const __grid_constant__ CUtensorMap tmDY1,
                   const __grid_constant__ CUtensorMap tmDY2, const WgradParams p) {
-  using Cfg = WgradCfg<BN, MT, NP>;
+  using Cfg = WgradCfg<BN, MT, NP, PIX>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kAChunks = MT * 128 / CW;        // chunks of both 128-row blocks, consecutive
   constexpr int kBChunks = BN / CWB;
-  constexpr int kAChunkBytes = kWgPix * CW * 2;
-  constexpr int kBChunkBytes = kWgPix * CWB * 2;
+  constexpr int kAChunkBytes = PIX * CW * 2;
+  constexpr int kBChunkBytes = PIX * CWB * 2;
   constexpr uint32_t kIdesc = make_idesc_bf16(BN, true, true);
 
   extern __shared__ uint8_t smem_raw[];
@@ -753,7 +757,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       ch_s[j] = tap - ch_r[j] * p.kw;
     }
     for (int it = 0; it < num_ks; ++it) {
-      const int p0 = (ks_begin + it) * kWgPix;
+      const int p0 = (ks_begin + it) * PIX;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
@@ -811,7 +815,7 @@ wgrad_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         for (int h = 0; h < MT; ++h) {
           if (h == 0 || second) {
 #pragma unroll
-            for (int ks = 0; ks < kWgPix / 16; ++ks) {
+            for (int ks = 0; ks < PIX / 16; ++ks) {
 #pragma unroll
               for (int t = 0; t < (NP == 3 ? 6 : 1); ++t) {
                 const int pa = NP == 3 ? plane_term_a(t) : 0;
@@ -1081,12 +1085,12 @@ struct WgradMaps {
   CUtensorMap x[3], dy[3];
 };
 
-template <int BN, int CW, int CWB, bool IM2COL, int MT, int NP>
+template <int BN, int CW, int CWB, bool IM2COL, int MT, int NP, int PIX = kWgPix>
 static int launch_wgrad(const WgradMaps& tm, WgradParams p, int n_tiles, int deterministic,
                         cudaStream_t stream) {
-  using Cfg = WgradCfg<BN, MT, NP>;
+  using Cfg = WgradCfg<BN, MT, NP, PIX>;
   static bool attr_set = false;
-  auto kern = wgrad_gemm_kernel<BN, CW, CWB, IM2COL, MT, NP>;
+  auto kern = wgrad_gemm_kernel<BN, CW, CWB, IM2COL, MT, NP, PIX>;
   const int m_tiles = ceil_div(p.Ktot, MT * 128);
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1132,11 +1136,18 @@ static int dispatch_wgrad_cwb(int cwb, int np, const WgradMaps& tm, const WgradP
         // measured: pays when the (tap,ci) extent and the pixel count are both large (otherwise
         // halving the number of CTAs costs more than the shared dy stage saves)
         const bool big = (p.Ktot >= 1024 && p.P >= 50176) || p.Ktot >= 4096;
-        if (p.Ktot > 128 && (g_conv_mtiles_mode == 2 || (g_conv_mtiles_mode == -1 && big)))
+        if (p.pix == 64 && p.Ktot > 128 &&
+            (g_conv_mtiles_mode == 2 || (g_conv_mtiles_mode == -1 && big)))
           return launch_wgrad<BN, CW, 64, IM2COL, 2, 1>(tm, p, nt, det, s);
+      }
+      if constexpr (BN <= 128) {
+        if (p.pix == 128) return launch_wgrad<BN, CW, 64, IM2COL, 1, 1, 128>(tm, p, nt, det, s);
       }
       return launch_wgrad<BN, CW, 64, IM2COL, 1, 1>(tm, p, nt, det, s);
     }
+  }
+  if constexpr (BN <= 128) {
+    if (p.pix == 128) return launch_wgrad<BN, CW, 32, IM2COL, 1, 1, 128>(tm, p, nt, det, s);
   }
   return launch_wgrad<BN, CW, 32, IM2COL, 1, 1>(tm, p, nt, det, s);
 }
@@ -1156,6 +1167,14 @@ static int dispatch_wgrad(int bn, int cw, int cwb, int np, const WgradMaps& tm, 
   if (bn == 128) return dispatch_wgrad_cw<128, IM2COL>(cw, cwb, np, tm, p, nt, det, s);
   if (bn == 64) return dispatch_wgrad_cw<64, IM2COL>(cw, cwb, np, tm, p, nt, det, s);
   return dispatch_wgrad_cw<32, IM2COL>(cw, cwb, np, tm, p, nt, det, s);
+}
+
+// 0: choose per problem; 64 / 128: force the pixels per stage where the shape allows it
+static int g_wgrad_pix = 0;
+static bool wgrad_wants_pix128(const WgradParams& p, int bn) {
+  (void)p;
+  (void)bn;
+  return false;     // set from measurements (tools/exp_wgrad_pix.py); off until measured
 }
 
 static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* dy, float* dw,
@@ -1179,25 +1198,30 @@ static int conv_wgrad_host(const acnn_conv_geom& g, const void* x, const void* d
   p.stride = g.stride;
   p.pad_h_lo = g.pad_h_lo;
   p.pad_w_lo = g.pad_w_lo;
-  p.stages_total = ceil_div(p.P, kWgPix);
+  int bn = g.Cout >= 256 ? 256 : (g.Cout >= 128 ? 128 : (g.Cout >= 64 ? 64 : 32));
+  if (np == 3 && bn > 128) bn = 128;   // three operand planes per stage: smem
+  // 128-pixel stages: only the bf16 path, N tile <= 128 (smem), enough pixels to split
+  p.pix = kWgPix;
+  if (np == 1 && bn <= 128 && p.P >= 4096 &&
+      (g_wgrad_pix == 128 || (g_wgrad_pix == 0 && wgrad_wants_pix128(p, bn))))
+    p.pix = 128;
+  p.stages_total = ceil_div(p.P, p.pix);
   p.stages_per_split = p.stages_total;
   p.dw = dw;
   const int cw = chunk_width(g.Cin);
   const int cwb = (g.Cout % 64 == 0) ? 64 : 32;
-  int bn = g.Cout >= 256 ? 256 : (g.Cout >= 128 ? 128 : (g.Cout >= 64 ? 64 : 32));
-  if (np == 3 && bn > 128) bn = 128;   // three operand planes per stage: smem
   ACNN_REQUIRE(g.Cout % bn == 0, "wgrad: Cout=%d not a multiple of its N tile %d", g.Cout, bn);
   WgradMaps tm;
   const int64_t x_plane = input_elems(g), dy_plane = (int64_t)p.P * g.Cout;
   for (int pl = 0; pl < np; ++pl) {
     const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x) + pl * x_plane;
     const __nv_bfloat16* dp = static_cast<const __nv_bfloat16*>(dy) + pl * dy_plane;
-    rc = make_map_2d(&tm.dy[pl], dp, p.P, g.Cout, g.Cout, kWgPix, cwb);
+    rc = make_map_2d(&tm.dy[pl], dp, p.P, g.Cout, g.Cout, p.pix, cwb);
     if (rc) return rc;
     if (plain) {
-      rc = make_map_2d(&tm.x[pl], xp, p.P, g.Cin, g.Cin, kWgPix, cw);
+      rc = make_map_2d(&tm.x[pl], xp, p.P, g.Cin, g.Cin, p.pix, cw);
     } else {
-      rc = make_map_im2col(&tm.x[pl], xp, g, cw, kWgPix);
+      rc = make_map_im2col(&tm.x[pl], xp, g, cw, p.pix);
     }
     if (rc) return rc;
   }
@@ -1220,6 +1244,12 @@ extern "C" {
 int acnn_set_conv_mtiles(int mode) {
   const int prev = acnn::g_conv_mtiles_mode;
   acnn::g_conv_mtiles_mode = (mode == 1 || mode == 2) ? mode : -1;
+  return prev;
+}
+
+int acnn_set_wgrad_pixels(int pix) {
+  const int prev = acnn::g_wgrad_pix;
+  acnn::g_wgrad_pix = (pix == 64 || pix == 128) ? pix : 0;
   return prev;
 }
 

@@ -225,11 +225,245 @@ static int ew(const float* in, const float* act, float* out, int64_t n, int mode
   return check_launch("ew");
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused SK attention chains: ONE launch per direction instead of 4 kernels + 2 memsets (forward) /
+// 6 kernels + 2 memsets (backward) per SK block -- 19 blocks per Assemble-ResNet-50 step, and every
+// one of those launches was pure latency (72 GB/s, <= 0.3 MMAC per image).  The chain runs on one
+// thread-block cluster of 8 CTAs: the GEMM phases are tiled 64x64 over the cluster (no split-K:
+// every output element has one owner, so the results are deterministic and nothing needs zeroing),
+// the phases are separated by cluster barriers (release / acquire: the intermediate [B, <=2f]
+// matrices round-trip through L2).
+// ------------------------------------------------------------------------------------------
+constexpr int kCluster = 8;
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+
+// One 64x64 tile of C = A*B at (m0, n0), K range [0, K); ACC: C += tile, else C = tile.
+template <bool ACC>
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ A, const float* __restrict__ B,
+                                          float* __restrict__ C, int M, int N, int K, int sAm,
+                                          int sAk, int sBk, int sBn, int m0, int n0,
+                                          float (*As)[kTM + 4], float (*Bs)[kTN + 4]) {
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += kTK) {
+#pragma unroll
+    for (int e = 0; e < (kTM * kTK) / kFT; ++e) {
+      const int idx = tid + e * kFT;
+      int mm, kk;
+      if (sAm == 1) { mm = idx % kTM; kk = idx / kTM; } else { kk = idx % kTK; mm = idx / kTK; }
+      const int m = m0 + mm, k = k0 + kk;
+      // intermediates written by other CTAs of the cluster: plain (coherent) loads, not __ldg
+      As[kk][mm] = (m < M && k < K) ? A[(size_t)m * sAm + (size_t)k * sAk] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < (kTN * kTK) / kFT; ++e) {
+      const int idx = tid + e * kFT;
+      int nn, kk;
+      if (sBn == 1) { nn = idx % kTN; kk = idx / kTN; } else { kk = idx % kTK; nn = idx / kTK; }
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < N && k < K) ? B[(size_t)k * sBk + (size_t)n * sBn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) {
+        float* dst = C + (size_t)m * N + n;
+        *dst = ACC ? *dst + acc[i][j] : acc[i][j];
+      }
+    }
+  }
+}
+
+// C[M][N] (=|+=) A*B with the 64x64 tiles dealt round-robin to the CTAs of the cluster, starting at
+// tile offset `first` (so that two GEMMs of one phase spread over different CTAs).
+template <bool ACC>
+__device__ __forceinline__ void cluster_gemm(const float* A, const float* B, float* C, int M, int N,
+                                             int K, int sAm, int sAk, int sBk, int sBn, int rank,
+                                             int first, float (*As)[kTM + 4], float (*Bs)[kTN + 4]) {
+  const int tn = (N + kTN - 1) / kTN, tm = (M + kTM - 1) / kTM;
+  for (int t = (rank + kCluster - first % kCluster) % kCluster; t < tm * tn; t += kCluster)
+    gemm_tile<ACC>(A, B, C, M, N, K, sAm, sAk, sBk, sBn, (t / tn) * kTM, (t % tn) * kTN, As, Bs);
+}
+
+struct SkFcFwdArgs {
+  const float *s, *w1, *gamma, *beta, *w2;
+  float *moving_mean, *moving_var, *zpre, *bnstat, *z, *att, *scratch;
+  float momentum, eps;
+  int training, B, f, d;
+};
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFT)
+sk_fc_fwd_fused_kernel(const SkFcFwdArgs p) {
+  pdl_entry();
+  __shared__ float As[kTK][kTM + 4];
+  __shared__ float Bs[kTK][kTN + 4];
+  const int rank = (int)cluster_cta_rank();
+  const int B = p.B, f = p.f, d = p.d;
+  // zpre[B,d] = s[B,f] * W1[d,f]^T
+  cluster_gemm<false>(p.s, p.w1, p.zpre, B, d, f, f, 1, 1, f, rank, 0, As, Bs);
+  cluster_sync_all();
+  // batch-norm over the batch + ReLU, one warp per channel
+  {
+    const int lane = threadIdx.x & 31;
+    for (int j = rank * (kFT / 32) + (threadIdx.x >> 5); j < d; j += kCluster * (kFT / 32)) {
+      float mean, var;
+      if (p.training) {
+        float sm = 0.f, q = 0.f;
+        for (int b = lane; b < B; b += 32) {
+          const float v = p.zpre[(size_t)b * d + j];
+          sm += v;
+          q += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          sm += __shfl_xor_sync(0xffffffffu, sm, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        mean = sm / B;
+        var = fmaxf(q / B - mean * mean, 0.f);
+        if (lane == 0) {
+          const float unbiased = var * ((float)B / fmaxf((float)B - 1.f, 1.f));
+          p.moving_mean[j] = p.moving_mean[j] * p.momentum + mean * (1.f - p.momentum);
+          p.moving_var[j] = p.moving_var[j] * p.momentum + unbiased * (1.f - p.momentum);
+        }
+      } else {
+        mean = p.moving_mean[j];
+        var = p.moving_var[j];
+      }
+      const float rstd = rsqrtf(var + p.eps);
+      if (lane == 0) {
+        p.bnstat[j] = mean;
+        p.bnstat[d + j] = rstd;
+      }
+      const float sc = p.gamma[j] * rstd, sh = p.beta[j] - mean * sc;
+      for (int b = lane; b < B; b += 32)
+        p.z[(size_t)b * d + j] = fmaxf(fmaf(p.zpre[(size_t)b * d + j], sc, sh), 0.f);
+    }
+  }
+  cluster_sync_all();
+  // a[B,2f] = z[B,d] * W2[2f,d]^T
+  cluster_gemm<false>(p.z, p.w2, p.scratch, B, 2 * f, d, d, 1, 1, d, rank, 0, As, Bs);
+  cluster_sync_all();
+  // 2-way softmax over the halves: att = sigmoid(a0 - a1)
+  for (int i = rank * kFT + threadIdx.x; i < B * f; i += kCluster * kFT) {
+    const int b = i / f, c = i - b * f;
+    const float dd = p.scratch[(size_t)b * 2 * f + c] - p.scratch[(size_t)b * 2 * f + f + c];
+    p.att[i] = 1.f / (1.f + expf(-dd));
+  }
+}
+
+struct SkFcBwdArgs {
+  const float *dA, *att, *z, *zpre, *bnstat, *gamma, *s, *w1, *w2;
+  float *dw1, *dw2, *dgamma, *dbeta, *ds, *scratch;
+  int B, f, d;
+};
+
+__global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kFT)
+sk_fc_bwd_fused_kernel(const SkFcBwdArgs p) {
+  pdl_entry();
+  __shared__ float As[kTK][kTM + 4];
+  __shared__ float Bs[kTK][kTN + 4];
+  const int rank = (int)cluster_cta_rank();
+  const int B = p.B, f = p.f, d = p.d;
+  float* da = p.scratch;                       // [B][2f]
+  float* dz = p.scratch + (size_t)B * 2 * f;   // [B][d]
+  // softmax-2 backward: da0 = att (1 - att) dA = -da1
+  for (int i = rank * kFT + threadIdx.x; i < B * f; i += kCluster * kFT) {
+    const int b = i / f, c = i - b * f;
+    const float t = p.att[i] * (1.f - p.att[i]) * p.dA[i];
+    da[(size_t)b * 2 * f + c] = t;
+    da[(size_t)b * 2 * f + f + c] = -t;
+  }
+  cluster_sync_all();
+  // dW2[2f,d] += da^T[2f,B] * z[B,d] ;  dz[B,d] = da[B,2f] * W2[2f,d]
+  cluster_gemm<true>(da, p.z, p.dw2, 2 * f, d, B, 1, 2 * f, d, 1, rank, 0, As, Bs);
+  cluster_gemm<false>(da, p.w2, dz, B, d, 2 * f, 2 * f, 1, d, 1, rank,
+                      ((2 * f + kTM - 1) / kTM) * ((d + kTN - 1) / kTN), As, Bs);
+  cluster_sync_all();
+  // ReLU + batch-norm (over the batch) backward, one warp per channel: dz -> dzpre in place
+  {
+    const int lane = threadIdx.x & 31;
+    for (int j = rank * (kFT / 32) + (threadIdx.x >> 5); j < d; j += kCluster * (kFT / 32)) {
+      const float mean = p.bnstat[j], rstd = p.bnstat[d + j];
+      float s1 = 0.f, s2 = 0.f;
+      for (int b = lane; b < B; b += 32) {
+        const size_t i = (size_t)b * d + j;
+        const float g = p.z[i] > 0.f ? dz[i] : 0.f;
+        s1 += g;
+        s2 += g * ((p.zpre[i] - mean) * rstd);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      const float k1 = p.gamma[j] * rstd;
+      for (int b = lane; b < B; b += 32) {
+        const size_t i = (size_t)b * d + j;
+        const float g = p.z[i] > 0.f ? dz[i] : 0.f;
+        const float xh = (p.zpre[i] - mean) * rstd;
+        dz[i] = k1 * (g - s1 / B - xh * s2 / B);
+      }
+      if (lane == 0) {
+        p.dgamma[j] += s2;
+        p.dbeta[j] += s1;
+      }
+    }
+  }
+  cluster_sync_all();
+  // dW1[d,f] += dzpre^T[d,B] * s[B,f] ;  ds[B,f] = dzpre[B,d] * W1[d,f]
+  cluster_gemm<true>(dz, p.s, p.dw1, d, f, B, 1, d, f, 1, rank, 0, As, Bs);
+  cluster_gemm<false>(dz, p.w1, p.ds, B, f, d, d, 1, f, 1, rank,
+                      ((d + kTM - 1) / kTM) * ((f + kTN - 1) / kTN), As, Bs);
+}
+
+// 1 (default): the fused cluster kernels; 0: the multi-launch split-K path (kept for comparison)
+static int g_sk_fc_fused = 1;
+
 }  // namespace acnn
 
 using namespace acnn;
 
 extern "C" {
+
+int acnn_set_sk_fc_fused(int on) {
+  const int prev = g_sk_fc_fused;
+  g_sk_fc_fused = on ? 1 : 0;
+  return prev;
+}
 
 int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const float* beta,
                    float* moving_mean, float* moving_var, float momentum, float eps, int training,
@@ -238,6 +472,13 @@ int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const fl
   ACNN_REQUIRE(s && w1 && gamma && beta && moving_mean && moving_var && w2 && zpre && bnstat && z &&
                    att && scratch, "sk_fc_fwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sk_fc_fused) {
+    SkFcFwdArgs a{s, w1, gamma, beta, w2, moving_mean, moving_var, zpre, bnstat, z, att, scratch,
+                  momentum, eps, training, B, f, d};
+    launch_k(sk_fc_fwd_fused_kernel, dim3(kCluster), dim3(kFT), 0, st, a);
+    count_launch();
+    return check_launch("sk_fc_fwd_fused");
+  }
   // zpre[B,d] = s[B,f] * W1[d,f]^T
   int rc = sgemm(s, w1, zpre, B, d, f, f, 1, 1, f, true, deterministic, st);
   if (rc) return rc;
@@ -258,6 +499,13 @@ int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const floa
   ACNN_REQUIRE(dA && att && z && zpre && bnstat && gamma && s && w1 && w2 && dw1 && dw2 && dgamma &&
                    dbeta && ds && scratch, "sk_fc_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_sk_fc_fused) {
+    SkFcBwdArgs a{dA, att, z, zpre, bnstat, gamma, s, w1, w2, dw1, dw2, dgamma, dbeta, ds, scratch,
+                  B, f, d};
+    launch_k(sk_fc_bwd_fused_kernel, dim3(kCluster), dim3(kFT), 0, st, a);
+    count_launch();
+    return check_launch("sk_fc_bwd_fused");
+  }
   float* da = scratch;                       // [B][2f]
   float* dz = scratch + (size_t)B * 2 * f;   // [B][d]
   launch_k(sk_gate_bwd_kernel, dim3((int)ceil_div64((int64_t)B * f, 256)), dim3(256), 0, st, dA, att, da, B, f);

@@ -107,7 +107,8 @@ class Model:
                  resnet_version=DEFAULT_VERSION, dtype="bf16", no_downsample=False,
                  zero_gamma=False, use_se_block=False, use_sk_block=False, bn_momentum=0.997,
                  embedding_size=0, anti_alias_filter_size=0, anti_alias_type="", pool_type="gap",
-                 loss_type="softmax", bl_alpha=2, bl_beta=4, *, seed=42, device="cuda:0"):
+                 loss_type="softmax", bl_alpha=2, bl_beta=4, *, seed=42, device="cuda:0",
+                 deterministic=None):
         if data_format not in (None, "channels_last"):
             raise ValueError("this implementation is NHWC only (data_format='channels_last')")
         if dtype not in ALLOWED_TYPES:
@@ -127,6 +128,9 @@ class Model:
         self.data_format = "channels_last"
         self.device = device
         self.seed = seed
+        # None: bit-reproducible steps in the fp32 mode only; True: also in bf16 (wgrad and the SE
+        # fc GEMMs run without split-K -- slower); every other reduction is ordered in both modes
+        self.deterministic = deterministic
         self._runtimes = {}          # (B, H, W, training, use_resnet_d, mixup, ls) -> Runtime
         self._primary = {}           # use_resnet_d -> Runtime owning the parameters
         self._pending_weights = None
@@ -144,7 +148,7 @@ class Model:
                               label_smoothing=label_smoothing, with_loss=with_loss,
                               dtype=self.dtype, use_dropblock=use_dropblock, kd_temp=kd_temp)
             prim = self._primary.get(bool(use_resnet_d))
-            rt = Runtime(plan, self.device, share=prim)
+            rt = Runtime(plan, self.device, share=prim, deterministic=self.deterministic)
             if prim is None:
                 self._primary[bool(use_resnet_d)] = rt
                 if self._pending_weights is not None:
@@ -241,7 +245,7 @@ def build_model(**flags) -> Model:
         "resnet_size", "data_format", "num_classes", "resnet_version", "dtype", "no_downsample",
         "zero_gamma", "use_se_block", "use_sk_block", "bn_momentum", "embedding_size",
         "anti_alias_filter_size", "anti_alias_type", "pool_type", "loss_type", "bl_alpha",
-        "bl_beta", "seed", "device")}
+        "bl_beta", "seed", "device", "deterministic")}
     if flags:
         raise TypeError("build_model: unknown flag(s) %s" % sorted(flags))
     ctor.setdefault("resnet_size", DEFAULTS["resnet_size"])

@@ -48,6 +48,14 @@ int acnn_set_pdl(int on);
  * per CTA tile.  -1 = choose per problem (default), 1 = always one, 2 = two wherever the shape
  * allows it (N tile <= 128).  Returns the previous mode. */
 int acnn_set_conv_mtiles(int mode);
+/* Tuning knob of the wgrad launcher (no effect on results beyond fp32 summation order): pixels
+ * (GEMM K) per pipeline stage, 64 or 128 (N tile <= 128 only); 0 = choose per problem (default).
+ * Returns the previous setting. */
+int acnn_set_wgrad_pixels(int pix);
+/* SK attention chains (acnn_sk_fc_fwd / acnn_sk_fc_bwd): 1 (default) = one fused launch per
+ * direction on a thread-block cluster of 8 CTAs (no split-K: deterministic); 0 = the multi-launch
+ * split-K path.  Same results up to fp32 summation order.  Returns the previous setting. */
+int acnn_set_sk_fc_fused(int on);
 
 /* Convolution geometry (correlation, no bias) -- nets/model_helper.py:67-78 conv2d_fixed_padding
  * + fixed_padding :40-64.  Ho = (H + pad_h_lo + pad_h_hi - kh) / stride + 1, same for W. */

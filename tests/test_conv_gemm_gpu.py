@@ -198,9 +198,17 @@ def test_dgrad_matches_autograd(lib, case, mt):
     assert _relerr(dxd.float().cpu(), dx_ref) < BF16_TOL
 
 
+@pytest.fixture(params=[64, 128], ids=["pix64", "pix128"])
+def wgrad_pix(lib, request):
+    """acnn_set_wgrad_pixels: pixels (GEMM K) per wgrad pipeline stage."""
+    prev = lib.acnn_set_wgrad_pixels(request.param)
+    yield request.param
+    lib.acnn_set_wgrad_pixels(prev)
+
+
 @pytest.mark.parametrize("mt", MT, ids=MT_IDS)
 @pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
-def test_wgrad_matches_autograd(lib, case, mt):
+def test_wgrad_matches_autograd(lib, case, mt, wgrad_pix):
     from assembled_cnn_b200 import _lib
     B, H, W, Cin, Cout, k, stride, pads = case
     g = _geom(B, H, W, Cin, Cout, k, stride, pads)
