@@ -21,7 +21,7 @@ static int pdl_default() {
   // resident dependent takes registers / SM slots from the still-running HBM-bound predecessor), so
   // it is opt-in
   const char* e = getenv("ACNN_PDL");
-  return (e && e[0] == '1') ? 1 : 0;
+  return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
 int g_use_pdl = pdl_default();
 
@@ -44,7 +44,7 @@ const char* acnn_last_error(void) { return acnn::g_err; }
 int acnn_version(void) { return 100; }
 int acnn_set_pdl(int on) {
   const int prev = acnn::g_use_pdl;
-  acnn::g_use_pdl = on ? 1 : 0;
+  acnn::g_use_pdl = (on == 1 || on == 2) ? on : 0;
   return prev;
 }
 int64_t acnn_launch_count(void) { return acnn::g_launches.load(std::memory_order_relaxed); }

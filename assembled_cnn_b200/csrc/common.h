@@ -29,7 +29,7 @@ int check_launch(const char* what);
 // resident, prologue done) while its predecessor drains, and only proceeds past the wait once the
 // predecessor grid has completed and flushed.  Meant to hide the per-kernel launch / drain latency
 // of the ~865 dependent launches of a step; measured NOT to pay here (kept as an opt-in knob).
-extern int g_use_pdl;   // 0 by default (measured slower, see common.cu); ACNN_PDL=1 / acnn_set_pdl(1)
+extern int g_use_pdl;   // 0 by default (mode 1 measured slower, see common.cu); ACNN_PDL=1|2 / acnn_set_pdl
 
 template <class... KArgs, class... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -43,7 +43,11 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  // mode 1: every launch; mode 2: only LIGHT dependents (few CTAs, little shared memory: the
+  // finalize / small-GEMM / loss kernels) -- their early-resident CTAs cost the still-running
+  // predecessor nothing, while their launch latency (~400 such launches per step) is hidden
+  const bool light = (size_t)grid.x * grid.y * grid.z <= 320 && smem <= 48 * 1024;
+  cfg.numAttrs = (g_use_pdl == 1 || (g_use_pdl == 2 && light)) ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);   // errors: check_launch()
 }
 

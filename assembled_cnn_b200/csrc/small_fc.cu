@@ -113,19 +113,20 @@ bn_batch_relu_fwd_kernel(const float* __restrict__ zpre, const float* __restrict
   if (j >= d) return;
   float mean, var;
   if (training) {
+    // two-pass (mean, then centred squares): with only B samples per channel and eps = 1e-5,
+    // E[x^2] - E[x]^2 in fp32 loses the variance of nearly constant channels
     float s = 0.f, q = 0.f;
+    for (int b = lane; b < B; b += 32) s += zpre[(size_t)b * d + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / B;
     for (int b = lane; b < B; b += 32) {
-      const float v = zpre[(size_t)b * d + j];
-      s += v;
-      q += v * v;
+      const float c = zpre[(size_t)b * d + j] - mean;
+      q += c * c;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    mean = s / B;
-    var = fmaxf(q / B - mean * mean, 0.f);
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    var = q / B;
     if (lane == 0) {
       const float unbiased = var * ((float)B / fmaxf((float)B - 1.f, 1.f));
       moving_mean[j] = moving_mean[j] * momentum + mean * (1.f - momentum);
@@ -226,9 +227,9 @@ static int ew(const float* in, const float* act, float* out, int64_t n, int mode
 }
 
 // ------------------------------------------------------------------------------------------
-// Fused SK attention chains: ONE launch per direction instead of 4 kernels + 2 memsets (forward) /
-// 6 kernels + 2 memsets (backward) per SK block -- 19 blocks per Assemble-ResNet-50 step, and every
-// one of those launches was pure latency (72 GB/s, <= 0.3 MMAC per image).  The chain runs on one
+// EXPERIMENT (measured slower, off by default -- see g_sk_fc_fused below): fused SK attention
+// chains, ONE launch per direction instead of 4 kernels + 2 memsets (forward) / 6 kernels + 2
+// memsets (backward) per SK block (19 blocks per Assemble-ResNet-50 step).  The chain runs on one
 // thread-block cluster of 8 CTAs: the GEMM phases are tiled 64x64 over the cluster (no split-K:
 // every output element has one owner, so the results are deterministic and nothing needs zeroing),
 // the phases are separated by cluster barriers (release / acquire: the intermediate [B, <=2f]
@@ -342,18 +343,17 @@ sk_fc_fwd_fused_kernel(const SkFcFwdArgs p) {
       float mean, var;
       if (p.training) {
         float sm = 0.f, q = 0.f;
+        for (int b = lane; b < B; b += 32) sm += p.zpre[(size_t)b * d + j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
+        mean = sm / B;
         for (int b = lane; b < B; b += 32) {
-          const float v = p.zpre[(size_t)b * d + j];
-          sm += v;
-          q += v * v;
+          const float c = p.zpre[(size_t)b * d + j] - mean;
+          q += c * c;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          sm += __shfl_xor_sync(0xffffffffu, sm, o);
-          q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        mean = sm / B;
-        var = fmaxf(q / B - mean * mean, 0.f);
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        var = q / B;
         if (lane == 0) {
           const float unbiased = var * ((float)B / fmaxf((float)B - 1.f, 1.f));
           p.moving_mean[j] = p.moving_mean[j] * p.momentum + mean * (1.f - p.momentum);
@@ -450,8 +450,12 @@ sk_fc_bwd_fused_kernel(const SkFcBwdArgs p) {
                       ((d + kTM - 1) / kTM) * ((f + kTN - 1) / kTN), As, Bs);
 }
 
-// 1 (default): the fused cluster kernels; 0: the multi-launch split-K path (kept for comparison)
-static int g_sk_fc_fused = 1;
+// 0 (default): the multi-launch split-K path; 1: the fused cluster kernels.  MEASURED (round 2,
+// profiles/r02_exp_knobs.txt): the fused chain is 5x SLOWER per SK block (+3.9 ms per training
+// step): eight CTAs walking un-pipelined 16-wide k-steps are a chain of global-load latencies,
+// where the split-K path spreads the same k-steps over ~296 CTAs.  Kept selectable (it is the
+// deterministic variant and the tests pin it), not used on the hot path.
+static int g_sk_fc_fused = 0;
 
 }  // namespace acnn
 

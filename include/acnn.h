@@ -41,8 +41,9 @@ const char* acnn_last_error(void);
 int acnn_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t acnn_launch_count(void);
-/* Programmatic dependent launch of every kernel of the library (no effect on results): 0 (default)
- * = plain stream order, 1 = on (measured slower on the full step).  Returns the previous setting. */
+/* Programmatic dependent launch (no effect on results): 0 (default) = plain stream order, 1 = every
+ * kernel (measured slower on the full step), 2 = only light dependents (<= 320 CTAs, <= 48 KiB
+ * shared memory).  Returns the previous setting. */
 int acnn_set_pdl(int on);
 /* Tuning knob of the conv GEMM launcher (no effect on results): M tiles (128 output pixels each)
  * per CTA tile.  -1 = choose per problem (default), 1 = always one, 2 = two wherever the shape
@@ -52,9 +53,10 @@ int acnn_set_conv_mtiles(int mode);
  * (GEMM K) per pipeline stage, 64 or 128 (N tile <= 128 only); 0 = choose per problem (default).
  * Returns the previous setting. */
 int acnn_set_wgrad_pixels(int pix);
-/* SK attention chains (acnn_sk_fc_fwd / acnn_sk_fc_bwd): 1 (default) = one fused launch per
- * direction on a thread-block cluster of 8 CTAs (no split-K: deterministic); 0 = the multi-launch
- * split-K path.  Same results up to fp32 summation order.  Returns the previous setting. */
+/* SK attention chains (acnn_sk_fc_fwd / acnn_sk_fc_bwd): 0 (default) = the multi-launch split-K
+ * path; 1 = one fused launch per direction on a thread-block cluster of 8 CTAs (no split-K:
+ * deterministic; measured 5x slower per block, so not the default).  Same results up to fp32
+ * summation order.  Returns the previous setting. */
 int acnn_set_sk_fc_fused(int on);
 
 /* Convolution geometry (correlation, no bias) -- nets/model_helper.py:67-78 conv2d_fixed_padding

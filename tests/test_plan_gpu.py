@@ -245,9 +245,9 @@ FEATURE_CONFIGS = {
                             kd_temp=1.0, dtype="fp32"),
     "dropblock_assemble": dict(cfg=dict(resnet_size=50, resnet_version=2, use_sk_block=True,
                                         anti_alias_type="sconv", anti_alias_filter_size=3),
-                               use_dropblock=True, B=2, HW=224),
+                               use_dropblock=True, B=4, HW=224),
     "dropblock_vanilla_fp32": dict(cfg=dict(resnet_size=50, resnet_version=1), use_dropblock=True,
-                                   B=2, HW=224, dtype="fp32"),
+                                   B=4, HW=224, dtype="fp32"),
 }
 
 

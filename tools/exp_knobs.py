@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """EXPERIMENT: step time of the BASELINE c3 training step under the library's tuning knobs (none of
-them changes results): fused SK attention chains on / off, wgrad pixels per stage 64 / 128.
+them changes results): programmatic dependent launch off / light kernels only / all, fused SK attention chains on / off,
+wgrad pixels per stage 64 / 128.
 
     python tools/exp_knobs.py [--steps 15]
 """
@@ -44,12 +45,16 @@ def step_ms():
     return e0.elapsed_time(e1) / args.steps, loss
 
 
-for fused in (1, 0):
-    for pix in (64, 128):
-        lib.acnn_set_sk_fc_fused(fused)
-        lib.acnn_set_wgrad_pixels(pix)
-        ms, loss = step_ms()
-        print("sk_fc_fused=%d wgrad_pixels=%3d : %.3f ms/step   loss %s" % (fused, pix, ms, loss),
-              flush=True)
-lib.acnn_set_sk_fc_fused(1)
+for pdl in (0, 2, 1):
+    lib.acnn_set_pdl(pdl)
+    ms, loss = step_ms()
+    print("pdl=%d : %.3f ms/step   loss %s" % (pdl, ms, loss), flush=True)
+lib.acnn_set_pdl(0)
+for fused, pix in ((0, 64), (0, 128), (1, 64)):
+    lib.acnn_set_sk_fc_fused(fused)
+    lib.acnn_set_wgrad_pixels(pix)
+    ms, loss = step_ms()
+    print("sk_fc_fused=%d wgrad_pixels=%3d : %.3f ms/step   loss %s" % (fused, pix, ms, loss),
+          flush=True)
+lib.acnn_set_sk_fc_fused(0)
 lib.acnn_set_wgrad_pixels(0)
