@@ -46,7 +46,21 @@ CONFIGS = {
     "baseline_c5_assemble_r152_alpha1_beta2": (dict(resnet_size=152, resnet_version=2, use_sk_block=True,
                                                     anti_alias_type="sconv", anti_alias_filter_size=3,
                                                     bl_alpha=1, bl_beta=2), False, 2, 64),
+    # GeM pooling + embedding head, flatten pooling (nets/resnet_model.py:552-599)
+    "assemble_r50_gem_embedding256": (dict(resnet_size=50, resnet_version=2, use_sk_block=True,
+                                           anti_alias_type="sconv", anti_alias_filter_size=3,
+                                           pool_type="gem", embedding_size=256), False, 4, 64),
+    "r50_rv1_flatten": (dict(resnet_size=50, resnet_version=1, pool_type="flatten"), False, 2, 64),
 }
+# DropBlock through the whole reference model (training mode, keep_prob 0.9, 224 px: the stage-4 map
+# must hold the 7x7 block): the uniform draws come from a seeded generator in CALL ORDER, so the
+# golden logits also pin the order and shapes of the reference's dropblock calls
+DROPBLOCK_CONFIGS = {
+    "assemble_r50_dropblock_kp0.9": (dict(resnet_size=50, resnet_version=2, use_sk_block=True,
+                                          anti_alias_type="sconv", anti_alias_filter_size=3), 2, 224, 0.9),
+    "vanilla_r50_dropblock_kp0.8": (dict(resnet_size=50, resnet_version=1), 2, 224, 0.8),
+}
+DROPBLOCK_SEED = 4242
 BLOCK_SIZES = {1: {50: [3, 4, 6, 3], 101: [3, 4, 23, 3], 152: [3, 8, 36, 3], 200: [3, 24, 36, 3]}}
 
 
@@ -176,6 +190,42 @@ def run_reference(flags, use_resnet_d, batch, size):
     return out, order
 
 
+def run_reference_dropblock(flags, batch, size, keep_prob):
+    sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
+    sys.path.insert(0, "/root/reference")
+    import tensorflow as tf
+    from nets import resnet_model
+    f = dict(flags)
+    rv = f.get("resnet_version", 1)
+    strides = [2, 2, 1, 2] if rv == 2 else [1, 2, 2, 2]
+    size_ = f.pop("resnet_size")
+
+    def make():
+        return resnet_model.Model(resnet_size=size_, bottleneck=True, num_classes=1001, num_filters=64,
+                                  kernel_size=7, conv_stride=2, first_pool_size=3, first_pool_stride=2,
+                                  block_sizes=block_sizes(size_, rv), block_strides=strides, **f)
+    tf.reset()
+    make()(tf.Tensor(seeded_input(batch, 64)), training=False)
+    order = list(tf.variables.order)
+    values = {n: seeded_value(i, n, s) for i, (n, s, _, _) in enumerate(order)}
+    x = seeded_input(batch, size)
+    g = torch.Generator().manual_seed(DROPBLOCK_SEED)
+    shapes = []
+
+    def uniform(shape):
+        shapes.append(list(shape))
+        return torch.rand(shape, generator=g)
+    tf.uniform_fn = uniform
+    try:
+        tf.reset(values)
+        y = make()(tf.Tensor(x), training=True, keep_prob=keep_prob)
+    finally:
+        tf.uniform_fn = None
+    return {"batch": batch, "size": size, "keep_prob": keep_prob, "num_dropblock_calls": len(shapes),
+            "first_shapes": shapes[:5], "last_shape": shapes[-1], "train_logits": digest(y.t),
+            "train_logits_row0_head": [float(v) for v in y.t[0, :8]]}
+
+
 MIXUP_B, MIXUP_HW, MIXUP_NC = 8, 4, 5
 LR_CASES = {   # name -> kwargs of functions/model_fns.py learning_rate_with_decay (+ probe steps)
     "cosine_warmup5_b1024": dict(learning_rate_decay_type="cosine", batch_size=1024, batch_denom=1024,
@@ -214,6 +264,21 @@ def mixup_inputs():
     return x, y, lam1, lam2
 
 
+def teacher_labels():
+    g = torch.Generator().manual_seed(79)
+    return torch.softmax(2 * torch.randn(MIXUP_B, MIXUP_NC, generator=g), dim=1)
+
+
+def feature_map():
+    g = torch.Generator().manual_seed(80)
+    return torch.relu(torch.randn(3, 5, 5, 6, generator=g)) * 2      # post-ReLU: exact zeros get clipped
+
+
+def dropblock_inputs():
+    g = torch.Generator().manual_seed(81)
+    return torch.randn(2, 12, 12, 4, generator=g), torch.rand(1, 6, 6, 4, generator=g)
+
+
 def loss_inputs():
     g = torch.Generator().manual_seed(78)
     logits = torch.randn(6, 11, generator=g) * 3
@@ -250,6 +315,28 @@ def run_train_pieces():
         mx, my, _ = mixup(tf.Tensor(x), tf.Tensor(y), alpha=0.2, keep_batch_size=keep)
         out["mixup_keep_%d" % keep] = {"x": digest(mx.t), "y": digest(my.t), "x_shape": list(mx.t.shape),
                                         "y_rows": my.t.tolist()}
+        # with knowledge-distillation teacher labels (y_t): the third return value
+        tf.beta_samples[:] = [lam1, lam2] if keep else [lam1]
+        yt = teacher_labels()
+        _, _, myt = mixup(tf.Tensor(x), tf.Tensor(y), alpha=0.2, keep_batch_size=keep, y_t=tf.Tensor(yt))
+        out["mixup_teacher_keep_%d" % keep] = {"yt_rows": myt.t.tolist()}
+    # nets/blocks.py:22-42 generalized_mean_pooling and :187-251 dropblock, from the reference source
+    gem, tf = reference_function("nets/blocks.py", "generalized_mean_pooling")
+    xg = feature_map()
+    out["gem"] = {"rows": gem(tf.Tensor(xg), data_format="channels_last").t.reshape(xg.shape[0], -1).tolist()}
+    bern, tf = reference_function("nets/blocks.py", "_bernoulli")
+    dropblock, tf = reference_function("nets/blocks.py", "dropblock")
+    dropblock.__globals__["_bernoulli"] = bern
+    xd, ud = dropblock_inputs()
+    tf.uniform_fn = lambda shape: ud.reshape(shape)
+    try:
+        for kp, gs in ((0.9, 1.0), (0.7, 0.25)):
+            y = dropblock(tf.Tensor(xd), kp, 7, gamma_scale=gs, data_format="channels_last")
+            out["dropblock_kp%g_gs%g" % (kp, gs)] = {
+                "out": digest(y.t), "zero_fraction": float((y.t == 0).float().mean()),
+                "row": y.t[1, 5, :, 2].tolist()}
+    finally:
+        tf.uniform_fn = None
     # losses/cls_losses.py:23-41 get_sup_loss (softmax + label smoothing)
     get_sup_loss, tf = reference_function("losses/cls_losses.py", "get_sup_loss")
     logits, yy = loss_inputs()
@@ -271,5 +358,8 @@ if __name__ == "__main__":
     for name, (flags, d, b, s) in CONFIGS.items():
         gold[name], _ = run_reference(flags, d, b, s)
         print(name, gold[name]["num_variables"], gold[name]["eval_logits"]["abs_sum"])
+    for name, (flags, b, s, kp) in DROPBLOCK_CONFIGS.items():
+        gold[name] = run_reference_dropblock(flags, b, s, kp)
+        print(name, gold[name]["num_dropblock_calls"], gold[name]["train_logits"]["abs_sum"])
     json.dump(gold, open(OUT, "w"), indent=1, sort_keys=True)
     print("wrote", OUT)

@@ -420,8 +420,16 @@ def pad(x, paddings, mode="CONSTANT", name=None):
     return Tensor(torch.nn.functional.pad(t, (0, 0, l0, l1, t0, t1)))
 
 
+uniform_fn = None      # shape -> tensor: the source of tf.random_uniform draws (set by the generator)
+
+
 def random_uniform(shape, minval=0, maxval=1, dtype=float32, seed=None):
-    raise NotImplementedError("DropBlock (keep_prob < 1) is outside the pinned path")
+    """DropBlock's _bernoulli draws (nets/blocks.py:187-188): TF's RNG is not reproducible, so the
+    golden generator installs a seeded source; the oracle test replays the same sequence."""
+    if uniform_fn is None:
+        raise NotImplementedError("tf.random_uniform without an installed uniform_fn")
+    shp = [int(v) for v in (_raw(shape).tolist() if hasattr(_raw(shape), "tolist") else shape)]
+    return Tensor(uniform_fn(tuple(shp)).to(dtype.torch) * (maxval - minval) + minval)
 
 
 class _Logging:

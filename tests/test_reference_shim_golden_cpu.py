@@ -185,3 +185,73 @@ def test_product_plan_inventory_matches_reference_code(name):
     assert hashlib.sha256(tr.encode()).hexdigest() == gold["trainable_sha256"]
     st = "\n".join("%s|%s" % (n, ",".join(map(str, p.tf_shape))) for n, p in plan.state.items())
     assert hashlib.sha256(st.encode()).hexdigest() == gold["state_sha256"]
+
+
+# ---------------------------------------------------------------------------------------------
+# SURVEY 8(f) rows against the reference's own code: DropBlock, GeM pooling, KD teacher mixup
+# (the GeM / embedding / flatten model configurations are part of mg.CONFIGS above)
+# ---------------------------------------------------------------------------------------------
+def test_gem_pooling_matches_reference_code():
+    """nets/blocks.py:22-42 generalized_mean_pooling executed through the stand-in."""
+    from oracle import tf_ops as T
+    got = T.generalized_mean_pooling(mg.feature_map())
+    assert torch.allclose(got, torch.tensor(PIECES["gem"]["rows"]), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("kp,gs", [(0.9, 1.0), (0.7, 0.25)])
+def test_dropblock_function_matches_reference_code(kp, gs):
+    """nets/blocks.py:187-251 dropblock (+ _bernoulli) executed through the stand-in with the same
+    uniform draws."""
+    from oracle import tf_ops as T
+    x, u = mg.dropblock_inputs()
+    y = T.dropblock(x, kp, 7, gs, u)
+    gold = PIECES["dropblock_kp%g_gs%g" % (kp, gs)]
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(mg.digest(y)[k], gold["out"][k], 1e-5)
+    assert abs(float((y == 0).float().mean()) - gold["zero_fraction"]) < 1e-9
+    assert torch.allclose(y[1, 5, :, 2], torch.tensor(gold["row"]), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("keep", [False, True], ids=["mixup_type_1", "mixup_type_2"])
+def test_teacher_label_mixup_matches_reference_code(keep):
+    """utils/data_util.py:128-156: the y_t path, including the type-2 second half that mixes the
+    SUPERVISED labels (`lam2_y * y1`, :154)."""
+    from oracle import tf_ops as T
+    x, y, lam1, lam2 = mg.mixup_inputs()
+    _, _, myt = T.mixup(x, y, lam1, lam2 if keep else None, keep_batch_size=keep,
+                        y_t=mg.teacher_labels())
+    assert torch.allclose(myt, torch.tensor(PIECES["mixup_teacher_keep_%d" % keep]["yt_rows"]),
+                          atol=1e-6)
+
+
+@pytest.mark.parametrize("name", sorted(mg.DROPBLOCK_CONFIGS))
+def test_dropblock_through_the_whole_reference_model(name):
+    """The reference's Model.__call__(training=True, keep_prob=...) at 224 px with the uniform draws
+    replayed from the same seeded generator IN CALL ORDER: pins where the reference calls dropblock
+    (34 calls for Assemble-ResNet-50, 29 for the vanilla net), their mask shapes and the logits."""
+    from oracle import model as M
+    flags, batch, size, kp = mg.DROPBLOCK_CONFIGS[name]
+    gold = GOLD[name]
+    model, vs = M.build(seed=1, input_hw=64, **flags)
+    for i, n in enumerate(list(vs.vars)):
+        vs.vars[n] = mg.seeded_value(i, n, tuple(vs.vars[n].shape))
+    x = mg.seeded_input(batch, size)
+    g = torch.Generator().manual_seed(mg.DROPBLOCK_SEED)
+    shapes = []
+
+    def uniform(shape):
+        shapes.append(list(shape))
+        return torch.rand(shape, generator=g)
+    with torch.no_grad():
+        y = M.forward(model, vs, x, training=True, keep_prob=kp, dropblock_u=uniform)
+    assert len(shapes) == gold["num_dropblock_calls"]
+    assert shapes[:5] == gold["first_shapes"] and shapes[-1] == gold["last_shape"]
+    got = mg.digest(y)
+    assert _close(got["abs_sum"], gold["train_logits"]["abs_sum"], 5e-3), (got, gold["train_logits"])
+    for a, b in zip(y[0, :8].tolist(), gold["train_logits_row0_head"]):
+        assert _close(a, b, 5e-3, 1e-3)
+    # the product's plan draws its masks at the same sites, in the same order, with the same shapes
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    plan = build_plan(ModelConfig(**flags), batch, size, size, training=True, use_dropblock=True)
+    plan_shapes = [[1] + list(plan.tensors[n].shape) for n in plan.meta["dropblock_u"]]
+    assert plan_shapes == shapes
