@@ -30,36 +30,52 @@ __device__ __forceinline__ int reflect(int i, int n) {
 }
 
 // ---------------------------------------------------------------------------- blur-pool
+// Every thread handles kBlurRows consecutive output rows of one (column, channel-group): the loads
+// of all its windows are independent and issued back to back (one row per thread measured 0.33-0.44
+// of the HBM peak forward and 0.07-0.14 backward: too little in flight per short-lived CTA).
+constexpr int kBlurRows = 4;
+
 template <class T>
 __global__ void __launch_bounds__(kPT)
 blurpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, Binomial bw, int H, int W,
                     int C, int filt, int stride, int pad, int Ho, int Wo) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
-  // grid = (ceil(Wo * C/8 / threads), Ho, B): no 64-bit index decomposition per element
+  // grid = (ceil(Wo * C/8 / threads), ceil(Ho / kBlurRows), B): no 64-bit index decomposition
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
   if (idx >= Wo * CG) return;
   const int q = idx / CG;
   const int cg = idx - q * CG;
-  const int p = blockIdx.y;
+  const int p0 = blockIdx.y * kBlurRows;
   const int64_t b = blockIdx.z;
-  {
-    const int64_t i = ((b * Ho + p) * Wo + q) * CG + cg;
-    float acc[8];
+  float acc[kBlurRows][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int r = 0; r < filt; ++r) {
-      const int ih = reflect(p * stride + r - pad, H);
-      for (int s = 0; s < filt; ++s) {
-        const int iw = reflect(q * stride + s - pad, W);
-        float v[8];
-        load8(x + ((b * H + ih) * W + iw) * C + cg * 8, v);
-        const float wt = bw.w[r] * bw.w[s];
+  for (int r = 0; r < kBlurRows; ++r)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
+    for (int k = 0; k < 8; ++k) acc[r][k] = 0.f;
+  for (int s = 0; s < filt; ++s) {
+    const int iw = reflect(q * stride + s - pad, W);
+    for (int t = 0; t < filt; ++t) {
+      V8<T> v[kBlurRows];
+#pragma unroll
+      for (int r = 0; r < kBlurRows; ++r) {
+        const int p = p0 + r < Ho ? p0 + r : Ho - 1;          // clamped: loads stay unconditional
+        const int ih = reflect(p * stride + t - pad, H);
+        v[r].ld(x + ((b * H + ih) * W + iw) * C + cg * 8);
+      }
+      const float wt = bw.w[t] * bw.w[s];
+#pragma unroll
+      for (int r = 0; r < kBlurRows; ++r) {
+        float f[8];
+        v[r].unpack(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[r][k] = fmaf(wt, f[k], acc[r][k]);
       }
     }
-    store8(out + i * 8, acc);
+  }
+#pragma unroll
+  for (int r = 0; r < kBlurRows; ++r) {
+    if (p0 + r < Ho) store8(out + (((b * Ho + p0 + r) * Wo + q) * CG + cg) * 8, acc[r]);
   }
 }
 
@@ -89,16 +105,30 @@ blurpool_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx,
                     Binomial bw, int H, int W, int C, int filt, int stride, int pad, int Ho,
                     int Wo) {
   pdl_wait();   // multi-wave grid: an early trigger would let the next kernel's CTAs take SM slots from this one
-  // grid = (ceil(W * C/8 / threads), H, B)
+  // grid = (ceil(W * C/8 / threads), ceil(H / kBlurRows), B)
   const int CG = C >> 3;
   const int idx = blockIdx.x * kPT + threadIdx.x;
   if (idx >= W * CG) return;
   const int iw = idx / CG;
   const int cg = idx - iw * CG;
-  const int ih = blockIdx.y;
+  const int ih0 = blockIdx.y * kBlurRows;
   const int64_t b = blockIdx.z;
-  {
-    const int64_t i = ((b * H + ih) * W + iw) * CG + cg;
+  // the two full-size streams of all rows first (2 * kBlurRows loads in flight), then the gathers
+  V8<T> addv[kBlurRows], maskv[kBlurRows];
+#pragma unroll
+  for (int r = 0; r < kBlurRows; ++r) {
+    const int ih = ih0 + r < H ? ih0 + r : H - 1;
+    const size_t off = (((size_t)b * H + ih) * W + iw) * C + cg * 8;
+    addv[r].zero();
+    maskv[r].zero();
+    if (add_src) addv[r].ld(add_src + off);
+    if (mask_src) maskv[r].ld(mask_src + off);
+  }
+#pragma unroll
+  for (int r = 0; r < kBlurRows; ++r) {
+    const int ih = ih0 + r;
+    if (ih >= H) break;
+    const size_t off = (((size_t)b * H + ih) * W + iw) * C + cg * 8;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
@@ -111,8 +141,20 @@ blurpool_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx,
         for (int k = 0; k < 8; ++k) acc[k] = fmaf(wt, v[k], acc[k]);
       });
     });
-    grad_epilogue(acc, add_src, mask_src, (size_t)i * 8);
-    store8(dx + i * 8, acc);
+    if (add_src) {
+      float a[8];
+      addv[r].unpack(a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += a[k];
+    }
+    if (mask_src) {
+      float m[8];
+      maskv[r].unpack(m);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (!(m[k] > 0.f)) acc[k] = 0.f;
+    }
+    store8(dx + off, acc);
   }
 }
 
@@ -661,7 +703,7 @@ int acnn_blurpool_fwd(const void* x, void* out, int B, int H, int W, int C, int 
   ACNN_REQUIRE(pad < H && pad < W, "blurpool_fwd: reflect pad %d >= size", pad);
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
   ACNN_REQUIRE(Ho <= 65535 && B <= 65535, "blurpool_fwd: Ho / B exceed the grid limits");
-  dim3 grid(ceil_div(Wo * (C / 8), kPT), Ho, B);
+  dim3 grid(ceil_div(Wo * (C / 8), kPT), ceil_div(Ho, kBlurRows), B);
   ACNN_BY_DTYPE(dtype, launch_k(blurpool_fwd_kernel<T>, grid, dim3(kPT), 0, (cudaStream_t)stream,
                                 (const T*)x, (T*)out, binomial(filt), H, W, C, filt, stride, pad,
                                 Ho, Wo));
@@ -676,7 +718,7 @@ int acnn_blurpool_bwd(const void* dout, void* dx, const void* add_src, const voi
   const int pad = (filt - 1) / 2;
   const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
   ACNN_REQUIRE(H <= 65535 && B <= 65535, "blurpool_bwd: H / B exceed the grid limits");
-  dim3 grid(ceil_div(W * (C / 8), kPT), H, B);
+  dim3 grid(ceil_div(W * (C / 8), kPT), ceil_div(H, kBlurRows), B);
   ACNN_BY_DTYPE(dtype, launch_k(blurpool_bwd_kernel<T>, grid, dim3(kPT), 0, (cudaStream_t)stream,
                                 (const T*)dout, (T*)dx, (const T*)add_src, (const T*)mask_src,
                                 binomial(filt), H, W, C, filt, stride, pad, Ho, Wo));
