@@ -166,24 +166,30 @@ __host__ __device__ constexpr int plane_term_b(int t) { return t == 2 ? 2 : ((t 
 // (x = hi + mid + lo, 24 mantissa bits) whose six significant cross products are accumulated in the
 // same fp32 TMEM accumulator -- the fp32 parity mode (acnn.h ACNN_F32) on the same TMA / im2col /
 // descriptor / epilogue code as the bf16 path.
-static inline int fprop_stage_bytes(int bn, int mt, int np) {
-  return np * (mt * kBM * kStageK * 2 + bn * kStageK * 2);
+static inline int fprop_stage_bytes(int bn, int mt, int np, bool pair = false) {
+  return np * (mt * kBM * kStageK * 2 + (pair ? bn / 2 : bn) * kStageK * 2);
 }
-static inline int fprop_stages(int bn, int mt, int np, bool has_add, bool has_mask, bool out_f32) {
+static inline int fprop_stages(int bn, int mt, int np, bool has_add, bool has_mask, bool out_f32,
+                               bool pair = false) {
   const int half_n = bn > 128 ? 128 : bn;
   const int tile = kBM * half_n * 2;
   const int fixed = 1024 + (out_f32 ? 0 : tile) + (has_add ? tile : 0) + (has_mask ? tile : 0);
-  int st = (kSmemBudget - fixed) / fprop_stage_bytes(bn, mt, np);
+  int st = (kSmemBudget - fixed) / fprop_stage_bytes(bn, mt, np, pair);
   if (st > kMaxStages) st = kMaxStages;
   if (st < 2) st = 2;
   return st;
 }
 
-template <int BN, int MT, int NP = 1>
+// CG2: a CTA PAIR (tcgen05 cta_group::2) computes one 256 x BN tile: each CTA stages its own 128 rows
+// of A and only HALF of the weight tile, the leader issues one M = 256 MMA that reads both halves.
+// Shared-memory ingest per SM per k-block drops from A + B to A + B/2 -- what bounds the N = 256
+// tiles.
+template <int BN, int MT, int NP = 1, bool CG2 = false>
 struct FpropCfg {
   static constexpr int kAHalfBytes = kBM * kStageK * 2;   // 16 KiB per M tile
   static constexpr int kABytes = MT * kAHalfBytes;        // one plane
-  static constexpr int kBBytes = BN * kStageK * 2;        // one plane
+  static constexpr int kBRows = CG2 ? BN / 2 : BN;        // weight rows staged by this CTA
+  static constexpr int kBBytes = kBRows * kStageK * 2;    // one plane
   static constexpr int kStageBytes = NP * (kABytes + kBBytes);
   static_assert(2 * kStageBytes + 1024 <= kSmemBudget, "two pipeline stages must fit");
   // the epilogue handles the accumulator in column halves of <= 128 (one staging buffer each for
@@ -199,9 +205,10 @@ struct FpropCfg {
   static constexpr int kAccCols = (NP == 3 ? 2 : MT) * BN;
   static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // two accumulator stages
   static_assert(2 * kAccCols <= 512 && (NP == 1 || MT == 1), "TMEM holds 512 columns");
+  static_assert(!CG2 || (MT == 1 && NP == 1), "CTA pairs: one M tile per CTA, bf16 operands");
   // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
   static int stages_for(bool has_add, bool has_mask, bool out_f32) {
-    return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32);
+    return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32, CG2);
   }
   static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32) {
     return 1024 + stages * kStageBytes + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
@@ -213,19 +220,19 @@ struct FpropCfg {
 // runs ahead across tiles through the smem ring; the MMA issuer alternates between two TMEM
 // accumulators; the 8 epilogue warps (two per TMEM lane quarter, alternating 32-column chunks)
 // drain accumulator i while the tensor core fills i^1.
-template <int BN, int CW, bool IM2COL, int MT, int NP>
+template <int BN, int CW, bool IM2COL, int MT, int NP, bool CG2>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd,
                  const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmA1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmB2, const ConvGemmParams p) {
-  using Cfg = FpropCfg<BN, MT, NP>;
-  constexpr int kTileM = MT * kBM;              // output pixels per CTA tile
+  using Cfg = FpropCfg<BN, MT, NP, CG2>;
+  constexpr int kTileM = (CG2 ? 2 : MT) * kBM;  // output pixels per CTA tile (per CTA pair with CG2)
   constexpr int kChunks = kStageK / CW;        // A chunks (one filter tap each when Cin < 64)
   constexpr int kChunkBytes = kBM * CW * 2;
   constexpr int kKSteps = CW / 16;             // UMMA K = 16 bf16
-  constexpr uint32_t kIdesc = make_idesc_bf16(BN, false, false);
+  constexpr uint32_t kIdesc = make_idesc_bf16_m(CG2 ? 256 : 128, BN, false, false);
   constexpr int kHalfN = Cfg::kHalfN;
   constexpr int kNHalf = Cfg::kNHalf;
   constexpr int kSubW = Cfg::kSubW;
@@ -251,12 +258,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.Ktot + kStageK - 1) / kStageK;
-  // static tile schedule: this CTA owns N tile n_tile and M tiles m_first, m_first + m_step, ...
-  const int n_tile = blockIdx.x % p.n_tiles;
-  const int m_first = blockIdx.x / p.n_tiles;
-  const int m_step = gridDim.x / p.n_tiles;
+  // static tile schedule: this CTA (CG2: this CTA pair) owns N tile n_tile and M tiles m_first,
+  // m_first + m_step, ...; with CG2 the CTA of rank r in its pair computes rows r*128.. of the tile
+  const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
+  const int unit = CG2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int units = CG2 ? (gridDim.x >> 1) : gridDim.x;
+  const int n_tile = unit % p.n_tiles;
+  const int m_first = unit / p.n_tiles;
+  const int m_step = units / p.n_tiles;
   const int n0 = n_tile * BN;
   const int my_tiles = m_first < p.m_tiles ? (p.m_tiles - m_first + m_step - 1) / m_step : 0;
+  const int m_rank_off = CG2 ? static_cast<int>(cta_rank) * kBM : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -276,14 +288,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 1);
+      mbar_init(&tempty_bar[s], CG2 ? 2 : 1);      // CG2: the epilogues of both CTAs release it
     }
     mbar_init(&aux_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
+  if (warp == 1) {
+    if (CG2) tmem_alloc_pair<Cfg::kTmemCols>(&tmem_base_smem);
+    else tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync();      // the peer's barriers are initialised before any remote arrive
+  else __syncthreads();
   tc_fence_after();
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail of
   // the preceding kernel; its outputs are read only after this point
@@ -304,12 +320,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // The whole warp stays converged (so the uniform-datapath TMA/MMA instructions need no
     // election loops) and every lane tracks the same loop state; one elected lane issues.
     uint32_t soff = 0, sbar = 0, phase = 0;             // stage byte offset / barrier offset
-    const uint32_t b_bytes = BN * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
-    const uint32_t full_bytes = NP * (MT * kChunks * kChunkBytes + b_bytes);
-    const uint32_t tail_bytes = NP * (MT * tail_chunks * kChunkBytes + b_bytes);
+    const uint32_t b_bytes = Cfg::kBRows * (p.b_sw_bytes < 128 ? p.b_sw_bytes : 128);
+    // CG2: both CTAs' loads complete on the LEADER's full barrier (cluster address of rank 0)
+    const uint32_t full_bytes = (CG2 ? 2 : 1) * NP * (MT * kChunks * kChunkBytes + b_bytes);
+    const uint32_t tail_bytes = (CG2 ? 2 : 1) * NP * (MT * tail_chunks * kChunkBytes + b_bytes);
+    const uint32_t full0_lead = CG2 ? mapa_shared(full0, 0) : full0;
+    const int nb0 = n0 + (CG2 ? static_cast<int>(cta_rank) * Cfg::kBRows : 0);
     const int Cin = p.Cin, fkw = p.kw;
     for (int it = 0; it < my_tiles; ++it) {
-      const int m0 = (m_first + it * m_step) * kTileM;
+      const int m0 = (m_first + it * m_step) * kTileM + m_rank_off;
       int img[MT], h0[MT], w0[MT];
 #pragma unroll
       for (int h = 0; h < MT; ++h) {
@@ -331,14 +350,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int nch = (kChunks > 1 && last) ? tail_chunks : kChunks;
         mbar_wait_a(empty0 + sbar, phase ^ 1);
         const bool leader = elect_one();
-        const uint32_t fb = full0 + sbar;
+        const uint32_t fb = CG2 ? full0_lead + sbar : full0 + sbar;
         const uint32_t sa = smem_a0 + soff;
         if (leader) {
-          mbar_expect_tx_a(fb, (kChunks > 1 && last) ? tail_bytes : full_bytes);
+          if (!CG2 || cta_rank == 0)
+            mbar_expect_tx_a(full0 + sbar, (kChunks > 1 && last) ? tail_bytes : full_bytes);
+          if (CG2) {
+            tma_load_2d_pair(sa + Cfg::kABytes, &tmB, fb, k0, nb0);
+          } else {
 #pragma unroll
-          for (int pl = 0; pl < NP; ++pl)
-            tma_load_2d_a(sa + NP * Cfg::kABytes + pl * Cfg::kBBytes,
-                          pl == 0 ? &tmB : (pl == 1 ? &tmB1 : &tmB2), fb, k0, n0);
+            for (int pl = 0; pl < NP; ++pl)
+              tma_load_2d_a(sa + NP * Cfg::kABytes + pl * Cfg::kBBytes,
+                            pl == 0 ? &tmB : (pl == 1 ? &tmB1 : &tmB2), fb, k0, n0);
+          }
         }
 #pragma unroll
         for (int j = 0; j < kChunks; ++j) {
@@ -352,10 +376,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   const uint32_t dst =
                       sa + pl * Cfg::kABytes + h * Cfg::kAHalfBytes + j * kChunkBytes;
                   if (IM2COL) {
-                    tma_load_im2col_4d_a(dst, mA, fb, tc, w0[h], h0[h], img[h], (uint16_t)ts,
-                                         (uint16_t)tr);
+                    if (CG2)
+                      tma_load_im2col_4d_pair(dst, mA, fb, tc, w0[h], h0[h], img[h], (uint16_t)ts,
+                                              (uint16_t)tr);
+                    else
+                      tma_load_im2col_4d_a(dst, mA, fb, tc, w0[h], h0[h], img[h], (uint16_t)ts,
+                                           (uint16_t)tr);
                   } else {
-                    tma_load_2d_a(dst, mA, fb, k0 + j * CW, m0 + h * kBM);
+                    if (CG2) tma_load_2d_pair(dst, mA, fb, k0 + j * CW, m0 + h * kBM);
+                    else tma_load_2d_a(dst, mA, fb, k0 + j * CW, m0 + h * kBM);
                   }
                 }
               }
@@ -383,10 +412,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint64_t a_desc0 = make_smem_desc(smem_a0, 16, 8 * CW * 2, swizzle_layout_type(CW * 2));
     const uint64_t b_desc0 = make_smem_desc(smem_a0 + NP * Cfg::kABytes, 16, 8 * p.b_sw_bytes,
                                             swizzle_layout_type(p.b_sw_bytes));
-    for (int it = 0; it < my_tiles; ++it) {
+    // CG2: only the leader CTA of the pair issues MMAs (they span both CTAs' operands and TMEM)
+    for (int it = 0; it < ((!CG2 || cta_rank == 0) ? my_tiles : 0); ++it) {
       const uint32_t acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);   // epilogue has drained this accumulator
+      mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1);   // epilogue(s) have drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -413,18 +443,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     // NP == 3: t = 5 is hi*hi -> accumulator 0; t < 5 -> the small-term
                     // accumulator at column offset BN (its first MMA of a tile is t = 0)
                     const bool small = NP == 3 && t < 5;
-                    umma_bf16(tmem_d + h * BN + (small ? BN : 0),
-                              da0 + ((pa * Cfg::kABytes + h * Cfg::kAHalfBytes + j * kChunkBytes +
-                                      ks * 32) >> 4),
-                              db0 + ((pb * Cfg::kBBytes + (j * kKSteps + ks) * 32) >> 4), kIdesc,
-                              (j | ks | (small ? t : 0)) ? 1u : static_cast<uint32_t>(kb != 0));
+                    const uint32_t d_col = tmem_d + h * BN + (small ? BN : 0);
+                    const uint64_t da =
+                        da0 + ((pa * Cfg::kABytes + h * Cfg::kAHalfBytes + j * kChunkBytes + ks * 32) >> 4);
+                    const uint64_t db = db0 + ((pb * Cfg::kBBytes + (j * kKSteps + ks) * 32) >> 4);
+                    const uint32_t accum =
+                        (j | ks | (small ? t : 0)) ? 1u : static_cast<uint32_t>(kb != 0);
+                    if (CG2) umma_bf16_pair(d_col, da, db, kIdesc, accum);
+                    else umma_bf16(d_col, da, db, kIdesc, accum);
                   }
                 }
               }
             }
           }
-          umma_commit_a(empty0 + sbar);
-          if (last) umma_commit_a(tfull0 + acc * 8);
+          if (CG2) {      // frees the stage / publishes the accumulator in BOTH CTAs
+            umma_commit_pair(empty0 + sbar);
+            if (last) umma_commit_pair(tfull0 + acc * 8);
+          } else {
+            umma_commit_a(empty0 + sbar);
+            if (last) umma_commit_a(tfull0 + acc * 8);
+          }
         }
         __syncwarp();
         soff16 += Cfg::kStageBytes >> 4;
@@ -462,7 +500,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (it >> 1) & 1;
 #pragma unroll
       for (int mh = 0; mh < MT; ++mh) {
-      const int m0 = (m_first + it * m_step) * kTileM + mh * kBM;
+      const int m0 = (m_first + it * m_step) * kTileM + mh * kBM + m_rank_off;
       const uint32_t acc_col = acc * Cfg::kAccCols + mh * BN;
       const int row = m0 + r;
       const bool row_ok = row < p.M;
@@ -571,7 +609,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!p.out_f32) fence_proxy_async();             // generic smem writes -> async proxy
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (leader) {
-          if (hf == kNHalf - 1 && mh == MT - 1) mbar_arrive(&tempty_bar[acc]);
+          if (hf == kNHalf - 1 && mh == MT - 1) {
+            if (CG2 && cta_rank != 0)     // the leader's MMA warp waits for both CTAs' epilogues
+              mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+            else
+              mbar_arrive(&tempty_bar[acc]);
+          }
           if (!p.out_f32) {
 #pragma unroll
             for (int sub = 0; sub < kNSub; ++sub)
@@ -629,7 +672,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         // one partial row per CTA of this N tile, plain stores: bn_finalize sums the rows in a
         // fixed order (deterministic; no pre-zeroed accumulator)
-        float* row = p.ch_part + static_cast<size_t>(m_first) * 2 * p.Cout;
+        float* row = p.ch_part +
+                     static_cast<size_t>(CG2 ? m_first * 2 + static_cast<int>(cta_rank) : m_first) * 2 *
+                         p.Cout;
         row[n0 + col] = ss;
         row[p.Cout + n0 + col] = qq;
       }
@@ -637,10 +682,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (CG2) cluster_sync();      // neither CTA may leave (or free TMEM) while the pair is in flight
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    if (CG2) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+    else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
@@ -903,12 +950,12 @@ struct ConvMaps {
   CUtensorMap a[3], b[3], c, add, mask;
 };
 
-template <int BN, int CW, bool IM2COL, int MT, int NP>
+template <int BN, int CW, bool IM2COL, int MT, int NP, bool CG2 = false>
 static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per_n,
                             cudaStream_t stream) {
-  using Cfg = FpropCfg<BN, MT, NP>;
+  using Cfg = FpropCfg<BN, MT, NP, CG2>;
   static bool attr_set = false;
-  auto kern = conv_gemm_kernel<BN, CW, IM2COL, MT, NP>;
+  auto kern = conv_gemm_kernel<BN, CW, IM2COL, MT, NP, CG2>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kSmemBudget + 2048);
@@ -920,12 +967,29 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per
   }
   ConvGemmParams q = p;
   q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32);
-  q.m_tiles = ceil_div(p.M, MT * kBM);
+  q.m_tiles = ceil_div(p.M, (CG2 ? 2 : MT) * kBM);
   q.n_tiles = p.Cout / BN;
-  const int grid = per_n * q.n_tiles;
-  launch_k(kern, dim3(grid), dim3(kConvThreads),
-           Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32), stream, tm.a[0], tm.b[0],
-           tm.c, tm.add, tm.mask, tm.a[1], tm.a[2], tm.b[1], tm.b[2], q);
+  const int smem = Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32);
+  if (CG2) {
+    // per_n CTA PAIRS per N tile, launched as clusters of two (ranks 2i, 2i+1 share a TPC)
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * per_n * q.n_tiles);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    (void)cudaLaunchKernelEx(&cfg, kern, tm.a[0], tm.b[0], tm.c, tm.add, tm.mask, tm.a[1], tm.a[2],
+                             tm.b[1], tm.b[2], q);
+  } else {
+    launch_k(kern, dim3(per_n * q.n_tiles), dim3(kConvThreads), smem, stream, tm.a[0], tm.b[0], tm.c,
+             tm.add, tm.mask, tm.a[1], tm.a[2], tm.b[1], tm.b[2], q);
+  }
   count_launch();
   return check_launch("conv_gemm_kernel");
 }
@@ -938,8 +1002,13 @@ static int g_conv_mtiles_mode = -1;
 struct ConvTiling {
   int bn;      // N tile
   int mt;      // M tiles (128 pixels) per CTA tile
-  int per_n;   // CTAs per N tile = rows of the partial statistics buffer
+  int per_n;   // CTAs (pair = 1: CTA pairs) per N tile
+  int pair;    // 1: CTA pairs (tcgen05 cta_group::2), one 256 x bn tile per pair
+  int parts;   // rows of the partial statistics buffer (= CTAs per N tile)
 };
+
+// 0 (default): off; 1: N = 256 tiles run on CTA pairs (acnn_set_conv_cta_pairs)
+static int g_conv_pairs = 0;
 
 static ConvTiling conv_tiling(int M, int Cout, bool has_add, bool has_mask, bool out_f32, int np) {
   ConvTiling t;
@@ -962,10 +1031,13 @@ static ConvTiling conv_tiling(int M, int Cout, bool has_add, bool has_mask, bool
   // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
   // its per-channel statistics), at most one CTA per SM
   const int n_tiles = Cout / t.bn;
-  const int m_tiles = ceil_div(M, t.mt * kBM);
-  t.per_n = num_sms() / n_tiles;
+  t.pair = (g_conv_pairs && t.bn == 256 && np == 1 && t.mt == 1 &&
+            ceil_div(M, 2 * kBM) * n_tiles >= num_sms() / 2) ? 1 : 0;
+  const int m_tiles = ceil_div(M, (t.pair ? 2 : t.mt) * kBM);
+  t.per_n = (t.pair ? num_sms() / 2 : num_sms()) / n_tiles;
   if (t.per_n < 1) t.per_n = 1;
   if (t.per_n > m_tiles) t.per_n = m_tiles;
+  t.parts = t.pair ? 2 * t.per_n : t.per_n;
   return t;
 }
 
@@ -985,6 +1057,12 @@ static int dispatch_conv_cw(int cw, bool im2col, const ConvMaps& tm, const ConvG
 template <int BN>
 static int dispatch_conv_gemm(const ConvTiling& t, int np, int cw, bool im2col, const ConvMaps& tm,
                               const ConvGemmParams& p, cudaStream_t s) {
+  if constexpr (BN == 256) {
+    if (t.pair) {     // full-width (64-channel) chunks only: bounds the instantiation count
+      if (im2col) return launch_conv_gemm<256, 64, true, 1, 1, true>(tm, p, t.per_n, s);
+      return launch_conv_gemm<256, 64, false, 1, 1, true>(tm, p, t.per_n, s);
+    }
+  }
   if constexpr (BN <= 128) {
     if (np == 3) return dispatch_conv_cw<BN, 1, 3>(cw, im2col, tm, p, t.per_n, s);
     if (t.mt == 2) return dispatch_conv_cw<BN, 2, 1>(cw, im2col, tm, p, t.per_n, s);
@@ -1055,7 +1133,13 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   ACNN_REQUIRE(p.b_sw_bytes == 128 || p.b_sw_bytes == 64 || p.b_sw_bytes == 32,
                "conv: unsupported K=%d", p.Ktot);
 
-  const ConvTiling t = conv_tiling(p.M, g.Cout, p.has_add, p.has_mask, out_f32 != 0, np);
+  ConvTiling t = conv_tiling(p.M, g.Cout, p.has_add, p.has_mask, out_f32 != 0, np);
+  if (t.pair && cw != 64) {       // pairs are instantiated for 64-channel chunks only
+    const int keep = g_conv_pairs;
+    g_conv_pairs = 0;
+    t = conv_tiling(p.M, g.Cout, p.has_add, p.has_mask, out_f32 != 0, np);
+    g_conv_pairs = keep;
+  }
   const int bn = t.bn;
   ConvMaps tm;
   const int64_t x_plane = input_elems(g);
@@ -1068,7 +1152,8 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
       rc = make_map_im2col(&tm.a[pl], xp, g, cw, kBM);
     }
     if (rc) return rc;
-    rc = make_map_2d(&tm.b[pl], wp, g.Cout, p.Ktot, p.Ktot, bn, p.Ktot >= 64 ? 64 : p.Ktot);
+    rc = make_map_2d(&tm.b[pl], wp, g.Cout, p.Ktot, p.Ktot, t.pair ? bn / 2 : bn,
+                     p.Ktot >= 64 ? 64 : p.Ktot);
     if (rc) return rc;
   }
   for (int pl = np; pl < 3; ++pl) {   // placeholders
@@ -1262,7 +1347,20 @@ int acnn_conv_stats_parts(const acnn_conv_geom* g) {
   if (!g) return 0;
   int Ho, Wo;
   if (!acnn::out_hw(*g, &Ho, &Wo) || g->Cout % 32 != 0) return 0;
-  return acnn::conv_tiling(g->B * Ho * Wo, g->Cout, false, false, false, 1).per_n;
+  acnn::ConvTiling t = acnn::conv_tiling(g->B * Ho * Wo, g->Cout, false, false, false, 1);
+  if (t.pair && g->Cin % 64 != 0) {
+    const int keep = acnn::g_conv_pairs;
+    acnn::g_conv_pairs = 0;
+    t = acnn::conv_tiling(g->B * Ho * Wo, g->Cout, false, false, false, 1);
+    acnn::g_conv_pairs = keep;
+  }
+  return t.parts;
+}
+
+int acnn_set_conv_cta_pairs(int on) {
+  const int prev = acnn::g_conv_pairs;
+  acnn::g_conv_pairs = on ? 1 : 0;
+  return prev;
 }
 
 int acnn_conv_fprop(const acnn_conv_geom* g, const void* x, const void* w, void* y,

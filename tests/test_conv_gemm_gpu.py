@@ -316,3 +316,62 @@ def test_fp32_mode_fprop_dgrad_wgrad(lib, case):
                                        1, wdg[0].numel(), st), "conv_dgrad fp32")
         torch.cuda.synchronize()
         assert _relerr(dx.cpu(), dx_ref) < F32MODE_TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# CTA pairs (tcgen05 cta_group::2) for the N = 256 tiles: acnn_set_conv_cta_pairs(1)
+# ---------------------------------------------------------------------------------------------
+@contextlib.contextmanager
+def _pairs(lib, on):
+    prev = lib.acnn_set_conv_cta_pairs(on)
+    try:
+        yield
+    finally:
+        lib.acnn_set_conv_cta_pairs(prev)
+
+
+PAIR_CASES = [
+    # B, H, W, Cin, Cout, k   (M / 256 * Cout / 256 >= 74 pair tiles, 64-channel chunks)
+    (64, 28, 28, 64, 256, 1),       # 1x1, one k-block, 196 pair tiles
+    (16, 28, 28, 256, 512, 1),      # 1x1, K = 256, two N tiles
+    (37, 14, 14, 128, 256, 3),      # 3x3 im2col, ragged M (7252 = 28.3 pair tiles... x1 -> below 74: single-CTA path)
+    (64, 14, 14, 128, 512, 3),      # 3x3 im2col, 49 pair tiles x 2 N tiles
+    (50, 20, 20, 64, 256, 3),       # ragged: M = 20000 (78.1 pair tiles), tiles cross image borders
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=[str(c) for c in PAIR_CASES])
+def test_cta_pair_fprop_dgrad_match_single_cta_and_oracle(lib, case):
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout, k = case
+    g = _geom(B, H, W, Cin, Cout, k, 1)
+    x = _rand_bf16(B, H, W, Cin, seed=21)
+    w_hwio = _rand_bf16(k, k, Cin, Cout, seed=22, scale=(k * k * Cin) ** -0.5)
+    add = _rand_bf16(B, H, W, Cout, seed=23)
+    mask = _rand_bf16(B, H, W, Cout, seed=24)
+    st = torch.cuda.current_stream().cuda_stream
+    xd = x.bfloat16().cuda()
+    wd = w_hwio.permute(3, 0, 1, 2).contiguous().bfloat16().cuda()
+    addd, maskd = add.bfloat16().cuda(), mask.bfloat16().cuda()
+    outs = {}
+    for on in (0, 1):
+        with _pairs(lib, on):
+            parts = lib.acnn_conv_stats_parts(g)
+            sp = torch.full((parts, 2, Cout), float("nan"), device="cuda")
+            y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            y2 = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), y.data_ptr(),
+                                           sp.data_ptr(), None, None, None, 0, 0, 0, st), "fprop")
+            _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), y2.data_ptr(), None,
+                                           addd.data_ptr(), maskd.data_ptr(), None, 0, 0, 0, st))
+            torch.cuda.synchronize()
+            outs[on] = (y.float().cpu(), y2.float().cpu(), sp.double().sum(0).cpu(), parts)
+    # identical math, identical k order within a tile: the pair path reproduces the single-CTA path
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert _relerr(outs[1][2], outs[0][2]) < 1e-5
+    # and a sampled check against the oracle (first and last image)
+    for b in (0, B - 1):
+        ref = _ref_conv(x[b:b + 1], w_hwio, g)
+        assert _relerr(outs[1][0][b:b + 1], ref) < BF16_TOL
+        want = (ref + add[b:b + 1]) * (mask[b:b + 1] > 0)
+        assert _relerr(outs[1][1][b:b + 1], want) < BF16_TOL
