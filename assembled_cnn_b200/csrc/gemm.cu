@@ -1007,10 +1007,16 @@ struct ConvTiling {
   int parts;   // rows of the partial statistics buffer (= CTAs per N tile)
 };
 
-// 0 (default): off; 1: N = 256 tiles run on CTA pairs (acnn_set_conv_cta_pairs)
-static int g_conv_pairs = 0;
+// 1 (default): N = 256 tiles with K >= 512 run on CTA pairs; 0: off (acnn_set_conv_cta_pairs;
+// ACNN_CONV_PAIRS=0|1 sets the initial value)
+static int conv_pairs_default() {
+  const char* e = getenv("ACNN_CONV_PAIRS");
+  return e ? (e[0] == '1') : 1;
+}
+static int g_conv_pairs = conv_pairs_default();
 
-static ConvTiling conv_tiling(int M, int Cout, bool has_add, bool has_mask, bool out_f32, int np) {
+static ConvTiling conv_tiling(int M, int Cout, int Ktot, int cw, bool has_add, bool has_mask,
+                              bool out_f32, int np) {
   ConvTiling t;
   // N tile: 256 halves the A-operand traffic per FLOP (128 B/clk of smem reads at BN=128 is the
   // SM's whole shared-memory bandwidth); dense / tiny-M problems keep 128 for more CTAs
@@ -1031,7 +1037,10 @@ static ConvTiling conv_tiling(int M, int Cout, bool has_add, bool has_mask, bool
   // persistent grid: a multiple of n_tiles so that every CTA keeps one N tile (its weights and
   // its per-channel statistics), at most one CTA per SM
   const int n_tiles = Cout / t.bn;
-  t.pair = (g_conv_pairs && t.bn == 256 && np == 1 && t.mt == 1 &&
+  // CTA pairs: measured per layer (profiles/r02_exp_cta_pairs.txt) -- K >= 512 gains 15-25 % (the
+  // k-loop is shared-memory-ingest bound), small K loses 10-20 % (epilogue-bound tiles, and a pair
+  // schedules half as many, twice as large units); 64-channel chunks only (instantiation count)
+  t.pair = (g_conv_pairs && t.bn == 256 && np == 1 && t.mt == 1 && cw == 64 && Ktot >= 512 &&
             ceil_div(M, 2 * kBM) * n_tiles >= num_sms() / 2) ? 1 : 0;
   const int m_tiles = ceil_div(M, (t.pair ? 2 : t.mt) * kBM);
   t.per_n = (t.pair ? num_sms() / 2 : num_sms()) / n_tiles;
@@ -1133,13 +1142,8 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
   ACNN_REQUIRE(p.b_sw_bytes == 128 || p.b_sw_bytes == 64 || p.b_sw_bytes == 32,
                "conv: unsupported K=%d", p.Ktot);
 
-  ConvTiling t = conv_tiling(p.M, g.Cout, p.has_add, p.has_mask, out_f32 != 0, np);
-  if (t.pair && cw != 64) {       // pairs are instantiated for 64-channel chunks only
-    const int keep = g_conv_pairs;
-    g_conv_pairs = 0;
-    t = conv_tiling(p.M, g.Cout, p.has_add, p.has_mask, out_f32 != 0, np);
-    g_conv_pairs = keep;
-  }
+  const ConvTiling t =
+      conv_tiling(p.M, g.Cout, p.Ktot, cw, p.has_add, p.has_mask, out_f32 != 0, np);
   const int bn = t.bn;
   ConvMaps tm;
   const int64_t x_plane = input_elems(g);
@@ -1347,14 +1351,8 @@ int acnn_conv_stats_parts(const acnn_conv_geom* g) {
   if (!g) return 0;
   int Ho, Wo;
   if (!acnn::out_hw(*g, &Ho, &Wo) || g->Cout % 32 != 0) return 0;
-  acnn::ConvTiling t = acnn::conv_tiling(g->B * Ho * Wo, g->Cout, false, false, false, 1);
-  if (t.pair && g->Cin % 64 != 0) {
-    const int keep = acnn::g_conv_pairs;
-    acnn::g_conv_pairs = 0;
-    t = acnn::conv_tiling(g->B * Ho * Wo, g->Cout, false, false, false, 1);
-    acnn::g_conv_pairs = keep;
-  }
-  return t.parts;
+  return acnn::conv_tiling(g->B * Ho * Wo, g->Cout, g->kh * g->kw * g->Cin,
+                           acnn::chunk_width(g->Cin), false, false, false, 1).parts;
 }
 
 int acnn_set_conv_cta_pairs(int on) {

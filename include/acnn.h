@@ -49,9 +49,9 @@ int acnn_set_pdl(int on);
  * per CTA tile.  -1 = choose per problem (default), 1 = always one, 2 = two wherever the shape
  * allows it (N tile <= 128).  Returns the previous mode. */
 int acnn_set_conv_mtiles(int mode);
-/* 1: the N = 256 conv tiles run on CTA pairs (tcgen05 cta_group::2: a cluster of two CTAs computes one
- * 256 x 256 tile, each staging half of the weight tile); 0: single-CTA tiles.  No effect on results
- * beyond fp32 summation order; changes acnn_conv_stats_parts().  Returns the previous setting. */
+/* 1 (default): the N = 256 conv tiles with K >= 512 run on CTA pairs (tcgen05 cta_group::2: a cluster
+ * of two CTAs computes one 256 x 256 tile, each staging half of the weight tile); 0: single-CTA tiles.
+ * Results are bit-identical; changes acnn_conv_stats_parts().  Returns the previous setting. */
 int acnn_set_conv_cta_pairs(int on);
 /* Tuning knob of the wgrad launcher (no effect on results beyond fp32 summation order): pixels
  * (GEMM K) per pipeline stage, 64 or 128 (N tile <= 128 only); 0 = choose per problem (default).
