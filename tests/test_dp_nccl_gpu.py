@@ -55,18 +55,33 @@ def _worker(rank, port, out_path, use_graph):
     assert tr.world == WORLD and tr.local_batch == B_LOCAL and len(tr._buckets) >= 4
     x, lab = _data()
     sl = slice(rank * B_LOCAL, (rank + 1) * B_LOCAL)
+    rt = tr.rt
+    backup = (rt.params.clone(), rt.state.clone(), rt.momentum.clone())
     loss = tr.train_step(x[sl], lab[sl]).tolist()
     torch.cuda.synchronize()
     w = model.get_weights()
     # every replica holds the same variables after the step
-    flat = torch.cat([tr.rt.params, tr.rt.state])
+    flat = torch.cat([rt.params, rt.state])
     other = flat.clone()
     dist.broadcast(other, src=0)
     same = bool(torch.equal(flat, other))
+    # STRICT check of the bucketed, overlapped all-reduce (no ReLU-flip noise involved): the gradient
+    # buffer the SGD step consumed must be bit-for-bit g_0 + g_1 of the replicas' local gradients
+    # (fp32 mode is deterministic, and a two-term fp32 sum has one rounding whatever the order).
+    reduced = rt.grads.clone()
+    for buf, b in zip((rt.params, rt.state, rt.momentum), backup):
+        buf.copy_(b)
+    rt.run_forward()                       # inputs / labels / hyper-parameters are still staged
+    rt.run(rt.plan.backward)
+    torch.cuda.synchronize()
+    local = [torch.empty_like(rt.grads) for _ in range(WORLD)]
+    dist.all_gather(local, rt.grads)
+    strict = bool(torch.equal(reduced, local[0] + local[1]))
+    assert float(reduced.abs().max()) > 0
     if rank == 0:
-        torch.save({"w": w, "loss": loss, "same": same}, out_path)
+        torch.save({"w": w, "loss": loss, "same": same, "strict": strict}, out_path)
     else:
-        assert same
+        assert same and strict
     dist.barrier()
     dist.destroy_process_group()
 
@@ -78,27 +93,38 @@ def test_two_gpu_trainer_matches_oracle_mirrored_strategy(tmp_path, use_graph):
     out = str(tmp_path / "dp.pt")
     mp.spawn(_worker, args=(_free_port(), out, use_graph), nprocs=WORLD, join=True)
     got = torch.load(out)
-    assert got["same"]
+    assert got["same"] and got["strict"]
     from oracle import model as M
-    model, vs = M.build(seed=42, dtype=torch.float32, input_hw=64, **KW)
-    for n in vs.vars:
-        vs.vars[n] = vs.vars[n].double()
-    vs.dtype = torch.float64
     x, lab = _data()
-    onehot = torch.nn.functional.one_hot(lab.long(), 1001).double()
-    mom = {n: torch.zeros_like(v) for n, v in vs.vars.items() if vs.trainable[n]}
-    before = {n: v.clone() for n, v in vs.vars.items()}
-    out_o = M.train_step(model, vs, mom, x.double(), onehot, lr=0.05, momentum=0.9,
-                         label_smoothing=0.1, weight_decay=1e-4, n_replicas=WORLD)
+
+    def oracle(dt):
+        model, vs = M.build(seed=42, dtype=torch.float32, input_hw=64, **KW)
+        for n in vs.vars:
+            vs.vars[n] = vs.vars[n].to(dt)
+        vs.dtype = dt
+        onehot = torch.nn.functional.one_hot(lab.long(), 1001).to(dt)
+        mom = {n: torch.zeros_like(v) for n, v in vs.vars.items() if vs.trainable[n]}
+        before = {n: v.clone() for n, v in vs.vars.items()}
+        M.train_step(model, vs, mom, x.to(dt), onehot, lr=0.05, momentum=0.9, label_smoothing=0.1,
+                     weight_decay=1e-4, n_replicas=WORLD)
+        return vs, before
+
+    vs, before = oracle(torch.float64)
+    vs32, _ = oracle(torch.float32)
     nrel = lambda a, b: ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
     # moving statistics: the MEAN over the replicas' updates (forward quantities: tight)
     worst_state = max(nrel(got["w"][n], vs.vars[n]) for n in vs.vars if not vs.trainable[n])
-    # weights: w - lr * (mean gradient + wd w); gradients carry the ReLU-flip noise of any fp32
-    # implementation (tests/test_parity_fp32_gpu.py), so compare the UPDATE direction loosely and
-    # the large tensors tightly
-    worst_w = max(nrel(got["w"][n], vs.vars[n]) for n in vs.vars if vs.trainable[n]
-                  and before[n].abs().max() > 0)
-    print("2-GPU DP vs oracle(n_replicas=2): moving stats worst %.2e, weights worst %.2e, "
-          "rank-0 CE %.5f" % (worst_state, worst_w, got["loss"][0]))
+    # weights after w - lr * (mean gradient + wd w): gradients of a ReLU network carry the mask-flip
+    # noise of ANY fp32 evaluation (tests/test_parity_fp32_gpu.py), so the yardstick is the oracle's
+    # own fp32-vs-fp64 difference on the same step
+    worst = (0.0, 0.0, "")
+    for n in vs.vars:
+        if vs.trainable[n] and before[n].abs().max() > 0:
+            err, yard = nrel(got["w"][n], vs.vars[n]), nrel(vs32.vars[n], vs.vars[n])
+            assert err <= max(1e-3, 4 * yard), (n, err, yard)
+            if err > worst[0]:
+                worst = (err, yard, n)
+    print("2-GPU DP vs oracle(n_replicas=2): moving stats worst %.2e, weights worst %.2e "
+          "(oracle fp32-vs-fp64 on it %.2e, %s), rank-0 CE %.5f; reduced == g0 + g1 bitwise"
+          % (worst_state, worst[0], worst[1], worst[2], got["loss"][0]))
     assert worst_state < 1e-3
-    assert worst_w < 1e-3
