@@ -1179,6 +1179,11 @@ struct WgradMaps {
   CUtensorMap x[3], dy[3];
 };
 
+// fixed cost of one wgrad CTA (pipeline fill + atomic epilogue) in units of pipeline stages, for
+// the split-K cost model (default 16: measured, profiles/r02_exp_wgrad_split.txt: -0.5 ms per c3 step
+// against 0 = the round-1 "two waves of CTAs" rule; flat from 4 to 1000); acnn_set_wgrad_overhead_stages
+static int g_wgrad_overhead_stages = 16;
+
 template <int BN, int CW, int CWB, bool IM2COL, int MT, int NP, int PIX = kWgPix>
 static int launch_wgrad(const WgradMaps& tm, WgradParams p, int n_tiles, int deterministic,
                         cudaStream_t stream) {
@@ -1195,12 +1200,32 @@ static int launch_wgrad(const WgradMaps& tm, WgradParams p, int n_tiles, int det
     }
     attr_set = true;
   }
-  // split the pixel (K) range so that roughly two waves of CTAs cover the GPU; deterministic mode:
-  // no split -- every dw element receives exactly one (atomic) add onto the zeroed buffer
+  // split the pixel (K) range over CTAs; deterministic mode: no split -- every dw element receives
+  // exactly one (atomic) add onto the zeroed buffer
   const int ctas_per_sm = Cfg::kSmemBytes <= 110 * 1024 ? 2 : 1;
   const int tiles = m_tiles * n_tiles;
-  int splits = ceil_div(2 * ctas_per_sm * num_sms(), tiles);
   const int max_splits = p.stages_total >= 8 ? p.stages_total / 4 : 1;
+  int splits;
+  if (g_wgrad_overhead_stages <= 0) {
+    // (round-1 rule: roughly two waves of CTAs)
+    splits = ceil_div(2 * ctas_per_sm * num_sms(), tiles);
+  } else {
+    // cost model: an SM runs its CTAs' pipeline stages back to back (co-resident CTAs share the
+    // tensor pipe) and pays a fixed pipeline-fill + epilogue cost, worth g_wgrad_overhead_stages
+    // stages, once per round of resident CTAs; pick the split count with the least modelled time
+    // (avoids e.g. 2.2 waves of CTAs where 0.97 waves do the same work in less time)
+    splits = 1;
+    int64_t best = -1;
+    for (int s = 1; s <= max_splits; ++s) {
+      const int per = ceil_div(p.stages_total, s);
+      const int s_eff = ceil_div(p.stages_total, per);
+      if (s_eff != s) continue;
+      const int per_sm = ceil_div(tiles * s, num_sms());
+      const int64_t t = (int64_t)per_sm * per +
+                        (int64_t)ceil_div(per_sm, ctas_per_sm) * g_wgrad_overhead_stages;
+      if (best < 0 || t < best) { best = t; splits = s; }
+    }
+  }
   if (splits > max_splits) splits = max_splits;
   if (splits < 1 || deterministic) splits = 1;
   p.stages_per_split = ceil_div(p.stages_total, splits);
@@ -1338,6 +1363,12 @@ extern "C" {
 int acnn_set_conv_mtiles(int mode) {
   const int prev = acnn::g_conv_mtiles_mode;
   acnn::g_conv_mtiles_mode = (mode == 1 || mode == 2) ? mode : -1;
+  return prev;
+}
+
+int acnn_set_wgrad_overhead_stages(int stages) {
+  const int prev = acnn::g_wgrad_overhead_stages;
+  acnn::g_wgrad_overhead_stages = stages < 0 ? 0 : stages;
   return prev;
 }
 

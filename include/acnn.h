@@ -57,6 +57,11 @@ int acnn_set_conv_cta_pairs(int on);
  * (GEMM K) per pipeline stage, 64 or 128 (N tile <= 128 only); 0 = choose per problem (default).
  * Returns the previous setting. */
 int acnn_set_wgrad_pixels(int pix);
+/* Tuning knob of the wgrad launcher's split-K choice (no effect on results beyond fp32 summation
+ * order): the fixed cost of one CTA (pipeline fill + atomic epilogue) in pipeline stages used by the
+ * cost model that picks the number of pixel splits (default 16); 0 = the round-1 "two waves of CTAs"
+ * rule.  Returns the previous setting. */
+int acnn_set_wgrad_overhead_stages(int stages);
 /* SK attention chains (acnn_sk_fc_fwd / acnn_sk_fc_bwd): 0 (default) = the multi-launch split-K
  * path; 1 = one fused launch per direction on a thread-block cluster of 8 CTAs (no split-K:
  * deterministic; measured 5x slower per block, so not the default).  Same results up to fp32
