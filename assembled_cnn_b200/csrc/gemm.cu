@@ -494,6 +494,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc_s[hf][e] = acc_q[hf][e] = 0.f;
     uint32_t aux_n = 0;                                // completed aux-barrier phases
+    // add / mask half tiles are fetched ONE HALF AHEAD: the loads of the next half are issued as
+    // soon as every thread has consumed the current one (they then overlap this half's TMA store,
+    // the statistics pass and the next half's TMEM reads instead of stalling all 8 warps for an
+    // L2 / HBM round trip per half -- what bounded the small-K dgrad layers)
+    auto issue_aux = [&](int am0, int anh) {
+      mbar_expect_tx(&aux_bar, (p.has_add ? Cfg::kTileBytes : 0) +
+                                   (p.has_mask ? Cfg::kTileBytes : 0));
+#pragma unroll
+      for (int sub = 0; sub < kNSub; ++sub) {
+        if (p.has_add)
+          tma_load_2d(s_add + sub * kSubBytes, &tmAdd, &aux_bar, anh + sub * kSubW, am0);
+        if (p.has_mask)
+          tma_load_2d(s_mask + sub * kSubBytes, &tmMask, &aux_bar, anh + sub * kSubW, am0);
+      }
+    };
+    if (leader && has_aux && my_tiles > 0) issue_aux(m_first * kTileM + m_rank_off, n0);
 
     for (int it = 0; it < my_tiles; ++it) {
       const int acc = it & 1;
@@ -510,17 +526,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (leader) {
           // the previous TMA store must have finished READING the staging buffer
           if (!p.out_f32) tma_store_wait_read();
-          if (has_aux) {
-            mbar_expect_tx(&aux_bar, (p.has_add ? Cfg::kTileBytes : 0) +
-                                         (p.has_mask ? Cfg::kTileBytes : 0));
-#pragma unroll
-            for (int sub = 0; sub < kNSub; ++sub) {
-              if (p.has_add)
-                tma_load_2d(s_add + sub * kSubBytes, &tmAdd, &aux_bar, nh + sub * kSubW, m0);
-              if (p.has_mask)
-                tma_load_2d(s_mask + sub * kSubBytes, &tmMask, &aux_bar, nh + sub * kSubW, m0);
-            }
-          }
         }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");   // staging buffers free for everyone
         if (hf == 0 && mh == 0) {
@@ -620,6 +625,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int sub = 0; sub < kNSub; ++sub)
               tma_store_2d(&tmC, s_out + sub * kSubBytes, nh + sub * kSubW, m0);
             tma_store_commit();
+          }
+          if (has_aux) {
+            // the staging tiles were consumed by everyone before the barrier above: fetch the next
+            // half's (same rows / next column half, else the next M tile of this CTA)
+            if (hf + 1 < kNHalf) issue_aux(m0, nh + kHalfN);
+            else if (mh + 1 < MT) issue_aux(m0 + kBM, n0);
+            else if (it + 1 < my_tiles)
+              issue_aux((m_first + (it + 1) * m_step) * kTileM + m_rank_off, n0);
           }
         }
         if (stats && st_on) {
