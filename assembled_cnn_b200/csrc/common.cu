@@ -24,6 +24,7 @@ static int pdl_default() {
   return (e && (e[0] == '1' || e[0] == '2')) ? e[0] - '0' : 0;
 }
 int g_use_pdl = pdl_default();
+int g_stream_grid_cap = 148 * 16;   // vec.cuh grid_for(); acnn_set_stream_grid_cap
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -45,6 +46,11 @@ int acnn_version(void) { return 100; }
 int acnn_set_pdl(int on) {
   const int prev = acnn::g_use_pdl;
   acnn::g_use_pdl = (on == 1 || on == 2) ? on : 0;
+  return prev;
+}
+int acnn_set_stream_grid_cap(int blocks) {
+  const int prev = acnn::g_stream_grid_cap;
+  acnn::g_stream_grid_cap = blocks >= 148 ? blocks : 148 * 16;
   return prev;
 }
 int64_t acnn_launch_count(void) { return acnn::g_launches.load(std::memory_order_relaxed); }

@@ -130,7 +130,11 @@ __device__ __forceinline__ void grad_epilogue(float (&v)[8], const T* add_src,
   }
 }
 
-inline int grid_for(int64_t work_items, int threads = 256, int max_blocks = 148 * 16) {
+// cap of the grid-stride elementwise kernels' grids (acnn_set_stream_grid_cap; common.cu)
+extern int g_stream_grid_cap;
+
+inline int grid_for(int64_t work_items, int threads = 256, int max_blocks = -1) {
+  if (max_blocks < 0) max_blocks = g_stream_grid_cap;
   int64_t b = (work_items + threads - 1) / threads;
   if (b > max_blocks) b = max_blocks;
   if (b < 1) b = 1;

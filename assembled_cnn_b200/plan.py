@@ -25,6 +25,22 @@ BLOCK_SIZES = {   # functions/model_fns.py:113-127
     2: {50: [3, 4, 6, 3], 101: [4, 8, 18, 3], 152: [5, 12, 30, 3]},
 }
 ALIGN = 256   # every tensor of a flat buffer starts at a multiple of 256 elements
+def _sk_job_floats(M, N, K, share):
+    tiles = -(-M // 64) * -(-N // 64)
+    s = max(1, min(share // tiles, K // 32, 8))
+    kper = -(-(-(-K // s)) // 16) * 16
+    return -(-K // kper) * M * N
+
+
+def sk_fc_scratch_floats(B, f, d, G=148):
+    """Mirror of acnn_sk_fc_scratch_floats (csrc/small_fc.cu; tests/test_abi_cpu.py compares them):
+    da [B,2f] + dz [B,d] + the K-split partial tiles of the widest phase of the fused SK chains."""
+    fwd = max(_sk_job_floats(B, d, f, G), _sk_job_floats(B, 2 * f, d, G))
+    bwd = max(_sk_job_floats(2 * f, d, B, G // 2) + _sk_job_floats(B, d, 2 * f, G // 2),
+              _sk_job_floats(d, f, B, G // 2) + _sk_job_floats(B, f, d, G // 2))
+    return B * (2 * f + d) + max(fwd, bwd)
+
+
 # capacities (rows) of the per-CTA partial-sum buffers the reductions write (include/acnn.h:
 # acnn_conv_stats_parts / acnn_bn_bwd_reduce_parts / acnn_sk_bn_bwd_reduce_parts give the real counts)
 STATS_PARTS_CAP = 148
@@ -586,7 +602,7 @@ class PlanBuilder:
         zpre = self.slot("work", B * d)
         z = self.slot("work", B * d)
         att = self.slot("work", B * f)
-        scratch = self.slot("work", B * (2 * f + d))
+        scratch = self.slot("work", sk_fc_scratch_floats(B, f, d))
         v = self.tensor("v", (B, H, W, f))
         dims = dict(B=B, HW=H * W, f=f, d=d)
         self.emit("sk_gap", y=co.y.name, bn=co.bn, s=s, **dims)

@@ -359,6 +359,7 @@ class Runtime:
 
     def op_sk_fc(self, op):
         bn = op.bn
+        assert op.scratch.size >= self.lib.acnn_sk_fc_scratch_floats(op.B, op.f, op.d)
         self._chk(self.lib.acnn_sk_fc_fwd(
             self.S(op.s), self.P(op.w1), self.P(bn.gamma), self.P(bn.beta), self.P(bn.mm),
             self.P(bn.mv), self.bn_momentum, self.eps, 1 if self.training else 0, self.P(op.w2),

@@ -62,11 +62,19 @@ int acnn_set_wgrad_pixels(int pix);
  * cost model that picks the number of pixel splits (default 16); 0 = the round-1 "two waves of CTAs"
  * rule.  Returns the previous setting. */
 int acnn_set_wgrad_overhead_stages(int stages);
-/* SK attention chains (acnn_sk_fc_fwd / acnn_sk_fc_bwd): 0 (default) = the multi-launch split-K
- * path; 1 = one fused launch per direction on a thread-block cluster of 8 CTAs (no split-K:
- * deterministic; measured 5x slower per block, so not the default).  Same results up to fp32
- * summation order.  Returns the previous setting. */
+/* Tuning knob: the largest grid (CTAs) of the grid-stride elementwise kernels (bn_act, bn_bwd_apply,
+ * ...); no effect on results.  Values below 148 restore the default.  Returns the previous setting. */
+int acnn_set_stream_grid_cap(int blocks);
+/* SK attention chains (acnn_sk_fc_fwd / acnn_sk_fc_bwd): 1 = ONE cooperative launch per direction
+ * (the whole grid walks GEMM / batch-norm / gate phases separated by grid barriers; K-split partials
+ * summed in split order: deterministic, no atomics, nothing to zero); 0 = the multi-launch path (4 + 6
+ * kernels and 4 memsets per SK block; split-K with atomics unless deterministic); -1 (default) = fused
+ * when the call asks for deterministic results, multi-launch otherwise (measured 0.37 ms per c3 step
+ * faster than fused).  Same results up to fp32 summation order.  Returns the previous setting. */
 int acnn_set_sk_fc_fused(int on);
+/* floats of the `scratch` argument of acnn_sk_fc_fwd / acnn_sk_fc_bwd (da [B,2f] + dz [B,d] + the
+ * K-split partial tiles of the widest phase, sized for 148 CTAs; callable without a GPU) */
+int64_t acnn_sk_fc_scratch_floats(int B, int f, int d);
 
 /* Convolution geometry (correlation, no bias) -- nets/model_helper.py:67-78 conv2d_fixed_padding
  * + fixed_padding :40-64.  Ho = (H + pad_h_lo + pad_h_hi - kh) / stride + 1, same for W. */
@@ -183,7 +191,7 @@ int acnn_sk_gap(const void* y, const float* scale, const float* shift, float* s,
 int acnn_sk_fc_fwd(const float* s, const float* w1, const float* gamma, const float* beta,
                    float* moving_mean, float* moving_var, float momentum, float eps, int training,
                    const float* w2, float* zpre, float* bnstat, float* z, float* att,
-                   float* scratch /* >= B*2f floats */, int B, int f, int d, int deterministic,
+                   float* scratch /* acnn_sk_fc_scratch_floats(B, f, d) floats */, int B, int f, int d, int deterministic,
                    void* stream);
 /* v[B,HW,f] = att*u0 + (1-att)*u1                                           (blocks.py:152) */
 int acnn_sk_combine(const void* y, const float* scale, const float* shift, const float* att,
@@ -196,7 +204,7 @@ int acnn_sk_bwd_gate(const void* dv, const void* y, const float* scale, const fl
 int acnn_sk_fc_bwd(const float* dA, const float* att, const float* z, const float* zpre,
                    const float* bnstat, const float* gamma, const float* s, const float* w1,
                    const float* w2, float* dw1, float* dw2, float* dgamma, float* dbeta, float* ds,
-                   float* scratch /* >= B*(2f+d) floats */, int B, int f, int d, int deterministic,
+                   float* scratch /* acnn_sk_fc_scratch_floats(B, f, d) floats */, int B, int f, int d, int deterministic,
                    void* stream);
 /* g_h = (att_h*dv + ds/HW) * [u_h > 0] for both halves; partial rows as acnn_bn_bwd_reduce over 2f
  * channels, acnn_sk_bn_bwd_reduce_parts(B, HW, f) rows. */

@@ -101,3 +101,15 @@ def test_learning_rate_schedule_matches_oracle():
             assert abs(fn(step) - want) < 1e-12, (decay, step)
     kp = keep_prob_decay(1.0, 0.9, 1000)
     assert kp(0) == 1.0 and abs(kp(500) - 0.95) < 1e-12 and abs(kp(5000) - 0.9) < 1e-12
+
+
+def test_sk_fc_scratch_formula_matches_library():
+    """plan.py sizes the scratch of the fused SK attention chains with a Python mirror of
+    acnn_sk_fc_scratch_floats (a pure host function: no GPU needed)."""
+    from assembled_cnn_b200 import _lib
+    from assembled_cnn_b200.plan import sk_fc_scratch_floats
+    lib = _lib.load()
+    for B in (1, 2, 5, 12, 64, 128, 256, 300):
+        for f in (64, 128, 256, 512, 96):
+            d = max(f // 2, 32)
+            assert lib.acnn_sk_fc_scratch_floats(B, f, d) == sk_fc_scratch_floats(B, f, d), (B, f)

@@ -167,8 +167,10 @@ def test_checkpoint_round_trip_and_warm_start(tmp_path):
 
 
 def test_sk_fc_fused_matches_multi_launch_path(lib):
-    """The fused cluster kernels of the SK attention chain against the multi-launch split-K path
-    (acnn_set_sk_fc_fused), forward and backward, at the Assemble-ResNet-50 shapes."""
+    """The fused cooperative kernels of the SK attention chain (one launch per direction, K-split
+    partials summed in split order) against the multi-launch split-K path (acnn_set_sk_fc_fused),
+    forward and backward, at the Assemble-ResNet-50 shapes and at ragged batches; two fused runs are
+    bit-identical (poisoned scratch: nothing needs zeroing)."""
     from assembled_cnn_b200 import _lib
     st = torch.cuda.current_stream().cuda_stream
     for B, f in ((256, 64), (256, 512), (12, 128), (5, 256)):
@@ -179,12 +181,15 @@ def test_sk_fc_fused_matches_multi_launch_path(lib):
         gamma, beta = 0.5 + torch.rand(d, generator=g).cuda(), 0.1 * rnd(d)
         dA = rnd(B, f)
         outs = []
-        for fused in (0, 1):
+        for fused in (0, 1, 1):
             lib.acnn_set_sk_fc_fused(fused)
             mm, mv = torch.zeros(d, device="cuda"), torch.ones(d, device="cuda")
             zpre, z, att = (torch.full((B, n), float("nan"), device="cuda") for n in (d, d, f))
             bnstat = torch.zeros(2 * d, device="cuda")
-            scratch = torch.zeros(B * (2 * f + d), device="cuda")
+            n_scr = lib.acnn_sk_fc_scratch_floats(B, f, d)
+            assert n_scr >= B * (2 * f + d)
+            scratch = (torch.zeros(n_scr, device="cuda") if fused == 0
+                       else torch.full((n_scr,), float("nan"), device="cuda"))
             _lib.check(lib.acnn_sk_fc_fwd(s_.data_ptr(), w1.data_ptr(), gamma.data_ptr(),
                                           beta.data_ptr(), mm.data_ptr(), mv.data_ptr(), 0.997, 1e-5,
                                           1, w2.data_ptr(), zpre.data_ptr(), bnstat.data_ptr(),
@@ -201,8 +206,9 @@ def test_sk_fc_fused_matches_multi_launch_path(lib):
                                           0, st), "sk_fc_bwd")
             torch.cuda.synchronize()
             outs.append([t.clone() for t in (zpre, z, att, bnstat, mm, mv, dw1, dw2, dg, db, ds)])
-        lib.acnn_set_sk_fc_fused(1)
-        for a, b in zip(*outs):
+        lib.acnn_set_sk_fc_fused(-1)
+        for a, b, c in zip(*outs):
             assert torch.isfinite(b).all()
             scale = a.abs().max().item() + 1e-12
             assert (a - b).abs().max().item() <= 2e-5 * scale, (B, f)
+            assert torch.equal(b, c), (B, f)

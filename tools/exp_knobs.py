@@ -56,5 +56,5 @@ for fused, pix in ((0, 64), (0, 128), (1, 64)):
     ms, loss = step_ms()
     print("sk_fc_fused=%d wgrad_pixels=%3d : %.3f ms/step   loss %s" % (fused, pix, ms, loss),
           flush=True)
-lib.acnn_set_sk_fc_fused(0)
+lib.acnn_set_sk_fc_fused(-1)
 lib.acnn_set_wgrad_pixels(0)
