@@ -705,6 +705,365 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 convolution WITHOUT im2col copies ("halo" kernel).
+//
+// The im2col kernel above fetches every input pixel nine times (once per filter tap) from L2 into
+// shared memory; for small-N layers (N <= 128: the stem, the 56x56 SK convs and their dgrads) that
+// ingest -- not the tensor pipe, not HBM -- is the bound (147 KB of A per 128 x 64-channel tile).
+// Here a CTA tile is a 16 x 8 PATCH of output pixels of one image, and ONE 18 x 10 pixel halo tile
+// per 64-channel chunk is loaded by a 4-D tiled TMA box at (h0-1, w0-1) (out-of-image pixels are
+// zero-filled: the padding).  The A operand of filter tap (r, s) is the same shared-memory tile read
+// through a descriptor that starts (r*10 + s) pixel rows further on, with 10 pixel rows between 8-row
+// groups (group g = output row h0+g, 8 pixels): the tensor core's swizzle is a function of the
+// absolute shared-memory address, like TMA's, so any row may start a descriptor and the group stride
+// need not be a multiple of the swizzle atom (probed on the B200: tools/microtests/halo_desc.cu,
+// profiles/r02_microtest_halo_desc.txt).  23 KB of A per tile and chunk instead of 147 KB.
+// Weight tiles [BN x CW] per (tap, chunk) stream through their own ring; when the whole N-tile slab
+// fits the ring it is loaded once and stays (weights-stationary: the stem layers).
+// Epilogue = the im2col kernel's (mask / add one half ahead, bf16 staging, TMA store, statistics),
+// with 4-D boxes for the patch and the out-of-image rows excluded from the statistics.
+// ------------------------------------------------------------------------------------------
+constexpr int kHaloH = 18, kHaloW = 10, kPatchH = 16, kPatchW = 8;
+constexpr int kHaloMaxB = 32;      // weight ring slots (barriers)
+
+struct HaloParams {
+  int H, W, B;            // output = input spatial size
+  int Cin, Cout;
+  int n_tiles, ph, pw;    // N tiles; patches per image
+  int m_tiles;            // B * ph * pw
+  int a_stages, b_slots, stationary;
+  float* ch_part;
+  int has_add, has_mask;
+};
+
+template <int BN, int CW>
+struct HaloCfg {
+  static constexpr int kRowB = CW * 2;
+  static constexpr int kABytes = kHaloH * kHaloW * kRowB;
+  static constexpr int kAStage = (kABytes + 1023) / 1024 * 1024;
+  static constexpr int kBTile = BN * kRowB;
+  static constexpr int kSubW = BN < 64 ? BN : 64;
+  static constexpr int kTileBytes = kBM * BN * 2;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static_assert(BN <= 128 && kBTile % 512 == 0, "halo kernel: N tile <= 128");
+};
+
+template <int BN, int CW>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd,
+                 const __grid_constant__ CUtensorMap tmMask, const HaloParams p) {
+  using Cfg = HaloCfg<BN, CW>;
+  constexpr int kRowB = Cfg::kRowB;
+  constexpr int kKSteps = CW / 16;
+  constexpr uint32_t kIdesc = make_idesc_bf16_m(128, BN, false, false);
+  constexpr uint32_t kLayout = swizzle_layout_type(kRowB);
+  constexpr int kSubW = Cfg::kSubW;
+  constexpr int kSubRowB = kSubW * 2;
+  constexpr int kSubBytes = kBM * kSubRowB;
+  constexpr int kNSub = BN / kSubW;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t a_full[4], a_empty[4];
+  __shared__ uint64_t b_full[kHaloMaxB], b_empty[kHaloMaxB];
+  __shared__ uint64_t tfull_bar[2], tempty_bar[2];
+  __shared__ uint64_t aux_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int AS = p.a_stages, NB = p.b_slots;
+  uint8_t* s_out = smem + AS * Cfg::kAStage + NB * Cfg::kBTile;
+  uint8_t* s_add = s_out + Cfg::kTileBytes;
+  uint8_t* s_mask = s_add + (p.has_add ? Cfg::kTileBytes : 0);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nchunks = p.Cin / CW;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  const int m_first = blockIdx.x / p.n_tiles;
+  const int m_step = gridDim.x / p.n_tiles;
+  const int n0 = n_tile * BN;
+  const int my_tiles = m_first < p.m_tiles ? (p.m_tiles - m_first + m_step - 1) / m_step : 0;
+  const int tpi = p.ph * p.pw;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    if (p.has_add) tma_prefetch_desc(&tmAdd);
+    if (p.has_mask) tma_prefetch_desc(&tmMask);
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 1);
+    }
+    mbar_init(&aux_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_entry();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t a_base = smem_u32(smem), b_base = a_base + AS * Cfg::kAStage;
+  const uint32_t afull0 = smem_u32(a_full), aempty0 = smem_u32(a_empty);
+  const uint32_t bfull0 = smem_u32(b_full), bempty0 = smem_u32(b_empty);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    int a_it = 0, b_it = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int tile = m_first + it * m_step;
+      const int img = tile / tpi;
+      const int rem = tile - img * tpi;
+      const int h0 = (rem / p.pw) * kPatchH, w0 = (rem % p.pw) * kPatchW;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        const int sa = a_it % AS;
+        mbar_wait_a(aempty0 + sa * 8, ((a_it / AS) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx_a(afull0 + sa * 8, Cfg::kABytes);
+          tma_load_4d_tile_a(a_base + sa * Cfg::kAStage, &tmA, afull0 + sa * 8, kc * CW, w0 - 1,
+                             h0 - 1, img);
+        }
+        __syncwarp();
+        ++a_it;
+        if (!p.stationary || it == 0) {
+          for (int t = 0; t < 9; ++t) {
+            const int sb = p.stationary ? kc * 9 + t : b_it % NB;
+            if (!p.stationary) mbar_wait_a(bempty0 + sb * 8, ((b_it / NB) & 1) ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx_a(bfull0 + sb * 8, Cfg::kBTile);
+              tma_load_2d_a(b_base + sb * Cfg::kBTile, &tmB, bfull0 + sb * 8, t * p.Cin + kc * CW,
+                            n0);
+            }
+            __syncwarp();
+            ++b_it;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
+    int a_it = 0, b_it = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait_a(tempty0 + acc * 8, ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kc = 0; kc < nchunks; ++kc) {
+        const int sa = a_it % AS;
+        mbar_wait_a(afull0 + sa * 8, (a_it / AS) & 1);
+        const uint32_t a_addr = a_base + sa * Cfg::kAStage;
+#pragma unroll 1
+        for (int t = 0; t < 9; ++t) {
+          const int sb = p.stationary ? kc * 9 + t : b_it % NB;
+          if (!p.stationary || it == 0) mbar_wait_a(bfull0 + sb * 8, p.stationary ? 0 : (b_it / NB) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            // tap (r, s): the halo tile read (r*10 + s) pixel rows further on; 8-row groups (one
+            // output row each) 10 pixel rows apart
+            const uint32_t a_tap = a_addr + ((t / 3) * kHaloW + (t % 3)) * kRowB;
+            const uint32_t b_tap = b_base + sb * Cfg::kBTile;
+#pragma unroll
+            for (int ks = 0; ks < kKSteps; ++ks)
+              umma_bf16(tmem_d, make_smem_desc(a_tap + ks * 32, 16, kHaloW * kRowB, kLayout),
+                        make_smem_desc(b_tap + ks * 32, 16, 8 * kRowB, kLayout), kIdesc,
+                        (kc | t | ks) ? 1u : 0u);
+            if (!p.stationary) umma_commit_a(bempty0 + sb * 8);
+            if (t == 8) {
+              umma_commit_a(aempty0 + sa * 8);
+              if (kc == nchunks - 1) umma_commit_a(tfull0 + acc * 8);
+            }
+          }
+          __syncwarp();
+          ++b_it;
+        }
+        ++a_it;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int quarter = warp & 3;
+    const int egrp = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane;                 // TMEM lane = patch pixel (r/8, r%8)
+    const bool leader = (warp == 2 && lane == 0);
+    const bool stats = p.ch_part != nullptr;
+    const bool has_aux = p.has_add || p.has_mask;
+    const int swz = (kSubRowB == 128) ? (r & 7) : ((r >> 1) & 3);
+    constexpr int kNChunk = BN / 8;
+    constexpr int kStatThreads = (BN == 32) ? 128 : kEpiThreads;
+    constexpr int kNRg = kStatThreads / kNChunk;
+    const int st_t = threadIdx.x - 64;
+    const bool st_on = st_t < kStatThreads;
+    const int st_chunk = st_t % kNChunk, st_rg = st_t / kNChunk;
+    float acc_s[8], acc_q[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc_s[e] = acc_q[e] = 0.f;
+    uint32_t aux_n = 0;
+    auto tile_origin = [&](int it, int* img, int* h0, int* w0) {
+      const int tile = m_first + it * m_step;
+      *img = tile / tpi;
+      const int rem = tile - *img * tpi;
+      *h0 = (rem / p.pw) * kPatchH;
+      *w0 = (rem % p.pw) * kPatchW;
+    };
+    auto issue_aux = [&](int it) {
+      int img, h0, w0;
+      tile_origin(it, &img, &h0, &w0);
+      mbar_expect_tx(&aux_bar, (p.has_add ? Cfg::kTileBytes : 0) +
+                                   (p.has_mask ? Cfg::kTileBytes : 0));
+#pragma unroll
+      for (int sub = 0; sub < kNSub; ++sub) {
+        if (p.has_add)
+          tma_load_4d_tile_a(smem_u32(s_add + sub * kSubBytes), &tmAdd, smem_u32(&aux_bar),
+                             n0 + sub * kSubW, w0, h0, img);
+        if (p.has_mask)
+          tma_load_4d_tile_a(smem_u32(s_mask + sub * kSubBytes), &tmMask, smem_u32(&aux_bar),
+                             n0 + sub * kSubW, w0, h0, img);
+      }
+    };
+    if (leader && has_aux && my_tiles > 0) issue_aux(0);
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const int acc = it & 1;
+      int img, h0, w0;
+      tile_origin(it, &img, &h0, &w0);
+      if (leader) tma_store_wait_read();               // staging buffer free again
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (has_aux) {
+        mbar_wait(&aux_bar, aux_n & 1);
+        ++aux_n;
+      }
+#pragma unroll
+      for (int c2 = 0; c2 < (BN / 32 + 1) / 2; ++c2) {
+        const int c = c2 * 2 + egrp;
+        if (c >= BN / 32) break;                       // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        const int sub = (c * 32) / kSubW;
+        const int j0 = ((c * 32) % kSubW) / 8;
+        const int soff = sub * kSubBytes + r * kSubRowB;
+        if (p.has_add) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_add + soff + (((j0 + q) ^ swz) << 4));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
+              f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+            }
+          }
+        }
+        if (p.has_mask) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float lo = __uint_as_float(w4[e] << 16);
+              const float hi = __uint_as_float(w4[e] & 0xffff0000u);
+              if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
+              if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
+            }
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(s_out + soff + (((j0 + q) ^ swz) << 4)) =
+              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (leader) {
+        mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+        for (int sub = 0; sub < kNSub; ++sub)
+          tma_store_4d(&tmC, s_out + sub * kSubBytes, n0 + sub * kSubW, w0, h0, img);
+        tma_store_commit();
+        if (has_aux && it + 1 < my_tiles) issue_aux(it + 1);
+      }
+      if (stats && st_on) {
+        // column sums of the tile as stored (bf16-rounded), patch pixels outside the image excluded
+        // (they were computed from real neighbours and are clipped by the store)
+        const int sub = st_chunk / (kSubW / 8), jj = st_chunk % (kSubW / 8);
+#pragma unroll 4
+        for (int i = 0; i < kBM / kNRg; ++i) {
+          const int rr = st_rg + i * kNRg;
+          if (h0 + (rr >> 3) >= p.H || w0 + (rr & 7) >= p.W) continue;
+          const int sw = (kSubRowB == 128) ? (rr & 7) : ((rr >> 1) & 3);
+          const uint4 u = *reinterpret_cast<const uint4*>(s_out + sub * kSubBytes + rr * kSubRowB +
+                                                          ((jj ^ sw) << 4));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(w4[e] << 16);
+            const float hi = __uint_as_float(w4[e] & 0xffff0000u);
+            acc_s[2 * e] += lo;
+            acc_q[2 * e] = fmaf(lo, lo, acc_q[2 * e]);
+            acc_s[2 * e + 1] += hi;
+            acc_q[2 * e + 1] = fmaf(hi, hi, acc_q[2 * e + 1]);
+          }
+        }
+      }
+    }
+    if (leader) tma_store_wait_all();
+    if (stats && my_tiles > 0) {
+      float* red_sum = reinterpret_cast<float*>(s_out);
+      float* red_sq = red_sum + kNRg * BN;
+      static_assert(2 * kNRg * BN * 4 <= Cfg::kTileBytes, "staging buffer too small for stats");
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (st_on) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          red_sum[st_rg * BN + st_chunk * 8 + e] = acc_s[e];
+          red_sq[st_rg * BN + st_chunk * 8 + e] = acc_q[e];
+        }
+      }
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      for (int col = st_t; col < BN; col += kEpiThreads) {
+        float ss = 0.f, qq = 0.f;
+        for (int g2 = 0; g2 < kNRg; ++g2) {
+          ss += red_sum[g2 * BN + col];
+          qq += red_sq[g2 * BN + col];
+        }
+        float* row = p.ch_part + static_cast<size_t>(m_first) * 2 * p.Cout;
+        row[n0 + col] = ss;
+        row[p.Cout + n0 + col] = qq;
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // wgrad kernel:  D[(tap,ci) = M 128 rows][co = N] += sum over pixels of  x_im2col^T * dy
 // ------------------------------------------------------------------------------------------
 struct WgradParams {
@@ -1107,6 +1466,130 @@ static int64_t input_elems(const acnn_conv_geom& g) {
   return (int64_t)g.B * img;
 }
 
+// ---- halo (im2col-free 3x3) kernel: eligibility, tiling, launch --------------------------------
+// 0: off; 1 (default): where measured to pay (N <= 128 and images of >= 56 rows: patches of 16 x 8
+// waste <= 12.5 % of a 56 x 56 image, 27 % of 28 x 28); 2: wherever the kernel applies
+// (acnn_set_conv_halo; ACNN_CONV_HALO=0|1|2 sets the initial value)
+static int conv_halo_default() {
+  const char* e = getenv("ACNN_CONV_HALO");
+  return e ? (e[0] - '0') : 1;
+}
+static int g_conv_halo = conv_halo_default();
+
+static int halo_bn(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32); }
+
+static bool use_halo(const acnn_conv_geom& g, int np, bool out_f32, bool has_bias) {
+  if (g_conv_halo <= 0) return false;
+  const bool applies = g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad_h_lo == 1 &&
+                       g.pad_h_hi == 1 && g.pad_w_lo == 1 && g.pad_w_hi == 1 &&
+                       g.x_pix_stride <= 0 && g.x_row_pitch <= 0 && g.x_img_pitch <= 0 && np == 1 &&
+                       !out_f32 && !has_bias && (g.Cin % 64 == 0 || g.Cin == 32) &&
+                       g.Cout % 32 == 0;
+  if (!applies) return false;
+  if (g_conv_halo >= 2) return true;
+  return g.Cout <= 128 && g.H >= 56;
+}
+
+// CTAs per N tile of the halo kernel's persistent grid (= partial statistics rows)
+static int halo_per_n(const acnn_conv_geom& g) {
+  const int n_tiles = g.Cout / halo_bn(g.Cout);
+  const int m_tiles = g.B * ceil_div(g.H, kPatchH) * ceil_div(g.W, kPatchW);
+  int per_n = num_sms() / n_tiles;
+  if (per_n < 1) per_n = 1;
+  return per_n > m_tiles ? m_tiles : per_n;
+}
+
+static int make_map_4d(CUtensorMap* m, const void* base, int C, int W, int H, int B, int box_c,
+                       int box_w, int box_h) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              swizzle_enum(box_c * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-d) failed (%d): C=%d W=%d H=%d B=%d box=%dx%dx%d", (int)r,
+              C, W, H, B, box_c, box_w, box_h);
+    return ACNN_ERR_CUDA;
+  }
+  return ACNN_OK;
+}
+
+template <int BN, int CW>
+static int launch_conv_halo(const acnn_conv_geom& g, const void* x, const void* w, void* y,
+                            float* ch_part, const void* add_src, const void* mask_src,
+                            cudaStream_t stream) {
+  using Cfg = HaloCfg<BN, CW>;
+  static bool attr_set = false;
+  auto kern = conv_halo_kernel<BN, CW>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBudget + 2048);
+    if (e != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(conv_halo): %s", cudaGetErrorString(e));
+      return ACNN_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  HaloParams p;
+  p.H = g.H; p.W = g.W; p.B = g.B; p.Cin = g.Cin; p.Cout = g.Cout;
+  p.n_tiles = g.Cout / BN;
+  p.ph = ceil_div(g.H, kPatchH);
+  p.pw = ceil_div(g.W, kPatchW);
+  p.m_tiles = g.B * p.ph * p.pw;
+  p.ch_part = ch_part;
+  p.has_add = add_src != nullptr;
+  p.has_mask = mask_src != nullptr;
+  const int nchunks = g.Cin / CW;
+  const int fixed = 1024 + Cfg::kTileBytes * (1 + p.has_add + p.has_mask);
+  p.a_stages = 3;
+  p.b_slots = (kSmemBudget - fixed - p.a_stages * Cfg::kAStage) / Cfg::kBTile;
+  if (p.b_slots < 3) {
+    p.a_stages = 2;
+    p.b_slots = (kSmemBudget - fixed - p.a_stages * Cfg::kAStage) / Cfg::kBTile;
+  }
+  if (p.b_slots > kHaloMaxB) p.b_slots = kHaloMaxB;
+  ACNN_REQUIRE(p.b_slots >= 2, "conv (halo): shared memory does not fit");
+  p.stationary = nchunks * 9 <= p.b_slots ? 1 : 0;
+  if (p.stationary) p.b_slots = nchunks * 9;
+  const int smem = fixed + p.a_stages * Cfg::kAStage + p.b_slots * Cfg::kBTile;
+  CUtensorMap tmA, tmB, tmC, tmAdd, tmMask;
+  int rc = make_map_4d(&tmA, x, g.Cin, g.W, g.H, g.B, CW, kHaloW, kHaloH);
+  if (rc) return rc;
+  if ((rc = make_map_2d(&tmB, w, g.Cout, 9 * g.Cin, 9 * g.Cin, BN, CW))) return rc;
+  if ((rc = make_map_4d(&tmC, y, g.Cout, g.W, g.H, g.B, Cfg::kSubW, kPatchW, kPatchH))) return rc;
+  tmAdd = tmMask = tmC;
+  if (add_src && (rc = make_map_4d(&tmAdd, add_src, g.Cout, g.W, g.H, g.B, Cfg::kSubW, kPatchW,
+                                   kPatchH)))
+    return rc;
+  if (mask_src && (rc = make_map_4d(&tmMask, mask_src, g.Cout, g.W, g.H, g.B, Cfg::kSubW, kPatchW,
+                                    kPatchH)))
+    return rc;
+  launch_k(kern, dim3(halo_per_n(g) * p.n_tiles), dim3(kConvThreads), smem, stream, tmA, tmB, tmC,
+           tmAdd, tmMask, p);
+  count_launch();
+  return check_launch("conv_halo_kernel");
+}
+
+static int conv_halo_host(const acnn_conv_geom& g, const void* x, const void* w, void* y,
+                          float* ch_part, const void* add_src, const void* mask_src,
+                          cudaStream_t stream) {
+  const int bn = halo_bn(g.Cout);
+  const bool c64 = g.Cin % 64 == 0;
+  if (bn == 128) {
+    return c64 ? launch_conv_halo<128, 64>(g, x, w, y, ch_part, add_src, mask_src, stream)
+               : launch_conv_halo<128, 32>(g, x, w, y, ch_part, add_src, mask_src, stream);
+  }
+  if (bn == 64) {
+    return c64 ? launch_conv_halo<64, 64>(g, x, w, y, ch_part, add_src, mask_src, stream)
+               : launch_conv_halo<64, 32>(g, x, w, y, ch_part, add_src, mask_src, stream);
+  }
+  return c64 ? launch_conv_halo<32, 64>(g, x, w, y, ch_part, add_src, mask_src, stream)
+             : launch_conv_halo<32, 32>(g, x, w, y, ch_part, add_src, mask_src, stream);
+}
+
 // precision 0: x / w are bf16.  precision 1 (fp32 parity mode): x and w each are THREE consecutive
 // bf16 planes (acnn_split3 / acnn_prep_weights with planes = 3), plane p of x at x + p * numel(x),
 // plane p of w at w + p * w_plane_stride elements; y must be fp32 (out_f32), no fused epilogue.
@@ -1129,6 +1612,8 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
                "conv: padding / filter exceed the TMA im2col corner range");
   int rc = load_driver_fns();
   if (rc) return rc;
+  if (use_halo(g, precision ? 3 : 1, out_f32 != 0, bias != nullptr))
+    return conv_halo_host(g, x, w, y, ch_part, add_src, mask_src, stream);
 
   const bool plain = is_plain(g);
   const int cw = chunk_width(g.Cin);
@@ -1379,6 +1864,12 @@ int acnn_set_conv_mtiles(int mode) {
   return prev;
 }
 
+int acnn_set_conv_halo(int mode) {
+  const int prev = acnn::g_conv_halo;
+  acnn::g_conv_halo = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return prev;
+}
+
 int acnn_set_wgrad_overhead_stages(int stages) {
   const int prev = acnn::g_wgrad_overhead_stages;
   acnn::g_wgrad_overhead_stages = stages < 0 ? 0 : stages;
@@ -1395,6 +1886,7 @@ int acnn_conv_stats_parts(const acnn_conv_geom* g) {
   if (!g) return 0;
   int Ho, Wo;
   if (!acnn::out_hw(*g, &Ho, &Wo) || g->Cout % 32 != 0) return 0;
+  if (acnn::use_halo(*g, 1, false, false)) return acnn::halo_per_n(*g);
   return acnn::conv_tiling(g->B * Ho * Wo, g->Cout, g->kh * g->kw * g->Cin,
                            acnn::chunk_width(g->Cin), false, false, false, 1).parts;
 }

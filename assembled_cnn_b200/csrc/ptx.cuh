@@ -151,6 +151,27 @@ __device__ __forceinline__ void tma_load_im2col_4d_a(uint32_t smem_dst, const CU
       : "memory");
 }
 
+// 4-D tiled load over an NHWC tensor (coords c, w, h, n; signed: elements outside the tensor are
+// zero-filled) -- the halo tiles of the im2col-free 3x3 kernel.
+__device__ __forceinline__ void tma_load_4d_tile_a(uint32_t smem_dst, const CUtensorMap* m,
+                                                   uint32_t bar, int32_t c, int32_t w, int32_t h,
+                                                   int32_t n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(smem_dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+// 4-D tiled store smem -> global; elements outside the tensor are clipped.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int32_t c,
+                                             int32_t w, int32_t h, int32_t n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(smem_src)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+
 // 2-D tiled store smem -> global (bulk async group); rows/cols outside the tensor are clipped.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0,
                                              int32_t c1) {

@@ -53,6 +53,13 @@ int acnn_set_conv_mtiles(int mode);
  * of two CTAs computes one 256 x 256 tile, each staging half of the weight tile); 0: single-CTA tiles.
  * Results are bit-identical; changes acnn_conv_stats_parts().  Returns the previous setting. */
 int acnn_set_conv_cta_pairs(int on);
+/* 3x3 / stride 1 / pad 1 convolutions (fprop and dgrad) on the im2col-free "halo" kernel: a CTA tile
+ * is a 16 x 8 patch of output pixels, one 18 x 10 halo tile per 64-channel chunk is loaded once and
+ * the nine filter taps read shifted windows of it through the tensor core's shared-memory
+ * descriptors.  0 = off (im2col TMA kernel everywhere); 1 (default) = where it pays (N <= 128, >= 56
+ * rows); 2 = wherever it applies.  Same results up to fp32 summation order of the statistics;
+ * changes acnn_conv_stats_parts().  Returns the previous setting. */
+int acnn_set_conv_halo(int mode);
 /* Tuning knob of the wgrad launcher (no effect on results beyond fp32 summation order): pixels
  * (GEMM K) per pipeline stage, 64 or 128 (N tile <= 128 only); 0 = choose per problem (default).
  * Returns the previous setting. */

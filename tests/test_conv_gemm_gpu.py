@@ -375,3 +375,86 @@ def test_cta_pair_fprop_dgrad_match_single_cta_and_oracle(lib, case):
         assert _relerr(outs[1][0][b:b + 1], ref) < BF16_TOL
         want = (ref + add[b:b + 1]) * (mask[b:b + 1] > 0)
         assert _relerr(outs[1][1][b:b + 1], want) < BF16_TOL
+
+
+@contextlib.contextmanager
+def _halo(lib, mode):
+    prev = lib.acnn_set_conv_halo(mode)
+    try:
+        yield
+    finally:
+        lib.acnn_set_conv_halo(prev)
+
+
+HALO_CASES = [
+    # B, H, W, Cin, Cout   (3x3, stride 1, pad 1)
+    (2, 20, 12, 64, 64),       # ragged patches both ways (20 = 16 + 4, 12 = 8 + 4); weights stationary
+    (2, 16, 8, 64, 32),        # exactly one patch per image, N = 32
+    (3, 7, 7, 64, 128),        # image smaller than a patch
+    (2, 24, 20, 128, 128),     # two 64-channel chunks, weight tiles streamed through the ring
+    (2, 18, 18, 256, 64),      # four chunks, N = 64, streamed
+    (2, 20, 12, 32, 32),       # 32-channel rows (64-byte swizzle), N = 32
+    (2, 20, 12, 32, 64),       # 32-channel rows, N = 64
+    (2, 14, 14, 64, 256),      # two N tiles of 128 (mode 2 only)
+    (12, 56, 56, 64, 128),     # 336 patches: several per CTA, rings and both accumulators wrap
+    (10, 112, 112, 32, 32),    # the stem's shape class: 980 patches, 64-byte rows
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=[str(c) for c in HALO_CASES])
+def test_halo_kernel_fprop_dgrad_match_oracle_and_im2col(lib, case):
+    """The im2col-free 3x3 kernel (acnn_set_conv_halo(2): wherever it applies) against the oracle and
+    against the im2col TMA kernel (mode 0): plain + statistics, add + mask epilogue, and the dgrad
+    entry point.  The two kernels add the K terms in different orders (chunk-major vs tap-major), so
+    they agree to a bf16 ulp, not bit for bit; two halo runs are bit-identical."""
+    from assembled_cnn_b200 import _lib
+    B, H, W, Cin, Cout = case
+    g = _geom(B, H, W, Cin, Cout, 3, 1)
+    x = _rand_bf16(B, H, W, Cin, seed=31)
+    w_hwio = _rand_bf16(3, 3, Cin, Cout, seed=32, scale=(9 * Cin) ** -0.5)
+    add = _rand_bf16(B, H, W, Cout, seed=33)
+    mask = _rand_bf16(B, H, W, Cout, seed=34)
+    st = torch.cuda.current_stream().cuda_stream
+    xd = x.bfloat16().cuda()
+    wd = w_hwio.permute(3, 0, 1, 2).contiguous().bfloat16().cuda()
+    addd, maskd = add.bfloat16().cuda(), mask.bfloat16().cuda()
+    outs = {}
+    for mode in (0, 2, 2):
+        with _halo(lib, mode):
+            parts = lib.acnn_conv_stats_parts(g)
+            assert 1 <= parts <= 148
+            sp = torch.full((parts, 2, Cout), float("nan"), device="cuda")
+            y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            y2 = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device="cuda")
+            _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), y.data_ptr(),
+                                           sp.data_ptr(), None, None, None, 0, 0, 0, st), "fprop")
+            _lib.check(lib.acnn_conv_fprop(g, xd.data_ptr(), wd.data_ptr(), y2.data_ptr(), None,
+                                           addd.data_ptr(), maskd.data_ptr(), None, 0, 0, 0, st))
+            torch.cuda.synchronize()
+            prev = outs.get(mode)
+            outs[mode] = (y.float().cpu(), y2.float().cpu(), sp.double().sum(0).cpu(), sp.cpu())
+            if prev is not None:           # second halo run: bit-identical, statistics rows included
+                assert torch.equal(prev[0], outs[mode][0]) and torch.equal(prev[1], outs[mode][1])
+                assert torch.equal(prev[3], outs[mode][3])
+    ref = _ref_conv(x, w_hwio, g)
+    yh, y2h, sh, _ = outs[2]
+    assert _relerr(yh, ref) < BF16_TOL
+    assert _relerr(y2h, (ref + add) * (mask > 0)) < BF16_TOL
+    assert _relerr(yh, outs[0][0]) < BF16_TOL and _relerr(y2h, outs[0][1]) < BF16_TOL
+    # statistics of the stored tensor, out-of-image patch pixels excluded
+    assert _relerr(sh[1], (yh * yh).sum(dim=(0, 1, 2))) < 1e-3
+    s1 = yh.double().sum(dim=(0, 1, 2))
+    assert _relerr(sh[0], s1) < 1e-3 or (sh[0] - s1).abs().max() < 1e-2
+    # dgrad entry point (its N is Cin, its K channels are Cout)
+    xg = x.clone().requires_grad_(True)
+    yy = _ref_conv(xg, w_hwio, g)
+    dy = _rand_bf16(*yy.shape, seed=35)
+    (dx_ref,) = torch.autograd.grad(yy, xg, dy)
+    wdg = w_hwio.flip(0, 1).permute(2, 0, 1, 3).contiguous().bfloat16().cuda()
+    dxd = torch.full((B, H, W, Cin), float("nan"), dtype=torch.bfloat16, device="cuda")
+    if Cout % 64 == 0 or Cout == 32:
+        with _halo(lib, 2):
+            _lib.check(lib.acnn_conv_dgrad(g, dy.bfloat16().cuda().data_ptr(), wdg.data_ptr(),
+                                           dxd.data_ptr(), None, None, 0, 0, st), "conv_dgrad")
+        torch.cuda.synchronize()
+        assert _relerr(dxd.float().cpu(), dx_ref) < BF16_TOL
