@@ -1472,7 +1472,7 @@ static int64_t input_elems(const acnn_conv_geom& g) {
 // (acnn_set_conv_halo; ACNN_CONV_HALO=0|1|2 sets the initial value)
 static int conv_halo_default() {
   const char* e = getenv("ACNN_CONV_HALO");
-  return e ? (e[0] - '0') : 1;
+  return e ? (e[0] - '0') : 0;
 }
 static int g_conv_halo = conv_halo_default();
 
