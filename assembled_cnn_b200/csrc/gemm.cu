@@ -144,6 +144,7 @@ struct ConvGemmParams {
   const float* bias;
   int has_add, has_mask;
   int out_f32;
+  int out_bufs;     // 1 or 2 output staging half tiles (2: a half's TMA store drains under the next)
 };
 
 constexpr int kBM = 128;        // output pixels per CTA tile == UMMA M == TMEM lanes
@@ -170,10 +171,11 @@ static inline int fprop_stage_bytes(int bn, int mt, int np, bool pair = false) {
   return np * (mt * kBM * kStageK * 2 + (pair ? bn / 2 : bn) * kStageK * 2);
 }
 static inline int fprop_stages(int bn, int mt, int np, bool has_add, bool has_mask, bool out_f32,
-                               bool pair = false) {
+                               bool pair = false, int out_bufs = 1) {
   const int half_n = bn > 128 ? 128 : bn;
   const int tile = kBM * half_n * 2;
-  const int fixed = 1024 + (out_f32 ? 0 : tile) + (has_add ? tile : 0) + (has_mask ? tile : 0);
+  const int fixed =
+      1024 + (out_f32 ? 0 : out_bufs * tile) + (has_add ? tile : 0) + (has_mask ? tile : 0);
   int st = (kSmemBudget - fixed) / fprop_stage_bytes(bn, mt, np, pair);
   if (st > kMaxStages) st = kMaxStages;
   if (st < 2) st = 2;
@@ -207,12 +209,12 @@ struct FpropCfg {
   static_assert(2 * kAccCols <= 512 && (NP == 1 || MT == 1), "TMEM holds 512 columns");
   static_assert(!CG2 || (MT == 1 && NP == 1), "CTA pairs: one M tile per CTA, bf16 operands");
   // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
-  static int stages_for(bool has_add, bool has_mask, bool out_f32) {
-    return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32, CG2);
+  static int stages_for(bool has_add, bool has_mask, bool out_f32, int out_bufs = 1) {
+    return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32, CG2, out_bufs);
   }
-  static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32) {
-    return 1024 + stages * kStageBytes + (out_f32 ? 0 : kTileBytes) + (has_add ? kTileBytes : 0) +
-           (has_mask ? kTileBytes : 0);
+  static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32, int out_bufs = 1) {
+    return 1024 + stages * kStageBytes + (out_f32 ? 0 : out_bufs * kTileBytes) +
+           (has_add ? kTileBytes : 0) + (has_mask ? kTileBytes : 0);
   }
 };
 
@@ -251,8 +253,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int kStages = p.stages;
-  uint8_t* s_out = smem + kStages * Cfg::kStageBytes;
-  uint8_t* s_add = s_out + (p.out_f32 ? 0 : Cfg::kTileBytes);
+  uint8_t* s_out0 = smem + kStages * Cfg::kStageBytes;
+  uint8_t* s_add = s_out0 + (p.out_f32 ? 0 : p.out_bufs * Cfg::kTileBytes);
   uint8_t* s_mask = s_add + (p.has_add ? Cfg::kTileBytes : 0);
 
   const int warp = threadIdx.x >> 5;
@@ -494,6 +496,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc_s[hf][e] = acc_q[hf][e] = 0.f;
     uint32_t aux_n = 0;                                // completed aux-barrier phases
+    // output staging: with two buffers the TMA store of a half tile keeps draining (its shared-
+    // memory reads are paced by the memory system accepting the writes) under the next half's TMEM
+    // reads instead of stalling all 8 warps -- what bounded the store-heavy small-K tiles
+    const bool two_out = p.out_bufs == 2;
+    uint32_t ebuf = 0;
     // add / mask half tiles are fetched ONE HALF AHEAD: the loads of the next half are issued as
     // soon as every thread has consumed the current one (they then overlap this half's TMA store,
     // the statistics pass and the next half's TMEM reads instead of stalling all 8 warps for an
@@ -523,9 +530,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int hf = 0; hf < kNHalf; ++hf) {
         const int nh = n0 + hf * kHalfN;               // first output column of this half
-        if (leader) {
-          // the previous TMA store must have finished READING the staging buffer
-          if (!p.out_f32) tma_store_wait_read();
+        uint8_t* s_out = s_out0 + ebuf * Cfg::kTileBytes;
+        if (leader && !p.out_f32) {
+          // the TMA store that last used this staging buffer must have finished READING it
+          if (two_out) tma_store_wait_read1();
+          else tma_store_wait_read();
         }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");   // staging buffers free for everyone
         if (hf == 0 && mh == 0) {
@@ -657,13 +666,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        if (two_out) ebuf ^= 1;
       }
       }   // mh
     }
     if (leader && !p.out_f32) tma_store_wait_all();
     if (stats && my_tiles > 0) {
       // final cross-row-group reduction in the (now idle) output staging buffer
-      float* red_sum = reinterpret_cast<float*>(s_out);
+      float* red_sum = reinterpret_cast<float*>(s_out0);
       float* red_sq = red_sum + kNRg * BN;
       static_assert(2 * kNRg * BN * 4 <= Cfg::kTileBytes, "staging buffer too small for stats");
       asm volatile("bar.sync 1, 256;\n" ::: "memory");   // the last TMA store has drained
@@ -732,6 +742,7 @@ struct HaloParams {
   int n_tiles, ph, pw;    // N tiles; patches per image
   int m_tiles;            // B * ph * pw
   int a_stages, b_slots, stationary;
+  int out_bufs;           // 1 or 2 output staging tiles (2: the TMA store of tile i overlaps tile i+1)
   float* ch_part;
   int has_add, has_mask;
 };
@@ -773,8 +784,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int AS = p.a_stages, NB = p.b_slots;
-  uint8_t* s_out = smem + AS * Cfg::kAStage + NB * Cfg::kBTile;
-  uint8_t* s_add = s_out + Cfg::kTileBytes;
+  uint8_t* s_out0 = smem + AS * Cfg::kAStage + NB * Cfg::kBTile;
+  uint8_t* s_add = s_out0 + p.out_bufs * Cfg::kTileBytes;
   uint8_t* s_mask = s_add + (p.has_add ? Cfg::kTileBytes : 0);
 
   const int warp = threadIdx.x >> 5;
@@ -820,33 +831,42 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    int a_it = 0, b_it = 0;
+    // ring positions / phases advance incrementally (no runtime division in the issue loops)
+    uint32_t sa = 0, a_ph = 0, sb = 0, b_ph = 0;
+    if (p.stationary && my_tiles > 0) {
+      // the whole weight slab of this N tile: loaded once, ONE barrier, stays for the CTA's lifetime
+      if (elect_one()) {
+        mbar_expect_tx_a(bfull0, static_cast<uint32_t>(nchunks) * 9 * Cfg::kBTile);
+        for (int kc = 0; kc < nchunks; ++kc)
+          for (int t = 0; t < 9; ++t)
+            tma_load_2d_a(b_base + (kc * 9 + t) * Cfg::kBTile, &tmB, bfull0, t * p.Cin + kc * CW, n0);
+      }
+      __syncwarp();
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const int tile = m_first + it * m_step;
       const int img = tile / tpi;
       const int rem = tile - img * tpi;
       const int h0 = (rem / p.pw) * kPatchH, w0 = (rem % p.pw) * kPatchW;
       for (int kc = 0; kc < nchunks; ++kc) {
-        const int sa = a_it % AS;
-        mbar_wait_a(aempty0 + sa * 8, ((a_it / AS) & 1) ^ 1);
+        mbar_wait_a(aempty0 + sa * 8, a_ph ^ 1);
         if (elect_one()) {
           mbar_expect_tx_a(afull0 + sa * 8, Cfg::kABytes);
           tma_load_4d_tile_a(a_base + sa * Cfg::kAStage, &tmA, afull0 + sa * 8, kc * CW, w0 - 1,
                              h0 - 1, img);
         }
         __syncwarp();
-        ++a_it;
-        if (!p.stationary || it == 0) {
+        if (++sa == static_cast<uint32_t>(AS)) { sa = 0; a_ph ^= 1; }
+        if (!p.stationary) {
           for (int t = 0; t < 9; ++t) {
-            const int sb = p.stationary ? kc * 9 + t : b_it % NB;
-            if (!p.stationary) mbar_wait_a(bempty0 + sb * 8, ((b_it / NB) & 1) ^ 1);
+            mbar_wait_a(bempty0 + sb * 8, b_ph ^ 1);
             if (elect_one()) {
               mbar_expect_tx_a(bfull0 + sb * 8, Cfg::kBTile);
               tma_load_2d_a(b_base + sb * Cfg::kBTile, &tmB, bfull0 + sb * 8, t * p.Cin + kc * CW,
                             n0);
             }
             __syncwarp();
-            ++b_it;
+            if (++sb == static_cast<uint32_t>(NB)) { sb = 0; b_ph ^= 1; }
           }
         }
       }
@@ -854,41 +874,63 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t tfull0 = smem_u32(tfull_bar), tempty0 = smem_u32(tempty_bar);
-    int a_it = 0, b_it = 0;
+    uint32_t sa = 0, a_ph = 0, sb = 0, b_ph = 0;
+    // descriptors are built once; every tap / k-step / ring slot is an add on the address field
+    const uint64_t a_desc0 = make_smem_desc(a_base, 16, kHaloW * kRowB, kLayout);
+    const uint64_t b_desc0 = make_smem_desc(b_base, 16, 8 * kRowB, kLayout);
+    if (p.stationary && my_tiles > 0) {
+      mbar_wait_a(bfull0, 0);
+      tc_fence_after();
+    }
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t acc = it & 1;
       mbar_wait_a(tempty0 + acc * 8, ((it >> 1) & 1) ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
       for (int kc = 0; kc < nchunks; ++kc) {
-        const int sa = a_it % AS;
-        mbar_wait_a(afull0 + sa * 8, (a_it / AS) & 1);
-        const uint32_t a_addr = a_base + sa * Cfg::kAStage;
-#pragma unroll 1
-        for (int t = 0; t < 9; ++t) {
-          const int sb = p.stationary ? kc * 9 + t : b_it % NB;
-          if (!p.stationary || it == 0) mbar_wait_a(bfull0 + sb * 8, p.stationary ? 0 : (b_it / NB) & 1);
-          tc_fence_after();
+        mbar_wait_a(afull0 + sa * 8, a_ph);
+        tc_fence_after();
+        const uint64_t a_st = a_desc0 + ((sa * Cfg::kAStage) >> 4);
+        if (p.stationary) {
           if (elect_one()) {
-            // tap (r, s): the halo tile read (r*10 + s) pixel rows further on; 8-row groups (one
-            // output row each) 10 pixel rows apart
-            const uint32_t a_tap = a_addr + ((t / 3) * kHaloW + (t % 3)) * kRowB;
-            const uint32_t b_tap = b_base + sb * Cfg::kBTile;
+            const uint64_t b_st = b_desc0 + ((static_cast<uint32_t>(kc) * 9 * Cfg::kBTile) >> 4);
 #pragma unroll
-            for (int ks = 0; ks < kKSteps; ++ks)
-              umma_bf16(tmem_d, make_smem_desc(a_tap + ks * 32, 16, kHaloW * kRowB, kLayout),
-                        make_smem_desc(b_tap + ks * 32, 16, 8 * kRowB, kLayout), kIdesc,
-                        (kc | t | ks) ? 1u : 0u);
-            if (!p.stationary) umma_commit_a(bempty0 + sb * 8);
-            if (t == 8) {
-              umma_commit_a(aempty0 + sa * 8);
-              if (kc == nchunks - 1) umma_commit_a(tfull0 + acc * 8);
+            for (int t = 0; t < 9; ++t) {
+              // tap (r, s): the halo tile read (r*10 + s) pixel rows further on; 8-row groups (one
+              // output row each) 10 pixel rows apart
+#pragma unroll
+              for (int ks = 0; ks < kKSteps; ++ks)
+                umma_bf16(tmem_d, a_st + ((((t / 3) * kHaloW + (t % 3)) * kRowB + ks * 32) >> 4),
+                          b_st + ((t * Cfg::kBTile + ks * 32) >> 4), kIdesc,
+                          (t | ks) ? 1u : static_cast<uint32_t>(kc != 0));
             }
+            umma_commit_a(aempty0 + sa * 8);
+            if (kc == nchunks - 1) umma_commit_a(tfull0 + acc * 8);
           }
           __syncwarp();
-          ++b_it;
+        } else {
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait_a(bfull0 + sb * 8, b_ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t a_tap = a_st + ((((t / 3) * kHaloW + (t % 3)) * kRowB) >> 4);
+              const uint64_t b_tap = b_desc0 + ((sb * Cfg::kBTile) >> 4);
+#pragma unroll
+              for (int ks = 0; ks < kKSteps; ++ks)
+                umma_bf16(tmem_d, a_tap + ((ks * 32) >> 4), b_tap + ((ks * 32) >> 4), kIdesc,
+                          (kc | t | ks) ? 1u : 0u);
+              umma_commit_a(bempty0 + sb * 8);
+              if (t == 8) {
+                umma_commit_a(aempty0 + sa * 8);
+                if (kc == nchunks - 1) umma_commit_a(tfull0 + acc * 8);
+              }
+            }
+            __syncwarp();
+            if (++sb == static_cast<uint32_t>(NB)) { sb = 0; b_ph ^= 1; }
+          }
         }
-        ++a_it;
+        if (++sa == static_cast<uint32_t>(AS)) { sa = 0; a_ph ^= 1; }
       }
     }
   } else {
@@ -938,7 +980,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int acc = it & 1;
       int img, h0, w0;
       tile_origin(it, &img, &h0, &w0);
-      if (leader) tma_store_wait_read();               // staging buffer free again
+      // staging buffer free again: with two buffers only the store issued two tiles ago must have
+      // finished reading (the previous tile's store keeps draining under this tile's TMEM reads)
+      uint8_t* s_out = s_out0 + ((p.out_bufs == 2 && (it & 1)) ? Cfg::kTileBytes : 0);
+      if (leader) {
+        if (p.out_bufs == 2) tma_store_wait_read1();
+        else tma_store_wait_read();
+      }
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -1030,7 +1078,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     if (leader) tma_store_wait_all();
     if (stats && my_tiles > 0) {
-      float* red_sum = reinterpret_cast<float*>(s_out);
+      float* red_sum = reinterpret_cast<float*>(s_out0);
       float* red_sq = red_sum + kNRg * BN;
       static_assert(2 * kNRg * BN * 4 <= Cfg::kTileBytes, "staging buffer too small for stats");
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
@@ -1322,6 +1370,15 @@ struct ConvMaps {
   CUtensorMap a[3], b[3], c, add, mask;
 };
 
+// output staging buffers of the conv GEMM epilogue: 0 = per problem (default), 1 = always one,
+// 2 = two wherever shared memory allows (acnn_set_conv_out_bufs; ACNN_CONV_OUT_BUFS sets the
+// initial value)
+static int conv_out_bufs_default() {
+  const char* e = getenv("ACNN_CONV_OUT_BUFS");
+  return e ? (e[0] - '0') : 0;
+}
+static int g_conv_out_bufs = conv_out_bufs_default();
+
 template <int BN, int CW, bool IM2COL, int MT, int NP, bool CG2 = false>
 static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per_n,
                             cudaStream_t stream) {
@@ -1338,10 +1395,22 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per
     attr_set = true;
   }
   ConvGemmParams q = p;
-  q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32);
+  // a second output staging half tile where the ring stays deep enough without its bytes: all of K
+  // in flight, or >= 4 stages (g_conv_out_bufs: 0 = this rule, 1 / 2 = force where it fits)
+  q.out_bufs = 1;
+  if (!p.out_f32 && g_conv_out_bufs != 1) {
+    const int st2 = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32, 2);
+    const int num_kb = ceil_div(p.Ktot, kStageK);
+    const int need = g_conv_out_bufs == 2 ? (MT == 2 ? 3 : 2)
+                                          : (num_kb + 1 < 4 ? num_kb + 1 : 4);
+    if (st2 >= need && st2 >= (MT == 2 ? 3 : 2) &&
+        Cfg::smem_bytes(st2, p.has_add, p.has_mask, p.out_f32, 2) <= kSmemBudget + 1024)
+      q.out_bufs = 2;
+  }
+  q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32, q.out_bufs);
   q.m_tiles = ceil_div(p.M, (CG2 ? 2 : MT) * kBM);
   q.n_tiles = p.Cout / BN;
-  const int smem = Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32);
+  const int smem = Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32, q.out_bufs);
   if (CG2) {
     // per_n CTA PAIRS per N tile, launched as clusters of two (ranks 2i, 2i+1 share a TPC)
     cudaLaunchConfig_t cfg{};
@@ -1478,7 +1547,38 @@ static int g_conv_halo = conv_halo_default();
 
 static int halo_bn(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 64 : 32); }
 
-static bool use_halo(const acnn_conv_geom& g, int np, bool out_f32, bool has_bias) {
+// Shared-memory plan of the halo kernel for one problem (a pure function of the shape).
+struct HaloPlan {
+  int a_stages, b_slots, stationary, out_bufs, smem;
+};
+static HaloPlan halo_plan(int bn, int cw, int Cin, bool has_add, bool has_mask) {
+  HaloPlan h;
+  const int row_b = cw * 2;
+  const int a_stage = (kHaloH * kHaloW * row_b + 1023) / 1024 * 1024;
+  const int b_tile = bn * row_b;
+  const int tile = kBM * bn * 2;
+  const int nchunks = Cin / cw;
+  // two output staging tiles where they are cheap (N <= 64: 8 / 16 KiB)
+  h.out_bufs = bn <= 64 ? 2 : 1;
+  const int fixed = 1024 + tile * (h.out_bufs + (has_add ? 1 : 0) + (has_mask ? 1 : 0));
+  h.a_stages = 3;
+  h.b_slots = (kSmemBudget - fixed - h.a_stages * a_stage) / b_tile;
+  if (h.b_slots < nchunks * 9) {         // one A stage fewer if that makes the slab stationary
+    const int b2 = (kSmemBudget - fixed - 2 * a_stage) / b_tile;
+    if (b2 >= nchunks * 9 || h.b_slots < 3) {
+      h.a_stages = 2;
+      h.b_slots = b2;
+    }
+  }
+  if (h.b_slots > kHaloMaxB) h.b_slots = kHaloMaxB;
+  h.stationary = (h.b_slots >= 2 && nchunks * 9 <= h.b_slots) ? 1 : 0;
+  if (h.stationary) h.b_slots = nchunks * 9;
+  h.smem = fixed + h.a_stages * a_stage + h.b_slots * b_tile;
+  return h;
+}
+
+static bool use_halo(const acnn_conv_geom& g, int np, bool out_f32, bool has_bias, bool has_add,
+                     bool has_mask) {
   if (g_conv_halo <= 0) return false;
   const bool applies = g.kh == 3 && g.kw == 3 && g.stride == 1 && g.pad_h_lo == 1 &&
                        g.pad_h_hi == 1 && g.pad_w_lo == 1 && g.pad_w_hi == 1 &&
@@ -1487,7 +1587,10 @@ static bool use_halo(const acnn_conv_geom& g, int np, bool out_f32, bool has_bia
                        g.Cout % 32 == 0;
   if (!applies) return false;
   if (g_conv_halo >= 2) return true;
-  return g.Cout <= 128 && g.H >= 56;
+  // mode 1: only where the weight slab of an N tile stays in shared memory (otherwise the weight
+  // stream replaces the im2col re-reads as the ingest bound) and the 16 x 8 patches waste little
+  const HaloPlan h = halo_plan(halo_bn(g.Cout), g.Cin % 64 == 0 ? 64 : 32, g.Cin, has_add, has_mask);
+  return h.stationary && g.H >= 56;
 }
 
 // CTAs per N tile of the halo kernel's persistent grid (= partial statistics rows)
@@ -1543,18 +1646,13 @@ static int launch_conv_halo(const acnn_conv_geom& g, const void* x, const void* 
   p.has_add = add_src != nullptr;
   p.has_mask = mask_src != nullptr;
   const int nchunks = g.Cin / CW;
-  const int fixed = 1024 + Cfg::kTileBytes * (1 + p.has_add + p.has_mask);
-  p.a_stages = 3;
-  p.b_slots = (kSmemBudget - fixed - p.a_stages * Cfg::kAStage) / Cfg::kBTile;
-  if (p.b_slots < 3) {
-    p.a_stages = 2;
-    p.b_slots = (kSmemBudget - fixed - p.a_stages * Cfg::kAStage) / Cfg::kBTile;
-  }
-  if (p.b_slots > kHaloMaxB) p.b_slots = kHaloMaxB;
+  const HaloPlan hp = halo_plan(BN, CW, g.Cin, p.has_add != 0, p.has_mask != 0);
+  p.out_bufs = hp.out_bufs;
+  p.a_stages = hp.a_stages;
+  p.b_slots = hp.b_slots;
+  p.stationary = hp.stationary;
   ACNN_REQUIRE(p.b_slots >= 2, "conv (halo): shared memory does not fit");
-  p.stationary = nchunks * 9 <= p.b_slots ? 1 : 0;
-  if (p.stationary) p.b_slots = nchunks * 9;
-  const int smem = fixed + p.a_stages * Cfg::kAStage + p.b_slots * Cfg::kBTile;
+  const int smem = hp.smem;
   CUtensorMap tmA, tmB, tmC, tmAdd, tmMask;
   int rc = make_map_4d(&tmA, x, g.Cin, g.W, g.H, g.B, CW, kHaloW, kHaloH);
   if (rc) return rc;
@@ -1612,7 +1710,8 @@ static int conv_gemm_host(const acnn_conv_geom& g, const void* x, const void* w,
                "conv: padding / filter exceed the TMA im2col corner range");
   int rc = load_driver_fns();
   if (rc) return rc;
-  if (use_halo(g, precision ? 3 : 1, out_f32 != 0, bias != nullptr))
+  if (use_halo(g, precision ? 3 : 1, out_f32 != 0, bias != nullptr, add_src != nullptr,
+               mask_src != nullptr))
     return conv_halo_host(g, x, w, y, ch_part, add_src, mask_src, stream);
 
   const bool plain = is_plain(g);
@@ -1870,6 +1969,12 @@ int acnn_set_conv_halo(int mode) {
   return prev;
 }
 
+int acnn_set_conv_out_bufs(int mode) {
+  const int prev = acnn::g_conv_out_bufs;
+  acnn::g_conv_out_bufs = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return prev;
+}
+
 int acnn_set_wgrad_overhead_stages(int stages) {
   const int prev = acnn::g_wgrad_overhead_stages;
   acnn::g_wgrad_overhead_stages = stages < 0 ? 0 : stages;
@@ -1886,7 +1991,7 @@ int acnn_conv_stats_parts(const acnn_conv_geom* g) {
   if (!g) return 0;
   int Ho, Wo;
   if (!acnn::out_hw(*g, &Ho, &Wo) || g->Cout % 32 != 0) return 0;
-  if (acnn::use_halo(*g, 1, false, false)) return acnn::halo_per_n(*g);
+  if (acnn::use_halo(*g, 1, false, false, false, false)) return acnn::halo_per_n(*g);
   return acnn::conv_tiling(g->B * Ho * Wo, g->Cout, g->kh * g->kw * g->Cin,
                            acnn::chunk_width(g->Cin), false, false, false, 1).parts;
 }

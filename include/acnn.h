@@ -60,6 +60,11 @@ int acnn_set_conv_cta_pairs(int on);
  * rows); 2 = wherever it applies.  Same results up to fp32 summation order of the statistics;
  * changes acnn_conv_stats_parts().  Returns the previous setting. */
 int acnn_set_conv_halo(int mode);
+/* Output staging buffers of the conv GEMM epilogue (no effect on results): 0 (default) = a second
+ * half-tile buffer where the shared-memory ring stays deep enough without its bytes (all of K in
+ * flight or >= 4 stages), so that a half tile's TMA store drains under the next half's TMEM reads;
+ * 1 = always one buffer; 2 = two wherever they fit.  Returns the previous setting. */
+int acnn_set_conv_out_bufs(int mode);
 /* Tuning knob of the wgrad launcher (no effect on results beyond fp32 summation order): pixels
  * (GEMM K) per pipeline stage, 64 or 128 (N tile <= 128 only); 0 = choose per problem (default).
  * Returns the previous setting. */
