@@ -1370,12 +1370,13 @@ struct ConvMaps {
   CUtensorMap a[3], b[3], c, add, mask;
 };
 
-// output staging buffers of the conv GEMM epilogue: 0 = per problem (default), 1 = always one,
-// 2 = two wherever shared memory allows (acnn_set_conv_out_bufs; ACNN_CONV_OUT_BUFS sets the
-// initial value)
+// output staging buffers of the conv GEMM epilogue: 0 = two where the ring stays deep, 1 = always
+// one (default: the interleaved A/B of the c3 step shows no difference beyond noise -- 23.76 / 23.69
+// / 23.86 ms for 1 / 0 / 2, profiles/r02_exp_ab.txt -- so the deeper ring is kept), 2 = two wherever
+// shared memory allows (acnn_set_conv_out_bufs; ACNN_CONV_OUT_BUFS sets the initial value)
 static int conv_out_bufs_default() {
   const char* e = getenv("ACNN_CONV_OUT_BUFS");
-  return e ? (e[0] - '0') : 0;
+  return e ? (e[0] - '0') : 1;
 }
 static int g_conv_out_bufs = conv_out_bufs_default();
 
@@ -1536,12 +1537,11 @@ static int64_t input_elems(const acnn_conv_geom& g) {
 }
 
 // ---- halo (im2col-free 3x3) kernel: eligibility, tiling, launch --------------------------------
-// 0: off; 1 (default): where measured to pay (N <= 128 and images of >= 56 rows: patches of 16 x 8
-// waste <= 12.5 % of a 56 x 56 image, 27 % of 28 x 28); 2: wherever the kernel applies
+// 0: off; 1 (default): where measured to pay (use_halo below); 2: wherever the kernel applies
 // (acnn_set_conv_halo; ACNN_CONV_HALO=0|1|2 sets the initial value)
 static int conv_halo_default() {
   const char* e = getenv("ACNN_CONV_HALO");
-  return e ? (e[0] - '0') : 0;
+  return e ? (e[0] - '0') : 1;
 }
 static int g_conv_halo = conv_halo_default();
 
@@ -1587,10 +1587,13 @@ static bool use_halo(const acnn_conv_geom& g, int np, bool out_f32, bool has_bia
                        g.Cout % 32 == 0;
   if (!applies) return false;
   if (g_conv_halo >= 2) return true;
-  // mode 1: only where the weight slab of an N tile stays in shared memory (otherwise the weight
-  // stream replaces the im2col re-reads as the ingest bound) and the 16 x 8 patches waste little
+  // mode 1 = where measured to pay (profiles/r02_exp_halo_layers.txt): the weight slab of an N tile
+  // stays in shared memory (otherwise the weight stream replaces the im2col re-reads as the ingest
+  // bound: 56x56 128->64 dgrad 0.163 -> 0.244 ms), full 64-channel chunks (32-channel chunks halve
+  // the tensor work per tile under the same epilogue: slower), and images of >= 56 rows (16 x 8
+  // patches waste <= 12.5 % of a 56 x 56 image, 27 % of 28 x 28)
   const HaloPlan h = halo_plan(halo_bn(g.Cout), g.Cin % 64 == 0 ? 64 : 32, g.Cin, has_add, has_mask);
-  return h.stationary && g.H >= 56;
+  return h.stationary && g.Cin % 64 == 0 && g.H >= 56;
 }
 
 // CTAs per N tile of the halo kernel's persistent grid (= partial statistics rows)

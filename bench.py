@@ -159,9 +159,41 @@ def effective_cores():
     return max(1, min(n, 64))
 
 
-def cpu_reference(cfg_name, steps, warmup, hw=224):
+def _cpu_probe(cfg, model, vs, batch, hw):
+    """Seconds of one CPU step of the configuration at `batch` (its second run: the first pays
+    one-time initialisation)."""
+    import torch
+    from oracle import model as M, tf_ops as T
+    x, lab = synth_batch(2 * batch if cfg["kind"] == "train" else batch, hw, 1234)
+    onehot = torch.nn.functional.one_hot(lab.long(), 1001).float()
+    t = 0.0
+    for _ in range(2):
+        t0 = time.perf_counter()
+        if cfg["kind"] == "train":
+            names = [n for n in vs.vars if vs.trainable[n]]
+            mom = {n: torch.zeros_like(vs.vars[n]) for n in names}
+            backup = {n: vs.vars[n].clone() for n in vs.vars}
+            lam = torch.full((batch,), 0.5)
+            xm, ym = T.mixup(x, onehot, lam, keep_batch_size=False)
+            M.train_step(model, vs, mom, xm, ym, lr=0.0, momentum=0.9, label_smoothing=0.1,
+                         weight_decay=1e-4)
+            for n in backup:
+                vs.vars[n] = backup[n]
+        else:
+            with torch.no_grad():
+                if cfg["kind"] == "eval":
+                    M.forward(model, vs, x, training=False)
+                else:
+                    M.loss_fn(model, vs, x, onehot, training=True, label_smoothing=0.1,
+                              weight_decay=1e-4)
+        t = time.perf_counter() - t0
+    return t
+
+
+def cpu_reference(cfg_name, steps, warmup, hw=224, budget_s=None):
     """The reference's TF1 CPU path, restated (oracle/model.py): same workload, host cores, on a
-    bounded sample (small batch, few steps)."""
+    bounded sample (small batch).  With `budget_s` a probe step picks the largest batch of
+    8 / 4 / 2 / 1 for which warmup + steps steps fit the budget."""
     import torch
     from oracle import model as M, tf_ops as T
     cfg = CONFIGS[cfg_name]
@@ -171,6 +203,11 @@ def cpu_reference(cfg_name, steps, warmup, hw=224):
     flags = cfg["model"]
     model, vs = M.build(seed=42, input_hw=64, **flags)
     batch = {"c1": 1, "c2": 8, "c3": 8, "c5": 4}[cfg_name]
+    if budget_s is not None and batch > 1:
+        t_probe = _cpu_probe(cfg, model, vs, batch, hw)      # also pages the code / weights in
+        while batch > 1 and t_probe * (steps + warmup) > budget_s:
+            batch //= 2
+            t_probe /= 2.0
     times = []
     if cfg["kind"] == "train":
         names = [n for n in vs.vars if vs.trainable[n]]
@@ -211,7 +248,8 @@ def cpu_baseline_subprocess(cfg_name, timeout_s=240):
     """Times the oracle in a child process (bounded: the bench line must not hang on a slow host)."""
     try:
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
-                            "--steps", "2", "--config", cfg_name], capture_output=True, text=True,
+                            "--steps", "2", "--warmup", "1", "--config", cfg_name],
+                           capture_output=True, text=True,
                            timeout=timeout_s)
         for ln in reversed(r.stdout.strip().splitlines()):
             if ln.startswith("{"):
@@ -224,20 +262,26 @@ def cpu_baseline_subprocess(cfg_name, timeout_s=240):
 
 
 def run_reference_arm(args):
+    """`--impl reference`: the reference's CPU path (oracle port) on the host cores, EXACTLY
+    --steps K timed steps after --warmup W, on the b200 arm's configuration / metric / unit; each
+    step is a bounded sample of the workload (a small CPU batch, shrunk further if a probe step says
+    K + W steps would not end within a few minutes).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warmup = 1
-    cb, sec, batch = cpu_reference(args.config, steps, warmup)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cb, sec, batch = cpu_reference(args.config, steps, warmup, budget_s=150.0)
     cfg = CONFIGS[args.config]
+    world = args.gpus
+    B = args.batch or cfg["batch"]
     line = {
         "impl": "reference", "metric": cfg["metric"], "value": cb["value"], "unit": "images/sec",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": cfg["workload"] + ", CPU batch %d" % batch, "name": args.config,
-                   "note": "reference = torch-CPU restatement of the TF1 path (oracle port)"},
+        "config": {"workload": cfg["workload"], "name": args.config, "per_gpu_batch": B,
+                   "global_batch": B * world, "parallelism": "dp%d" % world,
+                   "sample": "CPU batch %d per step (bounded sample of the workload)" % batch},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},

@@ -56,14 +56,16 @@ int acnn_set_conv_cta_pairs(int on);
 /* 3x3 / stride 1 / pad 1 convolutions (fprop and dgrad) on the im2col-free "halo" kernel: a CTA tile
  * is a 16 x 8 patch of output pixels, one 18 x 10 halo tile per 64-channel chunk is loaded once and
  * the nine filter taps read shifted windows of it through the tensor core's shared-memory
- * descriptors.  0 = off (im2col TMA kernel everywhere); 1 (default) = where it pays (N <= 128, >= 56
- * rows); 2 = wherever it applies.  Same results up to fp32 summation order of the statistics;
- * changes acnn_conv_stats_parts().  Returns the previous setting. */
+ * descriptors.  0 = off (im2col TMA kernel everywhere); 1 (default) = where it pays (the weight slab
+ * of an N tile fits shared memory next to the halo ring, Cin a multiple of 64, >= 56 rows);
+ * 2 = wherever it applies.  Same results up to fp32 summation order of the statistics; changes
+ * acnn_conv_stats_parts().  Returns the previous setting. */
 int acnn_set_conv_halo(int mode);
-/* Output staging buffers of the conv GEMM epilogue (no effect on results): 0 (default) = a second
- * half-tile buffer where the shared-memory ring stays deep enough without its bytes (all of K in
- * flight or >= 4 stages), so that a half tile's TMA store drains under the next half's TMEM reads;
- * 1 = always one buffer; 2 = two wherever they fit.  Returns the previous setting. */
+/* Output staging buffers of the conv GEMM epilogue (no effect on results): 1 (default) = one half-
+ * tile buffer; 0 = a second one where the shared-memory ring stays deep enough without its bytes
+ * (all of K in flight or >= 4 stages), so that a half tile's TMA store drains under the next
+ * half's TMEM reads (measured: no difference on the c3 step); 2 = two wherever they fit.  Returns
+ * the previous setting. */
 int acnn_set_conv_out_bufs(int mode);
 /* Tuning knob of the wgrad launcher (no effect on results beyond fp32 summation order): pixels
  * (GEMM K) per pipeline stage, 64 or 128 (N tile <= 128 only); 0 = choose per problem (default).
