@@ -743,6 +743,7 @@ struct HaloParams {
   int m_tiles;            // B * ph * pw
   int a_stages, b_slots, stationary;
   int out_bufs;           // 1 or 2 output staging tiles (2: the TMA store of tile i overlaps tile i+1)
+  int split_epi;          // N <= 64: two independent 4-warp epilogue groups alternate tiles
   float* ch_part;
   int has_add, has_mask;
 };
@@ -757,6 +758,32 @@ struct HaloCfg {
   static constexpr int kTileBytes = kBM * BN * 2;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
   static_assert(BN <= 128 && kBTile % 512 == 0, "halo kernel: N tile <= 128");
+};
+
+// Patch coordinates of the tiles first, first + step, ... advanced without divisions (three integer
+// divisions per tile sat on the epilogue's critical path).
+struct PatchIter {
+  int img, row, col;          // image, patch row / column inside the image
+  int d_img, d_row, d_col;
+  int ph, pw;
+  __device__ __forceinline__ PatchIter(int first, int step, int ph_, int pw_) : ph(ph_), pw(pw_) {
+    const int tpi = ph * pw;
+    img = first / tpi;
+    int rem = first - img * tpi;
+    row = rem / pw;
+    col = rem - row * pw;
+    d_img = step / tpi;
+    rem = step - d_img * tpi;
+    d_row = rem / pw;
+    d_col = rem - d_row * pw;
+  }
+  __device__ __forceinline__ void next() {
+    col += d_col;
+    if (col >= pw) { col -= pw; ++row; }
+    row += d_row;
+    if (row >= ph) { row -= ph; ++img; }
+    img += d_img;
+  }
 };
 
 template <int BN, int CW>
@@ -778,15 +805,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint64_t a_full[4], a_empty[4];
   __shared__ uint64_t b_full[kHaloMaxB], b_empty[kHaloMaxB];
   __shared__ uint64_t tfull_bar[2], tempty_bar[2];
-  __shared__ uint64_t aux_bar;
+  __shared__ uint64_t aux_bars[2];
   __shared__ uint32_t tmem_base_smem;
+  uint64_t& aux_bar = aux_bars[0];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int AS = p.a_stages, NB = p.b_slots;
   uint8_t* s_out0 = smem + AS * Cfg::kAStage + NB * Cfg::kBTile;
   uint8_t* s_add = s_out0 + p.out_bufs * Cfg::kTileBytes;
-  uint8_t* s_mask = s_add + (p.has_add ? Cfg::kTileBytes : 0);
+  uint8_t* s_mask = s_add + (p.has_add ? (p.split_epi ? 2 : 1) * Cfg::kTileBytes : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -816,7 +844,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 1);
     }
-    mbar_init(&aux_bar, 1);
+    mbar_init(&aux_bars[0], 1);
+    mbar_init(&aux_bars[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_smem);
@@ -938,167 +967,242 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     const int egrp = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;                 // TMEM lane = patch pixel (r/8, r%8)
-    const bool leader = (warp == 2 && lane == 0);
     const bool stats = p.ch_part != nullptr;
     const bool has_aux = p.has_add || p.has_mask;
     const int swz = (kSubRowB == 128) ? (r & 7) : ((r >> 1) & 3);
     constexpr int kNChunk = BN / 8;
-    constexpr int kStatThreads = (BN == 32) ? 128 : kEpiThreads;
-    constexpr int kNRg = kStatThreads / kNChunk;
-    const int st_t = threadIdx.x - 64;
-    const bool st_on = st_t < kStatThreads;
-    const int st_chunk = st_t % kNChunk, st_rg = st_t / kNChunk;
     float acc_s[8], acc_q[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc_s[e] = acc_q[e] = 0.f;
     uint32_t aux_n = 0;
-    auto tile_origin = [&](int it, int* img, int* h0, int* w0) {
-      const int tile = m_first + it * m_step;
-      *img = tile / tpi;
-      const int rem = tile - *img * tpi;
-      *h0 = (rem / p.pw) * kPatchH;
-      *w0 = (rem % p.pw) * kPatchW;
-    };
-    auto issue_aux = [&](int it) {
-      int img, h0, w0;
-      tile_origin(it, &img, &h0, &w0);
-      mbar_expect_tx(&aux_bar, (p.has_add ? Cfg::kTileBytes : 0) +
-                                   (p.has_mask ? Cfg::kTileBytes : 0));
+    // one 32-column chunk of the accumulator: TMEM -> (+add) (x mask) -> bf16 -> swizzled staging
+    auto drain_chunk = [&](uint32_t taddr, int c, const uint8_t* sa_, const uint8_t* sm_,
+                           uint8_t* so_) {
+      uint32_t v[32];
+      tmem_ld_32x32(taddr, v);
+      tmem_ld_wait();
+      float f[32];
 #pragma unroll
-      for (int sub = 0; sub < kNSub; ++sub) {
-        if (p.has_add)
-          tma_load_4d_tile_a(smem_u32(s_add + sub * kSubBytes), &tmAdd, smem_u32(&aux_bar),
-                             n0 + sub * kSubW, w0, h0, img);
-        if (p.has_mask)
-          tma_load_4d_tile_a(smem_u32(s_mask + sub * kSubBytes), &tmMask, smem_u32(&aux_bar),
-                             n0 + sub * kSubW, w0, h0, img);
-      }
-    };
-    if (leader && has_aux && my_tiles > 0) issue_aux(0);
-
-    for (int it = 0; it < my_tiles; ++it) {
-      const int acc = it & 1;
-      int img, h0, w0;
-      tile_origin(it, &img, &h0, &w0);
-      // staging buffer free again: with two buffers only the store issued two tiles ago must have
-      // finished reading (the previous tile's store keeps draining under this tile's TMEM reads)
-      uint8_t* s_out = s_out0 + ((p.out_bufs == 2 && (it & 1)) ? Cfg::kTileBytes : 0);
-      if (leader) {
-        if (p.out_bufs == 2) tma_store_wait_read1();
-        else tma_store_wait_read();
-      }
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
-      tc_fence_after();
-      if (has_aux) {
-        mbar_wait(&aux_bar, aux_n & 1);
-        ++aux_n;
-      }
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+      const int sub = (c * 32) / kSubW;
+      const int j0 = ((c * 32) % kSubW) / 8;
+      const int soff = sub * kSubBytes + r * kSubRowB;
+      if (p.has_add) {
 #pragma unroll
-      for (int c2 = 0; c2 < (BN / 32 + 1) / 2; ++c2) {
-        const int c = c2 * 2 + egrp;
-        if (c >= BN / 32) break;                       // warp-uniform
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        float f[32];
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sa_ + soff + (((j0 + q) ^ swz) << 4));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-        const int sub = (c * 32) / kSubW;
-        const int j0 = ((c * 32) % kSubW) / 8;
-        const int soff = sub * kSubBytes + r * kSubRowB;
-        if (p.has_add) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = *reinterpret_cast<const uint4*>(s_add + soff + (((j0 + q) ^ swz) << 4));
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
-              f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
-            }
+          for (int e = 0; e < 4; ++e) {
+            f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
+            f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
           }
         }
-        if (p.has_mask) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 u = *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
-            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lo = __uint_as_float(w4[e] << 16);
-              const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-              if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
-              if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
-            }
-          }
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(s_out + soff + (((j0 + q) ^ swz) << 4)) =
-              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
       }
-      tc_fence_before();
-      fence_proxy_async();
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      if (leader) {
-        mbar_arrive(&tempty_bar[acc]);
+      if (p.has_mask) {
 #pragma unroll
-        for (int sub = 0; sub < kNSub; ++sub)
-          tma_store_4d(&tmC, s_out + sub * kSubBytes, n0 + sub * kSubW, w0, h0, img);
-        tma_store_commit();
-        if (has_aux && it + 1 < my_tiles) issue_aux(it + 1);
-      }
-      if (stats && st_on) {
-        // column sums of the tile as stored (bf16-rounded), patch pixels outside the image excluded
-        // (they were computed from real neighbours and are clipped by the store)
-        const int sub = st_chunk / (kSubW / 8), jj = st_chunk % (kSubW / 8);
-#pragma unroll 4
-        for (int i = 0; i < kBM / kNRg; ++i) {
-          const int rr = st_rg + i * kNRg;
-          if (h0 + (rr >> 3) >= p.H || w0 + (rr & 7) >= p.W) continue;
-          const int sw = (kSubRowB == 128) ? (rr & 7) : ((rr >> 1) & 3);
-          const uint4 u = *reinterpret_cast<const uint4*>(s_out + sub * kSubBytes + rr * kSubRowB +
-                                                          ((jj ^ sw) << 4));
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sm_ + soff + (((j0 + q) ^ swz) << 4));
           const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float lo = __uint_as_float(w4[e] << 16);
             const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-            acc_s[2 * e] += lo;
-            acc_q[2 * e] = fmaf(lo, lo, acc_q[2 * e]);
-            acc_s[2 * e + 1] += hi;
-            acc_q[2 * e + 1] = fmaf(hi, hi, acc_q[2 * e + 1]);
+            if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
+            if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
           }
         }
       }
-    }
-    if (leader) tma_store_wait_all();
-    if (stats && my_tiles > 0) {
-      float* red_sum = reinterpret_cast<float*>(s_out0);
-      float* red_sq = red_sum + kNRg * BN;
-      static_assert(2 * kNRg * BN * 4 <= Cfg::kTileBytes, "staging buffer too small for stats");
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      if (st_on) {
+      uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          red_sum[st_rg * BN + st_chunk * 8 + e] = acc_s[e];
-          red_sq[st_rg * BN + st_chunk * 8 + e] = acc_q[e];
+      for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(so_ + soff + (((j0 + q) ^ swz) << 4)) =
+            make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+    };
+    // column sums of the tile as stored (bf16-rounded): this thread's 16-byte chunk `chunk` over the
+    // rows rg, rg + nrg, ...; patch pixels outside the image excluded (they were computed from real
+    // neighbours and are clipped by the store)
+    auto stat_rows = [&](const uint8_t* so_, int chunk, int rg, int nrg, int h0, int w0) {
+      const int sub = chunk / (kSubW / 8), jj = chunk % (kSubW / 8);
+#pragma unroll 4
+      for (int rr = rg; rr < kBM; rr += nrg) {
+        if (h0 + (rr >> 3) >= p.H || w0 + (rr & 7) >= p.W) continue;
+        const int sw = (kSubRowB == 128) ? (rr & 7) : ((rr >> 1) & 3);
+        const uint4 u = *reinterpret_cast<const uint4*>(so_ + sub * kSubBytes + rr * kSubRowB +
+                                                        ((jj ^ sw) << 4));
+        const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = __uint_as_float(w4[e] << 16);
+          const float hi = __uint_as_float(w4[e] & 0xffff0000u);
+          acc_s[2 * e] += lo;
+          acc_q[2 * e] = fmaf(lo, lo, acc_q[2 * e]);
+          acc_s[2 * e + 1] += hi;
+          acc_q[2 * e + 1] = fmaf(hi, hi, acc_q[2 * e + 1]);
         }
       }
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      for (int col = st_t; col < BN; col += kEpiThreads) {
-        float ss = 0.f, qq = 0.f;
-        for (int g2 = 0; g2 < kNRg; ++g2) {
-          ss += red_sum[g2 * BN + col];
-          qq += red_sq[g2 * BN + col];
+    };
+    auto issue_aux = [&](uint64_t* bar, uint8_t* sa_, uint8_t* sm_, int img, int h0, int w0) {
+      mbar_expect_tx(bar, (p.has_add ? Cfg::kTileBytes : 0) + (p.has_mask ? Cfg::kTileBytes : 0));
+#pragma unroll
+      for (int sub = 0; sub < kNSub; ++sub) {
+        if (p.has_add)
+          tma_load_4d_tile_a(smem_u32(sa_ + sub * kSubBytes), &tmAdd, smem_u32(bar),
+                             n0 + sub * kSubW, w0, h0, img);
+        if (p.has_mask)
+          tma_load_4d_tile_a(smem_u32(sm_ + sub * kSubBytes), &tmMask, smem_u32(bar),
+                             n0 + sub * kSubW, w0, h0, img);
+      }
+    };
+
+    if (BN <= 64 && p.split_epi) {
+      // ---- two independent 4-warp groups: group g drains accumulator g of the tiles g, g + 2, ...
+      // with its own staging / aux buffers, named barrier and TMA store queue, so the per-tile chain
+      // (barrier -> TMEM load -> convert -> stage -> barrier -> store -> statistics) of one tile
+      // overlaps the next tile's: the chain, not the tensor pipe, paced the N <= 64 tiles
+      const int gt = threadIdx.x - 64 - egrp * 128;      // thread index inside the group
+      const bool gleader = gt == 0;
+      uint8_t* so_ = s_out0 + egrp * Cfg::kTileBytes;
+      uint8_t* sa_ = s_add + egrp * Cfg::kTileBytes;
+      uint8_t* sm_ = s_mask + egrp * Cfg::kTileBytes;
+      uint64_t* abar = &aux_bars[egrp];
+      constexpr int kNRgS = 128 / kNChunk;               // row groups inside one epilogue group
+      const int st_chunk = gt % kNChunk, st_rg = gt / kNChunk;
+      PatchIter pi(m_first + egrp * m_step, 2 * m_step, p.ph, p.pw);
+      if (gleader && has_aux && egrp < my_tiles)
+        issue_aux(abar, sa_, sm_, pi.img, pi.row * kPatchH, pi.col * kPatchW);
+      for (int it = egrp; it < my_tiles; it += 2) {
+        const int img = pi.img, h0 = pi.row * kPatchH, w0 = pi.col * kPatchW;
+        pi.next();
+        if (gleader) tma_store_wait_read();              // this group's previous store has read so_
+        if (egrp == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+        mbar_wait(&tfull_bar[egrp], (it >> 1) & 1);
+        tc_fence_after();
+        if (has_aux) {
+          mbar_wait(abar, aux_n & 1);
+          ++aux_n;
         }
-        float* row = p.ch_part + static_cast<size_t>(m_first) * 2 * p.Cout;
-        row[n0 + col] = ss;
-        row[p.Cout + n0 + col] = qq;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c)
+          drain_chunk(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + egrp * BN + c * 32, c,
+                      sa_, sm_, so_);
+        tc_fence_before();
+        fence_proxy_async();
+        if (egrp == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+        if (gleader) {
+          mbar_arrive(&tempty_bar[egrp]);
+#pragma unroll
+          for (int sub = 0; sub < kNSub; ++sub)
+            tma_store_4d(&tmC, so_ + sub * kSubBytes, n0 + sub * kSubW, w0, h0, img);
+          tma_store_commit();
+          if (has_aux && it + 2 < my_tiles)
+            issue_aux(abar, sa_, sm_, pi.img, pi.row * kPatchH, pi.col * kPatchW);
+        }
+        if (stats) stat_rows(so_, st_chunk, st_rg, kNRgS, h0, w0);
+      }
+      if (gleader) tma_store_wait_all();
+      if (stats && my_tiles > 0) {
+        // cross-group / cross-row-group reduction in the (now idle) staging buffers
+        float* red_sum = reinterpret_cast<float*>(s_out0);
+        float* red_sq = red_sum + 2 * kNRgS * BN;
+        static_assert(BN > 64 || 2 * 2 * kNRgS * BN * 4 <= 2 * Cfg::kTileBytes,
+                      "staging buffers too small for stats");
+        asm volatile("bar.sync 3, 256;\n" ::: "memory");  // both groups' stores have drained
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          red_sum[(egrp * kNRgS + st_rg) * BN + st_chunk * 8 + e] = acc_s[e];
+          red_sq[(egrp * kNRgS + st_rg) * BN + st_chunk * 8 + e] = acc_q[e];
+        }
+        asm volatile("bar.sync 3, 256;\n" ::: "memory");
+        for (int col = threadIdx.x - 64; col < BN; col += kEpiThreads) {
+          float ss = 0.f, qq = 0.f;
+          for (int g2 = 0; g2 < 2 * kNRgS; ++g2) {
+            ss += red_sum[g2 * BN + col];
+            qq += red_sq[g2 * BN + col];
+          }
+          float* row = p.ch_part + static_cast<size_t>(m_first) * 2 * p.Cout;
+          row[n0 + col] = ss;
+          row[p.Cout + n0 + col] = qq;
+        }
+      }
+    } else {
+      // ---- all 8 warps on one tile at a time (two warps per TMEM lane quarter, alternating chunks)
+      const bool leader = (warp == 2 && lane == 0);
+      constexpr int kStatThreads = (BN == 32) ? 128 : kEpiThreads;
+      constexpr int kNRg = kStatThreads / kNChunk;
+      const int st_t = threadIdx.x - 64;
+      const bool st_on = st_t < kStatThreads;
+      const int st_chunk = st_t % kNChunk, st_rg = st_t / kNChunk;
+      PatchIter pi(m_first, m_step, p.ph, p.pw);
+      if (leader && has_aux && my_tiles > 0)
+        issue_aux(&aux_bar, s_add, s_mask, pi.img, pi.row * kPatchH, pi.col * kPatchW);
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        const int img = pi.img, h0 = pi.row * kPatchH, w0 = pi.col * kPatchW;
+        pi.next();
+        // staging buffer free again: with two buffers only the store issued two tiles ago must
+        // have finished reading (the previous tile's store drains under this tile's TMEM reads)
+        uint8_t* s_out = s_out0 + ((p.out_bufs == 2 && (it & 1)) ? Cfg::kTileBytes : 0);
+        if (leader) {
+          if (p.out_bufs == 2) tma_store_wait_read1();
+          else tma_store_wait_read();
+        }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+        tc_fence_after();
+        if (has_aux) {
+          mbar_wait(&aux_bar, aux_n & 1);
+          ++aux_n;
+        }
+#pragma unroll
+        for (int c2 = 0; c2 < (BN / 32 + 1) / 2; ++c2) {
+          const int c = c2 * 2 + egrp;
+          if (c >= BN / 32) break;                       // warp-uniform
+          drain_chunk(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, c,
+                      s_add, s_mask, s_out);
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (leader) {
+          mbar_arrive(&tempty_bar[acc]);
+#pragma unroll
+          for (int sub = 0; sub < kNSub; ++sub)
+            tma_store_4d(&tmC, s_out + sub * kSubBytes, n0 + sub * kSubW, w0, h0, img);
+          tma_store_commit();
+          if (has_aux && it + 1 < my_tiles)
+            issue_aux(&aux_bar, s_add, s_mask, pi.img, pi.row * kPatchH, pi.col * kPatchW);
+        }
+        if (stats && st_on) stat_rows(s_out, st_chunk, st_rg, kNRg, h0, w0);
+      }
+      if (leader) tma_store_wait_all();
+      if (stats && my_tiles > 0) {
+        float* red_sum = reinterpret_cast<float*>(s_out0);
+        float* red_sq = red_sum + kNRg * BN;
+        static_assert(2 * kNRg * BN * 4 <= Cfg::kTileBytes, "staging buffer too small for stats");
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (st_on) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            red_sum[st_rg * BN + st_chunk * 8 + e] = acc_s[e];
+            red_sq[st_rg * BN + st_chunk * 8 + e] = acc_q[e];
+          }
+        }
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        for (int col = st_t; col < BN; col += kEpiThreads) {
+          float ss = 0.f, qq = 0.f;
+          for (int g2 = 0; g2 < kNRg; ++g2) {
+            ss += red_sum[g2 * BN + col];
+            qq += red_sq[g2 * BN + col];
+          }
+          float* row = p.ch_part + static_cast<size_t>(m_first) * 2 * p.Cout;
+          row[n0 + col] = ss;
+          row[p.Cout + n0 + col] = qq;
+        }
       }
     }
   }
@@ -1549,8 +1653,16 @@ static int halo_bn(int Cout) { return Cout % 128 == 0 ? 128 : (Cout % 64 == 0 ? 
 
 // Shared-memory plan of the halo kernel for one problem (a pure function of the shape).
 struct HaloPlan {
-  int a_stages, b_slots, stationary, out_bufs, smem;
+  int a_stages, b_slots, stationary, out_bufs, split_epi, smem;
 };
+// 1 (default): N <= 64 tiles use two independent epilogue groups; 0: all 8 warps on one tile
+// (acnn_set_conv_halo_split; ACNN_CONV_HALO_SPLIT sets the initial value)
+static int conv_halo_split_default() {
+  const char* e = getenv("ACNN_CONV_HALO_SPLIT");
+  return e ? (e[0] - '0') : 1;
+}
+static int g_conv_halo_split = conv_halo_split_default();
+
 static HaloPlan halo_plan(int bn, int cw, int Cin, bool has_add, bool has_mask) {
   HaloPlan h;
   const int row_b = cw * 2;
@@ -1558,9 +1670,13 @@ static HaloPlan halo_plan(int bn, int cw, int Cin, bool has_add, bool has_mask) 
   const int b_tile = bn * row_b;
   const int tile = kBM * bn * 2;
   const int nchunks = Cin / cw;
-  // two output staging tiles where they are cheap (N <= 64: 8 / 16 KiB)
+  // two output staging tiles where they are cheap (N <= 64: 8 / 16 KiB); the split epilogue also
+  // doubles the add / mask staging (one set per group)
   h.out_bufs = bn <= 64 ? 2 : 1;
-  const int fixed = 1024 + tile * (h.out_bufs + (has_add ? 1 : 0) + (has_mask ? 1 : 0));
+  h.split_epi = (bn <= 64 && g_conv_halo_split) ? 1 : 0;
+  const int aux_sets = h.split_epi ? 2 : 1;
+  const int fixed =
+      1024 + tile * (h.out_bufs + (has_add ? aux_sets : 0) + (has_mask ? aux_sets : 0));
   h.a_stages = 3;
   h.b_slots = (kSmemBudget - fixed - h.a_stages * a_stage) / b_tile;
   if (h.b_slots < nchunks * 9) {         // one A stage fewer if that makes the slab stationary
@@ -1589,11 +1705,10 @@ static bool use_halo(const acnn_conv_geom& g, int np, bool out_f32, bool has_bia
   if (g_conv_halo >= 2) return true;
   // mode 1 = where measured to pay (profiles/r02_exp_halo_layers.txt): the weight slab of an N tile
   // stays in shared memory (otherwise the weight stream replaces the im2col re-reads as the ingest
-  // bound: 56x56 128->64 dgrad 0.163 -> 0.244 ms), full 64-channel chunks (32-channel chunks halve
-  // the tensor work per tile under the same epilogue: slower), and images of >= 56 rows (16 x 8
-  // patches waste <= 12.5 % of a 56 x 56 image, 27 % of 28 x 28)
+  // bound: 56x56 128->64 dgrad 0.163 -> 0.243 ms) and the images have >= 56 rows (16 x 8 patches
+  // waste <= 12.5 % of a 56 x 56 image, 27 % of 28 x 28)
   const HaloPlan h = halo_plan(halo_bn(g.Cout), g.Cin % 64 == 0 ? 64 : 32, g.Cin, has_add, has_mask);
-  return h.stationary && g.Cin % 64 == 0 && g.H >= 56;
+  return h.stationary && g.H >= 56;
 }
 
 // CTAs per N tile of the halo kernel's persistent grid (= partial statistics rows)
@@ -1651,6 +1766,7 @@ static int launch_conv_halo(const acnn_conv_geom& g, const void* x, const void* 
   const int nchunks = g.Cin / CW;
   const HaloPlan hp = halo_plan(BN, CW, g.Cin, p.has_add != 0, p.has_mask != 0);
   p.out_bufs = hp.out_bufs;
+  p.split_epi = hp.split_epi;
   p.a_stages = hp.a_stages;
   p.b_slots = hp.b_slots;
   p.stationary = hp.stationary;
@@ -1969,6 +2085,12 @@ int acnn_set_conv_mtiles(int mode) {
 int acnn_set_conv_halo(int mode) {
   const int prev = acnn::g_conv_halo;
   acnn::g_conv_halo = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return prev;
+}
+
+int acnn_set_conv_halo_split(int on) {
+  const int prev = acnn::g_conv_halo_split;
+  acnn::g_conv_halo_split = on ? 1 : 0;
   return prev;
 }
 

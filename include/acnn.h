@@ -61,6 +61,11 @@ int acnn_set_conv_cta_pairs(int on);
  * 2 = wherever it applies.  Same results up to fp32 summation order of the statistics; changes
  * acnn_conv_stats_parts().  Returns the previous setting. */
 int acnn_set_conv_halo(int mode);
+/* Halo kernel epilogue at N <= 64 (no effect on results beyond fp32 summation order of the
+ * statistics): 1 (default) = two independent 4-warp groups alternate tiles (own accumulator stage,
+ * staging buffers, named barrier and TMA store queue), 0 = all 8 warps on one tile at a time.
+ * Returns the previous setting. */
+int acnn_set_conv_halo_split(int on);
 /* Output staging buffers of the conv GEMM epilogue (no effect on results): 1 (default) = one half-
  * tile buffer; 0 = a second one where the shared-memory ring stays deep enough without its bytes
  * (all of K in flight or >= 4 stages), so that a half tile's TMA store drains under the next

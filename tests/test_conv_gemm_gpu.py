@@ -401,8 +401,16 @@ HALO_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 0], ids=["split_epilogue", "joint_epilogue"])
+def halo_split(request, lib):
+    """Both epilogue organisations of the halo kernel at N <= 64 (acnn_set_conv_halo_split)."""
+    prev = lib.acnn_set_conv_halo_split(request.param)
+    yield request.param
+    lib.acnn_set_conv_halo_split(prev)
+
+
 @pytest.mark.parametrize("case", HALO_CASES, ids=[str(c) for c in HALO_CASES])
-def test_halo_kernel_fprop_dgrad_match_oracle_and_im2col(lib, case):
+def test_halo_kernel_fprop_dgrad_match_oracle_and_im2col(lib, case, halo_split):
     """The im2col-free 3x3 kernel (acnn_set_conv_halo(2): wherever it applies) against the oracle and
     against the im2col TMA kernel (mode 0): plain + statistics, add + mask epilogue, and the dgrad
     entry point.  The two kernels add the K terms in different orders (chunk-major vs tap-major), so
