@@ -578,28 +578,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   *reinterpret_cast<const uint4*>(s_add + soff + (((j0 + q) ^ swz) << 4));
               const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
-                f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
-              }
+              for (int e = 0; e < 4; ++e)
+                bf16x2_add(f[q * 8 + e * 2 + 0], f[q * 8 + e * 2 + 1], w4[e]);
             }
           }
-          if (p.has_mask) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u =
-                  *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
-              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float lo = __uint_as_float(w4[e] << 16);
-                const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-                if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
-                if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
-              }
-            }
-          }
+          // ReLU mask of the destination tensor: 0xffff per bf16 half that is > 0, applied to the
+          // packed bf16 output below (zeroing the half == zeroing the fp32 value before rounding)
           if (p.out_f32) {
+            if (p.has_mask) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u =
+                    *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const uint32_t k2 = bf16x2_gt0_mask(w4[e]);
+                  if (!(k2 & 0xffffu)) f[q * 8 + e * 2 + 0] = 0.f;
+                  if (!(k2 >> 16)) f[q * 8 + e * 2 + 1] = 0.f;
+                }
+              }
+            }
             if (row_ok) {
               float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) +
                                                       static_cast<size_t>(row) * p.Cout + col0);
@@ -611,6 +610,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t pk[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            if (p.has_mask) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u =
+                    *reinterpret_cast<const uint4*>(s_mask + soff + (((j0 + q) ^ swz) << 4));
+                pk[q * 4 + 0] &= bf16x2_gt0_mask(u.x);
+                pk[q * 4 + 1] &= bf16x2_gt0_mask(u.y);
+                pk[q * 4 + 2] &= bf16x2_gt0_mask(u.z);
+                pk[q * 4 + 3] &= bf16x2_gt0_mask(u.w);
+              }
+            }
             // stage in the TMA swizzle layout: 16-byte piece j of row r at piece j ^ swz
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -656,14 +666,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                             rr * kRowBytes + ((jj ^ sw) << 4));
             const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lo = __uint_as_float(w4[e] << 16);
-              const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-              acc_s[hf][2 * e] += lo;
-              acc_q[hf][2 * e] = fmaf(lo, lo, acc_q[hf][2 * e]);
-              acc_s[hf][2 * e + 1] += hi;
-              acc_q[hf][2 * e + 1] = fmaf(hi, hi, acc_q[hf][2 * e + 1]);
-            }
+            for (int e = 0; e < 4; ++e)
+              bf16x2_sum_sq(acc_s[hf][2 * e], acc_q[hf][2 * e], acc_s[hf][2 * e + 1],
+                            acc_q[hf][2 * e + 1], w4[e]);
           }
         }
         if (two_out) ebuf ^= 1;
@@ -993,29 +998,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint4 u = *reinterpret_cast<const uint4*>(sa_ + soff + (((j0 + q) ^ swz) << 4));
           const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            f[q * 8 + e * 2 + 0] += __uint_as_float(w4[e] << 16);
-            f[q * 8 + e * 2 + 1] += __uint_as_float(w4[e] & 0xffff0000u);
-          }
-        }
-      }
-      if (p.has_mask) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 u = *reinterpret_cast<const uint4*>(sm_ + soff + (((j0 + q) ^ swz) << 4));
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float lo = __uint_as_float(w4[e] << 16);
-            const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-            if (!(lo > 0.f)) f[q * 8 + e * 2 + 0] = 0.f;
-            if (!(hi > 0.f)) f[q * 8 + e * 2 + 1] = 0.f;
-          }
+          for (int e = 0; e < 4; ++e)
+            bf16x2_add(f[q * 8 + e * 2 + 0], f[q * 8 + e * 2 + 1], w4[e]);
         }
       }
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+      if (p.has_mask) {        // ReLU mask of the destination tensor, applied to the packed halves
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 u = *reinterpret_cast<const uint4*>(sm_ + soff + (((j0 + q) ^ swz) << 4));
+          pk[q * 4 + 0] &= bf16x2_gt0_mask(u.x);
+          pk[q * 4 + 1] &= bf16x2_gt0_mask(u.y);
+          pk[q * 4 + 2] &= bf16x2_gt0_mask(u.z);
+          pk[q * 4 + 3] &= bf16x2_gt0_mask(u.w);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         *reinterpret_cast<uint4*>(so_ + soff + (((j0 + q) ^ swz) << 4)) =
@@ -1034,14 +1033,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                         ((jj ^ sw) << 4));
         const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float lo = __uint_as_float(w4[e] << 16);
-          const float hi = __uint_as_float(w4[e] & 0xffff0000u);
-          acc_s[2 * e] += lo;
-          acc_q[2 * e] = fmaf(lo, lo, acc_q[2 * e]);
-          acc_s[2 * e + 1] += hi;
-          acc_q[2 * e + 1] = fmaf(hi, hi, acc_q[2 * e + 1]);
-        }
+        for (int e = 0; e < 4; ++e)
+          bf16x2_sum_sq(acc_s[2 * e], acc_q[2 * e], acc_s[2 * e + 1], acc_q[2 * e + 1], w4[e]);
       }
     };
     auto issue_aux = [&](uint64_t* bar, uint8_t* sa_, uint8_t* sm_, int img, int h0, int w0) {

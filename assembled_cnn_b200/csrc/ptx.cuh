@@ -280,6 +280,38 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n, bool a_mn_major, b
          | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
+// Mixed-precision epilogue arithmetic on packed bf16 pairs (sm_100: FHADD.BF16 / FHFMA.BF16 /
+// HSET2.BF16_V2 -- one instruction per element where unpack + FADD / FFMA / FSETP + FSEL took two to
+// three).  Results are bit-identical to unpacking to fp32 first: the bf16 operand converts exactly
+// and the fp32 add / fma rounds once.
+// c0 += lo(pair), c1 += hi(pair)
+__device__ __forceinline__ void bf16x2_add(float& c0, float& c1, uint32_t pair) {
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "add.f32.bf16 %0, lo, %0;\n\t"
+      "add.f32.bf16 %1, hi, %1;\n\t}\n"
+      : "+f"(c0), "+f"(c1)
+      : "r"(pair));
+}
+// (s0, q0) += (lo, lo^2), (s1, q1) += (hi, hi^2)
+__device__ __forceinline__ void bf16x2_sum_sq(float& s0, float& q0, float& s1, float& q1,
+                                              uint32_t pair) {
+  asm("{\n\t.reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %4;\n\t"
+      "add.f32.bf16 %0, lo, %0;\n\t"
+      "fma.rn.f32.bf16 %1, lo, lo, %1;\n\t"
+      "add.f32.bf16 %2, hi, %2;\n\t"
+      "fma.rn.f32.bf16 %3, hi, hi, %3;\n\t}\n"
+      : "+f"(s0), "+f"(q0), "+f"(s1), "+f"(q1)
+      : "r"(pair));
+}
+// 0xffff in each half whose bf16 value is > 0 (false for -0, 0, NaN), else 0
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t pair) {
+  uint32_t m;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;\n" : "=r"(m) : "r"(pair), "r"(0u));
+  return m;
+}
+
 __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
