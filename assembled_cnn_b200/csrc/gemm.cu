@@ -145,6 +145,8 @@ struct ConvGemmParams {
   int has_add, has_mask;
   int out_f32;
   int out_bufs;     // 1 or 2 output staging half tiles (2: a half's TMA store drains under the next)
+  int split_epi;    // two independent 4-warp epilogue groups alternate tiles (implies out_bufs = 2
+                    // and two sets of add / mask staging tiles)
 };
 
 constexpr int kBM = 128;        // output pixels per CTA tile == UMMA M == TMEM lanes
@@ -171,11 +173,11 @@ static inline int fprop_stage_bytes(int bn, int mt, int np, bool pair = false) {
   return np * (mt * kBM * kStageK * 2 + (pair ? bn / 2 : bn) * kStageK * 2);
 }
 static inline int fprop_stages(int bn, int mt, int np, bool has_add, bool has_mask, bool out_f32,
-                               bool pair = false, int out_bufs = 1) {
+                               bool pair = false, int out_bufs = 1, int aux_sets = 1) {
   const int half_n = bn > 128 ? 128 : bn;
   const int tile = kBM * half_n * 2;
-  const int fixed =
-      1024 + (out_f32 ? 0 : out_bufs * tile) + (has_add ? tile : 0) + (has_mask ? tile : 0);
+  const int fixed = 1024 + (out_f32 ? 0 : out_bufs * tile) + (has_add ? aux_sets * tile : 0) +
+                    (has_mask ? aux_sets * tile : 0);
   int st = (kSmemBudget - fixed) / fprop_stage_bytes(bn, mt, np, pair);
   if (st > kMaxStages) st = kMaxStages;
   if (st < 2) st = 2;
@@ -209,14 +211,188 @@ struct FpropCfg {
   static_assert(2 * kAccCols <= 512 && (NP == 1 || MT == 1), "TMEM holds 512 columns");
   static_assert(!CG2 || (MT == 1 && NP == 1), "CTA pairs: one M tile per CTA, bf16 operands");
   // smem: [stages x (A|B)] [out staging] [add staging] [mask staging]
-  static int stages_for(bool has_add, bool has_mask, bool out_f32, int out_bufs = 1) {
-    return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32, CG2, out_bufs);
+  static int stages_for(bool has_add, bool has_mask, bool out_f32, int out_bufs = 1,
+                        int aux_sets = 1) {
+    return fprop_stages(BN, MT, NP, has_add, has_mask, out_f32, CG2, out_bufs, aux_sets);
   }
-  static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32, int out_bufs = 1) {
+  static int smem_bytes(int stages, bool has_add, bool has_mask, bool out_f32, int out_bufs = 1,
+                        int aux_sets = 1) {
     return 1024 + stages * kStageBytes + (out_f32 ? 0 : out_bufs * kTileBytes) +
-           (has_add ? kTileBytes : 0) + (has_mask ? kTileBytes : 0);
+           (has_add ? aux_sets * kTileBytes : 0) + (has_mask ? aux_sets * kTileBytes : 0);
   }
 };
+
+// Split epilogue of conv_gemm_kernel (one M tile per CTA tile, bf16 output, no bias): the 8 epilogue
+// warps form two independent groups of four (one warp per TMEM lane quarter); group g drains
+// accumulator stage g of the tiles g, g + 2, ... with its own output / add / mask staging tiles, named
+// barrier (1 + g, 128 threads), aux mbarrier and TMA store queue, so the chain of one tile (barrier ->
+// TMEM load -> convert -> stage -> barrier -> store -> statistics, per column half) overlaps the next
+// tile's.  That chain -- not the tensor pipe, not HBM -- paces tiles with one or two k-blocks (the
+// small-K 1x1 convolutions).  Same arithmetic per element as the joint epilogue; the statistics are
+// summed in a different (fixed) order.
+template <int BN>
+__device__ __forceinline__ void conv_epilogue_split(
+    const ConvGemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmAdd,
+    const CUtensorMap* tmMask, uint32_t tmem_base, uint8_t* s_out0, uint8_t* s_add, uint8_t* s_mask,
+    uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* aux_bars, int n0, int m_first, int m_step,
+    int my_tiles) {
+  using Cfg = FpropCfg<BN, 1, 1, false>;
+  constexpr int kHalfN = Cfg::kHalfN;
+  constexpr int kNHalf = Cfg::kNHalf;
+  constexpr int kSubW = Cfg::kSubW;
+  constexpr int kRowBytes = kSubW * 2;
+  constexpr int kSubBytes = kBM * kRowBytes;
+  constexpr int kNSub = kHalfN / kSubW;
+  constexpr int kNChunk = kHalfN / 8;                  // 16-byte column chunks of a half tile
+  constexpr int kNRg = 128 / kNChunk;                  // row groups inside one epilogue group
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int quarter = warp & 3;
+  const int grp = (warp - 2) >> 2;
+  const int r = quarter * 32 + lane;                   // row inside the tile == TMEM lane
+  const int gt = static_cast<int>(threadIdx.x) - 64 - grp * 128;   // thread index inside the group
+  const bool gleader = gt == 0;
+  const bool stats = p.ch_part != nullptr;
+  const bool has_aux = p.has_add || p.has_mask;
+  const int swz = (kRowBytes == 128) ? (r & 7) : ((r >> 1) & 3);
+  uint8_t* so_ = s_out0 + grp * Cfg::kTileBytes;
+  uint8_t* sa_ = s_add + grp * Cfg::kTileBytes;
+  uint8_t* sm_ = s_mask + grp * Cfg::kTileBytes;
+  uint64_t* abar = &aux_bars[grp];
+  const int st_chunk = gt % kNChunk, st_rg = gt / kNChunk;
+  float acc_s[kNHalf][8], acc_q[kNHalf][8];
+#pragma unroll
+  for (int hf = 0; hf < kNHalf; ++hf)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc_s[hf][e] = acc_q[hf][e] = 0.f;
+  uint32_t aux_n = 0;
+  auto group_sync = [&]() {
+    if (grp == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+    else asm volatile("bar.sync 2, 128;\n" ::: "memory");
+  };
+  auto issue_aux = [&](int am0, int anh) {
+    mbar_expect_tx(abar, (p.has_add ? Cfg::kTileBytes : 0) + (p.has_mask ? Cfg::kTileBytes : 0));
+#pragma unroll
+    for (int sub = 0; sub < kNSub; ++sub) {
+      if (p.has_add) tma_load_2d(sa_ + sub * kSubBytes, tmAdd, abar, anh + sub * kSubW, am0);
+      if (p.has_mask) tma_load_2d(sm_ + sub * kSubBytes, tmMask, abar, anh + sub * kSubW, am0);
+    }
+  };
+  if (gleader && has_aux && grp < my_tiles) issue_aux((m_first + grp * m_step) * kBM, n0);
+
+  for (int it = grp; it < my_tiles; it += 2) {
+    const int m0 = (m_first + it * m_step) * kBM;
+#pragma unroll
+    for (int hf = 0; hf < kNHalf; ++hf) {
+      const int nh = n0 + hf * kHalfN;
+      if (gleader) tma_store_wait_read();              // this group's previous store has read so_
+      group_sync();
+      if (hf == 0) {
+        mbar_wait(&tfull_bar[grp], (it >> 1) & 1);
+        tc_fence_after();
+      }
+      if (has_aux) {
+        mbar_wait(abar, aux_n & 1);
+        ++aux_n;
+      }
+#pragma unroll
+      for (int c = 0; c < kHalfN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + grp * Cfg::kAccCols +
+                          hf * kHalfN + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        const int sub = (c * 32) / kSubW;
+        const int j0 = ((c * 32) % kSubW) / 8;
+        const int soff = sub * kSubBytes + r * kRowBytes;
+        if (p.has_add) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(sa_ + soff + (((j0 + q) ^ swz) << 4));
+            const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              bf16x2_add(f[q * 8 + e * 2 + 0], f[q * 8 + e * 2 + 1], w4[e]);
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+        if (p.has_mask) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(sm_ + soff + (((j0 + q) ^ swz) << 4));
+            pk[q * 4 + 0] &= bf16x2_gt0_mask(u.x);
+            pk[q * 4 + 1] &= bf16x2_gt0_mask(u.y);
+            pk[q * 4 + 2] &= bf16x2_gt0_mask(u.z);
+            pk[q * 4 + 3] &= bf16x2_gt0_mask(u.w);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(so_ + soff + (((j0 + q) ^ swz) << 4)) =
+              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+      }
+      if (hf == kNHalf - 1) tc_fence_before();
+      fence_proxy_async();
+      group_sync();
+      if (gleader) {
+        if (hf == kNHalf - 1) mbar_arrive(&tempty_bar[grp]);
+#pragma unroll
+        for (int sub = 0; sub < kNSub; ++sub)
+          tma_store_2d(tmC, so_ + sub * kSubBytes, nh + sub * kSubW, m0);
+        tma_store_commit();
+        if (has_aux) {
+          if (hf + 1 < kNHalf) issue_aux(m0, nh + kHalfN);
+          else if (it + 2 < my_tiles) issue_aux((m_first + (it + 2) * m_step) * kBM, n0);
+        }
+      }
+      if (stats) {
+        // column sums of the half tile as stored (bf16-rounded); rows past M were computed from
+        // zero-filled operands and contribute zero
+        const int sub = st_chunk / (kSubW / 8), jj = st_chunk % (kSubW / 8);
+#pragma unroll 4
+        for (int rr = st_rg; rr < kBM; rr += kNRg) {
+          const int sw = (kRowBytes == 128) ? (rr & 7) : ((rr >> 1) & 3);
+          const uint4 u = *reinterpret_cast<const uint4*>(so_ + sub * kSubBytes + rr * kRowBytes +
+                                                          ((jj ^ sw) << 4));
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            bf16x2_sum_sq(acc_s[hf][2 * e], acc_q[hf][2 * e], acc_s[hf][2 * e + 1],
+                          acc_q[hf][2 * e + 1], w4[e]);
+        }
+      }
+    }
+  }
+  if (gleader) tma_store_wait_all();
+  if (stats && my_tiles > 0) {
+    // cross-group / cross-row-group reduction in the (now idle) staging tiles
+    float* red_sum = reinterpret_cast<float*>(s_out0);
+    float* red_sq = red_sum + 2 * kNRg * BN;
+    static_assert(2 * 2 * kNRg * BN * 4 <= 2 * Cfg::kTileBytes, "staging tiles too small for stats");
+    asm volatile("bar.sync 3, 256;\n" ::: "memory");    // both groups' stores have drained
+#pragma unroll
+    for (int hf = 0; hf < kNHalf; ++hf)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        red_sum[(grp * kNRg + st_rg) * BN + hf * kHalfN + st_chunk * 8 + e] = acc_s[hf][e];
+        red_sq[(grp * kNRg + st_rg) * BN + hf * kHalfN + st_chunk * 8 + e] = acc_q[hf][e];
+      }
+    asm volatile("bar.sync 3, 256;\n" ::: "memory");
+    for (int col = static_cast<int>(threadIdx.x) - 64; col < BN; col += kEpiThreads) {
+      float ss = 0.f, qq = 0.f;
+      for (int g2 = 0; g2 < 2 * kNRg; ++g2) {
+        ss += red_sum[g2 * BN + col];
+        qq += red_sq[g2 * BN + col];
+      }
+      float* row = p.ch_part + static_cast<size_t>(m_first) * 2 * p.Cout;
+      row[n0 + col] = ss;
+      row[p.Cout + n0 + col] = qq;
+    }
+  }
+}
 
 // One CTA per SM walks output tiles (fixed N tile, M tiles strided by the grid).  The TMA producer
 // runs ahead across tiles through the smem ring; the MMA issuer alternates between two TMEM
@@ -247,15 +423,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint64_t empty_bar[kMaxStages];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
-  __shared__ uint64_t aux_bar;
+  __shared__ uint64_t aux_bars[2];
   __shared__ uint32_t tmem_base_smem;
+  uint64_t& aux_bar = aux_bars[0];
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const int kStages = p.stages;
   uint8_t* s_out0 = smem + kStages * Cfg::kStageBytes;
   uint8_t* s_add = s_out0 + (p.out_f32 ? 0 : p.out_bufs * Cfg::kTileBytes);
-  uint8_t* s_mask = s_add + (p.has_add ? Cfg::kTileBytes : 0);
+  uint8_t* s_mask = s_add + (p.has_add ? (p.split_epi ? 2 : 1) * Cfg::kTileBytes : 0);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -292,7 +469,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], CG2 ? 2 : 1);      // CG2: the epilogues of both CTAs release it
     }
-    mbar_init(&aux_bar, 1);
+    mbar_init(&aux_bars[0], 1);
+    mbar_init(&aux_bars[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -474,6 +652,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
+    if constexpr (MT == 1 && NP == 1 && !CG2) {
+      if (p.split_epi) {
+        conv_epilogue_split<BN>(p, &tmC, &tmAdd, &tmMask, tmem_base, s_out0, s_add, s_mask,
+                                tfull_bar, tempty_bar, aux_bars, n0, m_first, m_step, my_tiles);
+        goto epilogue_done;
+      }
+    }
+    {
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
     const int egrp = (warp - 2) >> 2;                  // 0 / 1: even / odd 32-column chunks
     const int r = quarter * 32 + lane;                 // row inside the tile == TMEM lane
@@ -707,6 +893,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         row[p.Cout + n0 + col] = qq;
       }
     }
+    }
+  epilogue_done:;
   }
   __syncwarp();
   tc_fence_before();
@@ -1477,6 +1665,16 @@ static int conv_out_bufs_default() {
 }
 static int g_conv_out_bufs = conv_out_bufs_default();
 
+// split epilogue of the conv GEMM kernel: 0 = off, 1 (default) = where the epilogue chain paces the
+// tile (K <= 256), 2 = wherever it fits (acnn_set_conv_split_epilogue; ACNN_CONV_SPLIT_EPI sets the
+// initial value).  Interleaved A/B of the c3 step: 23.36 / 23.14 / 23.19 ms for 0 / 1 / 2
+// (profiles/r02_exp_ab.txt); per layer profiles/r02_exp_split_epilogue_layers.txt
+static int conv_split_epi_default() {
+  const char* e = getenv("ACNN_CONV_SPLIT_EPI");
+  return e ? (e[0] - '0') : 1;
+}
+static int g_conv_split_epi = conv_split_epi_default();
+
 template <int BN, int CW, bool IM2COL, int MT, int NP, bool CG2 = false>
 static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per_n,
                             cudaStream_t stream) {
@@ -1505,10 +1703,28 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per
         Cfg::smem_bytes(st2, p.has_add, p.has_mask, p.out_f32, 2) <= kSmemBudget + 1024)
       q.out_bufs = 2;
   }
-  q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32, q.out_bufs);
+  // split epilogue (two 4-warp groups alternate tiles): one M tile per CTA tile, bf16 output, no
+  // bias; needs two output staging tiles and two sets of add / mask tiles.  Mode 1 = where the
+  // epilogue chain, not the k-loop, paces a tile (K <= 256: at most four k-blocks) and the ring still
+  // holds all of K or 3 stages; mode 2 = wherever it fits with >= 2 stages
+  q.split_epi = 0;
+  if (MT == 1 && NP == 1 && !CG2 && !p.out_f32 && !p.bias && g_conv_split_epi > 0) {
+    const int num_kb = ceil_div(p.Ktot, kStageK);
+    const int st2 = Cfg::stages_for(p.has_add, p.has_mask, false, 2, 2);
+    const bool fits = st2 >= 2 && Cfg::smem_bytes(st2, p.has_add, p.has_mask, false, 2, 2) <=
+                                      kSmemBudget + 1024;
+    const int need = num_kb + 1 < 3 ? num_kb + 1 : 3;
+    if (fits && (g_conv_split_epi >= 2 || (num_kb <= 4 && st2 >= need))) {
+      q.split_epi = 1;
+      q.out_bufs = 2;
+    }
+  }
+  const int aux_sets = q.split_epi ? 2 : 1;
+  q.stages = Cfg::stages_for(p.has_add, p.has_mask, p.out_f32, q.out_bufs, aux_sets);
   q.m_tiles = ceil_div(p.M, (CG2 ? 2 : MT) * kBM);
   q.n_tiles = p.Cout / BN;
-  const int smem = Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32, q.out_bufs);
+  const int smem =
+      Cfg::smem_bytes(q.stages, p.has_add, p.has_mask, p.out_f32, q.out_bufs, aux_sets);
   if (CG2) {
     // per_n CTA PAIRS per N tile, launched as clusters of two (ranks 2i, 2i+1 share a TPC)
     cudaLaunchConfig_t cfg{};
@@ -2078,6 +2294,12 @@ int acnn_set_conv_mtiles(int mode) {
 int acnn_set_conv_halo(int mode) {
   const int prev = acnn::g_conv_halo;
   acnn::g_conv_halo = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return prev;
+}
+
+int acnn_set_conv_split_epilogue(int mode) {
+  const int prev = acnn::g_conv_split_epi;
+  acnn::g_conv_split_epi = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   return prev;
 }
 

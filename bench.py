@@ -622,7 +622,7 @@ def conv_roofline(tr, rt, step_fn, peaks, ms_step):
             "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_unit": "bytes per step "
             "(dram__bytes_read+write summed over the same launches, ncu)", "traffic_source": traffic_src,
             "algorithmic_bytes_per_step": alg_bytes,
-            "kernel": "conv_gemm_kernel + wgrad_gemm_kernel (all %d tcgen05 launches of a step)" % len(evs),
+            "kernel": "conv_gemm_kernel + conv_halo_kernel + wgrad_gemm_kernel (all %d tcgen05 launches of a step)" % len(evs),
             "launch_ms_sum": t_ms, "share_of_step": t_ms / ms_step,
             "algorithmic_gflop_per_step": fl / 1e9,
             "executed_gflop_per_step": executed / 1e9,

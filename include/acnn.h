@@ -66,6 +66,12 @@ int acnn_set_conv_halo(int mode);
  * staging buffers, named barrier and TMA store queue), 0 = all 8 warps on one tile at a time.
  * Returns the previous setting. */
 int acnn_set_conv_halo_split(int on);
+/* Epilogue organisation of the conv GEMM kernel (one-M-tile, single-CTA tiles with bf16 output; no
+ * effect on results beyond fp32 summation order of the statistics): 0 = all 8 epilogue warps on one
+ * tile at a time; 1 (default) = two independent 4-warp groups alternate tiles where the epilogue
+ * chain paces the tile (K <= 256) and shared memory holds the doubled staging; 2 = wherever it fits.
+ * Returns the previous setting. */
+int acnn_set_conv_split_epilogue(int mode);
 /* Output staging buffers of the conv GEMM epilogue (no effect on results): 1 (default) = one half-
  * tile buffer; 0 = a second one where the shared-memory ring stays deep enough without its bytes
  * (all of K in flight or >= 4 stages), so that a half tile's TMA store drains under the next

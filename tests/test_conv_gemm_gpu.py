@@ -43,6 +43,16 @@ def _relerr(a, b):
     return (a.double() - b.double()).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
+@pytest.fixture(autouse=True, params=[0, 2], ids=["epi_joint", "epi_split"])
+def conv_split_epilogue(request, lib):
+    """Every test of this file under both epilogue organisations of conv_gemm_kernel
+    (acnn_set_conv_split_epilogue: 0 = all 8 warps on one tile, 2 = two 4-warp groups alternating
+    tiles wherever the doubled staging fits)."""
+    prev = lib.acnn_set_conv_split_epilogue(request.param)
+    yield request.param
+    lib.acnn_set_conv_split_epilogue(prev)
+
+
 @contextlib.contextmanager
 def _mtiles(lib, mode):
     """acnn_set_conv_mtiles: 2 forces two 128-pixel M tiles per CTA tile wherever legal."""

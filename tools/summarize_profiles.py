@@ -87,7 +87,7 @@ def dram(src, dst, dst_json=None):
                      % (k, a[0], a[1], a[2] / 1e9, a[2] / 1e6 / a[1] if a[1] else 0, a[3] / 1e9))
     print("wrote", dst)
     if dst_json:
-        g = [d for d in per.values() if "gemm_kernel" in d["k"]]
+        g = [d for d in per.values() if "gemm_kernel" in d["k"] or "conv_halo_kernel" in d["k"]]
         out = {"source": dst, "launches": len(g),
                "dram_bytes_per_step": sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in g),
                "l2_bytes_per_step": sum(d.get("lts__t_bytes.sum", 0) for d in g),
