@@ -14,6 +14,7 @@ backward -> all-reduce -> SGD).  torch tensors are the device-memory container o
 """
 from __future__ import annotations
 
+import os
 import math
 from collections import namedtuple
 
@@ -369,7 +370,7 @@ class Trainer:
         rt.run_forward()
         # (a second stream for the wgrad GEMMs was measured to give nothing under a CUDA graph:
         # every kernel already spans the GPU; Runtime.run(..., overlap_wgrad=True) keeps the option)
-        rt.run(rt.plan.backward)
+        rt.run(rt.plan.backward, overlap_wgrad=os.environ.get("ACNN_OVERLAP_WGRAD", "0") == "1")
 
     def prefetch(self, images, labels):
         """Start the host->device copy of the next step's inputs (pinned host tensors) on a side
