@@ -230,13 +230,18 @@ struct FpropCfg {
 // tile's.  That chain -- not the tensor pipe, not HBM -- paces tiles with one or two k-blocks (the
 // small-K 1x1 convolutions).  Same arithmetic per element as the joint epilogue; the statistics are
 // summed in a different (fixed) order.
-template <int BN>
+// MT == 2 (two M tiles per CTA tile): the two groups drain the two M tiles of EVERY tile concurrently
+// (group g = M tile g, both waiting on the same accumulator barrier; the "accumulator empty" barrier
+// then counts two arrivals) instead of alternating tiles.
+template <int BN, int MT>
 __device__ __forceinline__ void conv_epilogue_split(
     const ConvGemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmAdd,
     const CUtensorMap* tmMask, uint32_t tmem_base, uint8_t* s_out0, uint8_t* s_add, uint8_t* s_mask,
     uint64_t* tfull_bar, uint64_t* tempty_bar, uint64_t* aux_bars, int n0, int m_first, int m_step,
     int my_tiles) {
-  using Cfg = FpropCfg<BN, 1, 1, false>;
+  using Cfg = FpropCfg<BN, MT, 1, false>;
+  constexpr bool kPerMt = MT == 2;                     // groups = M tiles of one CTA tile
+  constexpr int kTileM = MT * kBM;
   constexpr int kHalfN = Cfg::kHalfN;
   constexpr int kNHalf = Cfg::kNHalf;
   constexpr int kSubW = Cfg::kSubW;
@@ -277,17 +282,20 @@ __device__ __forceinline__ void conv_epilogue_split(
       if (p.has_mask) tma_load_2d(sm_ + sub * kSubBytes, tmMask, abar, anh + sub * kSubW, am0);
     }
   };
-  if (gleader && has_aux && grp < my_tiles) issue_aux((m_first + grp * m_step) * kBM, n0);
+  const int it0 = kPerMt ? 0 : grp, it_step = kPerMt ? 1 : 2;
+  const int m_off = kPerMt ? grp * kBM : 0;            // this group's M tile inside the CTA tile
+  if (gleader && has_aux && it0 < my_tiles) issue_aux((m_first + it0 * m_step) * kTileM + m_off, n0);
 
-  for (int it = grp; it < my_tiles; it += 2) {
-    const int m0 = (m_first + it * m_step) * kBM;
+  for (int it = it0; it < my_tiles; it += it_step) {
+    const int m0 = (m_first + it * m_step) * kTileM + m_off;
+    const int acc = kPerMt ? (it & 1) : grp;           // TMEM accumulator stage of this tile
 #pragma unroll
     for (int hf = 0; hf < kNHalf; ++hf) {
       const int nh = n0 + hf * kHalfN;
       if (gleader) tma_store_wait_read();              // this group's previous store has read so_
       group_sync();
       if (hf == 0) {
-        mbar_wait(&tfull_bar[grp], (it >> 1) & 1);
+        mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
         tc_fence_after();
       }
       if (has_aux) {
@@ -297,8 +305,8 @@ __device__ __forceinline__ void conv_epilogue_split(
 #pragma unroll
       for (int c = 0; c < kHalfN / 32; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + grp * Cfg::kAccCols +
-                          hf * kHalfN + c * 32, v);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * Cfg::kAccCols +
+                          (kPerMt ? grp * BN : 0) + hf * kHalfN + c * 32, v);
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -338,14 +346,15 @@ __device__ __forceinline__ void conv_epilogue_split(
       fence_proxy_async();
       group_sync();
       if (gleader) {
-        if (hf == kNHalf - 1) mbar_arrive(&tempty_bar[grp]);
+        if (hf == kNHalf - 1) mbar_arrive(&tempty_bar[acc]);
 #pragma unroll
         for (int sub = 0; sub < kNSub; ++sub)
           tma_store_2d(tmC, so_ + sub * kSubBytes, nh + sub * kSubW, m0);
         tma_store_commit();
         if (has_aux) {
           if (hf + 1 < kNHalf) issue_aux(m0, nh + kHalfN);
-          else if (it + 2 < my_tiles) issue_aux((m_first + (it + 2) * m_step) * kBM, n0);
+          else if (it + it_step < my_tiles)
+            issue_aux((m_first + (it + it_step) * m_step) * kTileM + m_off, n0);
         }
       }
       if (stats) {
@@ -467,7 +476,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], CG2 ? 2 : 1);      // CG2: the epilogues of both CTAs release it
+      // CG2: the epilogues of both CTAs release it; split epilogue with two M tiles: both groups
+      mbar_init(&tempty_bar[s], (CG2 || (MT == 2 && p.split_epi)) ? 2 : 1);
     }
     mbar_init(&aux_bars[0], 1);
     mbar_init(&aux_bars[1], 1);
@@ -652,10 +662,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    if constexpr (MT == 1 && NP == 1 && !CG2) {
+    if constexpr (NP == 1 && !CG2) {
       if (p.split_epi) {
-        conv_epilogue_split<BN>(p, &tmC, &tmAdd, &tmMask, tmem_base, s_out0, s_add, s_mask,
-                                tfull_bar, tempty_bar, aux_bars, n0, m_first, m_step, my_tiles);
+        conv_epilogue_split<BN, MT>(p, &tmC, &tmAdd, &tmMask, tmem_base, s_out0, s_add, s_mask,
+                                    tfull_bar, tempty_bar, aux_bars, n0, m_first, m_step, my_tiles);
         goto epilogue_done;
       }
     }
@@ -1674,6 +1684,14 @@ static int conv_split_epi_default() {
   return e ? (e[0] - '0') : 1;
 }
 static int g_conv_split_epi = conv_split_epi_default();
+// the same for two-M-tile CTA tiles (the two groups take the two M tiles of every tile): 0 = off,
+// 1 (default) = K <= 256, 2 = wherever it fits (acnn_set_conv_split_mt2; ACNN_CONV_SPLIT_MT2 sets
+// the initial value).  Interleaved A/B of the c3 step: 23.28 / 23.11 / 23.17 ms for 0 / 1 / 2
+static int conv_split_mt2_default() {
+  const char* e = getenv("ACNN_CONV_SPLIT_MT2");
+  return e ? (e[0] - '0') : 1;
+}
+static int g_conv_split_mt2 = conv_split_mt2_default();
 
 template <int BN, int CW, bool IM2COL, int MT, int NP, bool CG2 = false>
 static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per_n,
@@ -1708,13 +1726,15 @@ static int launch_conv_gemm(const ConvMaps& tm, const ConvGemmParams& p, int per
   // epilogue chain, not the k-loop, paces a tile (K <= 256: at most four k-blocks) and the ring still
   // holds all of K or 3 stages; mode 2 = wherever it fits with >= 2 stages
   q.split_epi = 0;
-  if (MT == 1 && NP == 1 && !CG2 && !p.out_f32 && !p.bias && g_conv_split_epi > 0) {
+  const int split_mode = MT == 2 ? g_conv_split_mt2 : g_conv_split_epi;
+  if (NP == 1 && !CG2 && !p.out_f32 && !p.bias && split_mode > 0) {
     const int num_kb = ceil_div(p.Ktot, kStageK);
     const int st2 = Cfg::stages_for(p.has_add, p.has_mask, false, 2, 2);
-    const bool fits = st2 >= 2 && Cfg::smem_bytes(st2, p.has_add, p.has_mask, false, 2, 2) <=
-                                      kSmemBudget + 1024;
+    const int min_st = MT == 2 ? 3 : 2;
+    const bool fits = st2 >= min_st && Cfg::smem_bytes(st2, p.has_add, p.has_mask, false, 2, 2) <=
+                                           kSmemBudget + 1024;
     const int need = num_kb + 1 < 3 ? num_kb + 1 : 3;
-    if (fits && (g_conv_split_epi >= 2 || (num_kb <= 4 && st2 >= need))) {
+    if (fits && (split_mode >= 2 || (num_kb <= 4 && st2 >= need))) {
       q.split_epi = 1;
       q.out_bufs = 2;
     }
@@ -2300,6 +2320,12 @@ int acnn_set_conv_halo(int mode) {
 int acnn_set_conv_split_epilogue(int mode) {
   const int prev = acnn::g_conv_split_epi;
   acnn::g_conv_split_epi = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
+  return prev;
+}
+
+int acnn_set_conv_split_mt2(int mode) {
+  const int prev = acnn::g_conv_split_mt2;
+  acnn::g_conv_split_mt2 = mode < 0 ? 0 : (mode > 2 ? 2 : mode);
   return prev;
 }
 

@@ -72,6 +72,10 @@ int acnn_set_conv_halo_split(int on);
  * chain paces the tile (K <= 256) and shared memory holds the doubled staging; 2 = wherever it fits.
  * Returns the previous setting. */
 int acnn_set_conv_split_epilogue(int mode);
+/* The same for CTA tiles of two M tiles (N <= 128): the two groups drain the two M tiles of every tile
+ * concurrently.  0 = off, 1 (default) = where K <= 256, 2 = wherever the doubled staging fits with a
+ * ring of >= 3 stages.  Returns the previous setting. */
+int acnn_set_conv_split_mt2(int mode);
 /* Output staging buffers of the conv GEMM epilogue (no effect on results): 1 (default) = one half-
  * tile buffer; 0 = a second one where the shared-memory ring stays deep enough without its bytes
  * (all of K in flight or >= 4 stages), so that a half tile's TMA store drains under the next

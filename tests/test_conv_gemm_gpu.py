@@ -46,11 +46,14 @@ def _relerr(a, b):
 @pytest.fixture(autouse=True, params=[0, 2], ids=["epi_joint", "epi_split"])
 def conv_split_epilogue(request, lib):
     """Every test of this file under both epilogue organisations of conv_gemm_kernel
-    (acnn_set_conv_split_epilogue: 0 = all 8 warps on one tile, 2 = two 4-warp groups alternating
-    tiles wherever the doubled staging fits)."""
+    (acnn_set_conv_split_epilogue / acnn_set_conv_split_mt2: 0 = all 8 warps on one tile, 2 = two
+    4-warp groups -- alternating tiles, or one M tile each of a two-M-tile CTA tile -- wherever the
+    doubled staging fits)."""
     prev = lib.acnn_set_conv_split_epilogue(request.param)
+    prev2 = lib.acnn_set_conv_split_mt2(request.param)
     yield request.param
     lib.acnn_set_conv_split_epilogue(prev)
+    lib.acnn_set_conv_split_mt2(prev2)
 
 
 @contextlib.contextmanager
