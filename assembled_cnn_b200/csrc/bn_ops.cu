@@ -299,6 +299,67 @@ bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ y,
                         [C](int a, int c) { return a * C + c; });
 }
 
+// Two batch norms fed by the SAME gradient g (the block-final BN and the projection-shortcut BN of a
+// residual block's first unit: out = relu(bn_a(y_a) + bn_b(y_b))): one pass reads g once and writes
+// one partial row per BN (sum g is shared).  Same per-thread summation order as two calls of
+// bn_bwd_reduce_kernel, so the results are bit-identical to the separate kernels.
+template <class T>
+__global__ void __launch_bounds__(kT, 2)
+bn_bwd_reduce2_kernel(const T* __restrict__ g, const T* __restrict__ ya, const T* __restrict__ yb,
+                      const float* __restrict__ mean_a, const float* __restrict__ rstd_a,
+                      const float* __restrict__ mean_b, const float* __restrict__ rstd_b,
+                      float* sums_a, float* sums_b, int64_t M, int C) {
+  pdl_entry();
+  const int CG = C >> 3;
+  const int RPB = kT / CG;
+  const int cg = threadIdx.x % CG;
+  const int rsub = threadIdx.x / CG;
+  const int c0 = cg << 3;
+  float mua[8], rsa[8], mub[8], rsb[8];
+  loadf8(mean_a + c0, mua);
+  loadf8(rstd_a + c0, rsa);
+  loadf8(mean_b + c0, mub);
+  loadf8(rstd_b + c0, rsb);
+  float acc_a[2][8], acc_b[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc_a[0][i] = acc_a[1][i] = acc_b[0][i] = acc_b[1][i] = 0.f;
+  const int64_t step = (int64_t)gridDim.x * RPB;
+  for (int64_t r0 = (int64_t)blockIdx.x * RPB + rsub; r0 < M; r0 += 4 * step) {
+    V8<T> gq[4], aq[4], bq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {          // 12 x 16 B in flight per thread (row index clamped)
+      int64_t r = r0 + u * step;
+      r = r < M ? r : M - 1;
+      gq[u].ld(g + r * C + c0);
+      aq[u].ld(ya + r * C + c0);
+      bq[u].ld(yb + r * C + c0);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * step;
+      const float valid = r < M ? 1.f : 0.f;
+      float gv[8], av[8], bv[8];
+      gq[u].unpack(gv);
+      aq[u].unpack(av);
+      bq[u].unpack(bv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float gg = gv[i] * valid;
+        acc_a[0][i] += gg;
+        acc_a[1][i] += gg * ((av[i] - mua[i]) * rsa[i]);
+        acc_b[1][i] += gg * ((bv[i] - mub[i]) * rsb[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc_b[0][i] = acc_a[0][i];
+  block_reduce_store<2>(acc_a, CG, sums_a + (size_t)blockIdx.x * 2 * C,
+                        [C](int a, int c) { return a * C + c; });
+  __syncthreads();                          // the reduction scratch is reused
+  block_reduce_store<2>(acc_b, CG, sums_b + (size_t)blockIdx.x * 2 * C,
+                        [C](int a, int c) { return a * C + c; });
+}
+
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int nparts,
                                        const float* __restrict__ gamma,
                                        const float* __restrict__ mean,
@@ -388,6 +449,55 @@ bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ y,
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = fmaf(k1[k], gv[k], fmaf(k2[k], yv[k], k3[k]));
       store8(dy + i * 8, o);
+    }
+  }
+}
+
+// dy_a = k1a*g + k2a*ya + k3a and dy_b = k1b*g + k2b*yb + k3b in one pass (g read once): the two
+// batch norms of bn_bwd_reduce2_kernel.
+template <class T>
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply2_kernel(const T* __restrict__ g, const T* __restrict__ ya, const T* __restrict__ yb,
+                     const float* __restrict__ coef_a, const float* __restrict__ coef_b,
+                     T* __restrict__ dya, T* __restrict__ dyb, int C, int64_t nvec) {
+  pdl_wait();   // multi-wave grid (see bn_bwd_apply_kernel)
+  const int CG = C >> 3;
+  const int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int cg = (int)(i0 % CG);           // loop-invariant (see bn_act_kernel)
+  const int c0 = cg << 3;
+  float k1a[8], k2a[8], k3a[8], k1b[8], k2b[8], k3b[8];
+  loadf8(coef_a + c0, k1a);
+  loadf8(coef_a + C + c0, k2a);
+  loadf8(coef_a + 2 * C + c0, k3a);
+  loadf8(coef_b + c0, k1b);
+  loadf8(coef_b + C + c0, k2b);
+  loadf8(coef_b + 2 * C + c0, k3b);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t ib = i0; ib < nvec; ib += 2 * stride) {
+    V8<T> gq[2], aq[2], bq[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {          // batched loads (index clamped)
+      int64_t i = ib + u * stride;
+      i = i < nvec ? i : nvec - 1;
+      gq[u].ld(g + i * 8);
+      aq[u].ld(ya + i * 8);
+      bq[u].ld(yb + i * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = ib + u * stride;
+      if (i >= nvec) break;
+      float gv[8], av[8], bv[8], oa[8], ob[8];
+      gq[u].unpack(gv);
+      aq[u].unpack(av);
+      bq[u].unpack(bv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        oa[k] = fmaf(k1a[k], gv[k], fmaf(k2a[k], av[k], k3a[k]));
+        ob[k] = fmaf(k1b[k], gv[k], fmaf(k2b[k], bv[k], k3b[k]));
+      }
+      store8(dya + i * 8, oa);
+      store8(dyb + i * 8, ob);
     }
   }
 }
@@ -946,6 +1056,32 @@ int acnn_bn_bwd_reduce(const void* g, const void* y, const float* mean, const fl
                                 addbc, parts, M, HW, C));
   count_launch();
   return check_launch("bn_bwd_reduce");
+}
+
+int acnn_bn_bwd_reduce2(const void* g, const void* ya, const void* yb, const float* mean_a,
+                        const float* rstd_a, const float* mean_b, const float* rstd_b, float* parts_a,
+                        float* parts_b, int B, int HW, int C, int dtype, void* stream) {
+  ACNN_REQUIRE(g && ya && yb && mean_a && rstd_a && mean_b && rstd_b && parts_a && parts_b &&
+                   cg_ok(C) && ACNN_DTYPE_OK(dtype), "bn_bwd_reduce2: bad arguments C=%d", C);
+  const int64_t M = (int64_t)B * HW;
+  ACNN_BY_DTYPE(dtype, launch_k(bn_bwd_reduce2_kernel<T>, dim3(bn_bwd_reduce_grid(M, C)), dim3(kT), 0,
+                                (cudaStream_t)stream, (const T*)g, (const T*)ya, (const T*)yb, mean_a,
+                                rstd_a, mean_b, rstd_b, parts_a, parts_b, M, C));
+  count_launch();
+  return check_launch("bn_bwd_reduce2");
+}
+
+int acnn_bn_bwd_apply2(const void* g, const void* ya, const void* yb, const float* coef_a,
+                       const float* coef_b, void* dya, void* dyb, int B, int HW, int C, int dtype,
+                       void* stream) {
+  ACNN_REQUIRE(g && ya && yb && coef_a && coef_b && dya && dyb && cg_ok(C) && ACNN_DTYPE_OK(dtype),
+               "bn_bwd_apply2: bad arguments");
+  const int64_t nvec = (int64_t)B * HW * C / 8;
+  ACNN_BY_DTYPE(dtype, launch_k(bn_bwd_apply2_kernel<T>, dim3(grid_for(nvec)), dim3(kT), 0,
+                                (cudaStream_t)stream, (const T*)g, (const T*)ya, (const T*)yb, coef_a,
+                                coef_b, (T*)dya, (T*)dyb, C, nvec));
+  count_launch();
+  return check_launch("bn_bwd_apply2");
 }
 
 int acnn_bn_bwd_finalize(const float* parts, int nparts, const float* gamma, const float* mean,

@@ -16,6 +16,7 @@ Parameters are enumerated in the reference's variable creation order with TF-sty
 """
 from __future__ import annotations
 
+import os
 import math
 from collections import OrderedDict
 from dataclasses import dataclass, field
@@ -222,6 +223,9 @@ class PlanBuilder:
         if self.use_dropblock and cfg.use_se_block:
             raise NotImplementedError("use_dropblock together with use_se_block")
         self.kd_temp = float(kd_temp) if training else 0.0
+        # backward of the two batch norms of a projection block's output in one pass each
+        # (bn_backward2; ACNN_FUSE_BN_PAIRS=0 keeps the separate kernels for A/B runs)
+        self.fuse_bn_pairs = os.environ.get("ACNN_FUSE_BN_PAIRS", "1") == "1"
         self._identity_bns = {}
         if dtype not in ("bf16", "fp32"):
             raise ValueError("dtype must be one of: ('bf16', 'fp32')")
@@ -528,6 +532,24 @@ class PlanBuilder:
                   shape=y.shape)
         return dy.name
 
+    def bn_backward2(self, co_a: ConvOut, co_b: ConvOut, g: str):
+        """Backward of the two batch norms summed into one residual output (block-final BN and
+        projection-shortcut BN, same gradient g, same shape): g is read once per pass instead of
+        twice (ops bn_bwd_reduce2 / bn_bwd_apply2; bit-identical to two bn_backward calls)."""
+        assert co_a.y.shape == co_b.y.shape
+        outs = []
+        for co in (co_a, co_b):
+            outs.append((self.slot("work", BWD_PARTS_CAP * 2 * co.bn.C), self.slot("work", 3 * co.bn.C),
+                         self.tensor("dy", co.y.shape)))
+        (sa, ca, da), (sb, cb, db) = outs
+        self.emit("bn_bwd_reduce2", g=g, y=co_a.y.name, bn=co_a.bn, sums=sa, y2=co_b.y.name,
+                  bn2=co_b.bn, sums2=sb, shape=co_a.y.shape)
+        self.emit("bn_bwd_finalize", bn=co_a.bn, sums=sa, coef=ca)
+        self.emit("bn_bwd_finalize", bn=co_b.bn, sums=sb, coef=cb)
+        self.emit("bn_bwd_apply2", g=g, y=co_a.y.name, coef=ca, dy=da.name, y2=co_b.y.name, coef2=cb,
+                  dy2=db.name, shape=co_a.y.shape)
+        return da.name, db.name
+
     def conv_backward(self, co: ConvOut, dy: str, need_dgrad=True):
         g = co.geom
         dyp = self.planes(dy)
@@ -714,6 +736,11 @@ class PlanBuilder:
                 self.emit("se_fc_bwd", de=de, e=se["e"], h=se["h"], q=se["q"], w1=se["w1"],
                           w2=se["w2"], dq=dq, scratch=se["scratch"], **dims)
                 dy3 = self.bn_backward(co3, g, gate=se["e"], addbc=dq)
+            elif mode == "bn" and self.fuse_bn_pairs:
+                dy3, dys = self.bn_backward2(co3, shortcut, g)
+                self.conv_backward(co3, dy3)
+                self.conv_backward(shortcut, dys)
+                return
             else:
                 dy3 = self.bn_backward(co3, g)
             self.conv_backward(co3, dy3)

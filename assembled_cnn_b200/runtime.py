@@ -483,6 +483,24 @@ class Runtime:
                                              self.S(op.gate), self.S(op.addbc), self.T(op.dy), B,
                                              H * W, C_, self.adt, self.stream), op)
 
+    def op_bn_bwd_reduce2(self, op):
+        B, H, W, C_ = op.shape
+        bn, bn2 = op.bn, op.bn2
+        n = self.lib.acnn_bn_bwd_reduce_parts(B, H * W, C_)
+        assert 1 <= n and n * 2 * C_ <= op.sums.size and n * 2 * C_ <= op.sums2.size
+        self._parts_cache[("bwd", op.sums.buf, op.sums.offset)] = n
+        self._parts_cache[("bwd", op.sums2.buf, op.sums2.offset)] = n
+        self._chk(self.lib.acnn_bn_bwd_reduce2(
+            self.T(op.g), self.T(op.y), self.T(op.y2), self.S(bn.work, 2 * C_),
+            self.S(bn.work, 3 * C_), self.S(bn2.work, 2 * C_), self.S(bn2.work, 3 * C_),
+            self.S(op.sums), self.S(op.sums2), B, H * W, C_, self.adt, self.stream), op)
+
+    def op_bn_bwd_apply2(self, op):
+        B, H, W, C_ = op.shape
+        self._chk(self.lib.acnn_bn_bwd_apply2(
+            self.T(op.g), self.T(op.y), self.T(op.y2), self.S(op.coef), self.S(op.coef2),
+            self.T(op.dy), self.T(op.dy2), B, H * W, C_, self.adt, self.stream), op)
+
     def op_sk_bwd_gate(self, op):
         bn = op.bn
         self._chk(self.lib.acnn_sk_bwd_gate(self.T(op.dv), self.T(op.y), self.S(bn.work),

@@ -204,6 +204,17 @@ int acnn_bn_bwd_finalize(const float* parts, int nparts, const float* gamma, con
                          int C, void* stream);
 int acnn_bn_bwd_apply(const void* g, const void* y, const float* coef, const float* gate,
                       const float* addbc, void* dy, int B, int HW, int C, int dtype, void* stream);
+/* The same for TWO batch norms fed by one gradient g -- the block-final BN and the projection-
+ * shortcut BN of a residual block's first unit, out = relu(bn_a(y_a) + bn_b(y_b))
+ * (nets/resnet_model.py:42-45,81-97): g is read once per pass instead of twice.  parts_a / parts_b as
+ * acnn_bn_bwd_reduce (acnn_bn_bwd_reduce_parts(B, HW, C) rows each); results bit-identical to the
+ * single-BN entry points (no gate / addbc: not used with the SE gate). */
+int acnn_bn_bwd_reduce2(const void* g, const void* ya, const void* yb, const float* mean_a,
+                        const float* rstd_a, const float* mean_b, const float* rstd_b, float* parts_a,
+                        float* parts_b, int B, int HW, int C, int dtype, void* stream);
+int acnn_bn_bwd_apply2(const void* g, const void* ya, const void* yb, const float* coef_a,
+                       const float* coef_b, void* dya, void* dyb, int B, int HW, int C, int dtype,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Selective-kernel block after its 3x3 conv (nets/blocks.py:128-152).  y = raw conv output

@@ -503,6 +503,26 @@ class PlanInterpreter:
         ge = self._eff_grad(g, op, B, C)
         self.store(op.dy, c[:C] * ge + c[C:2 * C] * y + c[2 * C:])
 
+    def op_bn_bwd_reduce2(self, op):
+        """Two batch norms fed by one gradient (plan.bn_backward2): two bn_bwd_reduce in one op."""
+        g = self.t[op.g]
+        for yname, bn, sums in ((op.y, op.bn, op.sums), (op.y2, op.bn2, op.sums2)):
+            y = self.t[yname]
+            C = y.shape[-1]
+            _, _, mean, rstd = self.bn_scale_shift(bn)
+            s = self.slot(sums)
+            s.zero_()
+            s[:C] = g.sum(dim=(0, 1, 2))
+            s[C:2 * C] = (g * (y - mean) * rstd).sum(dim=(0, 1, 2))
+
+    def op_bn_bwd_apply2(self, op):
+        g = self.t[op.g]
+        for yname, coef, dy in ((op.y, op.coef, op.dy), (op.y2, op.coef2, op.dy2)):
+            y = self.t[yname]
+            C = y.shape[-1]
+            c = self.slot(coef)
+            self.store(dy, c[:C] * g + c[C:2 * C] * y + c[2 * C:])
+
     def op_sk_bwd_gate(self, op):
         _, u0, u1 = self._sk_u(op)
         dv = self.t[op.dv]

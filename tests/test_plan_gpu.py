@@ -77,6 +77,10 @@ def _outputs(op):
         return G(a["w"])
     if k in ("bn_bwd_reduce", "sk_bn_bwd_reduce"):
         return [("parts", a["sums"], 2 * a["bn"].C)]
+    if k == "bn_bwd_reduce2":
+        return [("parts", a["sums"], 2 * a["bn"].C), ("parts", a["sums2"], 2 * a["bn2"].C)]
+    if k == "bn_bwd_apply2":
+        return T("dy") + T("dy2")
     if k == "bn_bwd_finalize":
         return S("coef") + G(a["bn"].gamma, a["bn"].beta)
     if k in ("bn_bwd_apply", "sk_bn_bwd_apply"):
