@@ -54,7 +54,7 @@ records = []
 orig_run = rt.run
 
 
-def timed_run(ops):
+def timed_run(ops, overlap_wgrad=False):
     for op in ops:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
