@@ -14,7 +14,6 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-_GRAD_WRITERS = ("conv_wgrad", "sk_fc_bwd", "se_fc_bwd", "s2d_wgrad_unpack")
 
 
 # bucket boundaries as fractions of the flat buffer, from its end: the early layers hold few parameters
@@ -28,17 +27,7 @@ def grad_buckets(plan, cuts=DEFAULT_CUTS):
     and the index of the backward op after which every gradient of the range (and of all later
     ranges) is final.  Parameters are laid out in creation (= forward) order, the backward produces
     their gradients roughly from the end of the buffer to its beginning."""
-    done_at = {}
-    for i, op in enumerate(plan.backward):
-        a = op.a
-        if op.kind in _GRAD_WRITERS:
-            for key in ("w", "w1", "w2"):
-                if isinstance(a.get(key), str) and a[key] in plan.params:
-                    done_at[a[key]] = i
-        if op.kind in ("bn_bwd_finalize", "sk_fc_bwd") and a.get("bn") is not None:
-            for n in (a["bn"].gamma, a["bn"].beta):
-                if n in plan.params:
-                    done_at[n] = i
+    done_at = plan.grad_done_at()
     total = plan.param_elems
     offsets = sorted(p.offset for p in plan.params.values())
     bounds = [total]

@@ -210,6 +210,24 @@ class Plan:
     def all_ops(self):
         return self.forward + self.backward + self.update
 
+    _GRAD_WRITERS = ("conv_wgrad", "sk_fc_bwd", "se_fc_bwd", "s2d_wgrad_unpack")
+
+    def grad_done_at(self):
+        """name -> index of the backward op after which that variable's gradient is final (the
+        data-parallel schedule of dp.py; acnn_variable_info.grad_ready_op of the native plan)."""
+        done_at = {}
+        for i, op in enumerate(self.backward):
+            a = op.a
+            if op.kind in self._GRAD_WRITERS:
+                for key in ("w", "w1", "w2"):
+                    if isinstance(a.get(key), str) and a[key] in self.params:
+                        done_at[a[key]] = i
+            if op.kind in ("bn_bwd_finalize", "sk_fc_bwd") and a.get("bn") is not None:
+                for n in (a["bn"].gamma, a["bn"].beta):
+                    if n in self.params:
+                        done_at[n] = i
+        return done_at
+
 
 class PlanBuilder:
     def __init__(self, cfg: ModelConfig, batch: int, height: int = 224, width: int = 224, *,
@@ -1068,3 +1086,51 @@ class PlanBuilder:
 
 def build_plan(cfg: ModelConfig, batch: int, height: int = 224, width: int = 224, **kw) -> Plan:
     return PlanBuilder(cfg, batch, height, width, **kw).plan
+
+
+# ------------------------------------------------------------------------------------------------
+# Canonical text of a plan -- the same format as acnn_plan_dump() of the model-level C ABI
+# (csrc/model_plan.cu builds the plan natively; tests/test_native_plan_cpu.py compares the two texts)
+def _fmt(v):
+    if v is None:
+        return "-"
+    if isinstance(v, bool):
+        return "1" if v else "0"
+    if isinstance(v, int):
+        return str(v)
+    if isinstance(v, float):
+        return "%.9g" % v
+    if isinstance(v, str):
+        return v
+    if isinstance(v, Slot):
+        return "%s:%d:%d" % (v.buf, v.offset, v.size)
+    if isinstance(v, BN):
+        return "bn(C=%d,count=%d,gamma=%s,beta=%s,mm=%s,mv=%s,stats=%s,work=%s)" % (
+            v.C, v.count, _fmt(v.gamma), _fmt(v.beta), _fmt(v.mm), _fmt(v.mv), _fmt(v.stats),
+            _fmt(v.work))
+    if isinstance(v, Geom):
+        return "g" + _fmt(v.astuple())
+    if isinstance(v, (tuple, list)):
+        return "(" + ",".join(_fmt(x) for x in v) + ")"
+    raise TypeError("plan dump: cannot format %r" % (v,))
+
+
+def dump(plan: Plan) -> str:
+    out = ["sizes param_elems=%d state_elems=%d dgrad_elems=%d zero_elems=%d work_elems=%d" % (
+        plan.param_elems, plan.state_elems, plan.dgrad_elems, plan.zero_elems, plan.work_elems)]
+    for k in sorted(plan.meta):
+        if plan.meta[k] is not None:
+            out.append("meta %s=%s" % (k, _fmt(plan.meta[k])))
+    for buffer, table in (("params", plan.params), ("state", plan.state)):
+        for p in table.values():
+            out.append("var %s buffer=%s kind=%s tf_shape=%s store_shape=%s offset=%d size=%d decay=%d "
+                       "zero_init=%d dgrad_off=%d" % (
+                           p.name, buffer, p.kind, _fmt(p.tf_shape), _fmt(p.store_shape), p.offset,
+                           p.size, p.decay, p.zero_init, p.dgrad_off))
+    for t in plan.tensors.values():
+        out.append("tensor %s shape=%s dtype=%s relu=%d" % (t.name, _fmt(t.shape), t.dtype, t.relu))
+    for tag, ops in (("F", plan.forward), ("B", plan.backward), ("U", plan.update)):
+        for i, op in enumerate(ops):
+            kv = " ".join("%s=%s" % (k, _fmt(op.a[k])) for k in sorted(op.a) if op.a[k] is not None)
+            out.append(("op %s %d %s %s" % (tag, i, op.kind, kv)).rstrip())
+    return "\n".join(out) + "\n"

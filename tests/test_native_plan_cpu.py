@@ -1,0 +1,182 @@
+"""The model-level C ABI (include/acnn_model.h) builds its layer plan in C++ (csrc/model_plan.cu); the
+op-by-op parity tests drive the Python plan (assembled_cnn_b200/plan.py) in lockstep with the oracle's
+interpreter.  These CPU tests pin the two to the SAME plan -- variables (TF names, creation order,
+layouts, offsets), buffers, and every op with every argument -- by comparing their canonical texts,
+so whatever the lockstep tests prove about the Python plan holds for the native one.  No GPU: acnn_create
+is host logic."""
+import ctypes as C
+import difflib
+import os
+import re
+
+import pytest
+
+from assembled_cnn_b200 import _lib, native
+from assembled_cnn_b200.plan import ModelConfig, build_plan, dump
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ASSEMBLE = dict(resnet_size=50, resnet_version=2, use_sk_block=True, anti_alias_type="sconv",
+                anti_alias_filter_size=3)
+
+CASES = [
+    # (constructor flags, batch, H, W, step flags)
+    (dict(resnet_size=50), 4, 64, 64, dict(training=True)),
+    (dict(resnet_size=50), 1, 224, 224, dict(training=False, with_loss=False)),            # BASELINE C1
+    (ASSEMBLE, 256, 224, 224, dict(training=True, mixup_type=1, label_smoothing=0.1)),     # BASELINE C3
+    (ASSEMBLE, 256, 224, 224, dict(training=False, with_loss=True, label_smoothing=0.1)),  # C2 eval
+    (dict(ASSEMBLE, resnet_size=152, bl_alpha=1, bl_beta=2), 128, 224, 224,
+     dict(training=True, mixup_type=1, label_smoothing=0.1)),                               # BASELINE C5
+    (ASSEMBLE, 8, 128, 128, dict(training=True, mixup_type=2, dtype="fp32")),
+    (ASSEMBLE, 8, 128, 128, dict(training=False, with_loss=True, dtype="fp32")),
+    (dict(ASSEMBLE, use_resnet_d=True), 4, 64, 64, dict(training=True)),
+    (dict(resnet_size=50, use_resnet_d=True), 4, 64, 64, dict(training=True, mixup_type=1)),
+    (dict(resnet_size=50, resnet_version=2, use_se_block=True, anti_alias_type="proj",
+          anti_alias_filter_size=5), 4, 64, 64, dict(training=True)),
+    (dict(resnet_size=50, use_se_block=True, zero_gamma=True), 4, 64, 64,
+     dict(training=True, dtype="fp32")),
+    (dict(resnet_size=101, resnet_version=2, use_sk_block=True, anti_alias_type="sconv,proj",
+          anti_alias_filter_size=3, no_downsample=True), 2, 96, 64, dict(training=True)),
+    (dict(resnet_size=200), 2, 64, 64, dict(training=True)),
+    (dict(resnet_size=101, no_downsample=True), 3, 64, 96, dict(training=False, with_loss=True)),
+    (dict(ASSEMBLE, pool_type="gem", embedding_size=256), 4, 64, 64, dict(training=True)),
+    (dict(ASSEMBLE, pool_type="gem", embedding_size=256), 4, 64, 64, dict(training=False)),
+    (dict(resnet_size=50, pool_type="flatten", num_classes=10), 4, 64, 64, dict(training=True)),
+    (dict(resnet_size=50, pool_type="flatten", embedding_size=64), 4, 64, 64,
+     dict(training=True, dtype="fp32")),
+    (ASSEMBLE, 4, 224, 224, dict(training=True, use_dropblock=True, mixup_type=1)),
+    (dict(resnet_size=50), 4, 224, 224, dict(training=True, use_dropblock=True)),
+    (dict(resnet_size=50, use_resnet_d=True), 4, 224, 224,
+     dict(training=True, use_dropblock=True, dtype="fp32")),
+    (ASSEMBLE, 4, 64, 64, dict(training=True, kd_temp=2.0, mixup_type=2)),
+    (ASSEMBLE, 4, 64, 64, dict(training=True, kd_temp=4.0, mixup_type=1, label_smoothing=0.1)),
+    (dict(ASSEMBLE, bl_alpha=4, bl_beta=2, bn_momentum=0.9), 4, 64, 64, dict(training=True)),
+]
+
+
+def _diff(a, b):
+    d = list(difflib.unified_diff(a.splitlines(), b.splitlines(), "python", "native", lineterm="", n=0))
+    return "%d differing lines\n%s" % (len(d), "\n".join(d[:40]))
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_native_plan_equals_python_plan(case):
+    flags, B, H, W, kw = CASES[case]
+    cfg = ModelConfig(**flags)
+    py = dump(build_plan(cfg, B, H, W, **kw))
+    nm = native.NativeModel(cfg, B, H, W, **kw)
+    cc = nm.dump()
+    assert py == cc, _diff(py, cc)
+    assert len(py.splitlines()) > 500
+    nm.close()
+
+
+def test_native_plan_honours_fuse_bn_pairs(monkeypatch):
+    monkeypatch.setenv("ACNN_FUSE_BN_PAIRS", "0")
+    cfg = ModelConfig(**ASSEMBLE)
+    py = dump(build_plan(cfg, 4, 64, 64, training=True))
+    cc = native.NativeModel(cfg, 4, 64, 64, training=True).dump()
+    assert "bn_bwd_reduce2" not in py and py == cc, _diff(py, cc)
+
+
+def test_model_abi_symbols_and_struct_layouts():
+    """Every function include/acnn_model.h declares is exported and bound; the ctypes mirrors of the
+    ABI structs have the C sizes (checked through struct_size and a compiled probe-free identity:
+    acnn_create rejects a config whose struct_size differs)."""
+    l = native.lib()
+    header = re.sub(r"/\*.*?\*/", " ", open(native.MODEL_HEADER).read(), flags=re.S)
+    declared = set(re.findall(r"\b(acnn_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(native.PROTOTYPES), declared ^ set(native.PROTOTYPES)
+    for name in declared:
+        assert hasattr(l, name), name
+    c = native.Config()
+    l.acnn_model_config_init(C.byref(c))
+    assert c.struct_size == C.sizeof(native.Config)          # layout agrees with the library's
+    assert (c.resnet_size, c.resnet_version, c.num_classes, c.bl_alpha, c.bl_beta) == (50, 1, 1001, 2, 4)
+    assert c.pool_type == b"gap" and c.bn_momentum == 0.997 and c.deterministic == -1
+    c.struct_size -= 4
+    h = C.c_void_p()
+    assert l.acnn_create(C.byref(c), C.byref(h)) != 0
+    assert b"struct_size" in l.acnn_last_error()
+
+
+def test_create_errors_match_reference_messages():
+    """nets/resnet_model.py:201-215 / functions/model_fns.py:131-135 argument errors, as status codes."""
+    l = native.lib()
+
+    def rc(**over):
+        c = native.Config()
+        l.acnn_model_config_init(C.byref(c))
+        for k, v in over.items():
+            setattr(c, k, v)
+        h = C.c_void_p()
+        r = l.acnn_create(C.byref(c), C.byref(h))
+        if r == 0:
+            l.acnn_destroy(h)
+        return r, l.acnn_last_error().decode()
+
+    assert rc()[0] == 0
+    r, msg = rc(resnet_version=3)
+    assert r == 1 and "Resnet version should be 1 or 2" in msg
+    r, msg = rc(resnet_size=18)
+    assert r == 3 and "non-bottleneck" in msg
+    r, msg = rc(resnet_size=51)
+    assert r == 1 and "Could not find layers" in msg
+    assert rc(height=100)[0] == 1 and rc(mixup_type=3)[0] == 1 and rc(dtype=7)[0] == 1
+    assert rc(pool_type=b"max")[0] == 3 and rc(loss_type=b"sigmoid")[0] == 3
+    r, msg = rc(use_dropblock=1, height=64, width=64)
+    assert r == 1 and "dropblock" in msg
+
+
+def test_variable_inventory_in_tf_creation_order():
+    """acnn_variable_info_get lists trainables and moving statistics interleaved in the reference's
+    creation order (kernel, gamma, beta, moving_mean, moving_variance per conv), TF names."""
+    nm = native.NativeModel(ModelConfig(**ASSEMBLE), 2, 64, 64, training=True)
+    l, vi = nm.lib, native.VariableInfo()
+    names = []
+    for i in range(nm.sizes.n_variables):
+        assert l.acnn_variable_info_get(nm.handle, i, C.byref(vi)) == 0
+        names.append(vi.name.decode())
+    assert names[:5] == ["resnet_model/stage0/conv2d/kernel",
+                         "resnet_model/stage0_1/batch_normalization/gamma",
+                         "resnet_model/stage0_1/batch_normalization/beta",
+                         "resnet_model/stage0_1/batch_normalization/moving_mean",
+                         "resnet_model/stage0_1/batch_normalization/moving_variance"]
+    assert names[-2:] == ["resnet_model/dense/kernel", "resnet_model/dense/bias"]
+    py = build_plan(ModelConfig(**ASSEMBLE), 2, 64, 64, training=True)
+    assert [n for n in names if n in py.params] == list(py.params)
+    assert [n for n in names if n in py.state] == list(py.state)
+    assert len(names) == len(py.params) + len(py.state)
+    # gradient readiness: every trainable except dense/bias (written by the loss op in the forward
+    # list) gets its gradient from a backward op; later layers are ready earlier
+    done = nm.grad_done_at()
+    assert set(py.params) - set(done) == {"resnet_model/dense/bias"}
+    assert done["resnet_model/dense/kernel"] == 0
+    assert done["resnet_model/stage0/conv2d/kernel"] == max(done.values())
+    from assembled_cnn_b200 import dp
+    assert dp.grad_buckets(py) == dp.grad_buckets(nm)
+
+
+def test_workspace_layout_is_disjoint_and_aligned():
+    nm = native.NativeModel(ModelConfig(**ASSEMBLE), 8, 128, 128, training=True, mixup_type=1)
+    s = nm.sizes
+    spans = [(s.hp_offset, 32), (s.decay_flags_offset, max(s.param_elems // 256, 1)),
+             (s.zero_offset, s.zero_bytes), (s.work_offset, s.work_bytes)]
+    esz = {"bf16": 2, "f32": 4, "i32": 4}
+    for name, t in nm.tensors.items():
+        n = esz[t.dtype]
+        for d in t.shape:
+            n *= d
+        spans.append((nm.tensor_offset[name], n))
+    spans.sort()
+    for (o, n), (o2, _) in zip(spans, spans[1:]):
+        assert o % 1024 == 0 and o + n <= o2
+    assert spans[-1][0] + spans[-1][1] <= s.workspace_bytes
+    assert s.loss_offset == s.zero_offset + 4 * nm.meta["loss"].offset
+    assert nm.meta["input_batch"] == 16 and s.n_loss_first == len(nm.forward) - 2
+    assert [op.kind for op in nm.forward[s.n_loss_first:]] == ["mix_labels", "softmax_ce"]
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_native_runtime_has_no_cpu_path():
+    with pytest.raises(_lib.AcnnError):
+        native.NativeRuntime(native.NativeModel(ModelConfig(resnet_size=50), 1, 64, 64, training=False))
