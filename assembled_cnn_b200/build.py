@@ -39,13 +39,17 @@ def _sources() -> list[str]:
 def _digest(path: str) -> str:
     h = hashlib.sha1()
     h.update(" ".join(NVCC_FLAGS).encode())
-    # every header change rebuilds everything (few files, seconds each)
-    for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".h", ".cuh")):
-            with open(os.path.join(CSRC, f), "rb") as fh:
-                h.update(fh.read())
-    with open(os.path.join(HERE, "..", "include", "acnn.h"), "rb") as fh:
-        h.update(fh.read())
+    # every header change rebuilds everything that can include it (few files, seconds each); the
+    # model-level headers are only seen by csrc/model_*.cu
+    model_src = os.path.basename(path).startswith("model_")
+    inc = os.path.join(HERE, "..", "include")
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))]
+    headers += [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
+    for f in headers:
+        if os.path.basename(f) in ("model_plan.h", "acnn_model.h") and not model_src:
+            continue
+        with open(f, "rb") as fh:
+            h.update(fh.read())
     with open(path, "rb") as fh:
         h.update(fh.read())
     return h.hexdigest()

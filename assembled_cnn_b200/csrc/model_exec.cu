@@ -699,6 +699,48 @@ int acnn_variable_info_get(const acnn_model* m, int i, acnn_variable_info* o) {
   return ACNN_OK;
 }
 
+static int convert_variable(const acnn_model* m, int i, const float* tf, float* st, float* tf_out,
+                            const float* st_in) {
+  ACNN_REQUIRE(m && i >= 0 && i < (int)m->plan.vars.size(), "acnn_variable_pack/unpack: bad index %d", i);
+  const Variable& v = m->plan.vars[i];
+  const bool pack = st != nullptr;
+  ACNN_REQUIRE(pack ? (tf != nullptr) : (tf_out != nullptr && st_in != nullptr), "null array");
+  if (v.kind == "conv_kernel") {   // HWIO <-> OHWI
+    const int64_t kh = v.tf_shape[0], kw = v.tf_shape[1], ci = v.tf_shape[2], co = v.tf_shape[3];
+    for (int64_t o = 0; o < co; ++o)
+      for (int64_t r = 0; r < kh; ++r)
+        for (int64_t c = 0; c < kw; ++c)
+          for (int64_t k = 0; k < ci; ++k) {
+            const int64_t a = ((r * kw + c) * ci + k) * co + o, b = ((o * kh + r) * kw + c) * ci + k;
+            if (pack) st[b] = tf[a]; else tf_out[a] = st_in[b];
+          }
+  } else if (v.kind == "dense_kernel") {   // [in, classes] <-> [ld_logits][in], padded rows zero
+    const int64_t in = v.tf_shape[0], nc = v.tf_shape[1];
+    if (pack) memset(st, 0, sizeof(float) * (size_t)v.size);
+    for (int64_t k = 0; k < in; ++k)
+      for (int64_t o = 0; o < nc; ++o) {
+        if (pack) st[o * in + k] = tf[k * nc + o]; else tf_out[k * nc + o] = st_in[o * in + k];
+      }
+  } else {   // vectors; the dense bias is zero-padded to ld_logits
+    const int64_t n = numel(v.tf_shape);
+    if (pack) {
+      memset(st, 0, sizeof(float) * (size_t)v.size);
+      memcpy(st, tf, sizeof(float) * (size_t)n);
+    } else {
+      memcpy(tf_out, st_in, sizeof(float) * (size_t)n);
+    }
+  }
+  return ACNN_OK;
+}
+
+int acnn_variable_pack(const acnn_model* m, int i, const float* tf_values, float* stored) {
+  ACNN_REQUIRE(stored, "acnn_variable_pack: null destination");
+  return convert_variable(m, i, tf_values, stored, nullptr, nullptr);
+}
+int acnn_variable_unpack(const acnn_model* m, int i, const float* stored, float* tf_values) {
+  return convert_variable(m, i, nullptr, nullptr, tf_values, stored);
+}
+
 int acnn_tensor_count(const acnn_model* m) { return m ? (int)m->plan.tensors.size() : -1; }
 
 int acnn_tensor_info_get(const acnn_model* m, int i, acnn_tensor_info* o) {
@@ -871,6 +913,27 @@ const char* acnn_op_kind(const acnn_model* m, int phase, int index) {
   if (!m || phase < 0 || phase > 2) return nullptr;
   const std::vector<Op>& l = phase == 0 ? m->plan.forward : (phase == 1 ? m->plan.backward : m->plan.update);
   return (index >= 0 && index < (int)l.size()) ? l[index].kind.c_str() : nullptr;
+}
+
+int acnn_op_conv_info(const acnn_model* m, int phase, int index, acnn_conv_geom* g, int64_t* alg_macs,
+                      int* aux_tiles) {
+  ACNN_REQUIRE(m && g && phase >= 0 && phase <= 2, "acnn_op_conv_info: bad argument");
+  const std::vector<Op>& l = phase == 0 ? m->plan.forward : (phase == 1 ? m->plan.backward : m->plan.update);
+  ACNN_REQUIRE(index >= 0 && index < (int)l.size(), "acnn_op_conv_info: op index %d out of range", index);
+  const Op& op = l[index];
+  const Val* gv = op.find("geom");
+  ACNN_REQUIRE(gv && (op.kind == "conv" || op.kind == "conv_dgrad" || op.kind == "conv_wgrad"),
+               "acnn_op_conv_info: op '%s' is not a GEMM", op.kind.c_str());
+  const Geom& s = gv->g;
+  memset(g, 0, sizeof(*g));
+  g->B = s.B; g->H = s.H; g->W = s.W; g->Cin = s.Cin; g->Cout = s.Cout; g->kh = s.kh; g->kw = s.kw;
+  g->stride = s.stride; g->pad_h_lo = s.pad_h_lo; g->pad_h_hi = s.pad_h_hi; g->pad_w_lo = s.pad_w_lo;
+  g->pad_w_hi = s.pad_w_hi;
+  const Val* am = op.find("alg_macs");
+  if (alg_macs)
+    *alg_macs = am ? am->i : (int64_t)s.B * s.Ho() * s.Wo() * s.Cout * s.kh * s.kw * s.Cin;
+  if (aux_tiles) *aux_tiles = (op.find("add_src") ? 1 : 0) + (op.find("mask_src") ? 1 : 0);
+  return ACNN_OK;
 }
 
 int64_t acnn_plan_dump(const acnn_model* m, char* buf, int64_t cap) {

@@ -26,6 +26,7 @@ from .hparams import DATASETS, DEFAULTS, params_from_flags
 from .plan import BLOCK_SIZES, ModelConfig, build_plan
 from .metrics import EvalMetrics
 from .runtime import Runtime
+from .native import NativeModel, NativeRuntime
 
 DEFAULT_VERSION = 1
 # dtype: 'bf16' = production path (bf16 storage, fp32 accumulation -- the analogue of the reference's
@@ -109,7 +110,7 @@ class Model:
                  zero_gamma=False, use_se_block=False, use_sk_block=False, bn_momentum=0.997,
                  embedding_size=0, anti_alias_filter_size=0, anti_alias_type="", pool_type="gap",
                  loss_type="softmax", bl_alpha=2, bl_beta=4, *, seed=42, device="cuda:0",
-                 deterministic=None):
+                 deterministic=None, native=None):
         if data_format not in (None, "channels_last"):
             raise ValueError("this implementation is NHWC only (data_format='channels_last')")
         if dtype not in ALLOWED_TYPES:
@@ -132,6 +133,10 @@ class Model:
         # None: bit-reproducible steps in the fp32 mode only; True: also in bf16 (wgrad and the SE
         # fc GEMMs run without split-K -- slower); every other reduction is ordered in both modes
         self.deterministic = deterministic
+        # True (default): the layer plan is built and executed inside libacnn.so through the model-level
+        # C ABI (include/acnn_model.h, native.NativeRuntime); False (ACNN_NATIVE_PLAN=0): the Python plan
+        # + per-op ctypes executor the lockstep parity tests drive (same plan, text-for-text)
+        self.native = (os.environ.get("ACNN_NATIVE_PLAN", "1") != "0") if native is None else bool(native)
         self._runtimes = {}          # (B, H, W, training, use_resnet_d, mixup, ls) -> Runtime
         self._primary = {}           # use_resnet_d -> Runtime owning the parameters
         self._pending_weights = None
@@ -145,11 +150,17 @@ class Model:
         rt = self._runtimes.get(key)
         if rt is None:
             cfg = ModelConfig(use_resnet_d=bool(use_resnet_d), **self.cfg_kwargs)
-            plan = build_plan(cfg, batch, height, width, training=training, mixup_type=mixup_type,
-                              label_smoothing=label_smoothing, with_loss=with_loss,
-                              dtype=self.dtype, use_dropblock=use_dropblock, kd_temp=kd_temp)
+            step = dict(training=training, mixup_type=mixup_type, label_smoothing=label_smoothing,
+                        with_loss=with_loss, dtype=self.dtype, use_dropblock=use_dropblock,
+                        kd_temp=kd_temp)
             prim = self._primary.get(bool(use_resnet_d))
-            rt = Runtime(plan, self.device, share=prim, deterministic=self.deterministic)
+            if self.native:
+                rt = NativeRuntime(NativeModel(cfg, batch, height, width,
+                                               deterministic=self.deterministic, **step),
+                                   self.device, share=prim)
+            else:
+                rt = Runtime(build_plan(cfg, batch, height, width, **step), self.device, share=prim,
+                             deterministic=self.deterministic)
             if prim is None:
                 self._primary[bool(use_resnet_d)] = rt
                 if self._pending_weights is not None:
@@ -246,7 +257,7 @@ def build_model(**flags) -> Model:
         "resnet_size", "data_format", "num_classes", "resnet_version", "dtype", "no_downsample",
         "zero_gamma", "use_se_block", "use_sk_block", "bn_momentum", "embedding_size",
         "anti_alias_filter_size", "anti_alias_type", "pool_type", "loss_type", "bl_alpha",
-        "bl_beta", "seed", "device", "deterministic")}
+        "bl_beta", "seed", "device", "deterministic", "native")}
     if flags:
         raise TypeError("build_model: unknown flag(s) %s" % sorted(flags))
     ctor.setdefault("resnet_size", DEFAULTS["resnet_size"])

@@ -71,6 +71,8 @@ PROTOTYPES = {
     "acnn_model_get_sizes": (_i, [_vp, C.POINTER(Sizes)]),
     "acnn_variable_count": (_i, [_vp]),
     "acnn_variable_info_get": (_i, [_vp, _i, C.POINTER(VariableInfo)]),
+    "acnn_variable_pack": (_i, [_vp, _i, _vp, _vp]),
+    "acnn_variable_unpack": (_i, [_vp, _i, _vp, _vp]),
     "acnn_tensor_count": (_i, [_vp]),
     "acnn_tensor_info_get": (_i, [_vp, _i, C.POINTER(TensorInfo)]),
     "acnn_find_tensor": (_i, [_vp, C.c_char_p, _i]),
@@ -90,6 +92,7 @@ PROTOTYPES = {
     "acnn_run_ops": (_i, [_vp, _i, _i, _i, _vp]),
     "acnn_clear_step_buffers": (_i, [_vp, _vp]),
     "acnn_op_kind": (C.c_char_p, [_vp, _i, _i]),
+    "acnn_op_conv_info": (_i, [_vp, _i, _i, C.POINTER(_lib.ConvGeom), C.POINTER(C.c_int64), C.POINTER(_i)]),
     "acnn_plan_dump": (_i64, [_vp, _vp, _i64]),
 }
 
@@ -154,6 +157,7 @@ class NativeModel:
 
     def __init__(self, cfg: ModelConfig, batch, height=224, width=224, **kw):
         self.lib = lib()
+        self.cfg, self.shape, self.step_kwargs = cfg, (batch, height, width), dict(kw)
         self.config = make_config(cfg, batch, height, width, **kw)
         h = _vp()
         _lib.check(self.lib.acnn_create(C.byref(self.config), C.byref(h)), "acnn_create")
@@ -216,6 +220,21 @@ class NativeModel:
 
     def all_ops(self):
         return self.forward + self.backward + self.update
+
+    def python_mirror(self):
+        """The plan.py plan of the same configuration -- op for op the same plan (pinned text-for-text by
+        tests/test_native_plan_cpu.py).  For the parity tests only: the oracle's interpreter
+        (oracle/plan_interp.py) walks Python op objects.  Nothing on the product path calls this."""
+        from .plan import build_plan
+        kw = {k: v for k, v in self.step_kwargs.items() if k not in ("deterministic", "loss_scale", "eps")}
+        return build_plan(self.cfg, *self.shape, **kw)
+
+    def conv_info(self, op):
+        """(acnn_conv_geom of the plan, algorithmic MACs, aux tiles of the epilogue) of a GEMM op."""
+        g, macs, aux = _lib.ConvGeom(), C.c_int64(), C.c_int()
+        _lib.check(self.lib.acnn_op_conv_info(self.handle, op.phase, op.index, C.byref(g), C.byref(macs),
+                                              C.byref(aux)), "acnn_op_conv_info")
+        return g, macs.value, aux.value
 
     def dump(self) -> str:
         n = self.lib.acnn_plan_dump(self.handle, None, 0)

@@ -210,6 +210,9 @@ class Plan:
     def all_ops(self):
         return self.forward + self.backward + self.update
 
+    def python_mirror(self):
+        return self
+
     _GRAD_WRITERS = ("conv_wgrad", "sk_fc_bwd", "se_fc_bwd", "s2d_wgrad_unpack")
 
     def grad_done_at(self):

@@ -570,26 +570,53 @@ def conv_roofline(tr, rt, step_fn, peaks, ms_step):
     import torch
     stream = torch.cuda.current_stream()
     evs = []
-    for name in ("op_conv", "op_conv_dgrad", "op_conv_wgrad"):
-        orig = getattr(rt, name)
+    GEMM = ("conv", "conv_dgrad", "conv_wgrad")
+    native = hasattr(rt.plan, "conv_info")
 
-        def wrapped(op, orig=orig):
-            g = op.geom
-            executed = 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.kh * g.kw * g.Cin
-            flops = 2.0 * op.a["alg_macs"] if op.a.get("alg_macs") else executed
-            # algorithmic HBM bytes: both activation tensors once (bf16) + the filter (bf16, or
-            # the fp32 gradient for wgrad) + the tiles the dgrad epilogue adds / masks with
-            nin, nout = g.B * g.H * g.W * g.Cin, g.B * g.Ho * g.Wo * g.Cout
-            nw = g.kh * g.kw * g.Cin * g.Cout
-            byt = 2.0 * (nin + nout) + (4.0 if op.kind == "conv_wgrad" else 2.0) * nw
-            if op.kind == "conv_dgrad":
-                byt += 2.0 * nin * ((op.add_src is not None) + (op.mask_src is not None))
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            orig(op)
-            b.record(stream)
-            evs.append((a, b, flops, byt, executed))
-        setattr(rt, name, wrapped)
+    def work_of(op):
+        """(algorithmic FLOPs, algorithmic HBM bytes, executed FLOPs) of one GEMM op."""
+        if native:      # geometry from the library (acnn_op_conv_info)
+            g, macs, aux = rt.plan.conv_info(op)
+            Ho, Wo = g.out_hw()
+        else:
+            g, Ho, Wo = op.geom, op.geom.Ho, op.geom.Wo
+            macs = op.a.get("alg_macs") or g.B * Ho * Wo * g.Cout * g.kh * g.kw * g.Cin
+            aux = (op.a.get("add_src") is not None) + (op.a.get("mask_src") is not None)
+        executed = 2.0 * g.B * Ho * Wo * g.Cout * g.kh * g.kw * g.Cin
+        # algorithmic HBM bytes: both activation tensors once (bf16) + the filter (bf16, or the
+        # fp32 gradient for wgrad) + the tiles the dgrad epilogue adds / masks with
+        nin, nout = g.B * g.H * g.W * g.Cin, g.B * Ho * Wo * g.Cout
+        nw = g.kh * g.kw * g.Cin * g.Cout
+        byt = 2.0 * (nin + nout) + (4.0 if op.kind == "conv_wgrad" else 2.0) * nw
+        if op.kind == "conv_dgrad":
+            byt += 2.0 * nin * aux
+        return 2.0 * macs, byt, executed
+
+    orig_run = type(rt).run
+
+    def run(ops, **kw):
+        """rt.run with every GEMM op launched on its own between two events."""
+        i = 0
+        while i < len(ops):
+            if ops[i].kind in GEMM:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                orig_run(rt, ops[i:i + 1])
+                b.record(stream)
+                evs.append((a, b) + work_of(ops[i]))
+                i += 1
+            else:
+                j = i
+                while j < len(ops) and ops[j].kind not in GEMM:
+                    j += 1
+                orig_run(rt, ops[i:j])
+                i = j
+
+    def run_forward():
+        rt.zero_step_buffers()
+        run(rt.plan.forward)
+
+    rt.run, rt.run_forward = run, run_forward
     was, was_world = tr.use_graph, tr.world
     tr.use_graph = False
     tr.world = 1        # rank 0 only: no collective inside this instrumented step
@@ -601,8 +628,7 @@ def conv_roofline(tr, rt, step_fn, peaks, ms_step):
     finally:
         tr.use_graph = was
         tr.world = was_world
-        for name in ("op_conv", "op_conv_dgrad", "op_conv_wgrad"):
-            delattr(rt, name)
+        del rt.run, rt.run_forward
     t_ms = sum(e[0].elapsed_time(e[1]) for e in evs)
     fl = sum(e[2] for e in evs)
     alg_bytes = sum(e[3] for e in evs)

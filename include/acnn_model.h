@@ -120,6 +120,14 @@ typedef struct acnn_variable_info {
 int acnn_variable_count(const acnn_model* m);
 int acnn_variable_info_get(const acnn_model* m, int i, acnn_variable_info* out);
 
+/* Layout conversion of variable i between the reference's layout (`tf_values`: prod(tf_shape) floats --
+ * HWIO conv kernels, [in,out] dense kernel, [classes] bias: what a TF checkpoint holds, utils/
+ * checkpoint_utils.py) and the stored one (`stored`: info.size floats at info.offset of its buffer --
+ * OHWI kernels, dense rows / bias zero-padded to ld_logits).  Host arrays, no GPU: a C host converts a
+ * checkpoint tensor and copies it to params + offset (or state + offset) itself. */
+int acnn_variable_pack(const acnn_model* m, int i, const float* tf_values, float* stored);
+int acnn_variable_unpack(const acnn_model* m, int i, const float* stored, float* tf_values);
+
 /* The statically shaped activation / gradient / input buffers of the step (inside the workspace). */
 #define ACNN_I32 2
 typedef struct acnn_tensor_info {
@@ -173,6 +181,13 @@ int acnn_run_ops(acnn_model* m, int phase, int first, int last, void* stream);
 int acnn_clear_step_buffers(acnn_model* m, void* stream);
 /* Kind name of an op ("conv", "bn_act", ...), NULL when out of range. */
 const char* acnn_op_kind(const acnn_model* m, int phase, int index);
+
+/* Geometry of a GEMM op (kind "conv" | "conv_dgrad" | "conv_wgrad") as the plan states it, its
+ * algorithmic multiply-accumulates (the stem's k x k x 3 conv, not its space-to-depth form; the
+ * stride-2 transposed conv, not its zero-inserted stride-1 form) and the number of extra tiles its
+ * epilogue reads (add_src / mask_src): what a roofline needs.  ACNN_ERR_INVALID for other ops. */
+int acnn_op_conv_info(const acnn_model* m, int phase, int index, acnn_conv_geom* g, int64_t* alg_macs,
+                      int* aux_tiles);
 
 /* Canonical text of the layer plan (sizes, meta, variables, tensors, ops): returns the byte count
  * needed (including the terminator); writes at most cap bytes.  Test / debugging aid. */

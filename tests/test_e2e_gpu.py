@@ -55,7 +55,7 @@ def test_train_step_vs_oracles():
     # same-rounding oracle in fp32 and fp64 accumulation: their distance is the yardstick
     refs = {}
     for dt in (torch.float32, torch.float64):
-        it = PI.PlanInterpreter(rt.plan, dtype=dt, emulate_bf16=True)
+        it = PI.PlanInterpreter(rt.plan.python_mirror(), dtype=dt, emulate_bf16=True)
         it.set_weights(vs.vars)
         it.hp.update(lr=0.05, momentum=0.9, weight_decay=1e-4)
         lg, ce, l2 = it.train_step(x, lab, lam)
@@ -202,7 +202,7 @@ def test_full_size_step_properties():
     assert abs(float(db.double().sum())) < 1e-4
     assert torch.isfinite(rt.grads).all()
     # first BN after the stem: moving_mean = (1 - 0.997) * batch_mean (initial value 0)
-    bn0 = rt.plan.bns[0]
+    bn0 = rt.plan.python_mirror().bns[0]
     w = rt.slot_view(bn0.work)
     mean = w[2 * bn0.C:3 * bn0.C]
     mm = rt.pview(bn0.mm)

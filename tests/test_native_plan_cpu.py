@@ -180,3 +180,70 @@ def test_workspace_layout_is_disjoint_and_aligned():
 def test_native_runtime_has_no_cpu_path():
     with pytest.raises(_lib.AcnnError):
         native.NativeRuntime(native.NativeModel(ModelConfig(resnet_size=50), 1, 64, 64, training=False))
+
+
+def build_c_host(tmp_path):
+    """gcc (no nvcc, no torch) builds tests/c_host/acnn_host.c against include/acnn_model.h."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc") or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("gcc / CUDA headers not available")
+    native.lib()
+    libdir = os.path.join(ROOT, "assembled_cnn_b200")
+    exe = str(tmp_path / "acnn_host")
+    cmd = ["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           "-I", "/usr/local/cuda/include", os.path.join(ROOT, "tests", "c_host", "acnn_host.c"),
+           "-o", exe, "-L", libdir, "-l:libacnn.so", "-L", "/usr/local/cuda/lib64", "-lcudart", "-lm",
+           "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_plain_c_host_builds_the_plan(tmp_path):
+    """The header is C (not C++), and a C program gets the same plan without Python or a GPU."""
+    import subprocess
+    exe = build_c_host(tmp_path)
+    r = subprocess.run([exe, "plan"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    nm = native.NativeModel(ModelConfig(**ASSEMBLE), 8, 64, 64, training=True, mixup_type=1,
+                            label_smoothing=0.1)
+    s = nm.sizes
+    assert "plan: %d variables (first resnet_model/stage0/conv2d/kernel), %d parameters" % (
+        s.n_variables, s.param_elems) in r.stdout, r.stdout
+    assert "%d+%d+%d ops" % (s.n_forward, s.n_backward, s.n_update) in r.stdout
+
+
+def test_variable_pack_unpack_match_runtime_layouts():
+    """acnn_variable_pack / _unpack (TF checkpoint layout <-> flat-buffer layout, host arrays) against
+    the layout code of the Python side (oracle.plan_interp set_weights / get_tf share it with
+    runtime.Runtime.set_tf): HWIO -> OHWI kernels, [in,out] -> padded [ld][in] dense, padded bias."""
+    import numpy as np
+    import torch
+    from oracle import plan_interp as PI
+    flags = dict(ASSEMBLE, pool_type="gem", embedding_size=64, num_classes=10)
+    nm = native.NativeModel(ModelConfig(**flags), 2, 64, 64, training=True)
+    py = nm.python_mirror()
+    it = PI.PlanInterpreter(py, dtype=torch.float32)
+    g = torch.Generator().manual_seed(0)
+    vals = {n: torch.randn(p.tf_shape, generator=g)
+            for n, p in list(py.params.items()) + list(py.state.items())}
+    it.set_weights(vals)
+    l, vi = nm.lib, native.VariableInfo()
+    kinds = set()
+    for i in range(nm.sizes.n_variables):
+        assert l.acnn_variable_info_get(nm.handle, i, C.byref(vi)) == 0
+        name = vi.name.decode()
+        tf = np.ascontiguousarray(vals[name].numpy())
+        stored = np.full(vi.size, np.nan, dtype=np.float32)
+        assert l.acnn_variable_pack(nm.handle, i, tf.ctypes.data_as(C.c_void_p),
+                                    stored.ctypes.data_as(C.c_void_p)) == 0
+        flat = (it.params if vi.buffer == 0 else it.state)[vi.offset:vi.offset + vi.size].numpy()
+        assert np.array_equal(stored, flat), name
+        back = np.empty_like(tf)
+        assert l.acnn_variable_unpack(nm.handle, i, stored.ctypes.data_as(C.c_void_p),
+                                      back.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(back, tf), name
+        kinds.add(vi.kind.decode())
+    assert kinds == {"conv_kernel", "dense_kernel", "dense_bias", "gamma", "beta", "moving_mean",
+                     "moving_variance"}

@@ -227,7 +227,10 @@ def _train_step_parity(kw, model_ctor_kw, B, hw, label, e2e_grad_check=True):
     for dtype in ("fp32", "bf16"):
         rt = results[dtype]["rt"]
         plan = rt.plan
-        it = PI.PlanInterpreter(plan, dtype=torch.float64, emulate_bf16=False)
+        # the oracle's interpreter walks the Python plan: the same plan as the library's, op for op
+        # (tests/test_native_plan_cpu.py)
+        pyplan = plan.python_mirror()
+        it = PI.PlanInterpreter(pyplan, dtype=torch.float64, emulate_bf16=False)
         # re-run forward + backward on the GPU from the ORIGINAL weights (the step above updated them)
         rt.set_weights(vs32.vars)
         it.set_weights(vs32.vars)
@@ -250,8 +253,8 @@ def _train_step_parity(kw, model_ctor_kw, B, hw, label, e2e_grad_check=True):
         torch.cuda.synchronize()
         it.grads.zero_()
         # dbias is accumulated by the forward's softmax_ce op on both sides
-        it.run([op for op in plan.forward if op.kind == "softmax_ce"])
-        it.run(plan.backward)
+        it.run([op for op in pyplan.forward if op.kind == "softmax_ce"])
+        it.run(pyplan.backward)
         ge = sorted(((_nrel(rt.get_tf(n, rt.grads), it.get_tf(n, it.grads)), n) for n in names),
                     reverse=True)
         print("%s %s mode: backward given the forward, all %d gradient tensors: worst %.2e (%s) "
