@@ -540,6 +540,8 @@ def main():
                        "l2": ("L2 flushed (256 MiB write) between timed iterations" if flush else
                               "per-step working set (activations + gradients, several GB) >> 126 MB L2"),
                        "cuda_graph": tr.use_graph,
+                       "executor": ("libacnn model-level C ABI (acnn_create / acnn_bind / acnn_run_ops)"
+                                    if hasattr(rt.plan, "conv_info") else "python plan + per-op ctypes"),
                        "result": last if not isinstance(last, list) or len(last) <= 4 else last[:4]},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "images/sec", "ms_per_step": ms_e2e,

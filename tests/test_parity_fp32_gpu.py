@@ -132,6 +132,68 @@ def test_c2_assemble_forward_and_loss():
             assert _nrel(ev, ref[torch.float64][1]) < 3e-2
 
 
+def test_c2_full_size_batch256_224():
+    """BASELINE config 2 AT ITS OWN SIZE: Assemble-ResNet-50 forward + loss, batch 256, 224 x 224,
+    against the fp32 CPU oracle run on the same 256 images (forward only, torch.no_grad: seconds).
+      * fp32 mode, eval-mode forward + loss at batch 256: logits and CE within 1e-3;
+      * fp32 mode, training-mode forward (batch statistics) at batch 64 (its training runtime at 256
+        would not leave room for the other models of this test): logits within 1e-3;
+      * bf16 production mode at batch 256 -- the benchmarked configuration: training-mode logits and
+        eval-mode logits / CE, reported and bounded (bf16 storage: ~1e-2)."""
+    import gc
+    from assembled_cnn_b200 import model_fns as F
+    from oracle import model as M
+    hw, B, Bs = 224, 256, 64
+    x, lab, _ = _inputs(B, hw, seed=12)
+    onehot = torch.nn.functional.one_hot(lab.long(), 1001).float()
+    omodel, vs = _oracle_vars(ASSEMBLE, hw, torch.float32, seed_bn=23)
+    with torch.no_grad():
+        ref_tr = M.forward(omodel, vs, x, training=True)
+        ref_tr_s = M.forward(omodel, vs, x[:Bs], training=True)
+        _, ref_ce, _, ref_ev = M.loss_fn(omodel, vs, x, onehot, training=False, label_smoothing=0.1,
+                                         weight_decay=1e-4)
+    ref_ce = float(ref_ce)
+    _, vs32 = _oracle_vars(ASSEMBLE, hw, torch.float32, seed_bn=23)
+
+    def eval_forward(model):
+        rt = model.runtime(B, hw, hw, training=False, label_smoothing=0.1, with_loss=True)
+        m = rt.plan.meta
+        rt.t[m["images"]].copy_(x)
+        rt.t[m["labels"]].copy_(lab)
+        rt.run_forward()
+        return rt.t[m["logits"]][:, :1001].float().cpu(), float(rt.slot_view(m["loss"])[0])
+
+    ctor = dict(num_classes=1001, resnet_version=2, use_sk_block=True, anti_alias_type="sconv",
+                anti_alias_filter_size=3)
+    # fp32 mode
+    model = F.Model(50, dtype="fp32", **ctor)
+    model.set_weights(vs32.vars)
+    ev, ce = eval_forward(model)
+    e_ev, e_ce = _nrel(ev, ref_ev), abs(ce - ref_ce) / abs(ref_ce)
+    got = model(x[:Bs], training=True).float().cpu()
+    e_tr = _nrel(got, ref_tr_s)
+    print("C2 full size, fp32 mode: eval logits B=256 %.2e, CE %.6f vs %.6f (rel %.2e); training-mode "
+          "logits B=64 %.2e" % (e_ev, ce, ref_ce, e_ce, e_tr))
+    assert e_ev < TOL and e_ce < TOL and e_tr < TOL
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+    # bf16 production mode, batch 256
+    model = F.Model(50, dtype="bf16", **ctor)
+    model.set_weights(vs32.vars)
+    ev, ce = eval_forward(model)
+    got = model(x, training=True).float().cpu()
+    b_ev, b_ce, b_tr = _nrel(ev, ref_ev), abs(ce - ref_ce) / abs(ref_ce), _nrel(got, ref_tr)
+    print("C2 full size, bf16 mode B=256: eval logits %.2e, CE rel %.2e; training-mode logits %.2e; "
+          "argmax agreement eval %.3f / train %.3f"
+          % (b_ev, b_ce, b_tr, float((ev.argmax(1) == ref_ev.argmax(1)).float().mean()),
+             float((got.argmax(1) == ref_tr.argmax(1)).float().mean())))
+    assert b_ev < 3e-2 and b_ce < 1e-2 and b_tr < 1e-1
+    del model
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
 def _train_step_parity(kw, model_ctor_kw, B, hw, label, e2e_grad_check=True):
     from assembled_cnn_b200.model_fns import Model, Trainer
     from assembled_cnn_b200.hparams import params_from_flags

@@ -187,6 +187,26 @@ def test_product_plan_inventory_matches_reference_code(name):
     assert hashlib.sha256(st.encode()).hexdigest() == gold["state_sha256"]
 
 
+@pytest.mark.parametrize("name", sorted(mg.CONFIGS))
+def test_native_plan_inventory_matches_reference_code(name):
+    """The same for the plan the product executes -- built in C++ behind acnn_create
+    (csrc/model_plan.cu, include/acnn_model.h): acnn_variable_info_get lists the reference's variables
+    in the reference's creation order with the reference's names and TF-layout shapes."""
+    import ctypes as C
+    from assembled_cnn_b200 import native
+    from assembled_cnn_b200.plan import ModelConfig
+    flags, d, batch, size = mg.CONFIGS[name]
+    gold = GOLD[name]
+    nm = native.NativeModel(ModelConfig(use_resnet_d=d, **flags), 2, 64, 64, training=True)
+    vi, rows = native.VariableInfo(), {0: [], 1: []}
+    for i in range(nm.sizes.n_variables):
+        assert nm.lib.acnn_variable_info_get(nm.handle, i, C.byref(vi)) == 0
+        rows[vi.buffer].append("%s|%s" % (vi.name.decode(), ",".join(map(str, vi.tf_shape[:vi.tf_rank]))))
+    assert len(rows[0]) == gold["num_trainable"]
+    assert hashlib.sha256("\n".join(rows[0]).encode()).hexdigest() == gold["trainable_sha256"]
+    assert hashlib.sha256("\n".join(rows[1]).encode()).hexdigest() == gold["state_sha256"]
+
+
 # ---------------------------------------------------------------------------------------------
 # SURVEY 8(f) rows against the reference's own code: DropBlock, GeM pooling, KD teacher mixup
 # (the GeM / embedding / flatten model configurations are part of mg.CONFIGS above)
@@ -255,3 +275,7 @@ def test_dropblock_through_the_whole_reference_model(name):
     plan = build_plan(ModelConfig(**flags), batch, size, size, training=True, use_dropblock=True)
     plan_shapes = [[1] + list(plan.tensors[n].shape) for n in plan.meta["dropblock_u"]]
     assert plan_shapes == shapes
+    # ... and so does the plan the library builds (acnn_find_tensor("dropblock_u", k))
+    from assembled_cnn_b200 import native
+    nm = native.NativeModel(ModelConfig(**flags), batch, size, size, training=True, use_dropblock=True)
+    assert [[1] + list(nm.tensors[n].shape) for n in nm.meta["dropblock_u"]] == shapes

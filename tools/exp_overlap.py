@@ -1,4 +1,5 @@
 import os, sys, time
+os.environ.setdefault('ACNN_NATIVE_PLAN', '0')   # per-op hooks live in the Python executor (same plan, same launches)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from assembled_cnn_b200.hparams import params_from_flags

@@ -9,6 +9,7 @@ the graph, which is what fusing it away would recover.
 """
 import argparse
 import os
+os.environ.setdefault('ACNN_NATIVE_PLAN', '0')   # per-op hooks live in the Python executor (same plan, same launches)
 import sys
 from collections import Counter
 

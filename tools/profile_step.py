@@ -7,6 +7,7 @@ warm-up so `-s/-c` can select it).
 """
 import argparse
 import os
+os.environ.setdefault('ACNN_NATIVE_PLAN', '0')   # per-op hooks live in the Python executor (same plan, same launches)
 import sys
 from collections import defaultdict
 
