@@ -7,7 +7,12 @@ PARITY UNPINNED at the level of this file: the reference (clovaai/assembled-cnn)
 golden vectors for this path and its arithmetic lives in the un-vendored dependency
 tensorflow==1.14.0 (README.md:85), which cannot be installed here (Python 3.12, no network).  This
 file restates the published TF-1.14 semantics at the reference's own call sites (file:line below);
-tests/test_oracle_known_answers.py pins each rule with hand-computed micro-vectors.  What IS pinned
+tests/test_oracle_known_answers.py pins each rule with hand-computed micro-vectors, and
+tests/test_oracle_independent_pins_cpu.py checks every rule that is a convention rather than arithmetic
+against an implementation written and validated against TensorFlow by somebody else (Hugging Face's
+port of the TF BiT checkpoints for 'SAME' padding, ATen's BatchNorm / cross_entropy(label_smoothing) /
+SGD / avg_pool2d(count_include_pad=False) kernels, scipy.ndimage 'mirror' correlation) -- independent,
+but still not TensorFlow itself.  What IS pinned
 against the reference itself is the model assembly built on these primitives: oracle/model.py is
 checked against golden vectors produced by executing the reference's own model code through a
 TF-API stand-in (tests/golden/make_reference_shim_golden.py, tests/test_reference_shim_golden_cpu.py).

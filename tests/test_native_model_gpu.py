@@ -251,7 +251,8 @@ def test_model_facade_runs_on_the_native_path():
 
 def test_plain_c_host_trains(tmp_path):
     """tests/c_host/acnn_host.c: cudaMalloc'd buffers, host-drawn initializers, host input arrays, three
-    acnn_step calls on the same batch -- finite losses that decrease."""
+    acnn_step calls -- finite, plausible losses and weights that move (the numbers of this call sequence
+    are checked against the oracle in test_c_abi_call_sequence_with_host_arrays_against_oracle)."""
     import subprocess
     from test_native_plan_cpu import build_c_host
     exe = build_c_host(tmp_path)
