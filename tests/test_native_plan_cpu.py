@@ -247,3 +247,79 @@ def test_variable_pack_unpack_match_runtime_layouts():
         kinds.add(vi.kind.decode())
     assert kinds == {"conv_kernel", "dense_kernel", "dense_bias", "gamma", "beta", "moving_mean",
                      "moving_variance"}
+
+
+# --------------------------------------------------------------------------------------------------
+# Property test over the flag space: for ANY flag combination the two plan builders either both refuse
+# or produce the same plan (hypothesis, derandomised: the same examples on every run).
+# --------------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+
+@st.composite
+def _flag_sets(draw, poisoned=False):
+    # poisoned: exactly one value that one of the argument checks refuses
+    poison = draw(st.sampled_from(["size", "filter", "pool", "embedding", "width", "db_se"])) if poisoned \
+        else None
+    version = draw(st.sampled_from([1, 2]))
+    size = draw(st.sampled_from([50, 50, 50, 101, 152] + ([200] if version == 1 else [])))
+    aa = draw(st.sampled_from(["sconv", "proj"] if poison == "filter" else
+                              ["", "sconv", "sconv", "proj", "sconv,proj"]))
+    flags = dict(
+        resnet_size=draw(st.sampled_from([18, 51] + ([200] if version == 2 else [34]))) if poison == "size"
+        else size,
+        resnet_version=version,
+        use_sk_block=draw(st.booleans()), use_se_block=draw(st.booleans()),
+        use_resnet_d=draw(st.booleans()), zero_gamma=draw(st.booleans()),
+        no_downsample=draw(st.booleans()), anti_alias_type=aa,
+        anti_alias_filter_size=(draw(st.sampled_from([0, 9])) if poison == "filter"
+                                else draw(st.sampled_from([1, 2, 3, 3, 4, 5, 7]))),
+        pool_type="max" if poison == "pool" else draw(st.sampled_from(["gap", "gap", "gem", "flatten"])),
+        embedding_size=48 if poison == "embedding" else draw(st.sampled_from([0, 0, 32, 64])),
+        bl_alpha=draw(st.sampled_from([1, 2, 4])), bl_beta=draw(st.sampled_from([1, 2, 4, 8])),
+        num_classes=draw(st.sampled_from([1001, 10, 128])),
+        bn_momentum=draw(st.sampled_from([0.997, 0.9])))
+    training = draw(st.booleans())
+    dropblock = poison == "db_se" or (draw(st.booleans()) and draw(st.booleans()))
+    if poison == "db_se":
+        flags["use_se_block"], training = True, True
+    elif dropblock:
+        flags["use_se_block"] = False
+    hw = (224, 224) if dropblock else (draw(st.sampled_from([32, 64, 96])),
+                                      100 if poison == "width" else draw(st.sampled_from([32, 64])))
+    kw = dict(training=training, mixup_type=draw(st.sampled_from([0, 0, 1, 2])),
+              label_smoothing=draw(st.sampled_from([0.0, 0.1])), with_loss=draw(st.booleans()),
+              dtype=draw(st.sampled_from(["bf16", "bf16", "fp32"])), use_dropblock=dropblock,
+              kd_temp=draw(st.sampled_from([0.0, 0.0, 2.0])))
+    return flags, draw(st.integers(1, 5)), hw, kw
+
+
+def _both(case):
+    flags, B, (H, W), kw = case
+    try:
+        py = dump(build_plan(ModelConfig(**flags), B, H, W, **kw))
+    except (ValueError, NotImplementedError, KeyError, AssertionError, ZeroDivisionError):
+        py = None
+    try:
+        nm = native.NativeModel(ModelConfig(**flags), B, H, W, **kw)
+        cc = nm.dump()
+        nm.close()
+    except (_lib.AcnnError, ValueError):
+        cc = None
+    return py, cc
+
+
+@settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(_flag_sets())
+def test_native_and_python_plans_agree_over_the_flag_space(case):
+    py, cc = _both(case)
+    assert py is not None, ("the Python builder refused a valid flag set", case)
+    assert cc is not None, ("acnn_create refused: " + native.lib().acnn_last_error().decode(), case)
+    assert py == cc, (case, _diff(py, cc))
+
+
+@settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(_flag_sets(poisoned=True))
+def test_native_and_python_plans_refuse_the_same_flag_sets(case):
+    py, cc = _both(case)
+    assert py is None and cc is None, (case, py is None, cc is None)
