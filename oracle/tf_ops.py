@@ -3,19 +3,22 @@
 TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is imported by the product package; only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may call it.
 
-PARITY UNPINNED at the level of this file: the reference (clovaai/assembled-cnn) ships no tests or
+PARITY UNPINNED AGAINST TENSORFLOW ITSELF: the reference (clovaai/assembled-cnn) ships no tests or
 golden vectors for this path and its arithmetic lives in the un-vendored dependency
 tensorflow==1.14.0 (README.md:85), which cannot be installed here (Python 3.12, no network).  This
-file restates the published TF-1.14 semantics at the reference's own call sites (file:line below);
-tests/test_oracle_known_answers.py pins each rule with hand-computed micro-vectors, and
-tests/test_oracle_independent_pins_cpu.py checks every rule that is a convention rather than arithmetic
-against an implementation written and validated against TensorFlow by somebody else (Hugging Face's
-port of the TF BiT checkpoints for 'SAME' padding, ATen's BatchNorm / cross_entropy(label_smoothing) /
-SGD / avg_pool2d(count_include_pad=False) kernels, scipy.ndimage 'mirror' correlation) -- independent,
-but still not TensorFlow itself.  What IS pinned
-against the reference itself is the model assembly built on these primitives: oracle/model.py is
-checked against golden vectors produced by executing the reference's own model code through a
-TF-API stand-in (tests/golden/make_reference_shim_golden.py, tests/test_reference_shim_golden_cpu.py).
+file restates the published TF-1.14 semantics at the reference's own call sites (file:line below).
+What it IS pinned against:
+  * hand-computed micro-vectors per rule (tests/test_oracle_known_answers.py);
+  * implementations written and validated against TensorFlow by others, rule by rule
+    (tests/test_oracle_independent_pins_cpu.py: Hugging Face's port of the TF BiT checkpoints for 'SAME'
+    padding, ATen's BatchNorm / cross_entropy(label_smoothing) / SGD / avg_pool2d(count_include_pad=
+    False) kernels, scipy.ndimage 'mirror' correlation);
+  * the reference's OWN model code executed end to end on those third-party kernels in float64
+    (tests/golden/tf1_shim no longer imports this file: its convolution padding is Hugging Face's, its
+    batch norm ATen's): the golden vectors of tests/golden/make_reference_shim_golden.py hold
+    inference- and training-mode logits, moving statistics, loss and gradient digests of 11
+    configurations up to ResNet-152 plus DropBlock through the whole model, and oracle/model.py built
+    on this file reproduces them to 1e-6 in float64 (tests/test_reference_shim_golden_cpu.py).
 
 All tensors are torch CPU tensors, activations NHWC (the reference's CPU layout,
 nets/resnet_model.py:196-198), conv kernels HWIO, dense kernels [in, out].

@@ -9,9 +9,12 @@ What the shim pins and what it does not:
   * pinned: everything the reference's Python decides (which ops, in which order, with which
     arguments; variable names / shapes / creation order through a faithful re-implementation of
     the TF1 variable_scope / tf.layers naming rules; initializer kinds);
-  * not pinned: the numerical semantics of the individual TF kernels (conv SAME padding, pooling
-    windows, fused batch norm): those are taken from oracle/tf_ops.py, the same primitives the
-    oracle uses, restated from the TF documentation.
+  * the numerical semantics of the individual TF kernels are NOT taken from the oracle: the kernels of
+    this stand-in are other people's code -- 'SAME' padding (convolutions and pools) is Hugging Face's
+    `DynamicPad2d` (transformers.models.bit, the port of Google's TF BiT checkpoints), fused batch
+    norm is ATen's `torch.nn.functional.batch_norm` (biased variance to normalise, unbiased variance
+    into the moving average), convolution / pooling arithmetic is ATen's -- so the golden vectors pin
+    oracle/tf_ops.py against implementations it shares no code with.  Still not TensorFlow itself.
 Layout: NHWC only (`tf.test.is_built_with_cuda()` is False, so the reference picks channels_last).
 """
 import contextlib
@@ -23,32 +26,56 @@ import torch
 
 _REPO = os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "..", ".."))
 sys.path.insert(0, _REPO)
-from oracle import tf_ops as _ops  # noqa: E402
-
 __version__ = "1.14.0-shim"
+# TF_SHIM_FLOAT64=1: the stand-in's tf.float32 computes in float64, so that golden vectors of
+# ill-conditioned quantities (training-mode logits of deep nets on a batch of 2) do not depend on the
+# summation order of whichever kernels produced them
+_F32 = torch.float64 if os.environ.get("TF_SHIM_FLOAT64") == "1" else torch.float32
+_NPF32 = np.float64 if _F32 == torch.float64 else np.float32
 import torch.nn.functional as _F  # noqa: E402
+from transformers.models.bit.modeling_bit import DynamicPad2d as _TFSamePad  # noqa: E402
 
 
 # ----------------------------------------------------------------------------- generic TF kernels
-def _pool_pads(t, k, s, padding):
+# (deliberately NOT oracle/tf_ops.py: see the module docstring)
+def _same_pad(x_nchw, k, s, value=0.0):
+    """TF 'SAME' padding of an NCHW tensor by Hugging Face's port of the rule."""
+    return _TFSamePad(k, s, 1, value=value)(x_nchw)
+
+
+def _conv2d(x_nhwc, w_hwio, stride, padding):
+    """tf.nn.conv2d / tf.layers.conv2d (no bias) on NHWC input with an HWIO kernel."""
+    x = x_nhwc.permute(0, 3, 1, 2)
     if padding == "SAME":
-        return _ops._same_pads(t.shape[1], k, s), _ops._same_pads(t.shape[2], k, s)
-    return (0, 0), (0, 0)
+        x = _same_pad(x, (w_hwio.shape[0], w_hwio.shape[1]), stride)
+    else:
+        assert padding == "VALID", padding
+    return _F.conv2d(x, w_hwio.permute(3, 2, 0, 1), stride=stride).permute(0, 2, 3, 1)
+
+
+def _batch_norm(x, gamma, beta, mm, mv, training, momentum, eps):
+    """tf.layers.batch_normalization(fused=True) by ATen's kernel (torch's momentum is 1 - TF's).
+    Returns (y, new_moving_mean, new_moving_variance)."""
+    rm, rv = mm.detach().clone(), mv.detach().clone()
+    y = _F.batch_norm(x.permute(0, 3, 1, 2), rm, rv, gamma, beta, bool(training), 1.0 - momentum, eps)
+    return y.permute(0, 2, 3, 1), rm, rv
 
 
 def _max_pool(t, k, s, padding):
     """tf.nn.max_pool: SAME pads with -inf, the odd cell after."""
-    (pt, pb), (pl, pr) = _pool_pads(t, k, s, padding)
-    x = _F.pad(t.permute(0, 3, 1, 2), (pl, pr, pt, pb), value=float("-inf"))
+    x = t.permute(0, 3, 1, 2)
+    if padding == "SAME":
+        x = _same_pad(x, k, s, value=float("-inf"))
     return _F.max_pool2d(x, k, s).permute(0, 2, 3, 1)
 
 
 def _avg_pool(t, k, s, padding):
     """tf.nn.avg_pool: VALID divides by k*k; SAME divides by the number of in-bounds cells."""
-    (pt, pb), (pl, pr) = _pool_pads(t, k, s, padding)
-    x = _F.pad(t.permute(0, 3, 1, 2), (pl, pr, pt, pb))
-    ssum = _F.avg_pool2d(x, k, s) * float(k * k)
-    ones = _F.pad(torch.ones(1, 1, t.shape[1], t.shape[2], dtype=t.dtype), (pl, pr, pt, pb))
+    x = t.permute(0, 3, 1, 2)
+    if padding != "SAME":
+        return _F.avg_pool2d(x, k, s).permute(0, 2, 3, 1)
+    ssum = _F.avg_pool2d(_same_pad(x, k, s), k, s) * float(k * k)
+    ones = _same_pad(torch.ones(1, 1, t.shape[1], t.shape[2], dtype=t.dtype), k, s)
     cnt = _F.avg_pool2d(ones, k, s) * float(k * k)
     return (ssum / cnt).permute(0, 2, 3, 1)
 
@@ -74,7 +101,7 @@ class DType:
         return "tf." + self.name
 
 
-float32 = DType("float32", torch.float32)
+float32 = DType("float32", _F32)
 float16 = DType("float16", torch.float16)
 int32 = DType("int32", torch.int32, False)
 _BY_TORCH = {torch.float32: float32, torch.float16: float16, torch.int32: int32,
@@ -92,7 +119,7 @@ def _raw(x):
     if isinstance(x, (list, tuple)) and x and isinstance(x[0], Tensor):
         return torch.stack([e.t for e in x], 0)        # a Python list of tensors converts by stacking
     if isinstance(x, (list, tuple, np.ndarray)):
-        return torch.as_tensor(np.asarray(x, dtype=np.float32))
+        return torch.as_tensor(np.asarray(x, dtype=_NPF32))
     return x
 
 
@@ -100,6 +127,8 @@ class Tensor:
     """Eager tensor with the handful of members the reference uses."""
 
     def __init__(self, t, name=None):
+        if _F32 is torch.float64 and torch.is_tensor(t) and t.dtype == torch.float32:
+            t = t.double()                 # float64 override: "tf.float32" data computes in float64
         self.t = t
         self.name = name
 
@@ -239,13 +268,13 @@ def _base_getter(name, shape=None, dtype=float32, initializer=None, trainable=Tr
     if variables.values is not None:
         v = variables.values[name]
         assert tuple(v.shape) == shape, (name, tuple(v.shape), shape)
-        v = v.clone().float()
+        v = v.clone().to(_F32)
     elif kind == "ones":
-        v = torch.ones(shape)
+        v = torch.ones(shape, dtype=_F32)
     elif kind == "constant":
-        v = torch.full(shape, initializer.value)
+        v = torch.full(shape, initializer.value, dtype=_F32)
     else:
-        v = torch.zeros(shape)
+        v = torch.zeros(shape, dtype=_F32)
     variables.order.append((name, shape, kind, bool(trainable)))
     if variables.requires_grad and trainable:
         v.requires_grad_(True)
@@ -279,7 +308,7 @@ class _Layers:
         cin = inputs.shape[-1]
         with self._scope(name, "conv2d"):
             w = get_variable("kernel", (k[0], k[1], cin, filters), initializer=kernel_initializer)
-            y = _ops.conv2d(inputs.t, w.t, strides, padding.upper())
+            y = _conv2d(inputs.t, w.t, strides, padding.upper())
             if use_bias:
                 y = y + get_variable("bias", (filters,), initializer=zeros_initializer()).t
         return Tensor(y)
@@ -293,8 +322,8 @@ class _Layers:
             beta = get_variable("beta", (c,), initializer=zeros_initializer())
             mm = get_variable("moving_mean", (c,), initializer=zeros_initializer(), trainable=False)
             mv = get_variable("moving_variance", (c,), initializer=ones_initializer(), trainable=False)
-        y, new_mm, new_mv = _ops.batch_norm(inputs.t, gamma.t, beta.t, mm.t, mv.t, bool(training),
-                                            momentum, epsilon)
+        y, new_mm, new_mv = _batch_norm(inputs.t, gamma.t, beta.t, mm.t, mv.t, bool(training),
+                                        momentum, epsilon)
         if training:                       # the UPDATE_OPS the reference's train op depends on
             mm.t, mv.t = new_mm.detach(), new_mv.detach()
         return Tensor(y)
@@ -355,11 +384,11 @@ class _NN:
             # reference's anti-alias filter relies on
             assert w.shape[2] == 1 and w.shape[3] == x.shape[3]
             return Tensor(_depthwise(x, w, strides[1], padding))
-        return Tensor(_ops.conv2d(x, w, strides[1], padding))
+        return Tensor(_conv2d(x, w, strides[1], padding))
 
 
 nn = _NN()
-nn.l2_loss = staticmethod(lambda t, name=None: Tensor((_raw(t).float() ** 2).sum() / 2))
+nn.l2_loss = staticmethod(lambda t, name=None: Tensor((_raw(t).to(_F32) ** 2).sum() / 2))
 
 
 def _axes(axis):
@@ -388,12 +417,12 @@ def concat(xs, axis, name=None): return Tensor(torch.cat([_raw(x) for x in xs], 
 def stack(xs, axis=0, name=None): return Tensor(torch.stack([torch.as_tensor(_raw(x)) for x in xs], dim=axis))
 def identity(x, name=None): return x
 def cast(x, dtype, name=None): return Tensor(torch.as_tensor(_raw(x)).to(dtype.torch))
-def to_float(x): return Tensor(torch.as_tensor(_raw(x), dtype=torch.float32))
+def to_float(x): return Tensor(torch.as_tensor(_raw(x), dtype=_F32))
 def multiply(a, b, name=None):
     r = torch.as_tensor(_raw(a)) * torch.as_tensor(_raw(b))
     return Tensor(r)
-def pow(x, p, name=None): return Tensor(torch.pow(torch.as_tensor(_raw(x), dtype=torch.float32), _raw(p)))
-def maximum(a, b, name=None): return Tensor(torch.maximum(_raw(a), torch.as_tensor(_raw(b), dtype=torch.float32)))
+def pow(x, p, name=None): return Tensor(torch.pow(torch.as_tensor(_raw(x), dtype=_F32), _raw(p)))
+def maximum(a, b, name=None): return Tensor(torch.maximum(_raw(a), torch.as_tensor(_raw(b), dtype=_F32)))
 def clip_by_value(x, lo, hi, name=None): return Tensor(torch.clamp(_raw(x), lo, hi))
 def sign(x, name=None): return Tensor(torch.sign(_raw(x)))
 def size(x, name=None): return Tensor(torch.tensor(_raw(x).numel()))
@@ -545,7 +574,7 @@ class _Losses:
     def softmax_cross_entropy(onehot_labels, logits, weights=1.0, label_smoothing=0, **kw):
         """tf.losses.softmax_cross_entropy: labels smoothed towards 1/num_classes, per-example
         cross entropy, reduction SUM_BY_NONZERO_WEIGHTS (= batch mean for a scalar weight)."""
-        y, z = _raw(onehot_labels).float(), _raw(logits).float()
+        y, z = _raw(onehot_labels).to(_F32), _raw(logits).to(_F32)
         if label_smoothing > 0:
             n = y.shape[1]
             y = y * (1 - label_smoothing) + label_smoothing / n

@@ -1,7 +1,9 @@
 """Known-answer micro-vectors that pin the oracle to the TF-1.14 semantics the reference relies on
-(SURVEY App. B).  The reference ships no tests for this path, so these hand-computed vectors are
-the pin of the TF kernel semantics ("parity unpinned" by the reference itself -- see oracle/tf_ops.py
-header; the model assembly is pinned separately by tests/test_reference_shim_golden_cpu.py)."""
+(SURVEY App. B).  The reference ships no tests for this path and TensorFlow 1.14 cannot be installed,
+so these hand-computed vectors are one of three pins of the TF kernel semantics (see the header of
+oracle/tf_ops.py): the others are third-party implementations rule by rule
+(tests/test_oracle_independent_pins_cpu.py) and the reference's own model code executed on third-party
+kernels in float64 (tests/test_reference_shim_golden_cpu.py)."""
 import math
 
 import torch
