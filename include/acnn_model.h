@@ -147,7 +147,10 @@ int acnn_find_tensor(const acnn_model* m, const char* role, int index);
 /* Records the caller-owned device buffers, lays the workspace out and enqueues its one-time
  * initialisation on `stream` (memset, weight descriptor table, decay flags, default hp).  grads /
  * momentum / w_dgrad may be NULL for an inference handle.  Variables are NOT initialised here (the
- * caller loads a checkpoint or draws the reference's initializers); moving variances must be set. */
+ * caller loads a checkpoint or draws the reference's initializers); moving variances must be set.
+ * The row counts of the partial-statistics buffers (acnn_conv_stats_parts() ...) are resolved here: set
+ * the tuning knobs of acnn.h that change them (acnn_set_conv_cta_pairs / _halo / _mtiles ...) BEFORE
+ * binding, or bind again after changing one. */
 int acnn_bind(acnn_model* m, float* params, float* grads, float* momentum, float* state,
               void* w_fprop, void* w_dgrad, void* workspace, void* stream);
 
