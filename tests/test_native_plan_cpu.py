@@ -323,3 +323,40 @@ def test_native_and_python_plans_agree_over_the_flag_space(case):
 def test_native_and_python_plans_refuse_the_same_flag_sets(case):
     py, cc = _both(case)
     assert py is None and cc is None, (case, py is None, cc is None)
+
+
+def test_op_conv_info_gives_the_algorithmic_flops_of_the_survey():
+    """acnn_op_conv_info (what bench.py's roofline reads): geometry of every GEMM op of the library's C3
+    plan equals the Python plan's, and the ALGORITHMIC multiply-accumulates add up to SURVEY 8(d)'s
+    34.12 GFLOP per image for the Assemble-ResNet-50 training step (11.45 forward), while the executed
+    ones are higher (space-to-depth stem, zero-inserted stride-2 dgrads)."""
+    B = 8
+    kw = dict(training=True, mixup_type=1, label_smoothing=0.1)
+    nm = native.NativeModel(ModelConfig(**ASSEMBLE), B, 224, 224, **kw)
+    py = build_plan(ModelConfig(**ASSEMBLE), B, 224, 224, **kw)
+    alg = executed = fwd = 0
+    n = 0
+    for nops, pops in ((nm.forward, py.forward), (nm.backward, py.backward)):
+        for nop, pop in zip(nops, pops):
+            if nop.kind not in ("conv", "conv_dgrad", "conv_wgrad"):
+                continue
+            g, macs, aux = nm.conv_info(nop)
+            pg = pop.geom
+            assert (g.B, g.H, g.W, g.Cin, g.Cout, g.kh, g.kw, g.stride, g.pad_h_lo, g.pad_h_hi, g.pad_w_lo,
+                    g.pad_w_hi) == pg.astuple()
+            ex = pg.B * pg.Ho * pg.Wo * pg.Cout * pg.kh * pg.kw * pg.Cin
+            assert macs == (pop.a.get("alg_macs") or ex)
+            assert aux == (pop.a.get("add_src") is not None) + (pop.a.get("mask_src") is not None)
+            alg += macs
+            executed += ex
+            fwd += macs if nop.phase == 0 else 0
+            n += 1
+    assert n == 230                                           # tcgen05 launches of a step
+    gflop = 2.0 * alg / B / 1e9
+    assert abs(gflop - 34.12) < 0.15 and abs(2.0 * fwd / B / 1e9 - 11.45) < 0.1, (gflop, fwd)
+    assert executed > alg
+    # a non-GEMM op is refused with a status code
+    import ctypes as C
+    g, m, a = _lib.ConvGeom(), C.c_int64(), C.c_int()
+    bn = next(op for op in nm.forward if op.kind == "bn_act")
+    assert nm.lib.acnn_op_conv_info(nm.handle, 0, bn.index, C.byref(g), C.byref(m), C.byref(a)) == 1
