@@ -261,6 +261,8 @@ LR_CASES = {   # name -> kwargs of functions/model_fns.py learning_rate_with_dec
                   piecewise_lr_boundary_epochs=[30], piecewise_lr_decay_rates=[1, 0.1], base_lr=0.05,
                   warmup_epochs=0, train_epochs=100),
 }
+KEEP_PROB_CASES = {"assemble_600_epochs_b1024": (1.0, 0.9, int(600 * 1281167 / 1024)),
+                   "short": (1.0, 0.7, 10000)}
 LR_STEPS = [0, 1, 100, 1250, 2501, 6254, 6256, 10000, 150134, 150136, 300000, 450408, 700000]
 
 
@@ -358,6 +360,11 @@ def run_train_pieces():
     for name, kw in LR_CASES.items():
         fn = lr_with_decay(**kw)
         out["lr_" + name] = [float(tf._raw(fn(tf.Tensor(torch.tensor(s))))) for s in LR_STEPS]
+    # functions/model_fns.py:26-33 keep_prob_decay (the DropBlock schedule, :221-228)
+    kp_decay, tf = reference_function("functions/model_fns.py", "keep_prob_decay")
+    for name, (kp0, kp1, steps) in KEEP_PROB_CASES.items():
+        fn = kp_decay(kp0, kp1, steps)
+        out["keep_prob_" + name] = [float(tf._raw(fn(tf.Tensor(torch.tensor(s))))) for s in LR_STEPS]
     return out
 
 

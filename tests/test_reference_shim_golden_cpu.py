@@ -232,6 +232,16 @@ def test_flag_names_and_defaults_match_reference_code():
                                         "loss_scale", "data_format", "num_gpus"}
 
 
+@pytest.mark.parametrize("case", sorted(mg.KEEP_PROB_CASES))
+def test_keep_prob_schedule_matches_reference_code(case):
+    """functions/model_fns.py:26-33 keep_prob_decay (tf.train.polynomial_decay, power 1, no cycle) executed
+    from the reference's source: the product's host-side schedule (Trainer feeds hp[4] from it)."""
+    from assembled_cnn_b200.model_fns import keep_prob_decay
+    fn = keep_prob_decay(*mg.KEEP_PROB_CASES[case])
+    for step, want in zip(mg.LR_STEPS, PIECES["keep_prob_" + case]):
+        assert abs(fn(step) - want) < 1e-6, (case, step, fn(step), want)
+
+
 @pytest.mark.parametrize("name", sorted(mg.CONFIGS))
 def test_product_plan_inventory_matches_reference_code(name):
     """The product's own layer plan (assembled_cnn_b200/plan.py): trainable variables in the reference's
