@@ -127,6 +127,21 @@ def reference_function(rel_path, name):
     return ns[name], tf
 
 
+def reference_if_blocks(rel_path, func_name, test_src):
+    """The `if <test_src>:` statements inside one function of a reference module, each compiled on its
+    own (for code the reference writes inline in a long function, e.g. the knowledge-distillation
+    branches of resnet_model_fn), to be exec'd in a namespace holding the names they read."""
+    import ast
+    sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
+    import tensorflow as tf
+    src = open(os.path.join("/root/reference", rel_path)).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == func_name)
+    blocks = sorted((n for n in ast.walk(fn) if isinstance(n, ast.If) and ast.unparse(n.test) == test_src),
+                    key=lambda n: n.lineno)            # source order (ast.walk is breadth-first)
+    return [compile(ast.fix_missing_locations(ast.Module(body=[b], type_ignores=[])), rel_path, "exec")
+            for b in blocks], tf
+
+
 def run_reference(flags, use_resnet_d, batch, size):
     sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
     sys.path.insert(0, "/root/reference")
@@ -290,6 +305,19 @@ def dropblock_inputs():
     return torch.randn(2, 12, 12, 4, generator=g), torch.rand(1, 6, 6, 4, generator=g)
 
 
+KD_TEMP, KD_B, KD_NC = 2.0, 6, 11
+
+
+def kd_inputs():
+    """(logits, kd label tensor = one-hot labels ++ teacher logits, as the reference's input pipeline
+    delivers it: nets/run_loop_classification.py:86-93)."""
+    g = torch.Generator().manual_seed(77)
+    logits = 2.0 * torch.randn(KD_B, KD_NC, generator=g)
+    onehot = torch.nn.functional.one_hot(torch.randint(0, KD_NC, (KD_B,), generator=g), KD_NC).float()
+    teacher_logits = 3.0 * torch.randn(KD_B, KD_NC, generator=g)
+    return logits, torch.cat([onehot, teacher_logits], 1)
+
+
 def loss_inputs():
     g = torch.Generator().manual_seed(78)
     logits = torch.randn(6, 11, generator=g) * 3
@@ -360,6 +388,18 @@ def run_train_pieces():
     for name, kw in LR_CASES.items():
         fn = lr_with_decay(**kw)
         out["lr_" + name] = [float(tf._raw(fn(tf.Tensor(torch.tensor(s))))) for s in LR_STEPS]
+    # nets/run_loop_classification.py:89-96 and :156-162: the two `if p['kd_temp'] > 0:` branches of
+    # resnet_model_fn (label split + temperatured teacher softmax; T^2 * CE(logits / T, teacher))
+    blocks, tf = reference_if_blocks("nets/run_loop_classification.py", "resnet_model_fn", "p['kd_temp'] > 0")
+    assert len(blocks) == 2, len(blocks)
+    logits, kd_labels = kd_inputs()
+    env = {"tf": tf, "p": {"kd_temp": KD_TEMP}, "labels": tf.Tensor(kd_labels), "logits": tf.Tensor(logits)}
+    for b in blocks:
+        exec(b, env)
+    out["kd"] = {"temp": KD_TEMP, "cross_entropy_kd": float(tf._raw(env["cross_entropy_kd"])),
+                 "teacher_labels": digest(tf._raw(env["teacher_labels"])),
+                 "teacher_row0": [float(v) for v in tf._raw(env["teacher_labels"])[0]],
+                 "onehot": digest(tf._raw(env["onehot_labels"]))}
     # functions/model_fns.py:26-33 keep_prob_decay (the DropBlock schedule, :221-228)
     kp_decay, tf = reference_function("functions/model_fns.py", "keep_prob_decay")
     for name, (kp0, kp1, steps) in KEEP_PROB_CASES.items():

@@ -407,6 +407,10 @@ def reduce_mean(x, axis=None, keepdims=False, keep_dims=None, name=None):
     return Tensor(t.mean() if axis is None else t.mean(dim=_axes(axis), keepdim=bool(kd)))
 
 
+def argmax(x, axis=None, name=None, **kw):
+    return Tensor(torch.argmax(_raw(x), dim=axis))
+
+
 def split(x, num_or_size_splits, axis=0, name=None):
     t = _raw(x)
     assert isinstance(num_or_size_splits, int)
@@ -525,6 +529,18 @@ class _Dummy:
 
     def __call__(self, *a, **k):
         raise NotImplementedError("%s is outside the pinned path" % self._n)
+
+
+class _Summary:
+    """tf.summary.*: logging side effects, no value on the pinned path."""
+
+    def __getattr__(self, k):
+        if k.startswith("__"):
+            raise AttributeError(k)
+        return lambda *a, **kw: None
+
+
+summary = _Summary()
 
 
 # ----------------------------------------------------------------------------- tf.train / tf.losses

@@ -232,6 +232,26 @@ def test_flag_names_and_defaults_match_reference_code():
                                         "loss_scale", "data_format", "num_gpus"}
 
 
+def test_kd_loss_matches_reference_code():
+    """nets/run_loop_classification.py:89-96,156-162 -- the two `if p['kd_temp'] > 0:` branches of
+    resnet_model_fn executed from the reference's source (label tensor = one-hot ++ teacher logits is split,
+    teacher labels = softmax(teacher logits / T), loss term = T^2 * CE(logits / T, teacher labels)): the
+    oracle's kd_loss and teacher labels (what the CUDA loss kernel and acnn_kd_teacher_labels are tested
+    against on the GPU, tests/test_features_gpu.py)."""
+    from oracle import tf_ops as T
+    gold = PIECES["kd"]
+    logits, kd_labels = mg.kd_inputs()
+    onehot, teacher_logits = kd_labels.split(mg.KD_NC, dim=1)        # as model_fn_cls splits it
+    teacher = torch.softmax(teacher_logits.double() / gold["temp"], dim=1)
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(mg.digest(teacher)[k], gold["teacher_labels"][k], 1e-9)
+        assert _close(mg.digest(onehot)[k], gold["onehot"][k], 1e-12)
+    for a, b in zip(teacher[0].tolist(), gold["teacher_row0"]):
+        assert _close(a, b, 1e-9)
+    got = T.kd_loss(logits, teacher, gold["temp"])
+    assert _close(float(got), gold["cross_entropy_kd"], 2e-6), (float(got), gold["cross_entropy_kd"])
+
+
 @pytest.mark.parametrize("case", sorted(mg.KEEP_PROB_CASES))
 def test_keep_prob_schedule_matches_reference_code(case):
     """functions/model_fns.py:26-33 keep_prob_decay (tf.train.polynomial_decay, power 1, no cycle) executed
