@@ -52,6 +52,19 @@ def get_block_sizes(resnet_size, resnet_version=1):
                          "Size received: {}; sizes allowed: {}.".format(resnet_size, choices.keys()))
 
 
+def per_device_batch_size(batch_size, num_gpus):
+    """official/utils/misc/distribution_utils.py:48-76: the global batch must divide over the replicas
+    (same ValueError text)."""
+    if num_gpus <= 1:
+        return batch_size
+    remainder = batch_size % num_gpus
+    if remainder:
+        raise ValueError("When running with multiple GPUs, batch size must be a multiple of the number of "
+                         "available GPUs. Found {} GPUs with a batch size of {}; try --batch_size={} instead."
+                         .format(num_gpus, batch_size, batch_size - remainder))
+    return int(batch_size / num_gpus)
+
+
 def keep_prob_decay(starter_kp, end_kp, decay_steps):
     """functions/model_fns.py:26-33 (linear polynomial decay, no cycle) as a host function."""
     def fn(global_step):
@@ -278,12 +291,7 @@ class Trainer:
         self.model = model
         self.p = p
         self.world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
-        # official/utils/misc/distribution_utils.py:48-76 per_device_batch_size
-        if p["batch_size"] % self.world:
-            raise ValueError("When running with multiple GPUs, batch size must be a multiple of "
-                             "the number of available GPUs. Found {} GPUs with a batch size of {}"
-                             .format(self.world, p["batch_size"]))
-        self.local_batch = p["batch_size"] // self.world
+        self.local_batch = per_device_batch_size(p["batch_size"], self.world)
         self.mixup_type = int(p.get("mixup_type", 0))
         self.kd_temp = float(p.get("kd_temp", 0) or 0)
         self.use_dropblock = bool(p.get("use_dropblock", False))

@@ -276,6 +276,7 @@ LR_CASES = {   # name -> kwargs of functions/model_fns.py learning_rate_with_dec
                   piecewise_lr_boundary_epochs=[30], piecewise_lr_decay_rates=[1, 0.1], base_lr=0.05,
                   warmup_epochs=0, train_epochs=100),
 }
+PER_DEVICE_CASES = [(256, 1), (256, 0), (2048, 8), (1024, 8), (512, 2), (96, 4)]
 KEEP_PROB_CASES = {"assemble_600_epochs_b1024": (1.0, 0.9, int(600 * 1281167 / 1024)),
                    "short": (1.0, 0.7, 10000)}
 LR_STEPS = [0, 1, 100, 1250, 2501, 6254, 6256, 10000, 150134, 150136, 300000, 450408, 700000]
@@ -400,6 +401,13 @@ def run_train_pieces():
                  "teacher_labels": digest(tf._raw(env["teacher_labels"])),
                  "teacher_row0": [float(v) for v in tf._raw(env["teacher_labels"])[0]],
                  "onehot": digest(tf._raw(env["onehot_labels"]))}
+    # official/utils/misc/distribution_utils.py:48-76 per_device_batch_size (values and the error text)
+    pdb, _ = reference_function("official/utils/misc/distribution_utils.py", "per_device_batch_size")
+    out["per_device_batch"] = {"cases": [[b, n, pdb(b, n)] for b, n in PER_DEVICE_CASES]}
+    try:
+        pdb(2050, 8)
+    except ValueError as e:
+        out["per_device_batch"]["error_2050_8"] = str(e)
     # functions/model_fns.py:26-33 keep_prob_decay (the DropBlock schedule, :221-228)
     kp_decay, tf = reference_function("functions/model_fns.py", "keep_prob_decay")
     for name, (kp0, kp1, steps) in KEEP_PROB_CASES.items():

@@ -252,6 +252,18 @@ def test_kd_loss_matches_reference_code():
     assert _close(float(got), gold["cross_entropy_kd"], 2e-6), (float(got), gold["cross_entropy_kd"])
 
 
+def test_per_device_batch_size_matches_reference_code():
+    """official/utils/misc/distribution_utils.py:48-76 executed from the reference's source: per-replica
+    batch and the ValueError text of an indivisible global batch (Trainer raises it)."""
+    from assembled_cnn_b200.model_fns import per_device_batch_size
+    gold = PIECES["per_device_batch"]
+    for b, n, want in gold["cases"]:
+        assert per_device_batch_size(b, n) == want
+    with pytest.raises(ValueError) as e:
+        per_device_batch_size(2050, 8)
+    assert str(e.value) == gold["error_2050_8"]
+
+
 @pytest.mark.parametrize("case", sorted(mg.KEEP_PROB_CASES))
 def test_keep_prob_schedule_matches_reference_code(case):
     """functions/model_fns.py:26-33 keep_prob_decay (tf.train.polynomial_decay, power 1, no cycle) executed
