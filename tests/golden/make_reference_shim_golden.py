@@ -127,6 +127,27 @@ def reference_function(rel_path, name):
     return ns[name], tf
 
 
+def reference_warm_start_list(trainable_names):
+    """utils/hook_utils.py:36-47 WarmStartHook.begin executed from the reference's source on a list of
+    trainable variable names (TF appends ':0' to a variable's name): which variables a fine-tuning run
+    restores.  The TF services the method touches are stubbed with recorders."""
+    import types
+    begin, tf = reference_function("utils/hook_utils.py", "begin")
+    var = lambda n: types.SimpleNamespace(name=n + ":0")
+    saved = {}
+    tf.contrib.framework = types.SimpleNamespace(get_trainable_variables=lambda: [var(n) for n in trainable_names])
+    tf.gfile = types.SimpleNamespace(IsDirectory=lambda path: False)
+    old_saver = getattr(tf.train, "Saver", None)
+    tf.train.Saver = lambda var_list: saved.setdefault("vars", list(var_list))
+    try:
+        hook = types.SimpleNamespace(checkpoint_path="ckpt", var_list_warm_start=[], saver=None)
+        begin(hook)
+    finally:
+        tf.train.Saver = old_saver
+    assert [v.name for v in saved["vars"]] == [v.name for v in hook.var_list_warm_start]
+    return [v.name[:-2] for v in hook.var_list_warm_start]
+
+
 def reference_if_blocks(rel_path, func_name, test_src):
     """The `if <test_src>:` statements inside one function of a reference module, each compiled on its
     own (for code the reference writes inline in a long function, e.g. the knowledge-distillation
@@ -420,7 +441,10 @@ if __name__ == "__main__":
     gold = {"train_pieces": run_train_pieces()}
     print("train pieces:", sorted(gold["train_pieces"]))
     for name, (flags, d, b, s) in CONFIGS.items():
-        gold[name], _ = run_reference(flags, d, b, s)
+        gold[name], order = run_reference(flags, d, b, s)
+        ws = reference_warm_start_list([o[0] for o in order if o[3]])
+        gold[name]["num_warm_start"] = len(ws)
+        gold[name]["warm_start_sha256"] = hashlib.sha256("\n".join(ws).encode()).hexdigest()
         print(name, gold[name]["num_variables"], gold[name]["eval_logits"]["abs_sum"])
     for name, (flags, b, s, kp) in DROPBLOCK_CONFIGS.items():
         gold[name] = run_reference_dropblock(flags, b, s, kp)

@@ -290,6 +290,21 @@ def test_product_plan_inventory_matches_reference_code(name):
 
 
 @pytest.mark.parametrize("name", sorted(mg.CONFIGS))
+def test_warm_start_filter_matches_reference_code(name):
+    """utils/hook_utils.py:36-47 WarmStartHook.begin executed from the reference's source on the variable
+    inventory of each configuration (SE blocks keep their dense layers, the classifier and the embedding
+    head are left out): checkpoint.warm_start_variables must select the same variables, in order."""
+    from assembled_cnn_b200 import checkpoint as C
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    flags, d, batch, size = mg.CONFIGS[name]
+    gold = GOLD[name]
+    plan = build_plan(ModelConfig(use_resnet_d=d, **flags), 2, 64, 64, training=True)
+    ws = C.warm_start_variables(list(plan.params))
+    assert len(ws) == gold["num_warm_start"] < len(plan.params)
+    assert hashlib.sha256("\n".join(ws).encode()).hexdigest() == gold["warm_start_sha256"]
+
+
+@pytest.mark.parametrize("name", sorted(mg.CONFIGS))
 def test_native_plan_inventory_matches_reference_code(name):
     """The same for the plan the product executes -- built in C++ behind acnn_create
     (csrc/model_plan.cu, include/acnn_model.h): acnn_variable_info_get lists the reference's variables
