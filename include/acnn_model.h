@@ -25,7 +25,9 @@
  * the ABI, only ENQUEUES on `stream` (a cudaStream_t passed as void*), performs no hidden
  * synchronisation or allocation after acnn_bind(), and is CUDA-graph capturable (inputs are read from
  * the static input buffers inside the workspace; hyper-parameters from the device vector `hp`).
- * One host thread per handle.  acnn_create() needs no GPU (the layer plan is host logic).
+ * One host thread per handle; the calling thread's current CUDA device must be the one that owns the
+ * bound buffers (one process per GPU sets it once).  acnn_create() needs no GPU (the layer plan is host
+ * logic).
  */
 #ifndef ACNN_MODEL_H_
 #define ACNN_MODEL_H_
