@@ -170,6 +170,50 @@ def test_float64_oracle_matches_reference_code_to_1e6(name):
         assert tight(mg.digest(mv)[k], gold["moving_variance_after"][k]), k
 
 
+@pytest.mark.parametrize("name", sorted(mg.CONFIGS))
+def test_product_plan_interpreted_in_float64_matches_reference_code(name):
+    """One hop fewer: the PRODUCT'S layer plan (assembled_cnn_b200/plan.py -- text-for-text the plan the
+    library builds, tests/test_native_plan_cpu.py), executed op by op by the float64 interpreter the GPU
+    lockstep tests compare every CUDA op with (oracle/plan_interp.py), against the float64 results of the
+    reference's own model code on third-party kernels: inference-mode logits, training-mode logits and the
+    moving statistics after the step to 1e-6, all 11 configurations (fp32-mode plan: fp32 tensors, two-pass
+    statistics, operand planes)."""
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    from oracle import plan_interp as PI
+    flags, d, batch, size = mg.CONFIGS[name]
+    gold = GOLD[name]
+    cfg = ModelConfig(use_resnet_d=d, **flags)
+    x = mg.seeded_input(batch, size).double()
+    values = None
+    for training in (False, True):
+        plan = build_plan(cfg, batch, size, size, training=training, with_loss=False, dtype="fp32")
+        if values is None:
+            names = list(plan.params) + list(plan.state)
+            # the seeded values are indexed by the reference's creation order (trainables and moving
+            # statistics interleaved): recover it from the oracle's variable store
+            _, _, vs = _oracle(flags, d, size)
+            values = {n: mg.seeded_value(i, n, tuple(vs.vars[n].shape)).double()
+                      for i, n in enumerate(list(vs.vars))}
+            assert sorted(values) == sorted(names)
+        it = PI.PlanInterpreter(plan, dtype=torch.float64)
+        it.set_weights(values)
+        labels = torch.zeros(batch, dtype=torch.int32) if training else None
+        y = it.forward(x, labels)
+        got = mg.digest(y)
+        want = gold["train_logits" if training else "eval_logits"]
+        for k in ("sum", "abs_sum", "first", "last"):
+            assert _close(got[k], want[k], 1e-6, 1e-9), (training, k, got[k], want[k])
+        if training:
+            mm = torch.cat([it.get_tf(n).flatten() for n in values if n.endswith("moving_mean")])
+            mv = torch.cat([it.get_tf(n).flatten() for n in values if n.endswith("moving_variance")])
+            for k in ("sum", "abs_sum", "first", "last"):
+                assert _close(mg.digest(mm)[k], gold["moving_mean_after"][k], 1e-6, 1e-9), k
+                assert _close(mg.digest(mv)[k], gold["moving_variance_after"][k], 1e-6, 1e-9), k
+        else:
+            for a, b in zip(y[0, :8].tolist(), gold["eval_logits_row0_head"]):
+                assert _close(a, b, 1e-6, 1e-9)
+
+
 @pytest.mark.parametrize("keep", [False, True], ids=["mixup_type_1", "mixup_type_2"])
 def test_mixup_matches_reference_code(keep):
     """utils/data_util.py:97-158 executed through the stand-in with the same lambdas."""
