@@ -227,6 +227,20 @@ def run_reference(flags, use_resnet_d, batch, size):
         tr = [o[0] for o in order if o[3]]
         picks = [tr[0], tr[len(tr) // 3], tr[len(tr) // 2], tr[-2], tr[-1]]
         out["grads_eval_mode"] = {n: digest(tf.variables.vars[n].t.grad) for n in picks}
+    # the same loss with TRAINING-mode batch norm (batch statistics): its value and gradient digests of a
+    # spread of variables -- what the product's explicit backward (hand-derived BN / SK / SE / pooling
+    # backward passes of the plan) is compared with in float64
+    get_sup_loss, _ = reference_function("losses/cls_losses.py", "get_sup_loss")
+    tf.reset(values, requires_grad=True)
+    y = make()(tf.Tensor(x), training=True, use_resnet_d=use_resnet_d)
+    lab = torch.nn.functional.one_hot(torch.arange(batch) * 37 % 1001, 1001).float()
+    ce = get_sup_loss(y, tf.Tensor(lab), None, 1001, {"cls_loss_type": "softmax", "label_smoothing": 0.1})
+    ce.t.backward()
+    out["ce_train_mode"] = float(ce.t)
+    tr = [o[0] for o in order if o[3]]
+    picks = sorted(set([tr[0], tr[1], tr[2], tr[len(tr) // 3], tr[len(tr) // 2], tr[-2], tr[-1]] + tr[5::61]),
+                   key=tr.index)
+    out["grads_train_mode"] = {n: digest(tf.variables.vars[n].t.grad) for n in picks}
     # nets/run_loop_classification.py:163-176: which trainable variables enter the L2 term
     exclude_batch_norm, _ = reference_function("nets/run_loop_classification.py", "exclude_batch_norm")
     decayed = [o[0] for o in order if o[3] and exclude_batch_norm(o[0] + ":0")]

@@ -214,6 +214,40 @@ def test_product_plan_interpreted_in_float64_matches_reference_code(name):
                 assert _close(a, b, 1e-6, 1e-9)
 
 
+@pytest.mark.parametrize("name", sorted(mg.CONFIGS))
+def test_product_plan_backward_in_float64_matches_autograd_through_reference_code(name):
+    """The plan's EXPLICIT backward (the reference relies on tf.gradients; the product emits hand-derived
+    batch-norm / SK / SE / blur-pool / pooling / merge backward passes and accumulates gradients through
+    fused epilogues) executed by the float64 interpreter, against torch autograd through the reference's
+    own training-mode graph on third-party kernels: the smoothed cross-entropy to 1e-6 and the gradient
+    digests of 10-23 variables spread over the net (stem, BL module, SK / SE fc kernels, BN gammas / betas,
+    dense kernel and bias) to 1e-5."""
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    from oracle import plan_interp as PI
+    flags, d, batch, size = mg.CONFIGS[name]
+    gold = GOLD[name]
+    plan = build_plan(ModelConfig(use_resnet_d=d, **flags), batch, size, size, training=True,
+                      label_smoothing=0.1, dtype="fp32")
+    _, _, vs = _oracle(flags, d, size)
+    values = {n: mg.seeded_value(i, n, tuple(vs.vars[n].shape)).double() for i, n in enumerate(list(vs.vars))}
+    it = PI.PlanInterpreter(plan, dtype=torch.float64)
+    it.set_weights(values)
+    it.hp.update(grad_scale=1.0)
+    labels = (torch.arange(batch) * 37 % 1001).int()
+    it.forward(mg.seeded_input(batch, size).double(), labels)
+    it.run(plan.backward)
+    ce = float(it.slot(plan.meta["loss"])[0])
+    assert _close(ce, gold["ce_train_mode"], 2e-6), (ce, gold["ce_train_mode"])
+    worst = 0.0
+    for n, want in gold["grads_train_mode"].items():
+        g = mg.digest(it.get_tf(n, it.grads))
+        assert _close(g["abs_sum"], want["abs_sum"], 1e-5, 1e-12), (n, g, want)
+        assert _close(g["sum"], want["sum"], 1e-5, 1e-5 * want["abs_sum"] + 1e-12), (n, g, want)
+        assert _close(g["first"], want["first"], 1e-5, 1e-6 * want["abs_sum"] + 1e-12), (n, g, want)
+        worst = max(worst, abs(g["abs_sum"] - want["abs_sum"]) / max(want["abs_sum"], 1e-30))
+    print("%s: %d gradient tensors, worst |sum| rel diff %.2e" % (name, len(gold["grads_train_mode"]), worst))
+
+
 @pytest.mark.parametrize("keep", [False, True], ids=["mixup_type_1", "mixup_type_2"])
 def test_mixup_matches_reference_code(keep):
     """utils/data_util.py:97-158 executed through the stand-in with the same lambdas."""
