@@ -248,6 +248,36 @@ def test_product_plan_backward_in_float64_matches_autograd_through_reference_cod
     print("%s: %d gradient tensors, worst |sum| rel diff %.2e" % (name, len(gold["grads_train_mode"]), worst))
 
 
+@pytest.mark.parametrize("name", sorted(mg.DROPBLOCK_CONFIGS))
+def test_product_dropblock_plan_in_float64_matches_reference_code(name):
+    """The product's DropBlock plan (mask ops at the reference's 34 / 29 call sites, `cbr_db` /
+    `residual_tail_db` tails, SK-output DropBlock) interpreted in float64 with the SAME uniform draws in
+    call order, against the reference's Model.__call__(training=True, keep_prob) on third-party kernels:
+    training-mode logits at 224 px to 1e-5."""
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    from oracle import model as M, plan_interp as PI
+    flags, batch, size, kp = mg.DROPBLOCK_CONFIGS[name]
+    gold = GOLD[name]
+    plan = build_plan(ModelConfig(**flags), batch, size, size, training=True, use_dropblock=True,
+                      dtype="fp32")
+    _, vs = M.build(seed=1, input_hw=64, **flags)
+    values = {n: mg.seeded_value(i, n, tuple(vs.vars[n].shape)).double() for i, n in enumerate(list(vs.vars))}
+    it = PI.PlanInterpreter(plan, dtype=torch.float64)
+    it.set_weights(values)
+    it.hp.update(keep_prob=kp)
+    g = torch.Generator().manual_seed(mg.DROPBLOCK_SEED)
+    assert len(plan.meta["dropblock_u"]) == gold["num_dropblock_calls"]
+    for u_name in plan.meta["dropblock_u"]:          # the reference draws [1, hs, ws, C] per call, in order
+        shape = plan.tensors[u_name].shape
+        it.t[u_name] = torch.rand((1,) + tuple(shape), generator=g)[0].double()
+    y = it.forward(mg.seeded_input(batch, size).double(), torch.zeros(batch, dtype=torch.int32))
+    got = mg.digest(y)
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(got[k], gold["train_logits"][k], 1e-5, 1e-8), (k, got[k], gold["train_logits"][k])
+    for a, b in zip(y[0, :8].tolist(), gold["train_logits_row0_head"]):
+        assert _close(a, b, 1e-5, 1e-8)
+
+
 @pytest.mark.parametrize("keep", [False, True], ids=["mixup_type_1", "mixup_type_2"])
 def test_mixup_matches_reference_code(keep):
     """utils/data_util.py:97-158 executed through the stand-in with the same lambdas."""
