@@ -170,13 +170,18 @@ def test_float64_oracle_matches_reference_code_to_1e6(name):
         assert tight(mg.digest(mv)[k], gold["moving_variance_after"][k]), k
 
 
-@pytest.mark.parametrize("name", sorted(mg.CONFIGS))
+# (one of the two 152-layer configurations -- BASELINE config 5 -- is enough for the interpreter tests: the
+# float64 interpretation of a 152-layer plan takes ~25 s)
+_INTERP_CONFIGS = [n for n in sorted(mg.CONFIGS) if n != "assemble_r152_rv2_sk_sconv"]
+
+
+@pytest.mark.parametrize("name", _INTERP_CONFIGS)
 def test_product_plan_interpreted_in_float64_matches_reference_code(name):
     """One hop fewer: the PRODUCT'S layer plan (assembled_cnn_b200/plan.py -- text-for-text the plan the
     library builds, tests/test_native_plan_cpu.py), executed op by op by the float64 interpreter the GPU
     lockstep tests compare every CUDA op with (oracle/plan_interp.py), against the float64 results of the
     reference's own model code on third-party kernels: inference-mode logits, training-mode logits and the
-    moving statistics after the step to 1e-6, all 11 configurations (fp32-mode plan: fp32 tensors, two-pass
+    moving statistics after the step to 1e-6, 10 configurations up to ResNet-152 (fp32-mode plan: fp32 tensors, two-pass
     statistics, operand planes)."""
     from assembled_cnn_b200.plan import ModelConfig, build_plan
     from oracle import plan_interp as PI
@@ -214,7 +219,7 @@ def test_product_plan_interpreted_in_float64_matches_reference_code(name):
                 assert _close(a, b, 1e-6, 1e-9)
 
 
-@pytest.mark.parametrize("name", sorted(mg.CONFIGS))
+@pytest.mark.parametrize("name", _INTERP_CONFIGS)
 def test_product_plan_backward_in_float64_matches_autograd_through_reference_code(name):
     """The plan's EXPLICIT backward (the reference relies on tf.gradients; the product emits hand-derived
     batch-norm / SK / SE / blur-pool / pooling / merge backward passes and accumulates gradients through
