@@ -249,6 +249,57 @@ def run_reference(flags, use_resnet_d, batch, size):
     return out, order
 
 
+C3_BATCH, C3_SIZE = 4, 64
+
+
+def c3_inputs():
+    """2B images, 2B class labels, B mixing coefficients (mixup type 1 halves the batch)."""
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn(2 * C3_BATCH, C3_SIZE, C3_SIZE, 3, generator=g)
+    labels = torch.randint(1, 1001, (2 * C3_BATCH,), generator=g)
+    lam = torch.rand(C3_BATCH, generator=g)
+    return x, labels, lam
+
+
+def run_reference_c3_composition():
+    """BASELINE config 3 as the reference composes it (nets/run_loop_classification.py:101-109,141-149):
+    utils/data_util.mixup(keep_batch_size=False) on images and one-hot labels -> Assemble-ResNet-50 in
+    training mode -> losses/cls_losses.get_sup_loss with label smoothing 0.1; gradients by autograd."""
+    sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
+    sys.path.insert(0, "/root/reference")
+    import tensorflow as tf
+    from nets import resnet_model
+    flags, d, _, _ = CONFIGS["assemble_r50_rv2_sk_sconv"]
+    f = dict(flags)
+    size_ = f.pop("resnet_size")
+    mixup, _ = reference_function("utils/data_util.py", "mixup")
+    get_sup_loss, _ = reference_function("losses/cls_losses.py", "get_sup_loss")
+
+    def make():
+        return resnet_model.Model(resnet_size=size_, bottleneck=True, num_classes=1001, num_filters=64,
+                                  kernel_size=7, conv_stride=2, first_pool_size=3, first_pool_stride=2,
+                                  block_sizes=block_sizes(size_, 2), block_strides=[2, 2, 1, 2], **f)
+    x, labels, lam = c3_inputs()
+    tf.reset()
+    make()(tf.Tensor(x[:C3_BATCH]), training=False)
+    order = list(tf.variables.order)
+    values = {n: seeded_value(i, n, s) for i, (n, s, _, _) in enumerate(order)}
+    tf.reset(values, requires_grad=True)
+    tf.beta_samples.clear()
+    tf.beta_samples.append(lam)
+    onehot = torch.nn.functional.one_hot(labels, 1001).float()
+    mx, my = mixup(tf.Tensor(x), tf.Tensor(onehot), keep_batch_size=False)[:2]
+    y = make()(mx, training=True)
+    ce = get_sup_loss(y, my, None, 1001, {"cls_loss_type": "softmax", "label_smoothing": 0.1})
+    ce.t.backward()
+    tr = [o[0] for o in order if o[3]]
+    picks = sorted(set([tr[0], tr[1], tr[2], tr[len(tr) // 3], tr[len(tr) // 2], tr[-2], tr[-1]] + tr[7::43]),
+                   key=tr.index)
+    return {"batch": C3_BATCH, "size": C3_SIZE, "mixed_images": digest(tf._raw(mx)),
+            "mixed_labels": digest(tf._raw(my)), "train_logits": digest(y.t), "cross_entropy": float(ce.t),
+            "grads": {n: digest(tf.variables.vars[n].t.grad) for n in picks}}
+
+
 def run_reference_dropblock(flags, batch, size, keep_prob):
     sys.path.insert(0, os.path.join(HERE, "tf1_shim"))
     sys.path.insert(0, "/root/reference")
@@ -460,6 +511,8 @@ if __name__ == "__main__":
         gold[name]["num_warm_start"] = len(ws)
         gold[name]["warm_start_sha256"] = hashlib.sha256("\n".join(ws).encode()).hexdigest()
         print(name, gold[name]["num_variables"], gold[name]["eval_logits"]["abs_sum"])
+    gold["c3_composition"] = run_reference_c3_composition()
+    print("c3 composition", gold["c3_composition"]["cross_entropy"], len(gold["c3_composition"]["grads"]))
     for name, (flags, b, s, kp) in DROPBLOCK_CONFIGS.items():
         gold[name] = run_reference_dropblock(flags, b, s, kp)
         print(name, gold[name]["num_dropblock_calls"], gold[name]["train_logits"]["abs_sum"])

@@ -283,6 +283,54 @@ def test_product_dropblock_plan_in_float64_matches_reference_code(name):
         assert _close(a, b, 1e-5, 1e-8)
 
 
+def test_c3_composition_matches_reference_code():
+    """BASELINE config 3 end to end as the reference composes it -- utils/data_util.mixup (type 1) ->
+    Assemble-ResNet-50 in training mode -> get_sup_loss(label_smoothing 0.1) -> gradients -- executed from
+    the reference's sources on third-party kernels in float64, against (a) the float64 oracle and (b) the
+    PRODUCT'S plan (mixup fused into pack_input / mix_labels, explicit backward) in the float64
+    interpreter: training-mode logits and the loss to 1e-6, 14 gradient digests to 1e-5."""
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    from oracle import model as M, plan_interp as PI, tf_ops as T
+    gold = GOLD["c3_composition"]
+    flags, d, _, _ = mg.CONFIGS["assemble_r50_rv2_sk_sconv"]
+    B, size = gold["batch"], gold["size"]
+    x, labels, lam = mg.c3_inputs()
+    model, vs = M.build(seed=1, input_hw=size, **flags)
+    values = {n: mg.seeded_value(i, n, tuple(vs.vars[n].shape)).double() for i, n in enumerate(list(vs.vars))}
+    # (a) oracle
+    for n in vs.vars:
+        vs.vars[n] = values[n].clone().requires_grad_(bool(vs.trainable[n]))
+    vs.dtype = torch.float64
+    onehot = torch.nn.functional.one_hot(labels, 1001).double()
+    mx, my = T.mixup(x.double(), onehot, lam.double(), keep_batch_size=False)
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(mg.digest(mx)[k], gold["mixed_images"][k], 1e-9)
+        assert _close(mg.digest(my)[k], gold["mixed_labels"][k], 1e-9)
+    loss, ce, _, y = M.loss_fn(model, vs, mx, my, training=True, label_smoothing=0.1, weight_decay=0.0)
+    ce.backward()
+    assert _close(float(ce.detach()), gold["cross_entropy"], 2e-6)
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(mg.digest(y)[k], gold["train_logits"][k], 1e-6, 1e-9), k
+    for n, want in gold["grads"].items():
+        g = mg.digest(vs.vars[n].grad)
+        assert _close(g["abs_sum"], want["abs_sum"], 1e-5, 1e-12), ("oracle", n, g, want)
+    # (b) the product's plan
+    plan = build_plan(ModelConfig(**flags), B, size, size, training=True, mixup_type=1, label_smoothing=0.1,
+                      dtype="fp32")
+    it = PI.PlanInterpreter(plan, dtype=torch.float64)
+    it.set_weights(values)
+    it.hp.update(grad_scale=1.0)
+    logits = it.forward(x.double(), labels.int(), lam.double())
+    it.run(plan.backward)
+    assert _close(float(it.slot(plan.meta["loss"])[0]), gold["cross_entropy"], 2e-6)
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(mg.digest(logits)[k], gold["train_logits"][k], 1e-6, 1e-9), k
+    for n, want in gold["grads"].items():
+        g = mg.digest(it.get_tf(n, it.grads))
+        assert _close(g["abs_sum"], want["abs_sum"], 1e-5, 1e-12), ("plan", n, g, want)
+        assert _close(g["sum"], want["sum"], 1e-5, 1e-5 * want["abs_sum"] + 1e-12), ("plan", n, g, want)
+
+
 @pytest.mark.parametrize("keep", [False, True], ids=["mixup_type_1", "mixup_type_2"])
 def test_mixup_matches_reference_code(keep):
     """utils/data_util.py:97-158 executed through the stand-in with the same lambdas."""
