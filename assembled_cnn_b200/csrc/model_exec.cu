@@ -816,6 +816,41 @@ int acnn_bind(acnn_model* m, float* params, float* grads, float* momentum, float
   return ACNN_OK;
 }
 
+int acnn_validate(acnn_model* m) {
+  ACNN_REQUIRE(m, "acnn_validate: null model");
+  // synthetic, suitably aligned, non-null addresses: resolve() only does pointer arithmetic on them
+  struct Saved {
+    float *params, *grads, *momentum, *state;
+    char *w_fprop, *w_dgrad, *ws;
+  } saved{m->params, m->grads, m->momentum, m->state, m->w_fprop, m->w_dgrad, m->ws};
+  char* const base = reinterpret_cast<char*>(uintptr_t(1) << 40);
+  const int64_t span = int64_t(1) << 36;
+  m->params = reinterpret_cast<float*>(base);
+  m->state = reinterpret_cast<float*>(base + span);
+  m->w_fprop = base + 2 * span;
+  m->ws = base + 3 * span;
+  if (m->plan.cfg.training) {
+    m->grads = reinterpret_cast<float*>(base + 4 * span);
+    m->momentum = reinterpret_cast<float*>(base + 5 * span);
+    m->w_dgrad = base + 6 * span;
+  } else {
+    m->grads = m->momentum = nullptr;
+    m->w_dgrad = nullptr;
+  }
+  std::vector<acnn_model::Launch> tmp;
+  int rc = resolve_all(m, m->plan.forward, &tmp);
+  if (rc == ACNN_OK) rc = resolve_all(m, m->plan.backward, &tmp);
+  if (rc == ACNN_OK) rc = resolve_all(m, m->plan.update, &tmp);
+  m->params = saved.params;
+  m->grads = saved.grads;
+  m->momentum = saved.momentum;
+  m->state = saved.state;
+  m->w_fprop = saved.w_fprop;
+  m->w_dgrad = saved.w_dgrad;
+  m->ws = saved.ws;
+  return rc;
+}
+
 int acnn_set_loss_scale(acnn_model* m, double loss_scale) {
   ACNN_REQUIRE(m && loss_scale > 0, "acnn_set_loss_scale: bad argument");
   m->loss_scale = loss_scale;

@@ -249,6 +249,9 @@ class Builder {
   ConvOut conv(int x, int filters, int k, int stride, bool with_bn = true, bool zero_gamma = false,
                bool need_dgrad = true) {
     const Shape xs = T(x).shape;
+    if (filters % 32 || xs[3] % 16)   // e.g. bl_alpha=4: the little branches would have 16 channels
+      fail(ACNN_ERR_UNSUPPORTED, "conv %d -> %d channels: the tensor-core tiles need input channels in "
+           "multiples of 16 and output channels in multiples of 32", (int)xs[3], filters);
     const std::string layer = unique("conv2d");
     ConvOut co;
     co.x = x;

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "acnn_tensor_info_get": (_i, [_vp, _i, C.POINTER(TensorInfo)]),
     "acnn_find_tensor": (_i, [_vp, C.c_char_p, _i]),
     "acnn_bind": (_i, [_vp] * 9),
+    "acnn_validate": (_i, [_vp]),
     "acnn_set_loss_scale": (_i, [_vp, C.c_double]),
     "acnn_set_dropblock": (_i, [_vp, C.c_uint64, _i]),
     "acnn_set_inputs": (_i, [_vp] * 7),
@@ -235,6 +236,10 @@ class NativeModel:
         _lib.check(self.lib.acnn_op_conv_info(self.handle, op.phase, op.index, C.byref(g), C.byref(macs),
                                               C.byref(aux)), "acnn_op_conv_info")
         return g, macs.value, aux.value
+
+    def validate(self):
+        """acnn_validate: every op resolves into a launch record (host-only; raises AcnnError otherwise)."""
+        _lib.check(self.lib.acnn_validate(self.handle), "acnn_validate")
 
     def dump(self) -> str:
         n = self.lib.acnn_plan_dump(self.handle, None, 0)

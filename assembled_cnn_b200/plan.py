@@ -417,6 +417,10 @@ class PlanBuilder:
              need_dgrad=True) -> ConvOut:
         """conv2d_fixed_padding (+ the batch-norm that always follows it in the reference)."""
         B, H, W, Cin = x.shape
+        if filters % 32 or Cin % 16:
+            # e.g. bl_alpha=4: the little branches would have 16 channels
+            raise NotImplementedError("conv %d -> %d channels: the tensor-core tiles need input channels in "
+                                      "multiples of 16 and output channels in multiples of 32" % (Cin, filters))
         layer = self._unique("conv2d")
         g = self._geom(x, filters, k, stride)
         w = self._param(self._full(layer + "/kernel"), (k, k, Cin, filters), "conv_kernel",

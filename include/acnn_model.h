@@ -156,6 +156,14 @@ int acnn_find_tensor(const acnn_model* m, const char* role, int index);
 int acnn_bind(acnn_model* m, float* params, float* grads, float* momentum, float* state,
               void* w_fprop, void* w_dgrad, void* workspace, void* stream);
 
+/* Host-only self-check, no GPU: resolves every op of the plan against synthetic buffer addresses exactly as
+ * acnn_bind would (same launch-record construction, nothing is launched or copied) and reports the first
+ * op that cannot be resolved -- a partial-statistics slot or scratch area of the plan smaller than the row
+ * count / scratch size the op level asks for (acnn_conv_stats_parts, acnn_bn_bwd_reduce_parts,
+ * acnn_sk_fc_scratch_floats, acnn_dropblock_scratch_floats ...), a missing weight layout, an unknown op.
+ * Leaves the handle as it was (bound or not). */
+int acnn_validate(acnn_model* m);
+
 /* Mutable step settings (read at enqueue time, not captured values of a CUDA graph's kernels: the
  * loss scale is a kernel argument, so re-capture after changing it). */
 int acnn_set_loss_scale(acnn_model* m, double loss_scale);

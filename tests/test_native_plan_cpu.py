@@ -49,7 +49,7 @@ CASES = [
      dict(training=True, use_dropblock=True, dtype="fp32")),
     (ASSEMBLE, 4, 64, 64, dict(training=True, kd_temp=2.0, mixup_type=2)),
     (ASSEMBLE, 4, 64, 64, dict(training=True, kd_temp=4.0, mixup_type=1, label_smoothing=0.1)),
-    (dict(ASSEMBLE, bl_alpha=4, bl_beta=2, bn_momentum=0.9), 4, 64, 64, dict(training=True)),
+    (dict(ASSEMBLE, bl_alpha=1, bl_beta=4, bn_momentum=0.9), 4, 64, 64, dict(training=True)),
 ]
 
 
@@ -67,6 +67,9 @@ def test_native_plan_equals_python_plan(case):
     cc = nm.dump()
     assert py == cc, _diff(py, cc)
     assert len(py.splitlines()) > 500
+    # every op of the plan resolves into a launch record (acnn_validate: the host side of acnn_bind on
+    # synthetic addresses -- partial-row buffers and scratch slots fit what the op level asks for)
+    nm.validate()
     nm.close()
 
 
@@ -259,9 +262,9 @@ from hypothesis import given, settings, strategies as st, HealthCheck
 @st.composite
 def _flag_sets(draw, poisoned=False):
     # poisoned: exactly one value that one of the argument checks refuses
-    poison = draw(st.sampled_from(["size", "filter", "pool", "embedding", "width", "db_se"])) if poisoned \
-        else None
-    version = draw(st.sampled_from([1, 2]))
+    poison = draw(st.sampled_from(["size", "filter", "pool", "embedding", "width", "db_se", "alpha"])) \
+        if poisoned else None
+    version = 2 if poison == "alpha" else draw(st.sampled_from([1, 2]))
     size = draw(st.sampled_from([50, 50, 50, 101, 152] + ([200] if version == 1 else [])))
     aa = draw(st.sampled_from(["sconv", "proj"] if poison == "filter" else
                               ["", "sconv", "sconv", "proj", "sconv,proj"]))
@@ -276,7 +279,9 @@ def _flag_sets(draw, poisoned=False):
                                 else draw(st.sampled_from([1, 2, 3, 3, 4, 5, 7]))),
         pool_type="max" if poison == "pool" else draw(st.sampled_from(["gap", "gap", "gem", "flatten"])),
         embedding_size=48 if poison == "embedding" else draw(st.sampled_from([0, 0, 32, 64])),
-        bl_alpha=draw(st.sampled_from([1, 2, 4])), bl_beta=draw(st.sampled_from([1, 2, 4, 8])),
+        # bl_alpha = 4 gives the little branches 16 channels: below the tensor-core tile (refused, version 2)
+        bl_alpha=4 if poison == "alpha" else draw(st.sampled_from([1, 2])),
+        bl_beta=draw(st.sampled_from([1, 2, 4, 8])),
         num_classes=draw(st.sampled_from([1001, 10, 128])),
         bn_momentum=draw(st.sampled_from([0.997, 0.9])))
     training = draw(st.booleans())
@@ -316,6 +321,10 @@ def test_native_and_python_plans_agree_over_the_flag_space(case):
     assert py is not None, ("the Python builder refused a valid flag set", case)
     assert cc is not None, ("acnn_create refused: " + native.lib().acnn_last_error().decode(), case)
     assert py == cc, (case, _diff(py, cc))
+    flags, B, (H, W), kw = case
+    nm = native.NativeModel(ModelConfig(**flags), B, H, W, **kw)
+    nm.validate()                       # ... and every op of it resolves (host side of acnn_bind)
+    nm.close()
 
 
 @settings(max_examples=30, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
