@@ -804,6 +804,9 @@ void Builder::run() {
     fail(ACNN_ERR_UNSUPPORTED, "only the softmax loss is on the hot path (SURVEY 8a a11)");
   if (!c.anti_alias_type.empty() && (c.anti_alias_filter_size < 1 || c.anti_alias_filter_size > 7))
     fail(ACNN_ERR_INVALID, "anti_alias_filter_size must be in 1..7");
+  if (c.resnet_version == 2 && (c.bl_alpha < 1 || c.bl_beta < 1 || (64 / c.bl_alpha) % 32))
+    fail(ACNN_ERR_UNSUPPORTED, "bl_alpha=%d: the little branches would have %d channels, below the 32-channel "
+         "tensor-core tile (bl_alpha 1 or 2)", c.bl_alpha, 64 / std::max(c.bl_alpha, 1));
   training_ = c.training;
   use_dropblock_ = c.use_dropblock && training_;
   if (use_dropblock_ && c.use_se_block) fail(ACNN_ERR_UNSUPPORTED, "use_dropblock together with use_se_block");

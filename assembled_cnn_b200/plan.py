@@ -187,6 +187,10 @@ class ModelConfig:
             raise NotImplementedError("only the softmax loss is on the hot path (SURVEY 8a a11)")
         if self.anti_alias_type and self.anti_alias_filter_size not in range(1, 8):
             raise ValueError("anti_alias_filter_size must be in 1..7")
+        if self.resnet_version == 2 and (self.bl_alpha < 1 or self.bl_beta < 1 or (64 // self.bl_alpha) % 32):
+            raise NotImplementedError("bl_alpha=%r: the little branches would have %d channels, below the "
+                                      "32-channel tensor-core tile (bl_alpha 1 or 2)"
+                                      % (self.bl_alpha, 64 // max(self.bl_alpha, 1)))
 
 
 class Plan:
