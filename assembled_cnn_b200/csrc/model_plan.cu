@@ -798,8 +798,10 @@ void Builder::run() {
     fail(ACNN_ERR_INVALID, "Could not find layers for selected Resnet size. Size received: %d", c.resnet_size);
   if (c.pool_type != "gap" && c.pool_type != "gem" && c.pool_type != "flatten")
     fail(ACNN_ERR_UNSUPPORTED, "pool_type='%s' (nets/resnet_model.py:560-573)", c.pool_type.c_str());
-  if (c.embedding_size && c.embedding_size % 32)
-    fail(ACNN_ERR_INVALID, "embedding_size must be a multiple of 32 (tensor-core N tile)");
+  if (c.embedding_size && (c.embedding_size < 32 || c.embedding_size > 2048 ||
+                           (c.embedding_size & (c.embedding_size - 1))))
+    fail(ACNN_ERR_INVALID, "embedding_size must be a power of two between 32 and 2048 (tensor-core N tile, "
+         "channel groups of the batch-norm kernels)");
   if (c.loss_type != "softmax")
     fail(ACNN_ERR_UNSUPPORTED, "only the softmax loss is on the hot path (SURVEY 8a a11)");
   if (!c.anti_alias_type.empty() && (c.anti_alias_filter_size < 1 || c.anti_alias_filter_size > 7))

@@ -181,8 +181,10 @@ class ModelConfig:
                                  self.resnet_size, BLOCK_SIZES[self.resnet_version].keys()))
         if self.pool_type not in ("gap", "gem", "flatten"):
             raise NotImplementedError("pool_type=%r (nets/resnet_model.py:560-573)" % self.pool_type)
-        if self.embedding_size and self.embedding_size % 32:
-            raise ValueError("embedding_size must be a multiple of 32 (tensor-core N tile)")
+        e = self.embedding_size
+        if e and (e < 32 or e > 2048 or e & (e - 1)):
+            raise ValueError("embedding_size must be a power of two between 32 and 2048 (tensor-core N tile, "
+                             "channel groups of the batch-norm kernels)")
         if self.loss_type != "softmax":
             raise NotImplementedError("only the softmax loss is on the hot path (SURVEY 8a a11)")
         if self.anti_alias_type and self.anti_alias_filter_size not in range(1, 8):

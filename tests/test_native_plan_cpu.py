@@ -278,7 +278,9 @@ def _flag_sets(draw, poisoned=False):
         anti_alias_filter_size=(draw(st.sampled_from([0, 9])) if poison == "filter"
                                 else draw(st.sampled_from([1, 2, 3, 3, 4, 5, 7]))),
         pool_type="max" if poison == "pool" else draw(st.sampled_from(["gap", "gap", "gem", "flatten"])),
-        embedding_size=48 if poison == "embedding" else draw(st.sampled_from([0, 0, 32, 64])),
+        # multiples of 32 that are not powers of two fail the batch-norm kernels' channel grouping
+        embedding_size=(draw(st.sampled_from([48, 96, 4096])) if poison == "embedding"
+                        else draw(st.sampled_from([0, 0, 32, 64, 512]))),
         # bl_alpha = 4 gives the little branches 16 channels: below the tensor-core tile (refused, version 2)
         bl_alpha=4 if poison == "alpha" else draw(st.sampled_from([1, 2])),
         bl_beta=draw(st.sampled_from([1, 2, 4, 8])),
