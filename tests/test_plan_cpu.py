@@ -60,7 +60,11 @@ def test_plan_train_step_matches_autograd_oracle(name, plan_dtype):
     if plan_dtype == "fp32" and name not in ("assemble_rv2_mix1", "rv1_d_sk_sconv_mix2",
                                              "rv2_se_proj5"):
         pytest.skip("fp32 plan: three configurations cover every op kind")
-    plan, model, vs, it, x, lab, lam1, lam2 = _setup(kw, d, mix, hw, plan_dtype=plan_dtype)
+    _check_train_step(kw, d, mix, hw, 4, plan_dtype)
+
+
+def _check_train_step(kw, d, mix, hw, B, plan_dtype):
+    plan, model, vs, it, x, lab, lam1, lam2 = _setup(kw, d, mix, hw, B=B, plan_dtype=plan_dtype)
     if plan_dtype == "fp32":
         # the parity mode's plan: fp32 tensors, operand planes, two-pass statistics, unfused
         # dgrad epilogue -- same mathematics
@@ -157,3 +161,40 @@ def test_flag_validation_errors_match_reference():
     ModelConfig(pool_type="gem", embedding_size=256).validate()      # supported
     with pytest.raises(ValueError):
         ModelConfig(embedding_size=100).validate()
+
+
+# --------------------------------------------------------------------------------------------------
+# The same check over the flag space (hypothesis, derandomised): whatever combination of the reference's
+# flags is requested, the plan's forward, EXPLICIT backward and SGD step agree with autograd through the
+# oracle in float64 -- shortcut kinds x SK / SE x anti-alias variants and filter sizes x pooling / embedding
+# heads x BigLittle widths x mixup types x storage modes.
+# --------------------------------------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st, HealthCheck
+
+
+@st.composite
+def _train_flag_sets(draw):
+    version = draw(st.sampled_from([1, 2]))
+    kw = dict(resnet_size=50, resnet_version=version,
+              use_sk_block=draw(st.booleans()), use_se_block=draw(st.booleans()),
+              zero_gamma=draw(st.booleans()) and draw(st.booleans()),
+              no_downsample=draw(st.booleans()),
+              anti_alias_type=draw(st.sampled_from(["", "sconv", "proj", "sconv,proj"])),
+              anti_alias_filter_size=draw(st.sampled_from([1, 2, 3, 4, 5, 7])),
+              pool_type=draw(st.sampled_from(["gap", "gap", "gem", "flatten"])),
+              embedding_size=draw(st.sampled_from([0, 0, 32, 64])),
+              bl_alpha=draw(st.sampled_from([1, 2])), bl_beta=draw(st.sampled_from([1, 2, 4])))
+    # 64 px: the stride-2 blur-pools of the last stage see 4x4 maps (REFLECT padding needs pad < size)
+    return (kw, draw(st.booleans()), draw(st.sampled_from([0, 1, 2])), 64,
+            # batch >= 4: with 2 samples and 1x1 stage-4 maps at 32 px the batch norms see two values per
+            # channel (x-hat = +-1) and the gradients are ill-conditioned even in float64
+            draw(st.sampled_from([4, 6])), draw(st.sampled_from(["bf16", "fp32"])))
+
+
+@settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@given(_train_flag_sets())
+def test_plan_train_step_matches_autograd_oracle_over_the_flag_space(case):
+    kw, d, mix, hw, B, plan_dtype = case
+    if mix == 2 and B % 2:
+        B += 1                      # mixup type 2 mixes the two halves of the batch
+    _check_train_step(kw, d, mix, hw, B, plan_dtype)
