@@ -540,6 +540,9 @@ class Builder {
   int blurpool(int x, int filt, int stride) {
     const Shape s = T(x).shape;
     const int B = (int)s[0], H = (int)s[1], W = (int)s[2], C = (int)s[3], pad = (filt - 1) / 2;
+    if (pad >= H || pad >= W)
+      fail(ACNN_ERR_INVALID, "anti-alias filter %d on a %dx%d feature map: REFLECT padding of %d needs a larger "
+           "map (tf.pad fails the same way, nets/blocks.py:70-75)", filt, H, W, pad);
     const int Ho = (H + 2 * pad - filt) / stride + 1, Wo = (W + 2 * pad - filt) / stride + 1;
     const int out = tensor("blur", {B, Ho, Wo, C});
 #define BLUR_A {"B", vint(B)}, {"H", vint(H)}, {"W", vint(W)}, {"C", vint(C)}, {"filt", vint(filt)}, \

@@ -685,6 +685,9 @@ class PlanBuilder:
     def blurpool(self, x: Tensor, filt, stride) -> Tensor:
         B, H, W, C = x.shape
         pad = (filt - 1) // 2
+        if pad >= H or pad >= W:
+            raise ValueError("anti-alias filter %d on a %dx%d feature map: REFLECT padding of %d needs a larger "
+                             "map (tf.pad fails the same way, nets/blocks.py:70-75)" % (filt, H, W, pad))
         Ho, Wo = (H + 2 * pad - filt) // stride + 1, (W + 2 * pad - filt) // stride + 1
         out = self.tensor("blur", (B, Ho, Wo, C))
         a = dict(B=B, H=H, W=W, C=C, filt=filt, stride=stride)

@@ -262,7 +262,8 @@ from hypothesis import given, settings, strategies as st, HealthCheck
 @st.composite
 def _flag_sets(draw, poisoned=False):
     # poisoned: exactly one value that one of the argument checks refuses
-    poison = draw(st.sampled_from(["size", "filter", "pool", "embedding", "width", "db_se", "alpha"])) \
+    poison = draw(st.sampled_from(["size", "filter", "pool", "embedding", "width", "db_se", "alpha",
+                                   "reflect"])) \
         if poisoned else None
     version = 2 if poison == "alpha" else draw(st.sampled_from([1, 2]))
     size = draw(st.sampled_from([50, 50, 50, 101, 152] + ([200] if version == 1 else [])))
@@ -287,13 +288,19 @@ def _flag_sets(draw, poisoned=False):
         num_classes=draw(st.sampled_from([1001, 10, 128])),
         bn_momentum=draw(st.sampled_from([0.997, 0.9])))
     training = draw(st.booleans())
-    dropblock = poison == "db_se" or (draw(st.booleans()) and draw(st.booleans()))
+    dropblock = poison == "db_se" or (poison != "width" and draw(st.booleans()) and draw(st.booleans()))
     if poison == "db_se":
         flags["use_se_block"], training = True, True
     elif dropblock:
         flags["use_se_block"] = False
     hw = (224, 224) if dropblock else (draw(st.sampled_from([32, 64, 96])),
                                       100 if poison == "width" else draw(st.sampled_from([32, 64])))
+    if poison == "reflect":         # 32 px: the last stride-2 blur-pool sees a 2x2 map, REFLECT pad 2 fails
+        flags.update(anti_alias_type="sconv", anti_alias_filter_size=5, no_downsample=False)
+        hw, dropblock = (32, 32), False
+    elif min(hw) == 32 and flags["anti_alias_type"] and flags["anti_alias_filter_size"] > 4 \
+            and poison != "filter":
+        flags["anti_alias_filter_size"] = 3
     kw = dict(training=training, mixup_type=draw(st.sampled_from([0, 0, 1, 2])),
               label_smoothing=draw(st.sampled_from([0.0, 0.1])), with_loss=draw(st.booleans()),
               dtype=draw(st.sampled_from(["bf16", "bf16", "fp32"])), use_dropblock=dropblock,
