@@ -4,9 +4,12 @@ TEST INFRASTRUCTURE ONLY (see oracle/tf_ops.py header).  PINNED against the refe
 the reference's nets/resnet_model.py + nets/blocks.py + nets/model_helper.py are executed through
 a TF-1.14 API stand-in (tests/golden/tf1_shim) to produce tests/golden/reference_shim_golden.json;
 tests/test_reference_shim_golden_cpu.py checks this file's variable inventory (names, shapes,
-initializers, creation order: 8 configurations up to ResNet-152) and its logits / BN moving
-statistics (inference and training mode) against it.  The numerical semantics of the individual TF
-kernels stay unpinned (TensorFlow 1.14 is not installable): they are shared with the stand-in.
+initializers, creation order: 11 configurations up to ResNet-152) and, in float64 to 1e-6, its logits
+(inference and training mode), BN moving statistics, loss and gradient digests against it -- plus
+DropBlock through the whole model, the knowledge-distillation branches and BASELINE config 3 as the
+reference composes it (mixup -> model -> smoothed cross-entropy -> gradients).  The stand-in's kernels
+are not this package's: 'SAME' padding is Hugging Face's TF port, batch norm / convolution / pooling are
+ATen's (it does not import oracle/).  What stays unpinned is TensorFlow 1.14 itself (not installable).
 
 Restates nets/resnet_model.py:35-599 (Model.__call__, block_layer, _bottleneck_block_v1),
 functions/model_fns.py:98-198 (topology constants), nets/run_loop_classification.py:86-179 (loss
