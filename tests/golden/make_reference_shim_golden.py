@@ -487,6 +487,33 @@ def run_train_pieces():
                  "teacher_labels": digest(tf._raw(env["teacher_labels"])),
                  "teacher_row0": [float(v) for v in tf._raw(env["teacher_labels"])[0]],
                  "onehot": digest(tf._raw(env["onehot_labels"]))}
+    # nets/run_loop_classification.py:101-109: the call site that maps mixup_type 1 / 2 onto
+    # data_util.mixup(keep_batch_size=False / True, y_t=teacher_labels), executed from the source with the
+    # reference's own mixup function behind `data_util`
+    import types
+    blocks, tf = reference_if_blocks("nets/run_loop_classification.py", "resnet_model_fn",
+                                     "p['mixup_type'] == 1 and mode == tf.estimator.ModeKeys.TRAIN")
+    assert len(blocks) == 1
+    ref_mixup, _ = reference_function("utils/data_util.py", "mixup")
+    tf.estimator = types.SimpleNamespace(ModeKeys=types.SimpleNamespace(TRAIN="train", EVAL="eval", PREDICT="infer"))
+    saved_logging, tf.logging = getattr(tf, "logging", None), tf.summary      # any tf.logging.* is a no-op
+    x, y, lam1, lam2 = mixup_inputs()
+    yt = teacher_labels()
+    for mtype in (1, 2):
+        for mode in ("train", "eval"):
+            tf.beta_samples.clear()
+            tf.beta_samples.extend([lam1, lam2][:mtype])
+            env = {"tf": tf, "p": {"mixup_type": mtype}, "mode": mode,
+                   "data_util": types.SimpleNamespace(mixup=ref_mixup),
+                   "features_sup_may_mixuped": tf.Tensor(x), "onehot_labels": tf.Tensor(y),
+                   "teacher_labels": tf.Tensor(yt)}
+            exec(blocks[0], env)
+            out["mixup_dispatch_type%d_%s" % (mtype, mode)] = {
+                "x_shape": list(tf._raw(env["features_sup_may_mixuped"]).shape),
+                "x": digest(tf._raw(env["features_sup_may_mixuped"])),
+                "y": digest(tf._raw(env["onehot_labels"])),
+                "yt": digest(tf._raw(env["teacher_labels"]))}
+    tf.logging = saved_logging
     # official/utils/misc/distribution_utils.py:48-76 per_device_batch_size (values and the error text)
     pdb, _ = reference_function("official/utils/misc/distribution_utils.py", "per_device_batch_size")
     out["per_device_batch"] = {"cases": [[b, n, pdb(b, n)] for b, n in PER_DEVICE_CASES]}

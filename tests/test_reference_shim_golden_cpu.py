@@ -393,6 +393,29 @@ def test_flag_names_and_defaults_match_reference_code():
                                         "loss_scale", "data_format", "num_gpus"}
 
 
+@pytest.mark.parametrize("mtype", [1, 2])
+def test_mixup_dispatch_matches_reference_call_site(mtype):
+    """nets/run_loop_classification.py:101-109 executed from the source with the reference's own mixup
+    behind it: mixup_type 1 -> mixup(keep_batch_size=False) (2B examples in, B out), mixup_type 2 ->
+    keep_batch_size=True, teacher labels passed through `y_t`, nothing in EVAL mode.  The oracle's
+    convention `keep_batch_size = (mixup_type == 2)` -- what the plan's pack_input / mix_labels /
+    kd_teacher ops are tested against -- reproduces images, labels and teacher labels."""
+    from oracle import tf_ops as T
+    x, y, lam1, lam2 = mg.mixup_inputs()
+    yt = mg.teacher_labels()
+    gold = PIECES["mixup_dispatch_type%d_train" % mtype]
+    mx, my, myt = T.mixup(x.double(), y.double(), lam1.double(), lam2.double() if mtype == 2 else None,
+                          keep_batch_size=(mtype == 2), y_t=yt.double())
+    assert list(mx.shape) == gold["x_shape"] and mx.shape[0] == (mg.MIXUP_B // 2 if mtype == 1 else mg.MIXUP_B)
+    for k in ("sum", "abs_sum", "first", "last"):
+        assert _close(mg.digest(mx)[k], gold["x"][k], 1e-9)
+        assert _close(mg.digest(my)[k], gold["y"][k], 1e-9)
+        assert _close(mg.digest(myt)[k], gold["yt"][k], 1e-9)
+    ev = PIECES["mixup_dispatch_type%d_eval" % mtype]            # EVAL: inputs untouched
+    assert ev["x_shape"] == list(x.shape) and _close(ev["x"]["sum"], mg.digest(x)["sum"], 1e-9)
+    assert _close(ev["y"]["sum"], mg.digest(y)["sum"], 1e-12)
+
+
 def test_kd_loss_matches_reference_code():
     """nets/run_loop_classification.py:89-96,156-162 -- the two `if p['kd_temp'] > 0:` branches of
     resnet_model_fn executed from the reference's source (label tensor = one-hot ++ teacher logits is split,
