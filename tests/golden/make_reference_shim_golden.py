@@ -514,6 +514,18 @@ def run_train_pieces():
                 "y": digest(tf._raw(env["onehot_labels"])),
                 "yt": digest(tf._raw(env["teacher_labels"]))}
     tf.logging = saved_logging
+    # functions/input_fns.py:98-102: the input pipeline delivers 2 x batch_size examples per step for mixup
+    # type 1 in training (and only then)
+    blocks, _ = reference_if_blocks("functions/input_fns.py", "input_fn_cls",
+                                    "flags_obj.mixup_type == 1 and is_training")
+    assert len(blocks) == 1
+    out["input_batch"] = []
+    for mtype in (0, 1, 2):
+        for is_training in (True, False):
+            env = {"flags_obj": types.SimpleNamespace(mixup_type=mtype, batch_size=256),
+                   "is_training": is_training, "num_epochs": 3}
+            exec(blocks[0], env)
+            out["input_batch"].append([mtype, is_training, env["batch_size"]])
     # official/utils/misc/distribution_utils.py:48-76 per_device_batch_size (values and the error text)
     pdb, _ = reference_function("official/utils/misc/distribution_utils.py", "per_device_batch_size")
     out["per_device_batch"] = {"cases": [[b, n, pdb(b, n)] for b, n in PER_DEVICE_CASES]}

@@ -436,6 +436,16 @@ def test_kd_loss_matches_reference_code():
     assert _close(float(got), gold["cross_entropy_kd"], 2e-6), (float(got), gold["cross_entropy_kd"])
 
 
+def test_input_batch_matches_reference_code():
+    """functions/input_fns.py:98-102 executed from the source: how many examples the input pipeline delivers
+    per step (2 x batch for mixup type 1 in training, batch otherwise) == the plan's input_batch."""
+    from assembled_cnn_b200.plan import ModelConfig, build_plan
+    for mtype, is_training, want in PIECES["input_batch"]:
+        plan = build_plan(ModelConfig(resnet_size=50), 256, 32, 32, training=is_training, mixup_type=mtype)
+        assert plan.meta["input_batch"] == want, (mtype, is_training)
+        assert plan.tensors[plan.meta["images"]].shape[0] == want
+
+
 def test_per_device_batch_size_matches_reference_code():
     """official/utils/misc/distribution_utils.py:48-76 executed from the reference's source: per-replica
     batch and the ValueError text of an indivisible global batch (Trainer raises it)."""
