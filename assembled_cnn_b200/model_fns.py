@@ -521,6 +521,12 @@ def l2_loss(rt: Runtime, weight_decay: float):
     return 0.5 * weight_decay * (w[rt.decay_flags.bool()[:w.shape[0]]].double() ** 2).sum().float()
 
 
+def predictions_of(logits):
+    """nets/run_loop_classification.py:126-130: the `predictions` dict of the EstimatorSpec."""
+    return {"classes": logits.argmax(dim=1), "probabilities": torch.softmax(logits, dim=1),
+            "probabilities_sigmoid": torch.sigmoid(logits)}
+
+
 def model_fn_cls(features, labels, mode, params):
     """functions/model_fns.py:201-239 -> nets/run_loop_classification.py:60-234.
 
@@ -554,10 +560,6 @@ def model_fn_cls(features, labels, mode, params):
                       loss_type=p["cls_loss_type"])
         entry = _TRAINERS[key] = {"model": model, "trainer": None}
     model = entry["model"]
-
-    def predictions_of(logits):
-        return {"classes": logits.argmax(dim=1), "probabilities": torch.softmax(logits, dim=1),
-                "probabilities_sigmoid": torch.sigmoid(logits)}
 
     if mode == PREDICT:
         logits = model(images, False, False, use_resnet_d=p["use_resnet_d"])

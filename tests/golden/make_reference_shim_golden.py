@@ -514,6 +514,17 @@ def run_train_pieces():
                 "y": digest(tf._raw(env["onehot_labels"])),
                 "yt": digest(tf._raw(env["teacher_labels"]))}
     tf.logging = saved_logging
+    # nets/run_loop_classification.py:126-130: the `predictions` dict (classes / probabilities /
+    # probabilities_sigmoid), the assignment statement executed from the source
+    import ast
+    src = open("/root/reference/nets/run_loop_classification.py").read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "resnet_model_fn")
+    node = next(n for n in ast.walk(fn) if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", "") == "predictions")
+    logits, _ = loss_inputs()
+    env = {"tf": tf, "logits": tf.Tensor(logits)}
+    exec(compile(ast.fix_missing_locations(ast.Module(body=[node], type_ignores=[])), "run_loop", "exec"), env)
+    out["predictions"] = {k: digest(tf._raw(v).double()) for k, v in env["predictions"].items()}
+    out["predictions"]["classes_list"] = [int(v) for v in tf._raw(env["predictions"]["classes"])]
     # functions/input_fns.py:98-102: the input pipeline delivers 2 x batch_size examples per step for mixup
     # type 1 in training (and only then)
     blocks, _ = reference_if_blocks("functions/input_fns.py", "input_fn_cls",

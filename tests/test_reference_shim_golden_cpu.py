@@ -436,6 +436,20 @@ def test_kd_loss_matches_reference_code():
     assert _close(float(got), gold["cross_entropy_kd"], 2e-6), (float(got), gold["cross_entropy_kd"])
 
 
+def test_predictions_dict_matches_reference_code():
+    """nets/run_loop_classification.py:126-130 executed from the source: keys and values of the
+    EstimatorSpec's `predictions` (what model_fn_cls returns in every mode)."""
+    from assembled_cnn_b200.model_fns import predictions_of
+    gold = PIECES["predictions"]
+    logits, _ = mg.loss_inputs()
+    got = predictions_of(logits.double())
+    assert set(got) == set(gold) - {"classes_list"}
+    assert got["classes"].tolist() == gold["classes_list"]
+    for key in ("probabilities", "probabilities_sigmoid"):
+        for k in ("sum", "abs_sum", "first", "last"):
+            assert _close(mg.digest(got[key])[k], gold[key][k], 1e-9), (key, k)
+
+
 def test_input_batch_matches_reference_code():
     """functions/input_fns.py:98-102 executed from the source: how many examples the input pipeline delivers
     per step (2 x batch for mixup type 1 in training, batch otherwise) == the plan's input_batch."""
