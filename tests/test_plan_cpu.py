@@ -191,7 +191,7 @@ def _train_flag_sets(draw):
             draw(st.sampled_from([4, 6])), draw(st.sampled_from(["bf16", "fp32"])))
 
 
-@settings(max_examples=8, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
+@settings(max_examples=5, deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 @given(_train_flag_sets())
 def test_plan_train_step_matches_autograd_oracle_over_the_flag_space(case):
     kw, d, mix, hw, B, plan_dtype = case
